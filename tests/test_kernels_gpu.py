@@ -1,0 +1,271 @@
+"""GPU parity of the individual sm_100a kernels (called through the C ABI) against plain fp32 PyTorch.
+
+Tolerances: bf16 GEMM / attention outputs are compared with fp32 math on the same bf16-rounded
+inputs; the bound is a few bf16 ulps of the output magnitude (stated per test).
+"""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from vist3a_b200 import ops as _ops
+
+    return _ops
+
+
+def _rel_l2(a, b):
+    a, b = a.double(), b.double()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def _gelu_tanh(x):
+    return torch.nn.functional.gelu(x, approximate="tanh")
+
+
+@pytest.mark.parametrize("two_cta", [False, True])
+@pytest.mark.parametrize("M,N,K", [(128, 64, 64), (256, 256, 128), (4096, 1536, 1536), (1000, 520, 200), (77, 1536, 4096),
+                                   (4096, 8960, 1536), (300, 64, 8960)])
+def test_gemm_bf16_plain(ops, M, N, K, two_cta):
+    g = torch.Generator(device="cuda").manual_seed(M * 7 + N * 3 + K)
+    a = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    w = (torch.randn(N, K, device="cuda", generator=g) / math.sqrt(K)).bfloat16()
+    ref = a.float() @ w.float().t()
+    out = ops.gemm(a, w, out_dtype=torch.float32, two_cta=two_cta)
+    torch.cuda.synchronize()
+    assert _rel_l2(out, ref) < 2e-5  # fp32 accumulation of exact bf16 products
+    out_bf = ops.gemm(a, w, two_cta=two_cta)
+    assert _rel_l2(out_bf.float(), ref) < 4e-3  # one bf16 rounding
+
+
+@pytest.mark.parametrize("act", ["gelu_tanh", "gelu_erf", "silu", "relu"])
+def test_gemm_bias_act(ops, act):
+    M, N, K = 512, 768, 256
+    g = torch.Generator(device="cuda").manual_seed(1)
+    a = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    w = (torch.randn(N, K, device="cuda", generator=g) / math.sqrt(K)).bfloat16()
+    b = torch.randn(N, device="cuda", generator=g)
+    pre = a.float() @ w.float().t() + b
+    fn = {"gelu_tanh": _gelu_tanh, "gelu_erf": torch.nn.functional.gelu, "silu": torch.nn.functional.silu,
+          "relu": torch.relu}[act]
+    ref = fn(pre)
+    out = ops.gemm(a, w, b, act=act, out_dtype=torch.float32)
+    # tanh.approx / __expf in the epilogue: absolute error ~1e-3 of O(1) values
+    assert float((out - ref).abs().max()) < 4e-3
+    assert _rel_l2(out, ref) < 1e-3
+
+
+def test_gemm_gate_residual_fp32_stream(ops):
+    # DiT: x32 = x + gate[b] * bf16(linear);   aggregator: x32 = x32 + bf16(ls * bf16(linear))
+    B, Lr, N, K = 2, 640, 512, 384
+    g = torch.Generator(device="cuda").manual_seed(2)
+    a = torch.randn(B * Lr, K, device="cuda", generator=g).bfloat16()
+    w = (torch.randn(N, K, device="cuda", generator=g) / math.sqrt(K)).bfloat16()
+    bias = torch.randn(N, device="cuda", generator=g)
+    gate = torch.randn(B, N, device="cuda", generator=g)
+    res = torch.randn(B * Lr, N, device="cuda", generator=g)
+    lin = (a.float() @ w.float().t() + bias).bfloat16().float()
+    ref = res + lin * gate.repeat_interleave(Lr, 0)
+    out = ops.gemm(a, w, bias, gate=gate, gate_bstride=N, rows_per_batch=Lr, residual=res, round_linear=True,
+                   out_dtype=torch.float32)
+    assert float((out - ref).abs().max()) < 5e-2 and _rel_l2(out, ref) < 2e-3
+    # in place on the residual
+    res2 = res.clone()
+    ops.gemm(a, w, bias, gate=gate, gate_bstride=N, rows_per_batch=Lr, residual=res2, out=res2, round_linear=True)
+    assert torch.equal(res2, out)
+    # bf16 stream with LayerScale (DINO blocks): x = x + bf16(ls * bf16(linear))
+    ls = torch.randn(N, device="cuda", generator=g)
+    resb = res.bfloat16()
+    refb = (resb.float() + (lin * ls).bfloat16().float()).bfloat16()
+    outb = ops.gemm(a, w, bias, gate=ls, gate_bstride=0, residual=resb, round_linear=True, round_gate=True)
+    assert _rel_l2(outb.float(), refb.float()) < 4e-3
+
+
+@pytest.mark.parametrize("M,N,K", [(1024, 256, 512), (500, 136, 72), (4096, 32, 1152)])
+def test_gemm_tf32(ops, M, N, K):
+    g = torch.Generator(device="cuda").manual_seed(3)
+    a = torch.randn(M, K, device="cuda", generator=g)
+    w = torch.randn(N, K, device="cuda", generator=g) / math.sqrt(K)
+    ref = a.double() @ w.double().t()
+    out = ops.gemm(a, w)
+    assert out.dtype == torch.float32
+    assert _rel_l2(out, ref) < 1.5e-3  # tf32 operands: 10-bit mantissa
+
+
+def test_gemm_strided_views(ops):
+    # A is a column slice of a wider buffer; C is a column slice of a fused output
+    g = torch.Generator(device="cuda").manual_seed(4)
+    big = torch.randn(700, 1024, device="cuda", generator=g).bfloat16()
+    a = big[:, 256:768]
+    w = (torch.randn(384, 512, device="cuda", generator=g) / 22.0).bfloat16()
+    outbuf = torch.zeros(700, 1152, device="cuda", dtype=torch.bfloat16)
+    ops.gemm(a, w, out=outbuf[:, 384:768])
+    ref = a.float() @ w.float().t()
+    assert _rel_l2(outbuf[:, 384:768].float(), ref) < 4e-3
+    assert float(outbuf[:, :384].abs().max()) == 0 and float(outbuf[:, 768:].abs().max()) == 0
+
+
+def test_gemm_rejects_bad_arguments(ops):
+    from vist3a_b200._lib import Vist3aError
+
+    a = torch.randn(64, 60, device="cuda").bfloat16()  # K stride not 16-byte aligned
+    w = torch.randn(64, 60, device="cuda").bfloat16()
+    with pytest.raises(Vist3aError):
+        ops.gemm(a, w)
+    with pytest.raises(RuntimeError):
+        ops.gemm(torch.randn(8, 8).bfloat16(), torch.randn(8, 8).bfloat16())
+
+
+@pytest.mark.parametrize("B,H,Lq,Lk,D", [(1, 2, 128, 128, 128), (1, 2, 256, 384, 64), (2, 3, 300, 77, 128), (1, 4, 1029, 1029, 64),
+                                         (1, 12, 4096, 4096, 128), (1, 12, 4096, 512, 128), (3, 16, 1029, 1029, 64)])
+def test_fmha(ops, B, H, Lq, Lk, D):
+    g = torch.Generator(device="cuda").manual_seed(Lq + Lk + D)
+    # slices of one fused [B, L, 3, H, D] buffer, as the block code uses them
+    qkv = torch.randn(B, max(Lq, Lk), 3, H, D, device="cuda", generator=g).bfloat16()
+    q, k, v = qkv[:, :Lq, 0], qkv[:, :Lk, 1], qkv[:, :Lk, 2]
+    ref = torch.nn.functional.scaled_dot_product_attention(q.float().transpose(1, 2), k.float().transpose(1, 2),
+                                                           v.float().transpose(1, 2)).transpose(1, 2)
+    out = ops.fmha(q, k, v)
+    torch.cuda.synchronize()
+    assert out.shape == (B, Lq, H, D)
+    err = float((out.float() - ref).abs().max())
+    assert err < 2e-2, err  # P and O rounded to bf16; values are O(1)
+    assert _rel_l2(out.float(), ref) < 8e-3
+
+
+def test_fmha_large_scores(ops):
+    # rows whose max moves by > 2^8 between kv tiles exercise the lazy-rescale path
+    g = torch.Generator(device="cuda").manual_seed(5)
+    B, H, L, D = 1, 2, 512, 64
+    q = (torch.randn(B, L, H, D, device="cuda", generator=g) * 4).bfloat16()
+    k = (torch.randn(B, L, H, D, device="cuda", generator=g) * 4).bfloat16()
+    k[:, 300:] *= 3
+    v = torch.randn(B, L, H, D, device="cuda", generator=g).bfloat16()
+    ref = torch.nn.functional.scaled_dot_product_attention(q.float().transpose(1, 2), k.float().transpose(1, 2),
+                                                           v.float().transpose(1, 2)).transpose(1, 2)
+    out = ops.fmha(q, k, v)
+    assert torch.isfinite(out).all()
+    assert _rel_l2(out.float(), ref) < 1e-2
+
+
+@pytest.mark.parametrize("din,dout", [(torch.bfloat16, torch.bfloat16), (torch.float32, torch.bfloat16),
+                                      (torch.float32, torch.float32)])
+@pytest.mark.parametrize("dim", [1024, 1536, 2048])
+def test_layernorm_modulated(ops, din, dout, dim):
+    g = torch.Generator(device="cuda").manual_seed(6)
+    B, Lr = 2, 333
+    x = (torch.randn(B * Lr, dim, device="cuda", generator=g) * 2 + 0.5).to(din)
+    mul = torch.randn(B, dim, device="cuda", generator=g)
+    add = torch.randn(B, dim, device="cuda", generator=g)
+    ref = torch.nn.functional.layer_norm(x.float(), (dim,), eps=1e-6) * mul.repeat_interleave(Lr, 0) + add.repeat_interleave(Lr, 0)
+    out = ops.layernorm(x, mul=mul, add=add, mul_bstride=dim, add_bstride=dim, rows_per_batch=Lr, eps=1e-6, out_dtype=dout)
+    tol = 1e-5 if dout == torch.float32 else 4e-3
+    assert _rel_l2(out.float(), ref) < tol
+    # affine LayerNorm: shared weight / bias
+    out2 = ops.layernorm(x, mul=mul[0], add=add[0], eps=1e-5, out_dtype=dout)
+    ref2 = torch.nn.functional.layer_norm(x.float(), (dim,), mul[0], add[0], eps=1e-5)
+    assert _rel_l2(out2.float(), ref2) < tol
+
+
+def test_rmsnorm_rope(ops):
+    g = torch.Generator(device="cuda").manual_seed(7)
+    L_, H, D = 96, 12, 128
+    dim = H * D
+    buf = torch.randn(2 * L_, 3 * dim, device="cuda", generator=g).bfloat16()
+    x = buf[:, dim:2 * dim]  # the K third of a fused QKV buffer
+    w = torch.randn(dim, device="cuda", generator=g)
+    ang = torch.rand(L_, D // 2, device="cuda", generator=g) * 6.28
+    cos, sin = ang.cos().contiguous(), ang.sin().contiguous()
+    xf = x.float()
+    n = xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + 1e-6) * w
+    n = n.view(2, L_, H, D // 2, 2)
+    re, im = n[..., 0], n[..., 1]
+    c, s = cos[None, :, None, :], sin[None, :, None, :]
+    ref = torch.stack([re * c - im * s, re * s + im * c], -1).reshape(2 * L_, dim)
+    keep = buf.clone()
+    ops.rmsnorm_rope_(x, w, D, eps=1e-6, cos=cos, sin=sin)
+    assert _rel_l2(x.float(), ref) < 4e-3
+    assert torch.equal(buf[:, :dim], keep[:, :dim]) and torch.equal(buf[:, 2 * dim:], keep[:, 2 * dim:])
+    # no-RoPE variant (cross-attention)
+    y = keep[:, :dim].clone()
+    ops.rmsnorm_rope_(y, w, D, eps=1e-6)
+    yf = keep[:, :dim].float()
+    assert _rel_l2(y.float(), yf * torch.rsqrt(yf.pow(2).mean(-1, keepdim=True) + 1e-6) * w) < 4e-3
+
+
+def test_modulation_and_timestep(ops):
+    g = torch.Generator(device="cuda").manual_seed(8)
+    B, D = 2, 1536
+    table = torch.randn(6, D, device="cuda", generator=g)
+    mod = torch.randn(B, 6 * D, device="cuda", generator=g)
+    out = ops.modulation(table, mod, nvec=6, broadcast=False, one_plus_mask=0b010010)
+    ref = table[None] + mod.view(B, 6, D)
+    ref[:, 1] += 1
+    ref[:, 4] += 1
+    assert torch.allclose(out, ref, atol=1e-6)
+    temb = torch.randn(B, D, device="cuda", generator=g)
+    out2 = ops.modulation(table[:2].contiguous(), temb, nvec=2, broadcast=True, one_plus_mask=0b10)
+    ref2 = table[None, :2] + temb[:, None]
+    ref2[:, 1] += 1
+    assert torch.allclose(out2, ref2, atol=1e-6)
+    t = torch.tensor([999.0, 17.5], device="cuda")
+    f = ops.timestep_features(t, 256)
+    half = 128
+    freqs = torch.exp(-math.log(10000.0) * torch.arange(half, device="cuda", dtype=torch.float32) / half)
+    a = t[:, None] * freqs[None]
+    ref3 = torch.cat([a.cos(), a.sin()], -1)
+    assert float((f - ref3).abs().max()) < 2e-4
+
+
+@pytest.mark.parametrize("M", [1, 2, 13])
+def test_skinny_linear(ops, M):
+    g = torch.Generator(device="cuda").manual_seed(9)
+    K, N = 2048, 777
+    x = torch.randn(M, K, device="cuda", generator=g)
+    w = torch.randn(N, K, device="cuda", generator=g) / 45.0
+    b = torch.randn(N, device="cuda", generator=g)
+    out = ops.skinny_linear(x, w, b, pre_act="silu", act=None)
+    ref = torch.nn.functional.silu(x).double() @ w.double().t() + b.double()
+    assert _rel_l2(out, ref) < 1e-5
+    wb = w.bfloat16()
+    out2 = ops.skinny_linear(x.bfloat16(), wb, b, act="gelu_tanh", out_dtype=torch.float32)
+    ref2 = _gelu_tanh(x.bfloat16().double() @ wb.double().t() + b.double())
+    assert _rel_l2(out2, ref2) < 1e-4
+
+
+def test_patchify_roundtrip(ops):
+    g = torch.Generator(device="cuda").manual_seed(10)
+    B, C_, T, H, W = 2, 16, 4, 64, 64
+    x = torch.randn(B, C_, T, H, W, device="cuda", generator=g).bfloat16()
+    a = ops.patchify(x)
+    ref = x.view(B, C_, T, H // 2, 2, W // 2, 2).permute(0, 2, 3, 5, 1, 4, 6).reshape(B * T * (H // 2) * (W // 2), C_ * 4)
+    assert torch.equal(a, ref)
+    # unpatchify consumes proj_out rows laid out (dy, dx, c)
+    p = torch.randn(B * T * 32 * 32, 64, device="cuda", generator=g).bfloat16()
+    u = ops.unpatchify(p, B, C_, T, H, W)
+    refu = p.view(B, T, 32, 32, 1, 2, 2, C_).permute(0, 7, 1, 4, 2, 5, 3, 6).reshape(B, C_, T, H, W)
+    assert torch.equal(u, refu)
+
+
+def test_cfg_axpby(ops):
+    g = torch.Generator(device="cuda").manual_seed(11)
+    c = torch.randn(1, 16, 4, 64, 64, device="cuda", generator=g).bfloat16()
+    u = torch.randn(1, 16, 4, 64, 64, device="cuda", generator=g).bfloat16()
+    out = ops.cfg_combine(c, u, 6.0)
+    assert torch.allclose(out, u.float() + 6.0 * (c.float() - u.float()), atol=1e-5)
+    x = torch.randn_like(out)
+    y = torch.randn_like(out)
+    z = ops.axpby_n(torch.empty_like(out), [out, x, y], [0.5, -1.25, 2.0])
+    assert torch.allclose(z, 0.5 * out - 1.25 * x + 2.0 * y, atol=1e-5)
+
+
+def test_launch_counter(ops):
+    from vist3a_b200 import _lib
+
+    n0 = _lib.launch_count()
+    ops.cfg_combine(torch.zeros(8, device="cuda"), torch.zeros(8, device="cuda"), 1.0)
+    assert _lib.launch_count() == n0 + 1

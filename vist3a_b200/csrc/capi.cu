@@ -1,0 +1,178 @@
+// extern "C" surface of libvist3a_sm100 (declared in include/vist3a_sm100.h) plus the host
+// utilities shared by the kernels' launchers.
+#include <atomic>
+
+#include "host_util.cuh"
+
+namespace v3a {
+
+// entry points implemented next to their kernels
+int gemm_entry(const vist3a_gemm_args*, cudaStream_t);
+int fmha_entry(const vist3a_fmha_args*, cudaStream_t);
+int layernorm_entry(const void*, int, long long, void*, int, long long, long long, long long, long long, const float*,
+                    long long, const float*, long long, float, cudaStream_t);
+int rmsnorm_rope_entry(void*, long long, long long, long long, long long, const float*, float, const float*,
+                       const float*, long long, cudaStream_t);
+int modulation_entry(const float*, const void*, int, int, float*, long long, long long, long long, unsigned,
+                     cudaStream_t);
+int skinny_linear_entry(const void*, int, long long, const void*, int, long long, const float*, void*, int, long long,
+                        long long, long long, long long, int, int, cudaStream_t);
+int timestep_features_entry(const float*, void*, int, long long, long long, cudaStream_t);
+int patchify_entry(const void*, int, void*, long long, long long, long long, long long, long long, cudaStream_t);
+int unpatchify_entry(const void*, int, long long, void*, int, long long, long long, long long, long long, long long,
+                     cudaStream_t);
+int cfg_combine_entry(const void*, const void*, int, float, float*, long long, cudaStream_t);
+int axpby_entry(float*, int, const float* const*, const float*, long long, cudaStream_t);
+
+char* last_error_buf() {
+  static thread_local char buf[512] = {0};
+  return buf;
+}
+
+int set_error(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(last_error_buf(), 512, fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+std::atomic<long long>& launch_counter() {
+  static std::atomic<long long> c{0};
+  return c;
+}
+
+namespace {
+struct DevInfo {
+  int sms = 0;
+  int major = 0, minor = 0;
+  bool valid = false;
+};
+DevInfo g_dev[64];
+std::mutex g_dev_mu;
+
+const DevInfo* dev_info() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  std::lock_guard<std::mutex> lk(g_dev_mu);
+  DevInfo& d = g_dev[dev];
+  if (!d.valid) {
+    if (cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return nullptr;
+    cudaDeviceGetAttribute(&d.major, cudaDevAttrComputeCapabilityMajor, dev);
+    cudaDeviceGetAttribute(&d.minor, cudaDevAttrComputeCapabilityMinor, dev);
+    d.valid = true;
+  }
+  return &d;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_encode = nullptr;
+std::once_flag g_encode_once;
+}  // namespace
+
+int num_sms() {
+  const DevInfo* d = dev_info();
+  return d ? d->sms : 148;
+}
+
+int check_arch() {
+  const DevInfo* d = dev_info();
+  if (!d) return set_error(VIST3A_ERR_CUDA, "no CUDA device available (the kernels of libvist3a_sm100 need an sm_100 GPU)");
+  if (d->major != 10) return set_error(VIST3A_ERR_ARCH, "device is sm_%d%d; libvist3a_sm100 is built for sm_100a only", d->major, d->minor);
+  return VIST3A_OK;
+}
+
+int encode_tensor_map(CUtensorMap* out, const void* base, int elem_bytes, bool is_float32, int rank,
+                      const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box, bool swizzle128) {
+  std::call_once(g_encode_once, [] {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+  });
+  if (!g_encode) return set_error(VIST3A_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+  cuuint64_t gdim[5];
+  cuuint64_t gstr[4];
+  cuuint32_t bdim[5];
+  cuuint32_t estr[5];
+  for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bdim[i] = box[i]; estr[i] = 1; }
+  for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
+  const CUtensorMapDataType dt = is_float32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                                            : (elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_UINT8);
+  CUresult r = g_encode(out, dt, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bdim, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return set_error(VIST3A_ERR_CUDA,
+                     "cuTensorMapEncodeTiled failed (%d): rank %d dims [%llu,%llu,%llu,%llu] stride0 %llu box [%u,%u]",
+                     (int)r, rank, (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 0),
+                     (unsigned long long)(rank > 2 ? dims[2] : 0), (unsigned long long)(rank > 3 ? dims[3] : 0),
+                     (unsigned long long)(rank > 1 ? strides_bytes[0] : 0), box[0], rank > 1 ? box[1] : 0);
+  return VIST3A_OK;
+}
+
+}  // namespace v3a
+
+using namespace v3a;
+#define ST(s) reinterpret_cast<cudaStream_t>(s)
+
+extern "C" {
+
+const char* vist3a_last_error(void) { return last_error_buf(); }
+int vist3a_abi_version(void) { return 1; }
+int64_t vist3a_launch_count(void) { return (int64_t)launch_counter().load(); }
+
+int vist3a_gemm(const vist3a_gemm_args* args, void* stream) { return gemm_entry(args, ST(stream)); }
+int vist3a_fmha_fwd(const vist3a_fmha_args* args, void* stream) { return fmha_entry(args, ST(stream)); }
+
+int vist3a_layernorm(const void* x, int32_t x_dtype, int64_t ldx, void* out, int32_t out_dtype, int64_t ldo,
+                     int64_t rows, int64_t dim, int64_t rows_per_batch, const float* mul, int64_t mul_bstride,
+                     const float* add, int64_t add_bstride, float eps, void* stream) {
+  return layernorm_entry(x, x_dtype, ldx, out, out_dtype, ldo, rows, dim, rows_per_batch, mul, mul_bstride, add,
+                         add_bstride, eps, ST(stream));
+}
+
+int vist3a_rmsnorm_rope(void* x, int64_t ldx, int64_t rows, int64_t dim, int64_t head_dim, const float* weight,
+                        float eps, const float* rope_cos, const float* rope_sin, int64_t rope_len, void* stream) {
+  return rmsnorm_rope_entry(x, ldx, rows, dim, head_dim, weight, eps, rope_cos, rope_sin, rope_len, ST(stream));
+}
+
+int vist3a_modulation(const float* table, const void* mod, int32_t mod_dtype, int32_t mod_is_broadcast, float* out,
+                      int64_t batch, int64_t nvec, int64_t dim, uint32_t one_plus_mask, void* stream) {
+  return modulation_entry(table, mod, mod_dtype, mod_is_broadcast, out, batch, nvec, dim, one_plus_mask, ST(stream));
+}
+
+int vist3a_skinny_linear(const void* x, int32_t x_dtype, int64_t ldx, const void* W, int32_t w_dtype, int64_t ldw,
+                         const float* bias, void* y, int32_t y_dtype, int64_t ldy, int64_t M, int64_t N, int64_t K,
+                         int32_t pre_act, int32_t act, void* stream) {
+  return skinny_linear_entry(x, x_dtype, ldx, W, w_dtype, ldw, bias, y, y_dtype, ldy, M, N, K, pre_act, act, ST(stream));
+}
+
+int vist3a_timestep_features(const float* t, void* out, int32_t out_dtype, int64_t batch, int64_t dim, void* stream) {
+  return timestep_features_entry(t, out, out_dtype, batch, dim, ST(stream));
+}
+
+int vist3a_patchify(const void* x, int32_t x_dtype, void* A, int64_t B, int64_t C, int64_t T, int64_t H, int64_t W,
+                    void* stream) {
+  return patchify_entry(x, x_dtype, A, B, C, T, H, W, ST(stream));
+}
+
+int vist3a_unpatchify(const void* P, int32_t p_dtype, int64_t ldp, void* out, int32_t out_dtype, int64_t B, int64_t C,
+                      int64_t T, int64_t H, int64_t W, void* stream) {
+  return unpatchify_entry(P, p_dtype, ldp, out, out_dtype, B, C, T, H, W, ST(stream));
+}
+
+int vist3a_cfg_combine(const void* cond, const void* uncond, int32_t in_dtype, float guidance, float* out, int64_t n,
+                       void* stream) {
+  return cfg_combine_entry(cond, uncond, in_dtype, guidance, out, n, ST(stream));
+}
+
+int vist3a_axpby_n(float* out, int32_t n_terms, const float* const* terms, const float* coeffs, int64_t n,
+                   void* stream) {
+  return axpby_entry(out, n_terms, terms, coeffs, n, ST(stream));
+}
+
+}  // extern "C"

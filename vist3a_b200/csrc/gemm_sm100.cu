@@ -1,0 +1,380 @@
+// tcgen05 GEMM with fused epilogues:  C[M,N] = epilogue(A[M,K] · W[N,K]^T)
+//
+// Persistent, warp-specialised kernel (one CTA — or one CTA pair — per SM):
+//   warp 0      TMA producer   (cp.async.bulk.tensor, 128B-swizzled K-major tiles, mbarrier ring)
+//   warp 1      MMA issuer     (one elected thread, tcgen05.mma, accumulators in TMEM)
+//   warp 2      TMEM allocator
+//   warps 4..7  epilogue       (tcgen05.ld -> registers -> bias/act/gate/residual -> global)
+// Two TMEM accumulator stages let the epilogue of tile i overlap the main loop of tile i+1.
+// kCta == 2 uses cta_group::2: the pair computes a 256 x BN tile, each CTA stages its own 128 rows
+// of A and half of the W tile, the leader CTA issues the MMAs for both.
+#include "common.cuh"
+#include "host_util.cuh"
+
+namespace v3a {
+
+struct GemmEpilogue {
+  void* C;
+  const float* bias;
+  const float* gate;
+  const void* residual;
+  long long ldc, ldr;
+  long long rows_per_batch, gate_bstride;
+  int out_fp32;
+  int act;
+  int round_linear;
+  int round_gate;
+};
+
+struct GemmShape {
+  int M, N, K;
+  int tiles_m, tiles_n;  // tiles_m counts 128*kCta-row tiles
+};
+
+template <int BN, int kCta, bool kTF32>
+struct GemmCfg {
+  static constexpr int BM = 128;                       // rows per CTA
+  static constexpr int ES = kTF32 ? 4 : 2;             // operand element size
+  static constexpr int BK = 128 / ES;                  // one 128-byte swizzle row of K per stage
+  static constexpr int UK = 32 / ES;                   // K per tcgen05.mma
+  static constexpr int BN_LOCAL = BN / kCta;           // W rows staged by this CTA
+  static constexpr int A_BYTES = BM * 128;
+  static constexpr int B_BYTES = BN_LOCAL * 128;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 8 ? 8 : (200 * 1024) / STAGE_BYTES;
+  static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;  // two accumulator stages
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static_assert(BN == 64 || BN == 128 || BN == 256, "BN");
+  static_assert(TMEM_COLS <= 512, "TMEM");
+};
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+  switch (act) {
+    case VIST3A_ACT_GELU_TANH: return gelu_tanh_f(v);
+    case VIST3A_ACT_GELU_ERF: return gelu_erf_f(v);
+    case VIST3A_ACT_SILU: return silu_f(v);
+    case VIST3A_ACT_RELU: return fmaxf(v, 0.0f);
+    default: return v;
+  }
+}
+
+template <int BN, int kCta, bool kTF32>
+__global__ void __launch_bounds__(256, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const GemmShape shape, const GemmEpilogue ep) {
+  using Cfg = GemmCfg<BN, kCta, kTF32>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  // 128B swizzle atoms need 1024-byte alignment
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + STAGES * Cfg::STAGE_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 2 + s); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+  auto smem_a = [&](int s) { return smem_base + s * Cfg::STAGE_BYTES; };
+  auto smem_b = [&](int s) { return smem_base + s * Cfg::STAGE_BYTES + Cfg::A_BYTES; };
+
+  const uint32_t warp = warp_id_sync();
+  const uint32_t lane = lane_id();
+  const uint32_t rank = (kCta == 2) ? cluster_ctarank() : 0u;
+  const bool leader = (rank == 0);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull_bar(s), 1);
+      mbar_init(tempty_bar(s), 4 * kCta);  // one arrival per epilogue warp (of both CTAs)
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<kCta>(tmem_slot, Cfg::TMEM_COLS);
+  tc_fence_before();
+  if constexpr (kCta == 2) cluster_sync_all(); else __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  const int num_kb = (shape.K + Cfg::BK - 1) / Cfg::BK;
+  const int num_tiles = shape.tiles_m * shape.tiles_n;
+  const int worker = blockIdx.x / kCta;
+  const int num_workers = gridDim.x / kCta;
+
+  if (warp == 0) {
+    // ------------------------------ TMA producer ------------------------------
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int tile = worker; tile < num_tiles; tile += num_workers) {
+        const int tm = tile % shape.tiles_m, tn = tile / shape.tiles_m;
+        const int m0 = (tm * kCta + (int)rank) * Cfg::BM;
+        const int n0 = tn * BN + (int)rank * Cfg::BN_LOCAL;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(empty_bar(s), ph ^ 1u);
+          if constexpr (kCta == 1) {
+            mbar_expect_tx(full_bar(s), Cfg::STAGE_BYTES);
+            tma_load_2d(smem_a(s), &tmA, full_bar(s), kb * Cfg::BK, m0);
+            tma_load_2d(smem_b(s), &tmB, full_bar(s), kb * Cfg::BK, n0);
+          } else {
+            if (leader) mbar_expect_tx(full_bar(s), 2 * Cfg::STAGE_BYTES);
+            tma_load_2d_2sm(smem_a(s), &tmA, full_bar(s), kb * Cfg::BK, m0);
+            tma_load_2d_2sm(smem_b(s), &tmB, full_bar(s), kb * Cfg::BK, n0);
+          }
+          if (++s == STAGES) { s = 0; ph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------ MMA issuer ------------------------------
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = make_idesc(kTF32 ? kFmtTF32 : kFmtBF16, 128 * kCta, BN, 0, 0);
+      int s = 0;
+      uint32_t ph = 0;
+      int as = 0;
+      uint32_t aph = 0;
+      for (int tile = worker; tile < num_tiles; tile += num_workers) {
+        mbar_wait(tempty_bar(as), aph ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(full_bar(s), ph);
+          tc_fence_after();
+          const uint64_t adesc = make_smem_desc_sw128(smem_a(s), 1024, 0);
+          const uint64_t bdesc = make_smem_desc_sw128(smem_b(s), 1024, 0);
+#pragma unroll
+          for (int k = 0; k < Cfg::BK / Cfg::UK; ++k) {
+            // advance 32 bytes along K inside the swizzle atom: +2 in the (addr >> 4) field
+            if constexpr (kTF32) umma_tf32_ss<kCta>(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) ? 1u : 0u);
+            else umma_f16_ss<kCta>(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) ? 1u : 0u);
+          }
+          if constexpr (kCta == 1) umma_commit(empty_bar(s)); else umma_commit_2sm_mc(empty_bar(s), 3);
+          if (++s == STAGES) { s = 0; ph ^= 1u; }
+        }
+        if constexpr (kCta == 1) umma_commit(tfull_bar(as)); else umma_commit_2sm_mc(tfull_bar(as), 3);
+        if (++as == 2) { as = 0; aph ^= 1u; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------ epilogue ------------------------------
+    const uint32_t q = warp & 3u;  // TMEM sub-partition of this warp: lanes [32q, 32q+32)
+    int as = 0;
+    uint32_t aph = 0;
+    for (int tile = worker; tile < num_tiles; tile += num_workers) {
+      const int tm = tile % shape.tiles_m, tn = tile / shape.tiles_m;
+      const int row = (tm * kCta + (int)rank) * Cfg::BM + (int)(q * 32u + lane);
+      const int n_tile = tn * BN;
+      mbar_wait(tfull_bar(as), aph);
+      tc_fence_after();
+      const bool row_ok = row < shape.M;
+      const long long b = row_ok ? (long long)row / ep.rows_per_batch : 0;
+      const float* gate_row = ep.gate ? ep.gate + b * ep.gate_bstride : nullptr;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        const int n0 = n_tile + c * 32;
+        if (n0 >= shape.N) break;  // warp-uniform
+        uint32_t r[32];
+        tmem_ld_x32(tmem_base + ((q * 32u) << 16) + (uint32_t)(as * BN + c * 32), r);
+        tmem_ld_wait();
+        if (row_ok) {
+          const int ncols = min(32, shape.N - n0);
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          if (ep.bias) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              if (j < ncols) {
+                const float4 bv = __ldg(reinterpret_cast<const float4*>(ep.bias + n0 + j));
+                v[j] += bv.x; v[j + 1] += bv.y; v[j + 2] += bv.z; v[j + 3] += bv.w;
+              }
+            }
+          }
+          if (ep.act != VIST3A_ACT_NONE) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], ep.act);
+          }
+          if (ep.round_linear) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = bf16_round(v[j]);
+          }
+          if (gate_row) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              if (j < ncols) {
+                const float4 g = __ldg(reinterpret_cast<const float4*>(gate_row + n0 + j));
+                v[j] *= g.x; v[j + 1] *= g.y; v[j + 2] *= g.z; v[j + 3] *= g.w;
+              }
+            }
+            if (ep.round_gate) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = bf16_round(v[j]);
+            }
+          }
+          if (ep.out_fp32) {
+            float* crow = reinterpret_cast<float*>(ep.C) + (long long)row * ep.ldc + n0;
+            if (ep.residual) {
+              const float* rrow = reinterpret_cast<const float*>(ep.residual) + (long long)row * ep.ldr + n0;
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                if (j < ncols) {
+                  const float4 x = *reinterpret_cast<const float4*>(rrow + j);
+                  v[j] += x.x; v[j + 1] += x.y; v[j + 2] += x.z; v[j + 3] += x.w;
+                }
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              if (j < ncols) *reinterpret_cast<float4*>(crow + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            }
+          } else {
+            __nv_bfloat16* crow = reinterpret_cast<__nv_bfloat16*>(ep.C) + (long long)row * ep.ldc + n0;
+            if (ep.residual) {
+              const __nv_bfloat16* rrow =
+                  reinterpret_cast<const __nv_bfloat16*>(ep.residual) + (long long)row * ep.ldr + n0;
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                if (j < ncols) {
+                  const uint4 x = *reinterpret_cast<const uint4*>(rrow + j);
+                  v[j] += bf16_lo(x.x); v[j + 1] += bf16_hi(x.x);
+                  v[j + 2] += bf16_lo(x.y); v[j + 3] += bf16_hi(x.y);
+                  v[j + 4] += bf16_lo(x.z); v[j + 5] += bf16_hi(x.z);
+                  v[j + 6] += bf16_lo(x.w); v[j + 7] += bf16_hi(x.w);
+                }
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              if (j < ncols) {
+                uint4 o;
+                o.x = pack_bf16(v[j], v[j + 1]);
+                o.y = pack_bf16(v[j + 2], v[j + 3]);
+                o.z = pack_bf16(v[j + 4], v[j + 5]);
+                o.w = pack_bf16(v[j + 6], v[j + 7]);
+                *reinterpret_cast<uint4*>(crow + j) = o;
+              }
+            }
+          }
+        }
+      }
+      // release the accumulator stage to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if constexpr (kCta == 1) mbar_arrive(tempty_bar(as)); else mbar_arrive_cluster(tempty_bar(as), 0);
+      }
+      if (++as == 2) { as = 0; aph ^= 1u; }
+    }
+  }
+
+  // ------------------------------ teardown ------------------------------
+  tc_fence_before();
+  if constexpr (kCta == 2) cluster_sync_all(); else __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<kCta>(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// ----------------------------------------------------------------------------------------
+// host side
+// ----------------------------------------------------------------------------------------
+
+template <int BN, int kCta, bool kTF32>
+static int launch_gemm(const vist3a_gemm_args& a, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN, kCta, kTF32>;
+  CUtensorMap tmA, tmB;
+  {
+    uint64_t dims[2] = {(uint64_t)a.K, (uint64_t)a.M};
+    uint64_t strides[1] = {(uint64_t)a.lda * Cfg::ES};
+    uint32_t box[2] = {(uint32_t)Cfg::BK, (uint32_t)Cfg::BM};
+    int rc = encode_tensor_map(&tmA, a.A, Cfg::ES, kTF32, 2, dims, strides, box, true);
+    if (rc) return rc;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)a.K, (uint64_t)a.N};
+    uint64_t strides[1] = {(uint64_t)a.ldw * Cfg::ES};
+    uint32_t box[2] = {(uint32_t)Cfg::BK, (uint32_t)Cfg::BN_LOCAL};
+    int rc = encode_tensor_map(&tmB, a.W, Cfg::ES, kTF32, 2, dims, strides, box, true);
+    if (rc) return rc;
+  }
+  GemmShape shape;
+  shape.M = (int)a.M; shape.N = (int)a.N; shape.K = (int)a.K;
+  shape.tiles_m = (int)((a.M + Cfg::BM * kCta - 1) / (Cfg::BM * kCta));
+  shape.tiles_n = (int)((a.N + BN - 1) / BN);
+  GemmEpilogue ep;
+  ep.C = a.C; ep.bias = a.bias; ep.gate = a.gate; ep.residual = a.residual;
+  ep.ldc = a.ldc; ep.ldr = a.ldr;
+  ep.rows_per_batch = a.rows_per_batch > 0 ? a.rows_per_batch : a.M;
+  ep.gate_bstride = a.gate_bstride;
+  ep.out_fp32 = a.out_dtype == VIST3A_DTYPE_F32;
+  ep.act = a.act; ep.round_linear = a.round_linear; ep.round_gate = a.round_gate;
+
+  auto kern = gemm_tcgen05_kernel<BN, kCta, kTF32>;
+  static bool attr_set = false;  // per template instantiation
+  if (!attr_set) {
+    V3A_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  const int tiles = shape.tiles_m * shape.tiles_n;
+  int workers = num_sms() / kCta;
+  if (workers > tiles) workers = tiles;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(workers * kCta));
+  cfg.blockDim = dim3(256);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kCta; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  V3A_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, shape, ep));
+  launch_counter().fetch_add(1);
+  return VIST3A_OK;
+}
+
+template <bool kTF32>
+static int dispatch_gemm(const vist3a_gemm_args& a, cudaStream_t stream) {
+  const bool two = (a.flags & VIST3A_GEMM_FLAG_2CTA) && !(a.flags & VIST3A_GEMM_FLAG_1CTA) && a.M > 128;
+  if (a.N > 128) return two ? launch_gemm<256, 2, kTF32>(a, stream) : launch_gemm<256, 1, kTF32>(a, stream);
+  if (a.N > 64) return two ? launch_gemm<128, 2, kTF32>(a, stream) : launch_gemm<128, 1, kTF32>(a, stream);
+  return launch_gemm<64, 1, kTF32>(a, stream);
+}
+
+int gemm_entry(const vist3a_gemm_args* args, cudaStream_t stream) {
+  V3A_REQUIRE(args != nullptr, VIST3A_ERR_INVALID, "gemm: null args");
+  const vist3a_gemm_args& a = *args;
+  V3A_REQUIRE(a.A && a.W && a.C, VIST3A_ERR_INVALID, "gemm: null A/W/C");
+  V3A_REQUIRE(a.M > 0 && a.N > 0 && a.K > 0, VIST3A_ERR_INVALID, "gemm: M,N,K must be positive (got %lld,%lld,%lld)",
+              (long long)a.M, (long long)a.N, (long long)a.K);
+  V3A_REQUIRE(a.in_dtype == VIST3A_DTYPE_BF16 || a.in_dtype == VIST3A_DTYPE_F32, VIST3A_ERR_INVALID, "gemm: in_dtype");
+  V3A_REQUIRE(a.out_dtype == VIST3A_DTYPE_BF16 || a.out_dtype == VIST3A_DTYPE_F32, VIST3A_ERR_INVALID,
+              "gemm: out_dtype");
+  const int es = a.in_dtype == VIST3A_DTYPE_F32 ? 4 : 2;
+  const int kalign = 16 / es;
+  V3A_REQUIRE(a.lda >= a.K && a.ldw >= a.K && a.lda % kalign == 0 && a.ldw % kalign == 0, VIST3A_ERR_INVALID,
+              "gemm: lda/ldw must be >= K and multiples of %d elements (16-byte TMA stride)", kalign);
+  V3A_REQUIRE(((uintptr_t)a.A & 15) == 0 && ((uintptr_t)a.W & 15) == 0 && ((uintptr_t)a.C & 15) == 0,
+              VIST3A_ERR_INVALID, "gemm: A/W/C must be 16-byte aligned");
+  const int nalign = a.out_dtype == VIST3A_DTYPE_F32 ? 4 : 8;
+  V3A_REQUIRE(a.N % nalign == 0 && a.ldc % nalign == 0 && a.ldc >= a.N, VIST3A_ERR_INVALID,
+              "gemm: N and ldc must be multiples of %d and ldc >= N", nalign);
+  if (a.residual)
+    V3A_REQUIRE(a.ldr % nalign == 0 && a.ldr >= a.N && ((uintptr_t)a.residual & 15) == 0, VIST3A_ERR_INVALID,
+                "gemm: residual stride/alignment");
+  if (a.bias) V3A_REQUIRE(((uintptr_t)a.bias & 15) == 0, VIST3A_ERR_INVALID, "gemm: bias alignment");
+  if (a.gate) V3A_REQUIRE(((uintptr_t)a.gate & 15) == 0 && a.gate_bstride % 4 == 0, VIST3A_ERR_INVALID, "gemm: gate alignment");
+  V3A_REQUIRE(a.M < (1ll << 31) && a.N < (1ll << 31) && a.K < (1ll << 31), VIST3A_ERR_INVALID, "gemm: dims exceed int32");
+  int rc = check_arch();
+  if (rc) return rc;
+  return a.in_dtype == VIST3A_DTYPE_F32 ? dispatch_gemm<true>(a, stream) : dispatch_gemm<false>(a, stream);
+}
+
+}  // namespace v3a

@@ -1,0 +1,42 @@
+// Host-side utilities shared by the C-ABI entry points: thread-local error string, device
+// attribute cache, and the TMA tensor-map encoder (resolved through the runtime so that the
+// library has no link-time dependency on libcuda and loads on a GPU-less build host).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <atomic>
+#include <mutex>
+#include <unordered_map>
+
+#include "../../include/vist3a_sm100.h"
+
+namespace v3a {
+
+char* last_error_buf();   // thread-local, 512 bytes (defined in capi.cu)
+int set_error(int code, const char* fmt, ...);
+int num_sms();            // SM count of the current device (cached per device)
+int check_arch();         // VIST3A_OK if the current device is sm_100, else VIST3A_ERR_ARCH
+std::atomic<long long>& launch_counter();  // kernels launched by this library in this process
+
+#define V3A_CUDA_OK(expr)                                                                             \
+  do {                                                                                                \
+    cudaError_t _e = (expr);                                                                          \
+    if (_e != cudaSuccess) return v3a::set_error(VIST3A_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(_e)); \
+  } while (0)
+
+#define V3A_REQUIRE(cond, code, ...)                        \
+  do {                                                      \
+    if (!(cond)) return v3a::set_error(code, __VA_ARGS__);  \
+  } while (0)
+
+// Encode a tiled tensor map with 128-byte swizzle (or no swizzle if swizzle128 == false).
+//   rank <= 5; dims[0] is the contiguous dimension; strides_bytes[i] is the stride of dim i+1.
+int encode_tensor_map(CUtensorMap* out, const void* base, int elem_bytes, bool is_float32, int rank,
+                      const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box, bool swizzle128);
+
+}  // namespace v3a
