@@ -1,0 +1,322 @@
+#!/usr/bin/env python
+"""Benchmark of the VIST3A hot path on B200 (BASELINE.json metric: denoise-steps/sec & Gaussians/sec,
+VIST3A-1.3B, 512x512x13 views).
+
+    python bench.py --gpus N --steps K --warmup W            # this framework (sm_100a kernels)
+    python bench.py --impl reference --gpus N --steps K ...   # the reference's CPU path (oracle port)
+
+A "step" is one denoise step of one prompt: cond forward + uncond forward of the Wan-1.3B DiT at
+L = 4096 latent tokens (13 views @ 512x512) and 512 text tokens, CFG combine, UniPC update.
+Workload = BASELINE.json configs[1].  Under torchrun every rank runs its own prompt (prompts shard
+over GPUs with no data-path collective in the denoise loop: weak scaling).
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+STEP_TFLOP = 27.756  # one denoise step (cond + uncond), 1.3B, L=4096, Lt=512
+FWD_BLOCK_GFLOP = 462.25
+METRIC = "denoise_steps_per_sec"
+UNIT = "steps/s"
+WORKLOAD = "VIST3A-1.3B DiT 50-step denoise, 512x512x13 views (latent [1,16,4,64,64], L=4096, 512 text tokens), batch 1 per GPU"
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_burst": d["bf16_tflops"], "bf16_sustained": d["bf16_tflops_sustained"], "src": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_burst": 1590.0, "bf16_sustained": 1400.0, "src": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clock / throttle-reason samples during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self._stop, self._th = index, [], threading.Event(), None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._th = threading.Thread(target=self._run, daemon=True)
+        self._th.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._th.join(timeout=6)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 7 for n, v in zip(names, r[3:7]) if v.lower().startswith("active")})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU baseline (oracle port of the DiT; diffusers is un-vendored so the reference itself cannot run)
+# --------------------------------------------------------------------------------------------------
+def cpu_sample(nb: int, repeats: int = 1):
+    """Time `nb` full-size 1.3B blocks (+embed/head) of the oracle on the host cores; returns (seconds, est steps/s)."""
+    import dataclasses
+
+    import torch
+
+    from oracle import wan_dit_ref as R
+
+    cfg = dataclasses.replace(R.WAN_1_3B, num_layers=nb)
+    sd = R.init_state_dict(cfg, seed=0, round_bf16=False)
+    lat, txt = R.synthetic_inputs(cfg, frames=4, hw=64, text_len=512, text_valid=200, seed=0)
+    t = torch.tensor([999.0])
+    times = []
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        R.wan_forward(sd, cfg, lat, t, txt)
+        times.append(time.perf_counter() - t0)
+    return times
+
+
+def run_reference(args):
+    import torch
+
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    nb = args.ref_blocks
+    cores = torch.get_num_threads()
+    times = cpu_sample(nb, repeats=args.warmup + args.steps)[args.warmup:]
+    # a denoise step = 2 forwards of 30 blocks; each timed sample is nb blocks of one forward
+    est_step = [2.0 * 30.0 / nb * t for t in times]
+    sps = 1.0 / statistics.mean(est_step)
+    sample = (f"each step times {nb} of 30 full-size 1.3B blocks (L=4096, Lt=512, fp32) of ONE cond forward incl. embed/head; "
+              f"steps/s = 1 / (2 * 30/{nb} * t_sample)")
+    line = {"impl": "reference", "metric": METRIC, "value": sps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * statistics.mean(est_step), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD},
+            "cpu_baseline": {"value": sps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": sps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "note": "reference DiT lives in un-vendored diffusers==0.33.1; timed arm is the oracle restatement (oracle/wan_dit_ref.py)"}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------------------------------
+def build_model(device):
+    """Random-init Wan-1.3B weights (N(0,0.02) weights, zero biases, table randn/sqrt(D)) made on the device."""
+    import math
+
+    import torch
+
+    from oracle.wan_dit_ref import WAN_1_3B, param_shapes  # shape manifest only (no oracle compute on this path)
+    from vist3a_b200.wan_dit import WanTransformer3DModelB200
+
+    cfg = WAN_1_3B
+    g = torch.Generator(device=device).manual_seed(0)
+    sd = {}
+    for k, shp in param_shapes(cfg).items():
+        if k.endswith("scale_shift_table"):
+            sd[k] = torch.randn(shp, device=device, generator=g) / math.sqrt(cfg.inner_dim)
+        elif "norm" in k and k.endswith(".weight"):
+            sd[k] = torch.ones(shp, device=device)
+        elif k.endswith(".bias"):
+            sd[k] = torch.zeros(shp, device=device)
+        else:
+            sd[k] = (torch.randn(shp, device=device, generator=g) * 0.02).bfloat16()
+    model = WanTransformer3DModelB200.from_state_dict(sd, cfg, device=device)
+    del sd
+    return cfg, model
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from vist3a_b200 import _lib, ops
+    from vist3a_b200.pipeline import DenoiseEngine
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: the product path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    _lib.load()
+    cfg, model = build_model(device)
+    B, T, HW, Lt = 1, 4, 64, 512
+    g = torch.Generator().manual_seed(1000 + rank)  # every rank denoises its own prompt
+    noise_h = torch.randn(B, 16, T, HW, HW, generator=g).pin_memory()
+    tc_h = torch.randn(B, Lt, cfg.text_dim, generator=g).bfloat16()
+    tc_h[:, 200:] = 0
+    tu_h = torch.randn(B, Lt, cfg.text_dim, generator=g).bfloat16()
+    tu_h[:, 60:] = 0
+    tc_h, tu_h = tc_h.pin_memory(), tu_h.pin_memory()
+    out_h = torch.empty_like(noise_h).pin_memory()
+
+    eng = DenoiseEngine(model, noise_h.shape, Lt, num_inference_steps=50, guidance_scale=6.0, flow_shift=5.0,
+                        use_graph=not args.no_graph)
+    eng.set_text(tc_h, tu_h)
+    eng.set_noise(noise_h)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, n):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(n):
+            fn(i)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            tms = torch.tensor([ms], device=device)
+            dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+            ms = float(tms)
+        return ms
+
+    # ---- device-resident throughput
+    nsteps = 50
+
+    def dev_step(i):
+        if eng.sampler.i >= nsteps:
+            eng.sampler.reset()
+        eng.step(eng.sampler.i)
+
+    for i in range(args.warmup):
+        dev_step(i)
+    n0 = _lib.launch_count()
+    with ClockSampler(local) as clk:
+        ms = timed(dev_step, args.steps)
+    launches_eager = _lib.launch_count() - n0
+    ms_step = ms / args.steps
+    value = world * args.steps / (ms / 1e3)
+
+    # ---- end to end through the public call with HOST buffers (H2D inputs + D2H result inside the timed region)
+    h2d = noise_h.numel() * 4 + tc_h.numel() * 2 + tu_h.numel() * 2
+    d2h = out_h.numel() * 4
+
+    def e2e_step(i):
+        if eng.sampler.i >= nsteps:
+            eng.sampler.reset()
+        eng.x.copy_(noise_h, non_blocking=True)       # this step's latents from pinned host memory
+        eng.set_text(tc_h, tu_h)                      # this step's text embeddings (H2D + text projections)
+        eng.step(eng.sampler.i)
+        out_h.copy_(eng.x, non_blocking=True)         # the step's result back to the host
+        torch.cuda.current_stream().synchronize()
+
+    for i in range(min(args.warmup, 3)):
+        e2e_step(i)
+    ms_e2e = timed(e2e_step, args.steps)
+    e2e_value = world * args.steps / (ms_e2e / 1e3)
+
+    # ---- per-kernel device timing of one eager step (roofline of the dominant kernel)
+    roof = None
+    launches_per_step = None
+    if rank == 0:
+        model_fwd = lambda: eng._forward()
+        model_fwd()
+        torch.cuda.synchronize()
+        n1 = _lib.launch_count()
+        with ops.OpTimer() as tm:
+            eng.xin[:B].copy_(eng.x)
+            eng.xin[B:].copy_(eng.x)
+            model_fwd()
+            ops.cfg_combine(eng.out[:B], eng.out[B:], eng.g, out=eng.eps)
+            eng.sampler.reset()
+            eng.sampler.step(eng.eps, eng.x)
+        launches_per_step = _lib.launch_count() - n1
+        summ = tm.summary()
+        tot = sum(d["ms"] for d in summ.values())
+        top = max((k for k in summ if summ[k]["flops"] > 0), key=lambda k: summ[k]["ms"])
+        pk = _peaks()
+        d = summ[top]
+        ach = d["flops"] / (d["ms"] / 1e3) / 1e12
+        roof = {"bound": "tensor", "kernel": top, "achieved": ach, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
+                "frac": ach / pk["bf16_sustained"], "frac_of_burst": ach / pk["bf16_burst"], "peak_src": pk["src"] + " (sustained: kernel timed inside a long step)",
+                "traffic": None, "launches_per_step": d["launches"], "avg_launch_ms": d["ms"] / d["launches"],
+                "share_of_step": d["ms"] / tot,
+                "step_model_tflops": STEP_TFLOP / (ms_step / 1e3), "step_frac_of_sustained": STEP_TFLOP / (ms_step / 1e3) / pk["bf16_sustained"],
+                "by_kernel": {k: {"ms": round(v["ms"], 4), "launches": v["launches"],
+                                  "tflops": (v["flops"] / (v["ms"] / 1e3) / 1e12) if v["flops"] else None,
+                                  "gbs": v["bytes"] / (v["ms"] / 1e3) / 1e9} for k, v in summ.items()}}
+
+    # ---- CPU baseline (rank 0, N=1 only): bounded sample of the oracle port on the host cores
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        nb = args.ref_blocks
+        t = cpu_sample(nb, repeats=2)[-1]
+        sps = 1.0 / (2.0 * 30.0 / nb * t)
+        cpu = {"value": sps, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+               "sample": f"{nb} of 30 full-size fp32 blocks of one cond forward (oracle/wan_dit_ref.py), {t:.2f} s; steps/s = 1/(2*30/{nb}*t)"}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+                "data": "synthetic",
+                "config": {"workload": WORKLOAD, "weights": "random-init Wan-1.3B (1.419 B params)", "cfg": "cond+uncond batched B=2",
+                           "cuda_graph": not args.no_graph, "l2": "working set (2.8 GB weights + activations) >> 126 MB L2; no flush needed",
+                           "prompts_per_gpu": 1},
+                "roofline": roof, "cpu_baseline": cpu, "clocks": clk.summary(),
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "ms_per_step": ms_e2e / args.steps},
+                "gpu_launches": launches_eager if args.no_graph else (launches_per_step or 0) * args.steps,
+                "gpu_launches_note": "graph replays re-launch the captured kernels; count = kernels per step x steps" if not args.no_graph else "eager",
+                "tflops_model": STEP_TFLOP * value}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-blocks", type=int, default=2, help="full-size blocks per CPU sample")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -228,3 +228,78 @@ def axpby_n(out: torch.Tensor, terms, coeffs) -> torch.Tensor:
     cf = (C.c_float * n)(*[float(c) for c in coeffs])
     L.check(L.load().vist3a_axpby_n(out.data_ptr(), n, ptrs, cf, out.numel(), _stream()))
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# per-launch device timing (bench.py roofline): CUDA events recorded on the launching stream around
+# every call of the wrapped op, with its algorithmic FLOPs / bytes.
+# ------------------------------------------------------------------------------------------------
+class OpTimer:
+    """with OpTimer() as t: ...run the path eagerly...; t.summary() -> {kernel class: {ms, launches, flops, bytes}}"""
+
+    def __init__(self):
+        self.records = []
+        self._saved = {}
+
+    def _wrap(self, name, fn, cost):
+        def wrapped(*a, **k):
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            out = fn(*a, **k)
+            e.record()
+            fl, by, tag = cost(out, a, k)
+            self.records.append((tag or name, s, e, fl, by))
+            return out
+        return wrapped
+
+    def __enter__(self):
+        import sys
+
+        mod = sys.modules[__name__]
+
+        def gemm_cost(out, args, kw):
+            a, w = args[0], args[1]
+            M, K = a.reshape(-1, a.shape[-1]).shape
+            N = w.shape[0]
+            by = M * K * a.element_size() + N * K * w.element_size() + M * N * out.element_size()
+            return 2.0 * M * N * K, by, "gemm_tcgen05"
+
+        def fmha_cost(out, args, kw):
+            q, kk = args[0], args[1]
+            B, Lq, H, D = q.shape
+            Lk = kk.shape[1]
+            return 4.0 * B * H * Lq * Lk * D, 2 * (2 * B * Lq * H * D + 2 * B * Lk * H * D), "fmha_tcgen05"
+
+        def io_cost(tag):
+            def f(out, args, kw):
+                ts = [t for t in args if isinstance(t, torch.Tensor)] + [out]
+                return 0.0, sum(t.numel() * t.element_size() for t in ts), tag
+            return f
+
+        table = {"gemm": gemm_cost, "fmha": fmha_cost, "layernorm": io_cost("layernorm"),
+                 "rmsnorm_rope_": io_cost("rmsnorm_rope"), "modulation": io_cost("small"), "skinny_linear": io_cost("small"),
+                 "timestep_features": io_cost("small"), "patchify": io_cost("small"), "unpatchify": io_cost("small"),
+                 "cfg_combine": io_cost("small"), "axpby_n": io_cost("small")}
+        for name, cost in table.items():
+            self._saved[name] = getattr(mod, name)
+            setattr(mod, name, self._wrap(name, self._saved[name], cost))
+        return self
+
+    def __exit__(self, *exc):
+        import sys
+
+        mod = sys.modules[__name__]
+        for name, fn in self._saved.items():
+            setattr(mod, name, fn)
+        torch.cuda.synchronize()
+        return False
+
+    def summary(self):
+        agg = {}
+        for tag, s, e, fl, by in self.records:
+            d = agg.setdefault(tag, {"ms": 0.0, "launches": 0, "flops": 0.0, "bytes": 0.0})
+            d["ms"] += s.elapsed_time(e)
+            d["launches"] += 1
+            d["flops"] += fl
+            d["bytes"] += by
+        return agg

@@ -1,0 +1,270 @@
+"""Wan-2.1 DiT denoiser on the sm_100a kernels -- drop-in for `pipe.transformer`.
+
+Mirrors the call surface of diffusers' `WanTransformer3DModel` as the reference uses it
+(/root/reference/inference_t23d.py:73-80,94-103 through WanPipeline; direct calls at
+/root/reference/train_vdm.py:557-562,598-603):
+
+    out, = model(hidden_states[B,16,T,H,W], timestep[B], encoder_hidden_states[B,Lt,4096], return_dict=False)
+
+plus `.config`, `.dtype`, `.device`, `.eval()`.  Weights are ingested from a diffusers-keyed state
+dict (`from_state_dict`); a PEFT LoRA adapter (train_vdm.py:370-388: r=8, alpha=16 on the eight
+attention projections) is folded into the base weights at load, so no rank-r GEMMs run per step.
+
+Data layout in HBM: the residual stream is one bf16 [B*L, D] matrix (token order t,h,w as
+`flatten(2).transpose(1,2)` gives); q/k/v of self-attention live in one fused [B*L, 3D] buffer
+written by a single N=3D GEMM and are consumed in place by RMSNorm+RoPE and attention (strided
+views, no transposes); text K/V of all layers are computed once per prompt and cached.
+dtype policy = the reference's CUDA-autocast trace: bf16 GEMM operands and
+residual stream, fp32 LayerNorm / RMSNorm statistics, fp32 AdaLN vectors and gated residual adds,
+bf16 rounding of each Linear output before gating.
+"""
+from __future__ import annotations
+
+import math
+from types import SimpleNamespace
+from typing import Dict, Optional
+
+import torch
+
+from . import ops
+
+
+def _rope_tables(head_dim: int, f: int, h: int, w: int, max_len: int, device) -> tuple:
+    """cos/sin [f*h*w, head_dim/2] fp32 of WanRotaryPosEmbed (fp64 angles; split 44/42/42 at d=128)."""
+    h_dim = w_dim = 2 * (head_dim // 6)
+    t_dim = head_dim - h_dim - w_dim
+    parts = []
+    for dim, n, shape in ((t_dim, f, (f, 1, 1)), (h_dim, h, (1, h, 1)), (w_dim, w, (1, 1, w))):
+        inv = 1.0 / (10000.0 ** (torch.arange(0, dim, 2, dtype=torch.float64)[: dim // 2] / dim))
+        ang = torch.outer(torch.arange(n, dtype=torch.float64), inv)  # [n, dim/2]
+        parts.append(ang.view(*shape, -1).expand(f, h, w, -1))
+    ang = torch.cat(parts, dim=-1).reshape(f * h * w, head_dim // 2)
+    return ang.cos().float().contiguous().to(device), ang.sin().float().contiguous().to(device)
+
+
+class WanTransformer3DModelB200(torch.nn.Module):
+    """B200-native WanTransformer3DModel (inference only)."""
+
+    def __init__(self, config, device="cuda"):
+        super().__init__()
+        cfg = config if isinstance(config, dict) else {k: getattr(config, k) for k in (
+            "patch_size", "num_attention_heads", "attention_head_dim", "in_channels", "out_channels", "text_dim",
+            "freq_dim", "ffn_dim", "num_layers", "cross_attn_norm", "eps", "rope_max_seq_len")}
+        self.config = SimpleNamespace(**cfg)
+        if tuple(self.config.patch_size) != (1, 2, 2):
+            raise NotImplementedError(f"patch_size {self.config.patch_size}: the patchify kernel implements Wan's (1,2,2)")
+        if self.config.attention_head_dim not in (64, 128):
+            raise NotImplementedError("attention_head_dim must be 64 or 128")
+        self._dev = torch.device(device)
+        self.w: Dict[str, torch.Tensor] = {}
+        self._rope_cache = {}
+        self._text_cache = None
+        self._ws = {}
+
+    # ------------------------------------------------------------------ module-like surface
+    @property
+    def dtype(self):
+        return torch.bfloat16
+
+    @property
+    def device(self):
+        return self._dev
+
+    def eval(self):
+        return self
+
+    def _apply(self, fn):  # .to()/.cuda() on the owning pipeline must not move or re-type our buffers
+        return self
+
+    # ------------------------------------------------------------------ weights
+    @classmethod
+    def from_state_dict(cls, sd: Dict[str, torch.Tensor], config, *, lora: Optional[Dict[str, torch.Tensor]] = None,
+                        lora_alpha: float = 16.0, lora_r: Optional[int] = None, device="cuda"):
+        m = cls(config, device)
+        m.load_weights(sd, lora=lora, lora_alpha=lora_alpha, lora_r=lora_r)
+        return m
+
+    def load_weights(self, sd, *, lora=None, lora_alpha=16.0, lora_r=None):
+        c, dev = self.config, self._dev
+        D = c.num_attention_heads * c.attention_head_dim
+
+        def lin_w(name):
+            wt = sd[name + ".weight"].to(torch.float32)
+            if lora is not None:
+                for pre in ("base_model.model.", ""):
+                    for mid in (".lora_A.weight", ".lora_A.default.weight"):
+                        ka = pre + name + mid
+                        if ka in lora:
+                            A = lora[ka].float()
+                            Bm = lora[ka.replace("lora_A", "lora_B")].float()
+                            r = lora_r or A.shape[0]
+                            wt = wt + (lora_alpha / r) * (Bm @ A)
+            return wt
+
+        def W(*names):  # bf16 [sum N, K] on device
+            return torch.cat([lin_w(n) for n in names], 0).to(dev, torch.bfloat16).contiguous()
+
+        def Bv(*names):  # fp32 [sum N]
+            return torch.cat([sd[n + ".bias"].float() for n in names], 0).to(dev).contiguous()
+
+        def V32(name):
+            return sd[name].float().to(dev).contiguous()
+
+        w = {}
+        w["patch.w"] = sd["patch_embedding.weight"].float().reshape(D, -1).to(dev, torch.bfloat16).contiguous()
+        w["patch.b"] = V32("patch_embedding.bias")
+        p = "condition_embedder."
+        for short, full in (("t1", "time_embedder.linear_1"), ("t2", "time_embedder.linear_2"), ("tp", "time_proj"),
+                            ("x1", "text_embedder.linear_1"), ("x2", "text_embedder.linear_2")):
+            w[short + ".w"], w[short + ".b"] = W(p + full), Bv(p + full)
+        w["out.table"] = V32("scale_shift_table").reshape(2, D).contiguous()
+        w["out.w"], w["out.b"] = W("proj_out"), Bv("proj_out")
+        for i in range(c.num_layers):
+            b = f"blocks.{i}."
+            k = f"b{i}."
+            w[k + "table"] = V32(b + "scale_shift_table").reshape(6, D).contiguous()
+            w[k + "qkv.w"] = W(b + "attn1.to_q", b + "attn1.to_k", b + "attn1.to_v")
+            w[k + "qkv.b"] = Bv(b + "attn1.to_q", b + "attn1.to_k", b + "attn1.to_v")
+            w[k + "nq1"], w[k + "nk1"] = V32(b + "attn1.norm_q.weight"), V32(b + "attn1.norm_k.weight")
+            w[k + "o1.w"], w[k + "o1.b"] = W(b + "attn1.to_out.0"), Bv(b + "attn1.to_out.0")
+            w[k + "q2.w"], w[k + "q2.b"] = W(b + "attn2.to_q"), Bv(b + "attn2.to_q")
+            w[k + "kv2.w"] = W(b + "attn2.to_k", b + "attn2.to_v")
+            w[k + "kv2.b"] = Bv(b + "attn2.to_k", b + "attn2.to_v")
+            w[k + "nq2"], w[k + "nk2"] = V32(b + "attn2.norm_q.weight"), V32(b + "attn2.norm_k.weight")
+            w[k + "o2.w"], w[k + "o2.b"] = W(b + "attn2.to_out.0"), Bv(b + "attn2.to_out.0")
+            if c.cross_attn_norm:
+                w[k + "n2.w"], w[k + "n2.b"] = V32(b + "norm2.weight"), V32(b + "norm2.bias")
+            w[k + "f1.w"], w[k + "f1.b"] = W(b + "ffn.net.0.proj"), Bv(b + "ffn.net.0.proj")
+            w[k + "f2.w"], w[k + "f2.b"] = W(b + "ffn.net.2"), Bv(b + "ffn.net.2")
+        self.w = w
+        self._text_cache = None
+
+    def weight_bytes(self) -> int:
+        return sum(t.numel() * t.element_size() for t in self.w.values())
+
+    # ------------------------------------------------------------------ per-prompt text state
+    def encode_text(self, encoder_hidden_states: torch.Tensor):
+        """Text MLP (4096 -> D -> D, GELU-tanh) and the K/V projections (+RMSNorm on K) of every
+        cross-attention layer: constant across the 50 steps of one prompt."""
+        c, w = self.config, self.w
+        B, Lt, _ = encoder_hidden_states.shape
+        D = c.num_attention_heads * c.attention_head_dim
+        x = encoder_hidden_states.to(self._dev, torch.bfloat16).reshape(B * Lt, -1)
+        t1 = ops.gemm(x, w["x1.w"], w["x1.b"], act="gelu_tanh")
+        txt = ops.gemm(t1, w["x2.w"], w["x2.b"])
+        kv = torch.empty((c.num_layers, B * Lt, 2 * D), dtype=torch.bfloat16, device=self._dev)
+        for i in range(c.num_layers):
+            k = f"b{i}."
+            ops.gemm(txt, w[k + "kv2.w"], w[k + "kv2.b"], out=kv[i])
+            ops.rmsnorm_rope_(kv[i][:, :D], w[k + "nk2"], c.attention_head_dim, eps=c.eps)
+        return SimpleNamespace(kv=kv, B=B, Lt=Lt)
+
+    def _text_state(self, enc: torch.Tensor):
+        key = (enc.data_ptr(), tuple(enc.shape), enc._version, enc.dtype)
+        if self._text_cache is None or self._text_cache[0] != key:
+            self._text_cache = (key, self.encode_text(enc))
+        return self._text_cache[1]
+
+    # ------------------------------------------------------------------ forward
+    def _workspace(self, B, L):
+        key = (B, L)
+        ws = self._ws.get(key)
+        if ws is None:
+            c = self.config
+            D = c.num_attention_heads * c.attention_head_dim
+            M, dev, bf = B * L, self._dev, torch.bfloat16
+            ws = SimpleNamespace(
+                x=torch.empty((M, D), dtype=bf, device=dev), h=torch.empty((M, D), dtype=bf, device=dev),
+                qkv=torch.empty((M, 3 * D), dtype=bf, device=dev), q2=torch.empty((M, D), dtype=bf, device=dev),
+                att=torch.empty((M, D), dtype=bf, device=dev), ffn=torch.empty((M, c.ffn_dim), dtype=bf, device=dev),
+                mod=torch.empty((B, 6, D), dtype=torch.float32, device=dev),
+                mod2=torch.empty((B, 2, D), dtype=torch.float32, device=dev),
+                po=torch.empty((M, self.w["out.w"].shape[0]), dtype=bf, device=dev))
+            self._ws = {key: ws}  # one live shape at a time
+        return ws
+
+    @torch.no_grad()
+    def forward(self, hidden_states, timestep, encoder_hidden_states, encoder_hidden_states_image=None,
+                return_dict: bool = False, attention_kwargs=None, text_state=None):
+        if encoder_hidden_states_image is not None:
+            raise NotImplementedError("image-conditioned Wan (I2V) is outside the VIST3A text-to-3D path")
+        if not self.w:
+            raise RuntimeError("weights not loaded: use WanTransformer3DModelB200.from_state_dict(...)")
+        c, w = self.config, self.w
+        H_, hd = c.num_attention_heads, c.attention_head_dim
+        D = H_ * hd
+        B, C_, T, Hh, Ww = hidden_states.shape
+        f, h, wd = T, Hh // 2, Ww // 2
+        L = f * h * wd
+        M = B * L
+        in_dtype = hidden_states.dtype
+        if hidden_states.dtype not in (torch.bfloat16, torch.float32):
+            hidden_states = hidden_states.to(torch.bfloat16)
+        hidden_states = hidden_states.to(self._dev)
+        ts = text_state if text_state is not None else self._text_state(encoder_hidden_states)
+        if ts.B != B:
+            raise ValueError(f"encoder_hidden_states batch {ts.B} != hidden_states batch {B}")
+        rk = (f, h, wd)
+        if rk not in self._rope_cache:
+            self._rope_cache[rk] = _rope_tables(hd, f, h, wd, c.rope_max_seq_len, self._dev)
+        cos, sin = self._rope_cache[rk]
+        ws = self._workspace(B, L)
+
+        # condition embedder (M = B rows: weight-streaming kernels)
+        tstep = torch.as_tensor(timestep).to(self._dev).reshape(-1)
+        if tstep.numel() == 1 and B > 1:
+            tstep = tstep.expand(B)
+        tfeat = ops.timestep_features(tstep, c.freq_dim)
+        t1 = ops.skinny_linear(tfeat, w["t1.w"], w["t1.b"], act="silu", out_dtype=torch.float32)
+        temb = ops.skinny_linear(t1, w["t2.w"], w["t2.b"], out_dtype=torch.float32)
+        tproj = ops.skinny_linear(temb, w["tp.w"], w["tp.b"], pre_act="silu", out_dtype=torch.float32)  # [B, 6D]
+
+        # patch embedding: gather 2x2 patches -> K=64 GEMM (+bias)
+        a = ops.patchify(hidden_states)
+        x = ops.gemm(a, w["patch.w"], w["patch.b"], out=ws.x)
+
+        for i in range(c.num_layers):
+            k = f"b{i}."
+            # mod = [shift1, 1+scale1, gate1, shift2, 1+scale2, gate2]
+            ops.modulation(w[k + "table"], tproj, nvec=6, broadcast=False, one_plus_mask=0b010010, out=ws.mod)
+            mod = ws.mod
+            # --- self-attention
+            ops.layernorm(x, mul=mod[:, 1], add=mod[:, 0], mul_bstride=6 * D, add_bstride=6 * D, rows_per_batch=L,
+                          eps=c.eps, out=ws.h)
+            ops.gemm(ws.h, w[k + "qkv.w"], w[k + "qkv.b"], out=ws.qkv)
+            ops.rmsnorm_rope_(ws.qkv[:, :D], w[k + "nq1"], hd, eps=c.eps, cos=cos, sin=sin)
+            ops.rmsnorm_rope_(ws.qkv[:, D:2 * D], w[k + "nk1"], hd, eps=c.eps, cos=cos, sin=sin)
+            qkv5 = ws.qkv.view(B, L, 3, H_, hd)
+            ops.fmha(qkv5[:, :, 0], qkv5[:, :, 1], qkv5[:, :, 2], out=ws.att.view(B, L, H_, hd))
+            ops.gemm(ws.att, w[k + "o1.w"], w[k + "o1.b"], gate=mod[:, 2], gate_bstride=6 * D, rows_per_batch=L,
+                     residual=x, out=x, round_linear=True)
+            # --- cross-attention
+            if c.cross_attn_norm:
+                ops.layernorm(x, mul=w[k + "n2.w"], add=w[k + "n2.b"], eps=c.eps, out=ws.h)
+                hq = ws.h
+            else:
+                hq = x
+            ops.gemm(hq, w[k + "q2.w"], w[k + "q2.b"], out=ws.q2)
+            ops.rmsnorm_rope_(ws.q2, w[k + "nq2"], hd, eps=c.eps)
+            kv5 = ts.kv[i].view(B, ts.Lt, 2, H_, hd)
+            ops.fmha(ws.q2.view(B, L, H_, hd), kv5[:, :, 0], kv5[:, :, 1], out=ws.att.view(B, L, H_, hd))
+            ops.gemm(ws.att, w[k + "o2.w"], w[k + "o2.b"], residual=x, out=x, round_linear=True)
+            # --- feed-forward
+            ops.layernorm(x, mul=mod[:, 4], add=mod[:, 3], mul_bstride=6 * D, add_bstride=6 * D, rows_per_batch=L,
+                          eps=c.eps, out=ws.h)
+            ops.gemm(ws.h, w[k + "f1.w"], w[k + "f1.b"], act="gelu_tanh", out=ws.ffn)
+            ops.gemm(ws.ffn, w[k + "f2.w"], w[k + "f2.b"], gate=mod[:, 5], gate_bstride=6 * D, rows_per_batch=L,
+                     residual=x, out=x, round_linear=True)
+
+        # output head: mod2 = [shift, 1+scale] from table + temb
+        ops.modulation(w["out.table"], temb, nvec=2, broadcast=True, one_plus_mask=0b10, out=ws.mod2)
+        ops.layernorm(x, mul=ws.mod2[:, 1], add=ws.mod2[:, 0], mul_bstride=2 * D, add_bstride=2 * D, rows_per_batch=L,
+                      eps=c.eps, out=ws.h)
+        ops.gemm(ws.h, w["out.w"], w["out.b"], out=ws.po)
+        out_dtype = in_dtype if in_dtype in (torch.bfloat16, torch.float32) else torch.bfloat16
+        out = ops.unpatchify(ws.po, B, c.out_channels, T, Hh, Ww, out_dtype=out_dtype)
+        if out.dtype != in_dtype:
+            out = out.to(in_dtype)
+        if return_dict:
+            return SimpleNamespace(sample=out)
+        return (out,)
