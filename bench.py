@@ -217,6 +217,14 @@ def run_ours(args):
 
     for i in range(args.warmup):
         dev_step(i)
+    if args.ncu_step:
+        # one denoise step between cudaProfilerStart/Stop: `ncu --profile-from-start off ... bench.py --no-graph --ncu-step`
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        dev_step(0)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        return
     n0 = _lib.launch_count()
     with ClockSampler(local) as clk:
         ms = timed(dev_step, args.steps)
@@ -259,6 +267,11 @@ def run_ours(args):
             eng.sampler.step(eng.eps, eng.x)
         launches_per_step = _lib.launch_count() - n1
         summ = tm.summary()
+        if args.detail:
+            for k, v in sorted(tm.summary(detail=True).items(), key=lambda kv: -kv[1]["ms"]):
+                tf = v["flops"] / (v["ms"] / 1e3) / 1e12 if v["flops"] else 0.0
+                print(f"# {k:55s} {v['launches']:4d} launches {v['ms']:9.3f} ms  {tf:8.1f} TFLOP/s  {v['bytes'] / (v['ms'] / 1e3) / 1e9:8.1f} GB/s",
+                      file=sys.stderr)
         tot = sum(d["ms"] for d in summ.values())
         top = max((k for k in summ if summ[k]["flops"] > 0), key=lambda k: summ[k]["ms"])
         pk = _peaks()
@@ -303,11 +316,13 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ncu-step", action="store_true", help="profile exactly one eager denoise step (for ncu --profile-from-start off)")
+    ap.add_argument("--detail", action="store_true", help="print per-shape kernel timings of one eager step to stderr")
     ap.add_argument("--ref-blocks", type=int, default=2, help="full-size blocks per CPU sample")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

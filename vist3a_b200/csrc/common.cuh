@@ -328,6 +328,6 @@ __device__ __forceinline__ float gelu_tanh_precise_f(float x) {
   return 0.5f * x * (1.0f + tanhf(u));
 }
 __device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
-__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+__device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 
 }  // namespace v3a

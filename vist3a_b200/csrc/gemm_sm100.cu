@@ -48,18 +48,31 @@ struct GemmCfg {
   static_assert(TMEM_COLS <= 512, "TMEM");
 };
 
-__device__ __forceinline__ float apply_act(float v, int act) {
+template <int ACT>
+__device__ __forceinline__ void act32(float (&v)[32]) {
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    if constexpr (ACT == VIST3A_ACT_GELU_TANH) v[j] = gelu_tanh_f(v[j]);
+    else if constexpr (ACT == VIST3A_ACT_GELU_ERF) v[j] = gelu_erf_f(v[j]);
+    else if constexpr (ACT == VIST3A_ACT_SILU) v[j] = silu_f(v[j]);
+    else if constexpr (ACT == VIST3A_ACT_RELU) v[j] = fmaxf(v[j], 0.0f);
+  }
+}
+// one warp-uniform dispatch per 32-column chunk (a per-element switch compiles to a jump table per element)
+__device__ __forceinline__ void apply_act32(float (&v)[32], int act) {
   switch (act) {
-    case VIST3A_ACT_GELU_TANH: return gelu_tanh_f(v);
-    case VIST3A_ACT_GELU_ERF: return gelu_erf_f(v);
-    case VIST3A_ACT_SILU: return silu_f(v);
-    case VIST3A_ACT_RELU: return fmaxf(v, 0.0f);
-    default: return v;
+    case VIST3A_ACT_GELU_TANH: act32<VIST3A_ACT_GELU_TANH>(v); break;
+    case VIST3A_ACT_GELU_ERF: act32<VIST3A_ACT_GELU_ERF>(v); break;
+    case VIST3A_ACT_SILU: act32<VIST3A_ACT_SILU>(v); break;
+    case VIST3A_ACT_RELU: act32<VIST3A_ACT_RELU>(v); break;
+    default: break;
   }
 }
 
+constexpr int kGemmThreads = 384;  // warps 0-3: TMA / MMA / TMEM alloc / idle; warps 4-11: epilogue
+
 template <int BN, int kCta, bool kTF32>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const GemmShape shape, const GemmEpilogue ep) {
   using Cfg = GemmCfg<BN, kCta, kTF32>;
@@ -92,7 +105,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), 4 * kCta);  // one arrival per epilogue warp (of both CTAs)
+      mbar_init(tempty_bar(s), 8 * kCta);  // one arrival per epilogue warp (of both CTAs)
     }
     fence_barrier_init();
   }
@@ -164,30 +177,36 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   } else if (warp >= 4) {
     // ------------------------------ epilogue ------------------------------
-    const uint32_t q = warp & 3u;  // TMEM sub-partition of this warp: lanes [32q, 32q+32)
+    // Two warps per TMEM lane quadrant: warp w reads lanes [32 (w%4), +32) and every other 32-column chunk.
+    const uint32_t q = warp & 3u;
+    const int half = (int)((warp - 4u) >> 2);
+    constexpr int NCHUNK = BN / 32;
     int as = 0;
     uint32_t aph = 0;
     for (int tile = worker; tile < num_tiles; tile += num_workers) {
       const int tm = tile % shape.tiles_m, tn = tile / shape.tiles_m;
       const int row = (tm * kCta + (int)rank) * Cfg::BM + (int)(q * 32u + lane);
       const int n_tile = tn * BN;
-      mbar_wait(tfull_bar(as), aph);
-      tc_fence_after();
       const bool row_ok = row < shape.M;
       const long long b = row_ok ? (long long)row / ep.rows_per_batch : 0;
       const float* gate_row = ep.gate ? ep.gate + b * ep.gate_bstride : nullptr;
+      mbar_wait(tfull_bar(as), aph);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((q * 32u) << 16) + (uint32_t)(as * BN);
+      uint32_t r[32];
+      if (n_tile + half * 32 < shape.N) tmem_ld_x32(taddr + (uint32_t)(half * 32), r);
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = half; c < NCHUNK; c += 2) {
         const int n0 = n_tile + c * 32;
         if (n0 >= shape.N) break;  // warp-uniform
-        uint32_t r[32];
-        tmem_ld_x32(tmem_base + ((q * 32u) << 16) + (uint32_t)(as * BN + c * 32), r);
         tmem_ld_wait();
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        // prefetch the next chunk of this warp while this one is processed
+        if (c + 2 < NCHUNK && n0 + 64 < shape.N) tmem_ld_x32(taddr + (uint32_t)((c + 2) * 32), r);
         if (row_ok) {
           const int ncols = min(32, shape.N - n0);
-          float v[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
           if (ep.bias) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
@@ -197,10 +216,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               }
             }
           }
-          if (ep.act != VIST3A_ACT_NONE) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], ep.act);
-          }
+          if (ep.act != VIST3A_ACT_NONE) apply_act32(v, ep.act);
           if (ep.round_linear) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = bf16_round(v[j]);
@@ -264,6 +280,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           }
         }
       }
+      tmem_ld_wait();
       // release the accumulator stage to the MMA warp
       tc_fence_before();
       __syncwarp();
@@ -328,7 +345,7 @@ static int launch_gemm(const vist3a_gemm_args& a, cudaStream_t stream) {
   if (workers > tiles) workers = tiles;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(workers * kCta));
-  cfg.blockDim = dim3(256);
+  cfg.blockDim = dim3(kGemmThreads);
   cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];

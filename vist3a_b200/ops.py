@@ -262,13 +262,15 @@ class OpTimer:
             M, K = a.reshape(-1, a.shape[-1]).shape
             N = w.shape[0]
             by = M * K * a.element_size() + N * K * w.element_size() + M * N * out.element_size()
-            return 2.0 * M * N * K, by, "gemm_tcgen05"
+            ep = ("+" + kw["act"] if kw.get("act") else "") + ("+gate" if kw.get("gate") is not None else "") + (
+                "+res" if kw.get("residual") is not None else "")
+            return 2.0 * M * N * K, by, f"gemm_tcgen05|{M}x{N}x{K}{ep}"
 
         def fmha_cost(out, args, kw):
             q, kk = args[0], args[1]
             B, Lq, H, D = q.shape
             Lk = kk.shape[1]
-            return 4.0 * B * H * Lq * Lk * D, 2 * (2 * B * Lq * H * D + 2 * B * Lk * H * D), "fmha_tcgen05"
+            return 4.0 * B * H * Lq * Lk * D, 2 * (2 * B * Lq * H * D + 2 * B * Lk * H * D), f"fmha_tcgen05|{B}x{H}x{Lq}x{Lk}x{D}"
 
         def io_cost(tag):
             def f(out, args, kw):
@@ -294,10 +296,11 @@ class OpTimer:
         torch.cuda.synchronize()
         return False
 
-    def summary(self):
+    def summary(self, detail: bool = False):
+        """aggregate by kernel class (default) or by kernel class | shape+epilogue (detail=True)"""
         agg = {}
         for tag, s, e, fl, by in self.records:
-            d = agg.setdefault(tag, {"ms": 0.0, "launches": 0, "flops": 0.0, "bytes": 0.0})
+            d = agg.setdefault(tag if detail else tag.split("|")[0], {"ms": 0.0, "launches": 0, "flops": 0.0, "bytes": 0.0})
             d["ms"] += s.elapsed_time(e)
             d["launches"] += 1
             d["flops"] += fl
