@@ -1,0 +1,181 @@
+"""ORACLE support (test infrastructure; only usable where /root/reference is mounted, i.e. in the
+build container -- never on the GPU box and never from vist3a_b200): imports the REAL reference
+decoder (`models/stitched_model.py:StitchVAE3D` -> `models/anysplat_stitched.py:AnySplatStitched`)
+on CPU so that oracle/decoder_ref.py can be validated against it and golden vectors generated.
+
+What is stubbed: third-party roots that the reference imports at module load but never
+executes on the `forward_with_latent(train=False, voxelize=False)` path, `VGGT.from_pretrained`
+(network) and the `AutoencoderKLWan` isinstance check.  The reference's forward code runs unmodified.
+
+`width="tiny"` shrinks constructor hyper-parameters only (embed dim, head counts, DPT feature
+widths) through the reference classes' own keyword arguments, so that a full weight set is a few MB
+and golden vectors can be committed; depth (24 alternating blocks, stitch after enc block 2) and
+every code path are those of the full model.
+"""
+from __future__ import annotations
+
+import functools
+import os
+import sys
+import types
+from dataclasses import dataclass
+
+import torch
+
+REFERENCE_ROOT = "/root/reference"
+
+_STUBS = [
+    "diffusers", "diffusers.configuration_utils", "diffusers.loaders", "diffusers.loaders.single_file_model",
+    "diffusers.models", "diffusers.models.activations", "diffusers.models.autoencoders", "diffusers.models.autoencoders.vae",
+    "diffusers.models.modeling_outputs", "diffusers.models.modeling_utils", "diffusers.pipelines", "diffusers.pipelines.wan",
+    "diffusers.pipelines.wan.pipeline_wan", "diffusers.utils", "diffusers.utils.accelerate_utils",
+    "dacite", "lightning", "lightning.pytorch", "lightning.pytorch.utilities", "skvideo", "skvideo.io", "matplotlib", "matplotlib.figure",
+    "matplotlib.pyplot", "matplotlib.cm", "matplotlib.colors", "omegaconf", "torch_scatter", "xformers", "xformers.ops", "e3nn", "e3nn.o3", "gsplat",
+    "colorspacious", "plyfile", "moviepy", "moviepy.editor", "lpips", "wandb", "imageio", "cv2", "open3d", "trimesh", "roma", "kornia", "hydra",
+]
+
+
+def available() -> bool:
+    return os.path.isdir(os.path.join(REFERENCE_ROOT, "models"))
+
+
+def _make_stub(name: str):
+    if name in sys.modules:
+        return
+    try:
+        __import__(name)
+        return
+    except Exception:
+        pass
+    m = types.ModuleType(name)
+    m.__path__ = []
+
+    def ga(attr):
+        if attr.startswith("__"):
+            raise AttributeError(attr)
+
+        def _decorator_or_obj(*a, **k):
+            if len(a) == 1 and callable(a[0]) and not k:
+                return a[0]
+            return None
+
+        cls = type(attr, (), {"__init__": lambda self, *a, **k: None, "__class_getitem__": classmethod(lambda c, x: c),
+                              "__call__": lambda self, *a, **k: None})
+        return cls
+
+    m.__getattr__ = ga
+    sys.modules[name] = m
+
+
+@dataclass(frozen=True)
+class RefWidth:
+    """constructor hyper-parameters of the reference model (defaults = the released model)"""
+    embed_dim: int = 1024
+    num_heads: int = 16            # aggregator + DINO heads (head_dim 64)
+    dino_depth: int = 24
+    cam_heads: int = 16
+    dpt_features: int = 256
+    dpt_out_channels: tuple = (256, 512, 1024, 1024)
+    pos_grid: int = 37             # DINO pos-embed grid (img_size 518 / 14)
+
+
+FULL = RefWidth()
+# dpt_features stays 256: the GS head hard-codes 128 merger channels = features // 2 (vggt_dpt_gs_head.py:69-76)
+TINY = RefWidth(embed_dim=64, num_heads=1, dino_depth=4, cam_heads=2, dpt_features=256, dpt_out_channels=(32, 32, 64, 64), pos_grid=37)
+
+
+def load_reference(width: RefWidth = FULL, resolution: int = 512, seed: int = 0, sh_degree: int = 4):
+    """Returns the reference StitchVAE3D (fp32, eval, checkpointing off) with seeded random init."""
+    if not available():
+        raise RuntimeError(f"{REFERENCE_ROOT} is not mounted here; the real reference can only be imported in the build container")
+    for n in _STUBS:
+        _make_stub(n)
+    if REFERENCE_ROOT not in sys.path:
+        sys.path.insert(0, REFERENCE_ROOT)
+    P = "third_party_model.anysplat.src.model"
+    import importlib
+
+    vggt_mod = importlib.import_module(P + ".encoder.vggt.models.vggt")
+    agg_mod = importlib.import_module(P + ".encoder.vggt.models.aggregator")
+    vit_mod = importlib.import_module(P + ".encoder.vggt.layers.vision_transformer")
+    cam_mod = importlib.import_module(P + ".encoder.vggt.heads.camera_head")
+    dpt_mod = importlib.import_module(P + ".encoder.vggt.heads.dpt_head")
+    enc_mod = importlib.import_module(P + ".encoder.anysplat")
+    gsh_mod = importlib.import_module(P + ".encoder.heads.vggt_dpt_gs_head")
+    import models.stitched_model as sm
+    from models.stitching_layer_builder import parse_conv_spec
+
+    W = width
+    VGGT = vggt_mod.VGGT
+
+    def vit_small_cfg(patch_size=16, num_register_tokens=0, **kw):
+        return vit_mod.DinoVisionTransformer(patch_size=patch_size, embed_dim=W.embed_dim, depth=W.dino_depth, num_heads=W.num_heads,
+                                             mlp_ratio=4, block_fn=functools.partial(vit_mod.Block, attn_class=vit_mod.MemEffAttention),
+                                             num_register_tokens=num_register_tokens, **kw)
+
+    saved = {}
+
+    def patch(obj, name, val):
+        saved[(obj, name)] = getattr(obj, name)
+        setattr(obj, name, val)
+
+    try:
+        if W != FULL:
+            patch(agg_mod, "vit_large", vit_small_cfg)
+            patch(vggt_mod, "Aggregator", functools.partial(agg_mod.Aggregator, num_heads=W.num_heads))
+            patch(vggt_mod, "CameraHead", functools.partial(cam_mod.CameraHead, num_heads=W.cam_heads))
+            patch(vggt_mod, "DPTHead", functools.partial(dpt_mod.DPTHead, features=W.dpt_features, out_channels=list(W.dpt_out_channels)))
+
+            class _GS(gsh_mod.VGGT_DPT_GS_Head):
+                def __init__(self, dim_in, patch_size, output_dim, activation, conf_activation, features):
+                    super().__init__(dim_in=2 * W.embed_dim, patch_size=patch_size, output_dim=output_dim, activation=activation,
+                                     conf_activation=conf_activation, features=W.dpt_features, out_channels=list(W.dpt_out_channels))
+
+            patch(enc_mod, "VGGT_DPT_GS_Head", _GS)
+        emb = W.embed_dim
+        patch(VGGT, "from_pretrained", classmethod(lambda cls, *a, **k: cls(embed_dim=emb)))
+
+        class FakeVAE(torch.nn.Module):
+            pass
+
+        patch(sm, "AutoencoderKLWan", FakeVAE)
+        patch(sm, "AutoencoderKLWan_wan", FakeVAE)
+
+        anysplat_mod = importlib.import_module(P + ".model.anysplat")
+        ga_mod = importlib.import_module(P + ".encoder.common.gaussian_adapter")
+        dec_mod = importlib.import_module(P + ".decoder.decoder_splatting_cuda")
+        cfg = enc_mod.EncoderAnySplatCfg(
+            name="anysplat", anchor_feat_dim=83, voxel_size=0.002, n_offsets=2, d_feature=32, add_view=False,
+            num_monocular_samples=32, backbone=None, visualizer=None,
+            gaussian_adapter=ga_mod.GaussianAdapterCfg(0.5, 15.0, sh_degree), apply_bounds_shim=True,
+            opacity_mapping=enc_mod.OpacityMappingCfg(0.0, 0.0, 1), gaussians_per_pixel=1, num_surfaces=1,
+            gs_params_head_type="dpt_gs", pred_head_type="depth", voxelize=False, intermediate_layer_idx=[4, 11, 17, 23])
+        torch.manual_seed(seed)
+        ff = anysplat_mod.AnySplat(cfg, dec_mod.DecoderSplattingCUDACfg("splatting_cuda", [1.0, 1.0, 1.0], False))
+        model = sm.StitchVAE3D(FakeVAE(), ff, torch.device("cpu"), "enc_blocks_2",
+                               parse_conv_spec(f"conv3d_k5x3x3_o{W.embed_dim}_s1x2x2_p2x1x1"), resolution)
+    finally:
+        for (obj, name), val in saved.items():
+            setattr(obj, name, val)
+    model = model.float().eval()
+    model.stitched_3d_model.grad_checkpointing = False
+    model.stitched_3d_model.encoder.aggregator.use_checkpoint = False
+    return model
+
+
+def decoder_state_dict(model) -> dict:
+    """the tensors the decoder path reads, with the reference's own state-dict key names (diffusion_vae excluded)"""
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items() if not k.startswith("diffusion_vae")}
+    return sd
+
+
+def outputs_to_dict(out) -> dict:
+    """flatten the reference's EncoderOutput into plain tensors"""
+    g = out.gaussians
+    d = {"means": g.means, "covariances": g.covariances, "harmonics": g.harmonics, "opacities": g.opacities, "scales": g.scales,
+         "rotations": g.rotations, "extrinsic": out.pred_context_pose["extrinsic"], "intrinsic": out.pred_context_pose["intrinsic"],
+         "depth": out.depth_dict["depth"], "last_pred_pose_enc": out.last_pred_pose_enc,
+         "scene_scale": out.infos["scene_scale"].reshape(1)}
+    for i, p in enumerate(out.pred_pose_enc_list):
+        d[f"pred_pose_enc_{i}"] = p
+    return {k: v.detach().float().contiguous() for k, v in d.items()}
