@@ -46,7 +46,8 @@ int64_t vist3a_launch_count(void);
  *   AS/.../heads/dpt_head.py:69-79, and (after im2col) models/stitching_layer_builder.py:32-42.
  * Epilogue, in order:  v = acc + bias[n];  v = act(v);  if round_linear: v = bf16(v);
  *   if gate: v *= gate[(row / rows_per_batch) * gate_bstride + n];  if round_gate: v = bf16(v);
- *   if residual: v += residual[row, n];  store as out_dtype.
+ *   if residual: v += residual[rmap(row), n];  if residual2: v += residual2[cmap(row), n];  v = post_act(v);
+ *   store C[cmap(row), n] as out_dtype.
  * ------------------------------------------------------------------------------------------ */
 #define VIST3A_ACT_NONE 0
 #define VIST3A_ACT_GELU_TANH 1 /* FeedForward(activation_fn="gelu-approximate"), Wan text embedder */
@@ -57,20 +58,43 @@ int64_t vist3a_launch_count(void);
 #define VIST3A_GEMM_FLAG_2CTA 1u       /* use cta_group::2 pairs (256-row tiles) */
 #define VIST3A_GEMM_FLAG_1CTA 2u       /* force single-CTA tiles */
 
+/* row -> memory-row mapping of C / residual:  mem_row = (row / rpg) * gstride + goff + row % rpg   (rpg == 0: identity).
+ * Lets a GEMM write into (or add from) a token buffer whose groups of rows are separated by other rows, e.g. the
+ * stitching conv writing patch tokens behind the 5 special tokens of every view (models/anysplat_stitched.py:181-202),
+ * or add one [rpg, N] table to every group (gstride = 0: DINO / DPT positional embeddings). */
+typedef struct vist3a_rowmap {
+  int64_t rpg, gstride, goff;
+} vist3a_rowmap;
+
+/* implicit-GEMM convolution over an NHWC activation (A operand fetched by 4-D TMA, zero padding by out-of-bounds fill):
+ *   A = x[n_img, h_in, w_in, c_in];  W = [N, kh*kw*c_in] with k = (dy*kw + dx)*c_in + c;  stride 1;
+ *   output row = pixel (n, y, x) of the h_out x w_out map, M = n_img*h_out*w_out.
+ * replaces: the 3x3 nn.Conv2d layers of AS/model/encoder/vggt/heads/dpt_head.py:346-359,375-376,437-439 (cuDNN). */
+typedef struct vist3a_conv {
+  int32_t enabled;
+  int32_t kh, kw, pad;
+  int32_t n_img, h, w, c_in; /* stride-1 "same"-style conv: h_out = h + 2*pad - kh + 1 */
+} vist3a_conv;
+
 typedef struct vist3a_gemm_args {
-  const void* A;          /* [M, K] in_dtype, row stride lda */
+  const void* A;          /* [M, K] in_dtype, row stride lda  (conv mode: NHWC tensor) */
   const void* W;          /* [N, K] in_dtype, row stride ldw (nn.Linear weight layout) */
   void* C;                /* [M, N] out_dtype, row stride ldc */
   const float* bias;      /* [N] fp32 or NULL */
   const float* gate;      /* fp32, index (row / rows_per_batch) * gate_bstride + n, or NULL */
-  const void* residual;   /* [M, N] out_dtype, row stride ldr, or NULL (may alias C) */
+  const void* residual;   /* out_dtype, row stride ldr, rows mapped by rmap, or NULL (may alias C) */
+  const void* residual2;  /* out_dtype, row stride ldc, rows mapped like C, or NULL */
   int64_t M, N, K;
   int64_t lda, ldw, ldc, ldr;
   int64_t rows_per_batch; /* >= 1 */
   int64_t gate_bstride;   /* 0 => one gate vector shared by all rows (LayerScale) */
+  vist3a_rowmap cmap;     /* row mapping of C and residual2 */
+  vist3a_rowmap rmap;     /* row mapping of residual */
+  vist3a_conv conv;
   int32_t in_dtype;       /* VIST3A_DTYPE_BF16 (kind::f16) or VIST3A_DTYPE_F32 (kind::tf32) */
   int32_t out_dtype;
-  int32_t act;
+  int32_t act;            /* applied to acc + bias */
+  int32_t post_act;       /* applied after the residual adds (VIST3A_ACT_NONE / VIST3A_ACT_RELU) */
   int32_t round_linear;   /* round (acc+bias, act) to bf16 before gate/residual (autocast Linear) */
   int32_t round_gate;     /* round the gated product to bf16 (bf16 LayerScale) */
   uint32_t flags;
@@ -103,14 +127,16 @@ int vist3a_fmha_fwd(const vist3a_fmha_args* args, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * LayerNorm with optional modulation:  out[r,:] = LN(x[r,:]) * mul[b,:] + add[b,:],  b = r / rows_per_batch
- * LN statistics in fp32 (biased variance), eps inside the sqrt.
+ * LN statistics in fp32 (biased variance), eps inside the sqrt.  mul_plus_one: use (1 + mul).  in_map / out_map (may be
+ * NULL) map row r to a memory row of x / out (e.g. the patch tokens behind the 5 special tokens of every view).
  * replaces: diffusers FP32LayerNorm + AdaLN-zero "(norm(x) * (1 + scale) + shift)" (mul = 1+scale,
  *   add = shift, batch stride = mul_bstride), FP32LayerNorm(elementwise_affine=True) of norm2
  *   (mul = weight, add = bias, bstride 0), and nn.LayerNorm in AS/.../layers/block.py:62,73.
  * ------------------------------------------------------------------------------------------ */
 int vist3a_layernorm(const void* x, int32_t x_dtype, int64_t ldx, void* out, int32_t out_dtype, int64_t ldo,
                      int64_t rows, int64_t dim, int64_t rows_per_batch, const float* mul, int64_t mul_bstride,
-                     const float* add, int64_t add_bstride, float eps, void* stream);
+                     const float* add, int64_t add_bstride, float eps, int32_t mul_plus_one,
+                     const vist3a_rowmap* in_map, const vist3a_rowmap* out_map, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * RMSNorm across all heads (+ optional interleaved-pair RoPE), in place on a strided bf16 matrix.
@@ -134,13 +160,15 @@ int vist3a_modulation(const float* table, const void* mod, int32_t mod_dtype, in
                       int64_t batch, int64_t nvec, int64_t dim, uint32_t one_plus_mask, void* stream);
 
 /* ------------------------------------------------------------------------------------------
- * Skinny linear for M <= 16 rows (HBM-bound weight streaming):  y = act(x W^T + b)
+ * Skinny linear for M <= 16 rows (HBM-bound weight streaming):  y = residual + gate[n] * act(pre_act(x) W^T + b)
+ * (gate [N] fp32 = LayerScale, residual [M, N] fp32; both optional)
  * replaces: Wan TimestepEmbedding / time_proj (M = batch) and every Linear of
  *   AS/model/encoder/vggt/heads/camera_head.py:87-170 (M = views).
  * ------------------------------------------------------------------------------------------ */
 int vist3a_skinny_linear(const void* x, int32_t x_dtype, int64_t ldx, const void* W, int32_t w_dtype, int64_t ldw,
                          const float* bias, void* y, int32_t y_dtype, int64_t ldy, int64_t M, int64_t N, int64_t K,
-                         int32_t pre_act, int32_t act, void* stream);
+                         int32_t pre_act, int32_t act, const float* gate, const float* residual, int64_t ldres,
+                         void* stream);
 
 /* sinusoidal timestep features: out[b, 0:half] = cos(t_b f_i), out[b, half:] = sin(t_b f_i),
  * f_i = exp(-ln(10000) i / half)  (diffusers Timesteps(flip_sin_to_cos=True, downscale_freq_shift=0)) */
@@ -170,6 +198,79 @@ int vist3a_cfg_combine(const void* cond, const void* uncond, int32_t in_dtype, f
                        void* stream);
 int vist3a_axpby_n(float* out, int32_t n_terms, const float* const* terms, const float* coeffs, int64_t n,
                    void* stream);
+
+
+/* ------------------------------------------------------------------------------------------
+ * Stitched latent -> 3D-Gaussian decoder kernels
+ * ------------------------------------------------------------------------------------------ */
+
+/* im2col of the stitching Conv3d with the trilinear T-upsample fused in:
+ *   latent [B, C, T, h, w] (fp32 or bf16) -> A [B*V*(h/2)*(w/2), C*45] bf16, V = 4(T-1)+1,
+ *   A[(b,v,oy,ox), c*45 + kt*9 + ky*3 + kx] = up(latent)[b, c, clamp(v+kt-2), clamp(2oy+ky-1), clamp(2ox+kx-1)]
+ *   with up() the align_corners=True linear interpolation along T.
+ * replaces: upsampling_layer (models/stitched_model.py:92-107) + the input side of
+ *   nn.Conv3d(k=(5,3,3), s=(1,2,2), p=(2,1,1), padding_mode="replicate") (models/stitching_layer_builder.py:32-42). */
+int vist3a_im2col_stitch(const void* latent, int32_t dtype, void* A, int64_t B, int64_t C, int64_t T, int64_t h,
+                         int64_t w, void* stream);
+
+/* generic NHWC im2col (fp32 -> fp32):  A[(n,oy,ox), (dy*kw+dx)*C + c] = x[n, oy*stride+dy-pad, ox*stride+dx-pad, c] (0 outside),
+ * row pitch ldA >= kh*kw*C (extra columns zeroed).  Used for the 7x7 RGB `input_merger`
+ * (AS/model/encoder/heads/vggt_dpt_gs_head.py:73-76) and the stride-2 3x3 resize conv (dpt_head.py:85-90). */
+int vist3a_im2col_nhwc(const float* x, float* A, int64_t ldA, int64_t n_img, int64_t h, int64_t w, int64_t C,
+                       int32_t kh, int32_t kw, int32_t stride, int32_t pad, void* stream);
+
+/* per-head LayerNorm(head_dim = 64) of q and k + 2-D rotary embedding, in place on a fused bf16 [rows, 3*heads*64] qkv buffer.
+ *   token p = row % tokens_per_view; p < n_special: position (0,0); else (1 + (p-n_special)/grid_w, 1 + (p-n_special)%grid_w)
+ *   rope: each 32-wide half (y then x) rotates pairs (j, j+16) by pos * base^(-j/16); cos/sin tables [max_pos, 16] fp32.
+ * replaces: q_norm/k_norm (AS/.../layers/attention.py:42-43,57) + RotaryPositionEmbedding2D (layers/rope.py:133-188). */
+int vist3a_qknorm_rope2d(void* qkv, int64_t ld, int64_t rows, int64_t heads, const float* qw, const float* qb,
+                         const float* kw, const float* kb, float eps, const float* cos_tab, const float* sin_tab,
+                         int64_t max_pos, int64_t tokens_per_view, int64_t n_special, int64_t grid_w, void* stream);
+
+/* bilinear resize, align_corners=True, NHWC fp32, with optional fused adds:
+ *   out[n,y,x,c] = lerp(in)[n,y,x,c] + (add ? add[n,y,x,c] : 0) + (pos_x ? (c < C/2 ? pos_x[x, c] : pos_y[y, c - C/2]) : 0)
+ * replaces: custom_interpolate (dpt_head.py:477-502), "out + direct_img_feat" (vggt_dpt_gs_head.py:168-169) and
+ *   _apply_pos_embed on the full-resolution map (dpt_head.py:267-277). */
+int vist3a_bilinear_nhwc(const float* in, float* out, int64_t n_img, int64_t h_in, int64_t w_in, int64_t h_out,
+                         int64_t w_out, int64_t C, const float* add, const float* pos_x, const float* pos_y,
+                         void* stream);
+
+/* depth-to-space after a k=s ConvTranspose2d expressed as a GEMM:  in [n*h*w, k*k*C] (col = (dy*k+dx)*C + c)
+ * -> out NHWC [n, h*k, w*k, C].   replaces: nn.ConvTranspose2d(k=4,s=4 / k=2,s=2) output scatter (dpt_head.py:85-90). */
+int vist3a_depth_to_space(const float* in, float* out, int64_t n_img, int64_t h, int64_t w, int64_t C, int32_t k,
+                          void* stream);
+
+/* fp32 attention for short sequences (L <= 32):  qkv [B, L, 3, H, D] -> out [B, L, H*D].
+ * replaces: F.scaled_dot_product_attention inside the camera-head trunk (AS/.../heads/camera_head.py:58-69; 13 tokens). */
+int vist3a_attention_small(const float* qkv, float* out, int64_t B, int64_t L, int64_t H, int64_t D, float scale,
+                           void* stream);
+
+/* out[r, :] = a[r, :] * b[r, :] + c[r, :]  (fp32, row strides in elements)
+ * replaces: "gate_msa * modulate(...) + pose_tokens" (camera_head.py:140-144). */
+int vist3a_fma_rows(float* out, int64_t ldo, const float* a, int64_t lda, const float* b, int64_t ldb, const float* c,
+                    int64_t ldc, int64_t rows, int64_t dim, void* stream);
+
+/* camera head output: activate pose encodings (relu on the 2 FoV entries) and build cameras.
+ *   pose_raw [S, 9] -> pose_act [S, 9]; extr [S, 3, 4] world->cam; intr [S, 3, 3] in pixels;
+ *   c2w [S, 4, 4] = inverse([R|t; 0 0 0 1]); intr_norm [S, 3, 3] (rows 0/1 divided by W/H).  Any output may be NULL.
+ * replaces: activate_pose (head_act.py:12-35), pose_encoding_to_extri_intri (utils/pose_enc.py:65-130),
+ *   pose packing (models/anysplat_stitched.py:475-494). */
+int vist3a_pose_to_cameras(const float* pose_raw, float* pose_act, float* extr, float* intr, float* c2w,
+                           float* intr_norm, int64_t S, int64_t H, int64_t W, void* stream);
+
+/* fused per-pixel epilogue of the decoder (HBM bound):
+ *   depth[p] = exp(dot(depth_feat[p, 0:cd], depth_w) + depth_b)                       (dpt_head.py output_conv2[2] + "exp")
+ *   means[p] = R^T ((u-cu) d / fx, (v-cv) d / fy, d) - R^T t                          (utils/geometry.py:10-58)
+ *   opacity = sigmoid(raw[0]); scales = min(0.001 softplus(raw[1:4]), 0.3); rot = q / (|q| + 1e-8);
+ *   harmonics = raw[8:8+3*d_sh] * sh_mask; cov = R S S^T R^T                          (gaussian_adapter.py:114-147)
+ *   scene_sum += |means[p]| (one atomicAdd per block)
+ * gs_raw [P, ld_raw] fp32 (P = S*H*W pixels, view-major), outputs contiguous fp32.
+ * replaces: models/anysplat_stitched.py:358-376,410-474. */
+int vist3a_gaussian_epilogue(const float* depth_feat, int64_t ld_df, int64_t cd, const float* depth_w, float depth_b,
+                             const float* gs_raw, int64_t ld_raw, const float* extr, const float* intr,
+                             const float* sh_mask, int64_t d_sh, int64_t S, int64_t H, int64_t W, float* depth,
+                             float* means, float* scales, float* rotations, float* opacities, float* harmonics,
+                             float* covariances, float* scene_sum, void* stream);
 
 #ifdef __cplusplus
 }

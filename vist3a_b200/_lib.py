@@ -35,7 +35,25 @@ EXPORTS = (
     "vist3a_unpatchify",
     "vist3a_cfg_combine",
     "vist3a_axpby_n",
+    "vist3a_im2col_stitch",
+    "vist3a_im2col_nhwc",
+    "vist3a_qknorm_rope2d",
+    "vist3a_bilinear_nhwc",
+    "vist3a_depth_to_space",
+    "vist3a_attention_small",
+    "vist3a_fma_rows",
+    "vist3a_pose_to_cameras",
+    "vist3a_gaussian_epilogue",
 )
+
+
+class RowMap(C.Structure):
+    _fields_ = [("rpg", C.c_int64), ("gstride", C.c_int64), ("goff", C.c_int64)]
+
+
+class Conv(C.Structure):
+    _fields_ = [("enabled", C.c_int32), ("kh", C.c_int32), ("kw", C.c_int32), ("pad", C.c_int32), ("n_img", C.c_int32),
+                ("h", C.c_int32), ("w", C.c_int32), ("c_in", C.c_int32)]
 
 
 class GemmArgs(C.Structure):
@@ -46,6 +64,7 @@ class GemmArgs(C.Structure):
         ("bias", C.c_void_p),
         ("gate", C.c_void_p),
         ("residual", C.c_void_p),
+        ("residual2", C.c_void_p),
         ("M", C.c_int64),
         ("N", C.c_int64),
         ("K", C.c_int64),
@@ -55,9 +74,13 @@ class GemmArgs(C.Structure):
         ("ldr", C.c_int64),
         ("rows_per_batch", C.c_int64),
         ("gate_bstride", C.c_int64),
+        ("cmap", RowMap),
+        ("rmap", RowMap),
+        ("conv", Conv),
         ("in_dtype", C.c_int32),
         ("out_dtype", C.c_int32),
         ("act", C.c_int32),
+        ("post_act", C.c_int32),
         ("round_linear", C.c_int32),
         ("round_gate", C.c_int32),
         ("flags", C.c_uint32),
@@ -125,15 +148,25 @@ def load(build_if_missing: bool = False) -> C.CDLL:
     lib.vist3a_gemm.argtypes = [C.POINTER(GemmArgs), C.c_void_p]
     lib.vist3a_fmha_fwd.argtypes = [C.POINTER(FmhaArgs), C.c_void_p]
     i64, i32, f32, vp, u32 = C.c_int64, C.c_int32, C.c_float, C.c_void_p, C.c_uint32
-    lib.vist3a_layernorm.argtypes = [vp, i32, i64, vp, i32, i64, i64, i64, i64, vp, i64, vp, i64, f32, vp]
+    lib.vist3a_layernorm.argtypes = [vp, i32, i64, vp, i32, i64, i64, i64, i64, vp, i64, vp, i64, f32, i32, C.POINTER(RowMap), C.POINTER(RowMap), vp]
     lib.vist3a_rmsnorm_rope.argtypes = [vp, i64, i64, i64, i64, vp, f32, vp, vp, i64, vp]
     lib.vist3a_modulation.argtypes = [vp, vp, i32, i32, vp, i64, i64, i64, u32, vp]
-    lib.vist3a_skinny_linear.argtypes = [vp, i32, i64, vp, i32, i64, vp, vp, i32, i64, i64, i64, i64, i32, i32, vp]
+    lib.vist3a_skinny_linear.argtypes = [vp, i32, i64, vp, i32, i64, vp, vp, i32, i64, i64, i64, i64, i32, i32, vp, vp, i64, vp]
     lib.vist3a_timestep_features.argtypes = [vp, vp, i32, i64, i64, vp]
     lib.vist3a_patchify.argtypes = [vp, i32, vp, i64, i64, i64, i64, i64, vp]
     lib.vist3a_unpatchify.argtypes = [vp, i32, i64, vp, i32, i64, i64, i64, i64, i64, vp]
     lib.vist3a_cfg_combine.argtypes = [vp, vp, i32, f32, vp, i64, vp]
     lib.vist3a_axpby_n.argtypes = [vp, i32, C.POINTER(vp), C.POINTER(f32), i64, vp]
+    lib.vist3a_im2col_stitch.argtypes = [vp, i32, vp, i64, i64, i64, i64, i64, vp]
+    lib.vist3a_im2col_nhwc.argtypes = [vp, vp, i64, i64, i64, i64, i64, i32, i32, i32, i32, vp]
+    lib.vist3a_qknorm_rope2d.argtypes = [vp, i64, i64, i64, vp, vp, vp, vp, f32, vp, vp, i64, i64, i64, i64, vp]
+    lib.vist3a_bilinear_nhwc.argtypes = [vp, vp, i64, i64, i64, i64, i64, i64, vp, vp, vp, vp]
+    lib.vist3a_depth_to_space.argtypes = [vp, vp, i64, i64, i64, i64, i32, vp]
+    lib.vist3a_attention_small.argtypes = [vp, vp, i64, i64, i64, i64, f32, vp]
+    lib.vist3a_fma_rows.argtypes = [vp, i64, vp, i64, vp, i64, vp, i64, i64, i64, vp]
+    lib.vist3a_pose_to_cameras.argtypes = [vp, vp, vp, vp, vp, vp, i64, i64, i64, vp]
+    lib.vist3a_gaussian_epilogue.argtypes = [vp, i64, i64, vp, f32, vp, i64, vp, vp, vp, i64, i64, i64, i64, vp, vp, vp, vp, vp, vp,
+                                             vp, vp, vp]
     _lib = lib
     return lib
 

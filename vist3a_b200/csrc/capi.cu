@@ -10,13 +10,27 @@ namespace v3a {
 int gemm_entry(const vist3a_gemm_args*, cudaStream_t);
 int fmha_entry(const vist3a_fmha_args*, cudaStream_t);
 int layernorm_entry(const void*, int, long long, void*, int, long long, long long, long long, long long, const float*,
-                    long long, const float*, long long, float, cudaStream_t);
+                    long long, const float*, long long, float, int, const vist3a_rowmap*, const vist3a_rowmap*, cudaStream_t);
 int rmsnorm_rope_entry(void*, long long, long long, long long, long long, const float*, float, const float*,
                        const float*, long long, cudaStream_t);
 int modulation_entry(const float*, const void*, int, int, float*, long long, long long, long long, unsigned,
                      cudaStream_t);
 int skinny_linear_entry(const void*, int, long long, const void*, int, long long, const float*, void*, int, long long,
-                        long long, long long, long long, int, int, cudaStream_t);
+                        long long, long long, long long, int, int, const float*, const float*, long long, cudaStream_t);
+int im2col_stitch_entry(const void*, int, void*, long long, long long, long long, long long, long long, cudaStream_t);
+int im2col_nhwc_entry(const float*, float*, long long, long long, long long, long long, long long, int, int, int, int, cudaStream_t);
+int qknorm_rope2d_entry(void*, long long, long long, long long, const float*, const float*, const float*, const float*, float,
+                        const float*, const float*, long long, long long, long long, long long, cudaStream_t);
+int bilinear_nhwc_entry(const float*, float*, long long, long long, long long, long long, long long, long long, const float*,
+                        const float*, const float*, cudaStream_t);
+int depth_to_space_entry(const float*, float*, long long, long long, long long, long long, int, cudaStream_t);
+int attention_small_entry(const float*, float*, long long, long long, long long, long long, float, cudaStream_t);
+int fma_rows_entry(float*, long long, const float*, long long, const float*, long long, const float*, long long, long long,
+                   long long, cudaStream_t);
+int pose_to_cameras_entry(const float*, float*, float*, float*, float*, float*, long long, long long, long long, cudaStream_t);
+int gaussian_epilogue_entry(const float*, long long, long long, const float*, float, const float*, long long, const float*,
+                            const float*, const float*, long long, long long, long long, long long, float*, float*, float*, float*,
+                            float*, float*, float*, float*, cudaStream_t);
 int timestep_features_entry(const float*, void*, int, long long, long long, cudaStream_t);
 int patchify_entry(const void*, int, void*, long long, long long, long long, long long, long long, cudaStream_t);
 int unpatchify_entry(const void*, int, long long, void*, int, long long, long long, long long, long long, long long,
@@ -122,7 +136,7 @@ using namespace v3a;
 extern "C" {
 
 const char* vist3a_last_error(void) { return last_error_buf(); }
-int vist3a_abi_version(void) { return 1; }
+int vist3a_abi_version(void) { return 2; }
 int64_t vist3a_launch_count(void) { return (int64_t)launch_counter().load(); }
 
 int vist3a_gemm(const vist3a_gemm_args* args, void* stream) { return gemm_entry(args, ST(stream)); }
@@ -130,9 +144,10 @@ int vist3a_fmha_fwd(const vist3a_fmha_args* args, void* stream) { return fmha_en
 
 int vist3a_layernorm(const void* x, int32_t x_dtype, int64_t ldx, void* out, int32_t out_dtype, int64_t ldo,
                      int64_t rows, int64_t dim, int64_t rows_per_batch, const float* mul, int64_t mul_bstride,
-                     const float* add, int64_t add_bstride, float eps, void* stream) {
+                     const float* add, int64_t add_bstride, float eps, int32_t mul_plus_one,
+                     const vist3a_rowmap* in_map, const vist3a_rowmap* out_map, void* stream) {
   return layernorm_entry(x, x_dtype, ldx, out, out_dtype, ldo, rows, dim, rows_per_batch, mul, mul_bstride, add,
-                         add_bstride, eps, ST(stream));
+                         add_bstride, eps, mul_plus_one, in_map, out_map, ST(stream));
 }
 
 int vist3a_rmsnorm_rope(void* x, int64_t ldx, int64_t rows, int64_t dim, int64_t head_dim, const float* weight,
@@ -147,8 +162,10 @@ int vist3a_modulation(const float* table, const void* mod, int32_t mod_dtype, in
 
 int vist3a_skinny_linear(const void* x, int32_t x_dtype, int64_t ldx, const void* W, int32_t w_dtype, int64_t ldw,
                          const float* bias, void* y, int32_t y_dtype, int64_t ldy, int64_t M, int64_t N, int64_t K,
-                         int32_t pre_act, int32_t act, void* stream) {
-  return skinny_linear_entry(x, x_dtype, ldx, W, w_dtype, ldw, bias, y, y_dtype, ldy, M, N, K, pre_act, act, ST(stream));
+                         int32_t pre_act, int32_t act, const float* gate, const float* residual, int64_t ldres,
+                         void* stream) {
+  return skinny_linear_entry(x, x_dtype, ldx, W, w_dtype, ldw, bias, y, y_dtype, ldy, M, N, K, pre_act, act, gate, residual,
+                             ldres, ST(stream));
 }
 
 int vist3a_timestep_features(const float* t, void* out, int32_t out_dtype, int64_t batch, int64_t dim, void* stream) {
@@ -173,6 +190,50 @@ int vist3a_cfg_combine(const void* cond, const void* uncond, int32_t in_dtype, f
 int vist3a_axpby_n(float* out, int32_t n_terms, const float* const* terms, const float* coeffs, int64_t n,
                    void* stream) {
   return axpby_entry(out, n_terms, terms, coeffs, n, ST(stream));
+}
+
+int vist3a_im2col_stitch(const void* latent, int32_t dtype, void* A, int64_t B, int64_t C, int64_t T, int64_t h,
+                         int64_t w, void* stream) {
+  return im2col_stitch_entry(latent, dtype, A, B, C, T, h, w, ST(stream));
+}
+int vist3a_im2col_nhwc(const float* x, float* A, int64_t ldA, int64_t n_img, int64_t h, int64_t w, int64_t C,
+                       int32_t kh, int32_t kw, int32_t stride, int32_t pad, void* stream) {
+  return im2col_nhwc_entry(x, A, ldA, n_img, h, w, C, kh, kw, stride, pad, ST(stream));
+}
+int vist3a_qknorm_rope2d(void* qkv, int64_t ld, int64_t rows, int64_t heads, const float* qw, const float* qb,
+                         const float* kw, const float* kb, float eps, const float* cos_tab, const float* sin_tab,
+                         int64_t max_pos, int64_t tokens_per_view, int64_t n_special, int64_t grid_w, void* stream) {
+  return qknorm_rope2d_entry(qkv, ld, rows, heads, qw, qb, kw, kb, eps, cos_tab, sin_tab, max_pos, tokens_per_view,
+                             n_special, grid_w, ST(stream));
+}
+int vist3a_bilinear_nhwc(const float* in, float* out, int64_t n_img, int64_t h_in, int64_t w_in, int64_t h_out,
+                         int64_t w_out, int64_t C, const float* add, const float* pos_x, const float* pos_y,
+                         void* stream) {
+  return bilinear_nhwc_entry(in, out, n_img, h_in, w_in, h_out, w_out, C, add, pos_x, pos_y, ST(stream));
+}
+int vist3a_depth_to_space(const float* in, float* out, int64_t n_img, int64_t h, int64_t w, int64_t C, int32_t k,
+                          void* stream) {
+  return depth_to_space_entry(in, out, n_img, h, w, C, k, ST(stream));
+}
+int vist3a_attention_small(const float* qkv, float* out, int64_t B, int64_t L, int64_t H, int64_t D, float scale,
+                           void* stream) {
+  return attention_small_entry(qkv, out, B, L, H, D, scale, ST(stream));
+}
+int vist3a_fma_rows(float* out, int64_t ldo, const float* a, int64_t lda, const float* b, int64_t ldb, const float* c,
+                    int64_t ldc, int64_t rows, int64_t dim, void* stream) {
+  return fma_rows_entry(out, ldo, a, lda, b, ldb, c, ldc, rows, dim, ST(stream));
+}
+int vist3a_pose_to_cameras(const float* pose_raw, float* pose_act, float* extr, float* intr, float* c2w,
+                           float* intr_norm, int64_t S, int64_t H, int64_t W, void* stream) {
+  return pose_to_cameras_entry(pose_raw, pose_act, extr, intr, c2w, intr_norm, S, H, W, ST(stream));
+}
+int vist3a_gaussian_epilogue(const float* depth_feat, int64_t ld_df, int64_t cd, const float* depth_w, float depth_b,
+                             const float* gs_raw, int64_t ld_raw, const float* extr, const float* intr,
+                             const float* sh_mask, int64_t d_sh, int64_t S, int64_t H, int64_t W, float* depth,
+                             float* means, float* scales, float* rotations, float* opacities, float* harmonics,
+                             float* covariances, float* scene_sum, void* stream) {
+  return gaussian_epilogue_entry(depth_feat, ld_df, cd, depth_w, depth_b, gs_raw, ld_raw, extr, intr, sh_mask, d_sh, S, H, W,
+                                 depth, means, scales, rotations, opacities, harmonics, covariances, scene_sum, ST(stream));
 }
 
 }  // extern "C"

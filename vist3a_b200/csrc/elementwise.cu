@@ -10,6 +10,13 @@
 namespace v3a {
 
 
+struct RowMap3 {
+  long long rpg, gstride, goff;
+  __device__ __forceinline__ long long operator()(long long row) const {
+    return rpg > 0 ? (row / rpg) * gstride + goff + row % rpg : row;
+  }
+};
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -48,17 +55,19 @@ template <int NCHUNK, bool kInF32, bool kOutF32>
 __global__ void __launch_bounds__(128) layernorm_kernel(const void* __restrict__ x, long long ldx, void* __restrict__ out,
                                                         long long ldo, long long rows, int dim, long long rows_per_batch,
                                                         const float* __restrict__ mul, long long mul_bs,
-                                                        const float* __restrict__ add, long long add_bs, float eps) {
+                                                        const float* __restrict__ add, long long add_bs, float eps,
+                                                        int mul_plus_one, RowMap3 imap, RowMap3 omap) {
   const long long row = (long long)blockIdx.x * 4 + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
+  const long long xrow = imap(row), orow = omap(row);
   float v[NCHUNK][8];
   float s = 0.f;
 #pragma unroll
   for (int i = 0; i < NCHUNK; ++i) {
     const int col = (lane + 32 * i) * 8;
     if (col < dim) {
-      load8<kInF32>(x, row * ldx + col, v[i]);
+      load8<kInF32>(x, xrow * ldx + col, v[i]);
 #pragma unroll
       for (int j = 0; j < 8; ++j) s += v[i][j];
     } else {
@@ -91,7 +100,7 @@ __global__ void __launch_bounds__(128) layernorm_kernel(const void* __restrict__
         float m[8];
         load8<true>(mrow, col, m);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] *= m[j];
+        for (int j = 0; j < 8; ++j) o[j] *= mul_plus_one ? 1.0f + m[j] : m[j];
       }
       if (arow) {
         float a[8];
@@ -99,7 +108,7 @@ __global__ void __launch_bounds__(128) layernorm_kernel(const void* __restrict__
 #pragma unroll
         for (int j = 0; j < 8; ++j) o[j] += a[j];
       }
-      store8<kOutF32>(out, row * ldo + col, o);
+      store8<kOutF32>(out, orow * ldo + col, o);
     }
   }
 }
@@ -107,13 +116,13 @@ __global__ void __launch_bounds__(128) layernorm_kernel(const void* __restrict__
 template <int NCHUNK>
 static int launch_ln(const void* x, int xdt, long long ldx, void* out, int odt, long long ldo, long long rows, int dim,
                      long long rpb, const float* mul, long long mbs, const float* add, long long abs_, float eps,
-                     cudaStream_t st) {
+                     int mp1, RowMap3 im, RowMap3 om, cudaStream_t st) {
   const unsigned grid = (unsigned)((rows + 3) / 4);
   const bool fi = xdt == VIST3A_DTYPE_F32, fo = odt == VIST3A_DTYPE_F32;
-  if (fi && fo) layernorm_kernel<NCHUNK, true, true><<<grid, 128, 0, st>>>(x, ldx, out, ldo, rows, dim, rpb, mul, mbs, add, abs_, eps);
-  else if (fi) layernorm_kernel<NCHUNK, true, false><<<grid, 128, 0, st>>>(x, ldx, out, ldo, rows, dim, rpb, mul, mbs, add, abs_, eps);
-  else if (fo) layernorm_kernel<NCHUNK, false, true><<<grid, 128, 0, st>>>(x, ldx, out, ldo, rows, dim, rpb, mul, mbs, add, abs_, eps);
-  else layernorm_kernel<NCHUNK, false, false><<<grid, 128, 0, st>>>(x, ldx, out, ldo, rows, dim, rpb, mul, mbs, add, abs_, eps);
+  if (fi && fo) layernorm_kernel<NCHUNK, true, true><<<grid, 128, 0, st>>>(x, ldx, out, ldo, rows, dim, rpb, mul, mbs, add, abs_, eps, mp1, im, om);
+  else if (fi) layernorm_kernel<NCHUNK, true, false><<<grid, 128, 0, st>>>(x, ldx, out, ldo, rows, dim, rpb, mul, mbs, add, abs_, eps, mp1, im, om);
+  else if (fo) layernorm_kernel<NCHUNK, false, true><<<grid, 128, 0, st>>>(x, ldx, out, ldo, rows, dim, rpb, mul, mbs, add, abs_, eps, mp1, im, om);
+  else layernorm_kernel<NCHUNK, false, false><<<grid, 128, 0, st>>>(x, ldx, out, ldo, rows, dim, rpb, mul, mbs, add, abs_, eps, mp1, im, om);
   V3A_CUDA_OK(cudaGetLastError());
   launch_counter().fetch_add(1);
   return VIST3A_OK;
@@ -121,7 +130,10 @@ static int launch_ln(const void* x, int xdt, long long ldx, void* out, int odt, 
 
 int layernorm_entry(const void* x, int xdt, long long ldx, void* out, int odt, long long ldo, long long rows,
                     long long dim, long long rpb, const float* mul, long long mbs, const float* add, long long abs_,
-                    float eps, cudaStream_t st) {
+                    float eps, int mp1, const vist3a_rowmap* in_map, const vist3a_rowmap* out_map, cudaStream_t st) {
+  RowMap3 im = {0, 0, 0}, om = {0, 0, 0};
+  if (in_map) im = {in_map->rpg, in_map->gstride, in_map->goff};
+  if (out_map) om = {out_map->rpg, out_map->gstride, out_map->goff};
   V3A_REQUIRE(x && out, VIST3A_ERR_INVALID, "layernorm: null pointer");
   V3A_REQUIRE(rows > 0 && dim > 0 && dim % 8 == 0 && dim <= 4096, VIST3A_ERR_INVALID,
               "layernorm: dim must be a multiple of 8 and <= 4096 (got %lld)", dim);
@@ -129,10 +141,10 @@ int layernorm_entry(const void* x, int xdt, long long ldx, void* out, int odt, l
   V3A_REQUIRE(mbs % 4 == 0 && abs_ % 4 == 0, VIST3A_ERR_INVALID, "layernorm: mul/add batch strides must be multiples of 4");
   if (rpb <= 0) rpb = rows;
   const int nchunk = (int)((dim + 255) / 256);
-  if (nchunk <= 4) return launch_ln<4>(x, xdt, ldx, out, odt, ldo, rows, (int)dim, rpb, mul, mbs, add, abs_, eps, st);
-  if (nchunk <= 6) return launch_ln<6>(x, xdt, ldx, out, odt, ldo, rows, (int)dim, rpb, mul, mbs, add, abs_, eps, st);
-  if (nchunk <= 8) return launch_ln<8>(x, xdt, ldx, out, odt, ldo, rows, (int)dim, rpb, mul, mbs, add, abs_, eps, st);
-  return launch_ln<16>(x, xdt, ldx, out, odt, ldo, rows, (int)dim, rpb, mul, mbs, add, abs_, eps, st);
+  if (nchunk <= 4) return launch_ln<4>(x, xdt, ldx, out, odt, ldo, rows, (int)dim, rpb, mul, mbs, add, abs_, eps, mp1, im, om, st);
+  if (nchunk <= 6) return launch_ln<6>(x, xdt, ldx, out, odt, ldo, rows, (int)dim, rpb, mul, mbs, add, abs_, eps, mp1, im, om, st);
+  if (nchunk <= 8) return launch_ln<8>(x, xdt, ldx, out, odt, ldo, rows, (int)dim, rpb, mul, mbs, add, abs_, eps, mp1, im, om, st);
+  return launch_ln<16>(x, xdt, ldx, out, odt, ldo, rows, (int)dim, rpb, mul, mbs, add, abs_, eps, mp1, im, om, st);
 }
 
 // ----------------------------------------------------------------------------------------
@@ -256,7 +268,8 @@ __global__ void __launch_bounds__(256) skinny_linear_kernel(const void* __restri
                                                             const void* __restrict__ W, long long ldw,
                                                             const float* __restrict__ bias, void* __restrict__ y,
                                                             int y_f32, long long ldy, int M, int N, int K, int pre_act,
-                                                            int act) {
+                                                            int act, const float* __restrict__ gate,
+                                                            const float* __restrict__ residual, long long ldres) {
   const int n = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (n >= N) return;
   const int lane = threadIdx.x & 31;
@@ -286,7 +299,9 @@ __global__ void __launch_bounds__(256) skinny_linear_kernel(const void* __restri
 #pragma unroll
     for (int m = 0; m < MT; ++m) {
       if (m < M) {
-        const float v = act_apply(acc[m] + b, act);
+        float v = act_apply(acc[m] + b, act);
+        if (gate) v *= gate[n];
+        if (residual) v += residual[(long long)m * ldres + n];
         if (y_f32) reinterpret_cast<float*>(y)[(long long)m * ldy + n] = v;
         else reinterpret_cast<__nv_bfloat16*>(y)[(long long)m * ldy + n] = __float2bfloat16_rn(v);
       }
@@ -296,7 +311,7 @@ __global__ void __launch_bounds__(256) skinny_linear_kernel(const void* __restri
 
 int skinny_linear_entry(const void* x, int xdt, long long ldx, const void* W, int wdt, long long ldw, const float* bias,
                         void* y, int ydt, long long ldy, long long M, long long N, long long K, int pre_act, int act,
-                        cudaStream_t st) {
+                        const float* gate, const float* residual, long long ldres, cudaStream_t st) {
   V3A_REQUIRE(x && W && y, VIST3A_ERR_INVALID, "skinny_linear: null pointer");
   V3A_REQUIRE(M > 0 && M <= 16 && N > 0 && K > 0 && K % 8 == 0, VIST3A_ERR_INVALID,
               "skinny_linear: need 1 <= M <= 16 and K %% 8 == 0 (got M=%lld K=%lld)", M, K);
@@ -306,10 +321,10 @@ int skinny_linear_entry(const void* x, int xdt, long long ldx, const void* W, in
   const int yf = ydt == VIST3A_DTYPE_F32;
 #define V3A_SKINNY(MT)                                                                                                             \
   do {                                                                                                                             \
-    if (xf && wf) skinny_linear_kernel<MT, true, true><<<grid, 256, 0, st>>>(x, ldx, W, ldw, bias, y, yf, ldy, (int)M, (int)N, (int)K, pre_act, act);   \
-    else if (xf) skinny_linear_kernel<MT, true, false><<<grid, 256, 0, st>>>(x, ldx, W, ldw, bias, y, yf, ldy, (int)M, (int)N, (int)K, pre_act, act);   \
-    else if (wf) skinny_linear_kernel<MT, false, true><<<grid, 256, 0, st>>>(x, ldx, W, ldw, bias, y, yf, ldy, (int)M, (int)N, (int)K, pre_act, act);   \
-    else skinny_linear_kernel<MT, false, false><<<grid, 256, 0, st>>>(x, ldx, W, ldw, bias, y, yf, ldy, (int)M, (int)N, (int)K, pre_act, act);          \
+    if (xf && wf) skinny_linear_kernel<MT, true, true><<<grid, 256, 0, st>>>(x, ldx, W, ldw, bias, y, yf, ldy, (int)M, (int)N, (int)K, pre_act, act, gate, residual, ldres);   \
+    else if (xf) skinny_linear_kernel<MT, true, false><<<grid, 256, 0, st>>>(x, ldx, W, ldw, bias, y, yf, ldy, (int)M, (int)N, (int)K, pre_act, act, gate, residual, ldres);   \
+    else if (wf) skinny_linear_kernel<MT, false, true><<<grid, 256, 0, st>>>(x, ldx, W, ldw, bias, y, yf, ldy, (int)M, (int)N, (int)K, pre_act, act, gate, residual, ldres);   \
+    else skinny_linear_kernel<MT, false, false><<<grid, 256, 0, st>>>(x, ldx, W, ldw, bias, y, yf, ldy, (int)M, (int)N, (int)K, pre_act, act, gate, residual, ldres);          \
   } while (0)
   if (M <= 2) V3A_SKINNY(2);
   else if (M <= 4) V3A_SKINNY(4);

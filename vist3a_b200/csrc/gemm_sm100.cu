@@ -1,34 +1,53 @@
 // tcgen05 GEMM with fused epilogues:  C[M,N] = epilogue(A[M,K] · W[N,K]^T)
 //
 // Persistent, warp-specialised kernel (one CTA — or one CTA pair — per SM):
-//   warp 0      TMA producer   (cp.async.bulk.tensor, 128B-swizzled K-major tiles, mbarrier ring)
-//   warp 1      MMA issuer     (one elected thread, tcgen05.mma, accumulators in TMEM)
-//   warp 2      TMEM allocator
-//   warps 4..7  epilogue       (tcgen05.ld -> registers -> bias/act/gate/residual -> global)
+//   warp 0       TMA producer   (cp.async.bulk.tensor, 128B-swizzled K-major tiles, mbarrier ring)
+//   warp 1       MMA issuer     (one elected thread, tcgen05.mma, accumulators in TMEM)
+//   warp 2       TMEM allocator
+//   warps 4..11  epilogue       (tcgen05.ld -> registers -> bias/act/gate/residual -> global)
 // Two TMEM accumulator stages let the epilogue of tile i overlap the main loop of tile i+1.
 // kCta == 2 uses cta_group::2: the pair computes a 256 x BN tile, each CTA stages its own 128 rows
 // of A and half of the W tile, the leader CTA issues the MMAs for both.
+//
+// Convolution mode (implicit GEMM): the A tile of 128 rows is an 8 x 16 patch of output pixels of one
+// NHWC image; for k-block (tap dy,dx ; channel block cb) the producer issues ONE 4-D TMA load at
+// coordinates (cb*BK, x0+dx-pad, y0+dy-pad, n): the box lands in smem exactly as the 128B-swizzled
+// K-major tile the MMA wants, and taps that fall outside the image are zero-filled by the TMA unit,
+// so there is no im2col buffer and no padding branch anywhere.
 #include "common.cuh"
 #include "host_util.cuh"
 
 namespace v3a {
+
+struct RowMap {
+  long long rpg, gstride, goff;
+  __device__ __forceinline__ long long operator()(long long row) const {
+    return rpg > 0 ? (row / rpg) * gstride + goff + row % rpg : row;
+  }
+};
 
 struct GemmEpilogue {
   void* C;
   const float* bias;
   const float* gate;
   const void* residual;
+  const void* residual2;
   long long ldc, ldr;
   long long rows_per_batch, gate_bstride;
+  RowMap cmap, rmap;
   int out_fp32;
-  int act;
+  int act, post_act;
   int round_linear;
   int round_gate;
 };
 
+constexpr int kConvTW = 16, kConvTH = 8;  // pixel patch of one 128-row A tile
+
 struct GemmShape {
   int M, N, K;
   int tiles_m, tiles_n;  // tiles_m counts 128*kCta-row tiles
+  // conv mode
+  int conv, kh, kw, pad, n_img, h, w, c_in, h_out, w_out, tiles_x, tiles_y, cblocks;
 };
 
 template <int BN, int kCta, bool kTF32>
@@ -66,6 +85,32 @@ __device__ __forceinline__ void apply_act32(float (&v)[32], int act) {
     case VIST3A_ACT_SILU: act32<VIST3A_ACT_SILU>(v); break;
     case VIST3A_ACT_RELU: act32<VIST3A_ACT_RELU>(v); break;
     default: break;
+  }
+}
+
+template <bool kF32>
+__device__ __forceinline__ void add_row32(float (&v)[32], const void* base, long long off, int ncols) {
+  if constexpr (kF32) {
+    const float* p = reinterpret_cast<const float*>(base) + off;
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      if (j < ncols) {
+        const float4 x = *reinterpret_cast<const float4*>(p + j);
+        v[j] += x.x; v[j + 1] += x.y; v[j + 2] += x.z; v[j + 3] += x.w;
+      }
+    }
+  } else {
+    const __nv_bfloat16* p = reinterpret_cast<const __nv_bfloat16*>(base) + off;
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {
+      if (j < ncols) {
+        const uint4 x = *reinterpret_cast<const uint4*>(p + j);
+        v[j] += bf16_lo(x.x); v[j + 1] += bf16_hi(x.x);
+        v[j + 2] += bf16_lo(x.y); v[j + 3] += bf16_hi(x.y);
+        v[j + 4] += bf16_lo(x.z); v[j + 5] += bf16_hi(x.z);
+        v[j + 6] += bf16_lo(x.w); v[j + 7] += bf16_hi(x.w);
+      }
+    }
   }
 }
 
@@ -116,7 +161,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
-  const int num_kb = (shape.K + Cfg::BK - 1) / Cfg::BK;
+  const int num_kb = shape.conv ? shape.kh * shape.kw * shape.cblocks : (shape.K + Cfg::BK - 1) / Cfg::BK;
   const int num_tiles = shape.tiles_m * shape.tiles_n;
   const int worker = blockIdx.x / kCta;
   const int num_workers = gridDim.x / kCta;
@@ -128,20 +173,36 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       uint32_t ph = 0;
       for (int tile = worker; tile < num_tiles; tile += num_workers) {
         const int tm = tile % shape.tiles_m, tn = tile / shape.tiles_m;
-        const int m0 = (tm * kCta + (int)rank) * Cfg::BM;
+        const int mt = tm * kCta + (int)rank;  // this CTA's 128-row tile
+        const int m0 = mt * Cfg::BM;
         const int n0 = tn * BN + (int)rank * Cfg::BN_LOCAL;
+        int img = 0, y0 = 0, x0 = 0;
+        if (shape.conv) {
+          const int per_img = shape.tiles_x * shape.tiles_y;
+          img = mt / per_img;
+          const int t2 = mt % per_img;
+          y0 = (t2 / shape.tiles_x) * kConvTH - shape.pad;
+          x0 = (t2 % shape.tiles_x) * kConvTW - shape.pad;
+        }
+        int cb = 0, dy = 0, dx = 0;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(empty_bar(s), ph ^ 1u);
           if constexpr (kCta == 1) {
             mbar_expect_tx(full_bar(s), Cfg::STAGE_BYTES);
-            tma_load_2d(smem_a(s), &tmA, full_bar(s), kb * Cfg::BK, m0);
+            if (shape.conv) tma_load_4d(smem_a(s), &tmA, full_bar(s), cb * Cfg::BK, x0 + dx, y0 + dy, img);
+            else tma_load_2d(smem_a(s), &tmA, full_bar(s), kb * Cfg::BK, m0);
             tma_load_2d(smem_b(s), &tmB, full_bar(s), kb * Cfg::BK, n0);
           } else {
             if (leader) mbar_expect_tx(full_bar(s), 2 * Cfg::STAGE_BYTES);
-            tma_load_2d_2sm(smem_a(s), &tmA, full_bar(s), kb * Cfg::BK, m0);
+            if (shape.conv) tma_load_4d_2sm(smem_a(s), &tmA, full_bar(s), cb * Cfg::BK, x0 + dx, y0 + dy, img);
+            else tma_load_2d_2sm(smem_a(s), &tmA, full_bar(s), kb * Cfg::BK, m0);
             tma_load_2d_2sm(smem_b(s), &tmB, full_bar(s), kb * Cfg::BK, n0);
           }
           if (++s == STAGES) { s = 0; ph ^= 1u; }
+          if (shape.conv && ++cb == shape.cblocks) {
+            cb = 0;
+            if (++dx == shape.kw) { dx = 0; ++dy; }
+          }
         }
       }
     }
@@ -185,11 +246,26 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     uint32_t aph = 0;
     for (int tile = worker; tile < num_tiles; tile += num_workers) {
       const int tm = tile % shape.tiles_m, tn = tile / shape.tiles_m;
-      const int row = (tm * kCta + (int)rank) * Cfg::BM + (int)(q * 32u + lane);
+      const int mt = tm * kCta + (int)rank;
+      const int r_in_tile = (int)(q * 32u + lane);
+      long long row;
+      bool row_ok;
+      if (shape.conv) {
+        const int per_img = shape.tiles_x * shape.tiles_y;
+        const int img = mt / per_img, t2 = mt % per_img;
+        const int y = (t2 / shape.tiles_x) * kConvTH + (r_in_tile >> 4);
+        const int x = (t2 % shape.tiles_x) * kConvTW + (r_in_tile & 15);
+        row_ok = img < shape.n_img && y < shape.h_out && x < shape.w_out;
+        row = ((long long)img * shape.h_out + y) * shape.w_out + x;
+      } else {
+        row = (long long)mt * Cfg::BM + r_in_tile;
+        row_ok = row < shape.M;
+      }
       const int n_tile = tn * BN;
-      const bool row_ok = row < shape.M;
-      const long long b = row_ok ? (long long)row / ep.rows_per_batch : 0;
+      const long long b = row_ok ? row / ep.rows_per_batch : 0;
       const float* gate_row = ep.gate ? ep.gate + b * ep.gate_bstride : nullptr;
+      const long long crow = row_ok ? ep.cmap(row) : 0;
+      const long long rrow = (row_ok && ep.residual) ? ep.rmap(row) : 0;
       mbar_wait(tfull_bar(as), aph);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((q * 32u) << 16) + (uint32_t)(as * BN);
@@ -235,37 +311,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
           }
           if (ep.out_fp32) {
-            float* crow = reinterpret_cast<float*>(ep.C) + (long long)row * ep.ldc + n0;
-            if (ep.residual) {
-              const float* rrow = reinterpret_cast<const float*>(ep.residual) + (long long)row * ep.ldr + n0;
-#pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                if (j < ncols) {
-                  const float4 x = *reinterpret_cast<const float4*>(rrow + j);
-                  v[j] += x.x; v[j + 1] += x.y; v[j + 2] += x.z; v[j + 3] += x.w;
-                }
-              }
-            }
+            if (ep.residual) add_row32<true>(v, ep.residual, rrow * ep.ldr + n0, ncols);
+            if (ep.residual2) add_row32<true>(v, ep.residual2, crow * ep.ldc + n0, ncols);
+            if (ep.post_act == VIST3A_ACT_RELU) act32<VIST3A_ACT_RELU>(v);
+            float* cp = reinterpret_cast<float*>(ep.C) + crow * ep.ldc + n0;
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
-              if (j < ncols) *reinterpret_cast<float4*>(crow + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+              if (j < ncols) *reinterpret_cast<float4*>(cp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
             }
           } else {
-            __nv_bfloat16* crow = reinterpret_cast<__nv_bfloat16*>(ep.C) + (long long)row * ep.ldc + n0;
-            if (ep.residual) {
-              const __nv_bfloat16* rrow =
-                  reinterpret_cast<const __nv_bfloat16*>(ep.residual) + (long long)row * ep.ldr + n0;
-#pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                if (j < ncols) {
-                  const uint4 x = *reinterpret_cast<const uint4*>(rrow + j);
-                  v[j] += bf16_lo(x.x); v[j + 1] += bf16_hi(x.x);
-                  v[j + 2] += bf16_lo(x.y); v[j + 3] += bf16_hi(x.y);
-                  v[j + 4] += bf16_lo(x.z); v[j + 5] += bf16_hi(x.z);
-                  v[j + 6] += bf16_lo(x.w); v[j + 7] += bf16_hi(x.w);
-                }
-              }
-            }
+            if (ep.residual) add_row32<false>(v, ep.residual, rrow * ep.ldr + n0, ncols);
+            if (ep.residual2) add_row32<false>(v, ep.residual2, crow * ep.ldc + n0, ncols);
+            if (ep.post_act == VIST3A_ACT_RELU) act32<VIST3A_ACT_RELU>(v);
+            __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(ep.C) + crow * ep.ldc + n0;
 #pragma unroll
             for (int j = 0; j < 32; j += 8) {
               if (j < ncols) {
@@ -274,7 +332,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 o.y = pack_bf16(v[j + 2], v[j + 3]);
                 o.z = pack_bf16(v[j + 4], v[j + 5]);
                 o.w = pack_bf16(v[j + 6], v[j + 7]);
-                *reinterpret_cast<uint4*>(crow + j) = o;
+                *reinterpret_cast<uint4*>(cp + j) = o;
               }
             }
           }
@@ -308,7 +366,26 @@ template <int BN, int kCta, bool kTF32>
 static int launch_gemm(const vist3a_gemm_args& a, cudaStream_t stream) {
   using Cfg = GemmCfg<BN, kCta, kTF32>;
   CUtensorMap tmA, tmB;
-  {
+  GemmShape shape = {};
+  shape.M = (int)a.M; shape.N = (int)a.N; shape.K = (int)a.K;
+  if (a.conv.enabled) {
+    const vist3a_conv& c = a.conv;
+    shape.conv = 1; shape.kh = c.kh; shape.kw = c.kw; shape.pad = c.pad;
+    shape.n_img = c.n_img; shape.h = c.h; shape.w = c.w; shape.c_in = c.c_in;
+    shape.h_out = c.h + 2 * c.pad - c.kh + 1;
+    shape.w_out = c.w + 2 * c.pad - c.kw + 1;
+    shape.tiles_x = (shape.w_out + kConvTW - 1) / kConvTW;
+    shape.tiles_y = (shape.h_out + kConvTH - 1) / kConvTH;
+    shape.cblocks = c.c_in / Cfg::BK;
+    const long long mtiles = (long long)c.n_img * shape.tiles_x * shape.tiles_y;
+    shape.tiles_m = (int)((mtiles + kCta - 1) / kCta);
+    uint64_t dims[4] = {(uint64_t)c.c_in, (uint64_t)c.w, (uint64_t)c.h, (uint64_t)c.n_img};
+    uint64_t strides[3] = {(uint64_t)c.c_in * Cfg::ES, (uint64_t)c.w * c.c_in * Cfg::ES, (uint64_t)c.h * c.w * c.c_in * Cfg::ES};
+    uint32_t box[4] = {(uint32_t)Cfg::BK, (uint32_t)kConvTW, (uint32_t)kConvTH, 1};
+    int rc = encode_tensor_map(&tmA, a.A, Cfg::ES, kTF32, 4, dims, strides, box, true);
+    if (rc) return rc;
+  } else {
+    shape.tiles_m = (int)((a.M + Cfg::BM * kCta - 1) / (Cfg::BM * kCta));
     uint64_t dims[2] = {(uint64_t)a.K, (uint64_t)a.M};
     uint64_t strides[1] = {(uint64_t)a.lda * Cfg::ES};
     uint32_t box[2] = {(uint32_t)Cfg::BK, (uint32_t)Cfg::BM};
@@ -322,17 +399,16 @@ static int launch_gemm(const vist3a_gemm_args& a, cudaStream_t stream) {
     int rc = encode_tensor_map(&tmB, a.W, Cfg::ES, kTF32, 2, dims, strides, box, true);
     if (rc) return rc;
   }
-  GemmShape shape;
-  shape.M = (int)a.M; shape.N = (int)a.N; shape.K = (int)a.K;
-  shape.tiles_m = (int)((a.M + Cfg::BM * kCta - 1) / (Cfg::BM * kCta));
   shape.tiles_n = (int)((a.N + BN - 1) / BN);
   GemmEpilogue ep;
-  ep.C = a.C; ep.bias = a.bias; ep.gate = a.gate; ep.residual = a.residual;
+  ep.C = a.C; ep.bias = a.bias; ep.gate = a.gate; ep.residual = a.residual; ep.residual2 = a.residual2;
   ep.ldc = a.ldc; ep.ldr = a.ldr;
   ep.rows_per_batch = a.rows_per_batch > 0 ? a.rows_per_batch : a.M;
   ep.gate_bstride = a.gate_bstride;
+  ep.cmap = {a.cmap.rpg, a.cmap.gstride, a.cmap.goff};
+  ep.rmap = {a.rmap.rpg, a.rmap.gstride, a.rmap.goff};
   ep.out_fp32 = a.out_dtype == VIST3A_DTYPE_F32;
-  ep.act = a.act; ep.round_linear = a.round_linear; ep.round_gate = a.round_gate;
+  ep.act = a.act; ep.post_act = a.post_act; ep.round_linear = a.round_linear; ep.round_gate = a.round_gate;
 
   auto kern = gemm_tcgen05_kernel<BN, kCta, kTF32>;
   static bool attr_set = false;  // per template instantiation
@@ -376,8 +452,21 @@ int gemm_entry(const vist3a_gemm_args* args, cudaStream_t stream) {
               "gemm: out_dtype");
   const int es = a.in_dtype == VIST3A_DTYPE_F32 ? 4 : 2;
   const int kalign = 16 / es;
-  V3A_REQUIRE(a.lda >= a.K && a.ldw >= a.K && a.lda % kalign == 0 && a.ldw % kalign == 0, VIST3A_ERR_INVALID,
-              "gemm: lda/ldw must be >= K and multiples of %d elements (16-byte TMA stride)", kalign);
+  V3A_REQUIRE(a.ldw >= a.K && a.ldw % kalign == 0, VIST3A_ERR_INVALID,
+              "gemm: ldw must be >= K and a multiple of %d elements (16-byte TMA stride)", kalign);
+  if (a.conv.enabled) {
+    const vist3a_conv& c = a.conv;
+    const int bk = 128 / es;
+    V3A_REQUIRE(c.kh > 0 && c.kw > 0 && c.pad >= 0 && c.n_img > 0 && c.h > 0 && c.w > 0 && c.c_in > 0, VIST3A_ERR_INVALID,
+                "gemm(conv): bad geometry");
+    V3A_REQUIRE(c.c_in % bk == 0, VIST3A_ERR_UNSUPPORTED, "gemm(conv): c_in (%d) must be a multiple of %d", c.c_in, bk);
+    V3A_REQUIRE(a.K == (int64_t)c.kh * c.kw * c.c_in, VIST3A_ERR_INVALID, "gemm(conv): K must equal kh*kw*c_in");
+    const long long ho = c.h + 2 * c.pad - c.kh + 1, wo = c.w + 2 * c.pad - c.kw + 1;
+    V3A_REQUIRE(ho > 0 && wo > 0 && a.M == (int64_t)c.n_img * ho * wo, VIST3A_ERR_INVALID, "gemm(conv): M must equal n_img*h_out*w_out");
+  } else {
+    V3A_REQUIRE(a.lda >= a.K && a.lda % kalign == 0, VIST3A_ERR_INVALID,
+                "gemm: lda must be >= K and a multiple of %d elements (16-byte TMA stride)", kalign);
+  }
   V3A_REQUIRE(((uintptr_t)a.A & 15) == 0 && ((uintptr_t)a.W & 15) == 0 && ((uintptr_t)a.C & 15) == 0,
               VIST3A_ERR_INVALID, "gemm: A/W/C must be 16-byte aligned");
   const int nalign = a.out_dtype == VIST3A_DTYPE_F32 ? 4 : 8;
@@ -386,8 +475,11 @@ int gemm_entry(const vist3a_gemm_args* args, cudaStream_t stream) {
   if (a.residual)
     V3A_REQUIRE(a.ldr % nalign == 0 && a.ldr >= a.N && ((uintptr_t)a.residual & 15) == 0, VIST3A_ERR_INVALID,
                 "gemm: residual stride/alignment");
+  if (a.residual2) V3A_REQUIRE(((uintptr_t)a.residual2 & 15) == 0, VIST3A_ERR_INVALID, "gemm: residual2 alignment");
   if (a.bias) V3A_REQUIRE(((uintptr_t)a.bias & 15) == 0, VIST3A_ERR_INVALID, "gemm: bias alignment");
   if (a.gate) V3A_REQUIRE(((uintptr_t)a.gate & 15) == 0 && a.gate_bstride % 4 == 0, VIST3A_ERR_INVALID, "gemm: gate alignment");
+  V3A_REQUIRE(a.cmap.rpg >= 0 && a.rmap.rpg >= 0, VIST3A_ERR_INVALID, "gemm: row maps");
+  V3A_REQUIRE(a.post_act == VIST3A_ACT_NONE || a.post_act == VIST3A_ACT_RELU, VIST3A_ERR_UNSUPPORTED, "gemm: post_act must be none or relu");
   V3A_REQUIRE(a.M < (1ll << 31) && a.N < (1ll << 31) && a.K < (1ll << 31), VIST3A_ERR_INVALID, "gemm: dims exceed int32");
   int rc = check_arch();
   if (rc) return rc;

@@ -50,21 +50,35 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
          out: Optional[torch.Tensor] = None, out_dtype: Optional[torch.dtype] = None,
          gate: Optional[torch.Tensor] = None, gate_bstride: int = 0, rows_per_batch: int = 0,
          residual: Optional[torch.Tensor] = None, round_linear: bool = False, round_gate: bool = False,
-         two_cta: Optional[bool] = None) -> torch.Tensor:
-    """out[M,N] = epilogue(a[M,K] @ w[N,K]^T); see vist3a_gemm in include/vist3a_sm100.h."""
-    _need_cuda(a, w, bias, gate, residual, out)
-    a2 = _rows2d(a)
+         two_cta: Optional[bool] = None, residual2: Optional[torch.Tensor] = None, post_act=None,
+         cmap: Optional[tuple] = None, rmap: Optional[tuple] = None, conv: Optional[dict] = None) -> torch.Tensor:
+    """out[M,N] = epilogue(a[M,K] @ w[N,K]^T); see vist3a_gemm in include/vist3a_sm100.h.
+    cmap / rmap = (rows_per_group, group_stride, group_offset) row maps of out(+residual2) / residual;
+    conv = dict(kh, kw, pad) with `a` an NHWC [n, h, w, c] tensor: implicit-GEMM convolution (stride 1)."""
+    _need_cuda(a, w, bias, gate, residual, residual2, out)
     w2 = _rows2d(w)
+    N, K2 = w2.shape
+    if conv is not None:
+        if a.dim() != 4 or not a.is_contiguous():
+            raise ValueError("gemm(conv): a must be a contiguous NHWC [n, h, w, c] tensor")
+        n_img, h_in, w_in, c_in = a.shape
+        kh, kw, pad = conv["kh"], conv["kw"], conv["pad"]
+        h_out, w_out = h_in + 2 * pad - kh + 1, w_in + 2 * pad - kw + 1
+        M, K = n_img * h_out * w_out, kh * kw * c_in
+        a2 = a
+    else:
+        a2 = _rows2d(a)
+        M, K = a2.shape
     if a2.dtype != w2.dtype:
         raise TypeError(f"gemm: A is {a2.dtype} but W is {w2.dtype}")
-    M, K = a2.shape
-    N, K2 = w2.shape
     if K != K2:
         raise ValueError(f"gemm: K mismatch {K} vs {K2}")
     if out is None:
+        if cmap is not None:
+            raise ValueError("gemm: a row-mapped output must be pre-allocated")
         out = torch.empty((M, N), dtype=out_dtype or a2.dtype, device=a.device)
     o2 = out if out.dim() == 2 else out.view(-1, out.shape[-1])
-    if o2.stride(-1) != 1 or o2.shape[0] != M or o2.shape[1] != N:
+    if o2.stride(-1) != 1 or o2.shape[1] != N or (cmap is None and o2.shape[0] != M):
         raise ValueError("gemm: out must be [M, N] with unit inner stride")
     for v, n in ((bias, "bias"), (gate, "gate")):
         if v is not None and v.dtype != torch.float32:
@@ -74,11 +88,26 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
         r2 = residual if residual.dim() == 2 else residual.view(-1, residual.shape[-1])
         if r2.dtype != o2.dtype or r2.stride(-1) != 1:
             raise TypeError("gemm: residual must have the output dtype and unit inner stride")
+        if r2.dim() == 1:
+            r2 = r2.view(1, -1)
     args = L.GemmArgs()
     args.A, args.W, args.C = a2.data_ptr(), w2.data_ptr(), o2.data_ptr()
     args.bias, args.gate, args.residual = _ptr(bias), _ptr(gate), _ptr(r2)
+    if residual2 is not None:
+        q2 = residual2 if residual2.dim() == 2 else residual2.view(-1, residual2.shape[-1])
+        if q2.dtype != o2.dtype or q2.stride(-1) != 1 or q2.stride(0) != o2.stride(0):
+            raise TypeError("gemm: residual2 must share the output's dtype and row stride")
+        args.residual2 = q2.data_ptr()
     args.M, args.N, args.K = M, N, K
-    args.lda, args.ldw, args.ldc = a2.stride(0), w2.stride(0), o2.stride(0)
+    args.lda, args.ldw, args.ldc = (0 if conv is not None else a2.stride(0)), w2.stride(0), o2.stride(0)
+    if cmap is not None:
+        args.cmap.rpg, args.cmap.gstride, args.cmap.goff = cmap
+    if rmap is not None:
+        args.rmap.rpg, args.rmap.gstride, args.rmap.goff = rmap
+    if conv is not None:
+        args.conv.enabled, args.conv.kh, args.conv.kw, args.conv.pad = 1, kh, kw, pad
+        args.conv.n_img, args.conv.h, args.conv.w, args.conv.c_in = n_img, h_in, w_in, c_in
+    args.post_act = ACT[post_act]
     args.ldr = r2.stride(0) if r2 is not None else 0
     args.rows_per_batch = rows_per_batch if rows_per_batch > 0 else M
     args.gate_bstride = gate_bstride
@@ -121,11 +150,15 @@ def fmha(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, scale: Optional[f
 
 def layernorm(x: torch.Tensor, *, mul: Optional[torch.Tensor] = None, add: Optional[torch.Tensor] = None,
               mul_bstride: int = 0, add_bstride: int = 0, rows_per_batch: int = 0, eps: float = 1e-6,
-              out: Optional[torch.Tensor] = None, out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
-    """out[r] = LN(x[r]) * mul[b] + add[b], b = r // rows_per_batch (fp32 statistics)."""
+              out: Optional[torch.Tensor] = None, out_dtype: Optional[torch.dtype] = None, mul_plus_one: bool = False,
+              in_map: Optional[tuple] = None, out_map: Optional[tuple] = None, rows: Optional[int] = None) -> torch.Tensor:
+    """out[r] = LN(x[r]) * mul[b] + add[b], b = r // rows_per_batch (fp32 statistics).
+    in_map / out_map = (rows_per_group, group_stride, group_offset) select memory rows of x / out; `rows` = rows to process."""
     _need_cuda(x, mul, add, out)
     x2 = _rows2d(x)
-    rows, dim = x2.shape
+    dim = x2.shape[1]
+    if rows is None:
+        rows = x2.shape[0]
     if out is None:
         out = torch.empty((rows, dim), dtype=out_dtype or x2.dtype, device=x.device)
     o2 = out if out.dim() == 2 else out.view(-1, out.shape[-1])
@@ -134,7 +167,9 @@ def layernorm(x: torch.Tensor, *, mul: Optional[torch.Tensor] = None, add: Optio
             raise TypeError("layernorm: mul/add must be float32")
     L.check(L.load().vist3a_layernorm(x2.data_ptr(), _dt(x2), x2.stride(0), o2.data_ptr(), _dt(o2), o2.stride(0), rows,
                                       dim, rows_per_batch if rows_per_batch > 0 else rows, _ptr(mul), mul_bstride,
-                                      _ptr(add), add_bstride, eps, _stream()))
+                                      _ptr(add), add_bstride, eps, int(mul_plus_one),
+                                      C.byref(L.RowMap(*in_map)) if in_map else None,
+                                      C.byref(L.RowMap(*out_map)) if out_map else None, _stream()))
     return out
 
 
@@ -165,9 +200,10 @@ def modulation(table: torch.Tensor, mod: torch.Tensor, *, nvec: int, broadcast: 
 
 
 def skinny_linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, *, pre_act=None, act=None,
-                  out_dtype: Optional[torch.dtype] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """y = act(pre_act(x) @ w^T + bias) for M <= 16 rows (weight-streaming, HBM bound)."""
-    _need_cuda(x, w, bias, out)
+                  out_dtype: Optional[torch.dtype] = None, out: Optional[torch.Tensor] = None,
+                  gate: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """y = residual + gate * act(pre_act(x) @ w^T + bias) for M <= 16 rows (weight-streaming, HBM bound)."""
+    _need_cuda(x, w, bias, out, gate, residual)
     x2 = _rows2d(x)
     M, K = x2.shape
     N = w.shape[0]
@@ -177,7 +213,8 @@ def skinny_linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor]
         raise TypeError("skinny_linear: bias must be float32")
     L.check(L.load().vist3a_skinny_linear(x2.data_ptr(), _dt(x2), x2.stride(0), w.data_ptr(), _dt(w), w.stride(0),
                                           _ptr(bias), out.data_ptr(), _dt(out), out.stride(0), M, N, K, ACT[pre_act],
-                                          ACT[act], _stream()))
+                                          ACT[act], _ptr(gate), _ptr(residual), residual.stride(0) if residual is not None else 0,
+                                          _stream()))
     return out
 
 
@@ -230,6 +267,122 @@ def axpby_n(out: torch.Tensor, terms, coeffs) -> torch.Tensor:
     return out
 
 
+
+# ------------------------------------------------------------------------------------------------
+# stitched-decoder kernels
+# ------------------------------------------------------------------------------------------------
+def im2col_stitch(latent: torch.Tensor) -> torch.Tensor:
+    """latent [B, C, T, h, w] -> bf16 [B*V*(h/2)*(w/2), C*45] (T-upsample + replicate pad fused), V = 4(T-1)+1."""
+    _need_cuda(latent)
+    latent = latent.contiguous()
+    B, Cc, T, h, w = latent.shape
+    V = (T - 1) * 4 + 1
+    A = torch.empty((B * V * (h // 2) * (w // 2), Cc * 45), dtype=torch.bfloat16, device=latent.device)
+    L.check(L.load().vist3a_im2col_stitch(latent.data_ptr(), _dt(latent), A.data_ptr(), B, Cc, T, h, w, _stream()))
+    return A
+
+
+def im2col_nhwc(x: torch.Tensor, kh: int, kw: int, stride: int, pad: int, k_pad: Optional[int] = None) -> torch.Tensor:
+    """x NHWC fp32 -> [n*ho*wo, k_pad] fp32 with column (dy*kw+dx)*C + c (zero beyond kh*kw*C)."""
+    _need_cuda(x)
+    if x.dtype != torch.float32 or not x.is_contiguous():
+        raise TypeError("im2col_nhwc: x must be contiguous float32 NHWC")
+    n, h, w, Cc = x.shape
+    ho, wo = (h + 2 * pad - kh) // stride + 1, (w + 2 * pad - kw) // stride + 1
+    ld = k_pad or kh * kw * Cc
+    A = torch.empty((n * ho * wo, ld), dtype=torch.float32, device=x.device)
+    L.check(L.load().vist3a_im2col_nhwc(x.data_ptr(), A.data_ptr(), ld, n, h, w, Cc, kh, kw, stride, pad, _stream()))
+    return A
+
+
+def qknorm_rope2d_(qkv: torch.Tensor, heads: int, qw, qb, kw, kb, cos_tab, sin_tab, *, tokens_per_view: int, n_special: int,
+                   grid_w: int, eps: float = 1e-5) -> torch.Tensor:
+    """in place on bf16 [rows, 3*heads*64]: LayerNorm(64) on every q / k head + 2-D RoPE."""
+    _need_cuda(qkv, qw, qb, kw, kb, cos_tab, sin_tab)
+    if qkv.dim() != 2 or qkv.dtype != torch.bfloat16 or qkv.stride(1) != 1:
+        raise TypeError("qknorm_rope2d_: qkv must be 2-D bfloat16 with unit inner stride")
+    L.check(L.load().vist3a_qknorm_rope2d(qkv.data_ptr(), qkv.stride(0), qkv.shape[0], heads, qw.data_ptr(), qb.data_ptr(),
+                                          kw.data_ptr(), kb.data_ptr(), eps, cos_tab.data_ptr(), sin_tab.data_ptr(),
+                                          cos_tab.shape[0], tokens_per_view, n_special, grid_w, _stream()))
+    return qkv
+
+
+def bilinear_nhwc(x: torch.Tensor, h_out: int, w_out: int, *, add: Optional[torch.Tensor] = None,
+                  pos_x: Optional[torch.Tensor] = None, pos_y: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """align_corners=True bilinear resize of NHWC fp32 (+ optional same-shape `add` and separable pos-embed tables)."""
+    _need_cuda(x, add, pos_x, pos_y)
+    if x.dtype != torch.float32 or not x.is_contiguous():
+        raise TypeError("bilinear_nhwc: x must be contiguous float32 NHWC")
+    n, h, w, Cc = x.shape
+    out = torch.empty((n, h_out, w_out, Cc), dtype=torch.float32, device=x.device)
+    L.check(L.load().vist3a_bilinear_nhwc(x.data_ptr(), out.data_ptr(), n, h, w, h_out, w_out, Cc, _ptr(add), _ptr(pos_x),
+                                          _ptr(pos_y), _stream()))
+    return out
+
+
+def depth_to_space(x: torch.Tensor, n: int, h: int, w: int, Cc: int, k: int) -> torch.Tensor:
+    """[n*h*w, k*k*C] (col (dy*k+dx)*C + c) -> NHWC [n, h*k, w*k, C]."""
+    _need_cuda(x)
+    out = torch.empty((n, h * k, w * k, Cc), dtype=torch.float32, device=x.device)
+    L.check(L.load().vist3a_depth_to_space(x.data_ptr(), out.data_ptr(), n, h, w, Cc, k, _stream()))
+    return out
+
+
+def attention_small(qkv: torch.Tensor, B: int, Lq: int, H: int, D: int) -> torch.Tensor:
+    """fp32 attention for L <= 32: qkv [B*L, 3*H*D] -> [B*L, H*D]."""
+    _need_cuda(qkv)
+    if qkv.dtype != torch.float32 or not qkv.is_contiguous():
+        raise TypeError("attention_small: qkv must be contiguous float32")
+    out = torch.empty((B * Lq, H * D), dtype=torch.float32, device=qkv.device)
+    L.check(L.load().vist3a_attention_small(qkv.data_ptr(), out.data_ptr(), B, Lq, H, D, D ** -0.5, _stream()))
+    return out
+
+
+def fma_rows(a: torch.Tensor, b: torch.Tensor, c: torch.Tensor) -> torch.Tensor:
+    """a * b + c on [rows, dim] fp32 views (row strides allowed)."""
+    _need_cuda(a, b, c)
+    rows, dim = a.shape
+    out = torch.empty((rows, dim), dtype=torch.float32, device=a.device)
+    L.check(L.load().vist3a_fma_rows(out.data_ptr(), out.stride(0), a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0),
+                                     c.data_ptr(), c.stride(0), rows, dim, _stream()))
+    return out
+
+
+def pose_to_cameras(pose_raw: torch.Tensor, H: int, W: int, cameras: bool = True):
+    """pose_raw [S, 9] fp32 -> dict(pose_act [S,9], extr [S,3,4], intr [S,3,3], c2w [S,4,4], intr_norm [S,3,3])."""
+    _need_cuda(pose_raw)
+    pose_raw = pose_raw.contiguous()
+    S = pose_raw.shape[0]
+    dev = pose_raw.device
+    out = {"pose_act": torch.empty((S, 9), dtype=torch.float32, device=dev)}
+    if cameras:
+        out.update(extr=torch.empty((S, 3, 4), dtype=torch.float32, device=dev), intr=torch.empty((S, 3, 3), dtype=torch.float32, device=dev),
+                   c2w=torch.empty((S, 4, 4), dtype=torch.float32, device=dev), intr_norm=torch.empty((S, 3, 3), dtype=torch.float32, device=dev))
+    L.check(L.load().vist3a_pose_to_cameras(pose_raw.data_ptr(), out["pose_act"].data_ptr(), _ptr(out.get("extr")), _ptr(out.get("intr")),
+                                            _ptr(out.get("c2w")), _ptr(out.get("intr_norm")), S, H, W, _stream()))
+    return out
+
+
+def gaussian_epilogue(depth_feat: torch.Tensor, depth_w: torch.Tensor, depth_b: float, gs_raw: torch.Tensor, extr: torch.Tensor,
+                      intr: torch.Tensor, sh_mask: torch.Tensor, S: int, H: int, W: int):
+    """fused depth activation + unprojection + Gaussian adapter; see vist3a_gaussian_epilogue."""
+    _need_cuda(depth_feat, depth_w, gs_raw, extr, intr, sh_mask)
+    P = S * H * W
+    d_sh = sh_mask.shape[0]
+    dev = gs_raw.device
+    f32 = torch.float32
+    o = dict(depth=torch.empty((P,), dtype=f32, device=dev), means=torch.empty((P, 3), dtype=f32, device=dev),
+             scales=torch.empty((P, 3), dtype=f32, device=dev), rotations=torch.empty((P, 4), dtype=f32, device=dev),
+             opacities=torch.empty((P,), dtype=f32, device=dev), harmonics=torch.empty((P, 3, d_sh), dtype=f32, device=dev),
+             covariances=torch.empty((P, 3, 3), dtype=f32, device=dev), scene_sum=torch.zeros((1,), dtype=f32, device=dev))
+    L.check(L.load().vist3a_gaussian_epilogue(depth_feat.data_ptr(), depth_feat.stride(0), depth_w.shape[0], depth_w.data_ptr(),
+                                              float(depth_b), gs_raw.data_ptr(), gs_raw.stride(0), extr.data_ptr(), intr.data_ptr(),
+                                              sh_mask.data_ptr(), d_sh, S, H, W, o["depth"].data_ptr(), o["means"].data_ptr(),
+                                              o["scales"].data_ptr(), o["rotations"].data_ptr(), o["opacities"].data_ptr(),
+                                              o["harmonics"].data_ptr(), o["covariances"].data_ptr(), o["scene_sum"].data_ptr(), _stream()))
+    return o
+
+
 # ------------------------------------------------------------------------------------------------
 # per-launch device timing (bench.py roofline): CUDA events recorded on the launching stream around
 # every call of the wrapped op, with its algorithmic FLOPs / bytes.
@@ -259,12 +412,17 @@ class OpTimer:
 
         def gemm_cost(out, args, kw):
             a, w = args[0], args[1]
-            M, K = a.reshape(-1, a.shape[-1]).shape
-            N = w.shape[0]
+            N, K = w.shape
+            M = out.numel() // N if kw.get("cmap") is None else (a.numel() // a.shape[-1])
+            if kw.get("conv") is not None:
+                cv = kw["conv"]
+                n_, h_, w_, _ = a.shape
+                M = n_ * (h_ + 2 * cv["pad"] - cv["kh"] + 1) * (w_ + 2 * cv["pad"] - cv["kw"] + 1)
             by = M * K * a.element_size() + N * K * w.element_size() + M * N * out.element_size()
             ep = ("+" + kw["act"] if kw.get("act") else "") + ("+gate" if kw.get("gate") is not None else "") + (
                 "+res" if kw.get("residual") is not None else "")
-            return 2.0 * M * N * K, by, f"gemm_tcgen05|{M}x{N}x{K}{ep}"
+            kind = ("tf32" if a.dtype == torch.float32 else "bf16") + ("conv" if kw.get("conv") is not None else "")
+            return 2.0 * M * N * K, by, f"gemm_tcgen05|{kind} {M}x{N}x{K}{ep}"
 
         def fmha_cost(out, args, kw):
             q, kk = args[0], args[1]
@@ -281,7 +439,9 @@ class OpTimer:
         table = {"gemm": gemm_cost, "fmha": fmha_cost, "layernorm": io_cost("layernorm"),
                  "rmsnorm_rope_": io_cost("rmsnorm_rope"), "modulation": io_cost("small"), "skinny_linear": io_cost("small"),
                  "timestep_features": io_cost("small"), "patchify": io_cost("small"), "unpatchify": io_cost("small"),
-                 "cfg_combine": io_cost("small"), "axpby_n": io_cost("small")}
+                 "cfg_combine": io_cost("small"), "axpby_n": io_cost("small"), "im2col_stitch": io_cost("im2col"),
+                 "im2col_nhwc": io_cost("im2col"), "qknorm_rope2d_": io_cost("qknorm_rope2d"), "bilinear_nhwc": io_cost("bilinear"),
+                 "depth_to_space": io_cost("depth_to_space"), "attention_small": io_cost("small"), "fma_rows": io_cost("small")}
         for name, cost in table.items():
             self._saved[name] = getattr(mod, name)
             setattr(mod, name, self._wrap(name, self._saved[name], cost))
