@@ -10,7 +10,7 @@ rc_all=0
 for f in "${files[@]}"; do
   name=$(basename "$f" .py)
   echo "=== $f"
-  timeout 900 python -m pytest "$f" -m gpu -q -x --no-header -p no:cacheprovider 2>&1 | tail -40 | tee "gpurun_out/${name}.log"
+  timeout 900 python -m pytest "$f" -m gpu -q --no-header -s -p no:cacheprovider 2>&1 | tail -60 | tee "gpurun_out/${name}.log"
   rc=${PIPESTATUS[0]}
   echo "rc=$rc" | tee -a "gpurun_out/${name}.log"
   [ $rc -ne 0 ] && rc_all=1

@@ -432,7 +432,8 @@ class OpTimer:
 
         def io_cost(tag):
             def f(out, args, kw):
-                ts = [t for t in args if isinstance(t, torch.Tensor)] + [out]
+                outs = list(out.values()) if isinstance(out, dict) else [out]
+                ts = [t for t in list(args) + list(kw.values()) + outs if isinstance(t, torch.Tensor)]
                 return 0.0, sum(t.numel() * t.element_size() for t in ts), tag
             return f
 
@@ -441,7 +442,8 @@ class OpTimer:
                  "timestep_features": io_cost("small"), "patchify": io_cost("small"), "unpatchify": io_cost("small"),
                  "cfg_combine": io_cost("small"), "axpby_n": io_cost("small"), "im2col_stitch": io_cost("im2col"),
                  "im2col_nhwc": io_cost("im2col"), "qknorm_rope2d_": io_cost("qknorm_rope2d"), "bilinear_nhwc": io_cost("bilinear"),
-                 "depth_to_space": io_cost("depth_to_space"), "attention_small": io_cost("small"), "fma_rows": io_cost("small")}
+                 "depth_to_space": io_cost("depth_to_space"), "attention_small": io_cost("small"), "fma_rows": io_cost("small"),
+                 "pose_to_cameras": io_cost("small"), "gaussian_epilogue": io_cost("gaussian_epilogue")}
         for name, cost in table.items():
             self._saved[name] = getattr(mod, name)
             setattr(mod, name, self._wrap(name, self._saved[name], cost))

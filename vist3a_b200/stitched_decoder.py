@@ -1,0 +1,594 @@
+"""Stitched latent -> 3D-Gaussian decoder on the sm_100a kernels -- drop-in for
+`StitchVAE3D.forward_with_latent` (/root/reference/models/stitched_model.py:165-173), i.e. the
+trilinear T-upsample + stitching Conv3d (models/stitching_layer_builder.py:21-42) feeding
+`AnySplatStitched.forward` (models/anysplat_stitched.py:167-525): 22 DINOv2 blocks, 24 x (frame,
+global) alternating-attention blocks, camera head, DPT depth head, DPT Gaussian head and the
+per-pixel Gaussian adapter (`voxelize=False`, `render_conf=False`, `opacity_conf=False`).
+
+Weights come from a state dict with the REFERENCE's key names (`stitching_layer.*`,
+`stitched_3d_model.encoder.*`), so `anysplat_stitched.pth` + the AnySplat checkpoint load unchanged.
+
+Data layout in HBM
+  tokens   fp32 [B*V*1029, C] residual stream (cls/camera + 4 register tokens first in every view);
+           the stitching GEMM and the final DINO norm write patch tokens straight behind the special
+           tokens through row maps, so no concatenation kernels exist;
+  qkv      bf16 [rows, 3C] written by one GEMM, normalised / rotated in place, consumed by attention
+           through strided views (frame: 13 sequences of 1029; global: one of 13377);
+  inter    4 x fp32 [B*V*1029, 2C] (frame | global halves) read by the heads through row maps;
+  heads    NHWC fp32 feature maps; every 3x3 convolution is an implicit GEMM whose A operand is
+           fetched by 4-D TMA boxes (zero padding = out-of-bounds fill), TF32 tcgen05 MMAs
+           (the reference runs these convs through cuDNN with TF32 allowed);
+  output   means/scales/rotations/opacities/harmonics/covariances fp32, contiguous per field.
+dtype policy: bf16 GEMM/attention operands and fp32 accumulation + fp32 residual stream in the
+transformer; fp32 activations with TF32 MMAs in the heads; fp32 LayerNorm statistics everywhere.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from types import SimpleNamespace
+from typing import Dict, List, Optional, Tuple
+
+import torch
+import torch.nn.functional as F
+
+from . import ops
+
+E = "stitched_3d_model.encoder."
+N_SPECIAL = 5  # cls/camera token + 4 register tokens
+
+
+# ------------------------------------------------------------------------------------------------
+# return types (AS/model/types.py:8-14, AS/model/encoder/encoder.py:16-23)
+# ------------------------------------------------------------------------------------------------
+@dataclass
+class Gaussians:
+    means: torch.Tensor          # [B, N, 3]
+    covariances: torch.Tensor    # [B, N, 3, 3]
+    harmonics: torch.Tensor      # [B, N, 3, d_sh]
+    opacities: torch.Tensor      # [B, N]
+    scales: torch.Tensor         # [B, N, 3]
+    rotations: torch.Tensor      # [B, N, 4] (xyzw)
+
+
+@dataclass
+class EncoderOutput:
+    gaussians: Gaussians
+    pred_pose_enc_list: Optional[List[torch.Tensor]]
+    pred_context_pose: dict
+    depth_dict: dict
+    infos: dict
+    distill_infos: Optional[dict] = None
+    last_pred_pose_enc: Optional[torch.Tensor] = None
+
+
+@dataclass(frozen=True)
+class DecoderConfig:
+    embed_dim: int = 1024
+    num_heads: int = 16
+    dino_blocks: int = 22
+    agg_depth: int = 24
+    cam_heads: int = 16
+    cam_trunk: int = 4
+    dpt_features: int = 256
+    dpt_out_channels: Tuple[int, ...] = (256, 512, 1024, 1024)
+    pos_grid: int = 37
+    patch: int = 14
+    sh_degree: int = 4
+    latent_channels: int = 16
+    inter_layers: Tuple[int, ...] = (4, 11, 17, 23)
+    resolution: int = 512  # video resolution; the VAE latent grid is resolution / 8
+
+    @property
+    def d_sh(self):
+        return (self.sh_degree + 1) ** 2
+
+    @property
+    def raw_gs_dim(self):
+        return 1 + 7 + 3 * self.d_sh
+
+
+def _conv_w(w: torch.Tensor) -> torch.Tensor:
+    """[N, C, kh, kw] -> [N, kh*kw*C] with k = (dy*kw + dx)*C + c (the implicit-GEMM / im2col order)"""
+    return w.permute(0, 2, 3, 1).reshape(w.shape[0], -1)
+
+
+def _sincos(p: torch.Tensor, d: int) -> torch.Tensor:
+    om = torch.arange(d // 2, dtype=torch.double) / (d / 2.0)
+    om = 1.0 / 100 ** om
+    out = torch.einsum("m,d->md", p.reshape(-1).double(), om)
+    return torch.cat([out.sin(), out.cos()], dim=1).float()
+
+
+def _dpt_pos_tables(C: int, h: int, w: int, W_img: int, H_img: int, ratio: float = 0.1):
+    """separable form of create_uv_grid + position_grid_to_embed (AS/.../heads/utils.py:11-108, dpt_head.py:267-277):
+    channels [0, C/2) depend on x only, [C/2, C) on y only.  -> pos_x [w, C/2], pos_y [h, C/2]"""
+    aspect = W_img / H_img
+    diag = (aspect ** 2 + 1.0) ** 0.5
+    sx, sy = aspect / diag, 1.0 / diag
+    xs = torch.linspace(-sx * (w - 1) / w, sx * (w - 1) / w, steps=w)
+    ys = torch.linspace(-sy * (h - 1) / h, sy * (h - 1) / h, steps=h)
+    return (_sincos(xs, C // 2) * ratio).contiguous(), (_sincos(ys, C // 2) * ratio).contiguous()
+
+
+def param_shapes(cfg: DecoderConfig) -> Dict[str, Tuple[int, ...]]:
+    """Parameter manifest of the stitched decoder under the reference's state-dict keys (what a real
+    `anysplat_stitched.pth` + AnySplat checkpoint provide; tests check it against the oracle's manifest)."""
+    C, C2, Fd, oc = cfg.embed_dim, 2 * cfg.embed_dim, cfg.dpt_features, cfg.dpt_out_channels
+    s: Dict[str, Tuple[int, ...]] = {"stitching_layer.weight": (C, cfg.latent_channels, 5, 3, 3), "stitching_layer.bias": (C,)}
+
+    def lin(name, n, k):
+        s[name + ".weight"], s[name + ".bias"] = (n, k), (n,)
+
+    def norm(name, n):
+        s[name + ".weight"], s[name + ".bias"] = (n,), (n,)
+
+    def block(p, dim, head_dim=None):
+        norm(p + "norm1", dim)
+        lin(p + "attn.qkv", 3 * dim, dim)
+        if head_dim:
+            norm(p + "attn.q_norm", head_dim)
+            norm(p + "attn.k_norm", head_dim)
+        lin(p + "attn.proj", dim, dim)
+        s[p + "ls1.gamma"] = (dim,)
+        norm(p + "norm2", dim)
+        lin(p + "mlp.fc1", 4 * dim, dim)
+        lin(p + "mlp.fc2", dim, 4 * dim)
+        s[p + "ls2.gamma"] = (dim,)
+
+    pe, ag, ch = E + "aggregator.patch_embed.", E + "aggregator.", E + "camera_head."
+    s[pe + "cls_token"], s[pe + "pos_embed"] = (1, 1, C), (1, 1 + cfg.pos_grid ** 2, C)
+    s[pe + "register_tokens"], s[pe + "mask_token"] = (1, 4, C), (1, C)
+    for i in range(cfg.dino_blocks):
+        block(pe + f"blocks.{i}.", C)
+    norm(pe + "norm", C)
+    s[ag + "camera_token"], s[ag + "register_token"] = (1, 2, 1, C), (1, 2, 4, C)
+    for i in range(cfg.agg_depth):
+        block(ag + f"frame_blocks.{i}.", C, C // cfg.num_heads)
+        block(ag + f"global_blocks.{i}.", C, C // cfg.num_heads)
+    s[ch + "empty_pose_tokens"] = (1, 1, 9)
+    for i in range(cfg.cam_trunk):
+        block(ch + f"trunk.{i}.", C2)
+    norm(ch + "token_norm", C2)
+    norm(ch + "trunk_norm", C2)
+    lin(ch + "embed_pose", C2, 9)
+    lin(ch + "poseLN_modulation.1", 3 * C2, C2)
+    lin(ch + "pose_branch.fc1", C2 // 2, C2)
+    lin(ch + "pose_branch.fc2", 9, C2 // 2)
+
+    def conv(name, co, ci, k, bias=True):
+        s[name + ".weight"] = (co, ci, k, k)
+        if bias:
+            s[name + ".bias"] = (co,)
+
+    for head, out_dim in (("depth_head.", 2), ("gaussian_param_head.", cfg.raw_gs_dim + 1)):
+        h = E + head
+        hf2 = 128 if out_dim > 50 else 32
+        norm(h + "norm", C2)
+        for k in range(4):
+            conv(h + f"projects.{k}", oc[k], C2, 1)
+            conv(h + f"scratch.layer{k + 1}_rn", Fd, oc[k], 3, bias=False)
+        conv(h + "resize_layers.0", oc[0], oc[0], 4)
+        conv(h + "resize_layers.1", oc[1], oc[1], 2)
+        conv(h + "resize_layers.3", oc[3], oc[3], 3)
+        for r in (1, 2, 3, 4):
+            p = h + f"scratch.refinenet{r}."
+            conv(p + "out_conv", Fd, Fd, 1)
+            for u in ((1, 2) if r != 4 else (2,)):
+                conv(p + f"resConfUnit{u}.conv1", Fd, Fd, 3)
+                conv(p + f"resConfUnit{u}.conv2", Fd, Fd, 3)
+        conv(h + "scratch.output_conv1", Fd // 2, Fd, 3)
+        conv(h + "scratch.output_conv2.0", hf2, Fd // 2, 3)
+        conv(h + "scratch.output_conv2.2", out_dim, hf2, 1)
+        if out_dim > 50:
+            conv(h + "input_merger.0", hf2, 3, 7)
+    return s
+
+
+def random_state_dict(cfg: DecoderConfig, seed: int = 0, device="cuda") -> Dict[str, torch.Tensor]:
+    """Random-init weights of the named architecture for benchmarking (no checkpoint is reachable offline), generated on
+    `device`.  Scales keep activations O(1) through the 70 blocks: matrices U(-1,1) * 0.8 sqrt(3 / fan_in), biases
+    0.02 U, norm weights 1 + 0.1 U, LayerScale 1.0 (DINOv2) / 0.01 (aggregator, camera trunk) as the reference
+    constructors set them (AS/.../layers/block.py:44-77, aggregator.py:99-133)."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    sd = {}
+    for k, shp in param_shapes(cfg).items():
+        u = torch.rand(shp, generator=g, device=device) * 2 - 1
+        if k.endswith("gamma"):
+            t = (1.0 if "patch_embed.blocks" in k else 0.01) * (1.0 + 0.2 * u)
+        elif "norm" in k and k.endswith(".weight"):
+            t = 1.0 + 0.1 * u
+        elif k.endswith(".bias"):
+            t = 0.02 * u
+        elif k.endswith("token") or k.endswith("tokens") or k.endswith("pos_embed"):
+            t = 0.02 * u
+        else:
+            fan_in = math.prod(shp[1:]) if len(shp) > 1 else shp[0]
+            if "resize_layers.0" in k or "resize_layers.1" in k:
+                fan_in = shp[0]
+            t = u * math.sqrt(3.0 / fan_in) * 0.8
+        if k.endswith("camera_head.pose_branch.fc2.bias"):  # quaternion w ~ 1, FoV ~ 1 rad after the 4 refinement iterations
+            t = t + torch.tensor([0, 0, 0, 0, 0, 0, 0.25, 0.25, 0.25], device=device)
+        sd[k] = t
+    return sd
+
+
+class StitchVAE3DB200(torch.nn.Module):
+    """B200-native StitchVAE3D (inference: `forward_with_latent`)."""
+
+    def __init__(self, config: DecoderConfig = DecoderConfig(), device="cuda"):
+        super().__init__()
+        self.cfg = config
+        self.device = torch.device(device)
+        self.w: Dict[str, torch.Tensor] = {}
+        self._tables = {}
+        if config.embed_dim // config.num_heads != 64:
+            raise NotImplementedError("the QK-norm + 2-D RoPE kernel implements the aggregator's 64-wide heads")
+
+    def eval(self):
+        return self
+
+    def _apply(self, fn):
+        return self
+
+    # ------------------------------------------------------------------ weights
+    @classmethod
+    def from_state_dict(cls, sd: Dict[str, torch.Tensor], config: DecoderConfig = DecoderConfig(), device="cuda"):
+        m = cls(config, device)
+        m.load_weights(sd)
+        return m
+
+    def load_weights(self, sd: Dict[str, torch.Tensor]):
+        cfg, dev = self.cfg, self.device
+        C = cfg.embed_dim
+        w: Dict[str, torch.Tensor] = {}
+
+        def f32(t):
+            return t.detach().float().contiguous().to(dev)
+
+        def bf(t):
+            return t.detach().float().to(dev, torch.bfloat16).contiguous()
+
+        self.stitching_layer = SimpleNamespace(weight=sd["stitching_layer.weight"], bias=sd["stitching_layer.bias"])
+        w["stitch.w"] = bf(sd["stitching_layer.weight"].reshape(C, -1))  # k = c*45 + kt*9 + ky*3 + kx
+        w["stitch.b"] = f32(sd["stitching_layer.bias"])
+        pe = E + "aggregator.patch_embed."
+        self._pos_embed = sd[pe + "pos_embed"].detach().float().cpu()
+        self._cls = sd[pe + "cls_token"].detach().float().cpu().reshape(1, C)
+        self._reg = sd[pe + "register_tokens"].detach().float().cpu().reshape(4, C)
+
+        def block(dst, src, conv=bf):
+            for n in ("norm1", "norm2"):
+                w[dst + n + ".w"], w[dst + n + ".b"] = f32(sd[src + n + ".weight"]), f32(sd[src + n + ".bias"])
+            for n, m in (("qkv", "attn.qkv"), ("proj", "attn.proj"), ("fc1", "mlp.fc1"), ("fc2", "mlp.fc2")):
+                w[dst + n + ".w"], w[dst + n + ".b"] = conv(sd[src + m + ".weight"]), f32(sd[src + m + ".bias"])
+            w[dst + "ls1"], w[dst + "ls2"] = f32(sd[src + "ls1.gamma"]), f32(sd[src + "ls2.gamma"])
+            if src + "attn.q_norm.weight" in sd:
+                for n in ("q_norm", "k_norm"):
+                    w[dst + n + ".w"], w[dst + n + ".b"] = f32(sd[src + f"attn.{n}.weight"]), f32(sd[src + f"attn.{n}.bias"])
+
+        for i in range(cfg.dino_blocks):
+            block(f"dino{i}.", pe + f"blocks.{i}.")
+        w["dino.norm.w"], w["dino.norm.b"] = f32(sd[pe + "norm.weight"]), f32(sd[pe + "norm.bias"])
+        ag = E + "aggregator."
+        cam = sd[ag + "camera_token"].detach().float().reshape(2, 1, C)
+        reg = sd[ag + "register_token"].detach().float().reshape(2, 4, C)
+        w["agg.special"] = f32(torch.cat([cam, reg], dim=1))  # [2 slots (first view / other views), 5, C]
+        for i in range(cfg.agg_depth):
+            block(f"frame{i}.", ag + f"frame_blocks.{i}.")
+            block(f"global{i}.", ag + f"global_blocks.{i}.")
+        # camera head: fp32 weights streamed by the skinny-linear kernel
+        ch = E + "camera_head."
+        for i in range(cfg.cam_trunk):
+            block(f"cam{i}.", ch + f"trunk.{i}.", conv=f32)
+        for n in ("token_norm", "trunk_norm"):
+            w["cam." + n + ".w"], w["cam." + n + ".b"] = f32(sd[ch + n + ".weight"]), f32(sd[ch + n + ".bias"])
+        w["cam.empty"] = f32(F.pad(sd[ch + "empty_pose_tokens"].detach().float().reshape(1, 9), (0, 7)))
+        w["cam.embed.w"] = f32(F.pad(sd[ch + "embed_pose.weight"].detach().float(), (0, 7)))  # K 9 -> 16
+        w["cam.embed.b"] = f32(sd[ch + "embed_pose.bias"])
+        w["cam.mod.w"], w["cam.mod.b"] = f32(sd[ch + "poseLN_modulation.1.weight"]), f32(sd[ch + "poseLN_modulation.1.bias"])
+        w["cam.fc1.w"], w["cam.fc1.b"] = f32(sd[ch + "pose_branch.fc1.weight"]), f32(sd[ch + "pose_branch.fc1.bias"])
+        w["cam.fc2.w"], w["cam.fc2.b"] = f32(sd[ch + "pose_branch.fc2.weight"]), f32(sd[ch + "pose_branch.fc2.bias"])
+        # DPT heads (fp32 weights, TF32 MMAs)
+        for tag, head in (("dh.", E + "depth_head."), ("gh.", E + "gaussian_param_head.")):
+            w[tag + "norm.w"], w[tag + "norm.b"] = f32(sd[head + "norm.weight"]), f32(sd[head + "norm.bias"])
+            for k in range(4):
+                w[tag + f"proj{k}.w"] = f32(sd[head + f"projects.{k}.weight"].flatten(1))
+                w[tag + f"proj{k}.b"] = f32(sd[head + f"projects.{k}.bias"])
+                w[tag + f"rn{k}.w"] = f32(_conv_w(sd[head + f"scratch.layer{k + 1}_rn.weight"]))
+            for k, ks in ((0, 4), (1, 2)):  # ConvTranspose2d(k = s): W'[(dy*k+dx)*Co + co, ci] = w[ci, co, dy, dx]
+                wt = sd[head + f"resize_layers.{k}.weight"].detach().float()
+                w[tag + f"up{k}.w"] = f32(wt.permute(2, 3, 1, 0).reshape(ks * ks * wt.shape[1], wt.shape[0]))
+                w[tag + f"up{k}.b"] = f32(sd[head + f"resize_layers.{k}.bias"].detach().float().repeat(ks * ks))
+            w[tag + "down3.w"] = f32(_conv_w(sd[head + "resize_layers.3.weight"]))
+            w[tag + "down3.b"] = f32(sd[head + "resize_layers.3.bias"])
+            for r in (1, 2, 3, 4):
+                p = head + f"scratch.refinenet{r}."
+                w[tag + f"rf{r}.out.w"], w[tag + f"rf{r}.out.b"] = f32(sd[p + "out_conv.weight"].flatten(1)), f32(sd[p + "out_conv.bias"])
+                for u in ((1, 2) if r != 4 else (2,)):
+                    for c in (1, 2):
+                        w[tag + f"rf{r}.u{u}c{c}.w"] = f32(_conv_w(sd[p + f"resConfUnit{u}.conv{c}.weight"]))
+                        w[tag + f"rf{r}.u{u}c{c}.b"] = f32(sd[p + f"resConfUnit{u}.conv{c}.bias"])
+            w[tag + "oc1.w"], w[tag + "oc1.b"] = f32(_conv_w(sd[head + "scratch.output_conv1.weight"])), f32(sd[head + "scratch.output_conv1.bias"])
+            w[tag + "oc2a.w"], w[tag + "oc2a.b"] = f32(_conv_w(sd[head + "scratch.output_conv2.0.weight"])), f32(sd[head + "scratch.output_conv2.0.bias"])
+        w["dh.oc2b.w"] = f32(sd[E + "depth_head.scratch.output_conv2.2.weight"][0].flatten())  # depth channel only
+        self._depth_b = float(sd[E + "depth_head.scratch.output_conv2.2.bias"][0])
+        g = E + "gaussian_param_head."
+        w["gh.oc2b.w"] = f32(sd[g + "scratch.output_conv2.2.weight"].flatten(1))
+        w["gh.oc2b.b"] = f32(sd[g + "scratch.output_conv2.2.bias"])
+        mw = _conv_w(sd[g + "input_merger.0.weight"].detach().float())  # [128, 147]
+        self._merger_k = (mw.shape[1] + 3) // 4 * 4
+        w["gh.merger.w"] = f32(F.pad(mw, (0, self._merger_k - mw.shape[1])))
+        w["gh.merger.b"] = f32(sd[g + "input_merger.0.bias"])
+        m = torch.ones(cfg.d_sh)
+        for deg in range(1, cfg.sh_degree + 1):  # AS/model/encoder/common/gaussian_adapter.py:34-40
+            m[deg ** 2:(deg + 1) ** 2] = 0.1 * 0.25 ** deg
+        w["sh_mask"] = f32(m)
+        # 2-D RoPE tables (AS/.../layers/rope.py:100-115): base 100, 16 frequencies per axis
+        inv = 1.0 / (100.0 ** (torch.arange(0, 32, 2).float() / 32))
+        ang = torch.arange(64).float()[:, None] * inv[None]
+        w["rope.cos"], w["rope.sin"] = f32(ang.cos()), f32(ang.sin())
+        self.w = w
+        self._tables = {}
+
+    def weight_bytes(self) -> int:
+        return sum(t.numel() * t.element_size() for t in self.w.values())
+
+    # ------------------------------------------------------------------ shape-dependent constants
+    def _shape_tables(self, gh: int, gw: int, H: int, W: int):
+        key = (gh, gw, H, W)
+        t = self._tables.get(key)
+        if t is not None:
+            return t
+        cfg, dev = self.cfg, self.device
+        C = cfg.embed_dim
+        pe = self._pos_embed
+        N = pe.shape[1] - 1
+        M = int(math.sqrt(N))
+        if gh * gw == N and gh == gw:
+            patch_pe = pe[0, 1:]
+        else:  # vision_transformer.py:184-216 (`size=` branch, bicubic + antialias): a per-shape constant
+            patch_pe = F.interpolate(pe[:, 1:].reshape(1, M, M, C).permute(0, 3, 1, 2), size=(gw, gh), mode="bicubic",
+                                     antialias=True).permute(0, 2, 3, 1).reshape(-1, C)
+        t = SimpleNamespace()
+        t.pos = patch_pe.contiguous().to(dev)                                         # [gh*gw, C]
+        t.special = torch.cat([self._cls + pe[0, :1], self._reg], 0).contiguous().to(dev)  # [5, C]
+        t.dpt = {}
+        for k, oc in enumerate(cfg.dpt_out_channels):  # [gh*gw, oc] tables added by the projection GEMM epilogues of both heads
+            px, py = _dpt_pos_tables(oc, gh, gw, W, H)
+            t.dpt[k] = torch.cat([px[None].expand(gh, gw, -1), py[:, None].expand(gh, gw, -1)], -1).reshape(gh * gw, oc).contiguous().to(dev)
+        px, py = _dpt_pos_tables(cfg.dpt_features // 2, H, W, W, H)
+        t.full_px, t.full_py = px.to(dev), py.to(dev)
+        self._tables[key] = t
+        return t
+
+    # ------------------------------------------------------------------ transformer
+    def _block(self, p: str, x: torch.Tensor, *, seqs: int, seq_len: int, eps: float, rope: Optional[dict], ws) -> None:
+        """AS/.../layers/block.py:81-107 on the fp32 stream x [rows, C] (in place)."""
+        w, cfg = self.w, self.cfg
+        C, Hn = cfg.embed_dim, cfg.num_heads
+        ops.layernorm(x, mul=w[p + "norm1.w"], add=w[p + "norm1.b"], eps=eps, out=ws.h)
+        ops.gemm(ws.h, w[p + "qkv.w"], w[p + "qkv.b"], out=ws.qkv)
+        if rope is not None:
+            ops.qknorm_rope2d_(ws.qkv, Hn, w[p + "q_norm.w"], w[p + "q_norm.b"], w[p + "k_norm.w"], w[p + "k_norm.b"], w["rope.cos"],
+                               w["rope.sin"], tokens_per_view=rope["tpv"], n_special=N_SPECIAL, grid_w=rope["gw"], eps=1e-5)
+        q5 = ws.qkv.view(seqs, seq_len, 3, Hn, C // Hn)
+        ops.fmha(q5[:, :, 0], q5[:, :, 1], q5[:, :, 2], out=ws.att.view(seqs, seq_len, Hn, C // Hn))
+        ops.gemm(ws.att, w[p + "proj.w"], w[p + "proj.b"], gate=w[p + "ls1"], residual=x, out=x)
+        ops.layernorm(x, mul=w[p + "norm2.w"], add=w[p + "norm2.b"], eps=eps, out=ws.h)
+        ops.gemm(ws.h, w[p + "fc1.w"], w[p + "fc1.b"], act="gelu_erf", out=ws.mlp)
+        ops.gemm(ws.mlp, w[p + "fc2.w"], w[p + "fc2.b"], gate=w[p + "ls2"], residual=x, out=x)
+
+    def _aggregate(self, latent: torch.Tensor, H: int, W: int) -> List[torch.Tensor]:
+        cfg, w, dev = self.cfg, self.w, self.device
+        C = cfg.embed_dim
+        B, _, T, lh, lw = latent.shape
+        V = (T - 1) * 4 + 1
+        gh, gw = lh // 2, lw // 2
+        if (gh, gw) != (H // cfg.patch, W // cfg.patch):
+            raise ValueError(f"latent grid {lh}x{lw} -> {gh}x{gw} tokens does not match the {H}x{W} image ({H // cfg.patch}x{W // cfg.patch} patches)")
+        npatch = gh * gw
+        P = npatch + N_SPECIAL
+        BV = B * V
+        rows = BV * P
+        tb = self._shape_tables(gh, gw, H, W)
+        ws = SimpleNamespace(h=torch.empty((rows, C), dtype=torch.bfloat16, device=dev),
+                             qkv=torch.empty((rows, 3 * C), dtype=torch.bfloat16, device=dev),
+                             att=torch.empty((rows, C), dtype=torch.bfloat16, device=dev),
+                             mlp=torch.empty((rows, 4 * C), dtype=torch.bfloat16, device=dev))
+        pmap = (npatch, P, N_SPECIAL)  # patch-token rows of the [BV*P] stream
+        # --- stitching conv: upsample + replicate pad + im2col, then one GEMM (+bias +pos-embed) into the patch rows
+        x = torch.empty((rows, C), dtype=torch.float32, device=dev)
+        a = ops.im2col_stitch(latent)
+        ops.gemm(a, w["stitch.w"], w["stitch.b"], out=x, residual=tb.pos, rmap=(npatch, 0, 0), cmap=pmap)
+        del a
+        x.view(BV, P, C)[:, :N_SPECIAL].copy_(tb.special)
+        # --- DINOv2 blocks (eps 1e-6, no QK norm / RoPE), sequences = views
+        for i in range(cfg.dino_blocks):
+            self._block(f"dino{i}.", x, seqs=BV, seq_len=P, eps=1e-6, rope=None, ws=ws)
+        # --- final DINO norm on the patch rows -> aggregator stream; camera/register tokens in front
+        t = torch.empty((rows, C), dtype=torch.float32, device=dev)
+        ops.layernorm(x, mul=w["dino.norm.w"], add=w["dino.norm.b"], eps=1e-6, out=t, in_map=pmap, out_map=pmap, rows=BV * npatch)
+        del x
+        t5 = t.view(B, V, P, C)
+        t5[:, 0, :N_SPECIAL].copy_(w["agg.special"][0])
+        if V > 1:
+            t5[:, 1:, :N_SPECIAL].copy_(w["agg.special"][1])
+        rope = {"tpv": P, "gw": gw}
+        inters = []
+        for i in range(cfg.agg_depth):
+            keep = i in cfg.inter_layers
+            self._block(f"frame{i}.", t, seqs=BV, seq_len=P, eps=1e-5, rope=rope, ws=ws)
+            if keep:
+                it = torch.empty((rows, 2 * C), dtype=torch.float32, device=dev)
+                it[:, :C].copy_(t)
+            self._block(f"global{i}.", t, seqs=B, seq_len=V * P, eps=1e-5, rope=rope, ws=ws)
+            if keep:
+                it[:, C:].copy_(t)
+                inters.append(it)
+        return inters
+
+    # ------------------------------------------------------------------ camera head
+    def _camera_head(self, inter_last: torch.Tensor, B: int, V: int, P: int, iters: int = 4) -> List[torch.Tensor]:
+        """AS/.../heads/camera_head.py:87-170 -> list of activated pose encodings [B, V, 9]"""
+        w, cfg = self.w, self.cfg
+        C2 = 2 * cfg.embed_dim
+        Hn = cfg.cam_heads
+        if V > 16:
+            raise NotImplementedError("camera head kernels handle up to 16 views per scene")
+        per_batch = []
+        for b in range(B):
+            cam_rows = inter_last.view(B, V, P, C2)[b, :, 0]  # [V, C2] view, row stride P*C2
+            tok = ops.layernorm(cam_rows, mul=w["cam.token_norm.w"], add=w["cam.token_norm.b"], eps=1e-5, out_dtype=torch.float32)
+            pred = None
+            outs = []
+            for _ in range(iters):
+                inp = w["cam.empty"].expand(V, -1).contiguous() if pred is None else pred
+                emb = ops.skinny_linear(inp, w["cam.embed.w"], w["cam.embed.b"], out_dtype=torch.float32)
+                mod = ops.skinny_linear(emb, w["cam.mod.w"], w["cam.mod.b"], pre_act="silu", out_dtype=torch.float32)  # shift | scale | gate
+                mlo = ops.layernorm(tok, mul=mod[:, C2:2 * C2], add=mod[:, :C2], mul_bstride=3 * C2, add_bstride=3 * C2, rows_per_batch=1,
+                                    eps=1e-6, mul_plus_one=True, out_dtype=torch.float32)
+                x = ops.fma_rows(mod[:, 2 * C2:], mlo, tok)
+                for i in range(cfg.cam_trunk):
+                    p = f"cam{i}."
+                    h = ops.layernorm(x, mul=w[p + "norm1.w"], add=w[p + "norm1.b"], eps=1e-5, out_dtype=torch.float32)
+                    qkv = ops.skinny_linear(h, w[p + "qkv.w"], w[p + "qkv.b"], out_dtype=torch.float32)
+                    att = ops.attention_small(qkv, 1, V, Hn, C2 // Hn)
+                    x = ops.skinny_linear(att, w[p + "proj.w"], w[p + "proj.b"], gate=w[p + "ls1"], residual=x, out_dtype=torch.float32)
+                    h = ops.layernorm(x, mul=w[p + "norm2.w"], add=w[p + "norm2.b"], eps=1e-5, out_dtype=torch.float32)
+                    m = ops.skinny_linear(h, w[p + "fc1.w"], w[p + "fc1.b"], act="gelu_erf", out_dtype=torch.float32)
+                    x = ops.skinny_linear(m, w[p + "fc2.w"], w[p + "fc2.b"], gate=w[p + "ls2"], residual=x, out_dtype=torch.float32)
+                h = ops.layernorm(x, mul=w["cam.trunk_norm.w"], add=w["cam.trunk_norm.b"], eps=1e-5, out_dtype=torch.float32)
+                m = ops.skinny_linear(h, w["cam.fc1.w"], w["cam.fc1.b"], act="gelu_erf", out_dtype=torch.float32)
+                new = torch.zeros((V, 16), dtype=torch.float32, device=self.device)
+                ops.skinny_linear(m, w["cam.fc2.w"], w["cam.fc2.b"], out=new, residual=pred)  # pred + delta (cols 9..15 stay 0)
+                pred = new
+                outs.append(pred)
+            per_batch.append(outs)
+        return [torch.stack([per_batch[b][i][:, :9] for b in range(B)], 0) for i in range(iters)]  # raw (pre-activation) encodings
+
+    # ------------------------------------------------------------------ DPT trunk
+    def _conv3(self, x, wt, bias=None, **kw):
+        n, h, wd, _ = x.shape
+        out = torch.empty((n, h, wd, wt.shape[0]), dtype=torch.float32, device=x.device)
+        ops.gemm(x, wt, bias, conv=dict(kh=3, kw=3, pad=1), out=out.view(-1, wt.shape[0]), **kw)
+        return out
+
+    def _fusion(self, tag: str, r: int, x: Optional[torch.Tensor], skip_relu: torch.Tensor, size: Tuple[int, int]) -> torch.Tensor:
+        """FeatureFusionBlock.forward (dpt_head.py:442-474).  `skip_relu` already holds relu(skip): ResidualConvUnit's
+        in-place ReLU (dpt_head.py:362-404) rectifies its input tensor, so the skip connection adds relu(x)."""
+        w = self.w
+        p = tag + f"rf{r}."
+        if x is not None:
+            c1 = self._conv3(skip_relu, w[p + "u1c1.w"], w[p + "u1c1.b"], act="relu")
+            C = x.shape[-1]
+            # s = relu(x + conv2(c1) + b + relu(skip))  (the trailing relu is unit 2's in-place activation)
+            s = self._conv3(c1, w[p + "u1c2.w"], w[p + "u1c2.b"], residual=skip_relu.view(-1, C), residual2=x.view(-1, C), post_act="relu")
+        else:
+            s = skip_relu
+        c1 = self._conv3(s, w[p + "u2c1.w"], w[p + "u2c1.b"], act="relu")
+        C = s.shape[-1]
+        o = self._conv3(c1, w[p + "u2c2.w"], w[p + "u2c2.b"], residual=s.view(-1, C))
+        o = ops.bilinear_nhwc(o, size[0], size[1])
+        out = torch.empty_like(o)
+        ops.gemm(o.view(-1, C), w[p + "out.w"], w[p + "out.b"], out=out.view(-1, C))
+        return out
+
+    def _dpt_trunk(self, tag: str, inters: List[torch.Tensor], BV: int, gh: int, gw: int, tb) -> torch.Tensor:
+        """DPTHead._forward_impl up to scratch.output_conv1 (dpt_head.py:194-252,279-309) -> NHWC [BV, 8gh, 8gw, F/2]"""
+        cfg, w, dev = self.cfg, self.w, self.device
+        C2 = 2 * cfg.embed_dim
+        npatch = gh * gw
+        P = npatch + N_SPECIAL
+        pmap = (npatch, P, N_SPECIAL)
+        feats = []
+        for k, it in enumerate(inters):
+            oc = cfg.dpt_out_channels[k]
+            xn = ops.layernorm(it, mul=w[tag + "norm.w"], add=w[tag + "norm.b"], eps=1e-5, in_map=pmap, rows=BV * npatch, out_dtype=torch.float32)
+            x = ops.gemm(xn, w[tag + f"proj{k}.w"], w[tag + f"proj{k}.b"], residual=tb.dpt[k], rmap=(npatch, 0, 0))  # + pos embed
+            del xn
+            if k in (0, 1):
+                ks = 4 if k == 0 else 2
+                y = ops.gemm(x, w[tag + f"up{k}.w"], w[tag + f"up{k}.b"])
+                x = ops.depth_to_space(y, BV, gh, gw, oc, ks)
+                del y
+            elif k == 2:
+                x = x.view(BV, gh, gw, oc)
+            else:
+                a = ops.im2col_nhwc(x.view(BV, gh, gw, oc), 3, 3, 2, 1)
+                ho, wo = (gh - 1) // 2 + 1, (gw - 1) // 2 + 1
+                x = ops.gemm(a, w[tag + "down3.w"], w[tag + "down3.b"]).view(BV, ho, wo, oc)
+                del a
+            feats.append(self._conv3(x, w[tag + f"rn{k}.w"], None, act="relu"))  # relu: the consuming ResidualConvUnit's in-place activation
+        l1, l2, l3, l4 = feats
+        out = self._fusion(tag, 4, None, l4, l3.shape[1:3])
+        out = self._fusion(tag, 3, out, l3, l2.shape[1:3])
+        out = self._fusion(tag, 2, out, l2, l1.shape[1:3])
+        out = self._fusion(tag, 1, out, l1, (2 * l1.shape[1], 2 * l1.shape[2]))
+        return self._conv3(out, w[tag + "oc1.w"], w[tag + "oc1.b"])
+
+    # ------------------------------------------------------------------ forward
+    @torch.no_grad()
+    def forward_with_latent(self, latent: torch.Tensor, feedforward_image: torch.Tensor, train: bool = False) -> EncoderOutput:
+        """latent [B, 16, T, res/8, res/8] (de-normalised VAE latent), feedforward_image [B, 3, V, H, W] in [-1, 1]."""
+        if train:
+            raise NotImplementedError("the B200 decoder is an inference engine (train=False)")
+        if not self.w:
+            raise RuntimeError("weights not loaded: use StitchVAE3DB200.from_state_dict(...)")
+        cfg, w, dev = self.cfg, self.w, self.device
+        B, ci, V, H, W = feedforward_image.shape
+        if latent.dtype not in (torch.float32, torch.bfloat16):
+            latent = latent.float()
+        latent = latent.to(dev).contiguous()
+        if latent.shape[0] != B or (latent.shape[2] - 1) * 4 + 1 != V:
+            raise ValueError(f"latent {tuple(latent.shape)} does not match {V} views x batch {B}")
+        lat_hw = cfg.resolution // 8
+        if latent.shape[-2:] != (lat_hw, lat_hw):  # upsampling_layer also resizes H, W to resolution/8 (stitched_model.py:92-107)
+            raise NotImplementedError(f"latent grid {tuple(latent.shape[-2:])} != resolution/8 = {lat_hw}: spatial resampling is not on the hot path")
+        gh, gw = H // cfg.patch, W // cfg.patch
+        P = gh * gw + N_SPECIAL
+        BV = B * V
+        tb = self._shape_tables(gh, gw, H, W)
+        inters = self._aggregate(latent, H, W)
+        # --- cameras
+        pose_raw = self._camera_head(inters[-1], B, V, P)
+        cams = ops.pose_to_cameras(pose_raw[-1].reshape(BV, 9), H, W)
+        pose_list = [ops.pose_to_cameras(p.reshape(BV, 9), H, W, cameras=False)["pose_act"].view(B, V, 9) for p in pose_raw[:-1]]
+        pose_list.append(cams["pose_act"].view(B, V, 9))
+        # --- depth head
+        d = self._dpt_trunk("dh.", inters, BV, gh, gw, tb)
+        d = ops.bilinear_nhwc(d, H, W, pos_x=tb.full_px, pos_y=tb.full_py)
+        dfeat = self._conv3(d, w["dh.oc2a.w"], w["dh.oc2a.b"], act="relu")
+        del d
+        # --- Gaussian head
+        img01 = ((feedforward_image.to(dev, torch.float32).permute(0, 2, 3, 4, 1) + 1) / 2).reshape(BV, H, W, ci).contiguous()
+        a = ops.im2col_nhwc(img01, 7, 7, 1, 3, k_pad=self._merger_k)
+        merged = ops.gemm(a, w["gh.merger.w"], w["gh.merger.b"], act="relu")
+        del a
+        g = self._dpt_trunk("gh.", inters, BV, gh, gw, tb)
+        del inters
+        g = ops.bilinear_nhwc(g, H, W, add=merged, pos_x=tb.full_px, pos_y=tb.full_py)
+        del merged
+        gfeat = self._conv3(g, w["gh.oc2a.w"], w["gh.oc2a.b"], act="relu")
+        del g
+        raw = ops.gemm(gfeat.view(BV * H * W, -1), w["gh.oc2b.w"], w["gh.oc2b.b"])
+        del gfeat
+        # --- fused depth activation + unprojection + Gaussian adapter
+        o = ops.gaussian_epilogue(dfeat.view(BV * H * W, -1), w["dh.oc2b.w"], self._depth_b, raw, cams["extr"], cams["intr"], w["sh_mask"], BV, H, W)
+        N = V * H * W
+        gauss = Gaussians(means=o["means"].view(B, N, 3), covariances=o["covariances"].view(B, N, 3, 3),
+                          harmonics=o["harmonics"].view(B, N, 3, cfg.d_sh), opacities=o["opacities"].view(B, N),
+                          scales=o["scales"].view(B, N, 3), rotations=o["rotations"].view(B, N, 4))
+        scene_scale = (o["scene_sum"] / float(BV * H * W)).clamp_min(1e-8).reshape(())
+        return EncoderOutput(
+            gaussians=gauss,
+            pred_pose_enc_list=pose_list,
+            pred_context_pose=dict(extrinsic=cams["c2w"].view(B, V, 4, 4), intrinsic=cams["intr_norm"].view(B, V, 3, 3)),
+            depth_dict=dict(depth=o["depth"].view(B, V, H, W, 1), conf_valid_mask=torch.ones((B, V, H, W), dtype=torch.bool, device=dev)),
+            infos=dict(scene_scale=scene_scale, voxelize_ratio=float(N) / (H * W * V)),
+            distill_infos=None,
+            last_pred_pose_enc=pose_list[-1],
+        )
+
+    def forward(self, *a, **k):
+        raise NotImplementedError("StitchVAE3D.forward (VAE encode of images) is outside the text-to-3D hot path; call forward_with_latent")
