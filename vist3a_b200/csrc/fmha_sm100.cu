@@ -1,20 +1,26 @@
 // tcgen05 fused attention forward (non-causal, no mask):  O = softmax(Q K^T * scale) V
 //
-// One CTA per (batch, head, 256-row query block) = TWO 128-row query tiles processed in ping-pong, so the
-// tensor pipe works on one tile while the softmax of the other runs (MUFU.EX2 is the co-bottleneck of
-// attention on this part: 128x128 exponentials cost as many SM cycles as the 2 MMAs of a d=128 tile).
-//   warp 0        TMA producer: Q tiles once, then K and V tiles of 128 keys through mbarrier rings
-//   warp 1        MMA issuer:   S_i = Q_i K^T (SS) into TMEM,  O_i += P_i V (TS: P from TMEM, V MN-major smem)
+// One CTA per (batch, head, 256-row query block) = TWO independent 128-row query tiles; each tile has its own MMA
+// issuing warp and its own softmax warpgroup, so the tiles never wait for each other.
+//   warp 0        TMA producer: Q tiles once, then K and V tiles of BKV keys through mbarrier rings
+//   warp 1 / 3    MMA issuer of query tile 0 / 1:  S = Q K^T (SS) into TMEM,  O += P V (TS: P from TMEM, V MN-major smem).
+//                 The whole warp runs the warp-uniform control flow, one elected lane issues: descriptors stay in
+//                 uniform registers (no per-MMA R2UR / elect waterfall).
 //   warp 2        TMEM allocator
-//   warps 4..7    softmax of query tile 0   } thread t owns query row t (TMEM lane t): tcgen05.ld S, online
-//   warps 8..11   softmax of query tile 1   } max with lazy rescale of O (only when the running max grows by
-//                                             more than 2^8), FFMA2 + MUFU.EX2, bf16 P -> tcgen05.st
-// TMEM map (512 columns), d = 128:  S0|P0 [0,128)  S1|P1 [128,256)  O0 [256,384)  O1 [384,512)
-//     P_i overwrites the first 64 columns of S_i; the in-order tensor pipe makes QK(j+1) wait for PV(j).
-//                         d = 64:   S0 [0,128) S1 [128,256) P0 [256,320) P1 [320,384) O0 [384,448) O1 [448,512)
-//     P has its own columns, so QK_i(j+1) is issued as soon as the softmax warps have pulled S_i(j) into
-//     registers and the score tile of step j+1 is ready before the exponentials of step j are done.
-// Control warps shrink to 56 registers (setmaxnreg) so that each softmax thread can hold its 128-wide row.
+//   warps 4..7    softmax of query tile 0   } thread t owns query row t (TMEM lane t): tcgen05.ld S, online max with
+//   warps 8..11   softmax of query tile 1   } lazy rescale of O (only when the running max grows by more than 2^8),
+//                                             exponentials, bf16 P -> tcgen05.st
+// MUFU.EX2 is the co-bottleneck of attention on this part (16 results/clk/SM: a 128x128 score tile costs as many SM
+// cycles in exponentials as its two d=128 MMAs, twice as many at d=64).  Hence:
+//   * the score tile of the next step is always produced while the warpgroup is still exponentiating the current one
+//       d=128: 64 keys per step, S double-buffered, P(j) overwrites the buffer S(j) came from; the in-order tensor pipe
+//              orders QK(j+2) behind P(j) V, so no "S free" handshake exists at all
+//       d=64:  128 keys per step, S and P in separate columns; QK(j+1) is issued as soon as the softmax warps have pulled
+//              S(j) into registers;
+//   * kPoly of every 8 column pairs take their exp2 on the FMA pipe (Cody-Waite split + degree-3 minimax polynomial,
+//     rel. error 1e-4 << bf16 rounding of P) instead of the MUFU.
+// TMEM map, 256 columns per query tile:  d=128: S0|P0 [0,64)  S1|P1 [64,128)  O [128,256)
+//                                        d=64:  S [0,128)  P [128,192)  O [192,256)
 #include "common.cuh"
 #include "host_util.cuh"
 
@@ -29,18 +35,27 @@ struct FmhaParams {
 
 template <int D>
 struct FmhaCfg {
-  static constexpr int BQ = 128, BKV = 128, QT = 2;  // two query tiles per CTA
+  static constexpr int BQ = 128, QT = 2;             // two query tiles per CTA
+  static constexpr int BKV = (D == 128) ? 64 : 128;  // keys per step
+  static constexpr bool ALIAS = (D == 128);          // P(j) overwrites S(j)
+  static constexpr int NSB = ALIAS ? 2 : 1;          // score buffers per query tile
   static constexpr int SLABS = D / 64;               // 64-element (128-byte) column slabs
-  static constexpr int SLAB_BYTES = 128 * 128;       // 128 rows x 128 B
-  static constexpr int TILE_BYTES = SLABS * SLAB_BYTES;
-  static constexpr bool ALIAS = (D == 128);
-  static constexpr int KV_STAGES = (D == 128) ? 2 : 4;
-  static constexpr int NBARS = 1 + 4 * KV_STAGES + 8;
-  static constexpr int SMEM_BYTES = TILE_BYTES * (QT + 2 * KV_STAGES) + 1024 + 8 * NBARS + 16;
+  static constexpr int Q_SLAB_BYTES = BQ * 128;
+  static constexpr int KV_SLAB_BYTES = BKV * 128;
+  static constexpr int Q_TILE_BYTES = SLABS * Q_SLAB_BYTES;
+  static constexpr int KV_TILE_BYTES = SLABS * KV_SLAB_BYTES;   // 16 KB either way
+  static constexpr int KV_STAGES = 4;
+  static constexpr int PT = NSB + 1 + 4;             // barriers per query tile: s_full[NSB], s_free, p_full[2], pv_done[2]
+  static constexpr int NBARS = 1 + 4 * KV_STAGES + 2 * PT;
+  static constexpr int SMEM_BYTES = Q_TILE_BYTES * QT + KV_TILE_BYTES * 2 * KV_STAGES + 1024 + 8 * NBARS + 16;
+  static constexpr uint32_t TILE_COLS = 256;
   static constexpr uint32_t TM_S = 0;
-  static constexpr uint32_t TM_P = ALIAS ? 0 : 256;
-  static constexpr uint32_t P_STRIDE = ALIAS ? 128 : 64;
-  static constexpr uint32_t TM_O = ALIAS ? 256 : 384;
+  static constexpr uint32_t S_STRIDE = 64;           // between the NSB score buffers (ALIAS only)
+  static constexpr uint32_t TM_P = ALIAS ? 0 : 128;
+  static constexpr uint32_t P_STRIDE = ALIAS ? 64 : 0;
+  static constexpr uint32_t TM_O = ALIAS ? 128 : 192;
+  static constexpr int POLY = 2;                     // of every 8 column pairs, this many use the FMA-pipe exp2
+  static_assert(TM_O + D <= TILE_COLS, "TMEM budget");
 };
 
 constexpr int kFmhaThreads = 384;
@@ -50,17 +65,38 @@ __device__ __forceinline__ float ex2_approx(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-// (y0, y1) = (x0, x1) * (c, c) + (b, b) as one packed FFMA2
-__device__ __forceinline__ void fma2(float x0, float x1, uint64_t cc, uint64_t bb, float& y0, float& y1) {
-  uint64_t xx, yy;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(xx) : "f"(x0), "f"(x1));
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(yy) : "l"(xx), "l"(cc), "l"(bb));
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(y0), "=f"(y1) : "l"(yy));
-}
-__device__ __forceinline__ uint64_t splat2(float v) {
+__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
   uint64_t r;
-  asm("mov.b64 %0, {%1, %1};" : "=l"(r) : "f"(v));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
   return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {  // packed 2 x fp32 FFMA2
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+// exp2 of two values on the FMA / ALU pipes: y = n + f (n integer, |f| <= 0.5), 2^f by a degree-3 minimax polynomial
+// (max rel. error 1.0e-4), 2^n by adding n to the exponent field.  y is clamped to >= -126.
+__device__ __forceinline__ void exp2_poly2(float y0, float y1, float& e0, float& e1) {
+  const uint64_t one = pack2(1.0f, 1.0f);
+  const uint64_t magic = pack2(12582912.0f, 12582912.0f);      // 1.5 * 2^23: rounds to nearest integer
+  const uint64_t nmagic = pack2(-12582912.0f, -12582912.0f);
+  const uint64_t neg1 = pack2(-1.0f, -1.0f);
+  const uint64_t yy = pack2(fmaxf(y0, -126.0f), fmaxf(y1, -126.0f));
+  const uint64_t t = fma2(yy, one, magic);
+  const uint64_t n = fma2(t, one, nmagic);
+  const uint64_t f = fma2(n, neg1, yy);
+  uint64_t q = fma2(f, pack2(0.055008664727211f, 0.055008664727211f), pack2(0.24221056699752808f, 0.24221056699752808f));
+  q = fma2(q, f, pack2(0.6932829022407532f, 0.6932829022407532f));
+  q = fma2(q, f, one);
+  float t0, t1, q0, q1;
+  unpack2(t, t0, t1);
+  unpack2(q, q0, q1);
+  e0 = __int_as_float(__float_as_int(q0) + (__float_as_int(t0) << 23));
+  e1 = __int_as_float(__float_as_int(q1) + (__float_as_int(t1) << 23));
 }
 
 template <int D>
@@ -69,21 +105,25 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 const __grid_constant__ CUtensorMap tmV, const FmhaParams p) {
   using Cfg = FmhaCfg<D>;
   constexpr int ST = Cfg::KV_STAGES;
+  constexpr int NSB = Cfg::NSB;
+  constexpr int BKV = Cfg::BKV;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  auto smem_q = [&](int i) { return smem_base + Cfg::TILE_BYTES * i; };
-  auto smem_k = [&](int s) { return smem_base + Cfg::TILE_BYTES * (Cfg::QT + s); };
-  auto smem_v = [&](int s) { return smem_base + Cfg::TILE_BYTES * (Cfg::QT + ST + s); };
-  const uint32_t bar_base = smem_base + Cfg::TILE_BYTES * (Cfg::QT + 2 * ST);
+  auto smem_q = [&](int i) { return smem_base + Cfg::Q_TILE_BYTES * i; };
+  auto smem_k = [&](int s) { return smem_base + Cfg::Q_TILE_BYTES * Cfg::QT + Cfg::KV_TILE_BYTES * s; };
+  auto smem_v = [&](int s) { return smem_base + Cfg::Q_TILE_BYTES * Cfg::QT + Cfg::KV_TILE_BYTES * (ST + s); };
+  const uint32_t bar_base = smem_base + Cfg::Q_TILE_BYTES * Cfg::QT + Cfg::KV_TILE_BYTES * 2 * ST;
   const uint32_t q_full = bar_base;
   auto k_full = [&](int s) { return bar_base + 8u * (1 + s); };
   auto k_empty = [&](int s) { return bar_base + 8u * (1 + ST + s); };
   auto v_full = [&](int s) { return bar_base + 8u * (1 + 2 * ST + s); };
   auto v_empty = [&](int s) { return bar_base + 8u * (1 + 3 * ST + s); };
-  auto s_full = [&](int i) { return bar_base + 8u * (1 + 4 * ST + i); };
-  auto s_free = [&](int i) { return bar_base + 8u * (3 + 4 * ST + i); };
-  auto p_full = [&](int i) { return bar_base + 8u * (5 + 4 * ST + i); };
-  auto pv_done = [&](int i) { return bar_base + 8u * (7 + 4 * ST + i); };
+  // Per query tile.  p_full / pv_done alternate between two barriers (step parity) so that a waiter is never two
+  // completions behind the barrier it polls (mbarrier parity waits only distinguish the current and the previous phase).
+  auto s_full = [&](int i, int b) { return bar_base + 8u * (1 + 4 * ST + i * Cfg::PT + b); };
+  auto s_free = [&](int i) { return bar_base + 8u * (1 + 4 * ST + i * Cfg::PT + NSB); };
+  auto p_full = [&](int i, int b) { return bar_base + 8u * (1 + 4 * ST + i * Cfg::PT + NSB + 1 + b); };
+  auto pv_done = [&](int i, int b) { return bar_base + 8u * (1 + 4 * ST + i * Cfg::PT + NSB + 3 + b); };
   const uint32_t tmem_slot = bar_base + 8u * Cfg::NBARS;
 
   const uint32_t warp = warp_id_sync();
@@ -91,7 +131,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const int q0 = blockIdx.x * (Cfg::BQ * Cfg::QT);
   const int head = blockIdx.y;
   const int batch = blockIdx.z;
-  const int n_kv = (p.len_kv + Cfg::BKV - 1) / Cfg::BKV;
+  const int n_kv = (p.len_kv + BKV - 1) / BKV;
   const int nq = (q0 + Cfg::BQ < p.len_q) ? 2 : 1;  // query tiles of this CTA that hold at least one row
 
   if (warp == 0 && lane == 0) {
@@ -103,15 +143,17 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     mbar_init(q_full, 1);
     for (int s = 0; s < ST; ++s) {
       mbar_init(k_full(s), 1);
-      mbar_init(k_empty(s), 1);
+      mbar_init(k_empty(s), (uint32_t)nq);  // one commit per MMA warp
       mbar_init(v_full(s), 1);
-      mbar_init(v_empty(s), 1);
+      mbar_init(v_empty(s), (uint32_t)nq);
     }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(s_full(i), 1);
+      for (int b = 0; b < NSB; ++b) mbar_init(s_full(i, b), 1);
       mbar_init(s_free(i), 4);  // one arrival per softmax warp of the tile
-      mbar_init(p_full(i), 4);
-      mbar_init(pv_done(i), 1);
+      for (int b = 0; b < 2; ++b) {
+        mbar_init(p_full(i, b), 4);
+        mbar_init(pv_done(i, b), 1);
+      }
     }
     fence_barrier_init();
   }
@@ -123,137 +165,157 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
   if (warp < 4) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
-    if (warp == 0 && lane == 0) {
-      // ------------------------------ TMA producer ------------------------------
-      mbar_expect_tx(q_full, (uint32_t)(nq * Cfg::TILE_BYTES));
-      for (int i = 0; i < nq; ++i) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+    if (warp == 0) {
+      // ------------------------------ TMA producer (warp-uniform control flow, one elected lane issues) ---------
+      if (elect_one()) {
+        mbar_expect_tx(q_full, (uint32_t)(nq * Cfg::Q_TILE_BYTES));
+        for (int i = 0; i < nq; ++i) {
 #pragma unroll
-        for (int sl = 0; sl < Cfg::SLABS; ++sl)
-          tma_load_4d(smem_q(i) + sl * Cfg::SLAB_BYTES, &tmQ, q_full, sl * 64, head, q0 + i * Cfg::BQ, batch);
+          for (int sl = 0; sl < Cfg::SLABS; ++sl)
+            tma_load_4d(smem_q(i) + sl * Cfg::Q_SLAB_BYTES, &tmQ, q_full, sl * 64, head, q0 + i * Cfg::BQ, batch);
+        }
       }
+      __syncwarp();
       int s = 0;
       uint32_t ph = 0;
       for (int j = 0; j < n_kv; ++j) {
         mbar_wait(k_empty(s), ph ^ 1u);
-        mbar_expect_tx(k_full(s), Cfg::TILE_BYTES);
+        if (elect_one()) {
+          mbar_expect_tx(k_full(s), Cfg::KV_TILE_BYTES);
 #pragma unroll
-        for (int sl = 0; sl < Cfg::SLABS; ++sl)
-          tma_load_4d(smem_k(s) + sl * Cfg::SLAB_BYTES, &tmK, k_full(s), sl * 64, head, j * Cfg::BKV, batch);
+          for (int sl = 0; sl < Cfg::SLABS; ++sl)
+            tma_load_4d(smem_k(s) + sl * Cfg::KV_SLAB_BYTES, &tmK, k_full(s), sl * 64, head, j * BKV, batch);
+        }
+        __syncwarp();
         mbar_wait(v_empty(s), ph ^ 1u);
-        mbar_expect_tx(v_full(s), Cfg::TILE_BYTES);
+        if (elect_one()) {
+          mbar_expect_tx(v_full(s), Cfg::KV_TILE_BYTES);
 #pragma unroll
-        for (int sl = 0; sl < Cfg::SLABS; ++sl)
-          tma_load_4d(smem_v(s) + sl * Cfg::SLAB_BYTES, &tmV, v_full(s), sl * 64, head, j * Cfg::BKV, batch);
+          for (int sl = 0; sl < Cfg::SLABS; ++sl)
+            tma_load_4d(smem_v(s) + sl * Cfg::KV_SLAB_BYTES, &tmV, v_full(s), sl * 64, head, j * BKV, batch);
+        }
+        __syncwarp();
         if (++s == ST) { s = 0; ph ^= 1u; }
       }
-    } else if (warp == 1 && lane == 0) {
-      // ------------------------------ MMA issuer ------------------------------
-      constexpr uint32_t idesc_qk = make_idesc(kFmtBF16, 128, 128, 0, 0);
+    } else if (warp != 2 && (int)(warp >> 1) < nq) {
+      // ------------------------------ MMA issuer of query tile i ------------------------------
+      const int i = (int)(warp >> 1);  // warp 1 -> tile 0, warp 3 -> tile 1
+      constexpr uint32_t idesc_qk = make_idesc(kFmtBF16, 128, BKV, 0, 0);
       constexpr uint32_t idesc_pv = make_idesc(kFmtBF16, 128, D, 0, 1);  // B (V) is MN-major
-      auto issue_qk = [&](int i, int j) {
-        const int s = j % ST;
-        mbar_wait(k_full(s), (uint32_t)(j / ST) & 1u);
+      const uint32_t t_base = tmem_base + (uint32_t)i * Cfg::TILE_COLS;
+      const uint64_t qdesc = make_smem_desc_sw128(smem_q(i), 1024, 0);
+      auto issue_qk = [&](int j, int s, uint32_t ph) {  // (s, ph) = ring slot / phase of key tile j
+        mbar_wait(k_full(s), ph);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + Cfg::TM_S + (uint32_t)(i * 128);
+        if (elect_one()) {
+          const uint32_t d_tmem = t_base + Cfg::TM_S + (uint32_t)(j % NSB) * Cfg::S_STRIDE;
+          const uint64_t bdesc = make_smem_desc_sw128(smem_k(s), 1024, 0);
 #pragma unroll
-        for (int kk = 0; kk < D / 16; ++kk) {
-          const uint32_t off = (uint32_t)((kk >> 2) * Cfg::SLAB_BYTES + (kk & 3) * 32);
-          const uint64_t adesc = make_smem_desc_sw128(smem_q(i) + off, 1024, 0);
-          const uint64_t bdesc = make_smem_desc_sw128(smem_k(s) + off, 1024, 0);
-          umma_f16_ss<1>(d_tmem, adesc, bdesc, idesc_qk, kk ? 1u : 0u);
+          for (int kk = 0; kk < D / 16; ++kk) {
+            // +32 B along K inside a swizzle atom = +2 in the (addr >> 4) field; next 64-wide slab = + SLAB_BYTES
+            const uint64_t ao = (uint64_t)(((kk >> 2) * Cfg::Q_SLAB_BYTES + (kk & 3) * 32) >> 4);
+            const uint64_t bo = (uint64_t)(((kk >> 2) * Cfg::KV_SLAB_BYTES + (kk & 3) * 32) >> 4);
+            umma_f16_ss<1>(d_tmem, qdesc + ao, bdesc + bo, idesc_qk, kk ? 1u : 0u);
+          }
+          umma_commit(s_full(i, j % NSB));
+          umma_commit(k_empty(s));
         }
-        umma_commit(s_full(i));
-        if (i == nq - 1) umma_commit(k_empty(s));
+        __syncwarp();
       };
-      auto issue_pv = [&](int i, int j) {
-        const int s = j % ST;
-        mbar_wait(v_full(s), (uint32_t)(j / ST) & 1u);
+      auto issue_pv = [&](int j, int s, uint32_t ph) {
+        mbar_wait(v_full(s), ph);
         tc_fence_after();
-        const uint32_t o_tmem = tmem_base + Cfg::TM_O + (uint32_t)(i * D);
-        const uint32_t p_tmem = tmem_base + Cfg::TM_P + (uint32_t)(i * Cfg::P_STRIDE);
-#pragma unroll
-        for (int kk = 0; kk < Cfg::BKV / 16; ++kk) {
+        if (elect_one()) {
+          const uint32_t p_tmem = t_base + Cfg::TM_P + (uint32_t)(j & 1) * Cfg::P_STRIDE;
           // V tile: kv rows at a 128 B pitch (K dimension), 64-wide head-dim slabs LBO apart (MN dimension)
-          const uint64_t bdesc = make_smem_desc_sw128(smem_v(s) + kk * 2048, 1024, Cfg::SLAB_BYTES);
-          umma_f16_ts(o_tmem, p_tmem + (uint32_t)(kk * 8), bdesc, idesc_pv, (j | kk) ? 1u : 0u);
+          const uint64_t bdesc = make_smem_desc_sw128(smem_v(s), 1024, Cfg::KV_SLAB_BYTES);
+#pragma unroll
+          for (int kk = 0; kk < BKV / 16; ++kk)
+            umma_f16_ts(t_base + Cfg::TM_O, p_tmem + (uint32_t)(kk * 8), bdesc + (uint64_t)((kk * 2048) >> 4), idesc_pv, (j | kk) ? 1u : 0u);
+          umma_commit(pv_done(i, j & 1));
+          umma_commit(v_empty(s));
         }
-        umma_commit(pv_done(i));
-        if (i == nq - 1) umma_commit(v_empty(s));
+        __syncwarp();
       };
       mbar_wait(q_full, 0);
-      for (int i = 0; i < nq; ++i) issue_qk(i, 0);
+      int qs = 0, vs = 0;  // ring positions of the key tile the next QK / PV reads
+      uint32_t qph = 0, vph = 0;
+      auto adv = [&](int& s_, uint32_t& ph_) { if (++s_ == ST) { s_ = 0; ph_ ^= 1u; } };
+      for (int j = 0; j < NSB && j < n_kv; ++j) {
+        issue_qk(j, qs, qph);
+        adv(qs, qph);
+      }
       for (int j = 0; j < n_kv; ++j) {
-        const uint32_t ph = (uint32_t)j & 1u;
-        const bool more = j + 1 < n_kv;
-        for (int i = 0; i < nq; ++i) {
-          if (!Cfg::ALIAS && more) {
-            mbar_wait(s_free(i), ph);  // softmax warps hold S_i(j) in registers
-            tc_fence_after();
-            issue_qk(i, j + 1);
-          }
-          mbar_wait(p_full(i), ph);
+        const bool more = j + NSB < n_kv;
+        if (!Cfg::ALIAS && more) {
+          mbar_wait(s_free(i), (uint32_t)j & 1u);  // the softmax warps hold S(j) in registers
           tc_fence_after();
-          issue_pv(i, j);
-          if (Cfg::ALIAS && more) issue_qk(i, j + 1);  // overwrites S_i|P_i: ordered behind P_i V by the in-order pipe
+          issue_qk(j + 1, qs, qph);
+          adv(qs, qph);
+        }
+        mbar_wait(p_full(i, j & 1), (uint32_t)(j >> 1) & 1u);
+        tc_fence_after();
+        issue_pv(j, vs, vph);
+        adv(vs, vph);
+        if (Cfg::ALIAS && more) {  // overwrites S(j)|P(j): ordered behind P(j) V by the in-order tensor pipe
+          issue_qk(j + 2, qs, qph);
+          adv(qs, qph);
         }
       }
     }
   } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
     // ------------------------------ softmax / correction / epilogue ------------------------------
     const int i = (int)(warp >> 2) - 1;  // query tile of this warpgroup
     if (i < nq) {
       const uint32_t wq = warp & 3u;     // TMEM lane quadrant this warp may access
-      const uint32_t lane_sel = (wq * 32u) << 16;
+      const uint32_t tile_base = tmem_base + ((wq * 32u) << 16) + (uint32_t)i * Cfg::TILE_COLS;
       const int row = q0 + i * Cfg::BQ + (int)(wq * 32u + lane);
-      const uint32_t s_addr = tmem_base + lane_sel + Cfg::TM_S + (uint32_t)(i * 128);
-      const uint32_t p_addr = tmem_base + lane_sel + Cfg::TM_P + (uint32_t)(i * Cfg::P_STRIDE);
-      const uint32_t o_addr = tmem_base + lane_sel + Cfg::TM_O + (uint32_t)(i * D);
+      const uint32_t o_addr = tile_base + Cfg::TM_O;
       float m_run = -INFINITY;  // running (possibly stale) row max of raw scores
       float l_run = 0.0f;       // running row sum of exp2((s - m_run) * scale_log2)
       const float c = p.scale_log2;
-      const uint64_t cc2 = splat2(c);
+      const uint64_t cc2 = pack2(c, c);
       for (int j = 0; j < n_kv; ++j) {
-        const uint32_t ph = (uint32_t)j & 1u;
-        mbar_wait(s_full(i), ph);
+        const int sb = j % NSB;
+        mbar_wait(s_full(i, sb), (uint32_t)(j / NSB) & 1u);
         tc_fence_after();
-        uint32_t r[128];
-        tmem_ld_x32(s_addr, r);
-        tmem_ld_x32(s_addr + 32, r + 32);
-        tmem_ld_x32(s_addr + 64, r + 64);
-        tmem_ld_x32(s_addr + 96, r + 96);
+        uint32_t r[BKV];
+        const uint32_t s_addr = tile_base + Cfg::TM_S + (uint32_t)sb * Cfg::S_STRIDE;
+#pragma unroll
+        for (int cb = 0; cb < BKV / 32; ++cb) tmem_ld_x32(s_addr + (uint32_t)(cb * 32), r + cb * 32);
         tmem_ld_wait();
         if (!Cfg::ALIAS) {
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(s_free(i));
         }
-        const int valid = p.len_kv - j * Cfg::BKV;  // keys of this tile that exist
-        if (valid < Cfg::BKV) {
+        const int valid = p.len_kv - j * BKV;  // keys of this tile that exist
+        if (valid < BKV) {
 #pragma unroll
-          for (int k = 0; k < 128; ++k)
+          for (int k = 0; k < BKV; ++k)
             if (k >= valid) r[k] = 0xff800000u;  // -inf
         }
         float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-        for (int k = 0; k < 128; k += 8) {
+        for (int k = 0; k < BKV; k += 8) {
 #pragma unroll
           for (int u = 0; u < 4; ++u)
             mx[u] = fmaxf(fmaxf(mx[u], __uint_as_float(r[k + 2 * u])), __uint_as_float(r[k + 2 * u + 1]));
         }
         const float m_new = fmaxf(m_run, fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])));
+        // d=64: the single P buffer is read by P(j-1) V.  (d=128: the commit behind s_full of this step covers P(j-2) V,
+        // the last reader of the buffer S(j) | P(j) lives in.)
+        if (!Cfg::ALIAS && j >= 1) mbar_wait(pv_done(i, (j - 1) & 1), (uint32_t)((j - 1) >> 1) & 1u);
         if (j == 0) {
           m_run = m_new;
         } else {
-          if (!Cfg::ALIAS) {
-            // P_i is read by P_i(j-1) V and O_i is accumulated by it: both must be finished before we touch them.
-            // (d = 128: the commit behind s_full(i) of this step already covers that MMA.)
-            mbar_wait(pv_done(i), ph ^ 1u);
-            tc_fence_after();
-          }
           const bool need = (m_new - m_run) * c > 8.0f;
           if (__any_sync(0xffffffffu, need)) {
+            // O is accumulated by P(j-1) V: it must have finished before the rows are rescaled
+            if (Cfg::ALIAS) mbar_wait(pv_done(i, (j - 1) & 1), (uint32_t)((j - 1) >> 1) & 1u);
+            tc_fence_after();
             const float f = need ? ex2_approx((m_run - m_new) * c) : 1.0f;
             if (need) m_run = m_new;
             l_run *= f;
@@ -269,16 +331,24 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             tmem_st_wait();
           }
         }
-        const uint64_t mc2 = splat2(-m_run * c);
+        tc_fence_after();
+        const float nmc = -m_run * c;
+        const uint64_t mc2 = pack2(nmc, nmc);
         float sum[4] = {0.f, 0.f, 0.f, 0.f};
+        const uint32_t p_addr = tile_base + Cfg::TM_P + (uint32_t)(j & 1) * Cfg::P_STRIDE;
 #pragma unroll
-        for (int cb = 0; cb < 4; ++cb) {
+        for (int cb = 0; cb < BKV / 32; ++cb) {
           uint32_t pk[16];
 #pragma unroll
           for (int k = 0; k < 16; ++k) {
-            float y0, y1;
-            fma2(__uint_as_float(r[cb * 32 + 2 * k]), __uint_as_float(r[cb * 32 + 2 * k + 1]), cc2, mc2, y0, y1);
-            const float e0 = ex2_approx(y0), e1 = ex2_approx(y1);
+            float y0, y1, e0, e1;
+            unpack2(fma2(pack2(__uint_as_float(r[cb * 32 + 2 * k]), __uint_as_float(r[cb * 32 + 2 * k + 1])), cc2, mc2), y0, y1);
+            if ((k & 7) < Cfg::POLY) {
+              exp2_poly2(y0, y1, e0, e1);
+            } else {
+              e0 = ex2_approx(y0);
+              e1 = ex2_approx(y1);
+            }
             sum[(2 * k) & 3] += e0;
             sum[(2 * k + 1) & 3] += e1;
             pk[k] = pack_bf16(e0, e1);
@@ -289,10 +359,10 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(p_full(i));
+        if (lane == 0) mbar_arrive(p_full(i, j & 1));
       }
       // ---- epilogue: O / l -> bf16 -> global ----
-      mbar_wait(pv_done(i), (uint32_t)(n_kv - 1) & 1u);
+      mbar_wait(pv_done(i, (n_kv - 1) & 1), (uint32_t)((n_kv - 1) >> 1) & 1u);  // the commit covers every earlier MMA too
       tc_fence_after();
       const float inv_l = 1.0f / l_run;
       __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(p.O) + (long long)batch * p.o_bs + (long long)row * p.o_rs +
@@ -327,11 +397,11 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
 
 static int make_qkv_map(CUtensorMap* tm, const void* ptr, long long B, long long H, long long L, long long D,
-                        long long bs, long long rs, long long hs) {
+                        long long bs, long long rs, long long hs, uint32_t box_rows) {
   // dims (fastest first): head_dim, heads, rows, batch
   uint64_t dims[4] = {(uint64_t)D, (uint64_t)H, (uint64_t)L, (uint64_t)B};
   uint64_t strides[3] = {(uint64_t)hs * 2, (uint64_t)rs * 2, (uint64_t)bs * 2};
-  uint32_t box[4] = {64, 1, 128, 1};
+  uint32_t box[4] = {64, 1, box_rows, 1};
   return encode_tensor_map(tm, ptr, 2, false, 4, dims, strides, box, true);
 }
 
@@ -340,9 +410,9 @@ static int launch_fmha(const vist3a_fmha_args& a, cudaStream_t stream) {
   using Cfg = FmhaCfg<D>;
   CUtensorMap tmQ, tmK, tmV;
   int rc;
-  if ((rc = make_qkv_map(&tmQ, a.Q, a.batch, a.heads, a.len_q, D, a.q_bs, a.q_rs, a.q_hs))) return rc;
-  if ((rc = make_qkv_map(&tmK, a.K, a.batch, a.heads, a.len_kv, D, a.k_bs, a.k_rs, a.k_hs))) return rc;
-  if ((rc = make_qkv_map(&tmV, a.V, a.batch, a.heads, a.len_kv, D, a.v_bs, a.v_rs, a.v_hs))) return rc;
+  if ((rc = make_qkv_map(&tmQ, a.Q, a.batch, a.heads, a.len_q, D, a.q_bs, a.q_rs, a.q_hs, Cfg::BQ))) return rc;
+  if ((rc = make_qkv_map(&tmK, a.K, a.batch, a.heads, a.len_kv, D, a.k_bs, a.k_rs, a.k_hs, Cfg::BKV))) return rc;
+  if ((rc = make_qkv_map(&tmV, a.V, a.batch, a.heads, a.len_kv, D, a.v_bs, a.v_rs, a.v_hs, Cfg::BKV))) return rc;
   FmhaParams p;
   p.O = a.O; p.o_bs = a.o_bs; p.o_rs = a.o_rs; p.o_hs = a.o_hs;
   p.len_q = (int)a.len_q; p.len_kv = (int)a.len_kv;
