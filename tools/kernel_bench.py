@@ -35,6 +35,7 @@ def main():
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--no-torch", action="store_true")
     ap.add_argument("--no-flush", action="store_true")
+    ap.add_argument("--fmha-flags", type=int, default=0)
     a = ap.parse_args()
     flush = None if a.no_flush else torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     res = []
@@ -68,7 +69,7 @@ def main():
         v = torch.randn(B, Lk, H, D, device="cuda").bfloat16()
         o = torch.empty_like(q)
         fl = 4 * B * H * Lq * Lk * D
-        ms = timeit(lambda: ops.fmha(q, k, v, out=o), a.iters, flush=flush)
+        ms = timeit(lambda: ops.fmha(q, k, v, out=o, flags=a.fmha_flags), a.iters, flush=flush)
         r = {"name": name, "B": B, "H": H, "Lq": Lq, "Lk": Lk, "D": D, "ms": round(ms, 4), "tflops": round(fl / ms / 1e9, 1)}
         if not a.no_torch:
             qt, kt, vt = (t.transpose(1, 2) for t in (q, k, v))

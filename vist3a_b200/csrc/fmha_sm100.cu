@@ -33,18 +33,18 @@ struct FmhaParams {
   float scale_log2;  // scale * log2(e)
 };
 
-template <int D>
+template <int D, int BKV_, int POLY_>
 struct FmhaCfg {
   static constexpr int BQ = 128, QT = 2;             // two query tiles per CTA
-  static constexpr int BKV = (D == 128) ? 64 : 128;  // keys per step
+  static constexpr int BKV = BKV_;                   // keys per step
   static constexpr bool ALIAS = (D == 128);          // P(j) overwrites S(j)
-  static constexpr int NSB = ALIAS ? 2 : 1;          // score buffers per query tile
+  static constexpr int NSB = (ALIAS && BKV == 64) ? 2 : 1;  // score buffers per query tile
   static constexpr int SLABS = D / 64;               // 64-element (128-byte) column slabs
   static constexpr int Q_SLAB_BYTES = BQ * 128;
   static constexpr int KV_SLAB_BYTES = BKV * 128;
   static constexpr int Q_TILE_BYTES = SLABS * Q_SLAB_BYTES;
   static constexpr int KV_TILE_BYTES = SLABS * KV_SLAB_BYTES;   // 16 KB either way
-  static constexpr int KV_STAGES = 4;
+  static constexpr int KV_STAGES = KV_TILE_BYTES > 16384 ? 2 : 4;
   static constexpr int PT = NSB + 1 + 4;             // barriers per query tile: s_full[NSB], s_free, p_full[2], pv_done[2]
   static constexpr int NBARS = 1 + 4 * KV_STAGES + 2 * PT;
   static constexpr int SMEM_BYTES = Q_TILE_BYTES * QT + KV_TILE_BYTES * 2 * KV_STAGES + 1024 + 8 * NBARS + 16;
@@ -52,9 +52,10 @@ struct FmhaCfg {
   static constexpr uint32_t TM_S = 0;
   static constexpr uint32_t S_STRIDE = 64;           // between the NSB score buffers (ALIAS only)
   static constexpr uint32_t TM_P = ALIAS ? 0 : 128;
-  static constexpr uint32_t P_STRIDE = ALIAS ? 64 : 0;
+  static constexpr uint32_t P_STRIDE = (NSB == 2) ? 64 : 0;
   static constexpr uint32_t TM_O = ALIAS ? 128 : 192;
-  static constexpr int POLY = 2;                     // of every 8 column pairs, this many use the FMA-pipe exp2
+  static_assert(D == 128 || BKV == 128, "d=64 runs 128-key steps");
+  static constexpr int POLY = POLY_;                     // of every 8 column pairs, this many use the FMA-pipe exp2
   static_assert(TM_O + D <= TILE_COLS, "TMEM budget");
 };
 
@@ -99,11 +100,11 @@ __device__ __forceinline__ void exp2_poly2(float y0, float y1, float& e0, float&
   e1 = __int_as_float(__float_as_int(q1) + (__float_as_int(t1) << 23));
 }
 
-template <int D>
+template <int D, int BKV_, int POLY_>
 __global__ void __launch_bounds__(kFmhaThreads, 1)
 fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const FmhaParams p) {
-  using Cfg = FmhaCfg<D>;
+  using Cfg = FmhaCfg<D, BKV_, POLY_>;
   constexpr int ST = Cfg::KV_STAGES;
   constexpr int NSB = Cfg::NSB;
   constexpr int BKV = Cfg::BKV;
@@ -259,7 +260,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         issue_pv(j, vs, vph);
         adv(vs, vph);
         if (Cfg::ALIAS && more) {  // overwrites S(j)|P(j): ordered behind P(j) V by the in-order tensor pipe
-          issue_qk(j + 2, qs, qph);
+          issue_qk(j + NSB, qs, qph);
           adv(qs, qph);
         }
       }
@@ -405,9 +406,9 @@ static int make_qkv_map(CUtensorMap* tm, const void* ptr, long long B, long long
   return encode_tensor_map(tm, ptr, 2, false, 4, dims, strides, box, true);
 }
 
-template <int D>
+template <int D, int BKV_, int POLY_>
 static int launch_fmha(const vist3a_fmha_args& a, cudaStream_t stream) {
-  using Cfg = FmhaCfg<D>;
+  using Cfg = FmhaCfg<D, BKV_, POLY_>;
   CUtensorMap tmQ, tmK, tmV;
   int rc;
   if ((rc = make_qkv_map(&tmQ, a.Q, a.batch, a.heads, a.len_q, D, a.q_bs, a.q_rs, a.q_hs, Cfg::BQ))) return rc;
@@ -417,7 +418,7 @@ static int launch_fmha(const vist3a_fmha_args& a, cudaStream_t stream) {
   p.O = a.O; p.o_bs = a.o_bs; p.o_rs = a.o_rs; p.o_hs = a.o_hs;
   p.len_q = (int)a.len_q; p.len_kv = (int)a.len_kv;
   p.scale_log2 = a.scale * 1.4426950408889634f;
-  auto kern = fmha_fwd_kernel<D>;
+  auto kern = fmha_fwd_kernel<D, BKV_, POLY_>;
   static bool attr_set = false;
   if (!attr_set) {
     V3A_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
@@ -446,7 +447,9 @@ int fmha_entry(const vist3a_fmha_args* args, cudaStream_t stream) {
               "fmha: pointers must be 16-byte aligned");
   int rc = check_arch();
   if (rc) return rc;
-  return a.head_dim == 128 ? launch_fmha<128>(a, stream) : launch_fmha<64>(a, stream);
+  // exponentials on the FMA pipe per 8 column pairs: 3 at d=64 (MUFU-bound), 2 at d=128 (measured optimum on B200)
+  if (a.head_dim == 64) return launch_fmha<64, 128, 3>(a, stream);
+  return launch_fmha<128, 64, 2>(a, stream);
 }
 
 }  // namespace v3a

@@ -168,25 +168,27 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
   if (warp == 0) {
     // ------------------------------ TMA producer ------------------------------
-    if (lane == 0) {
-      int s = 0;
-      uint32_t ph = 0;
-      for (int tile = worker; tile < num_tiles; tile += num_workers) {
-        const int tm = tile % shape.tiles_m, tn = tile / shape.tiles_m;
-        const int mt = tm * kCta + (int)rank;  // this CTA's 128-row tile
-        const int m0 = mt * Cfg::BM;
-        const int n0 = tn * BN + (int)rank * Cfg::BN_LOCAL;
-        int img = 0, y0 = 0, x0 = 0;
-        if (shape.conv) {
-          const int per_img = shape.tiles_x * shape.tiles_y;
-          img = mt / per_img;
-          const int t2 = mt % per_img;
-          y0 = (t2 / shape.tiles_x) * kConvTH - shape.pad;
-          x0 = (t2 % shape.tiles_x) * kConvTW - shape.pad;
-        }
-        int cb = 0, dy = 0, dx = 0;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(empty_bar(s), ph ^ 1u);
+    // The whole warp runs the (warp-uniform) control flow and the barrier waits; one elected lane issues, so the
+    // coordinates / descriptors stay in uniform registers (no per-instruction R2UR + elect waterfall).
+    int s = 0;
+    uint32_t ph = 0;
+    for (int tile = worker; tile < num_tiles; tile += num_workers) {
+      const int tm = tile % shape.tiles_m, tn = tile / shape.tiles_m;
+      const int mt = tm * kCta + (int)rank;  // this CTA's 128-row tile
+      const int m0 = mt * Cfg::BM;
+      const int n0 = tn * BN + (int)rank * Cfg::BN_LOCAL;
+      int img = 0, y0 = 0, x0 = 0;
+      if (shape.conv) {
+        const int per_img = shape.tiles_x * shape.tiles_y;
+        img = mt / per_img;
+        const int t2 = mt % per_img;
+        y0 = (t2 / shape.tiles_x) * kConvTH - shape.pad;
+        x0 = (t2 % shape.tiles_x) * kConvTW - shape.pad;
+      }
+      int cb = 0, dy = 0, dx = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(empty_bar(s), ph ^ 1u);
+        if (elect_one()) {
           if constexpr (kCta == 1) {
             mbar_expect_tx(full_bar(s), Cfg::STAGE_BYTES);
             if (shape.conv) tma_load_4d(smem_a(s), &tmA, full_bar(s), cb * Cfg::BK, x0 + dx, y0 + dy, img);
@@ -198,17 +200,18 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             else tma_load_2d_2sm(smem_a(s), &tmA, full_bar(s), kb * Cfg::BK, m0);
             tma_load_2d_2sm(smem_b(s), &tmB, full_bar(s), kb * Cfg::BK, n0);
           }
-          if (++s == STAGES) { s = 0; ph ^= 1u; }
-          if (shape.conv && ++cb == shape.cblocks) {
-            cb = 0;
-            if (++dx == shape.kw) { dx = 0; ++dy; }
-          }
+        }
+        __syncwarp();
+        if (++s == STAGES) { s = 0; ph ^= 1u; }
+        if (shape.conv && ++cb == shape.cblocks) {
+          cb = 0;
+          if (++dx == shape.kw) { dx = 0; ++dy; }
         }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------ MMA issuer ------------------------------
-    if (leader && lane == 0) {
+    // ------------------------------ MMA issuer (same scheme: uniform control flow, elected issue) -------------
+    if (leader) {
       constexpr uint32_t idesc = make_idesc(kTF32 ? kFmtTF32 : kFmtBF16, 128 * kCta, BN, 0, 0);
       int s = 0;
       uint32_t ph = 0;
@@ -221,18 +224,23 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(full_bar(s), ph);
           tc_fence_after();
-          const uint64_t adesc = make_smem_desc_sw128(smem_a(s), 1024, 0);
-          const uint64_t bdesc = make_smem_desc_sw128(smem_b(s), 1024, 0);
+          if (elect_one()) {
+            const uint64_t adesc = make_smem_desc_sw128(smem_a(s), 1024, 0);
+            const uint64_t bdesc = make_smem_desc_sw128(smem_b(s), 1024, 0);
 #pragma unroll
-          for (int k = 0; k < Cfg::BK / Cfg::UK; ++k) {
-            // advance 32 bytes along K inside the swizzle atom: +2 in the (addr >> 4) field
-            if constexpr (kTF32) umma_tf32_ss<kCta>(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) ? 1u : 0u);
-            else umma_f16_ss<kCta>(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) ? 1u : 0u);
+            for (int k = 0; k < Cfg::BK / Cfg::UK; ++k) {
+              // advance 32 bytes along K inside the swizzle atom: +2 in the (addr >> 4) field
+              if constexpr (kTF32) umma_tf32_ss<kCta>(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) ? 1u : 0u);
+              else umma_f16_ss<kCta>(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) ? 1u : 0u);
+            }
+            if constexpr (kCta == 1) umma_commit(empty_bar(s)); else umma_commit_2sm_mc(empty_bar(s), 3);
+            if (kb == num_kb - 1) {
+              if constexpr (kCta == 1) umma_commit(tfull_bar(as)); else umma_commit_2sm_mc(tfull_bar(as), 3);
+            }
           }
-          if constexpr (kCta == 1) umma_commit(empty_bar(s)); else umma_commit_2sm_mc(empty_bar(s), 3);
+          __syncwarp();
           if (++s == STAGES) { s = 0; ph ^= 1u; }
         }
-        if constexpr (kCta == 1) umma_commit(tfull_bar(as)); else umma_commit_2sm_mc(tfull_bar(as), 3);
         if (++as == 2) { as = 0; aph ^= 1u; }
       }
     }

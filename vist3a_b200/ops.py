@@ -122,7 +122,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
 
 
 def fmha(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, scale: Optional[float] = None,
-         out: Optional[torch.Tensor] = None) -> torch.Tensor:
+         out: Optional[torch.Tensor] = None, flags: int = 0) -> torch.Tensor:
     """Non-causal attention.  q [B, Lq, H, D], k/v [B, Lkv, H, D] (any strides with unit inner stride,
     e.g. slices of a fused QKV buffer); returns [B, Lq, H, D] bf16."""
     _need_cuda(q, k, v, out)
@@ -143,7 +143,7 @@ def fmha(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, scale: Optional[f
     a.v_bs, a.v_rs, a.v_hs = v.stride(0), v.stride(1), v.stride(2)
     a.o_bs, a.o_rs, a.o_hs = out.stride(0), out.stride(1), out.stride(2)
     a.scale = float(scale if scale is not None else D ** -0.5)
-    a.flags = 0
+    a.flags = flags
     L.check(L.load().vist3a_fmha_fwd(C.byref(a), _stream()))
     return out
 
