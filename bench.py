@@ -8,7 +8,10 @@ VIST3A-1.3B, 512x512x13 views).
 A "step" is one denoise step of one prompt: cond forward + uncond forward of the Wan-1.3B DiT at
 L = 4096 latent tokens (13 views @ 512x512) and 512 text tokens, CFG combine, UniPC update.
 Workload = BASELINE.json configs[1].  Under torchrun every rank runs its own prompt (prompts shard
-over GPUs with no data-path collective in the denoise loop: weak scaling).
+over GPUs with no data-path collective in the denoise loop: weak scaling).  The second half of the metric
+(Gaussians/sec, configs[2]) is measured in the same run and reported under "gaussians": the stitched
+latent->3DGS decoder at 13 views x 448x448 (2 609 152 Gaussians per prompt), decoder-only and end to end
+(50 denoise steps + decode + the NCCL all-gather of the Gaussian tensors when N > 1).
 Prints ONE JSON line on rank 0.
 """
 from __future__ import annotations
@@ -31,6 +34,9 @@ FWD_BLOCK_GFLOP = 462.25
 METRIC = "denoise_steps_per_sec"
 UNIT = "steps/s"
 WORKLOAD = "VIST3A-1.3B DiT 50-step denoise, 512x512x13 views (latent [1,16,4,64,64], L=4096, 512 text tokens), batch 1 per GPU"
+DECODER_TFLOP = 50.28  # transformer 43.75 (bf16) + heads 6.53 (tf32) per prompt at 13 views
+VIEWS, IMG = 13, 448
+N_GAUSS = VIEWS * IMG * IMG
 
 
 def _peaks():
@@ -39,6 +45,16 @@ def _peaks():
         d = json.load(open(p))
         return {"hbm_gbs": d["hbm_gbs"], "bf16_burst": d["bf16_tflops"], "bf16_sustained": d["bf16_tflops_sustained"], "src": "measured"}
     return {"hbm_gbs": 6650.0, "bf16_burst": 1590.0, "bf16_sustained": 1400.0, "src": "fallback"}
+
+
+def _ncu_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed `ncu --set full`
+    capture (profiles/ncu_traffic.json, written by tools/ncu_summary.py --traffic); None when no capture is committed."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        return json.load(open(p)).get(kernel)
+    except Exception:
+        return None
 
 
 class ClockSampler:
@@ -102,6 +118,22 @@ def cpu_sample(nb: int, repeats: int = 1):
     return times
 
 
+def cpu_decoder_sample():
+    """One forward of the decoder oracle (full widths: 1024-dim tokens, 22 + 48 blocks, DPT heads) on a reduced
+    view count / resolution (5 views x 224x224 -> 250 880 Gaussians); returns (seconds, Gaussians, description)."""
+    import torch
+
+    from oracle import decoder_ref as D
+
+    sd = D.init_state_dict(D.FULL, seed=1, round_bf16=False)
+    lat, img = D.synthetic_inputs(D.FULL, views_latent=2, latent_hw=32, image_hw=224, seed=2)
+    t0 = time.perf_counter()
+    out = D.decoder_forward(sd, D.FULL, lat, img, resolution=256)
+    dt = time.perf_counter() - t0
+    n = out["means"].shape[1]
+    return dt, n, "oracle/decoder_ref.py fp32, full-width model, 5 views x 224x224 (250 880 Gaussians; 1/10.4 of the 13 x 448x448 workload)"
+
+
 def run_reference(args):
     import torch
 
@@ -121,6 +153,8 @@ def run_reference(args):
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD},
             "cpu_baseline": {"value": sps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": sps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gaussians": None if args.no_decoder else (lambda r: {"decoder_gaussians_per_sec": r[1] / r[0], "unit": "Gaussians/s", "cores": cores,
+                                                                 "kind": "port", "sample": r[2] + f", {r[0]:.1f} s"})(cpu_decoder_sample()),
             "note": "reference DiT lives in un-vendored diffusers==0.33.1; timed arm is the oracle restatement (oracle/wan_dit_ref.py)"}
     print(json.dumps(line), flush=True)
 
@@ -128,30 +162,24 @@ def run_reference(args):
 # --------------------------------------------------------------------------------------------------
 # our arm
 # --------------------------------------------------------------------------------------------------
-def build_model(device):
-    """Random-init Wan-1.3B weights (N(0,0.02) weights, zero biases, table randn/sqrt(D)) made on the device."""
-    import math
+def build_models(device, with_decoder=True):
+    """Random-init weights of the named architectures, generated on the device (no checkpoint is reachable offline)."""
+    from types import SimpleNamespace
 
-    import torch
+    from vist3a_b200 import stitched_decoder as SD
+    from vist3a_b200 import wan_dit as WD
 
-    from oracle.wan_dit_ref import WAN_1_3B, param_shapes  # shape manifest only (no oracle compute on this path)
-    from vist3a_b200.wan_dit import WanTransformer3DModelB200
-
-    cfg = WAN_1_3B
-    g = torch.Generator(device=device).manual_seed(0)
-    sd = {}
-    for k, shp in param_shapes(cfg).items():
-        if k.endswith("scale_shift_table"):
-            sd[k] = torch.randn(shp, device=device, generator=g) / math.sqrt(cfg.inner_dim)
-        elif "norm" in k and k.endswith(".weight"):
-            sd[k] = torch.ones(shp, device=device)
-        elif k.endswith(".bias"):
-            sd[k] = torch.zeros(shp, device=device)
-        else:
-            sd[k] = (torch.randn(shp, device=device, generator=g) * 0.02).bfloat16()
-    model = WanTransformer3DModelB200.from_state_dict(sd, cfg, device=device)
+    cfg = WD.WAN_1_3B_CONFIG
+    sd = WD.random_state_dict(cfg, 0, device)
+    model = WD.WanTransformer3DModelB200.from_state_dict(sd, cfg, device=device)
     del sd
-    return cfg, model
+    dec = None
+    if with_decoder:
+        dcfg = SD.DecoderConfig()
+        sd = SD.random_state_dict(dcfg, 0, device)
+        dec = SD.StitchVAE3DB200.from_state_dict(sd, dcfg, device=device)
+        del sd
+    return SimpleNamespace(**cfg), model, dec
 
 
 def run_ours(args):
@@ -160,6 +188,7 @@ def run_ours(args):
 
     from vist3a_b200 import _lib, ops
     from vist3a_b200.pipeline import DenoiseEngine
+    from vist3a_b200.t23d import WAN_LATENTS_MEAN, WAN_LATENTS_STD, all_gather_gaussians
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -171,7 +200,7 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
     _lib.load()
-    cfg, model = build_model(device)
+    cfg, model, dec = build_models(device, with_decoder=not args.no_decoder)
     B, T, HW, Lt = 1, 4, 64, 512
     g = torch.Generator().manual_seed(1000 + rank)  # every rank denoises its own prompt
     noise_h = torch.randn(B, 16, T, HW, HW, generator=g).pin_memory()
@@ -250,6 +279,58 @@ def run_ours(args):
     ms_e2e = timed(e2e_step, args.steps)
     e2e_value = world * args.steps / (ms_e2e / 1e3)
 
+    # ---- Gaussians/s: stitched decoder at 13 views x 448x448 on the (de-normalised) denoised latent, + the Gaussian all-gather
+    gauss = None
+    dec_launches = 0
+    if dec is not None:
+        mean = torch.tensor(WAN_LATENTS_MEAN, device=device).view(1, 16, 1, 1, 1)
+        std = torch.tensor(WAN_LATENTS_STD, device=device).view(1, 16, 1, 1, 1)
+        lat = eng.x.clamp(-4, 4) * std + mean   # synthetic-weight DiT output, clamped to the range of real VAE latents
+        img_h = (torch.rand(1, 3, VIEWS, IMG, IMG, generator=g) * 2 - 1).pin_memory()
+        img = img_h.to(device)
+        outs = {}
+
+        def dec_step(i):
+            outs["o"] = dec.forward_with_latent(lat, img)
+
+        for i in range(2):
+            dec_step(i)
+        n2 = _lib.launch_count()
+        kd = max(2, min(args.steps, args.decoder_iters))
+        ms_dec = timed(dec_step, kd) / kd
+        dec_launches = _lib.launch_count() - n2
+        ms_gather = 0.0
+        if world > 1:
+            def gather_step(i):
+                outs["all"] = all_gather_gaussians(outs["o"].gaussians)
+
+            gather_step(0)
+            ms_gather = timed(gather_step, 3) / 3
+            outs.pop("all", None)
+        # end to end per prompt: H2D of the decoded views, 50 denoise steps, decode, gather, D2H of one scalar (scene scale)
+        def e2e_prompt(i):
+            img.copy_(img_h, non_blocking=True)
+            eng.set_text(tc_h, tu_h)
+            eng.set_noise(noise_h)
+            for k in range(nsteps):
+                eng.step(k)
+            o = dec.forward_with_latent(eng.x.clamp(-4, 4) * std + mean, img)
+            if world > 1:
+                all_gather_gaussians(o.gaussians)
+            o.infos["scene_scale"].cpu()
+
+        ms_prompt = timed(e2e_prompt, 1)
+        gauss = {"n_per_prompt": N_GAUSS, "unit": "Gaussians/s",
+                 "decoder_gaussians_per_sec": world * N_GAUSS / (ms_dec / 1e3), "decoder_ms": ms_dec,
+                 "decoder_tflops": DECODER_TFLOP / (ms_dec / 1e3), "gather_ms": ms_gather,
+                 "e2e_gaussians_per_sec": world * N_GAUSS / (ms_prompt / 1e3), "e2e_prompt_ms": ms_prompt,
+                 "e2e_what": "one prompt per GPU: H2D views, text projections, 50 CFG denoise steps, de-normalise, decode" +
+                             (", NCCL all-gather of all ranks' Gaussians" if world > 1 else "") + ", D2H of scene_scale",
+                 "decoder_launches_per_forward": dec_launches // kd,
+                 "latent": "denoised latent of the random-weight DiT, clamped to [-4, 4] before de-normalisation (real VAE latents are O(1))",
+                 "workload": "VIST3A-1.3B full stitched path: DiT -> conv3d_k5x3x3 stitch -> AnySplat enc_blocks_2 -> 3DGS, 512x512x13v"}
+        del outs
+
     # ---- per-kernel device timing of one eager step (roofline of the dominant kernel)
     roof = None
     launches_per_step = None
@@ -279,7 +360,7 @@ def run_ours(args):
         ach = d["flops"] / (d["ms"] / 1e3) / 1e12
         roof = {"bound": "tensor", "kernel": top, "achieved": ach, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
                 "frac": ach / pk["bf16_sustained"], "frac_of_burst": ach / pk["bf16_burst"], "peak_src": pk["src"] + " (sustained: kernel timed inside a long step)",
-                "traffic": None, "launches_per_step": d["launches"], "avg_launch_ms": d["ms"] / d["launches"],
+                "traffic": _ncu_traffic(top), "launches_per_step": d["launches"], "avg_launch_ms": d["ms"] / d["launches"],
                 "share_of_step": d["ms"] / tot,
                 "step_model_tflops": STEP_TFLOP / (ms_step / 1e3), "step_frac_of_sustained": STEP_TFLOP / (ms_step / 1e3) / pk["bf16_sustained"],
                 "by_kernel": {k: {"ms": round(v["ms"], 4), "launches": v["launches"],
@@ -294,6 +375,10 @@ def run_ours(args):
         sps = 1.0 / (2.0 * 30.0 / nb * t)
         cpu = {"value": sps, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
                "sample": f"{nb} of 30 full-size fp32 blocks of one cond forward (oracle/wan_dit_ref.py), {t:.2f} s; steps/s = 1/(2*30/{nb}*t)"}
+        if gauss is not None:
+            dt, n, what = cpu_decoder_sample()
+            gauss["cpu_baseline"] = {"decoder_gaussians_per_sec": n / dt, "cores": torch.get_num_threads(), "kind": "port",
+                                     "sample": what + f", {dt:.1f} s"}
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -302,7 +387,7 @@ def run_ours(args):
                 "config": {"workload": WORKLOAD, "weights": "random-init Wan-1.3B (1.419 B params)", "cfg": "cond+uncond batched B=2",
                            "cuda_graph": not args.no_graph, "l2": "working set (2.8 GB weights + activations) >> 126 MB L2; no flush needed",
                            "prompts_per_gpu": 1},
-                "roofline": roof, "cpu_baseline": cpu, "clocks": clk.summary(),
+                "roofline": roof, "cpu_baseline": cpu, "clocks": clk.summary(), "gaussians": gauss,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": ms_e2e / args.steps},
                 "gpu_launches": launches_eager if args.no_graph else (launches_per_step or 0) * args.steps,
@@ -324,6 +409,8 @@ def main():
     ap.add_argument("--ncu-step", action="store_true", help="profile exactly one eager denoise step (for ncu --profile-from-start off)")
     ap.add_argument("--detail", action="store_true", help="print per-shape kernel timings of one eager step to stderr")
     ap.add_argument("--ref-blocks", type=int, default=2, help="full-size blocks per CPU sample")
+    ap.add_argument("--no-decoder", action="store_true", help="skip the Gaussians/s leg (decoder + gather)")
+    ap.add_argument("--decoder-iters", type=int, default=3)
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

@@ -1,0 +1,74 @@
+"""Host logic of the multi-GPU path on CPU: prompt sharding and the Gaussian all-gather over a world_size-2 gloo group
+(the same code runs over NCCL on the GPUs)."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from vist3a_b200.stitched_decoder import Gaussians
+from vist3a_b200.t23d import all_gather_gaussians, pack_gaussians, shard_prompts, unpack_gaussians
+
+
+def _gauss(seed, n=37, d_sh=25):
+    g = torch.Generator().manual_seed(seed)
+    r = lambda *s: torch.randn(*s, generator=g)
+    return Gaussians(means=r(1, n, 3), covariances=r(1, n, 3, 3), harmonics=r(1, n, 3, d_sh), opacities=r(1, n), scales=r(1, n, 3),
+                     rotations=r(1, n, 4))
+
+
+def test_shard_prompts_matches_reference_slicing():
+    prompts = [f"p{i}" for i in range(11)]
+    seen = []
+    for r in range(4):
+        part = shard_prompts(prompts, r, 4)
+        assert part == prompts[r::4]
+        seen += part
+    assert sorted(seen) == sorted(prompts)           # every prompt exactly once
+    assert shard_prompts(prompts[:2], 3, 4) == []    # ragged: more ranks than prompts
+    with pytest.raises(ValueError):
+        shard_prompts(prompts, 4, 4)
+
+
+@pytest.mark.parametrize("cov", [False, True])
+def test_pack_unpack_roundtrip(cov):
+    g = _gauss(0)
+    rec = pack_gaussians(g, cov)
+    assert rec.shape == (1, 37, 86 + (9 if cov else 0))
+    back = unpack_gaussians(rec, 25, cov)
+    for k, v in back.items():
+        assert torch.equal(v, getattr(g, k))
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        mine = _gauss(100 + rank)
+        got = all_gather_gaussians(mine, with_covariances=True)
+        ok = len(got) == world
+        for r in range(world):
+            want = _gauss(100 + r)
+            for k, v in got[r].items():
+                ok = ok and torch.equal(v, getattr(want, k))
+        q.put((rank, ok))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_all_gather_gaussians_gloo_world2():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(0, True), (1, True)]

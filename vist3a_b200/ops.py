@@ -338,11 +338,12 @@ def attention_small(qkv: torch.Tensor, B: int, Lq: int, H: int, D: int) -> torch
     return out
 
 
-def fma_rows(a: torch.Tensor, b: torch.Tensor, c: torch.Tensor) -> torch.Tensor:
+def fma_rows(a: torch.Tensor, b: torch.Tensor, c: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """a * b + c on [rows, dim] fp32 views (row strides allowed)."""
-    _need_cuda(a, b, c)
+    _need_cuda(a, b, c, out)
     rows, dim = a.shape
-    out = torch.empty((rows, dim), dtype=torch.float32, device=a.device)
+    if out is None:
+        out = torch.empty((rows, dim), dtype=torch.float32, device=a.device)
     L.check(L.load().vist3a_fma_rows(out.data_ptr(), out.stride(0), a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0),
                                      c.data_ptr(), c.stride(0), rows, dim, _stream()))
     return out

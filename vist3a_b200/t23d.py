@@ -1,0 +1,104 @@
+"""Text -> 3D Gaussians on one GPU, and prompt sharding over the GPUs of one box.
+
+Mirrors the per-prompt body of /root/reference/inference_t23d.py:84-137:
+    latents = pipe(prompt..., num_inference_steps=50, guidance_scale=cfg, output_type="latent")   -> DenoiseEngine.run
+    latents = latents / (1 / std) + mean                                                          -> de-normalise (:104-113)
+    output  = stitched_decoder.forward_with_latent(latents, feedforward_image=..., train=False)   -> StitchVAE3DB200
+and its data-parallel layout (:58-62): `prompt_list[rank::world_size]`, one full model replica per GPU, no
+collective inside a prompt.  The one exchange step is the gather of the final Gaussian tensors
+(`all_gather_gaussians`): means, scales, rotations, opacities, harmonics (+ covariances) of every rank.
+
+Text encoding (UMT5) and the Wan VAE decode that produces `feedforward_image` are outside the hot path
+(SURVEY §8f): the caller passes text embeddings and the decoded views.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence
+
+import torch
+
+from . import ops
+from .pipeline import DenoiseEngine
+from .stitched_decoder import EncoderOutput, Gaussians
+
+# AutoencoderKLWan.config.latents_mean / latents_std (the reference's copy: utils/wan_utils.py:925-960)
+WAN_LATENTS_MEAN = (-0.7571, -0.7089, -0.9113, 0.1075, -0.1745, 0.9653, -0.1517, 1.5508, 0.4134, -0.0715, 0.5517, -0.3632,
+                    -0.1922, -0.9497, 0.2503, -0.2921)
+WAN_LATENTS_STD = (2.8184, 1.4541, 2.3275, 2.6558, 1.2196, 1.7708, 2.6052, 2.0743, 3.2687, 2.1526, 2.8652, 1.5579, 1.6382,
+                   1.1253, 2.8251, 1.9160)
+
+GAUSSIAN_FIELDS = ("means", "scales", "rotations", "opacities", "harmonics", "covariances")
+
+
+def shard_prompts(prompts: Sequence, rank: int, world_size: int) -> list:
+    """inference_t23d.py:62 -- `prompt_list[rank :: dist.get_world_size()]`"""
+    if not (0 <= rank < world_size):
+        raise ValueError(f"rank {rank} outside world of {world_size}")
+    return list(prompts[rank::world_size])
+
+
+class TextTo3DGS:
+    """One prompt -> EncoderOutput; owns the CUDA-graphed denoise engine and the decoder."""
+
+    def __init__(self, transformer, decoder, *, views: int = 13, resolution: int = 512, text_len: int = 512,
+                 num_inference_steps: int = 50, guidance_scale: float = 6.0, flow_shift: float = 5.0, use_graph: bool = True):
+        if (views - 1) % 4:
+            raise ValueError("views must be 4k+1 (Wan VAE temporal stride 4)")
+        self.tr, self.dec = transformer, decoder
+        self.dev = transformer.device
+        T = (views - 1) // 4 + 1
+        self.latent_shape = (1, 16, T, resolution // 8, resolution // 8)
+        self.engine = DenoiseEngine(transformer, self.latent_shape, text_len, num_inference_steps=num_inference_steps,
+                                    guidance_scale=guidance_scale, flow_shift=flow_shift, use_graph=use_graph)
+        # x * std + mean as one kernel:  out = std_c * x + mean_c * 1
+        shp = (1, 16, 1, 1, 1)
+        self._std = torch.tensor(WAN_LATENTS_STD, device=self.dev).view(shp).expand(self.latent_shape).contiguous()
+        self._mean = torch.tensor(WAN_LATENTS_MEAN, device=self.dev).view(shp).expand(self.latent_shape).contiguous()
+        self._lat = torch.empty(self.latent_shape, dtype=torch.float32, device=self.dev)
+
+    @torch.no_grad()
+    def denoise(self, noise: torch.Tensor, text_cond: torch.Tensor, text_uncond: torch.Tensor) -> torch.Tensor:
+        """50-step CFG sampling -> de-normalised VAE latent [1, 16, T, h, w] fp32 (what the decoder is stitched onto)."""
+        x = self.engine.run(noise, text_cond, text_uncond)
+        ops.fma_rows(x.view(-1, x.shape[-1]), self._std.view(-1, x.shape[-1]), self._mean.view(-1, x.shape[-1]), out=self._lat.view(-1, x.shape[-1]))
+        return self._lat
+
+    @torch.no_grad()
+    def generate(self, noise: torch.Tensor, text_cond: torch.Tensor, text_uncond: torch.Tensor,
+                 feedforward_image: torch.Tensor) -> EncoderOutput:
+        latent = self.denoise(noise, text_cond, text_uncond)
+        return self.dec.forward_with_latent(latent, feedforward_image, train=False)
+
+
+def pack_gaussians(g: Gaussians, with_covariances: bool = False) -> torch.Tensor:
+    """[B, N, F] fp32 record per Gaussian: means 3 | scales 3 | rotations 4 | opacity 1 | harmonics 3*d_sh (| covariances 9)."""
+    B, N = g.opacities.shape
+    parts = [g.means, g.scales, g.rotations, g.opacities.unsqueeze(-1), g.harmonics.reshape(B, N, -1)]
+    if with_covariances:
+        parts.append(g.covariances.reshape(B, N, 9))
+    return torch.cat(parts, dim=-1).contiguous()
+
+
+def unpack_gaussians(rec: torch.Tensor, d_sh: int, with_covariances: bool = False) -> Dict[str, torch.Tensor]:
+    B, N, _ = rec.shape
+    sizes = [3, 3, 4, 1, 3 * d_sh] + ([9] if with_covariances else [])
+    m, s, r, o, h, *c = rec.split(sizes, dim=-1)
+    out = {"means": m, "scales": s, "rotations": r, "opacities": o.squeeze(-1), "harmonics": h.reshape(B, N, 3, d_sh)}
+    if c:
+        out["covariances"] = c[0].reshape(B, N, 3, 3)
+    return out
+
+
+def all_gather_gaussians(g: Gaussians, group=None, with_covariances: bool = False) -> List[Dict[str, torch.Tensor]]:
+    """The single exchange step of the multi-GPU path: every rank contributes the Gaussians of its prompt and
+    receives everybody's.  One `all_gather_into_tensor` of a fixed-size record buffer (N = V*H*W per prompt when
+    voxelisation is off), NCCL over NVLink on GPUs, gloo on CPU in the tests.  Returns one dict per rank."""
+    import torch.distributed as dist
+
+    rec = pack_gaussians(g, with_covariances)
+    world = dist.get_world_size(group)
+    B = rec.shape[0]
+    out = torch.empty((world * B,) + tuple(rec.shape[1:]), dtype=rec.dtype, device=rec.device)  # rank-major concatenation
+    dist.all_gather_into_tensor(out, rec, group=group)
+    d_sh = g.harmonics.shape[-1]
+    return [unpack_gaussians(out[r * B:(r + 1) * B], d_sh, with_covariances) for r in range(world)]

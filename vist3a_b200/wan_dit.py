@@ -29,6 +29,62 @@ import torch
 from . import ops
 
 
+# WanTransformer3DModel.config values of the two released sizes (diffusers 0.33.1)
+WAN_1_3B_CONFIG = dict(patch_size=(1, 2, 2), num_attention_heads=12, attention_head_dim=128, in_channels=16, out_channels=16,
+                       text_dim=4096, freq_dim=256, ffn_dim=8960, num_layers=30, cross_attn_norm=True, eps=1e-6,
+                       rope_max_seq_len=1024)
+WAN_14B_CONFIG = dict(WAN_1_3B_CONFIG, num_attention_heads=40, ffn_dim=13824, num_layers=40)
+
+
+def param_shapes(cfg: dict) -> Dict[str, tuple]:
+    """diffusers-keyed parameter manifest of WanTransformer3DModel (what `from_state_dict` ingests)."""
+    D, Fd = cfg["num_attention_heads"] * cfg["attention_head_dim"], cfg["ffn_dim"]
+    pt, ph, pw = cfg["patch_size"]
+    po = cfg["out_channels"] * pt * ph * pw
+    s: Dict[str, tuple] = {"patch_embedding.weight": (D, cfg["in_channels"], pt, ph, pw), "patch_embedding.bias": (D,),
+                           "scale_shift_table": (1, 2, D), "proj_out.weight": (po, D), "proj_out.bias": (po,)}
+
+    def lin(name, n, k):
+        s[name + ".weight"], s[name + ".bias"] = (n, k), (n,)
+
+    ce = "condition_embedder."
+    lin(ce + "time_embedder.linear_1", D, cfg["freq_dim"])
+    lin(ce + "time_embedder.linear_2", D, D)
+    lin(ce + "time_proj", 6 * D, D)
+    lin(ce + "text_embedder.linear_1", D, cfg["text_dim"])
+    lin(ce + "text_embedder.linear_2", D, D)
+    for i in range(cfg["num_layers"]):
+        b = f"blocks.{i}."
+        s[b + "scale_shift_table"] = (1, 6, D)
+        for a in ("attn1.", "attn2."):
+            for l in ("to_q", "to_k", "to_v", "to_out.0"):
+                lin(b + a + l, D, D)
+            s[b + a + "norm_q.weight"], s[b + a + "norm_k.weight"] = (D,), (D,)
+        if cfg["cross_attn_norm"]:
+            s[b + "norm2.weight"], s[b + "norm2.bias"] = (D,), (D,)
+        lin(b + "ffn.net.0.proj", Fd, D)
+        lin(b + "ffn.net.2", D, Fd)
+    return s
+
+
+def random_state_dict(cfg: dict, seed: int = 0, device="cuda") -> Dict[str, torch.Tensor]:
+    """Random-init weights of the named architecture for benchmarking (no checkpoint is reachable offline): Linear/Conv
+    N(0, 0.02) in bf16, zero biases, scale_shift_table = randn / sqrt(D), RMSNorm/LayerNorm weights 1."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    D = cfg["num_attention_heads"] * cfg["attention_head_dim"]
+    sd = {}
+    for k, shp in param_shapes(cfg).items():
+        if k.endswith("scale_shift_table"):
+            sd[k] = torch.randn(shp, device=device, generator=g) / math.sqrt(D)
+        elif "norm" in k and k.endswith(".weight"):
+            sd[k] = torch.ones(shp, device=device)
+        elif k.endswith(".bias"):
+            sd[k] = torch.zeros(shp, device=device)
+        else:
+            sd[k] = (torch.randn(shp, device=device, generator=g) * 0.02).bfloat16()
+    return sd
+
+
 def _rope_tables(head_dim: int, f: int, h: int, w: int, max_len: int, device) -> tuple:
     """cos/sin [f*h*w, head_dim/2] fp32 of WanRotaryPosEmbed (fp64 angles; split 44/42/42 at d=128)."""
     h_dim = w_dim = 2 * (head_dim // 6)
