@@ -21,6 +21,8 @@ def main():
     ap.add_argument("--iters", type=int, default=3)
     ap.add_argument("--detail", action="store_true")
     ap.add_argument("--batch", type=int, default=1)
+    ap.add_argument("--ncu", action="store_true", help="one warm forward between cudaProfilerStart/Stop (ncu --profile-from-start off)")
+    ap.add_argument("--ncu-all", action="store_true", help="two forwards and exit (ncu -k filters the kernel)")
     a = ap.parse_args()
     torch.cuda.set_device(0)
     cfg = DecoderConfig()
@@ -34,6 +36,14 @@ def main():
     for _ in range(2):
         o = m.forward_with_latent(lat, img)
     torch.cuda.synchronize()
+    if a.ncu_all:
+        return
+    if a.ncu:
+        torch.cuda.profiler.start()
+        o = m.forward_with_latent(lat, img)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        return
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s.record()
     for _ in range(a.iters):
