@@ -250,6 +250,14 @@ int vist3a_attention_small(const float* qkv, float* out, int64_t B, int64_t L, i
 int vist3a_fma_rows(float* out, int64_t ldo, const float* a, int64_t lda, const float* b, int64_t ldb, const float* c,
                     int64_t ldc, int64_t rows, int64_t dim, void* stream);
 
+/* transposed epilogue of a swapped-operand skinny linear.  For M <= 16 tokens the weight matrix is the streamed (A) operand
+ * of vist3a_gemm:  ct[n, m] = sum_k W[n, k] x[m, k]  (ct is [N, ldct >= 16] fp32); this finishes
+ *   y[m, n] = residual[m, n] + gate[n] * act(ct[n, m] + bias[n])        (bias / gate / residual optional)
+ * replaces: bias, activation, LayerScale and residual add of the nn.Linear layers inside the camera-head trunk
+ *   (AS/.../heads/camera_head.py:87-170; Block.forward AS/.../layers/block.py:81-107 at 13 tokens). */
+int vist3a_bias_act_t(const float* ct, int64_t ldct, const float* bias, int32_t act, const float* gate, const float* residual,
+                      int64_t ldr, float* y, int64_t ldy, int64_t M, int64_t N, void* stream);
+
 /* camera head output: activate pose encodings (relu on the 2 FoV entries) and build cameras.
  *   pose_raw [S, 9] -> pose_act [S, 9]; extr [S, 3, 4] world->cam; intr [S, 3, 3] in pixels;
  *   c2w [S, 4, 4] = inverse([R|t; 0 0 0 1]); intr_norm [S, 3, 3] (rows 0/1 divided by W/H).  Any output may be NULL.

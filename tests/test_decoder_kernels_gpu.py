@@ -208,6 +208,26 @@ def test_skinny_linear_fp32_gate_residual(ops):
     assert _rel_l2(out, ref) < 1e-6
 
 
+@pytest.mark.parametrize("N,K", [(6144, 2048), (2048, 8192), (384, 128), (9, 1024)])
+def test_linear_tokens16_weight_streaming(ops, N, K):
+    """camera-head linears: weights are the streamed TMA operand (TF32), 13 tokens padded to 16"""
+    M = 13
+    g = torch.Generator(device="cuda").manual_seed(17)
+    x16 = torch.zeros(16, K, device="cuda")
+    x16[:M] = torch.randn(M, K, device="cuda", generator=g)
+    w = torch.randn(N, K, device="cuda", generator=g) / math.sqrt(K)
+    b, gate = torch.randn(N, device="cuda", generator=g), torch.randn(N, device="cuda", generator=g)
+    res = torch.zeros(16, N, device="cuda")
+    res[:M] = torch.randn(M, N, device="cuda", generator=g)
+    ref = res[:M].double() + gate.double() * F.gelu(x16[:M].double() @ w.double().t() + b.double())
+    out = ops.linear_tokens16(x16, M, w, b, act="gelu_erf", gate=gate, residual=res)
+    assert out.shape == (16, N) and float(out[M:].abs().max()) == 0.0
+    assert _rel_l2(out[:M], ref) < 1e-3          # tf32 operands
+    res2 = res.clone()
+    ops.linear_tokens16(x16, M, w, b, act="gelu_erf", gate=gate, residual=res2, out=res2)   # in place on the residual
+    assert torch.equal(res2[:M], out[:M])
+
+
 def test_pose_to_cameras_matches_oracle(ops):
     from oracle import decoder_ref as D
 

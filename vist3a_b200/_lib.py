@@ -42,6 +42,7 @@ EXPORTS = (
     "vist3a_depth_to_space",
     "vist3a_attention_small",
     "vist3a_fma_rows",
+    "vist3a_bias_act_t",
     "vist3a_pose_to_cameras",
     "vist3a_gaussian_epilogue",
 )
@@ -164,6 +165,7 @@ def load(build_if_missing: bool = False) -> C.CDLL:
     lib.vist3a_depth_to_space.argtypes = [vp, vp, i64, i64, i64, i64, i32, vp]
     lib.vist3a_attention_small.argtypes = [vp, vp, i64, i64, i64, i64, f32, vp]
     lib.vist3a_fma_rows.argtypes = [vp, i64, vp, i64, vp, i64, vp, i64, i64, i64, vp]
+    lib.vist3a_bias_act_t.argtypes = [vp, i64, vp, i32, vp, vp, i64, vp, i64, i64, i64, vp]
     lib.vist3a_pose_to_cameras.argtypes = [vp, vp, vp, vp, vp, vp, i64, i64, i64, vp]
     lib.vist3a_gaussian_epilogue.argtypes = [vp, i64, i64, vp, f32, vp, i64, vp, vp, vp, i64, i64, i64, i64, vp, vp, vp, vp, vp, vp,
                                              vp, vp, vp]

@@ -25,6 +25,8 @@ int bilinear_nhwc_entry(const float*, float*, long long, long long, long long, l
                         const float*, const float*, cudaStream_t);
 int depth_to_space_entry(const float*, float*, long long, long long, long long, long long, int, cudaStream_t);
 int attention_small_entry(const float*, float*, long long, long long, long long, long long, float, cudaStream_t);
+int bias_act_t_entry(const float*, long long, const float*, int, const float*, const float*, long long, float*, long long, long long,
+                     long long, cudaStream_t);
 int fma_rows_entry(float*, long long, const float*, long long, const float*, long long, const float*, long long, long long,
                    long long, cudaStream_t);
 int pose_to_cameras_entry(const float*, float*, float*, float*, float*, float*, long long, long long, long long, cudaStream_t);
@@ -222,6 +224,10 @@ int vist3a_attention_small(const float* qkv, float* out, int64_t B, int64_t L, i
 int vist3a_fma_rows(float* out, int64_t ldo, const float* a, int64_t lda, const float* b, int64_t ldb, const float* c,
                     int64_t ldc, int64_t rows, int64_t dim, void* stream) {
   return fma_rows_entry(out, ldo, a, lda, b, ldb, c, ldc, rows, dim, ST(stream));
+}
+int vist3a_bias_act_t(const float* ct, int64_t ldct, const float* bias, int32_t act, const float* gate, const float* residual,
+                      int64_t ldr, float* y, int64_t ldy, int64_t M, int64_t N, void* stream) {
+  return bias_act_t_entry(ct, ldct, bias, act, gate, residual, ldr, y, ldy, M, N, ST(stream));
 }
 int vist3a_pose_to_cameras(const float* pose_raw, float* pose_act, float* extr, float* intr, float* c2w,
                            float* intr_norm, int64_t S, int64_t H, int64_t W, void* stream) {

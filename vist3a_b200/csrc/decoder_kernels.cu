@@ -340,6 +340,42 @@ int fma_rows_entry(float* out, long long ldo, const float* a, long long lda, con
 }
 
 // ----------------------------------------------------------------------------------------
+// transposed epilogue of a swapped-operand skinny linear: the tcgen05 GEMM streams the weight matrix as its A operand
+// (ct[n, m] = sum_k W[n, k] x[m, k], 16 padded token columns); this kernel finishes y[m, n] = res + gate[n] * act(ct + b[n])
+// ----------------------------------------------------------------------------------------
+__device__ __forceinline__ float act_apply_f(float v, int act) {
+  switch (act) {
+    case VIST3A_ACT_GELU_TANH: return gelu_tanh_precise_f(v);
+    case VIST3A_ACT_GELU_ERF: return gelu_erf_f(v);
+    case VIST3A_ACT_SILU: return v / (1.0f + expf(-v));
+    case VIST3A_ACT_RELU: return fmaxf(v, 0.f);
+    default: return v;
+  }
+}
+__global__ void __launch_bounds__(256) bias_act_t_kernel(const float* __restrict__ ct, long long ldct, const float* __restrict__ bias,
+                                                         int act, const float* __restrict__ gate, const float* __restrict__ res,
+                                                         long long ldr, float* __restrict__ y, long long ldy, int M, int N) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)M * N) return;
+  const int n = (int)(i % N), m = (int)(i / N);  // consecutive threads -> consecutive n: coalesced y / bias / gate / residual
+  float v = ct[(long long)n * ldct + m] + (bias ? bias[n] : 0.f);
+  v = act_apply_f(v, act);
+  if (gate) v *= gate[n];
+  if (res) v += res[(long long)m * ldr + n];
+  y[(long long)m * ldy + n] = v;
+}
+
+int bias_act_t_entry(const float* ct, long long ldct, const float* bias, int act, const float* gate, const float* res, long long ldr,
+                     float* y, long long ldy, long long M, long long N, cudaStream_t st) {
+  V3A_REQUIRE(ct && y && M > 0 && N > 0 && ldct >= M && ldy >= N, VIST3A_ERR_INVALID, "bias_act_t: bad arguments");
+  V3A_REQUIRE(!res || ldr >= N, VIST3A_ERR_INVALID, "bias_act_t: residual stride");
+  bias_act_t_kernel<<<grid_for(M * N, 256), 256, 0, st>>>(ct, ldct, bias, act, gate, res, ldr, y, ldy, (int)M, (int)N);
+  V3A_CUDA_OK(cudaGetLastError());
+  launch_counter().fetch_add(1);
+  return VIST3A_OK;
+}
+
+// ----------------------------------------------------------------------------------------
 // pose encoding -> cameras
 // ----------------------------------------------------------------------------------------
 __global__ void pose_to_cameras_kernel(const float* __restrict__ pose_raw, float* __restrict__ pose_act, float* __restrict__ extr,

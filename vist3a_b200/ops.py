@@ -328,12 +328,15 @@ def depth_to_space(x: torch.Tensor, n: int, h: int, w: int, Cc: int, k: int) -> 
     return out
 
 
-def attention_small(qkv: torch.Tensor, B: int, Lq: int, H: int, D: int) -> torch.Tensor:
+def attention_small(qkv: torch.Tensor, B: int, Lq: int, H: int, D: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """fp32 attention for L <= 32: qkv [B*L, 3*H*D] -> [B*L, H*D]."""
-    _need_cuda(qkv)
+    _need_cuda(qkv, out)
     if qkv.dtype != torch.float32 or not qkv.is_contiguous():
         raise TypeError("attention_small: qkv must be contiguous float32")
-    out = torch.empty((B * Lq, H * D), dtype=torch.float32, device=qkv.device)
+    if out is None:
+        out = torch.empty((B * Lq, H * D), dtype=torch.float32, device=qkv.device)
+    elif not out.is_contiguous() or out.shape != (B * Lq, H * D):
+        raise ValueError("attention_small: out must be contiguous [B*L, H*D]")
     L.check(L.load().vist3a_attention_small(qkv.data_ptr(), out.data_ptr(), B, Lq, H, D, D ** -0.5, _stream()))
     return out
 
@@ -346,6 +349,25 @@ def fma_rows(a: torch.Tensor, b: torch.Tensor, c: torch.Tensor, out: Optional[to
         out = torch.empty((rows, dim), dtype=torch.float32, device=a.device)
     L.check(L.load().vist3a_fma_rows(out.data_ptr(), out.stride(0), a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0),
                                      c.data_ptr(), c.stride(0), rows, dim, _stream()))
+    return out
+
+
+def linear_tokens16(x16: torch.Tensor, M: int, w: torch.Tensor, bias: Optional[torch.Tensor] = None, *, act=None,
+                    gate: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None,
+                    out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """nn.Linear for M <= 16 tokens, HBM-bound on the weights: the weight matrix [N, K] is streamed by TMA as the A operand of
+    the tcgen05 GEMM (TF32 for fp32 weights) against the 16-row padded token matrix x16 [16, K]; a transposed epilogue kernel
+    adds bias / activation / LayerScale / residual.  Returns y [16, N] (rows >= M are left untouched)."""
+    _need_cuda(x16, w, bias, gate, residual, out)
+    if x16.shape[0] != 16 or not x16.is_contiguous() or M > 16:
+        raise ValueError("linear_tokens16: x16 must be a contiguous [16, K] buffer holding M <= 16 token rows")
+    N = w.shape[0]
+    ct = gemm(w, x16, out_dtype=torch.float32, two_cta=False)  # [N, 16] = W x^T
+    if out is None:
+        out = torch.zeros((16, N), dtype=torch.float32, device=x16.device)
+    L.check(L.load().vist3a_bias_act_t(ct.data_ptr(), ct.stride(0), _ptr(bias), ACT[act], _ptr(gate), _ptr(residual),
+                                       residual.stride(0) if residual is not None else 0, out.data_ptr(), out.stride(0), M, N,
+                                       _stream()))
     return out
 
 
@@ -444,7 +466,7 @@ class OpTimer:
                  "cfg_combine": io_cost("small"), "axpby_n": io_cost("small"), "im2col_stitch": io_cost("im2col"),
                  "im2col_nhwc": io_cost("im2col"), "qknorm_rope2d_": io_cost("qknorm_rope2d"), "bilinear_nhwc": io_cost("bilinear"),
                  "depth_to_space": io_cost("depth_to_space"), "attention_small": io_cost("small"), "fma_rows": io_cost("small"),
-                 "pose_to_cameras": io_cost("small"), "gaussian_epilogue": io_cost("gaussian_epilogue")}
+                 "pose_to_cameras": io_cost("small"), "linear_tokens16": io_cost("linear_tokens16"), "gaussian_epilogue": io_cost("gaussian_epilogue")}
         for name, cost in table.items():
             self._saved[name] = getattr(mod, name)
             setattr(mod, name, self._wrap(name, self._saved[name], cost))

@@ -437,31 +437,38 @@ class StitchVAE3DB200(torch.nn.Module):
         if V > 16:
             raise NotImplementedError("camera head kernels handle up to 16 views per scene")
         per_batch = []
+        dev = self.device
+
+        def buf(n):  # 16-row padded token matrix (rows >= V stay zero): B operand of the weight-streaming GEMMs
+            return torch.zeros((16, n), dtype=torch.float32, device=dev)
+
         for b in range(B):
             cam_rows = inter_last.view(B, V, P, C2)[b, :, 0]  # [V, C2] view, row stride P*C2
             tok = ops.layernorm(cam_rows, mul=w["cam.token_norm.w"], add=w["cam.token_norm.b"], eps=1e-5, out_dtype=torch.float32)
             pred = None
             outs = []
+            emb, h, x, att16 = buf(C2), buf(C2), buf(C2), buf(C2)
             for _ in range(iters):
                 inp = w["cam.empty"].expand(V, -1).contiguous() if pred is None else pred
-                emb = ops.skinny_linear(inp, w["cam.embed.w"], w["cam.embed.b"], out_dtype=torch.float32)
-                mod = ops.skinny_linear(emb, w["cam.mod.w"], w["cam.mod.b"], pre_act="silu", out_dtype=torch.float32)  # shift | scale | gate
-                mlo = ops.layernorm(tok, mul=mod[:, C2:2 * C2], add=mod[:, :C2], mul_bstride=3 * C2, add_bstride=3 * C2, rows_per_batch=1,
+                # poseLN_modulation = Sequential(SiLU, Linear): the embedding is only consumed through the SiLU
+                ops.skinny_linear(inp, w["cam.embed.w"], w["cam.embed.b"], act="silu", out=emb[:V])
+                mod = ops.linear_tokens16(emb, V, w["cam.mod.w"], w["cam.mod.b"])  # shift | scale | gate
+                mlo = ops.layernorm(tok, mul=mod[:V, C2:2 * C2], add=mod[:V, :C2], mul_bstride=3 * C2, add_bstride=3 * C2, rows_per_batch=1,
                                     eps=1e-6, mul_plus_one=True, out_dtype=torch.float32)
-                x = ops.fma_rows(mod[:, 2 * C2:], mlo, tok)
+                ops.fma_rows(mod[:V, 2 * C2:], mlo, tok, out=x[:V])
                 for i in range(cfg.cam_trunk):
                     p = f"cam{i}."
-                    h = ops.layernorm(x, mul=w[p + "norm1.w"], add=w[p + "norm1.b"], eps=1e-5, out_dtype=torch.float32)
-                    qkv = ops.skinny_linear(h, w[p + "qkv.w"], w[p + "qkv.b"], out_dtype=torch.float32)
-                    att = ops.attention_small(qkv, 1, V, Hn, C2 // Hn)
-                    x = ops.skinny_linear(att, w[p + "proj.w"], w[p + "proj.b"], gate=w[p + "ls1"], residual=x, out_dtype=torch.float32)
-                    h = ops.layernorm(x, mul=w[p + "norm2.w"], add=w[p + "norm2.b"], eps=1e-5, out_dtype=torch.float32)
-                    m = ops.skinny_linear(h, w[p + "fc1.w"], w[p + "fc1.b"], act="gelu_erf", out_dtype=torch.float32)
-                    x = ops.skinny_linear(m, w[p + "fc2.w"], w[p + "fc2.b"], gate=w[p + "ls2"], residual=x, out_dtype=torch.float32)
-                h = ops.layernorm(x, mul=w["cam.trunk_norm.w"], add=w["cam.trunk_norm.b"], eps=1e-5, out_dtype=torch.float32)
-                m = ops.skinny_linear(h, w["cam.fc1.w"], w["cam.fc1.b"], act="gelu_erf", out_dtype=torch.float32)
-                new = torch.zeros((V, 16), dtype=torch.float32, device=self.device)
-                ops.skinny_linear(m, w["cam.fc2.w"], w["cam.fc2.b"], out=new, residual=pred)  # pred + delta (cols 9..15 stay 0)
+                    ops.layernorm(x[:V], mul=w[p + "norm1.w"], add=w[p + "norm1.b"], eps=1e-5, out=h[:V])
+                    qkv = ops.linear_tokens16(h, V, w[p + "qkv.w"], w[p + "qkv.b"])
+                    ops.attention_small(qkv[:V], 1, V, Hn, C2 // Hn, out=att16[:V])
+                    ops.linear_tokens16(att16, V, w[p + "proj.w"], w[p + "proj.b"], gate=w[p + "ls1"], residual=x, out=x)
+                    ops.layernorm(x[:V], mul=w[p + "norm2.w"], add=w[p + "norm2.b"], eps=1e-5, out=h[:V])
+                    m = ops.linear_tokens16(h, V, w[p + "fc1.w"], w[p + "fc1.b"], act="gelu_erf")
+                    ops.linear_tokens16(m, V, w[p + "fc2.w"], w[p + "fc2.b"], gate=w[p + "ls2"], residual=x, out=x)
+                ops.layernorm(x[:V], mul=w["cam.trunk_norm.w"], add=w["cam.trunk_norm.b"], eps=1e-5, out=h[:V])
+                m = ops.linear_tokens16(h, V, w["cam.fc1.w"], w["cam.fc1.b"], act="gelu_erf")
+                new = torch.zeros((V, 16), dtype=torch.float32, device=dev)
+                ops.skinny_linear(m[:V], w["cam.fc2.w"], w["cam.fc2.b"], out=new, residual=pred)  # pred + delta (cols 9..15 stay 0)
                 pred = new
                 outs.append(pred)
             per_batch.append(outs)
