@@ -34,7 +34,7 @@ extern "C" {
 #define VIST3A_DTYPE_F32 1
 
 const char* vist3a_last_error(void);
-int vist3a_abi_version(void);
+int vist3a_abi_version(void); /* 3 */
 /* number of kernels this library has launched from the calling process (all threads) */
 int64_t vist3a_launch_count(void);
 
@@ -69,11 +69,18 @@ typedef struct vist3a_rowmap {
 /* implicit-GEMM convolution over an NHWC activation (A operand fetched by 4-D TMA, zero padding by out-of-bounds fill):
  *   A = x[n_img, h_in, w_in, c_in];  W = [N, kh*kw*c_in] with k = (dy*kw + dx)*c_in + c;  stride 1;
  *   output row = pixel (n, y, x) of the h_out x w_out map, M = n_img*h_out*w_out.
- * replaces: the 3x3 nn.Conv2d layers of AS/model/encoder/vggt/heads/dpt_head.py:346-359,375-376,437-439 (cuDNN). */
+ * pix_stride / row_stride / img_stride (elements, multiples of 4 floats / 8 bf16; 0 = dense NHWC) describe where pixel
+ * (n, y, x) starts.  A pix_stride smaller than c_in gives OVERLAPPING windows: with a 4-channel (RGB0) image whose rows are
+ * physically zero-padded, c_in = 32, pix_stride = 4, kw = 1 one TMA box row holds the 8 horizontal taps x 4 channels of a
+ * pixel, i.e. a 7x7 RGB convolution becomes kh = 7 k-blocks without any im2col buffer.
+ * replaces: the 3x3 nn.Conv2d layers of AS/model/encoder/vggt/heads/dpt_head.py:346-359,375-376,437-439 and the 7x7
+ *   input_merger of AS/model/encoder/heads/vggt_dpt_gs_head.py:73-76 (cuDNN). */
 typedef struct vist3a_conv {
   int32_t enabled;
-  int32_t kh, kw, pad;
-  int32_t n_img, h, w, c_in; /* stride-1 "same"-style conv: h_out = h + 2*pad - kh + 1 */
+  int32_t kh, kw, pad_y, pad_x;
+  int32_t n_img, h, w, c_in; /* stride-1 conv: h_out = h + 2*pad_y - kh + 1, w_out = w + 2*pad_x - kw + 1 */
+  int32_t reserved;
+  int64_t pix_stride, row_stride, img_stride;
 } vist3a_conv;
 
 typedef struct vist3a_gemm_args {
@@ -218,6 +225,13 @@ int vist3a_im2col_stitch(const void* latent, int32_t dtype, void* A, int64_t B, 
  * (AS/model/encoder/heads/vggt_dpt_gs_head.py:73-76) and the stride-2 3x3 resize conv (dpt_head.py:85-90). */
 int vist3a_im2col_nhwc(const float* x, float* A, int64_t ldA, int64_t n_img, int64_t h, int64_t w, int64_t C,
                        int32_t kh, int32_t kw, int32_t stride, int32_t pad, void* stream);
+
+/* RGB views -> zero-padded 4-channel NHWC image for the overlapping-window 7x7 convolution (see vist3a_conv):
+ *   image [B, 3, V, H, W] in [-1, 1] (fp32 or bf16)  ->  out [B*V, H, W + 8, 4] fp32,
+ *   out[(b,v), y, 3 + x, c] = (image[b, c, v, y, x] + 1) / 2 for c < 3, zero elsewhere.
+ * replaces: "context_image = (rearrange(context_image, 'b c v h w -> b v c h w') + 1) / 2" (models/anysplat_stitched.py:172-174)
+ *   and the zero padding of the 7x7 input_merger convolution. */
+int vist3a_rgb_to_nhwc4pad(const void* image, int32_t dtype, float* out, int64_t B, int64_t V, int64_t H, int64_t W, void* stream);
 
 /* per-head LayerNorm(head_dim = 64) of q and k + 2-D rotary embedding, in place on a fused bf16 [rows, 3*heads*64] qkv buffer.
  *   token p = row % tokens_per_view; p < n_special: position (0,0); else (1 + (p-n_special)/grid_w, 1 + (p-n_special)%grid_w)

@@ -126,6 +126,26 @@ def test_im2col_nhwc(ops, kh, stride, pad, C, kpad):
         assert float(out[:, kh * kh * C:].abs().max()) == 0.0
 
 
+@pytest.mark.parametrize("B,V,H,W,dtype", [(1, 2, 20, 36, torch.float32), (2, 3, 56, 56, torch.bfloat16), (1, 1, 224, 232, torch.float32)])
+def test_rgb7x7_overlapping_window_conv(ops, B, V, H, W, dtype):
+    """7x7 RGB input_merger without im2col: RGB0 image with physically padded rows, TMA boxes over overlapping windows"""
+    g = torch.Generator(device="cuda").manual_seed(19)
+    img = (torch.rand(B, 3, V, H, W, device="cuda", generator=g) * 2 - 1).to(dtype)
+    wt = torch.randn(128, 3, 7, 7, device="cuda", generator=g) / math.sqrt(147)
+    b = torch.randn(128, device="cuda", generator=g)
+    x01 = (img.float().permute(0, 2, 1, 3, 4).reshape(B * V, 3, H, W) + 1) / 2
+    ref = torch.relu(F.conv2d(x01.double(), wt.double(), b.double(), padding=3)).permute(0, 2, 3, 1)
+    rgb = ops.rgb_to_nhwc4pad(img)
+    assert rgb.shape == (B * V, H, W + 8, 4)
+    assert torch.equal(rgb[:, :, 3:3 + W, :3], x01.permute(0, 2, 3, 1)) and float(rgb[:, :, :3].abs().max()) == 0 and float(rgb[..., 3].abs().max()) == 0
+    mk = torch.zeros(128, 7, 8, 4, device="cuda")
+    mk[:, :, :7, :3] = wt.permute(0, 2, 3, 1)
+    out = torch.empty(B * V, H, W, 128, device="cuda")
+    ops.gemm(rgb, mk.reshape(128, 224), b, act="relu", out=out.view(-1, 128),
+             conv=dict(kh=7, kw=1, pad=3, pad_x=0, geom=(B * V, H, W, 32), strides=(4, (W + 8) * 4, H * (W + 8) * 4)))
+    assert _rel_l2(out, ref) < 1.5e-3
+
+
 def test_qknorm_rope2d_matches_oracle(ops):
     from oracle import decoder_ref as D
 

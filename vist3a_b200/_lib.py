@@ -43,6 +43,7 @@ EXPORTS = (
     "vist3a_attention_small",
     "vist3a_fma_rows",
     "vist3a_bias_act_t",
+    "vist3a_rgb_to_nhwc4pad",
     "vist3a_pose_to_cameras",
     "vist3a_gaussian_epilogue",
 )
@@ -53,8 +54,9 @@ class RowMap(C.Structure):
 
 
 class Conv(C.Structure):
-    _fields_ = [("enabled", C.c_int32), ("kh", C.c_int32), ("kw", C.c_int32), ("pad", C.c_int32), ("n_img", C.c_int32),
-                ("h", C.c_int32), ("w", C.c_int32), ("c_in", C.c_int32)]
+    _fields_ = [("enabled", C.c_int32), ("kh", C.c_int32), ("kw", C.c_int32), ("pad_y", C.c_int32), ("pad_x", C.c_int32),
+                ("n_img", C.c_int32), ("h", C.c_int32), ("w", C.c_int32), ("c_in", C.c_int32), ("reserved", C.c_int32),
+                ("pix_stride", C.c_int64), ("row_stride", C.c_int64), ("img_stride", C.c_int64)]
 
 
 class GemmArgs(C.Structure):
@@ -165,6 +167,7 @@ def load(build_if_missing: bool = False) -> C.CDLL:
     lib.vist3a_depth_to_space.argtypes = [vp, vp, i64, i64, i64, i64, i32, vp]
     lib.vist3a_attention_small.argtypes = [vp, vp, i64, i64, i64, i64, f32, vp]
     lib.vist3a_fma_rows.argtypes = [vp, i64, vp, i64, vp, i64, vp, i64, i64, i64, vp]
+    lib.vist3a_rgb_to_nhwc4pad.argtypes = [vp, i32, vp, i64, i64, i64, i64, vp]
     lib.vist3a_bias_act_t.argtypes = [vp, i64, vp, i32, vp, vp, i64, vp, i64, i64, i64, vp]
     lib.vist3a_pose_to_cameras.argtypes = [vp, vp, vp, vp, vp, vp, i64, i64, i64, vp]
     lib.vist3a_gaussian_epilogue.argtypes = [vp, i64, i64, vp, f32, vp, i64, vp, vp, vp, i64, i64, i64, i64, vp, vp, vp, vp, vp, vp,

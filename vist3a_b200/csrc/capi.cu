@@ -27,6 +27,7 @@ int depth_to_space_entry(const float*, float*, long long, long long, long long, 
 int attention_small_entry(const float*, float*, long long, long long, long long, long long, float, cudaStream_t);
 int bias_act_t_entry(const float*, long long, const float*, int, const float*, const float*, long long, float*, long long, long long,
                      long long, cudaStream_t);
+int rgb_to_nhwc4pad_entry(const void*, int, float*, long long, long long, long long, long long, cudaStream_t);
 int fma_rows_entry(float*, long long, const float*, long long, const float*, long long, const float*, long long, long long,
                    long long, cudaStream_t);
 int pose_to_cameras_entry(const float*, float*, float*, float*, float*, float*, long long, long long, long long, cudaStream_t);
@@ -138,7 +139,7 @@ using namespace v3a;
 extern "C" {
 
 const char* vist3a_last_error(void) { return last_error_buf(); }
-int vist3a_abi_version(void) { return 2; }
+int vist3a_abi_version(void) { return 3; }
 int64_t vist3a_launch_count(void) { return (int64_t)launch_counter().load(); }
 
 int vist3a_gemm(const vist3a_gemm_args* args, void* stream) { return gemm_entry(args, ST(stream)); }
@@ -228,6 +229,9 @@ int vist3a_fma_rows(float* out, int64_t ldo, const float* a, int64_t lda, const 
 int vist3a_bias_act_t(const float* ct, int64_t ldct, const float* bias, int32_t act, const float* gate, const float* residual,
                       int64_t ldr, float* y, int64_t ldy, int64_t M, int64_t N, void* stream) {
   return bias_act_t_entry(ct, ldct, bias, act, gate, residual, ldr, y, ldy, M, N, ST(stream));
+}
+int vist3a_rgb_to_nhwc4pad(const void* image, int32_t dtype, float* out, int64_t B, int64_t V, int64_t H, int64_t W, void* stream) {
+  return rgb_to_nhwc4pad_entry(image, dtype, out, B, V, H, W, ST(stream));
 }
 int vist3a_pose_to_cameras(const float* pose_raw, float* pose_act, float* extr, float* intr, float* c2w,
                            float* intr_norm, int64_t S, int64_t H, int64_t W, void* stream) {

@@ -335,6 +335,21 @@ __device__ __forceinline__ float gelu_tanh_precise_f(float x) {
   return 0.5f * x * (1.0f + tanhf(u));
 }
 __device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+// GELU(erf) for the GEMM epilogue: erf by Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7) with MUFU.RCP + MUFU.EX2 instead
+// of erff()'s ~25-instruction branchy expansion; 1 + erf(x/sqrt2) is formed without cancellation for x < 0.
+__device__ __forceinline__ float gelu_erf_fast_f(float x) {
+  const float u = fabsf(x) * 0.70710678118654752f;
+  float t, e;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, u, 1.0f)));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * u * u));
+  float q = fmaf(1.061405429f, t, -1.453152027f);
+  q = fmaf(q, t, 1.421413741f);
+  q = fmaf(q, t, -0.284496736f);
+  q = fmaf(q, t, 0.254829592f);
+  q = q * t * e;                       // 1 - erf(u)
+  const float h = 0.5f * q;
+  return x * (x >= 0.0f ? 1.0f - h : h);
+}
 __device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 
 }  // namespace v3a

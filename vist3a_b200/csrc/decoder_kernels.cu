@@ -76,6 +76,45 @@ int im2col_stitch_entry(const void* lat, int dt, void* A, long long B, long long
 }
 
 // ----------------------------------------------------------------------------------------
+// RGB views [B,3,V,H,W] in [-1,1] -> zero-padded RGB0 NHWC image [B*V, H, W+8, 4] in [0,1] (3 zero pixels left, 5 right)
+// ----------------------------------------------------------------------------------------
+template <bool kF32>
+__global__ void __launch_bounds__(256) rgb_to_nhwc4pad_kernel(const void* __restrict__ img, float4* __restrict__ out, int B, int V, int H, int W) {
+  const int Wp = W + 8;
+  const long long total = (long long)B * V * H * Wp;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int xp = (int)(i % Wp);
+  const int y = (int)((i / Wp) % H);
+  const long long n = i / ((long long)Wp * H);
+  const int v = (int)(n % V), b = (int)(n / V);
+  float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int x = xp - 3;
+  if (x >= 0 && x < W) {
+    const long long plane = (long long)H * W;
+    const long long base = (((long long)b * 3) * V + v) * plane + (long long)y * W + x;  // channel stride = V * plane
+    float c[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const long long idx = base + (long long)k * V * plane;
+      c[k] = kF32 ? reinterpret_cast<const float*>(img)[idx] : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(img)[idx]);
+    }
+    o = make_float4((c[0] + 1.0f) * 0.5f, (c[1] + 1.0f) * 0.5f, (c[2] + 1.0f) * 0.5f, 0.f);
+  }
+  out[i] = o;
+}
+
+int rgb_to_nhwc4pad_entry(const void* img, int dt, float* out, long long B, long long V, long long H, long long W, cudaStream_t st) {
+  V3A_REQUIRE(img && out && B > 0 && V > 0 && H > 0 && W > 0, VIST3A_ERR_INVALID, "rgb_to_nhwc4pad: bad arguments");
+  const long long total = B * V * H * (W + 8);
+  if (dt == VIST3A_DTYPE_F32) rgb_to_nhwc4pad_kernel<true><<<grid_for(total, 256), 256, 0, st>>>(img, (float4*)out, (int)B, (int)V, (int)H, (int)W);
+  else rgb_to_nhwc4pad_kernel<false><<<grid_for(total, 256), 256, 0, st>>>(img, (float4*)out, (int)B, (int)V, (int)H, (int)W);
+  V3A_CUDA_OK(cudaGetLastError());
+  launch_counter().fetch_add(1);
+  return VIST3A_OK;
+}
+
+// ----------------------------------------------------------------------------------------
 // generic NHWC im2col (fp32)
 // ----------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) im2col_nhwc_kernel(const float* __restrict__ x, float* __restrict__ A, long long ldA,

@@ -47,7 +47,7 @@ struct GemmShape {
   int M, N, K;
   int tiles_m, tiles_n;  // tiles_m counts 128*kCta-row tiles
   // conv mode
-  int conv, kh, kw, pad, n_img, h, w, c_in, h_out, w_out, tiles_x, tiles_y, cblocks;
+  int conv, kh, kw, pad_y, pad_x, n_img, h, w, c_in, h_out, w_out, tiles_x, tiles_y, cblocks;
 };
 
 template <int BN, int kCta, bool kTF32>
@@ -72,7 +72,7 @@ __device__ __forceinline__ void act32(float (&v)[32]) {
 #pragma unroll
   for (int j = 0; j < 32; ++j) {
     if constexpr (ACT == VIST3A_ACT_GELU_TANH) v[j] = gelu_tanh_f(v[j]);
-    else if constexpr (ACT == VIST3A_ACT_GELU_ERF) v[j] = gelu_erf_f(v[j]);
+    else if constexpr (ACT == VIST3A_ACT_GELU_ERF) v[j] = gelu_erf_fast_f(v[j]);
     else if constexpr (ACT == VIST3A_ACT_SILU) v[j] = silu_f(v[j]);
     else if constexpr (ACT == VIST3A_ACT_RELU) v[j] = fmaxf(v[j], 0.0f);
   }
@@ -182,8 +182,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int per_img = shape.tiles_x * shape.tiles_y;
         img = mt / per_img;
         const int t2 = mt % per_img;
-        y0 = (t2 / shape.tiles_x) * kConvTH - shape.pad;
-        x0 = (t2 % shape.tiles_x) * kConvTW - shape.pad;
+        y0 = (t2 / shape.tiles_x) * kConvTH - shape.pad_y;
+        x0 = (t2 % shape.tiles_x) * kConvTW - shape.pad_x;
       }
       int cb = 0, dy = 0, dx = 0;
       for (int kb = 0; kb < num_kb; ++kb) {
@@ -378,17 +378,20 @@ static int launch_gemm(const vist3a_gemm_args& a, cudaStream_t stream) {
   shape.M = (int)a.M; shape.N = (int)a.N; shape.K = (int)a.K;
   if (a.conv.enabled) {
     const vist3a_conv& c = a.conv;
-    shape.conv = 1; shape.kh = c.kh; shape.kw = c.kw; shape.pad = c.pad;
+    shape.conv = 1; shape.kh = c.kh; shape.kw = c.kw; shape.pad_y = c.pad_y; shape.pad_x = c.pad_x;
     shape.n_img = c.n_img; shape.h = c.h; shape.w = c.w; shape.c_in = c.c_in;
-    shape.h_out = c.h + 2 * c.pad - c.kh + 1;
-    shape.w_out = c.w + 2 * c.pad - c.kw + 1;
+    shape.h_out = c.h + 2 * c.pad_y - c.kh + 1;
+    shape.w_out = c.w + 2 * c.pad_x - c.kw + 1;
     shape.tiles_x = (shape.w_out + kConvTW - 1) / kConvTW;
     shape.tiles_y = (shape.h_out + kConvTH - 1) / kConvTH;
     shape.cblocks = c.c_in / Cfg::BK;
     const long long mtiles = (long long)c.n_img * shape.tiles_x * shape.tiles_y;
     shape.tiles_m = (int)((mtiles + kCta - 1) / kCta);
     uint64_t dims[4] = {(uint64_t)c.c_in, (uint64_t)c.w, (uint64_t)c.h, (uint64_t)c.n_img};
-    uint64_t strides[3] = {(uint64_t)c.c_in * Cfg::ES, (uint64_t)c.w * c.c_in * Cfg::ES, (uint64_t)c.h * c.w * c.c_in * Cfg::ES};
+    const uint64_t pix = c.pix_stride ? (uint64_t)c.pix_stride : (uint64_t)c.c_in;
+    const uint64_t row = c.row_stride ? (uint64_t)c.row_stride : (uint64_t)c.w * c.c_in;
+    const uint64_t im = c.img_stride ? (uint64_t)c.img_stride : (uint64_t)c.h * c.w * c.c_in;
+    uint64_t strides[3] = {pix * Cfg::ES, row * Cfg::ES, im * Cfg::ES};
     uint32_t box[4] = {(uint32_t)Cfg::BK, (uint32_t)kConvTW, (uint32_t)kConvTH, 1};
     int rc = encode_tensor_map(&tmA, a.A, Cfg::ES, kTF32, 4, dims, strides, box, true);
     if (rc) return rc;
@@ -465,11 +468,13 @@ int gemm_entry(const vist3a_gemm_args* args, cudaStream_t stream) {
   if (a.conv.enabled) {
     const vist3a_conv& c = a.conv;
     const int bk = 128 / es;
-    V3A_REQUIRE(c.kh > 0 && c.kw > 0 && c.pad >= 0 && c.n_img > 0 && c.h > 0 && c.w > 0 && c.c_in > 0, VIST3A_ERR_INVALID,
+    V3A_REQUIRE(c.kh > 0 && c.kw > 0 && c.pad_y >= 0 && c.pad_x >= 0 && c.n_img > 0 && c.h > 0 && c.w > 0 && c.c_in > 0, VIST3A_ERR_INVALID,
                 "gemm(conv): bad geometry");
+    V3A_REQUIRE(c.pix_stride >= 0 && c.row_stride >= 0 && c.img_stride >= 0 && (c.pix_stride * es) % 16 == 0 && (c.row_stride * es) % 16 == 0 &&
+                    (c.img_stride * es) % 16 == 0, VIST3A_ERR_INVALID, "gemm(conv): pixel / row / image strides must be multiples of 16 bytes");
     V3A_REQUIRE(c.c_in % bk == 0, VIST3A_ERR_UNSUPPORTED, "gemm(conv): c_in (%d) must be a multiple of %d", c.c_in, bk);
     V3A_REQUIRE(a.K == (int64_t)c.kh * c.kw * c.c_in, VIST3A_ERR_INVALID, "gemm(conv): K must equal kh*kw*c_in");
-    const long long ho = c.h + 2 * c.pad - c.kh + 1, wo = c.w + 2 * c.pad - c.kw + 1;
+    const long long ho = c.h + 2 * c.pad_y - c.kh + 1, wo = c.w + 2 * c.pad_x - c.kw + 1;
     V3A_REQUIRE(ho > 0 && wo > 0 && a.M == (int64_t)c.n_img * ho * wo, VIST3A_ERR_INVALID, "gemm(conv): M must equal n_img*h_out*w_out");
   } else {
     V3A_REQUIRE(a.lda >= a.K && a.lda % kalign == 0, VIST3A_ERR_INVALID,

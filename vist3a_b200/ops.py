@@ -54,16 +54,19 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
          cmap: Optional[tuple] = None, rmap: Optional[tuple] = None, conv: Optional[dict] = None) -> torch.Tensor:
     """out[M,N] = epilogue(a[M,K] @ w[N,K]^T); see vist3a_gemm in include/vist3a_sm100.h.
     cmap / rmap = (rows_per_group, group_stride, group_offset) row maps of out(+residual2) / residual;
-    conv = dict(kh, kw, pad) with `a` an NHWC [n, h, w, c] tensor: implicit-GEMM convolution (stride 1)."""
+    conv = dict(kh, kw, pad) with `a` an NHWC [n, h, w, c] tensor: implicit-GEMM convolution (stride 1).  Optional conv keys
+    pad_x, geom=(n, h, w, c_in) and strides=(pixel, row, image) in elements describe overlapping windows over a physically
+    padded image (see vist3a_conv in the header)."""
     _need_cuda(a, w, bias, gate, residual, residual2, out)
     w2 = _rows2d(w)
     N, K2 = w2.shape
     if conv is not None:
         if a.dim() != 4 or not a.is_contiguous():
             raise ValueError("gemm(conv): a must be a contiguous NHWC [n, h, w, c] tensor")
-        n_img, h_in, w_in, c_in = a.shape
+        n_img, h_in, w_in, c_in = conv.get("geom", a.shape)
         kh, kw, pad = conv["kh"], conv["kw"], conv["pad"]
-        h_out, w_out = h_in + 2 * pad - kh + 1, w_in + 2 * pad - kw + 1
+        pad_x = conv.get("pad_x", pad)
+        h_out, w_out = h_in + 2 * pad - kh + 1, w_in + 2 * pad_x - kw + 1
         M, K = n_img * h_out * w_out, kh * kw * c_in
         a2 = a
     else:
@@ -105,8 +108,10 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
     if rmap is not None:
         args.rmap.rpg, args.rmap.gstride, args.rmap.goff = rmap
     if conv is not None:
-        args.conv.enabled, args.conv.kh, args.conv.kw, args.conv.pad = 1, kh, kw, pad
+        args.conv.enabled, args.conv.kh, args.conv.kw, args.conv.pad_y, args.conv.pad_x = 1, kh, kw, pad, pad_x
         args.conv.n_img, args.conv.h, args.conv.w, args.conv.c_in = n_img, h_in, w_in, c_in
+        if "strides" in conv:
+            args.conv.pix_stride, args.conv.row_stride, args.conv.img_stride = conv["strides"]
     args.post_act = ACT[post_act]
     args.ldr = r2.stride(0) if r2 is not None else 0
     args.rows_per_batch = rows_per_batch if rows_per_batch > 0 else M
@@ -282,6 +287,18 @@ def im2col_stitch(latent: torch.Tensor) -> torch.Tensor:
     return A
 
 
+def rgb_to_nhwc4pad(image: torch.Tensor) -> torch.Tensor:
+    """image [B, 3, V, H, W] in [-1, 1] -> zero-padded RGB0 image [B*V, H, W+8, 4] fp32 in [0, 1] (3 zero pixels left, 5 right)."""
+    _need_cuda(image)
+    image = image.contiguous()
+    B, Cc, V, H, W = image.shape
+    if Cc != 3:
+        raise ValueError("rgb_to_nhwc4pad: expected 3 colour channels")
+    out = torch.empty((B * V, H, W + 8, 4), dtype=torch.float32, device=image.device)
+    L.check(L.load().vist3a_rgb_to_nhwc4pad(image.data_ptr(), _dt(image), out.data_ptr(), B, V, H, W, _stream()))
+    return out
+
+
 def im2col_nhwc(x: torch.Tensor, kh: int, kw: int, stride: int, pad: int, k_pad: Optional[int] = None) -> torch.Tensor:
     """x NHWC fp32 -> [n*ho*wo, k_pad] fp32 with column (dy*kw+dx)*C + c (zero beyond kh*kw*C)."""
     _need_cuda(x)
@@ -439,8 +456,8 @@ class OpTimer:
             M = out.numel() // N if kw.get("cmap") is None else (a.numel() // a.shape[-1])
             if kw.get("conv") is not None:
                 cv = kw["conv"]
-                n_, h_, w_, _ = a.shape
-                M = n_ * (h_ + 2 * cv["pad"] - cv["kh"] + 1) * (w_ + 2 * cv["pad"] - cv["kw"] + 1)
+                n_, h_, w_, _ = cv.get("geom", a.shape)
+                M = n_ * (h_ + 2 * cv["pad"] - cv["kh"] + 1) * (w_ + 2 * cv.get("pad_x", cv["pad"]) - cv["kw"] + 1)
             by = M * K * a.element_size() + N * K * w.element_size() + M * N * out.element_size()
             ep = ("+" + kw["act"] if kw.get("act") else "") + ("+gate" if kw.get("gate") is not None else "") + (
                 "+res" if kw.get("residual") is not None else "")
@@ -464,7 +481,7 @@ class OpTimer:
                  "rmsnorm_rope_": io_cost("rmsnorm_rope"), "modulation": io_cost("small"), "skinny_linear": io_cost("small"),
                  "timestep_features": io_cost("small"), "patchify": io_cost("small"), "unpatchify": io_cost("small"),
                  "cfg_combine": io_cost("small"), "axpby_n": io_cost("small"), "im2col_stitch": io_cost("im2col"),
-                 "im2col_nhwc": io_cost("im2col"), "qknorm_rope2d_": io_cost("qknorm_rope2d"), "bilinear_nhwc": io_cost("bilinear"),
+                 "im2col_nhwc": io_cost("im2col"), "rgb_to_nhwc4pad": io_cost("small"), "qknorm_rope2d_": io_cost("qknorm_rope2d"), "bilinear_nhwc": io_cost("bilinear"),
                  "depth_to_space": io_cost("depth_to_space"), "attention_small": io_cost("small"), "fma_rows": io_cost("small"),
                  "pose_to_cameras": io_cost("small"), "linear_tokens16": io_cost("linear_tokens16"), "gaussian_epilogue": io_cost("gaussian_epilogue")}
         for name, cost in table.items():

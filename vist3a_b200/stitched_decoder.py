@@ -316,9 +316,11 @@ class StitchVAE3DB200(torch.nn.Module):
         g = E + "gaussian_param_head."
         w["gh.oc2b.w"] = f32(sd[g + "scratch.output_conv2.2.weight"].flatten(1))
         w["gh.oc2b.b"] = f32(sd[g + "scratch.output_conv2.2.bias"])
-        mw = _conv_w(sd[g + "input_merger.0.weight"].detach().float())  # [128, 147]
-        self._merger_k = (mw.shape[1] + 3) // 4 * 4
-        w["gh.merger.w"] = f32(F.pad(mw, (0, self._merger_k - mw.shape[1])))
+        # 7x7 RGB input_merger as 7 k-blocks of an overlapping-window implicit GEMM: k = dy*32 + dx*4 + c (dx < 7, c < 3; rest zero)
+        mw = sd[g + "input_merger.0.weight"].detach().float()            # [128, 3, 7, 7]
+        mk = torch.zeros((mw.shape[0], 7, 8, 4), dtype=torch.float32)
+        mk[:, :, :7, :3] = mw.permute(0, 2, 3, 1).cpu()
+        w["gh.merger.w"] = f32(mk.reshape(mw.shape[0], 224))
         w["gh.merger.b"] = f32(sd[g + "input_merger.0.bias"])
         m = torch.ones(cfg.d_sh)
         for deg in range(1, cfg.sh_degree + 1):  # AS/model/encoder/common/gaussian_adapter.py:34-40
@@ -568,10 +570,13 @@ class StitchVAE3DB200(torch.nn.Module):
         dfeat = self._conv3(d, w["dh.oc2a.w"], w["dh.oc2a.b"], act="relu")
         del d
         # --- Gaussian head
-        img01 = ((feedforward_image.to(dev, torch.float32).permute(0, 2, 3, 4, 1) + 1) / 2).reshape(BV, H, W, ci).contiguous()
-        a = ops.im2col_nhwc(img01, 7, 7, 1, 3, k_pad=self._merger_k)
-        merged = ops.gemm(a, w["gh.merger.w"], w["gh.merger.b"], act="relu")
-        del a
+        if feedforward_image.dtype not in (torch.float32, torch.bfloat16):
+            feedforward_image = feedforward_image.float()
+        rgb = ops.rgb_to_nhwc4pad(feedforward_image.to(dev))              # [BV, H, W+8, 4] in [0, 1], rows zero-padded
+        merged = torch.empty((BV * H * W, w["gh.merger.w"].shape[0]), dtype=torch.float32, device=dev)
+        ops.gemm(rgb, w["gh.merger.w"], w["gh.merger.b"], act="relu", out=merged,
+                 conv=dict(kh=7, kw=1, pad=3, pad_x=0, geom=(BV, H, W, 32), strides=(4, (W + 8) * 4, H * (W + 8) * 4)))
+        del rgb
         g = self._dpt_trunk("gh.", inters, BV, gh, gw, tb)
         del inters
         g = ops.bilinear_nhwc(g, H, W, add=merged, pos_x=tb.full_px, pos_y=tb.full_py)
