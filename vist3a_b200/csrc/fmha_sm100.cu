@@ -74,6 +74,11 @@ __device__ __forceinline__ uint64_t pack2(float lo, float hi) {
 __device__ __forceinline__ void unpack2(uint64_t v, float& lo, float& hi) {
   asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
 }
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {  // packed 2 x fp32 FADD2
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
 __device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {  // packed 2 x fp32 FFMA2
   uint64_t d;
   asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
@@ -335,7 +340,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         tc_fence_after();
         const float nmc = -m_run * c;
         const uint64_t mc2 = pack2(nmc, nmc);
-        float sum[4] = {0.f, 0.f, 0.f, 0.f};
+        uint64_t sum2[2] = {0ull, 0ull};  // packed (even, odd) column partial sums
         const uint32_t p_addr = tile_base + Cfg::TM_P + (uint32_t)(j & 1) * Cfg::P_STRIDE;
 #pragma unroll
         for (int cb = 0; cb < BKV / 32; ++cb) {
@@ -350,13 +355,17 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
               e0 = ex2_approx(y0);
               e1 = ex2_approx(y1);
             }
-            sum[(2 * k) & 3] += e0;
-            sum[(2 * k + 1) & 3] += e1;
+            sum2[k & 1] = add2(sum2[k & 1], pack2(e0, e1));
             pk[k] = pack_bf16(e0, e1);
           }
           tmem_st_x16(p_addr + (uint32_t)(cb * 16), pk);
         }
-        l_run += (sum[0] + sum[1]) + (sum[2] + sum[3]);
+        {
+          float s0, s1, s2, s3;
+          unpack2(sum2[0], s0, s1);
+          unpack2(sum2[1], s2, s3);
+          l_run += (s0 + s1) + (s2 + s3);
+        }
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
