@@ -128,6 +128,7 @@ typedef struct vist3a_fmha_args {
   int64_t o_bs, o_rs, o_hs;
   float scale; /* multiplies QK^T; 1/sqrt(head_dim) in both references */
   uint32_t flags;
+  const float* q_row_scale; /* optional [batch * len_q] fp32: extra positive factor on the logits of query row (b, i), all heads */
 } vist3a_fmha_args;
 
 int vist3a_fmha_fwd(const vist3a_fmha_args* args, void* stream);
@@ -152,9 +153,18 @@ int vist3a_layernorm(const void* x, int32_t x_dtype, int64_t ldx, void* out, int
  * replaces: diffusers WanAttnProcessor2_0: attn.norm_q / norm_k (RMSNorm "rms_norm_across_heads",
  *   eps 1e-6) and apply_rotary_emb with WanRotaryPosEmbed frequencies.
  * cos/sin: [rope_len, head_dim/2] fp32, or NULL for no RoPE (cross-attention).
+ * nseg > 1 processes nseg column segments of the same rows in one launch (q and k of a fused qkv buffer): segment s starts
+ * at column s * seg_stride and uses weight[s * dim : (s + 1) * dim].
  * ------------------------------------------------------------------------------------------ */
 int vist3a_rmsnorm_rope(void* x, int64_t ldx, int64_t rows, int64_t dim, int64_t head_dim, const float* weight,
-                        float eps, const float* rope_cos, const float* rope_sin, int64_t rope_len, void* stream);
+                        float eps, const float* rope_cos, const float* rope_sin, int64_t rope_len, int64_t nseg,
+                        int64_t seg_stride, void* stream);
+
+/* out[r] = rsqrt(mean(x[r, 0:dim]^2) + eps) for a bf16 matrix (read-only pass).  With vist3a_fmha_args.q_row_scale this is the
+ * RMSNorm of the cross-attention queries: (q * rinv_r * w_q) . k == rinv_r * (q . (w_q * k)), so the per-row factor scales
+ * the logits inside the attention kernel and w_q is folded into the (per-prompt cached) text keys.
+ * replaces: attn2.norm_q of diffusers WanAttnProcessor2_0. */
+int vist3a_row_rinv(const void* x, int64_t ldx, int64_t rows, int64_t dim, float eps, float* out, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * AdaLN modulation vectors:  out[b, j, :] = table[j, :] + mod[b, j, :] (+ 1 where bit j of

@@ -197,6 +197,41 @@ def test_rmsnorm_rope(ops):
     assert _rel_l2(y.float(), yf * torch.rsqrt(yf.pow(2).mean(-1, keepdim=True) + 1e-6) * w) < 4e-3
 
 
+def test_rmsnorm_rope_two_segments_one_launch(ops):
+    """q and k of a fused qkv buffer normalised + rotated by ONE launch == two single-segment launches"""
+    g = torch.Generator(device="cuda").manual_seed(8)
+    L_, H, D = 64, 4, 128
+    dim = H * D
+    buf = torch.randn(2 * L_, 3 * dim, device="cuda", generator=g).bfloat16()
+    wq, wk = torch.randn(dim, device="cuda", generator=g), torch.randn(dim, device="cuda", generator=g)
+    ang = torch.rand(L_, D // 2, device="cuda", generator=g) * 6.28
+    cos, sin = ang.cos().contiguous(), ang.sin().contiguous()
+    a, b = buf.clone(), buf.clone()
+    ops.rmsnorm_rope_(a[:, :dim], wq, D, eps=1e-6, cos=cos, sin=sin)
+    ops.rmsnorm_rope_(a[:, dim:2 * dim], wk, D, eps=1e-6, cos=cos, sin=sin)
+    ops.rmsnorm_rope_(b[:, :2 * dim], torch.cat([wq, wk]), D, eps=1e-6, cos=cos, sin=sin, nseg=2)
+    assert torch.equal(a, b)
+
+
+def test_fmha_row_scale_is_query_rmsnorm(ops):
+    """cross-attention: RMSNorm(q) w_q . k  ==  rinv_q * (q . (w_q k)) with rinv from the read-only row pass"""
+    g = torch.Generator(device="cuda").manual_seed(9)
+    B, H, Lq, Lk, D = 2, 3, 200, 77, 128
+    dim = H * D
+    q = (torch.randn(B * Lq, dim, device="cuda", generator=g) * 3).bfloat16()
+    k = torch.randn(B, Lk, H, D, device="cuda", generator=g).bfloat16()
+    v = torch.randn(B, Lk, H, D, device="cuda", generator=g).bfloat16()
+    wq = 1 + 0.2 * torch.randn(dim, device="cuda", generator=g)
+    rinv = ops.row_rinv(q, eps=1e-6)
+    qf = q.float()
+    assert _rel_l2(rinv, torch.rsqrt(qf.pow(2).mean(-1) + 1e-6)) < 1e-5
+    qn = (qf * torch.rsqrt(qf.pow(2).mean(-1, keepdim=True) + 1e-6) * wq).view(B, Lq, H, D)
+    ref = torch.nn.functional.scaled_dot_product_attention(qn.transpose(1, 2), k.float().transpose(1, 2), v.float().transpose(1, 2)).transpose(1, 2)
+    kw = (k.float() * wq.view(1, 1, H, D)).bfloat16()
+    out = ops.fmha(q.view(B, Lq, H, D), kw, v, q_row_scale=rinv)
+    assert _rel_l2(out.float(), ref) < 1.2e-2   # bf16 rounding of w_q k and of P
+
+
 def test_modulation_and_timestep(ops):
     g = torch.Generator(device="cuda").manual_seed(8)
     B, D = 2, 1536

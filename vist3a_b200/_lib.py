@@ -28,6 +28,7 @@ EXPORTS = (
     "vist3a_fmha_fwd",
     "vist3a_layernorm",
     "vist3a_rmsnorm_rope",
+    "vist3a_row_rinv",
     "vist3a_modulation",
     "vist3a_skinny_linear",
     "vist3a_timestep_features",
@@ -115,6 +116,7 @@ class FmhaArgs(C.Structure):
         ("o_hs", C.c_int64),
         ("scale", C.c_float),
         ("flags", C.c_uint32),
+        ("q_row_scale", C.c_void_p),
     ]
 
 
@@ -152,7 +154,8 @@ def load(build_if_missing: bool = False) -> C.CDLL:
     lib.vist3a_fmha_fwd.argtypes = [C.POINTER(FmhaArgs), C.c_void_p]
     i64, i32, f32, vp, u32 = C.c_int64, C.c_int32, C.c_float, C.c_void_p, C.c_uint32
     lib.vist3a_layernorm.argtypes = [vp, i32, i64, vp, i32, i64, i64, i64, i64, vp, i64, vp, i64, f32, i32, C.POINTER(RowMap), C.POINTER(RowMap), vp]
-    lib.vist3a_rmsnorm_rope.argtypes = [vp, i64, i64, i64, i64, vp, f32, vp, vp, i64, vp]
+    lib.vist3a_rmsnorm_rope.argtypes = [vp, i64, i64, i64, i64, vp, f32, vp, vp, i64, i64, i64, vp]
+    lib.vist3a_row_rinv.argtypes = [vp, i64, i64, i64, f32, vp, vp]
     lib.vist3a_modulation.argtypes = [vp, vp, i32, i32, vp, i64, i64, i64, u32, vp]
     lib.vist3a_skinny_linear.argtypes = [vp, i32, i64, vp, i32, i64, vp, vp, i32, i64, i64, i64, i64, i32, i32, vp, vp, i64, vp]
     lib.vist3a_timestep_features.argtypes = [vp, vp, i32, i64, i64, vp]

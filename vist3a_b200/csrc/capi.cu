@@ -12,7 +12,8 @@ int fmha_entry(const vist3a_fmha_args*, cudaStream_t);
 int layernorm_entry(const void*, int, long long, void*, int, long long, long long, long long, long long, const float*,
                     long long, const float*, long long, float, int, const vist3a_rowmap*, const vist3a_rowmap*, cudaStream_t);
 int rmsnorm_rope_entry(void*, long long, long long, long long, long long, const float*, float, const float*,
-                       const float*, long long, cudaStream_t);
+                       const float*, long long, long long, long long, cudaStream_t);
+int row_rinv_entry(const void*, long long, long long, long long, float, float*, cudaStream_t);
 int modulation_entry(const float*, const void*, int, int, float*, long long, long long, long long, unsigned,
                      cudaStream_t);
 int skinny_linear_entry(const void*, int, long long, const void*, int, long long, const float*, void*, int, long long,
@@ -154,8 +155,13 @@ int vist3a_layernorm(const void* x, int32_t x_dtype, int64_t ldx, void* out, int
 }
 
 int vist3a_rmsnorm_rope(void* x, int64_t ldx, int64_t rows, int64_t dim, int64_t head_dim, const float* weight,
-                        float eps, const float* rope_cos, const float* rope_sin, int64_t rope_len, void* stream) {
-  return rmsnorm_rope_entry(x, ldx, rows, dim, head_dim, weight, eps, rope_cos, rope_sin, rope_len, ST(stream));
+                        float eps, const float* rope_cos, const float* rope_sin, int64_t rope_len, int64_t nseg,
+                        int64_t seg_stride, void* stream) {
+  return rmsnorm_rope_entry(x, ldx, rows, dim, head_dim, weight, eps, rope_cos, rope_sin, rope_len, nseg, seg_stride, ST(stream));
+}
+
+int vist3a_row_rinv(const void* x, int64_t ldx, int64_t rows, int64_t dim, float eps, float* out, void* stream) {
+  return row_rinv_entry(x, ldx, rows, dim, eps, out, ST(stream));
 }
 
 int vist3a_modulation(const float* table, const void* mod, int32_t mod_dtype, int32_t mod_is_broadcast, float* out,

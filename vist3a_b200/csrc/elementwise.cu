@@ -154,9 +154,11 @@ template <int NCHUNK>
 __global__ void __launch_bounds__(128) rmsnorm_rope_kernel(__nv_bfloat16* __restrict__ x, long long ldx, long long rows,
                                                            int dim, int head_dim, const float* __restrict__ weight,
                                                            float eps, const float* __restrict__ rcos,
-                                                           const float* __restrict__ rsin, long long rope_len) {
+                                                           const float* __restrict__ rsin, long long rope_len, long long seg_stride) {
   const long long row = (long long)blockIdx.x * 4 + (threadIdx.x >> 5);
   if (row >= rows) return;
+  x += (long long)blockIdx.y * seg_stride;   // segment (q | k of a fused qkv buffer) with its own weight vector
+  weight += (long long)blockIdx.y * dim;
   const int lane = threadIdx.x & 31;
   float v[NCHUNK][8];
   float ss = 0.f;
@@ -198,19 +200,49 @@ __global__ void __launch_bounds__(128) rmsnorm_rope_kernel(__nv_bfloat16* __rest
 }
 
 int rmsnorm_rope_entry(void* x, long long ldx, long long rows, long long dim, long long head_dim, const float* weight,
-                       float eps, const float* rcos, const float* rsin, long long rope_len, cudaStream_t st) {
+                       float eps, const float* rcos, const float* rsin, long long rope_len, long long nseg, long long seg_stride,
+                       cudaStream_t st) {
+  V3A_REQUIRE(nseg >= 1 && nseg <= 8 && (nseg == 1 || (seg_stride >= dim && seg_stride % 8 == 0 && ldx >= (nseg - 1) * seg_stride + dim)),
+              VIST3A_ERR_INVALID, "rmsnorm_rope: bad segment layout");
   V3A_REQUIRE(x && weight, VIST3A_ERR_INVALID, "rmsnorm_rope: null pointer");
   V3A_REQUIRE(rows > 0 && dim > 0 && dim % 8 == 0 && dim <= 8192, VIST3A_ERR_INVALID, "rmsnorm_rope: dim %lld unsupported", dim);
   V3A_REQUIRE(head_dim % 8 == 0 && dim % head_dim == 0, VIST3A_ERR_INVALID, "rmsnorm_rope: head_dim must divide dim");
   V3A_REQUIRE(ldx % 8 == 0 && ldx >= dim, VIST3A_ERR_INVALID, "rmsnorm_rope: bad row stride");
   V3A_REQUIRE((rcos == nullptr) == (rsin == nullptr), VIST3A_ERR_INVALID, "rmsnorm_rope: cos/sin must both be given");
   if (rcos) V3A_REQUIRE(rope_len > 0, VIST3A_ERR_INVALID, "rmsnorm_rope: rope_len");
-  const unsigned grid = (unsigned)((rows + 3) / 4);
+  const dim3 grid((unsigned)((rows + 3) / 4), (unsigned)nseg);
   __nv_bfloat16* xp = reinterpret_cast<__nv_bfloat16*>(x);
   const int nchunk = (int)((dim + 255) / 256);
-  if (nchunk <= 6) rmsnorm_rope_kernel<6><<<grid, 128, 0, st>>>(xp, ldx, rows, (int)dim, (int)head_dim, weight, eps, rcos, rsin, rope_len);
-  else if (nchunk <= 20) rmsnorm_rope_kernel<20><<<grid, 128, 0, st>>>(xp, ldx, rows, (int)dim, (int)head_dim, weight, eps, rcos, rsin, rope_len);
-  else rmsnorm_rope_kernel<32><<<grid, 128, 0, st>>>(xp, ldx, rows, (int)dim, (int)head_dim, weight, eps, rcos, rsin, rope_len);
+  if (nchunk <= 6) rmsnorm_rope_kernel<6><<<grid, 128, 0, st>>>(xp, ldx, rows, (int)dim, (int)head_dim, weight, eps, rcos, rsin, rope_len, seg_stride);
+  else if (nchunk <= 20) rmsnorm_rope_kernel<20><<<grid, 128, 0, st>>>(xp, ldx, rows, (int)dim, (int)head_dim, weight, eps, rcos, rsin, rope_len, seg_stride);
+  else rmsnorm_rope_kernel<32><<<grid, 128, 0, st>>>(xp, ldx, rows, (int)dim, (int)head_dim, weight, eps, rcos, rsin, rope_len, seg_stride);
+  V3A_CUDA_OK(cudaGetLastError());
+  launch_counter().fetch_add(1);
+  return VIST3A_OK;
+}
+
+// ----------------------------------------------------------------------------------------
+// per-row RMS reciprocal (read-only pass): out[r] = rsqrt(mean(x[r,:]^2) + eps)
+// ----------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) row_rinv_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, long long rows, int dim, float eps,
+                                                       float* __restrict__ out) {
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  float ss = 0.f;
+  for (int col = lane * 8; col < dim; col += 256) {
+    float v[8];
+    load8<false>(x, row * ldx + col, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) ss = fmaf(v[j], v[j], ss);
+  }
+  ss = warp_sum(ss);
+  if (lane == 0) out[row] = rsqrtf(ss / (float)dim + eps);
+}
+
+int row_rinv_entry(const void* x, long long ldx, long long rows, long long dim, float eps, float* out, cudaStream_t st) {
+  V3A_REQUIRE(x && out && rows > 0 && dim > 0 && dim % 8 == 0 && ldx % 8 == 0 && ldx >= dim, VIST3A_ERR_INVALID, "row_rinv: bad arguments");
+  row_rinv_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), ldx, rows, (int)dim, eps, out);
   V3A_CUDA_OK(cudaGetLastError());
   launch_counter().fetch_add(1);
   return VIST3A_OK;

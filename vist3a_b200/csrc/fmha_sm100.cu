@@ -31,6 +31,7 @@ struct FmhaParams {
   long long o_bs, o_rs, o_hs;
   int len_q, len_kv;
   float scale_log2;  // scale * log2(e)
+  const float* row_scale;  // optional per-(batch, query row) positive factor on the logits
 };
 
 template <int D, int BKV_, int POLY_>
@@ -281,7 +282,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const uint32_t o_addr = tile_base + Cfg::TM_O;
       float m_run = -INFINITY;  // running (possibly stale) row max of raw scores
       float l_run = 0.0f;       // running row sum of exp2((s - m_run) * scale_log2)
-      const float c = p.scale_log2;
+      const float c = (p.row_scale && row < p.len_q) ? p.scale_log2 * p.row_scale[(long long)batch * p.len_q + row] : p.scale_log2;
       const uint64_t cc2 = pack2(c, c);
       for (int j = 0; j < n_kv; ++j) {
         const int sb = j % NSB;
@@ -427,6 +428,7 @@ static int launch_fmha(const vist3a_fmha_args& a, cudaStream_t stream) {
   p.O = a.O; p.o_bs = a.o_bs; p.o_rs = a.o_rs; p.o_hs = a.o_hs;
   p.len_q = (int)a.len_q; p.len_kv = (int)a.len_kv;
   p.scale_log2 = a.scale * 1.4426950408889634f;
+  p.row_scale = a.q_row_scale;
   auto kern = fmha_fwd_kernel<D, BKV_, POLY_>;
   static bool attr_set = false;
   if (!attr_set) {

@@ -127,9 +127,10 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
 
 
 def fmha(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, scale: Optional[float] = None,
-         out: Optional[torch.Tensor] = None, flags: int = 0) -> torch.Tensor:
+         out: Optional[torch.Tensor] = None, flags: int = 0, q_row_scale: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Non-causal attention.  q [B, Lq, H, D], k/v [B, Lkv, H, D] (any strides with unit inner stride,
-    e.g. slices of a fused QKV buffer); returns [B, Lq, H, D] bf16."""
+    e.g. slices of a fused QKV buffer); returns [B, Lq, H, D] bf16.  q_row_scale [B*Lq] fp32 (optional) multiplies the
+    logits of each query row (all heads): the per-row RMSNorm factor of cross-attention queries (see vist3a_row_rinv)."""
     _need_cuda(q, k, v, out)
     B, Lq, H, D = q.shape
     Lk = k.shape[1]
@@ -149,6 +150,10 @@ def fmha(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, scale: Optional[f
     a.o_bs, a.o_rs, a.o_hs = out.stride(0), out.stride(1), out.stride(2)
     a.scale = float(scale if scale is not None else D ** -0.5)
     a.flags = flags
+    if q_row_scale is not None:
+        if q_row_scale.dtype != torch.float32 or not q_row_scale.is_contiguous() or q_row_scale.numel() != B * Lq or not q_row_scale.is_cuda:
+            raise TypeError("fmha: q_row_scale must be a contiguous CUDA float32 tensor of B*Lq elements")
+        a.q_row_scale = q_row_scale.data_ptr()
     L.check(L.load().vist3a_fmha_fwd(C.byref(a), _stream()))
     return out
 
@@ -179,16 +184,31 @@ def layernorm(x: torch.Tensor, *, mul: Optional[torch.Tensor] = None, add: Optio
 
 
 def rmsnorm_rope_(x: torch.Tensor, weight: torch.Tensor, head_dim: int, *, eps: float = 1e-6,
-                  cos: Optional[torch.Tensor] = None, sin: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """In place on a bf16 [rows, dim] matrix (may be a column slice of a wider buffer)."""
+                  cos: Optional[torch.Tensor] = None, sin: Optional[torch.Tensor] = None, nseg: int = 1) -> torch.Tensor:
+    """In place on a bf16 [rows, nseg*dim] matrix (may be a column slice of a wider buffer).  nseg > 1: the columns are nseg
+    independent segments (q | k of a fused qkv buffer), each normalised over its own `dim` columns with weight[s*dim:(s+1)*dim]."""
     _need_cuda(x, weight, cos, sin)
     if x.dim() != 2 or x.dtype != torch.bfloat16 or x.stride(1) != 1:
         raise TypeError("rmsnorm_rope_: x must be a 2-D bfloat16 tensor with unit inner stride")
     rows, dim = x.shape
+    if dim % nseg or weight.numel() != dim:
+        raise ValueError("rmsnorm_rope_: weight must hold one vector per segment")
+    dim //= nseg
     rope_len = cos.shape[0] if cos is not None else 0
     L.check(L.load().vist3a_rmsnorm_rope(x.data_ptr(), x.stride(0), rows, dim, head_dim, weight.data_ptr(), eps,
-                                         _ptr(cos), _ptr(sin), rope_len, _stream()))
+                                         _ptr(cos), _ptr(sin), rope_len, nseg, dim if nseg > 1 else 0, _stream()))
     return x
+
+
+def row_rinv(x: torch.Tensor, eps: float = 1e-6, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """rsqrt(mean(x^2, -1) + eps) per row of a bf16 [rows, dim] matrix -> fp32 [rows]."""
+    _need_cuda(x, out)
+    if x.dim() != 2 or x.dtype != torch.bfloat16 or x.stride(1) != 1:
+        raise TypeError("row_rinv: x must be a 2-D bfloat16 tensor with unit inner stride")
+    if out is None:
+        out = torch.empty((x.shape[0],), dtype=torch.float32, device=x.device)
+    L.check(L.load().vist3a_row_rinv(x.data_ptr(), x.stride(0), x.shape[0], x.shape[1], eps, out.data_ptr(), _stream()))
+    return out
 
 
 def modulation(table: torch.Tensor, mod: torch.Tensor, *, nvec: int, broadcast: bool, one_plus_mask: int,
@@ -478,7 +498,7 @@ class OpTimer:
             return f
 
         table = {"gemm": gemm_cost, "fmha": fmha_cost, "layernorm": io_cost("layernorm"),
-                 "rmsnorm_rope_": io_cost("rmsnorm_rope"), "modulation": io_cost("small"), "skinny_linear": io_cost("small"),
+                 "rmsnorm_rope_": io_cost("rmsnorm_rope"), "row_rinv": io_cost("rmsnorm_rope"), "modulation": io_cost("small"), "skinny_linear": io_cost("small"),
                  "timestep_features": io_cost("small"), "patchify": io_cost("small"), "unpatchify": io_cost("small"),
                  "cfg_combine": io_cost("small"), "axpby_n": io_cost("small"), "im2col_stitch": io_cost("im2col"),
                  "im2col_nhwc": io_cost("im2col"), "rgb_to_nhwc4pad": io_cost("small"), "qknorm_rope2d_": io_cost("qknorm_rope2d"), "bilinear_nhwc": io_cost("bilinear"),

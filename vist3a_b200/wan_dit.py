@@ -181,12 +181,14 @@ class WanTransformer3DModelB200(torch.nn.Module):
             w[k + "table"] = V32(b + "scale_shift_table").reshape(6, D).contiguous()
             w[k + "qkv.w"] = W(b + "attn1.to_q", b + "attn1.to_k", b + "attn1.to_v")
             w[k + "qkv.b"] = Bv(b + "attn1.to_q", b + "attn1.to_k", b + "attn1.to_v")
-            w[k + "nq1"], w[k + "nk1"] = V32(b + "attn1.norm_q.weight"), V32(b + "attn1.norm_k.weight")
+            w[k + "nqk1"] = torch.cat([V32(b + "attn1.norm_q.weight"), V32(b + "attn1.norm_k.weight")]).contiguous()
             w[k + "o1.w"], w[k + "o1.b"] = W(b + "attn1.to_out.0"), Bv(b + "attn1.to_out.0")
             w[k + "q2.w"], w[k + "q2.b"] = W(b + "attn2.to_q"), Bv(b + "attn2.to_q")
             w[k + "kv2.w"] = W(b + "attn2.to_k", b + "attn2.to_v")
             w[k + "kv2.b"] = Bv(b + "attn2.to_k", b + "attn2.to_v")
-            w[k + "nq2"], w[k + "nk2"] = V32(b + "attn2.norm_q.weight"), V32(b + "attn2.norm_k.weight")
+            # cross-attention: (q rinv_q w_q) . (k rinv_k w_k) = rinv_q * q . (k rinv_k (w_k w_q)): the query norm weight is folded
+            # into the cached text keys, the per-row factor rinv_q scales the logits inside the attention kernel
+            w[k + "nk2q2"] = (V32(b + "attn2.norm_k.weight") * V32(b + "attn2.norm_q.weight")).contiguous()
             w[k + "o2.w"], w[k + "o2.b"] = W(b + "attn2.to_out.0"), Bv(b + "attn2.to_out.0")
             if c.cross_attn_norm:
                 w[k + "n2.w"], w[k + "n2.b"] = V32(b + "norm2.weight"), V32(b + "norm2.bias")
@@ -212,7 +214,7 @@ class WanTransformer3DModelB200(torch.nn.Module):
         for i in range(c.num_layers):
             k = f"b{i}."
             ops.gemm(txt, w[k + "kv2.w"], w[k + "kv2.b"], out=kv[i])
-            ops.rmsnorm_rope_(kv[i][:, :D], w[k + "nk2"], c.attention_head_dim, eps=c.eps)
+            ops.rmsnorm_rope_(kv[i][:, :D], w[k + "nk2q2"], c.attention_head_dim, eps=c.eps)
         return SimpleNamespace(kv=kv, B=B, Lt=Lt)
 
     def _text_state(self, enc: torch.Tensor):
@@ -235,7 +237,8 @@ class WanTransformer3DModelB200(torch.nn.Module):
                 att=torch.empty((M, D), dtype=bf, device=dev), ffn=torch.empty((M, c.ffn_dim), dtype=bf, device=dev),
                 mod=torch.empty((B, 6, D), dtype=torch.float32, device=dev),
                 mod2=torch.empty((B, 2, D), dtype=torch.float32, device=dev),
-                po=torch.empty((M, self.w["out.w"].shape[0]), dtype=bf, device=dev))
+                po=torch.empty((M, self.w["out.w"].shape[0]), dtype=bf, device=dev),
+                rq=torch.empty((M,), dtype=torch.float32, device=dev))
             self._ws = {key: ws}  # one live shape at a time
         return ws
 
@@ -288,8 +291,7 @@ class WanTransformer3DModelB200(torch.nn.Module):
             ops.layernorm(x, mul=mod[:, 1], add=mod[:, 0], mul_bstride=6 * D, add_bstride=6 * D, rows_per_batch=L,
                           eps=c.eps, out=ws.h)
             ops.gemm(ws.h, w[k + "qkv.w"], w[k + "qkv.b"], out=ws.qkv)
-            ops.rmsnorm_rope_(ws.qkv[:, :D], w[k + "nq1"], hd, eps=c.eps, cos=cos, sin=sin)
-            ops.rmsnorm_rope_(ws.qkv[:, D:2 * D], w[k + "nk1"], hd, eps=c.eps, cos=cos, sin=sin)
+            ops.rmsnorm_rope_(ws.qkv[:, :2 * D], w[k + "nqk1"], hd, eps=c.eps, cos=cos, sin=sin, nseg=2)
             qkv5 = ws.qkv.view(B, L, 3, H_, hd)
             ops.fmha(qkv5[:, :, 0], qkv5[:, :, 1], qkv5[:, :, 2], out=ws.att.view(B, L, H_, hd))
             ops.gemm(ws.att, w[k + "o1.w"], w[k + "o1.b"], gate=mod[:, 2], gate_bstride=6 * D, rows_per_batch=L,
@@ -301,9 +303,9 @@ class WanTransformer3DModelB200(torch.nn.Module):
             else:
                 hq = x
             ops.gemm(hq, w[k + "q2.w"], w[k + "q2.b"], out=ws.q2)
-            ops.rmsnorm_rope_(ws.q2, w[k + "nq2"], hd, eps=c.eps)
+            ops.row_rinv(ws.q2, eps=c.eps, out=ws.rq)
             kv5 = ts.kv[i].view(B, ts.Lt, 2, H_, hd)
-            ops.fmha(ws.q2.view(B, L, H_, hd), kv5[:, :, 0], kv5[:, :, 1], out=ws.att.view(B, L, H_, hd))
+            ops.fmha(ws.q2.view(B, L, H_, hd), kv5[:, :, 0], kv5[:, :, 1], out=ws.att.view(B, L, H_, hd), q_row_scale=ws.rq)
             ops.gemm(ws.att, w[k + "o2.w"], w[k + "o2.b"], residual=x, out=x, round_linear=True)
             # --- feed-forward
             ops.layernorm(x, mul=mod[:, 4], add=mod[:, 3], mul_bstride=6 * D, add_bstride=6 * D, rows_per_batch=L,
