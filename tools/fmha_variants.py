@@ -1,0 +1,55 @@
+"""Correctness + timing of the attention kernel variants selected by vist3a_fmha_args.flags (bit0: ONE thread per query row (default two),
+bit1: 128-key aliased steps at d=128).  Run on the GPU box."""
+import json
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from vist3a_b200 import ops  # noqa: E402
+
+
+def timeit(fn, iters=20):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record(); fn(); e.record(); torch.cuda.synchronize()
+        ts.append(s.elapsed_time(e))
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
+def main():
+    for flags in (0, 1, 2, 3):
+        errs = []
+        for (B, H, Lq, Lk, D) in ((1, 2, 300, 333, 128), (2, 3, 1029, 1029, 64), (1, 2, 257, 129, 128), (1, 4, 640, 1100, 64)):
+            if D == 64 and flags >= 2:
+                continue
+            g = torch.Generator(device="cuda").manual_seed(B + Lq + D + flags)
+            q = torch.randn(B, Lq, H, D, device="cuda", generator=g).bfloat16()
+            k = torch.randn(B, Lk, H, D, device="cuda", generator=g).bfloat16()
+            v = torch.randn(B, Lk, H, D, device="cuda", generator=g).bfloat16()
+            q[:, : Lq // 2] *= 4  # large logits on half the rows: exercises the lazy rescale
+            o = ops.fmha(q, k, v, flags=flags)
+            ref = torch.nn.functional.scaled_dot_product_attention(q.transpose(1, 2).float(), k.transpose(1, 2).float(), v.transpose(1, 2).float()).transpose(1, 2)
+            errs.append(float((o.float() - ref).norm() / ref.norm()))
+        res = {"flags": flags, "rel_l2": [round(e, 5) for e in errs]}
+        for name, B, H, Lq, Lk, D in (("dit_self", 2, 12, 4096, 4096, 128), ("dit_cross", 2, 12, 4096, 512, 128), ("dec_frame", 13, 16, 1029, 1029, 64),
+                                      ("dec_global", 1, 16, 13377, 13377, 64)):
+            if D == 64 and flags >= 2:
+                continue
+            q = torch.randn(B, Lq, H, D, device="cuda").bfloat16()
+            k = torch.randn(B, Lk, H, D, device="cuda").bfloat16()
+            v = torch.randn(B, Lk, H, D, device="cuda").bfloat16()
+            o = torch.empty_like(q)
+            ms = timeit(lambda: ops.fmha(q, k, v, out=o, flags=flags))
+            res[name] = round(4 * B * H * Lq * Lk * D / ms / 1e9, 1)
+        print(json.dumps(res), flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -7,9 +7,9 @@
 //                 The whole warp runs the warp-uniform control flow, one elected lane issues: descriptors stay in
 //                 uniform registers (no per-MMA R2UR / elect waterfall).
 //   warp 2        TMEM allocator
-//   warps 4..7    softmax of query tile 0   } thread t owns query row t (TMEM lane t): tcgen05.ld S, online max with
-//   warps 8..11   softmax of query tile 1   } lazy rescale of O (only when the running max grows by more than 2^8),
-//                                             exponentials, bf16 P -> tcgen05.st
+//   warps 4..     softmax: SPLIT (1 or 2) warpgroups per query tile; a thread owns (a column half of) query row t (TMEM lane t):
+//                 tcgen05.ld S, online max (halves exchange their partial max through smem + a 64-thread named barrier) with lazy
+//                 rescale of O (only when the running max grows by more than 2^8), exponentials, bf16 P -> tcgen05.st
 // MUFU.EX2 is the co-bottleneck of attention on this part (16 results/clk/SM: a 128x128 score tile costs as many SM
 // cycles in exponentials as its two d=128 MMAs, twice as many at d=64).  Hence:
 //   * the score tile of the next step is always produced while the warpgroup is still exponentiating the current one
@@ -34,7 +34,7 @@ struct FmhaParams {
   const float* row_scale;  // optional per-(batch, query row) positive factor on the logits
 };
 
-template <int D, int BKV_, int POLY_>
+template <int D, int BKV_, int POLY_, int SPLIT_>
 struct FmhaCfg {
   static constexpr int BQ = 128, QT = 2;             // two query tiles per CTA
   static constexpr int BKV = BKV_;                   // keys per step
@@ -48,7 +48,12 @@ struct FmhaCfg {
   static constexpr int KV_STAGES = KV_TILE_BYTES > 16384 ? 2 : 4;
   static constexpr int PT = NSB + 1 + 4;             // barriers per query tile: s_full[NSB], s_free, p_full[2], pv_done[2]
   static constexpr int NBARS = 1 + 4 * KV_STAGES + 2 * PT;
-  static constexpr int SMEM_BYTES = Q_TILE_BYTES * QT + KV_TILE_BYTES * 2 * KV_STAGES + 1024 + 8 * NBARS + 16;
+  static constexpr int SPLIT = SPLIT_;               // threads per query row (softmax warpgroups per tile)
+  static constexpr int THREADS = 128 + 256 * SPLIT;
+  static constexpr int HC = BKV / SPLIT;             // score columns per softmax thread and step
+  static constexpr int XCH_BYTES = 2 * QT * 2 * 128 * 4;  // row-max / row-sum exchange between the two threads of a row
+  static constexpr int SMEM_BYTES = Q_TILE_BYTES * QT + KV_TILE_BYTES * 2 * KV_STAGES + 1024 + 8 * NBARS + 16 + XCH_BYTES;
+  static_assert(SPLIT == 1 || SPLIT == 2, "SPLIT");
   static constexpr uint32_t TILE_COLS = 256;
   static constexpr uint32_t TM_S = 0;
   static constexpr uint32_t S_STRIDE = 64;           // between the NSB score buffers (ALIAS only)
@@ -60,7 +65,6 @@ struct FmhaCfg {
   static_assert(TM_O + D <= TILE_COLS, "TMEM budget");
 };
 
-constexpr int kFmhaThreads = 384;
 
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
@@ -106,11 +110,13 @@ __device__ __forceinline__ void exp2_poly2(float y0, float y1, float& e0, float&
   e1 = __int_as_float(__float_as_int(q1) + (__float_as_int(t1) << 23));
 }
 
-template <int D, int BKV_, int POLY_>
-__global__ void __launch_bounds__(kFmhaThreads, 1)
+template <int D, int BKV_, int POLY_, int SPLIT_>
+__global__ void __launch_bounds__(128 + 256 * SPLIT_, 1)
 fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const FmhaParams p) {
-  using Cfg = FmhaCfg<D, BKV_, POLY_>;
+  using Cfg = FmhaCfg<D, BKV_, POLY_, SPLIT_>;
+  constexpr int SPLIT = Cfg::SPLIT;
+  constexpr int HC = Cfg::HC;
   constexpr int ST = Cfg::KV_STAGES;
   constexpr int NSB = Cfg::NSB;
   constexpr int BKV = Cfg::BKV;
@@ -132,6 +138,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   auto p_full = [&](int i, int b) { return bar_base + 8u * (1 + 4 * ST + i * Cfg::PT + NSB + 1 + b); };
   auto pv_done = [&](int i, int b) { return bar_base + 8u * (1 + 4 * ST + i * Cfg::PT + NSB + 3 + b); };
   const uint32_t tmem_slot = bar_base + 8u * Cfg::NBARS;
+  const uint32_t xch_base = tmem_slot + 16u;  // float [2 parities][2 tiles][2 halves][128 rows]
 
   const uint32_t warp = warp_id_sync();
   const uint32_t lane = lane_id();
@@ -156,9 +163,9 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     }
     for (int i = 0; i < 2; ++i) {
       for (int b = 0; b < NSB; ++b) mbar_init(s_full(i, b), 1);
-      mbar_init(s_free(i), 4);  // one arrival per softmax warp of the tile
+      mbar_init(s_free(i), 4 * SPLIT);  // one arrival per softmax warp of the tile
       for (int b = 0; b < 2; ++b) {
-        mbar_init(p_full(i, b), 4);
+        mbar_init(p_full(i, b), 4 * SPLIT);
         mbar_init(pv_done(i, b), 1);
       }
     }
@@ -172,7 +179,8 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
   if (warp < 4) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+    if constexpr (SPLIT == 1) asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+    // (SPLIT == 2: 20 warps at the launch-time 96 registers; see the note at the softmax branch)
     if (warp == 0) {
       // ------------------------------ TMA producer (warp-uniform control flow, one elected lane issues) ---------
       if (elect_one()) {
@@ -272,48 +280,68 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
     }
   } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
+    if constexpr (SPLIT == 1) asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
+    // SPLIT == 2 keeps the launch-time allocation (96 registers x 640 threads): setmaxnreg.inc above 96 deadlocked on B200 --
+    // the per-warp register allocation is coarser than the PTX granularity of 8, and 16 warps x 4096 registers is the whole file.
     // ------------------------------ softmax / correction / epilogue ------------------------------
-    const int i = (int)(warp >> 2) - 1;  // query tile of this warpgroup
+    // SPLIT threads share a query row: thread (tile i, half h, row) owns score columns [h*HC, (h+1)*HC) of every step, half of the
+    // O columns for the (rare) rescale and the output store; the two halves exchange their partial row max through shared memory
+    // and a 64-thread named barrier per step, so both take identical rescale decisions.
+    const int sw = (int)warp - 4;
+    const int i = sw / (4 * SPLIT);          // query tile
+    const int h = (sw >> 2) % SPLIT;         // column half
     if (i < nq) {
-      const uint32_t wq = warp & 3u;     // TMEM lane quadrant this warp may access
+      const uint32_t wq = warp & 3u;         // TMEM lane quadrant this warp may access
+      const int rit = (int)(wq * 32u + lane);  // row in tile
       const uint32_t tile_base = tmem_base + ((wq * 32u) << 16) + (uint32_t)i * Cfg::TILE_COLS;
-      const int row = q0 + i * Cfg::BQ + (int)(wq * 32u + lane);
-      const uint32_t o_addr = tile_base + Cfg::TM_O;
+      const int row = q0 + i * Cfg::BQ + rit;
+      constexpr int OC = D / SPLIT;          // O columns per thread
+      const uint32_t o_addr = tile_base + Cfg::TM_O + (uint32_t)(h * OC);
+      auto xch = [&](int par, int half) { return xch_base + 4u * (uint32_t)(((par * 2 + i) * 2 + half) * 128 + rit); };
+      const uint32_t pair_bar = 1u + (uint32_t)i * 4u + wq;  // named barrier shared by the two warps that own these 32 rows
       float m_run = -INFINITY;  // running (possibly stale) row max of raw scores
-      float l_run = 0.0f;       // running row sum of exp2((s - m_run) * scale_log2)
+      float l_run = 0.0f;       // running sum of exp2((s - m_run) * scale_log2) over this thread's columns
       const float c = (p.row_scale && row < p.len_q) ? p.scale_log2 * p.row_scale[(long long)batch * p.len_q + row] : p.scale_log2;
       const uint64_t cc2 = pack2(c, c);
       for (int j = 0; j < n_kv; ++j) {
         const int sb = j % NSB;
         mbar_wait(s_full(i, sb), (uint32_t)(j / NSB) & 1u);
         tc_fence_after();
-        uint32_t r[BKV];
-        const uint32_t s_addr = tile_base + Cfg::TM_S + (uint32_t)sb * Cfg::S_STRIDE;
+        uint32_t r[HC];
+        const uint32_t s_addr = tile_base + Cfg::TM_S + (uint32_t)sb * Cfg::S_STRIDE + (uint32_t)(h * HC);
 #pragma unroll
-        for (int cb = 0; cb < BKV / 32; ++cb) tmem_ld_x32(s_addr + (uint32_t)(cb * 32), r + cb * 32);
+        for (int cb = 0; cb < HC / 32; ++cb) tmem_ld_x32(s_addr + (uint32_t)(cb * 32), r + cb * 32);
         tmem_ld_wait();
         if (!Cfg::ALIAS) {
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(s_free(i));
         }
-        const int valid = p.len_kv - j * BKV;  // keys of this tile that exist
-        if (valid < BKV) {
+        const int valid = p.len_kv - j * BKV - h * HC;  // columns of this thread that hold existing keys
+        if (valid < HC) {
 #pragma unroll
-          for (int k = 0; k < BKV; ++k)
+          for (int k = 0; k < HC; ++k)
             if (k >= valid) r[k] = 0xff800000u;  // -inf
         }
         float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-        for (int k = 0; k < BKV; k += 8) {
+        for (int k = 0; k < HC; k += 8) {
 #pragma unroll
           for (int u = 0; u < 4; ++u)
             mx[u] = fmaxf(fmaxf(mx[u], __uint_as_float(r[k + 2 * u])), __uint_as_float(r[k + 2 * u + 1]));
         }
-        const float m_new = fmaxf(m_run, fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])));
-        // d=64: the single P buffer is read by P(j-1) V.  (d=128: the commit behind s_full of this step covers P(j-2) V,
-        // the last reader of the buffer S(j) | P(j) lives in.)
+        float m_tile = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+        if constexpr (SPLIT == 2) {
+          // (alias layout: this barrier also orders the partner's S loads before our P stores into the columns it read)
+          asm volatile("st.shared.f32 [%0], %1;" ::"r"(xch(j & 1, h)), "f"(m_tile) : "memory");
+          asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+          float other;
+          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(other) : "r"(xch(j & 1, h ^ 1)) : "memory");
+          m_tile = fmaxf(m_tile, other);
+        }
+        const float m_new = fmaxf(m_run, m_tile);
+        // d=64: the single P buffer is read by P(j-1) V.  (d=128: the commit behind s_full of this step covers the last reader
+        // of the buffer S(j) | P(j) lives in.)
         if (!Cfg::ALIAS && j >= 1) mbar_wait(pv_done(i, (j - 1) & 1), (uint32_t)((j - 1) >> 1) & 1u);
         if (j == 0) {
           m_run = m_new;
@@ -326,14 +354,14 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             const float f = need ? ex2_approx((m_run - m_new) * c) : 1.0f;
             if (need) m_run = m_new;
             l_run *= f;
-#pragma unroll
-            for (int cb = 0; cb < D / 32; ++cb) {
-              uint32_t o[32];
-              tmem_ld_x32(o_addr + (uint32_t)(cb * 32), o);
+#pragma unroll 1
+            for (int cb = 0; cb < OC / 16; ++cb) {  // 16 columns at a time: the score row stays live in registers
+              uint32_t o[16];
+              tmem_ld_x16(o_addr + (uint32_t)(cb * 16), o);
               tmem_ld_wait();
 #pragma unroll
-              for (int k = 0; k < 32; ++k) o[k] = __float_as_uint(__uint_as_float(o[k]) * f);
-              tmem_st_x32(o_addr + (uint32_t)(cb * 32), o);
+              for (int k = 0; k < 16; ++k) o[k] = __float_as_uint(__uint_as_float(o[k]) * f);
+              tmem_st_x16(o_addr + (uint32_t)(cb * 16), o);
             }
             tmem_st_wait();
           }
@@ -342,9 +370,9 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         const float nmc = -m_run * c;
         const uint64_t mc2 = pack2(nmc, nmc);
         uint64_t sum2[2] = {0ull, 0ull};  // packed (even, odd) column partial sums
-        const uint32_t p_addr = tile_base + Cfg::TM_P + (uint32_t)(j & 1) * Cfg::P_STRIDE;
+        const uint32_t p_addr = tile_base + Cfg::TM_P + (uint32_t)(j & 1) * Cfg::P_STRIDE + (uint32_t)(h * (HC / 2));
 #pragma unroll
-        for (int cb = 0; cb < BKV / 32; ++cb) {
+        for (int cb = 0; cb < HC / 32; ++cb) {
           uint32_t pk[16];
 #pragma unroll
           for (int k = 0; k < 16; ++k) {
@@ -373,13 +401,20 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         if (lane == 0) mbar_arrive(p_full(i, j & 1));
       }
       // ---- epilogue: O / l -> bf16 -> global ----
+      if constexpr (SPLIT == 2) {
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(xch(n_kv & 1, h)), "f"(l_run) : "memory");
+        asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+        float other;
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(other) : "r"(xch(n_kv & 1, h ^ 1)) : "memory");
+        l_run += other;
+      }
       mbar_wait(pv_done(i, (n_kv - 1) & 1), (uint32_t)((n_kv - 1) >> 1) & 1u);  // the commit covers every earlier MMA too
       tc_fence_after();
       const float inv_l = 1.0f / l_run;
       __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(p.O) + (long long)batch * p.o_bs + (long long)row * p.o_rs +
-                            (long long)head * p.o_hs;
+                            (long long)head * p.o_hs + h * OC;
 #pragma unroll
-      for (int cb = 0; cb < D / 32; ++cb) {
+      for (int cb = 0; cb < OC / 32; ++cb) {
         uint32_t o[32];
         tmem_ld_x32(o_addr + (uint32_t)(cb * 32), o);
         tmem_ld_wait();
@@ -416,9 +451,9 @@ static int make_qkv_map(CUtensorMap* tm, const void* ptr, long long B, long long
   return encode_tensor_map(tm, ptr, 2, false, 4, dims, strides, box, true);
 }
 
-template <int D, int BKV_, int POLY_>
+template <int D, int BKV_, int POLY_, int SPLIT_>
 static int launch_fmha(const vist3a_fmha_args& a, cudaStream_t stream) {
-  using Cfg = FmhaCfg<D, BKV_, POLY_>;
+  using Cfg = FmhaCfg<D, BKV_, POLY_, SPLIT_>;
   CUtensorMap tmQ, tmK, tmV;
   int rc;
   if ((rc = make_qkv_map(&tmQ, a.Q, a.batch, a.heads, a.len_q, D, a.q_bs, a.q_rs, a.q_hs, Cfg::BQ))) return rc;
@@ -429,7 +464,7 @@ static int launch_fmha(const vist3a_fmha_args& a, cudaStream_t stream) {
   p.len_q = (int)a.len_q; p.len_kv = (int)a.len_kv;
   p.scale_log2 = a.scale * 1.4426950408889634f;
   p.row_scale = a.q_row_scale;
-  auto kern = fmha_fwd_kernel<D, BKV_, POLY_>;
+  auto kern = fmha_fwd_kernel<D, BKV_, POLY_, SPLIT_>;
   static bool attr_set = false;
   if (!attr_set) {
     V3A_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
@@ -437,7 +472,7 @@ static int launch_fmha(const vist3a_fmha_args& a, cudaStream_t stream) {
   }
   const long long rows_per_cta = Cfg::BQ * Cfg::QT;
   dim3 grid((unsigned)((a.len_q + rows_per_cta - 1) / rows_per_cta), (unsigned)a.heads, (unsigned)a.batch);
-  kern<<<grid, kFmhaThreads, Cfg::SMEM_BYTES, stream>>>(tmQ, tmK, tmV, p);
+  kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tmQ, tmK, tmV, p);
   V3A_CUDA_OK(cudaGetLastError());
   launch_counter().fetch_add(1);
   return VIST3A_OK;
@@ -459,8 +494,13 @@ int fmha_entry(const vist3a_fmha_args* args, cudaStream_t stream) {
   int rc = check_arch();
   if (rc) return rc;
   // exponentials on the FMA pipe per 8 column pairs: 3 at d=64 (MUFU-bound), 2 at d=128 (measured optimum on B200)
-  if (a.head_dim == 64) return launch_fmha<64, 128, 3>(a, stream);
-  return launch_fmha<128, 64, 2>(a, stream);
+  // Default: two threads per query row (4 softmax warpgroups, 640 threads), 64-key double-buffered steps at d=128, 128-key steps at
+  // d=64 -- the fastest of the variants measured on B200 (tools/fmha_variants.py).  flags bit0 selects one thread per row (2 softmax
+  // warpgroups, setmaxnreg-enlarged register file), bit1 (d=128) the 128-key aliased steps; kept for A/B measurements.
+  const bool one = (a.flags & 1u) != 0;
+  if (a.head_dim == 64) return one ? launch_fmha<64, 128, 3, 1>(a, stream) : launch_fmha<64, 128, 3, 2>(a, stream);
+  if (a.flags & 2u) return one ? launch_fmha<128, 128, 2, 1>(a, stream) : launch_fmha<128, 128, 2, 2>(a, stream);
+  return one ? launch_fmha<128, 64, 2, 1>(a, stream) : launch_fmha<128, 64, 2, 2>(a, stream);
 }
 
 }  // namespace v3a
