@@ -201,7 +201,7 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=device)
     _lib.load()
     cfg, model, dec = build_models(device, with_decoder=not args.no_decoder)
-    B, T, HW, Lt = 1, 4, 64, 512
+    B, T, HW, Lt = args.prompts_per_gpu, 4, 64, 512
     g = torch.Generator().manual_seed(1000 + rank)  # every rank denoises its own prompt
     noise_h = torch.randn(B, 16, T, HW, HW, generator=g).pin_memory()
     tc_h = torch.randn(B, Lt, cfg.text_dim, generator=g).bfloat16()
@@ -259,7 +259,7 @@ def run_ours(args):
         ms = timed(dev_step, args.steps)
     launches_eager = _lib.launch_count() - n0
     ms_step = ms / args.steps
-    value = world * args.steps / (ms / 1e3)
+    value = world * B * args.steps / (ms / 1e3)   # one denoise step per prompt and timed iteration
 
     # ---- end to end through the public call with HOST buffers (H2D inputs + D2H result inside the timed region)
     h2d = noise_h.numel() * 4 + tc_h.numel() * 2 + tu_h.numel() * 2
@@ -277,7 +277,7 @@ def run_ours(args):
     for i in range(min(args.warmup, 3)):
         e2e_step(i)
     ms_e2e = timed(e2e_step, args.steps)
-    e2e_value = world * args.steps / (ms_e2e / 1e3)
+    e2e_value = world * B * args.steps / (ms_e2e / 1e3)
 
     # ---- Gaussians/s: stitched decoder at 13 views x 448x448 on the (de-normalised) denoised latent, + the Gaussian all-gather
     gauss = None
@@ -286,7 +286,7 @@ def run_ours(args):
         mean = torch.tensor(WAN_LATENTS_MEAN, device=device).view(1, 16, 1, 1, 1)
         std = torch.tensor(WAN_LATENTS_STD, device=device).view(1, 16, 1, 1, 1)
         lat = eng.x.clamp(-4, 4) * std + mean   # synthetic-weight DiT output, clamped to the range of real VAE latents
-        img_h = (torch.rand(1, 3, VIEWS, IMG, IMG, generator=g) * 2 - 1).pin_memory()
+        img_h = (torch.rand(B, 3, VIEWS, IMG, IMG, generator=g) * 2 - 1).pin_memory()
         img = img_h.to(device)
         outs = {}
 
@@ -321,9 +321,9 @@ def run_ours(args):
 
         ms_prompt = timed(e2e_prompt, 1)
         gauss = {"n_per_prompt": N_GAUSS, "unit": "Gaussians/s",
-                 "decoder_gaussians_per_sec": world * N_GAUSS / (ms_dec / 1e3), "decoder_ms": ms_dec,
-                 "decoder_tflops": DECODER_TFLOP / (ms_dec / 1e3), "gather_ms": ms_gather,
-                 "e2e_gaussians_per_sec": world * N_GAUSS / (ms_prompt / 1e3), "e2e_prompt_ms": ms_prompt,
+                 "decoder_gaussians_per_sec": world * B * N_GAUSS / (ms_dec / 1e3), "decoder_ms": ms_dec,
+                 "decoder_tflops": B * DECODER_TFLOP / (ms_dec / 1e3), "gather_ms": ms_gather,
+                 "e2e_gaussians_per_sec": world * B * N_GAUSS / (ms_prompt / 1e3), "e2e_prompt_ms": ms_prompt,
                  "e2e_what": "one prompt per GPU: H2D views, text projections, 50 CFG denoise steps, de-normalise, decode" +
                              (", NCCL all-gather of all ranks' Gaussians" if world > 1 else "") + ", D2H of scene_scale",
                  "decoder_launches_per_forward": dec_launches // kd,
@@ -362,7 +362,7 @@ def run_ours(args):
                 "frac": ach / pk["bf16_sustained"], "frac_of_burst": ach / pk["bf16_burst"], "peak_src": pk["src"] + " (sustained: kernel timed inside a long step)",
                 "traffic": _ncu_traffic(top), "launches_per_step": d["launches"], "avg_launch_ms": d["ms"] / d["launches"],
                 "share_of_step": d["ms"] / tot,
-                "step_model_tflops": STEP_TFLOP / (ms_step / 1e3), "step_frac_of_sustained": STEP_TFLOP / (ms_step / 1e3) / pk["bf16_sustained"],
+                "step_model_tflops": B * STEP_TFLOP / (ms_step / 1e3), "step_frac_of_sustained": B * STEP_TFLOP / (ms_step / 1e3) / pk["bf16_sustained"],
                 "by_kernel": {k: {"ms": round(v["ms"], 4), "launches": v["launches"],
                                   "tflops": (v["flops"] / (v["ms"] / 1e3) / 1e12) if v["flops"] else None,
                                   "gbs": v["bytes"] / (v["ms"] / 1e3) / 1e9} for k, v in summ.items()}}
@@ -386,7 +386,7 @@ def run_ours(args):
                 "data": "synthetic",
                 "config": {"workload": WORKLOAD, "weights": "random-init Wan-1.3B (1.419 B params)", "cfg": "cond+uncond batched B=2",
                            "cuda_graph": not args.no_graph, "l2": "working set (2.8 GB weights + activations) >> 126 MB L2; no flush needed",
-                           "prompts_per_gpu": 1},
+                           "prompts_per_gpu": B},
                 "roofline": roof, "cpu_baseline": cpu, "clocks": clk.summary(), "gaussians": gauss,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": ms_e2e / args.steps},
@@ -409,6 +409,7 @@ def main():
     ap.add_argument("--ncu-step", action="store_true", help="profile exactly one eager denoise step (for ncu --profile-from-start off)")
     ap.add_argument("--detail", action="store_true", help="print per-shape kernel timings of one eager step to stderr")
     ap.add_argument("--ref-blocks", type=int, default=2, help="full-size blocks per CPU sample")
+    ap.add_argument("--prompts-per-gpu", type=int, default=1, help="prompts batched per GPU (BASELINE configs[4] sweep: 1/2/4/8)")
     ap.add_argument("--no-decoder", action="store_true", help="skip the Gaussians/s leg (decoder + gather)")
     ap.add_argument("--decoder-iters", type=int, default=3)
     args = ap.parse_args()

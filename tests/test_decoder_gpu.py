@@ -109,6 +109,30 @@ def test_full_width_decoder_small_views():
     _check("full-width", errs, _autocast_floor(D, sd, D.FULL, lat, img, 128, ref))
 
 
+def test_decoder_runs_at_21_views_and_batch_2():
+    """BASELINE configs[3]/[4] shapes: 21 views (global attention over 21 609 tokens, 4 214 784 Gaussians) and two prompts per call
+    at 5 views; outputs finite, per-sample results independent of batching."""
+    from vist3a_b200.stitched_decoder import DecoderConfig, StitchVAE3DB200, random_state_dict
+
+    cfg = DecoderConfig()
+    m = StitchVAE3DB200.from_state_dict(random_state_dict(cfg, 0, "cuda"), cfg, "cuda")
+    g = torch.Generator(device="cuda").manual_seed(4)
+    lat = torch.randn(1, 16, 6, 64, 64, device="cuda", generator=g)
+    img = torch.rand(1, 3, 21, 448, 448, device="cuda", generator=g) * 2 - 1
+    o = m.forward_with_latent(lat, img)
+    assert o.gaussians.means.shape == (1, 21 * 448 * 448, 3)
+    for t in (o.gaussians.means, o.gaussians.covariances, o.gaussians.harmonics, o.depth_dict["depth"]):
+        assert bool(torch.isfinite(t).all())
+    del o
+    lat2 = torch.randn(2, 16, 2, 64, 64, device="cuda", generator=g)
+    img2 = torch.rand(2, 3, 5, 448, 448, device="cuda", generator=g) * 2 - 1
+    both = m.forward_with_latent(lat2, img2)
+    one = m.forward_with_latent(lat2[1:], img2[1:])
+    assert both.gaussians.means.shape == (2, 5 * 448 * 448, 3)
+    for k in GAUSS:
+        assert _rel(getattr(both.gaussians, k)[1], getattr(one.gaussians, k)[0]) < 1e-5, k   # frame/global attention never mix prompts
+
+
 def test_decoder_properties_at_13_views():
     """BASELINE size (13 views x 448x448, N = 2 609 152 Gaussians): size-independent invariants of the outputs"""
     from oracle import decoder_ref as D

@@ -107,6 +107,22 @@ def test_1p3b_two_layers_full_sequence():
     assert e_ours < TOL and e_ours < 1.5 * e_torch + 1e-3
 
 
+def test_14b_width_one_layer_21_views():
+    """BASELINE configs[3] shapes: Wan-14B widths (D=5120, 40 heads, F=13824) at the 21-view sequence (latent [1,16,6,64,64],
+    L=6144, 512 text tokens), 1 layer (the oracle's CPU forward of one 14B block takes ~20 s)."""
+    import dataclasses
+
+    cfg = dataclasses.replace(R.WAN_14B, num_layers=1)
+    sd = R.init_state_dict(cfg, seed=5, bias_std=0.02)
+    lat, txt = R.synthetic_inputs(cfg, frames=6, hw=64, text_len=512, text_valid=300, seed=6)
+    t = torch.tensor([640.0])
+    ref = R.wan_forward(sd, cfg, lat, t, txt)
+    out = _engine(sd, cfg)(lat.cuda(), t.cuda(), txt.cuda(), return_dict=False)[0]
+    e_ours = _rel(out, ref)
+    print(f"14B x1 layer, L=6144: ours {e_ours:.3e}")
+    assert out.shape == (1, 16, 6, 64, 64) and e_ours < TOL
+
+
 def test_text_cache_tracks_inplace_updates():
     cfg = R.WAN_TINY
     sd = R.init_state_dict(cfg, seed=3, bias_std=0.02)

@@ -236,10 +236,13 @@ def skinny_linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor]
         out = torch.empty((M, N), dtype=out_dtype or x2.dtype, device=x.device)
     if bias is not None and bias.dtype != torch.float32:
         raise TypeError("skinny_linear: bias must be float32")
-    L.check(L.load().vist3a_skinny_linear(x2.data_ptr(), _dt(x2), x2.stride(0), w.data_ptr(), _dt(w), w.stride(0),
-                                          _ptr(bias), out.data_ptr(), _dt(out), out.stride(0), M, N, K, ACT[pre_act],
-                                          ACT[act], _ptr(gate), _ptr(residual), residual.stride(0) if residual is not None else 0,
-                                          _stream()))
+    for m0 in range(0, M, 16):  # the kernel keeps 16 token rows in registers per pass over the weights
+        m1 = min(M, m0 + 16)
+        res = residual[m0:m1] if residual is not None else None
+        L.check(L.load().vist3a_skinny_linear(x2[m0:m1].data_ptr(), _dt(x2), x2.stride(0), w.data_ptr(), _dt(w), w.stride(0),
+                                              _ptr(bias), out[m0:m1].data_ptr(), _dt(out), out.stride(0), m1 - m0, N, K, ACT[pre_act],
+                                              ACT[act], _ptr(gate), _ptr(res), residual.stride(0) if residual is not None else 0,
+                                              _stream()))
     return out
 
 
@@ -394,14 +397,16 @@ def linear_tokens16(x16: torch.Tensor, M: int, w: torch.Tensor, bias: Optional[t
                     out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """nn.Linear for M <= 16 tokens, HBM-bound on the weights: the weight matrix [N, K] is streamed by TMA as the A operand of
     the tcgen05 GEMM (TF32 for fp32 weights) against the 16-row padded token matrix x16 [16, K]; a transposed epilogue kernel
-    adds bias / activation / LayerScale / residual.  Returns y [16, N] (rows >= M are left untouched)."""
+    adds bias / activation / LayerScale / residual.  x16 may also be a 32-row buffer (up to 32 tokens: 21-view scenes).
+    Returns y [rows(x16), N] (rows >= M are left untouched)."""
     _need_cuda(x16, w, bias, gate, residual, out)
-    if x16.shape[0] != 16 or not x16.is_contiguous() or M > 16:
-        raise ValueError("linear_tokens16: x16 must be a contiguous [16, K] buffer holding M <= 16 token rows")
+    TP = x16.shape[0]
+    if TP not in (16, 32) or not x16.is_contiguous() or M > TP:
+        raise ValueError("linear_tokens16: x16 must be a contiguous [16 or 32, K] buffer holding M <= rows token rows")
     N = w.shape[0]
-    ct = gemm(w, x16, out_dtype=torch.float32, two_cta=False)  # [N, 16] = W x^T
+    ct = gemm(w, x16, out_dtype=torch.float32, two_cta=False)  # [N, TP] = W x^T
     if out is None:
-        out = torch.zeros((16, N), dtype=torch.float32, device=x16.device)
+        out = torch.zeros((TP, N), dtype=torch.float32, device=x16.device)
     L.check(L.load().vist3a_bias_act_t(ct.data_ptr(), ct.stride(0), _ptr(bias), ACT[act], _ptr(gate), _ptr(residual),
                                        residual.stride(0) if residual is not None else 0, out.data_ptr(), out.stride(0), M, N,
                                        _stream()))

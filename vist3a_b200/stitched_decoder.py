@@ -436,13 +436,14 @@ class StitchVAE3DB200(torch.nn.Module):
         w, cfg = self.w, self.cfg
         C2 = 2 * cfg.embed_dim
         Hn = cfg.cam_heads
-        if V > 16:
-            raise NotImplementedError("camera head kernels handle up to 16 views per scene")
+        if V > 32:
+            raise NotImplementedError("camera head kernels handle up to 32 views per scene")
+        TP = 16 if V <= 16 else 32  # padded token rows of the weight-streaming GEMMs' B operand
         per_batch = []
         dev = self.device
 
-        def buf(n):  # 16-row padded token matrix (rows >= V stay zero): B operand of the weight-streaming GEMMs
-            return torch.zeros((16, n), dtype=torch.float32, device=dev)
+        def buf(n):  # padded token matrix (rows >= V stay zero): B operand of the weight-streaming GEMMs
+            return torch.zeros((TP, n), dtype=torch.float32, device=dev)
 
         for b in range(B):
             cam_rows = inter_last.view(B, V, P, C2)[b, :, 0]  # [V, C2] view, row stride P*C2
