@@ -34,9 +34,15 @@ extern "C" {
 #define VIST3A_DTYPE_F32 1
 
 const char* vist3a_last_error(void);
-int vist3a_abi_version(void); /* 3 */
+int vist3a_abi_version(void); /* 4 */
 /* number of kernels this library has launched from the calling process (all threads) */
 int64_t vist3a_launch_count(void);
+/* Programmatic dependent launch (PDL) of the hot kernels (GEMM, attention, LayerNorm, RMSNorm+RoPE, row_rinv): each is launched
+ * with the programmatic-stream-serialization attribute and executes griddepcontrol.wait before its first global-memory access,
+ * so its prologue (mbarrier init, TMEM allocation, tensor-map prefetch, CTA scheduling) overlaps the tail of the kernel before
+ * it in the stream -- also inside a captured CUDA graph.  Results are identical either way.  Default: on (env VIST3A_PDL=0 turns
+ * it off at load).  Returns the previous setting.  No counterpart in the reference (PyTorch launches are fully serialised). */
+int vist3a_set_pdl(int32_t enable);
 
 /* ------------------------------------------------------------------------------------------
  * GEMM  C[M,N] = epilogue( A[M,K] · W[N,K]^T )      tcgen05.mma + TMA + TMEM accumulators
@@ -303,6 +309,33 @@ int vist3a_gaussian_epilogue(const float* depth_feat, int64_t ld_df, int64_t cd,
                              const float* sh_mask, int64_t d_sh, int64_t S, int64_t H, int64_t W, float* depth,
                              float* means, float* scales, float* rotations, float* opacities, float* harmonics,
                              float* covariances, float* scene_sum, void* stream);
+
+/* Gaussian adapter on given positions (the voxelize=True branch): rows of feats hold (density, scales 3, quaternion xyzw 4,
+ * SH 3*d_sh) = raw_gs_dim values; means = pts, the other outputs as vist3a_gaussian_epilogue.
+ * replaces: map_pdf_to_opacity + UnifiedGaussianAdapter.forward on the fused voxels (models/anysplat_stitched.py:457-474,
+ *   AS/model/encoder/common/gaussian_adapter.py:114-147). */
+int vist3a_gaussian_adapter(const float* pts, const float* feats, int64_t ld_feats, const float* sh_mask, int64_t d_sh, int64_t P,
+                            float* means, float* scales, float* rotations, float* opacities, float* harmonics, float* covariances,
+                            void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Voxelised Gaussian fusion (integer / index work, HBM bound; no tensor cores)
+ * replaces: EncoderAnySplat.voxelizaton_with_fusion (AS/model/encoder/anysplat.py:298-335), called per batch element from
+ *   models/anysplat_stitched.py:419-440 when cfg.voxelize is set (released AnySplat configs: voxelize true, voxel_size 0.002):
+ *     voxel   = round_half_even(pts / voxel_size) -> int32 per axis
+ *     unique voxels in lexicographic (x, y, z) order (torch.unique(dim=0)), inverse index, counts
+ *     w_i     = exp(conf_i - max_voxel conf) / (sum_voxel exp(conf - max) + 1e-6)
+ *     voxel_pts = sum_i w_i pts_i ; voxel_feats = sum_i w_i feats_i      (summed in point order: the sort is stable)
+ * pts [N, 3] fp32; feats rows of feat_dim (<= 125) fp32 at stride ld_feats; conf_i = conf[i * conf_stride] (the confidence may be
+ * a column of the same rows).  voxel_pts [N, 3] and voxel_feats [N, feat_dim] have capacity for N voxels; the first *n_voxels
+ * rows are written.  inverse [N] / counts [N] (int32) are optional (NULL).  *n_voxels (device or pinned-host int64) is written by
+ * the last kernels of the call: read it after synchronising `stream`; -1 = the coordinate ranges need more than 64 key bits.
+ * workspace: vist3a_voxel_fusion_workspace_bytes(N) bytes of device memory, 256-byte aligned, caller-owned.
+ * Every stage is asynchronous on `stream` (no host round trip): radix passes beyond ceil(key bits / 8) exit immediately. */
+int64_t vist3a_voxel_fusion_workspace_bytes(int64_t n_points);
+int vist3a_voxel_fusion(const float* pts, const float* feats, int64_t ld_feats, int64_t feat_dim, const float* conf, int64_t conf_stride,
+                        int64_t n_points, float voxel_size, float* voxel_pts, float* voxel_feats, int32_t* inverse, int32_t* counts,
+                        int64_t* n_voxels, void* workspace, int64_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

@@ -6,6 +6,9 @@ on CPU so that oracle/decoder_ref.py can be validated against it and golden vect
 What is stubbed: third-party roots that the reference imports at module load but never
 executes on the `forward_with_latent(train=False, voxelize=False)` path, `VGGT.from_pretrained`
 (network) and the `AutoencoderKLWan` isinstance check.  The reference's forward code runs unmodified.
+The voxelize=True branch calls torch_scatter (absent here; rusty1s/pytorch_scatter, unpinned in requirements.txt):
+`scatter_add` / `scatter_max` are provided with that package's documented semantics (out[index[i]] += src[i] along dim 0;
+max with -inf-free reduction over present indices) on top of torch.index_add_ / index_reduce_.
 
 `width="tiny"` shrinks constructor hyper-parameters only (embed dim, head counts, DPT feature
 widths) through the reference classes' own keyword arguments, so that a full weight set is a few MB
@@ -37,6 +40,32 @@ _STUBS = [
 
 def available() -> bool:
     return os.path.isdir(os.path.join(REFERENCE_ROOT, "models"))
+
+
+def _install_torch_scatter():
+    """functional stand-in for the two torch_scatter calls of voxelizaton_with_fusion (AS/model/encoder/anysplat.py:314-333)"""
+    if "torch_scatter" in sys.modules and hasattr(sys.modules["torch_scatter"], "_vist3a_oracle"):
+        return
+    try:
+        import torch_scatter  # noqa: F401  (the real package, if it is ever installed)
+        return
+    except Exception:
+        pass
+    m = types.ModuleType("torch_scatter")
+
+    def scatter_add(src, index, dim=0, out=None, dim_size=None):
+        assert dim == 0 and out is None
+        n = int(index.max()) + 1 if dim_size is None else dim_size
+        return torch.zeros((n,) + tuple(src.shape[1:]), dtype=src.dtype, device=src.device).index_add_(0, index, src)
+
+    def scatter_max(src, index, dim=0, out=None, dim_size=None):
+        assert dim == 0 and out is None and src.dim() == 1
+        n = int(index.max()) + 1 if dim_size is None else dim_size
+        mx = torch.full((n,), -float("inf"), dtype=src.dtype, device=src.device).index_reduce_(0, index, src, "amax", include_self=True)
+        return mx, None  # the reference discards argmax (:314)
+
+    m.scatter_add, m.scatter_max, m._vist3a_oracle = scatter_add, scatter_max, True
+    sys.modules["torch_scatter"] = m
 
 
 def _make_stub(name: str):
@@ -84,10 +113,12 @@ FULL = RefWidth()
 TINY = RefWidth(embed_dim=64, num_heads=1, dino_depth=4, cam_heads=2, dpt_features=256, dpt_out_channels=(32, 32, 64, 64), pos_grid=37)
 
 
-def load_reference(width: RefWidth = FULL, resolution: int = 512, seed: int = 0, sh_degree: int = 4):
+def load_reference(width: RefWidth = FULL, resolution: int = 512, seed: int = 0, sh_degree: int = 4, voxelize: bool = False,
+                   voxel_size: float = 0.002):
     """Returns the reference StitchVAE3D (fp32, eval, checkpointing off) with seeded random init."""
     if not available():
         raise RuntimeError(f"{REFERENCE_ROOT} is not mounted here; the real reference can only be imported in the build container")
+    _install_torch_scatter()
     for n in _STUBS:
         _make_stub(n)
     if REFERENCE_ROOT not in sys.path:
@@ -145,11 +176,11 @@ def load_reference(width: RefWidth = FULL, resolution: int = 512, seed: int = 0,
         ga_mod = importlib.import_module(P + ".encoder.common.gaussian_adapter")
         dec_mod = importlib.import_module(P + ".decoder.decoder_splatting_cuda")
         cfg = enc_mod.EncoderAnySplatCfg(
-            name="anysplat", anchor_feat_dim=83, voxel_size=0.002, n_offsets=2, d_feature=32, add_view=False,
+            name="anysplat", anchor_feat_dim=83, voxel_size=voxel_size, n_offsets=2, d_feature=32, add_view=False,
             num_monocular_samples=32, backbone=None, visualizer=None,
             gaussian_adapter=ga_mod.GaussianAdapterCfg(0.5, 15.0, sh_degree), apply_bounds_shim=True,
             opacity_mapping=enc_mod.OpacityMappingCfg(0.0, 0.0, 1), gaussians_per_pixel=1, num_surfaces=1,
-            gs_params_head_type="dpt_gs", pred_head_type="depth", voxelize=False, intermediate_layer_idx=[4, 11, 17, 23])
+            gs_params_head_type="dpt_gs", pred_head_type="depth", voxelize=voxelize, intermediate_layer_idx=[4, 11, 17, 23])
         torch.manual_seed(seed)
         ff = anysplat_mod.AnySplat(cfg, dec_mod.DecoderSplattingCUDACfg("splatting_cuda", [1.0, 1.0, 1.0], False))
         model = sm.StitchVAE3D(FakeVAE(), ff, torch.device("cpu"), "enc_blocks_2",

@@ -23,9 +23,10 @@ def main():
     ap.add_argument("--batch", type=int, default=1)
     ap.add_argument("--ncu", action="store_true", help="one warm forward between cudaProfilerStart/Stop (ncu --profile-from-start off)")
     ap.add_argument("--ncu-all", action="store_true", help="two forwards and exit (ncu -k filters the kernel)")
+    ap.add_argument("--voxelize", action="store_true", help="voxelised-fusion branch (voxel_size 0.002)")
     a = ap.parse_args()
     torch.cuda.set_device(0)
-    cfg = DecoderConfig()
+    cfg = DecoderConfig(voxelize=a.voxelize)
     sd = random_state_dict(cfg, 0, "cuda")
     m = StitchVAE3DB200.from_state_dict(sd, cfg, "cuda")
     del sd
@@ -52,6 +53,8 @@ def main():
     torch.cuda.synchronize()
     ms = s.elapsed_time(e) / a.iters
     N = a.batch * V * 448 * 448
+    if a.voxelize:
+        print(f"voxels: {o.gaussians.means.shape[1]} of {V * 448 * 448} pixels (ratio {o.infos['voxelize_ratio']:.4f})")
     print(f"decoder {V} views: {ms:.2f} ms/forward, {N / ms * 1e3 / 1e6:.1f} M Gaussians/s, peak mem {torch.cuda.max_memory_allocated() / 1e9:.1f} GB")
     with ops.OpTimer() as t:
         m.forward_with_latent(lat, img)

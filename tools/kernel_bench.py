@@ -83,6 +83,22 @@ def main():
                 r["fa2"] = str(ex)[:60]
         print(json.dumps(r), flush=True)
         res.append(r)
+    # voxelised fusion at the BASELINE size (13 views x 448^2 points, 83 features + confidence per row): HBM-bound index work;
+    # algorithmic bytes = every point row read once + every voxel row written once
+    if not a.only or a.only in ("voxel", "voxel_fusion"):
+        n, c = 13 * 448 * 448, 83
+        g = torch.Generator(device="cuda").manual_seed(3)
+        for name, spread in (("voxel_sparse", 1.0), ("voxel_dense", 0.05)):   # ~1 point per voxel / many points per voxel
+            pts = (torch.randn(n, 3, device="cuda", generator=g) * spread).contiguous()
+            rows = torch.randn(n, c + 1, device="cuda", generator=g)
+            o = ops.voxel_fusion(pts, rows, rows[:, c], 0.002, feat_dim=c)
+            m = o["n_voxels"]
+            ms = timeit(lambda: ops.voxel_fusion(pts, rows, rows[:, c], 0.002, feat_dim=c), a.iters, flush=flush)
+            by = 4.0 * (n * (3 + c + 1) + m * (3 + c))
+            r = {"name": name, "points": n, "voxels": m, "ms": round(ms, 4), "algorithmic_GB": round(by / 1e9, 3), "GBps": round(by / ms / 1e6, 1),
+                 "note": "includes the host read of the voxel count (stream sync) and workspace allocation"}
+            print(json.dumps(r), flush=True)
+            res.append(r)
 
 
 if __name__ == "__main__":

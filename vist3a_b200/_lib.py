@@ -24,6 +24,7 @@ EXPORTS = (
     "vist3a_last_error",
     "vist3a_abi_version",
     "vist3a_launch_count",
+    "vist3a_set_pdl",
     "vist3a_gemm",
     "vist3a_fmha_fwd",
     "vist3a_layernorm",
@@ -47,6 +48,9 @@ EXPORTS = (
     "vist3a_rgb_to_nhwc4pad",
     "vist3a_pose_to_cameras",
     "vist3a_gaussian_epilogue",
+    "vist3a_gaussian_adapter",
+    "vist3a_voxel_fusion",
+    "vist3a_voxel_fusion_workspace_bytes",
 )
 
 
@@ -148,8 +152,12 @@ def load(build_if_missing: bool = False) -> C.CDLL:
     lib.vist3a_last_error.restype = C.c_char_p
     lib.vist3a_abi_version.restype = C.c_int
     lib.vist3a_launch_count.restype = C.c_int64
-    for name in EXPORTS[3:]:
+    lib.vist3a_set_pdl.restype = C.c_int
+    lib.vist3a_set_pdl.argtypes = [C.c_int32]
+    for name in EXPORTS[4:-1]:
         getattr(lib, name).restype = C.c_int
+    lib.vist3a_voxel_fusion_workspace_bytes.restype = C.c_int64
+    lib.vist3a_voxel_fusion_workspace_bytes.argtypes = [C.c_int64]
     lib.vist3a_gemm.argtypes = [C.POINTER(GemmArgs), C.c_void_p]
     lib.vist3a_fmha_fwd.argtypes = [C.POINTER(FmhaArgs), C.c_void_p]
     i64, i32, f32, vp, u32 = C.c_int64, C.c_int32, C.c_float, C.c_void_p, C.c_uint32
@@ -175,6 +183,8 @@ def load(build_if_missing: bool = False) -> C.CDLL:
     lib.vist3a_pose_to_cameras.argtypes = [vp, vp, vp, vp, vp, vp, i64, i64, i64, vp]
     lib.vist3a_gaussian_epilogue.argtypes = [vp, i64, i64, vp, f32, vp, i64, vp, vp, vp, i64, i64, i64, i64, vp, vp, vp, vp, vp, vp,
                                              vp, vp, vp]
+    lib.vist3a_gaussian_adapter.argtypes = [vp, vp, i64, vp, i64, i64, vp, vp, vp, vp, vp, vp, vp]
+    lib.vist3a_voxel_fusion.argtypes = [vp, vp, i64, i64, vp, i64, i64, f32, vp, vp, vp, vp, vp, vp, i64, vp]
     _lib = lib
     return lib
 
@@ -182,6 +192,11 @@ def load(build_if_missing: bool = False) -> C.CDLL:
 def check(rc: int) -> None:
     if rc != OK:
         raise Vist3aError(rc, load().vist3a_last_error().decode())
+
+
+def set_pdl(enable: bool) -> bool:
+    """Turn programmatic dependent launch of the hot kernels on/off (default on); returns the previous setting."""
+    return bool(load().vist3a_set_pdl(1 if enable else 0))
 
 
 def launch_count() -> int:

@@ -1,5 +1,7 @@
 // extern "C" surface of libvist3a_sm100 (declared in include/vist3a_sm100.h) plus the host
 // utilities shared by the kernels' launchers.
+#include <stdlib.h>
+
 #include <atomic>
 
 #include "host_util.cuh"
@@ -35,6 +37,11 @@ int pose_to_cameras_entry(const float*, float*, float*, float*, float*, float*, 
 int gaussian_epilogue_entry(const float*, long long, long long, const float*, float, const float*, long long, const float*,
                             const float*, const float*, long long, long long, long long, long long, float*, float*, float*, float*,
                             float*, float*, float*, float*, cudaStream_t);
+int gaussian_adapter_entry(const float*, const float*, long long, const float*, long long, long long, float*, float*, float*, float*, float*,
+                           float*, cudaStream_t);
+long long voxel_fusion_workspace_bytes(long long);
+int voxel_fusion_entry(const float*, const float*, long long, long long, const float*, long long, long long, float, float*, float*, int*, int*,
+                       long long*, void*, long long, cudaStream_t);
 int timestep_features_entry(const float*, void*, int, long long, long long, cudaStream_t);
 int patchify_entry(const void*, int, void*, long long, long long, long long, long long, long long, cudaStream_t);
 int unpatchify_entry(const void*, int, long long, void*, int, long long, long long, long long, long long, long long,
@@ -54,6 +61,18 @@ int set_error(int code, const char* fmt, ...) {
   va_end(ap);
   return code;
 }
+
+namespace {
+std::atomic<int>& pdl_flag() {
+  static std::atomic<int> f{[] {
+    const char* e = getenv("VIST3A_PDL");
+    return (e && e[0] == '0') ? 0 : 1;
+  }()};
+  return f;
+}
+}  // namespace
+bool pdl_enabled() { return pdl_flag().load(std::memory_order_relaxed) != 0; }
+int set_pdl(int enable) { return pdl_flag().exchange(enable ? 1 : 0); }
 
 std::atomic<long long>& launch_counter() {
   static std::atomic<long long> c{0};
@@ -140,8 +159,9 @@ using namespace v3a;
 extern "C" {
 
 const char* vist3a_last_error(void) { return last_error_buf(); }
-int vist3a_abi_version(void) { return 3; }
+int vist3a_abi_version(void) { return 4; }
 int64_t vist3a_launch_count(void) { return (int64_t)launch_counter().load(); }
+int vist3a_set_pdl(int32_t enable) { return set_pdl(enable); }
 
 int vist3a_gemm(const vist3a_gemm_args* args, void* stream) { return gemm_entry(args, ST(stream)); }
 int vist3a_fmha_fwd(const vist3a_fmha_args* args, void* stream) { return fmha_entry(args, ST(stream)); }
@@ -250,6 +270,19 @@ int vist3a_gaussian_epilogue(const float* depth_feat, int64_t ld_df, int64_t cd,
                              float* covariances, float* scene_sum, void* stream) {
   return gaussian_epilogue_entry(depth_feat, ld_df, cd, depth_w, depth_b, gs_raw, ld_raw, extr, intr, sh_mask, d_sh, S, H, W,
                                  depth, means, scales, rotations, opacities, harmonics, covariances, scene_sum, ST(stream));
+}
+
+int vist3a_gaussian_adapter(const float* pts, const float* feats, int64_t ld_feats, const float* sh_mask, int64_t d_sh, int64_t P,
+                            float* means, float* scales, float* rotations, float* opacities, float* harmonics, float* covariances,
+                            void* stream) {
+  return gaussian_adapter_entry(pts, feats, ld_feats, sh_mask, d_sh, P, means, scales, rotations, opacities, harmonics, covariances, ST(stream));
+}
+int64_t vist3a_voxel_fusion_workspace_bytes(int64_t n_points) { return voxel_fusion_workspace_bytes(n_points); }
+int vist3a_voxel_fusion(const float* pts, const float* feats, int64_t ld_feats, int64_t feat_dim, const float* conf, int64_t conf_stride,
+                        int64_t n_points, float voxel_size, float* voxel_pts, float* voxel_feats, int32_t* inverse, int32_t* counts,
+                        int64_t* n_voxels, void* workspace, int64_t workspace_bytes, void* stream) {
+  return voxel_fusion_entry(pts, feats, ld_feats, feat_dim, conf, conf_stride, n_points, voxel_size, voxel_pts, voxel_feats, inverse, counts,
+                            reinterpret_cast<long long*>(n_voxels), workspace, workspace_bytes, ST(stream));
 }
 
 }  // extern "C"

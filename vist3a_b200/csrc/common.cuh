@@ -39,6 +39,14 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
+// Programmatic dependent launch (PDL).  A kernel launched with the programmatic-stream-serialization attribute may start while
+// its predecessor in the stream is still draining: everything before pdl_wait() (barrier init, TMEM allocation, descriptor
+// prefetch) overlaps the predecessor's tail; pdl_wait() returns once the predecessor grid has completed and its writes are
+// visible, so it must precede the first global-memory access.  pdl_launch_dependents() lets the successor be scheduled as
+// soon as every CTA of this grid has issued it (or exited).  Both are no-ops for a kernel launched without the attribute.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ uint64_t globaltimer_ns() {
   uint64_t t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));

@@ -482,6 +482,34 @@ int pose_to_cameras_entry(const float* pose_raw, float* pose_act, float* extr, f
 constexpr int kGeTile = 64;     // Gaussians per block
 constexpr int kGeMaxRaw = 96;   // >= 8 + 3 * d_sh for sh_degree <= 4 (83) rounded up
 
+// Gaussian adapter of one element (gaussian_adapter.py:114-147, common/gaussians.py:8-44): r = raw[0..7] = (density, scales 3, quaternion xyzw 4),
+// o[3..5] scales, o[6..9] rotation (xyzw, normalised), o[10] opacity, o[11..19] covariance R S S^T R^T.
+__device__ __forceinline__ void gaussian_params(const float* r, float* o) {
+  float sc[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const float x = r[1 + i];
+    const float sp = x > 20.f ? x : log1pf(expf(x));  // F.softplus (threshold 20)
+    sc[i] = fminf(0.001f * sp, 0.3f);
+    o[3 + i] = sc[i];
+  }
+  const float qn = sqrtf(r[4] * r[4] + r[5] * r[5] + r[6] * r[6] + r[7] * r[7]) + 1e-8f;
+  const float qi = r[4] / qn, qj = r[5] / qn, qk = r[6] / qn, qr = r[7] / qn;
+  o[6] = qi; o[7] = qj; o[8] = qk; o[9] = qr;
+  o[10] = 1.0f / (1.0f + expf(-r[0]));
+  const float two_s = 2.0f / (qi * qi + qj * qj + qk * qk + qr * qr + 1e-8f);
+  float R[9];
+  R[0] = 1 - two_s * (qj * qj + qk * qk); R[1] = two_s * (qi * qj - qk * qr); R[2] = two_s * (qi * qk + qj * qr);
+  R[3] = two_s * (qi * qj + qk * qr); R[4] = 1 - two_s * (qi * qi + qk * qk); R[5] = two_s * (qj * qk - qi * qr);
+  R[6] = two_s * (qi * qk - qj * qr); R[7] = two_s * (qj * qk + qi * qr); R[8] = 1 - two_s * (qi * qi + qj * qj);
+  const float s2[3] = {sc[0] * sc[0], sc[1] * sc[1], sc[2] * sc[2]};
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+#pragma unroll
+    for (int b = 0; b < 3; ++b)
+      o[11 + a * 3 + b] = R[a * 3 + 0] * s2[0] * R[b * 3 + 0] + R[a * 3 + 1] * s2[1] * R[b * 3 + 1] + R[a * 3 + 2] * s2[2] * R[b * 3 + 2];
+}
+
 __global__ void __launch_bounds__(256) gaussian_epilogue_kernel(
     const float* __restrict__ depth_feat, long long ld_df, int cd, const float* __restrict__ depth_w, float depth_b,
     const float* __restrict__ gs_raw, long long ld_raw, const float* __restrict__ extr, const float* __restrict__ intr,
@@ -537,30 +565,7 @@ __global__ void __launch_bounds__(256) gaussian_epilogue_kernel(
       float* o = s_out[g];
       o[0] = mx; o[1] = my; o[2] = mz;
       nrm = sqrtf(mx * mx + my * my + mz * mz);
-      const float* r = s_raw[g];
-      float sc[3];
-#pragma unroll
-      for (int i = 0; i < 3; ++i) {
-        const float x = r[1 + i];
-        const float sp = x > 20.f ? x : log1pf(expf(x));  // F.softplus (threshold 20)
-        sc[i] = fminf(0.001f * sp, 0.3f);
-        o[3 + i] = sc[i];
-      }
-      const float qn = sqrtf(r[4] * r[4] + r[5] * r[5] + r[6] * r[6] + r[7] * r[7]) + 1e-8f;
-      const float qi = r[4] / qn, qj = r[5] / qn, qk = r[6] / qn, qr = r[7] / qn;
-      o[6] = qi; o[7] = qj; o[8] = qk; o[9] = qr;
-      o[10] = 1.0f / (1.0f + expf(-r[0]));
-      const float two_s = 2.0f / (qi * qi + qj * qj + qk * qk + qr * qr + 1e-8f);
-      float R[9];
-      R[0] = 1 - two_s * (qj * qj + qk * qk); R[1] = two_s * (qi * qj - qk * qr); R[2] = two_s * (qi * qk + qj * qr);
-      R[3] = two_s * (qi * qj + qk * qr); R[4] = 1 - two_s * (qi * qi + qk * qk); R[5] = two_s * (qj * qk - qi * qr);
-      R[6] = two_s * (qi * qk - qj * qr); R[7] = two_s * (qj * qk + qi * qr); R[8] = 1 - two_s * (qi * qi + qj * qj);
-      const float s2[3] = {sc[0] * sc[0], sc[1] * sc[1], sc[2] * sc[2]};
-#pragma unroll
-      for (int a = 0; a < 3; ++a)
-#pragma unroll
-        for (int b = 0; b < 3; ++b)
-          o[11 + a * 3 + b] = R[a * 3 + 0] * s2[0] * R[b * 3 + 0] + R[a * 3 + 1] * s2[1] * R[b * 3 + 1] + R[a * 3 + 2] * s2[2] * R[b * 3 + 2];
+      gaussian_params(s_raw[g], o);
     }
   }
   // block reduction of |means| for scene_scale
@@ -593,6 +598,49 @@ int gaussian_epilogue_entry(const float* depth_feat, long long ld_df, long long 
   gaussian_epilogue_kernel<<<grid_for(P, kGeTile), 256, 0, st>>>(depth_feat, ld_df, (int)cd, depth_w, depth_b, gs_raw, ld_raw, extr, intr,
                                                                  sh_mask, (int)d_sh, P, (int)(H * W), (int)W, depth, means, scales, rot,
                                                                  opac, harm, cov, scene_sum);
+  V3A_CUDA_OK(cudaGetLastError());
+  launch_counter().fetch_add(1);
+  return VIST3A_OK;
+}
+
+// ----------------------------------------------------------------------------------------
+// Gaussian adapter on fused voxels (voxelize=True branch): positions are given, rows hold the raw_gs_dim features
+// ----------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gaussian_adapter_kernel(const float* __restrict__ pts, const float* __restrict__ feats, long long ld_feats,
+                                                               const float* __restrict__ sh_mask, int d_sh, long long P, float* __restrict__ means,
+                                                               float* __restrict__ scales, float* __restrict__ rot, float* __restrict__ opac,
+                                                               float* __restrict__ harm, float* __restrict__ cov) {
+  __shared__ float s_raw[kGeTile][kGeMaxRaw + 1];
+  __shared__ float s_out[kGeTile][20];
+  const long long p0 = (long long)blockIdx.x * kGeTile;
+  const int n_here = (int)min((long long)kGeTile, P - p0);
+  const int nraw = 8 + 3 * d_sh;
+  for (int i = threadIdx.x; i < n_here * nraw; i += blockDim.x) {
+    const int g = i / nraw, c = i % nraw;
+    s_raw[g][c] = feats[(p0 + g) * ld_feats + c];
+  }
+  __syncthreads();
+  const int nh = 3 * d_sh;
+  for (int i = threadIdx.x; i < n_here * nh; i += blockDim.x) {
+    const int g = i / nh, c = i % nh;
+    harm[(p0 + g) * nh + c] = s_raw[g][8 + c] * sh_mask[c % d_sh];
+  }
+  if (threadIdx.x < n_here) gaussian_params(s_raw[threadIdx.x], s_out[threadIdx.x]);
+  __syncthreads();
+  for (int i = threadIdx.x; i < n_here * 3; i += blockDim.x) means[p0 * 3 + i] = pts[p0 * 3 + i];
+  for (int i = threadIdx.x; i < n_here * 3; i += blockDim.x) scales[p0 * 3 + i] = s_out[i / 3][3 + i % 3];
+  for (int i = threadIdx.x; i < n_here * 4; i += blockDim.x) rot[p0 * 4 + i] = s_out[i / 4][6 + i % 4];
+  for (int i = threadIdx.x; i < n_here; i += blockDim.x) opac[p0 + i] = s_out[i][10];
+  for (int i = threadIdx.x; i < n_here * 9; i += blockDim.x) cov[p0 * 9 + i] = s_out[i / 9][11 + i % 9];
+}
+
+int gaussian_adapter_entry(const float* pts, const float* feats, long long ld_feats, const float* sh_mask, long long d_sh, long long P, float* means,
+                           float* scales, float* rot, float* opac, float* harm, float* cov, cudaStream_t st) {
+  V3A_REQUIRE(pts && feats && sh_mask && means && scales && rot && opac && harm && cov, VIST3A_ERR_INVALID, "gaussian_adapter: null pointer");
+  V3A_REQUIRE(P > 0 && d_sh > 0 && 8 + 3 * d_sh <= kGeMaxRaw && ld_feats >= 8 + 3 * d_sh, VIST3A_ERR_INVALID, "gaussian_adapter: bad sizes (d_sh=%lld)", d_sh);
+  int rc = check_arch();
+  if (rc) return rc;
+  gaussian_adapter_kernel<<<grid_for(P, kGeTile), 256, 0, st>>>(pts, feats, ld_feats, sh_mask, (int)d_sh, P, means, scales, rot, opac, harm, cov);
   V3A_CUDA_OK(cudaGetLastError());
   launch_counter().fetch_add(1);
   return VIST3A_OK;

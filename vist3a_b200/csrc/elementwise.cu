@@ -57,6 +57,8 @@ __global__ void __launch_bounds__(128) layernorm_kernel(const void* __restrict__
                                                         const float* __restrict__ mul, long long mul_bs,
                                                         const float* __restrict__ add, long long add_bs, float eps,
                                                         int mul_plus_one, RowMap3 imap, RowMap3 omap) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long row = (long long)blockIdx.x * 4 + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -119,11 +121,12 @@ static int launch_ln(const void* x, int xdt, long long ldx, void* out, int odt, 
                      int mp1, RowMap3 im, RowMap3 om, cudaStream_t st) {
   const unsigned grid = (unsigned)((rows + 3) / 4);
   const bool fi = xdt == VIST3A_DTYPE_F32, fo = odt == VIST3A_DTYPE_F32;
-  if (fi && fo) layernorm_kernel<NCHUNK, true, true><<<grid, 128, 0, st>>>(x, ldx, out, ldo, rows, dim, rpb, mul, mbs, add, abs_, eps, mp1, im, om);
-  else if (fi) layernorm_kernel<NCHUNK, true, false><<<grid, 128, 0, st>>>(x, ldx, out, ldo, rows, dim, rpb, mul, mbs, add, abs_, eps, mp1, im, om);
-  else if (fo) layernorm_kernel<NCHUNK, false, true><<<grid, 128, 0, st>>>(x, ldx, out, ldo, rows, dim, rpb, mul, mbs, add, abs_, eps, mp1, im, om);
-  else layernorm_kernel<NCHUNK, false, false><<<grid, 128, 0, st>>>(x, ldx, out, ldo, rows, dim, rpb, mul, mbs, add, abs_, eps, mp1, im, om);
-  V3A_CUDA_OK(cudaGetLastError());
+  cudaError_t e;
+  if (fi && fo) e = launch_kernel(layernorm_kernel<NCHUNK, true, true>, dim3(grid), dim3(128), 0, st, true, 1, x, ldx, out, ldo, rows, dim, rpb, mul, mbs, add, abs_, eps, mp1, im, om);
+  else if (fi) e = launch_kernel(layernorm_kernel<NCHUNK, true, false>, dim3(grid), dim3(128), 0, st, true, 1, x, ldx, out, ldo, rows, dim, rpb, mul, mbs, add, abs_, eps, mp1, im, om);
+  else if (fo) e = launch_kernel(layernorm_kernel<NCHUNK, false, true>, dim3(grid), dim3(128), 0, st, true, 1, x, ldx, out, ldo, rows, dim, rpb, mul, mbs, add, abs_, eps, mp1, im, om);
+  else e = launch_kernel(layernorm_kernel<NCHUNK, false, false>, dim3(grid), dim3(128), 0, st, true, 1, x, ldx, out, ldo, rows, dim, rpb, mul, mbs, add, abs_, eps, mp1, im, om);
+  V3A_CUDA_OK(e);
   launch_counter().fetch_add(1);
   return VIST3A_OK;
 }
@@ -135,8 +138,8 @@ int layernorm_entry(const void* x, int xdt, long long ldx, void* out, int odt, l
   if (in_map) im = {in_map->rpg, in_map->gstride, in_map->goff};
   if (out_map) om = {out_map->rpg, out_map->gstride, out_map->goff};
   V3A_REQUIRE(x && out, VIST3A_ERR_INVALID, "layernorm: null pointer");
-  V3A_REQUIRE(rows > 0 && dim > 0 && dim % 8 == 0 && dim <= 4096, VIST3A_ERR_INVALID,
-              "layernorm: dim must be a multiple of 8 and <= 4096 (got %lld)", dim);
+  V3A_REQUIRE(rows > 0 && dim > 0 && dim % 8 == 0 && dim <= 8192, VIST3A_ERR_INVALID,
+              "layernorm: dim must be a multiple of 8 and <= 8192 (got %lld)", dim);
   V3A_REQUIRE(ldx % 8 == 0 && ldo % 8 == 0 && ldx >= dim && ldo >= dim, VIST3A_ERR_INVALID, "layernorm: bad row strides");
   V3A_REQUIRE(mbs % 4 == 0 && abs_ % 4 == 0, VIST3A_ERR_INVALID, "layernorm: mul/add batch strides must be multiples of 4");
   if (rpb <= 0) rpb = rows;
@@ -144,7 +147,9 @@ int layernorm_entry(const void* x, int xdt, long long ldx, void* out, int odt, l
   if (nchunk <= 4) return launch_ln<4>(x, xdt, ldx, out, odt, ldo, rows, (int)dim, rpb, mul, mbs, add, abs_, eps, mp1, im, om, st);
   if (nchunk <= 6) return launch_ln<6>(x, xdt, ldx, out, odt, ldo, rows, (int)dim, rpb, mul, mbs, add, abs_, eps, mp1, im, om, st);
   if (nchunk <= 8) return launch_ln<8>(x, xdt, ldx, out, odt, ldo, rows, (int)dim, rpb, mul, mbs, add, abs_, eps, mp1, im, om, st);
-  return launch_ln<16>(x, xdt, ldx, out, odt, ldo, rows, (int)dim, rpb, mul, mbs, add, abs_, eps, mp1, im, om, st);
+  if (nchunk <= 16) return launch_ln<16>(x, xdt, ldx, out, odt, ldo, rows, (int)dim, rpb, mul, mbs, add, abs_, eps, mp1, im, om, st);
+  if (nchunk <= 20) return launch_ln<20>(x, xdt, ldx, out, odt, ldo, rows, (int)dim, rpb, mul, mbs, add, abs_, eps, mp1, im, om, st);  // Wan-14B (5120)
+  return launch_ln<32>(x, xdt, ldx, out, odt, ldo, rows, (int)dim, rpb, mul, mbs, add, abs_, eps, mp1, im, om, st);
 }
 
 // ----------------------------------------------------------------------------------------
@@ -155,6 +160,8 @@ __global__ void __launch_bounds__(128) rmsnorm_rope_kernel(__nv_bfloat16* __rest
                                                            int dim, int head_dim, const float* __restrict__ weight,
                                                            float eps, const float* __restrict__ rcos,
                                                            const float* __restrict__ rsin, long long rope_len, long long seg_stride) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long row = (long long)blockIdx.x * 4 + (threadIdx.x >> 5);
   if (row >= rows) return;
   x += (long long)blockIdx.y * seg_stride;   // segment (q | k of a fused qkv buffer) with its own weight vector
@@ -213,10 +220,11 @@ int rmsnorm_rope_entry(void* x, long long ldx, long long rows, long long dim, lo
   const dim3 grid((unsigned)((rows + 3) / 4), (unsigned)nseg);
   __nv_bfloat16* xp = reinterpret_cast<__nv_bfloat16*>(x);
   const int nchunk = (int)((dim + 255) / 256);
-  if (nchunk <= 6) rmsnorm_rope_kernel<6><<<grid, 128, 0, st>>>(xp, ldx, rows, (int)dim, (int)head_dim, weight, eps, rcos, rsin, rope_len, seg_stride);
-  else if (nchunk <= 20) rmsnorm_rope_kernel<20><<<grid, 128, 0, st>>>(xp, ldx, rows, (int)dim, (int)head_dim, weight, eps, rcos, rsin, rope_len, seg_stride);
-  else rmsnorm_rope_kernel<32><<<grid, 128, 0, st>>>(xp, ldx, rows, (int)dim, (int)head_dim, weight, eps, rcos, rsin, rope_len, seg_stride);
-  V3A_CUDA_OK(cudaGetLastError());
+  cudaError_t e;
+  if (nchunk <= 6) e = launch_kernel(rmsnorm_rope_kernel<6>, grid, dim3(128), 0, st, true, 1, xp, ldx, rows, (int)dim, (int)head_dim, weight, eps, rcos, rsin, rope_len, seg_stride);
+  else if (nchunk <= 20) e = launch_kernel(rmsnorm_rope_kernel<20>, grid, dim3(128), 0, st, true, 1, xp, ldx, rows, (int)dim, (int)head_dim, weight, eps, rcos, rsin, rope_len, seg_stride);
+  else e = launch_kernel(rmsnorm_rope_kernel<32>, grid, dim3(128), 0, st, true, 1, xp, ldx, rows, (int)dim, (int)head_dim, weight, eps, rcos, rsin, rope_len, seg_stride);
+  V3A_CUDA_OK(e);
   launch_counter().fetch_add(1);
   return VIST3A_OK;
 }
@@ -226,6 +234,8 @@ int rmsnorm_rope_entry(void* x, long long ldx, long long rows, long long dim, lo
 // ----------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) row_rinv_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, long long rows, int dim, float eps,
                                                        float* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -242,8 +252,8 @@ __global__ void __launch_bounds__(256) row_rinv_kernel(const __nv_bfloat16* __re
 
 int row_rinv_entry(const void* x, long long ldx, long long rows, long long dim, float eps, float* out, cudaStream_t st) {
   V3A_REQUIRE(x && out && rows > 0 && dim > 0 && dim % 8 == 0 && ldx % 8 == 0 && ldx >= dim, VIST3A_ERR_INVALID, "row_rinv: bad arguments");
-  row_rinv_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), ldx, rows, (int)dim, eps, out);
-  V3A_CUDA_OK(cudaGetLastError());
+  V3A_CUDA_OK(launch_kernel(row_rinv_kernel, dim3((unsigned)((rows + 7) / 8)), dim3(256), 0, st, true, 1,
+                            reinterpret_cast<const __nv_bfloat16*>(x), ldx, rows, (int)dim, eps, out));
   launch_counter().fetch_add(1);
   return VIST3A_OK;
 }

@@ -177,6 +177,8 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  pdl_launch_dependents();
+  pdl_wait();  // PDL: q/k/v of the previous kernel are read (and O written) only after this point
 
   if (warp < 4) {
     if constexpr (SPLIT == 1) asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
@@ -472,8 +474,7 @@ static int launch_fmha(const vist3a_fmha_args& a, cudaStream_t stream) {
   }
   const long long rows_per_cta = Cfg::BQ * Cfg::QT;
   dim3 grid((unsigned)((a.len_q + rows_per_cta - 1) / rows_per_cta), (unsigned)a.heads, (unsigned)a.batch);
-  kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tmQ, tmK, tmV, p);
-  V3A_CUDA_OK(cudaGetLastError());
+  V3A_CUDA_OK(launch_kernel(kern, grid, dim3(Cfg::THREADS), Cfg::SMEM_BYTES, stream, /*pdl=*/true, 1, tmQ, tmK, tmV, p));
   launch_counter().fetch_add(1);
   return VIST3A_OK;
 }

@@ -160,6 +160,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  // PDL: the set-up above overlapped the tail of the previous kernel; its results are needed from here on
+  pdl_launch_dependents();
+  pdl_wait();
 
   const int num_kb = shape.conv ? shape.kh * shape.kw * shape.cblocks : (shape.K + Cfg::BK - 1) / Cfg::BK;
   const int num_tiles = shape.tiles_m * shape.tiles_n;
@@ -430,16 +433,8 @@ static int launch_gemm(const vist3a_gemm_args& a, cudaStream_t stream) {
   const int tiles = shape.tiles_m * shape.tiles_n;
   int workers = num_sms() / kCta;
   if (workers > tiles) workers = tiles;
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)(workers * kCta));
-  cfg.blockDim = dim3(kGemmThreads);
-  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = kCta; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr; cfg.numAttrs = 1;
-  V3A_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, shape, ep));
+  V3A_CUDA_OK(launch_kernel(kern, dim3((unsigned)(workers * kCta)), dim3(kGemmThreads), Cfg::SMEM_BYTES, stream, /*pdl=*/true, kCta,
+                            tmA, tmB, shape, ep));
   launch_counter().fetch_add(1);
   return VIST3A_OK;
 }

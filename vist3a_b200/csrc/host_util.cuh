@@ -23,6 +23,39 @@ int num_sms();            // SM count of the current device (cached per device)
 int check_arch();         // VIST3A_OK if the current device is sm_100, else VIST3A_ERR_ARCH
 std::atomic<long long>& launch_counter();  // kernels launched by this library in this process
 
+bool pdl_enabled();        // programmatic dependent launch on the hot kernels (vist3a_set_pdl / env VIST3A_PDL, default on)
+int set_pdl(int enable);   // returns the previous setting
+
+// Launch `kern` on `st`; with pdl (and PDL enabled) the launch carries the programmatic-stream-serialization attribute, so the
+// kernel's prologue overlaps the tail of its predecessor.  Only kernels that execute pdl_wait() before their first global-memory
+// access may be launched with pdl = true.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl,
+                                 int cluster, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  unsigned n = 0;
+  if (cluster > 1) {
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = (unsigned)cluster;
+    attr[n].val.clusterDim.y = 1;
+    attr[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  if (pdl && pdl_enabled()) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = n;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 #define V3A_CUDA_OK(expr)                                                                             \
   do {                                                                                                \
     cudaError_t _e = (expr);                                                                          \

@@ -1,0 +1,503 @@
+// Voxelised Gaussian fusion on the device (HBM-bound integer / index work, no tensor cores):
+//   replaces EncoderAnySplat.voxelizaton_with_fusion  (AS/model/encoder/anysplat.py:298-335, called from
+//   models/anysplat_stitched.py:419-440 when cfg.voxelize is set -- the released AnySplat configs set it, voxel_size 0.002)
+//
+//   voxel = round_half_even(p / voxel_size) as int32 per axis                       (anysplat.py:304)
+//   unique voxels in lexicographic (x, y, z) order, inverse index, counts           (torch.unique(dim=0), :305-307)
+//   per voxel: w_i = exp(conf_i - max conf) / (sum_j exp(conf_j - max conf) + 1e-6) (:313-319)
+//              voxel_pts = sum_i w_i p_i ;  voxel_feats = sum_i w_i f_i             (:322-333)
+//
+// Pipeline (every stage streams its arrays once, coalesced; nothing returns to the host):
+//   1. voxel_range_kernel      min / max voxel coordinate per axis                              (reads pts)
+//   2. voxel_key_kernel        order-preserving 64-bit key: the three offset coordinates packed with just the bits their
+//                              ranges need (x most significant), value = point index            (reads pts)
+//   3. LSD radix sort, 8-bit digits, only ceil(bits / 8) passes execute (later launches exit at once): per pass a
+//      per-block digit histogram, one exclusive scan over the digit-major (digit, block) table, and a STABLE scatter
+//      (warp-private digit counters + match.any ranking), so members of a voxel stay in point order
+//   4. segment heads -> voxel ids (block partials + scan), inverse / counts / segment starts
+//   5. voxel_reduce_kernel     one warp per voxel: softmax weights over the members' confidences, then the 3 + C weighted
+//                              sums in member (= point) order; lanes own output channels, member rows are read coalesced
+#include <limits.h>
+
+#include "common.cuh"
+#include "host_util.cuh"
+
+namespace v3a {
+
+namespace {
+
+constexpr int kSortThreads = 256;
+constexpr int kSortItems = 16;                          // keys per thread
+constexpr int kSortTile = kSortThreads * kSortItems;    // 4096 keys per block
+constexpr int kScanTile = 2048;                         // items per block of the segment-head scan (256 threads x 8)
+
+struct VoxelHeader {   // lives at the start of the workspace
+  int mn[3], mx[3];
+  int bits[3];         // bits per axis
+  int total_bits;
+  int npasses;         // radix passes that execute
+  int n_voxels;
+  int error;           // 1: coordinate ranges need more than 64 key bits
+};
+
+__device__ __forceinline__ int voxel_coord(float p, float voxel_size) {
+  // (p / voxel_size).round().int(): IEEE division, round half to even, then float -> int32 (saturating, NaN -> 0)
+  return __float2int_rz(rintf(__fdiv_rn(p, voxel_size)));
+}
+
+__global__ void voxel_init_kernel(VoxelHeader* h) {
+  if (threadIdx.x < 3) {
+    h->mn[threadIdx.x] = INT_MAX;
+    h->mx[threadIdx.x] = INT_MIN;
+  }
+  if (threadIdx.x == 0) {
+    h->n_voxels = 0;
+    h->error = 0;
+  }
+}
+
+__global__ void __launch_bounds__(256) voxel_range_kernel(const float* __restrict__ pts, long long N, float voxel_size, VoxelHeader* h) {
+  int mn[3] = {INT_MAX, INT_MAX, INT_MAX}, mx[3] = {INT_MIN, INT_MIN, INT_MIN};
+  // 3 N floats, read flat and coalesced; element e belongs to axis e % 3
+  const long long total = 3 * N;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int c = voxel_coord(pts[e], voxel_size);
+    const int a = (int)(e % 3);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      if (a == k) { mn[k] = min(mn[k], c); mx[k] = max(mx[k], c); }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    mn[k] = __reduce_min_sync(0xffffffffu, mn[k]);
+    mx[k] = __reduce_max_sync(0xffffffffu, mx[k]);
+  }
+  if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      if (mn[k] != INT_MAX) atomicMin(&h->mn[k], mn[k]);
+      if (mx[k] != INT_MIN) atomicMax(&h->mx[k], mx[k]);
+    }
+  }
+}
+
+__global__ void voxel_bits_kernel(VoxelHeader* h) {
+  if (threadIdx.x == 0) {
+    int total = 0;
+    for (int k = 0; k < 3; ++k) {
+      const unsigned long long range = (unsigned long long)((long long)h->mx[k] - (long long)h->mn[k]);
+      const int b = range == 0 ? 0 : 64 - __clzll(range);
+      h->bits[k] = b;
+      total += b;
+    }
+    h->total_bits = total;
+    h->error = total > 64 ? 1 : 0;
+    h->npasses = total > 64 ? 0 : (total + 7) / 8;
+  }
+}
+
+__global__ void __launch_bounds__(256) voxel_key_kernel(const float* __restrict__ pts, long long N, float voxel_size, const VoxelHeader* __restrict__ h,
+                                                        unsigned long long* __restrict__ keys, unsigned* __restrict__ vals) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const int by = h->bits[1], bz = h->bits[2];
+  const unsigned long long x = (unsigned long long)((long long)voxel_coord(pts[3 * i + 0], voxel_size) - h->mn[0]);
+  const unsigned long long y = (unsigned long long)((long long)voxel_coord(pts[3 * i + 1], voxel_size) - h->mn[1]);
+  const unsigned long long z = (unsigned long long)((long long)voxel_coord(pts[3 * i + 2], voxel_size) - h->mn[2]);
+  // shifts of 64 are undefined: by + bz <= 64 always, and x == 0 whenever bits[0] == 0
+  const int sxy = by + bz;
+  unsigned long long key = z;
+  if (bz < 64) key |= y << bz;
+  if (sxy < 64) key |= x << sxy;
+  keys[i] = key;
+  vals[i] = (unsigned)i;
+}
+
+// ------------------------------------------------------------------------------------------------
+// radix sort pass p (digit = bits [8p, 8p+8)); in/out buffers alternate with the pass index
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kSortThreads) radix_hist_kernel(const unsigned long long* __restrict__ keys_a, const unsigned long long* __restrict__ keys_b,
+                                                                  long long N, int pass, const VoxelHeader* __restrict__ h, unsigned* __restrict__ block_hist,
+                                                                  int nblocks) {
+  if (pass >= h->npasses) return;
+  const unsigned long long* keys = (pass & 1) ? keys_b : keys_a;
+  __shared__ unsigned cnt[256];
+  cnt[threadIdx.x] = 0;
+  __syncthreads();
+  const long long base = (long long)blockIdx.x * kSortTile;
+  const int shift = pass * 8;
+#pragma unroll 4
+  for (int k = 0; k < kSortItems; ++k) {
+    const long long i = base + k * kSortThreads + threadIdx.x;
+    if (i < N) atomicAdd(&cnt[(unsigned)(keys[i] >> shift) & 255u], 1u);
+  }
+  __syncthreads();
+  block_hist[(long long)threadIdx.x * nblocks + blockIdx.x] = cnt[threadIdx.x];
+}
+
+// exclusive scan of `n` counters in place (one block; n = 256 * nblocks)
+__global__ void __launch_bounds__(1024) radix_scan_kernel(unsigned* __restrict__ data, long long n, int pass, const VoxelHeader* __restrict__ h) {
+  if (pass >= h->npasses) return;
+  __shared__ unsigned warp_tot[32];
+  __shared__ unsigned carry_s;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  constexpr int PER = 8;
+  for (long long base = 0; base < n; base += 1024 * PER) {
+    unsigned v[PER];
+    unsigned s = 0;
+    const long long i0 = base + (long long)threadIdx.x * PER;
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+      v[k] = (i0 + k < n) ? data[i0 + k] : 0u;
+      s += v[k];
+    }
+    unsigned incl = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) warp_tot[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+      unsigned w = warp_tot[lane];
+      unsigned wi = w;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned t = __shfl_up_sync(0xffffffffu, wi, o);
+        if (lane >= o) wi += t;
+      }
+      warp_tot[lane] = wi - w;  // exclusive warp offsets
+    }
+    __syncthreads();
+    unsigned run = carry_s + warp_tot[wid] + (incl - s);
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+      if (i0 + k < n) data[i0 + k] = run;
+      run += v[k];
+    }
+    __syncthreads();
+    if (threadIdx.x == 1023) carry_s = run;  // last thread's running value = carry + chunk total
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(kSortThreads) radix_scatter_kernel(const unsigned long long* __restrict__ keys_a, unsigned long long* __restrict__ keys_b_,
+                                                                     const unsigned* __restrict__ vals_a, unsigned* __restrict__ vals_b_, long long N, int pass,
+                                                                     const VoxelHeader* __restrict__ h, const unsigned* __restrict__ block_off, int nblocks) {
+  if (pass >= h->npasses) return;
+  // pass parity selects the direction: even a -> b, odd b -> a
+  const unsigned long long* kin = (pass & 1) ? keys_b_ : keys_a;
+  unsigned long long* kout = (pass & 1) ? const_cast<unsigned long long*>(keys_a) : keys_b_;
+  const unsigned* vin = (pass & 1) ? vals_b_ : vals_a;
+  unsigned* vout = (pass & 1) ? const_cast<unsigned*>(vals_a) : vals_b_;
+  constexpr int NW = kSortThreads / 32;
+  __shared__ unsigned wcnt[NW][256];   // per-warp digit counters, then per-warp exclusive bases
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (int d = lane; d < 256; d += 32) wcnt[wid][d] = 0;
+  __syncwarp();
+  // warp w owns the contiguous slice [w * 512, (w + 1) * 512) of the block tile; 16 rounds of 32 keys in order
+  const long long wbase = (long long)blockIdx.x * kSortTile + (long long)wid * (kSortTile / NW);
+  const int shift = pass * 8;
+  unsigned long long key[kSortItems];
+  unsigned rank[kSortItems];
+#pragma unroll
+  for (int r = 0; r < kSortItems; ++r) {
+    const long long i = wbase + r * 32 + lane;
+    const bool ok = i < N;
+    key[r] = ok ? kin[i] : ~0ull;
+    const unsigned d = (unsigned)(key[r] >> shift) & 255u;
+    const unsigned act = __ballot_sync(0xffffffffu, ok);
+    unsigned peers = __match_any_sync(0xffffffffu, ok ? d : 256u + (unsigned)lane) & act;
+    const unsigned before = __popc(peers & ((1u << lane) - 1u));
+    unsigned basev = 0;
+    const int leader = __ffs(peers) - 1;
+    if (ok && lane == leader) {
+      basev = wcnt[wid][d];
+      wcnt[wid][d] = basev + __popc(peers);
+    }
+    basev = __shfl_sync(0xffffffffu, basev, leader < 0 ? 0 : leader);
+    rank[r] = basev + before;
+    __syncwarp();
+  }
+  __syncthreads();
+  // per digit: exclusive scan over the warps, plus the block's global offset
+  {
+    const int d = threadIdx.x;  // kSortThreads == 256 digits
+    unsigned run = block_off[(long long)d * nblocks + blockIdx.x];
+#pragma unroll
+    for (int w = 0; w < NW; ++w) {
+      const unsigned c = wcnt[w][d];
+      wcnt[w][d] = run;
+      run += c;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < kSortItems; ++r) {
+    const long long i = wbase + r * 32 + lane;
+    if (i < N) {
+      const unsigned d = (unsigned)(key[r] >> shift) & 255u;
+      const unsigned pos = wcnt[wid][d] + rank[r];
+      kout[pos] = key[r];
+      vout[pos] = vin[i];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// segment heads -> voxel ids
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ const unsigned long long* sorted_keys(const VoxelHeader* h, const unsigned long long* a, const unsigned long long* b) {
+  return (h->npasses & 1) ? b : a;
+}
+__device__ __forceinline__ const unsigned* sorted_vals(const VoxelHeader* h, const unsigned* a, const unsigned* b) { return (h->npasses & 1) ? b : a; }
+
+__global__ void __launch_bounds__(256) seg_count_kernel(const unsigned long long* __restrict__ keys_a, const unsigned long long* __restrict__ keys_b, long long N,
+                                                        const VoxelHeader* __restrict__ h, unsigned* __restrict__ partial) {
+  const unsigned long long* keys = sorted_keys(h, keys_a, keys_b);
+  const long long base = (long long)blockIdx.x * kScanTile;
+  unsigned c = 0;
+#pragma unroll
+  for (int k = 0; k < kScanTile / 256; ++k) {
+    const long long i = base + k * 256 + threadIdx.x;
+    if (i < N) c += (i == 0 || keys[i] != keys[i - 1]) ? 1u : 0u;
+  }
+  __shared__ unsigned ws[8];
+  c = __reduce_add_sync(0xffffffffu, c);
+  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned t = 0;
+    for (int w = 0; w < 8; ++w) t += ws[w];
+    partial[blockIdx.x] = t;
+  }
+}
+
+// one block: exclusive scan of the block partials; the total is the number of voxels
+__global__ void __launch_bounds__(1024) seg_scan_partials_kernel(unsigned* __restrict__ partial, int n, VoxelHeader* h, long long* __restrict__ n_voxels_out,
+                                                                 unsigned* __restrict__ seg_start, long long N) {
+  __shared__ unsigned warp_tot[32];
+  __shared__ unsigned carry_s;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  for (int base = 0; base < n; base += 1024) {
+    const int i = base + threadIdx.x;
+    const unsigned v = i < n ? partial[i] : 0u;
+    unsigned incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) warp_tot[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+      const unsigned w = warp_tot[lane];
+      unsigned wi = w;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned t = __shfl_up_sync(0xffffffffu, wi, o);
+        if (lane >= o) wi += t;
+      }
+      warp_tot[lane] = wi - w;
+    }
+    __syncthreads();
+    const unsigned excl = carry_s + warp_tot[wid] + incl - v;
+    if (i < n) partial[i] = excl;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry_s = excl + v;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const unsigned nv = h->error ? 0u : carry_s;
+    h->n_voxels = (int)nv;
+    if (n_voxels_out) *n_voxels_out = h->error ? -1ll : (long long)nv;
+    seg_start[nv] = (unsigned)N;  // sentinel: end of the last segment
+  }
+}
+
+__global__ void __launch_bounds__(256) seg_assign_kernel(const unsigned long long* __restrict__ keys_a, const unsigned long long* __restrict__ keys_b,
+                                                         const unsigned* __restrict__ vals_a, const unsigned* __restrict__ vals_b, long long N,
+                                                         const VoxelHeader* __restrict__ h, const unsigned* __restrict__ partial, unsigned* __restrict__ seg_start,
+                                                         int* __restrict__ inverse) {
+  const unsigned long long* keys = sorted_keys(h, keys_a, keys_b);
+  const unsigned* vals = sorted_vals(h, vals_a, vals_b);
+  // thread t owns 8 consecutive sorted positions
+  const long long i0 = (long long)blockIdx.x * kScanTile + (long long)threadIdx.x * 8;
+  unsigned head[8];
+  unsigned s = 0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const long long i = i0 + k;
+    head[k] = (i < N && (i == 0 || keys[i] != keys[i - 1])) ? 1u : 0u;
+    s += head[k];
+  }
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  unsigned incl = s;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  __shared__ unsigned ws[8];
+  if (lane == 31) ws[wid] = incl;
+  __syncthreads();
+  unsigned woff = 0;
+  for (int w = 0; w < wid; ++w) woff += ws[w];
+  unsigned run = partial[blockIdx.x] + woff + incl - s;  // heads before position i0
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const long long i = i0 + k;
+    if (i < N) {
+      run += head[k];
+      const unsigned seg = run - 1u;
+      if (head[k]) seg_start[seg] = (unsigned)i;
+      if (inverse) inverse[vals[i]] = (int)seg;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-voxel softmax-weighted fusion: one warp per voxel
+// ------------------------------------------------------------------------------------------------
+template <int NCH>  // channel rounds: 3 + C <= 32 * NCH
+__global__ void __launch_bounds__(256) voxel_reduce_kernel(const float* __restrict__ pts, const float* __restrict__ feats, long long ld_feats, int C,
+                                                           const float* __restrict__ conf, long long conf_stride, const unsigned* __restrict__ vals_a,
+                                                           const unsigned* __restrict__ vals_b, const VoxelHeader* __restrict__ h,
+                                                           const unsigned* __restrict__ seg_start, float* __restrict__ voxel_pts,
+                                                           float* __restrict__ voxel_feats, int* __restrict__ counts) {
+  const unsigned* vals = sorted_vals(h, vals_a, vals_b);
+  const int nv = h->n_voxels;
+  const int lane = threadIdx.x & 31;
+  for (long long v = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); v < nv; v += (long long)gridDim.x * 8) {
+    const unsigned s0 = seg_start[v], s1 = seg_start[v + 1];
+    const unsigned n = s1 - s0;
+    if (counts && lane == 0) counts[v] = (int)n;
+    // softmax statistics over the members (lanes stride over members)
+    float m = -INFINITY;
+    for (unsigned j = s0 + lane; j < s1; j += 32) m = fmaxf(m, conf[(long long)vals[j] * conf_stride]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    float den;
+    if (n == 1) {
+      den = 1.0f;  // exp(0)
+    } else {
+      float sacc = 0.f;
+      for (unsigned j = s0 + lane; j < s1; j += 32) sacc += expf(conf[(long long)vals[j] * conf_stride] - m);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, o);
+      den = sacc;
+    }
+    den += 1e-6f;
+    // weighted sums in member order: lane l owns output channels l, l + 32, ... (0..2 = xyz, 3.. = features)
+    float acc[NCH];
+#pragma unroll
+    for (int r = 0; r < NCH; ++r) acc[r] = 0.f;
+    for (unsigned j = s0; j < s1; ++j) {
+      const long long idx = vals[j];
+      const float w = __fdiv_rn(expf(conf[idx * conf_stride] - m), den);
+#pragma unroll
+      for (int r = 0; r < NCH; ++r) {
+        const int c = lane + 32 * r;
+        if (c < 3 + C) {
+          const float x = c < 3 ? pts[idx * 3 + c] : feats[idx * ld_feats + (c - 3)];
+          acc[r] = __fadd_rn(acc[r], __fmul_rn(x, w));
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < NCH; ++r) {
+      const int c = lane + 32 * r;
+      if (c < 3) voxel_pts[v * 3 + c] = acc[r];
+      else if (c < 3 + C) voxel_feats[v * C + (c - 3)] = acc[r];
+    }
+  }
+}
+
+inline long long align256(long long x) { return (x + 255) & ~255ll; }
+
+struct VoxelWorkspace {
+  VoxelHeader* header;
+  unsigned long long *keys_a, *keys_b;
+  unsigned *vals_a, *vals_b;
+  unsigned* block_hist;
+  unsigned* partial;
+  unsigned* seg_start;
+  long long bytes;
+  int nblocks, nscan;
+};
+
+VoxelWorkspace carve(void* ws, long long N) {
+  VoxelWorkspace w;
+  w.nblocks = (int)((N + kSortTile - 1) / kSortTile);
+  w.nscan = (int)((N + kScanTile - 1) / kScanTile);
+  char* p = reinterpret_cast<char*>(ws);
+  long long off = 0;
+  auto take = [&](long long bytes) { char* q = p ? p + off : nullptr; off += align256(bytes); return q; };
+  w.header = reinterpret_cast<VoxelHeader*>(take(sizeof(VoxelHeader)));
+  w.keys_a = reinterpret_cast<unsigned long long*>(take(8 * N));
+  w.keys_b = reinterpret_cast<unsigned long long*>(take(8 * N));
+  w.vals_a = reinterpret_cast<unsigned*>(take(4 * N));
+  w.vals_b = reinterpret_cast<unsigned*>(take(4 * N));
+  w.block_hist = reinterpret_cast<unsigned*>(take(4ll * 256 * w.nblocks));
+  w.partial = reinterpret_cast<unsigned*>(take(4ll * w.nscan));
+  w.seg_start = reinterpret_cast<unsigned*>(take(4 * (N + 1)));
+  w.bytes = off;
+  return w;
+}
+
+}  // namespace
+
+long long voxel_fusion_workspace_bytes(long long N) { return N > 0 ? carve(nullptr, N).bytes : 0; }
+
+int voxel_fusion_entry(const float* pts, const float* feats, long long ld_feats, long long C, const float* conf, long long conf_stride, long long N,
+                       float voxel_size, float* voxel_pts, float* voxel_feats, int* inverse, int* counts, long long* n_voxels, void* workspace,
+                       long long workspace_bytes, cudaStream_t st) {
+  V3A_REQUIRE(pts && feats && conf && voxel_pts && voxel_feats && n_voxels && workspace, VIST3A_ERR_INVALID, "voxel_fusion: null pointer");
+  V3A_REQUIRE(N > 0 && N < (1ll << 31) - kSortTile, VIST3A_ERR_INVALID, "voxel_fusion: N must be in (0, 2^31) (got %lld)", N);
+  V3A_REQUIRE(C > 0 && C + 3 <= 128 && ld_feats >= C && conf_stride >= 1, VIST3A_ERR_INVALID, "voxel_fusion: feature dim must be in [1, 125] (got %lld)", C);
+  V3A_REQUIRE(voxel_size > 0.f, VIST3A_ERR_INVALID, "voxel_fusion: voxel_size must be positive");
+  V3A_REQUIRE(((uintptr_t)workspace & 255) == 0, VIST3A_ERR_INVALID, "voxel_fusion: workspace must be 256-byte aligned");
+  const VoxelWorkspace w = carve(workspace, N);
+  V3A_REQUIRE(workspace_bytes >= w.bytes, VIST3A_ERR_INVALID, "voxel_fusion: workspace of %lld bytes needed, %lld given", w.bytes, workspace_bytes);
+  int rc = check_arch();
+  if (rc) return rc;
+  const int sms = num_sms();
+  long long launches = 0;
+  voxel_init_kernel<<<1, 32, 0, st>>>(w.header);
+  voxel_range_kernel<<<(unsigned)min((long long)sms * 8, (3 * N + 255) / 256), 256, 0, st>>>(pts, N, voxel_size, w.header);
+  voxel_bits_kernel<<<1, 32, 0, st>>>(w.header);
+  voxel_key_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(pts, N, voxel_size, w.header, w.keys_a, w.vals_a);
+  launches += 4;
+  for (int pass = 0; pass < 8; ++pass) {  // passes >= ceil(bits / 8) return immediately (device-side count: no host round trip)
+    radix_hist_kernel<<<w.nblocks, kSortThreads, 0, st>>>(w.keys_a, w.keys_b, N, pass, w.header, w.block_hist, w.nblocks);
+    radix_scan_kernel<<<1, 1024, 0, st>>>(w.block_hist, 256ll * w.nblocks, pass, w.header);
+    radix_scatter_kernel<<<w.nblocks, kSortThreads, 0, st>>>(w.keys_a, w.keys_b, w.vals_a, w.vals_b, N, pass, w.header, w.block_hist, w.nblocks);
+    launches += 3;
+  }
+  seg_count_kernel<<<w.nscan, 256, 0, st>>>(w.keys_a, w.keys_b, N, w.header, w.partial);
+  seg_scan_partials_kernel<<<1, 1024, 0, st>>>(w.partial, w.nscan, w.header, n_voxels, w.seg_start, N);
+  seg_assign_kernel<<<w.nscan, 256, 0, st>>>(w.keys_a, w.keys_b, w.vals_a, w.vals_b, N, w.header, w.partial, w.seg_start, inverse);
+  launches += 3;
+  const unsigned rgrid = (unsigned)min((N + 7) / 8, (long long)sms * 32);
+  const int nch = (int)((3 + C + 31) / 32);
+#define V3A_REDUCE(NCH_)                                                                                                                   \
+  voxel_reduce_kernel<NCH_><<<rgrid, 256, 0, st>>>(pts, feats, ld_feats, (int)C, conf, conf_stride, w.vals_a, w.vals_b, w.header, w.seg_start, \
+                                                   voxel_pts, voxel_feats, counts)
+  if (nch == 1) V3A_REDUCE(1);
+  else if (nch == 2) V3A_REDUCE(2);
+  else if (nch == 3) V3A_REDUCE(3);
+  else V3A_REDUCE(4);
+#undef V3A_REDUCE
+  launches += 1;
+  V3A_CUDA_OK(cudaGetLastError());
+  launch_counter().fetch_add(launches);
+  return VIST3A_OK;
+}
+
+}  // namespace v3a

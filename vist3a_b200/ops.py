@@ -448,6 +448,57 @@ def gaussian_epilogue(depth_feat: torch.Tensor, depth_w: torch.Tensor, depth_b: 
     return o
 
 
+def gaussian_adapter(pts: torch.Tensor, feats: torch.Tensor, sh_mask: torch.Tensor):
+    """Gaussian adapter on given positions (voxelize=True branch); pts [P,3], feats [P, >= 8 + 3 d_sh] rows; see vist3a_gaussian_adapter."""
+    _need_cuda(pts, feats, sh_mask)
+    P = pts.shape[0]
+    d_sh = sh_mask.shape[0]
+    dev, f32 = pts.device, torch.float32
+    if pts.dtype != f32 or feats.dtype != f32 or not pts.is_contiguous() or feats.stride(1) != 1:
+        raise ValueError("gaussian_adapter: fp32 contiguous points and unit-stride fp32 feature rows expected")
+    o = dict(means=torch.empty((P, 3), dtype=f32, device=dev), scales=torch.empty((P, 3), dtype=f32, device=dev),
+             rotations=torch.empty((P, 4), dtype=f32, device=dev), opacities=torch.empty((P,), dtype=f32, device=dev),
+             harmonics=torch.empty((P, 3, d_sh), dtype=f32, device=dev), covariances=torch.empty((P, 3, 3), dtype=f32, device=dev))
+    if P > 0:
+        L.check(L.load().vist3a_gaussian_adapter(pts.data_ptr(), feats.data_ptr(), feats.stride(0), sh_mask.data_ptr(), d_sh, P,
+                                                 o["means"].data_ptr(), o["scales"].data_ptr(), o["rotations"].data_ptr(),
+                                                 o["opacities"].data_ptr(), o["harmonics"].data_ptr(), o["covariances"].data_ptr(), _stream()))
+    return o
+
+
+def voxel_fusion(pts: torch.Tensor, feats: torch.Tensor, conf: torch.Tensor, voxel_size: float, *, feat_dim: Optional[int] = None,
+                 want_index: bool = False):
+    """Voxelised fusion (see vist3a_voxel_fusion): pts [N,3] fp32 contiguous, feats [N, >= feat_dim] unit-stride fp32 rows, conf a
+    1-D fp32 view of N values (may be a strided column of the feature rows).  Returns dict(pts [M,3], feats [M,C], n_voxels = M
+    [, inverse [N] int32, counts [M] int32]); reading M synchronises the stream (the output size is data dependent, as
+    torch.unique's is in the reference)."""
+    _need_cuda(pts, feats, conf)
+    N = pts.shape[0]
+    Cc = int(feat_dim if feat_dim is not None else feats.shape[1])
+    f32, dev = torch.float32, pts.device
+    if pts.dtype != f32 or feats.dtype != f32 or conf.dtype != f32 or not pts.is_contiguous() or feats.stride(1) != 1 or conf.dim() != 1:
+        raise ValueError("voxel_fusion: fp32 contiguous points, unit-stride fp32 feature rows and a 1-D fp32 confidence view expected")
+    if feats.shape[0] != N or conf.shape[0] != N:
+        raise ValueError("voxel_fusion: pts / feats / conf disagree on the number of points")
+    lib = L.load()
+    ws_bytes = int(lib.vist3a_voxel_fusion_workspace_bytes(N))
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+    vp = torch.empty((N, 3), dtype=f32, device=dev)
+    vf = torch.empty((N, Cc), dtype=f32, device=dev)
+    inv = torch.empty((N,), dtype=torch.int32, device=dev) if want_index else None
+    cnt = torch.empty((N,), dtype=torch.int32, device=dev) if want_index else None
+    nv = torch.zeros((1,), dtype=torch.int64, device=dev)
+    L.check(lib.vist3a_voxel_fusion(pts.data_ptr(), feats.data_ptr(), feats.stride(0), Cc, conf.data_ptr(), conf.stride(0), N, float(voxel_size),
+                                    vp.data_ptr(), vf.data_ptr(), _ptr(inv), _ptr(cnt), nv.data_ptr(), ws.data_ptr(), ws_bytes, _stream()))
+    M = int(nv.item())
+    if M < 0:
+        raise L.Vist3aError(L.ERR_UNSUPPORTED, "voxel_fusion: voxel coordinate ranges need more than 64 key bits")
+    out = dict(pts=vp[:M], feats=vf[:M], n_voxels=M)
+    if want_index:
+        out["inverse"], out["counts"] = inv, cnt[:M]
+    return out
+
+
 # ------------------------------------------------------------------------------------------------
 # per-launch device timing (bench.py roofline): CUDA events recorded on the launching stream around
 # every call of the wrapped op, with its algorithmic FLOPs / bytes.
@@ -502,7 +553,11 @@ class OpTimer:
                 return 0.0, sum(t.numel() * t.element_size() for t in ts), tag
             return f
 
-        table = {"gemm": gemm_cost, "fmha": fmha_cost, "layernorm": io_cost("layernorm"),
+        def voxel_cost(out, args, kw):  # algorithmic: every point row read once, every voxel row written once
+            n, m, c = args[0].shape[0], out["n_voxels"], out["feats"].shape[1]
+            return 0.0, 4.0 * (n * (3 + c + 1) + m * (3 + c)), "voxel_fusion"
+
+        table = {"voxel_fusion": voxel_cost, "gaussian_adapter": io_cost("gaussian_adapter"), "gemm": gemm_cost, "fmha": fmha_cost, "layernorm": io_cost("layernorm"),
                  "rmsnorm_rope_": io_cost("rmsnorm_rope"), "row_rinv": io_cost("rmsnorm_rope"), "modulation": io_cost("small"), "skinny_linear": io_cost("small"),
                  "timestep_features": io_cost("small"), "patchify": io_cost("small"), "unpatchify": io_cost("small"),
                  "cfg_combine": io_cost("small"), "axpby_n": io_cost("small"), "im2col_stitch": io_cost("im2col"),

@@ -3,7 +3,8 @@
 trilinear T-upsample + stitching Conv3d (models/stitching_layer_builder.py:21-42) feeding
 `AnySplatStitched.forward` (models/anysplat_stitched.py:167-525): 22 DINOv2 blocks, 24 x (frame,
 global) alternating-attention blocks, camera head, DPT depth head, DPT Gaussian head and the
-per-pixel Gaussian adapter (`voxelize=False`, `render_conf=False`, `opacity_conf=False`).
+per-pixel Gaussian adapter (`render_conf=False`, `opacity_conf=False`); `DecoderConfig.voxelize` selects the voxelised-fusion
+branch (models/anysplat_stitched.py:419-455 -> AS/model/encoder/anysplat.py:298-335) the released AnySplat configs enable.
 
 Weights come from a state dict with the REFERENCE's key names (`stitching_layer.*`,
 `stitched_3d_model.encoder.*`), so `anysplat_stitched.pth` + the AnySplat checkpoint load unchanged.
@@ -78,6 +79,8 @@ class DecoderConfig:
     latent_channels: int = 16
     inter_layers: Tuple[int, ...] = (4, 11, 17, 23)
     resolution: int = 512  # video resolution; the VAE latent grid is resolution / 8
+    voxelize: bool = False   # EncoderAnySplatCfg.voxelize (AS/model/encoder/anysplat.py:125; true in config/experiment/*.yaml)
+    voxel_size: float = 0.002  # config/experiment/dl3dv.yaml:20
 
     @property
     def d_sh(self):
@@ -222,6 +225,8 @@ class StitchVAE3DB200(torch.nn.Module):
         self.device = torch.device(device)
         self.w: Dict[str, torch.Tensor] = {}
         self._tables = {}
+        self.keep_voxel_inputs = False
+        self.voxel_inputs = None
         if config.embed_dim // config.num_heads != 64:
             raise NotImplementedError("the QK-norm + 2-D RoPE kernel implements the aggregator's 64-wide heads")
 
@@ -589,6 +594,25 @@ class StitchVAE3DB200(torch.nn.Module):
         # --- fused depth activation + unprojection + Gaussian adapter
         o = ops.gaussian_epilogue(dfeat.view(BV * H * W, -1), w["dh.oc2b.w"], self._depth_b, raw, cams["extr"], cams["intr"], w["sh_mask"], BV, H, W)
         N = V * H * W
+        if cfg.voxelize:
+            # voxelised fusion per batch element, padded to the largest voxel count (anysplat_stitched.py:419-455), then the adapter
+            Cr = cfg.raw_gs_dim
+            rawb, ptsb = raw.view(B, N, -1), o["means"].view(B, N, 3)
+            fused = [ops.voxel_fusion(ptsb[b], rawb[b], rawb[b][:, Cr], cfg.voxel_size, feat_dim=Cr) for b in range(B)]
+            if self.keep_voxel_inputs:  # tests: the fusion stage is checked against the oracle on exactly these inputs
+                self.voxel_inputs = dict(pts=ptsb.clone(), raw=rawb.clone(), counts=[f["n_voxels"] for f in fused])
+            N = max(f["n_voxels"] for f in fused)
+            if B == 1:
+                vp, vf = fused[0]["pts"], fused[0]["feats"]
+            else:
+                vp = torch.full((B, N, 3), -1e4, dtype=torch.float32, device=dev)
+                vf = torch.full((B, N, Cr), -1e10, dtype=torch.float32, device=dev)
+                for b, f in enumerate(fused):
+                    vp[b, :f["n_voxels"]] = f["pts"]
+                    vf[b, :f["n_voxels"]] = f["feats"]
+            depth_out = o["depth"]
+            o = ops.gaussian_adapter(vp.reshape(B * N, 3), vf.reshape(B * N, Cr), w["sh_mask"]) | dict(depth=depth_out, scene_sum=o["scene_sum"])
+            del fused, vp, vf
         gauss = Gaussians(means=o["means"].view(B, N, 3), covariances=o["covariances"].view(B, N, 3, 3),
                           harmonics=o["harmonics"].view(B, N, 3, cfg.d_sh), opacities=o["opacities"].view(B, N),
                           scales=o["scales"].view(B, N, 3), rotations=o["rotations"].view(B, N, 4))
