@@ -322,7 +322,9 @@ int vist3a_gaussian_adapter(const float* pts, const float* feats, int64_t ld_fea
  * Voxelised Gaussian fusion (integer / index work, HBM bound; no tensor cores)
  * replaces: EncoderAnySplat.voxelizaton_with_fusion (AS/model/encoder/anysplat.py:298-335), called per batch element from
  *   models/anysplat_stitched.py:419-440 when cfg.voxelize is set (released AnySplat configs: voxelize true, voxel_size 0.002):
- *     voxel   = round_half_even(pts / voxel_size) -> int32 per axis
+ *     voxel   = round_half_even(pts / voxel_size) -> int32 per axis  (IEEE fp32 division, as the reference's CPU path computes it;
+ *               torch's CUDA kernel for tensor / python-scalar multiplies by the rounded reciprocal, which differs by one ulp for a
+ *               few points per million at voxel_size 0.002 -- cell membership of those border points follows the CPU result)
  *     unique voxels in lexicographic (x, y, z) order (torch.unique(dim=0)), inverse index, counts
  *     w_i     = exp(conf_i - max_voxel conf) / (sum_voxel exp(conf - max) + 1e-6)
  *     voxel_pts = sum_i w_i pts_i ; voxel_feats = sum_i w_i feats_i      (summed in point order: the sort is stable)

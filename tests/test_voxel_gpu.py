@@ -102,7 +102,9 @@ def test_voxel_fusion_full_size_properties():
     rows[:, c] = 0.0  # equal confidences: every voxel is the plain mean of its members
     o = ops.voxel_fusion(pts, rows, rows[:, c], vs, feat_dim=c, want_index=True)
     m = o["n_voxels"]
-    cells = (pts / vs).round().int()
+    # IEEE division as on the reference's CPU path (the oracle): torch's CUDA `tensor / python_scalar` multiplies by the rounded
+    # reciprocal instead, which moves a handful of points per million across a cell border
+    cells = torch.div(pts, torch.full_like(pts, vs)).round().int()
     uniq, inv, cnt = torch.unique(cells, dim=0, return_inverse=True, return_counts=True)
     assert m == uniq.shape[0] and 0 < m < n
     assert torch.equal(o["inverse"].long(), inv) and torch.equal(o["counts"].long(), cnt)

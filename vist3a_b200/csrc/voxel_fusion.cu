@@ -58,14 +58,26 @@ __global__ void voxel_init_kernel(VoxelHeader* h) {
 
 __global__ void __launch_bounds__(256) voxel_range_kernel(const float* __restrict__ pts, long long N, float voxel_size, VoxelHeader* h) {
   int mn[3] = {INT_MAX, INT_MAX, INT_MAX}, mx[3] = {INT_MIN, INT_MIN, INT_MIN};
-  // 3 N floats, read flat and coalesced; element e belongs to axis e % 3
-  const long long total = 3 * N;
-  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
-    const int c = voxel_coord(pts[e], voxel_size);
-    const int a = (int)(e % 3);
+  // 4 points = 12 floats = three 16-byte loads per thread and iteration
+  const float4* p4 = reinterpret_cast<const float4*>(pts);
+  const long long groups = N / 4;
+  for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += (long long)gridDim.x * blockDim.x) {
+    const float4 a = p4[3 * g], b = p4[3 * g + 1], c = p4[3 * g + 2];
+    const float v[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
+#pragma unroll
+    for (int k = 0; k < 12; ++k) {
+      const int q = voxel_coord(v[k], voxel_size);
+      mn[k % 3] = min(mn[k % 3], q);
+      mx[k % 3] = max(mx[k % 3], q);
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (int)(N - 4 * groups)) {  // up to 3 tail points
+    const long long i = 4 * groups + threadIdx.x;
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-      if (a == k) { mn[k] = min(mn[k], c); mx[k] = max(mx[k], c); }
+      const int q = voxel_coord(pts[3 * i + k], voxel_size);
+      mn[k] = min(mn[k], q);
+      mx[k] = max(mx[k], q);
     }
   }
 #pragma unroll
@@ -136,22 +148,25 @@ __global__ void __launch_bounds__(kSortThreads) radix_hist_kernel(const unsigned
   block_hist[(long long)threadIdx.x * nblocks + blockIdx.x] = cnt[threadIdx.x];
 }
 
-// exclusive scan of `n` counters in place (one block; n = 256 * nblocks)
-__global__ void __launch_bounds__(1024) radix_scan_kernel(unsigned* __restrict__ data, long long n, int pass, const VoxelHeader* __restrict__ h) {
+// Block d scans row d of the digit-major table in place (exclusive, over the sort blocks) and records the digit total; the scatter
+// kernel adds the exclusive scan of the 256 totals (recomputed per block in shared memory: 256 values).
+__global__ void __launch_bounds__(256) radix_scan_kernel(unsigned* __restrict__ data, int nblocks, unsigned* __restrict__ digit_total, int pass,
+                                                         const VoxelHeader* __restrict__ h) {
   if (pass >= h->npasses) return;
-  __shared__ unsigned warp_tot[32];
+  __shared__ unsigned warp_tot[8];
   __shared__ unsigned carry_s;
+  unsigned* row = data + (long long)blockIdx.x * nblocks;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   if (threadIdx.x == 0) carry_s = 0;
   __syncthreads();
-  constexpr int PER = 8;
-  for (long long base = 0; base < n; base += 1024 * PER) {
+  constexpr int PER = 4;
+  for (int base = 0; base < nblocks; base += 256 * PER) {
     unsigned v[PER];
     unsigned s = 0;
-    const long long i0 = base + (long long)threadIdx.x * PER;
+    const int i0 = base + (int)threadIdx.x * PER;
 #pragma unroll
     for (int k = 0; k < PER; ++k) {
-      v[k] = (i0 + k < n) ? data[i0 + k] : 0u;
+      v[k] = (i0 + k < nblocks) ? row[i0 + k] : 0u;
       s += v[k];
     }
     unsigned incl = s;
@@ -162,32 +177,26 @@ __global__ void __launch_bounds__(1024) radix_scan_kernel(unsigned* __restrict__
     }
     if (lane == 31) warp_tot[wid] = incl;
     __syncthreads();
-    if (wid == 0) {
-      unsigned w = warp_tot[lane];
-      unsigned wi = w;
+    unsigned woff = 0;
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const unsigned t = __shfl_up_sync(0xffffffffu, wi, o);
-        if (lane >= o) wi += t;
-      }
-      warp_tot[lane] = wi - w;  // exclusive warp offsets
-    }
-    __syncthreads();
-    unsigned run = carry_s + warp_tot[wid] + (incl - s);
+    for (int w = 0; w < 8; ++w) woff += (w < wid) ? warp_tot[w] : 0u;
+    unsigned run = carry_s + woff + (incl - s);
 #pragma unroll
     for (int k = 0; k < PER; ++k) {
-      if (i0 + k < n) data[i0 + k] = run;
+      if (i0 + k < nblocks) row[i0 + k] = run;
       run += v[k];
     }
     __syncthreads();
-    if (threadIdx.x == 1023) carry_s = run;  // last thread's running value = carry + chunk total
+    if (threadIdx.x == 255) carry_s = run;  // carry + chunk total
     __syncthreads();
   }
+  if (threadIdx.x == 0) digit_total[blockIdx.x] = carry_s;
 }
 
 __global__ void __launch_bounds__(kSortThreads) radix_scatter_kernel(const unsigned long long* __restrict__ keys_a, unsigned long long* __restrict__ keys_b_,
                                                                      const unsigned* __restrict__ vals_a, unsigned* __restrict__ vals_b_, long long N, int pass,
-                                                                     const VoxelHeader* __restrict__ h, const unsigned* __restrict__ block_off, int nblocks) {
+                                                                     const VoxelHeader* __restrict__ h, const unsigned* __restrict__ block_off, int nblocks,
+                                                                     const unsigned* __restrict__ digit_total) {
   if (pass >= h->npasses) return;
   // pass parity selects the direction: even a -> b, odd b -> a
   const unsigned long long* kin = (pass & 1) ? keys_b_ : keys_a;
@@ -196,7 +205,24 @@ __global__ void __launch_bounds__(kSortThreads) radix_scatter_kernel(const unsig
   unsigned* vout = (pass & 1) ? const_cast<unsigned*>(vals_a) : vals_b_;
   constexpr int NW = kSortThreads / 32;
   __shared__ unsigned wcnt[NW][256];   // per-warp digit counters, then per-warp exclusive bases
+  __shared__ unsigned dbase[256];      // exclusive scan of the digit totals
+  __shared__ unsigned dwarp[8];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  {
+    const unsigned t = digit_total[threadIdx.x];
+    unsigned incl = t;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned u = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += u;
+    }
+    if (lane == 31) dwarp[wid] = incl;
+    __syncthreads();
+    unsigned woff = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) woff += (w < wid) ? dwarp[w] : 0u;
+    dbase[threadIdx.x] = woff + incl - t;
+  }
   for (int d = lane; d < 256; d += 32) wcnt[wid][d] = 0;
   __syncwarp();
   // warp w owns the contiguous slice [w * 512, (w + 1) * 512) of the block tile; 16 rounds of 32 keys in order
@@ -227,7 +253,7 @@ __global__ void __launch_bounds__(kSortThreads) radix_scatter_kernel(const unsig
   // per digit: exclusive scan over the warps, plus the block's global offset
   {
     const int d = threadIdx.x;  // kSortThreads == 256 digits
-    unsigned run = block_off[(long long)d * nblocks + blockIdx.x];
+    unsigned run = dbase[d] + block_off[(long long)d * nblocks + blockIdx.x];
 #pragma unroll
     for (int w = 0; w < NW; ++w) {
       const unsigned c = wcnt[w][d];
@@ -324,7 +350,7 @@ __global__ void __launch_bounds__(1024) seg_scan_partials_kernel(unsigned* __res
 __global__ void __launch_bounds__(256) seg_assign_kernel(const unsigned long long* __restrict__ keys_a, const unsigned long long* __restrict__ keys_b,
                                                          const unsigned* __restrict__ vals_a, const unsigned* __restrict__ vals_b, long long N,
                                                          const VoxelHeader* __restrict__ h, const unsigned* __restrict__ partial, unsigned* __restrict__ seg_start,
-                                                         int* __restrict__ inverse) {
+                                                         unsigned* __restrict__ seg_of, int* __restrict__ inverse) {
   const unsigned long long* keys = sorted_keys(h, keys_a, keys_b);
   const unsigned* vals = sorted_vals(h, vals_a, vals_b);
   // thread t owns 8 consecutive sorted positions
@@ -357,65 +383,121 @@ __global__ void __launch_bounds__(256) seg_assign_kernel(const unsigned long lon
       run += head[k];
       const unsigned seg = run - 1u;
       if (head[k]) seg_start[seg] = (unsigned)i;
+      seg_of[i] = seg;
       if (inverse) inverse[vals[i]] = (int)seg;
     }
   }
 }
 
 // ------------------------------------------------------------------------------------------------
-// per-voxel softmax-weighted fusion: one warp per voxel
+// per-voxel softmax-weighted fusion.  One warp owns 32 consecutive voxels = one contiguous range of sorted members:
+//   phase 1  lane-per-voxel softmax statistics (max, denominator) in member order; voxels with one member need none
+//   phase 2  the members of the range, 32 at a time: lane-per-member weights, then four members in flight at once -- their rows
+//            (3 + C values, lanes own channels: coalesced 128-byte reads) are fetched before any is accumulated, so a warp keeps
+//            twelve independent loads outstanding instead of one dependent chain per voxel; the accumulator is flushed
+//            (coalesced row store) whenever the member's voxel changes.  Sums run in member (= point) order.
 // ------------------------------------------------------------------------------------------------
 template <int NCH>  // channel rounds: 3 + C <= 32 * NCH
 __global__ void __launch_bounds__(256) voxel_reduce_kernel(const float* __restrict__ pts, const float* __restrict__ feats, long long ld_feats, int C,
                                                            const float* __restrict__ conf, long long conf_stride, const unsigned* __restrict__ vals_a,
                                                            const unsigned* __restrict__ vals_b, const VoxelHeader* __restrict__ h,
-                                                           const unsigned* __restrict__ seg_start, float* __restrict__ voxel_pts,
-                                                           float* __restrict__ voxel_feats, int* __restrict__ counts) {
+                                                           const unsigned* __restrict__ seg_start, const unsigned* __restrict__ seg_of,
+                                                           float* __restrict__ voxel_pts, float* __restrict__ voxel_feats, int* __restrict__ counts) {
+  constexpr unsigned kFull = 0xffffffffu;
   const unsigned* vals = sorted_vals(h, vals_a, vals_b);
-  const int nv = h->n_voxels;
+  const long long nv = h->n_voxels;
   const int lane = threadIdx.x & 31;
-  for (long long v = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); v < nv; v += (long long)gridDim.x * 8) {
-    const unsigned s0 = seg_start[v], s1 = seg_start[v + 1];
-    const unsigned n = s1 - s0;
-    if (counts && lane == 0) counts[v] = (int)n;
-    // softmax statistics over the members (lanes stride over members)
-    float m = -INFINITY;
-    for (unsigned j = s0 + lane; j < s1; j += 32) m = fmaxf(m, conf[(long long)vals[j] * conf_stride]);
+  const long long nbatch = (nv + 31) / 32;
+  for (long long bt = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); bt < nbatch; bt += (long long)gridDim.x * 8) {
+    const long long v0 = bt * 32;
+    const int nvalid = (int)min(32ll, nv - v0);
+    const bool vok = lane < nvalid;
+    const unsigned s0 = seg_start[v0 + (vok ? lane : nvalid - 1)];
+    const unsigned s1 = seg_start[v0 + (vok ? lane : nvalid - 1) + 1];
+    const unsigned n = vok ? s1 - s0 : 0u;
+    if (counts && vok) counts[v0 + lane] = (int)n;
+    // ---- phase 1
+    float m = 0.f, den = 1.0f;  // one member: exp(0) = 1
+    const unsigned nmax = __reduce_max_sync(kFull, n);
+    if (nmax > 1 && nmax <= 64) {
+      if (n > 1) {
+        m = -INFINITY;
+        for (unsigned j = s0; j < s1; ++j) m = fmaxf(m, conf[(long long)vals[j] * conf_stride]);
+        den = 0.f;
+        for (unsigned j = s0; j < s1; ++j) den += expf(conf[(long long)vals[j] * conf_stride] - m);
+      }
+    } else if (nmax > 64) {  // long segments: the warp shares each voxel's members
+      for (int k = 0; k < nvalid; ++k) {
+        const unsigned a = __shfl_sync(kFull, s0, k), b = __shfl_sync(kFull, s1, k);
+        if (b - a <= 1) continue;
+        float mk = -INFINITY;
+        for (unsigned j = a + lane; j < b; j += 32) mk = fmaxf(mk, conf[(long long)vals[j] * conf_stride]);
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-    float den;
-    if (n == 1) {
-      den = 1.0f;  // exp(0)
-    } else {
-      float sacc = 0.f;
-      for (unsigned j = s0 + lane; j < s1; j += 32) sacc += expf(conf[(long long)vals[j] * conf_stride] - m);
+        for (int o = 16; o > 0; o >>= 1) mk = fmaxf(mk, __shfl_xor_sync(kFull, mk, o));
+        float sk = 0.f;
+        for (unsigned j = a + lane; j < b; j += 32) sk += expf(conf[(long long)vals[j] * conf_stride] - mk);
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, o);
-      den = sacc;
+        for (int o = 16; o > 0; o >>= 1) sk += __shfl_xor_sync(kFull, sk, o);
+        if (lane == k) { m = mk; den = sk; }
+      }
     }
     den += 1e-6f;
-    // weighted sums in member order: lane l owns output channels l, l + 32, ... (0..2 = xyz, 3.. = features)
+    // ---- phase 2
+    const unsigned r0 = __shfl_sync(kFull, s0, 0);
+    const unsigned r1 = __shfl_sync(kFull, s1, nvalid - 1);
     float acc[NCH];
 #pragma unroll
     for (int r = 0; r < NCH; ++r) acc[r] = 0.f;
-    for (unsigned j = s0; j < s1; ++j) {
-      const long long idx = vals[j];
-      const float w = __fdiv_rn(expf(conf[idx * conf_stride] - m), den);
+    int cur = 0;  // voxel (relative to v0) the accumulator belongs to
+    auto flush = [&](int rel) {
+      const long long v = v0 + rel;
 #pragma unroll
       for (int r = 0; r < NCH; ++r) {
         const int c = lane + 32 * r;
-        if (c < 3 + C) {
-          const float x = c < 3 ? pts[idx * 3 + c] : feats[idx * ld_feats + (c - 3)];
-          acc[r] = __fadd_rn(acc[r], __fmul_rn(x, w));
+        if (c < 3) voxel_pts[v * 3 + c] = acc[r];
+        else if (c < 3 + C) voxel_feats[v * C + (c - 3)] = acc[r];
+        acc[r] = 0.f;
+      }
+    };
+    for (unsigned base = r0; base < r1; base += 32) {
+      const unsigned j = base + lane;
+      const bool ok = j < r1;
+      const long long idx = ok ? (long long)vals[j] : 0ll;
+      const int rel = ok ? (int)((long long)seg_of[j] - v0) : 0;
+      const unsigned nn = __shfl_sync(kFull, n, rel);
+      const float mm = __shfl_sync(kFull, m, rel), dd = __shfl_sync(kFull, den, rel);
+      const float e = (ok && nn > 1) ? expf(conf[idx * conf_stride] - mm) : 1.0f;
+      const float w = __fdiv_rn(e, dd);
+      const int cnt = (int)min(32u, r1 - base);
+      for (int k = 0; k < cnt; k += 4) {
+        float x[4][NCH];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (k + u < cnt) {
+            const long long iu = __shfl_sync(kFull, idx, k + u);
+#pragma unroll
+            for (int r = 0; r < NCH; ++r) {
+              const int c = lane + 32 * r;
+              x[u][r] = c < 3 ? pts[iu * 3 + c] : (c < 3 + C ? feats[iu * ld_feats + (c - 3)] : 0.f);
+            }
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (k + u < cnt) {
+            const int ru = __shfl_sync(kFull, rel, k + u);
+            const float wu = __shfl_sync(kFull, w, k + u);
+            if (ru != cur) {  // warp-uniform
+              flush(cur);
+              cur = ru;
+            }
+#pragma unroll
+            for (int r = 0; r < NCH; ++r) acc[r] = __fadd_rn(acc[r], __fmul_rn(x[u][r], wu));
+          }
         }
       }
     }
-#pragma unroll
-    for (int r = 0; r < NCH; ++r) {
-      const int c = lane + 32 * r;
-      if (c < 3) voxel_pts[v * 3 + c] = acc[r];
-      else if (c < 3 + C) voxel_feats[v * C + (c - 3)] = acc[r];
-    }
+    if (r1 > r0) flush(cur);
   }
 }
 
@@ -426,8 +508,10 @@ struct VoxelWorkspace {
   unsigned long long *keys_a, *keys_b;
   unsigned *vals_a, *vals_b;
   unsigned* block_hist;
+  unsigned* digit_total;
   unsigned* partial;
   unsigned* seg_start;
+  unsigned* seg_of;
   long long bytes;
   int nblocks, nscan;
 };
@@ -445,8 +529,10 @@ VoxelWorkspace carve(void* ws, long long N) {
   w.vals_a = reinterpret_cast<unsigned*>(take(4 * N));
   w.vals_b = reinterpret_cast<unsigned*>(take(4 * N));
   w.block_hist = reinterpret_cast<unsigned*>(take(4ll * 256 * w.nblocks));
+  w.digit_total = reinterpret_cast<unsigned*>(take(4 * 256));
   w.partial = reinterpret_cast<unsigned*>(take(4ll * w.nscan));
   w.seg_start = reinterpret_cast<unsigned*>(take(4 * (N + 1)));
+  w.seg_of = reinterpret_cast<unsigned*>(take(4 * N));
   w.bytes = off;
   return w;
 }
@@ -469,26 +555,28 @@ int voxel_fusion_entry(const float* pts, const float* feats, long long ld_feats,
   if (rc) return rc;
   const int sms = num_sms();
   long long launches = 0;
+  V3A_REQUIRE(((uintptr_t)pts & 15) == 0, VIST3A_ERR_INVALID, "voxel_fusion: pts must be 16-byte aligned");
   voxel_init_kernel<<<1, 32, 0, st>>>(w.header);
-  voxel_range_kernel<<<(unsigned)min((long long)sms * 8, (3 * N + 255) / 256), 256, 0, st>>>(pts, N, voxel_size, w.header);
+  voxel_range_kernel<<<(unsigned)min((long long)sms * 8, (N / 4 + 255) / 256 + 1), 256, 0, st>>>(pts, N, voxel_size, w.header);
   voxel_bits_kernel<<<1, 32, 0, st>>>(w.header);
   voxel_key_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(pts, N, voxel_size, w.header, w.keys_a, w.vals_a);
   launches += 4;
   for (int pass = 0; pass < 8; ++pass) {  // passes >= ceil(bits / 8) return immediately (device-side count: no host round trip)
     radix_hist_kernel<<<w.nblocks, kSortThreads, 0, st>>>(w.keys_a, w.keys_b, N, pass, w.header, w.block_hist, w.nblocks);
-    radix_scan_kernel<<<1, 1024, 0, st>>>(w.block_hist, 256ll * w.nblocks, pass, w.header);
-    radix_scatter_kernel<<<w.nblocks, kSortThreads, 0, st>>>(w.keys_a, w.keys_b, w.vals_a, w.vals_b, N, pass, w.header, w.block_hist, w.nblocks);
+    radix_scan_kernel<<<256, 256, 0, st>>>(w.block_hist, w.nblocks, w.digit_total, pass, w.header);
+    radix_scatter_kernel<<<w.nblocks, kSortThreads, 0, st>>>(w.keys_a, w.keys_b, w.vals_a, w.vals_b, N, pass, w.header, w.block_hist, w.nblocks,
+                                                             w.digit_total);
     launches += 3;
   }
   seg_count_kernel<<<w.nscan, 256, 0, st>>>(w.keys_a, w.keys_b, N, w.header, w.partial);
   seg_scan_partials_kernel<<<1, 1024, 0, st>>>(w.partial, w.nscan, w.header, n_voxels, w.seg_start, N);
-  seg_assign_kernel<<<w.nscan, 256, 0, st>>>(w.keys_a, w.keys_b, w.vals_a, w.vals_b, N, w.header, w.partial, w.seg_start, inverse);
+  seg_assign_kernel<<<w.nscan, 256, 0, st>>>(w.keys_a, w.keys_b, w.vals_a, w.vals_b, N, w.header, w.partial, w.seg_start, w.seg_of, inverse);
   launches += 3;
-  const unsigned rgrid = (unsigned)min((N + 7) / 8, (long long)sms * 32);
+  const unsigned rgrid = (unsigned)min((N + 255) / 256, (long long)sms * 32);  // a warp per 32 voxels, 8 warps per block
   const int nch = (int)((3 + C + 31) / 32);
 #define V3A_REDUCE(NCH_)                                                                                                                   \
   voxel_reduce_kernel<NCH_><<<rgrid, 256, 0, st>>>(pts, feats, ld_feats, (int)C, conf, conf_stride, w.vals_a, w.vals_b, w.header, w.seg_start, \
-                                                   voxel_pts, voxel_feats, counts)
+                                                   w.seg_of, voxel_pts, voxel_feats, counts)
   if (nch == 1) V3A_REDUCE(1);
   else if (nch == 2) V3A_REDUCE(2);
   else if (nch == 3) V3A_REDUCE(3);
