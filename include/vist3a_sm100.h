@@ -133,7 +133,8 @@ typedef struct vist3a_fmha_args {
   int64_t v_bs, v_rs, v_hs;
   int64_t o_bs, o_rs, o_hs;
   float scale; /* multiplies QK^T; 1/sqrt(head_dim) in both references */
-  uint32_t flags;
+  uint32_t flags; /* 0 = tuned default; kernel-variant selectors for A/B measurements only (results identical up to rounding):
+                     bit0 one thread per query row, bit1 128-key steps (d=128), bit2 single MMA-issuing warp, bits 3.. = 1 + FMA-pipe exp2 share */
   const float* q_row_scale; /* optional [batch * len_q] fp32: extra positive factor on the logits of query row (b, i), all heads */
 } vist3a_fmha_args;
 

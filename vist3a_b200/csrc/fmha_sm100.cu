@@ -32,7 +32,20 @@ struct FmhaParams {
   int len_q, len_kv;
   float scale_log2;  // scale * log2(e)
   const float* row_scale;  // optional per-(batch, query row) positive factor on the logits
+  int single_issuer;       // one MMA-issuing warp for both query tiles (flags bit 2)
+  long long* trace;        // debug: 32 clock64 stamps / phase sums per CTA (v3a_debug_fmha_trace), normally null
 };
+
+static long long* g_fmha_trace = nullptr;
+extern "C" void v3a_debug_fmha_trace(void* buf) { g_fmha_trace = reinterpret_cast<long long*>(buf); }
+#define FMHA_TRACE_ADD(slot, val)                                                                                     \
+  do {                                                                                                                \
+    if (p.trace) p.trace[((long long)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 32 + (slot)] = (val); \
+  } while (0)
+#define FMHA_TRACE(slot)                                                                                              \
+  do {                                                                                                                \
+    if (p.trace) p.trace[((long long)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 32 + (slot)] = clock64(); \
+  } while (0)
 
 template <int D, int BKV_, int POLY_, int SPLIT_>
 struct FmhaCfg {
@@ -113,7 +126,7 @@ __device__ __forceinline__ void exp2_poly2(float y0, float y1, float& e0, float&
 template <int D, int BKV_, int POLY_, int SPLIT_>
 __global__ void __launch_bounds__(128 + 256 * SPLIT_, 1)
 fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                const __grid_constant__ CUtensorMap tmV, const FmhaParams p) {
+                const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO, const FmhaParams p) {
   using Cfg = FmhaCfg<D, BKV_, POLY_, SPLIT_>;
   constexpr int SPLIT = Cfg::SPLIT;
   constexpr int HC = Cfg::HC;
@@ -147,11 +160,20 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const int batch = blockIdx.z;
   const int n_kv = (p.len_kv + BKV - 1) / BKV;
   const int nq = (q0 + Cfg::BQ < p.len_q) ? 2 : 1;  // query tiles of this CTA that hold at least one row
+  if (threadIdx.x == 0) {
+    FMHA_TRACE(0);
+    if (p.trace) {
+      unsigned smid;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      p.trace[((long long)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 32 + 12] = smid;
+    }
+  }
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
+    tma_prefetch_desc(&tmO);
   }
   if (warp == 1 && lane == 0) {
     mbar_init(q_full, 1);
@@ -177,8 +199,10 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  if (threadIdx.x == 0) FMHA_TRACE(1);
   pdl_launch_dependents();
   pdl_wait();  // PDL: q/k/v of the previous kernel are read (and O written) only after this point
+  if (threadIdx.x == 0) FMHA_TRACE(2);
 
   if (warp < 4) {
     if constexpr (SPLIT == 1) asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
@@ -194,6 +218,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
       }
       __syncwarp();
+      if (lane == 0) FMHA_TRACE(3);
       int s = 0;
       uint32_t ph = 0;
       for (int j = 0; j < n_kv; ++j) {
@@ -215,18 +240,16 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         __syncwarp();
         if (++s == ST) { s = 0; ph ^= 1u; }
       }
-    } else if (warp != 2 && (int)(warp >> 1) < nq) {
-      // ------------------------------ MMA issuer of query tile i ------------------------------
-      const int i = (int)(warp >> 1);  // warp 1 -> tile 0, warp 3 -> tile 1
+    } else if (warp != 2) {
+      // ------------------------------ MMA issue ------------------------------
       constexpr uint32_t idesc_qk = make_idesc(kFmtBF16, 128, BKV, 0, 0);
       constexpr uint32_t idesc_pv = make_idesc(kFmtBF16, 128, D, 0, 1);  // B (V) is MN-major
-      const uint32_t t_base = tmem_base + (uint32_t)i * Cfg::TILE_COLS;
-      const uint64_t qdesc = make_smem_desc_sw128(smem_q(i), 1024, 0);
-      auto issue_qk = [&](int j, int s, uint32_t ph) {  // (s, ph) = ring slot / phase of key tile j
+      auto issue_qk = [&](int i, int j, int s, uint32_t ph) {  // (s, ph) = ring slot / phase of key tile j
         mbar_wait(k_full(s), ph);
         tc_fence_after();
         if (elect_one()) {
-          const uint32_t d_tmem = t_base + Cfg::TM_S + (uint32_t)(j % NSB) * Cfg::S_STRIDE;
+          const uint32_t d_tmem = tmem_base + (uint32_t)i * Cfg::TILE_COLS + Cfg::TM_S + (uint32_t)(j % NSB) * Cfg::S_STRIDE;
+          const uint64_t qdesc = make_smem_desc_sw128(smem_q(i), 1024, 0);
           const uint64_t bdesc = make_smem_desc_sw128(smem_k(s), 1024, 0);
 #pragma unroll
           for (int kk = 0; kk < D / 16; ++kk) {
@@ -240,10 +263,11 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
         __syncwarp();
       };
-      auto issue_pv = [&](int j, int s, uint32_t ph) {
+      auto issue_pv = [&](int i, int j, int s, uint32_t ph) {
         mbar_wait(v_full(s), ph);
         tc_fence_after();
         if (elect_one()) {
+          const uint32_t t_base = tmem_base + (uint32_t)i * Cfg::TILE_COLS;
           const uint32_t p_tmem = t_base + Cfg::TM_P + (uint32_t)(j & 1) * Cfg::P_STRIDE;
           // V tile: kv rows at a 128 B pitch (K dimension), 64-wide head-dim slabs LBO apart (MN dimension)
           const uint64_t bdesc = make_smem_desc_sw128(smem_v(s), 1024, Cfg::KV_SLAB_BYTES);
@@ -255,30 +279,98 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
         __syncwarp();
       };
-      mbar_wait(q_full, 0);
-      int qs = 0, vs = 0;  // ring positions of the key tile the next QK / PV reads
-      uint32_t qph = 0, vph = 0;
       auto adv = [&](int& s_, uint32_t& ph_) { if (++s_ == ST) { s_ = 0; ph_ ^= 1u; } };
-      for (int j = 0; j < NSB && j < n_kv; ++j) {
-        issue_qk(j, qs, qph);
-        adv(qs, qph);
-      }
-      for (int j = 0; j < n_kv; ++j) {
-        const bool more = j + NSB < n_kv;
-        if (!Cfg::ALIAS && more) {
-          mbar_wait(s_free(i), (uint32_t)j & 1u);  // the softmax warps hold S(j) in registers
+      const bool trm = p.trace != nullptr && warp == 1;
+      long long mm_wait = 0, mm_issue = 0, mt = 0;
+      if (p.single_issuer) {
+        // ONE warp serves both query tiles, polling their barriers and issuing whichever block (P V of step j, then Q K^T of step
+        // j + NSB) is ready as a whole: the in-order tensor pipe then finishes a tile's block in its own 512 cycles instead of
+        // interleaving it MMA by MMA with the other tile's (two issuing warps), which delayed BOTH score tiles by a full 1024.
+        if (warp == 1) {
+          mbar_wait(q_full, 0);
+          if (lane == 0) FMHA_TRACE(4);
+          int qs[2] = {0, 0}, vs[2] = {0, 0}, jq[2] = {0, 0}, jp[2] = {0, 0};
+          uint32_t qph[2] = {0, 0}, vph[2] = {0, 0};
+          for (int j = 0; j < NSB && j < n_kv; ++j) {
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+              if (i < nq) {
+                issue_qk(i, j, qs[i], qph[i]);
+                adv(qs[i], qph[i]);
+                jq[i] = j + 1;
+              }
+            }
+            if (j == 0 && lane == 0) FMHA_TRACE(5);
+          }
+          int remaining = nq * n_kv;
+          if (trm) mt = clock64();
+          while (remaining > 0) {
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+              if (i >= nq) continue;
+              if (!Cfg::ALIAS && jq[i] < n_kv) {  // Q K^T of the next step as soon as the softmax warps hold S in registers
+                if (__any_sync(0xffffffffu, mbar_try_wait(s_free(i), (uint32_t)(jq[i] - 1) & 1u))) {
+                  tc_fence_after();
+                  if (trm) { const long long t2 = clock64(); mm_wait += t2 - mt; mt = t2; }
+                  issue_qk(i, jq[i], qs[i], qph[i]);
+                  adv(qs[i], qph[i]);
+                  ++jq[i];
+                  if (trm) { const long long t2 = clock64(); mm_issue += t2 - mt; mt = t2; }
+                }
+              }
+              if (jp[i] < n_kv) {
+                const int j = jp[i];
+                if (__any_sync(0xffffffffu, mbar_try_wait(p_full(i, j & 1), (uint32_t)(j >> 1) & 1u))) {
+                  tc_fence_after();
+                  if (trm) { const long long t2 = clock64(); mm_wait += t2 - mt; mt = t2; }
+                  issue_pv(i, j, vs[i], vph[i]);
+                  adv(vs[i], vph[i]);
+                  if (Cfg::ALIAS && j + NSB < n_kv) {  // overwrites S(j)|P(j): ordered behind P(j) V by the in-order tensor pipe
+                    issue_qk(i, j + NSB, qs[i], qph[i]);
+                    adv(qs[i], qph[i]);
+                  }
+                  ++jp[i];
+                  --remaining;
+                  if (trm) { const long long t2 = clock64(); mm_issue += t2 - mt; mt = t2; }
+                }
+              }
+            }
+          }
+          if (trm && lane == 0) { FMHA_TRACE_ADD(21, mm_wait); FMHA_TRACE_ADD(22, mm_issue); }
+        }
+      } else if ((int)(warp >> 1) < nq) {
+        // one issuing warp per query tile (warp 1 -> tile 0, warp 3 -> tile 1)
+        const int i = (int)(warp >> 1);
+        mbar_wait(q_full, 0);
+        if (warp == 1 && lane == 0) FMHA_TRACE(4);
+        int qs = 0, vs = 0;  // ring positions of the key tile the next QK / PV reads
+        uint32_t qph = 0, vph = 0;
+        for (int j = 0; j < NSB && j < n_kv; ++j) {
+          issue_qk(i, j, qs, qph);
+          adv(qs, qph);
+          if (j == 0 && warp == 1 && lane == 0) FMHA_TRACE(5);
+        }
+        for (int j = 0; j < n_kv; ++j) {
+          const bool more = j + NSB < n_kv;
+          if (trm) mt = clock64();
+          if (!Cfg::ALIAS && more) {
+            mbar_wait(s_free(i), (uint32_t)j & 1u);  // the softmax warps hold S(j) in registers
+            tc_fence_after();
+            issue_qk(i, j + 1, qs, qph);
+            adv(qs, qph);
+          }
+          mbar_wait(p_full(i, j & 1), (uint32_t)(j >> 1) & 1u);
           tc_fence_after();
-          issue_qk(j + 1, qs, qph);
-          adv(qs, qph);
+          if (trm) { const long long t2 = clock64(); mm_wait += t2 - mt; mt = t2; }
+          issue_pv(i, j, vs, vph);
+          adv(vs, vph);
+          if (Cfg::ALIAS && more) {  // overwrites S(j)|P(j): ordered behind P(j) V by the in-order tensor pipe
+            issue_qk(i, j + NSB, qs, qph);
+            adv(qs, qph);
+          }
+          if (trm) mm_issue += clock64() - mt;
         }
-        mbar_wait(p_full(i, j & 1), (uint32_t)(j >> 1) & 1u);
-        tc_fence_after();
-        issue_pv(j, vs, vph);
-        adv(vs, vph);
-        if (Cfg::ALIAS && more) {  // overwrites S(j)|P(j): ordered behind P(j) V by the in-order tensor pipe
-          issue_qk(j + NSB, qs, qph);
-          adv(qs, qph);
-        }
+        if (trm && lane == 0) { FMHA_TRACE_ADD(21, mm_wait); FMHA_TRACE_ADD(22, mm_issue); }
       }
     }
   } else {
@@ -305,15 +397,21 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       float l_run = 0.0f;       // running sum of exp2((s - m_run) * scale_log2) over this thread's columns
       const float c = (p.row_scale && row < p.len_q) ? p.scale_log2 * p.row_scale[(long long)batch * p.len_q + row] : p.scale_log2;
       const uint64_t cc2 = pack2(c, c);
+      const bool tr = p.trace != nullptr && warp == 4;
+      long long ph_wait = 0, ph_ld = 0, ph_max = 0, ph_exp = 0, ph_st = 0, tt = 0;
       for (int j = 0; j < n_kv; ++j) {
         const int sb = j % NSB;
+        if (tr) tt = clock64();
         mbar_wait(s_full(i, sb), (uint32_t)(j / NSB) & 1u);
         tc_fence_after();
+        if (tr) { const long long t2 = clock64(); ph_wait += t2 - tt; tt = t2; }
+        if (j == 0 && warp == 4 && lane == 0) FMHA_TRACE(6);
         uint32_t r[HC];
         const uint32_t s_addr = tile_base + Cfg::TM_S + (uint32_t)sb * Cfg::S_STRIDE + (uint32_t)(h * HC);
 #pragma unroll
         for (int cb = 0; cb < HC / 32; ++cb) tmem_ld_x32(s_addr + (uint32_t)(cb * 32), r + cb * 32);
         tmem_ld_wait();
+        if (tr) { const long long t2 = clock64(); ph_ld += t2 - tt; tt = t2; }
         if (!Cfg::ALIAS) {
           tc_fence_before();
           __syncwarp();
@@ -369,6 +467,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           }
         }
         tc_fence_after();
+        if (tr) { const long long t2 = clock64(); ph_max += t2 - tt; tt = t2; }
         const float nmc = -m_run * c;
         const uint64_t mc2 = pack2(nmc, nmc);
         uint64_t sum2[2] = {0ull, 0ull};  // packed (even, odd) column partial sums
@@ -397,10 +496,17 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           unpack2(sum2[1], s2, s3);
           l_run += (s0 + s1) + (s2 + s3);
         }
+        if (tr) { const long long t2 = clock64(); ph_exp += t2 - tt; tt = t2; }
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(p_full(i, j & 1));
+        if (tr) { const long long t2 = clock64(); ph_st += t2 - tt; tt = t2; }
+        if (j == 0 && warp == 4 && lane == 0) FMHA_TRACE(7);
+      }
+      if (warp == 4 && lane == 0) {
+        FMHA_TRACE(8);
+        FMHA_TRACE_ADD(16, ph_wait); FMHA_TRACE_ADD(17, ph_ld); FMHA_TRACE_ADD(18, ph_max); FMHA_TRACE_ADD(19, ph_exp); FMHA_TRACE_ADD(20, ph_st);
       }
       // ---- epilogue: O / l -> bf16 -> global ----
       if constexpr (SPLIT == 2) {
@@ -412,31 +518,46 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
       mbar_wait(pv_done(i, (n_kv - 1) & 1), (uint32_t)((n_kv - 1) >> 1) & 1u);  // the commit covers every earlier MMA too
       tc_fence_after();
+      if (warp == 4 && lane == 0) FMHA_TRACE(9);
       const float inv_l = 1.0f / l_run;
-      __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(p.O) + (long long)batch * p.o_bs + (long long)row * p.o_rs +
-                            (long long)head * p.o_hs + h * OC;
+      // O / l -> bf16 -> this tile's Q buffer (free: every MMA has completed) in the 128B-swizzled box layout, then ONE bulk tensor store
+      // per 64-column slab.  (Per-thread row stores are uncoalesced -- 32 rows per instruction -- and cost ~7000 cycles per CTA.)
+      // Rows past len_q are clipped by the TMA unit.
 #pragma unroll
       for (int cb = 0; cb < OC / 32; ++cb) {
         uint32_t o[32];
         tmem_ld_x32(o_addr + (uint32_t)(cb * 32), o);
         tmem_ld_wait();
-        if (row < p.len_q) {
+        const int col0 = h * OC + cb * 32;  // first of 32 consecutive output columns
+        const uint32_t srow = smem_q(i) + (uint32_t)((col0 >> 6) * Cfg::Q_SLAB_BYTES + rit * 128);
 #pragma unroll
-          for (int k = 0; k < 32; k += 8) {
-            uint4 w;
-            w.x = pack_bf16(__uint_as_float(o[k]) * inv_l, __uint_as_float(o[k + 1]) * inv_l);
-            w.y = pack_bf16(__uint_as_float(o[k + 2]) * inv_l, __uint_as_float(o[k + 3]) * inv_l);
-            w.z = pack_bf16(__uint_as_float(o[k + 4]) * inv_l, __uint_as_float(o[k + 5]) * inv_l);
-            w.w = pack_bf16(__uint_as_float(o[k + 6]) * inv_l, __uint_as_float(o[k + 7]) * inv_l);
-            *reinterpret_cast<uint4*>(orow + cb * 32 + k) = w;
-          }
+        for (int k = 0; k < 32; k += 8) {
+          const uint32_t chunk = (uint32_t)(((col0 & 63) + k) >> 3);
+          const uint32_t dst = srow + ((chunk ^ ((uint32_t)rit & 7u)) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst),
+                       "r"(pack_bf16(__uint_as_float(o[k]) * inv_l, __uint_as_float(o[k + 1]) * inv_l)),
+                       "r"(pack_bf16(__uint_as_float(o[k + 2]) * inv_l, __uint_as_float(o[k + 3]) * inv_l)),
+                       "r"(pack_bf16(__uint_as_float(o[k + 4]) * inv_l, __uint_as_float(o[k + 5]) * inv_l)),
+                       "r"(pack_bf16(__uint_as_float(o[k + 6]) * inv_l, __uint_as_float(o[k + 7]) * inv_l))
+                       : "memory");
         }
       }
+      fence_proxy_async_smem();
+      asm volatile("bar.sync %0, %1;" ::"r"(9u + (uint32_t)i), "r"(128u * SPLIT) : "memory");  // all threads of this tile
+      if (h == 0 && rit == 0) {
+#pragma unroll
+        for (int sl = 0; sl < Cfg::SLABS; ++sl)
+          tma_store_4d(&tmO, smem_q(i) + sl * Cfg::Q_SLAB_BYTES, sl * 64, head, q0 + i * Cfg::BQ, batch);
+        tma_store_commit();
+        tma_store_wait_read<0>();  // the buffer must stay intact until the TMA unit has read it (the CTA exits next)
+      }
+      if (warp == 4 && lane == 0) FMHA_TRACE(10);
     }
   }
 
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) FMHA_TRACE(11);
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc<1>(tmem_base, 512);
@@ -456,16 +577,19 @@ static int make_qkv_map(CUtensorMap* tm, const void* ptr, long long B, long long
 template <int D, int BKV_, int POLY_, int SPLIT_>
 static int launch_fmha(const vist3a_fmha_args& a, cudaStream_t stream) {
   using Cfg = FmhaCfg<D, BKV_, POLY_, SPLIT_>;
-  CUtensorMap tmQ, tmK, tmV;
+  CUtensorMap tmQ, tmK, tmV, tmO;
   int rc;
   if ((rc = make_qkv_map(&tmQ, a.Q, a.batch, a.heads, a.len_q, D, a.q_bs, a.q_rs, a.q_hs, Cfg::BQ))) return rc;
   if ((rc = make_qkv_map(&tmK, a.K, a.batch, a.heads, a.len_kv, D, a.k_bs, a.k_rs, a.k_hs, Cfg::BKV))) return rc;
   if ((rc = make_qkv_map(&tmV, a.V, a.batch, a.heads, a.len_kv, D, a.v_bs, a.v_rs, a.v_hs, Cfg::BKV))) return rc;
+  if ((rc = make_qkv_map(&tmO, a.O, a.batch, a.heads, a.len_q, D, a.o_bs, a.o_rs, a.o_hs, Cfg::BQ))) return rc;
   FmhaParams p;
   p.O = a.O; p.o_bs = a.o_bs; p.o_rs = a.o_rs; p.o_hs = a.o_hs;
   p.len_q = (int)a.len_q; p.len_kv = (int)a.len_kv;
   p.scale_log2 = a.scale * 1.4426950408889634f;
   p.row_scale = a.q_row_scale;
+  p.trace = g_fmha_trace;
+  p.single_issuer = (a.flags & 4u) ? 1 : 0;
   auto kern = fmha_fwd_kernel<D, BKV_, POLY_, SPLIT_>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -474,7 +598,7 @@ static int launch_fmha(const vist3a_fmha_args& a, cudaStream_t stream) {
   }
   const long long rows_per_cta = Cfg::BQ * Cfg::QT;
   dim3 grid((unsigned)((a.len_q + rows_per_cta - 1) / rows_per_cta), (unsigned)a.heads, (unsigned)a.batch);
-  V3A_CUDA_OK(launch_kernel(kern, grid, dim3(Cfg::THREADS), Cfg::SMEM_BYTES, stream, /*pdl=*/true, 1, tmQ, tmK, tmV, p));
+  V3A_CUDA_OK(launch_kernel(kern, grid, dim3(Cfg::THREADS), Cfg::SMEM_BYTES, stream, /*pdl=*/true, 1, tmQ, tmK, tmV, tmO, p));
   launch_counter().fetch_add(1);
   return VIST3A_OK;
 }
@@ -494,14 +618,30 @@ int fmha_entry(const vist3a_fmha_args* args, cudaStream_t stream) {
               "fmha: pointers must be 16-byte aligned");
   int rc = check_arch();
   if (rc) return rc;
-  // exponentials on the FMA pipe per 8 column pairs: 3 at d=64 (MUFU-bound), 2 at d=128 (measured optimum on B200)
   // Default: two threads per query row (4 softmax warpgroups, 640 threads), 64-key double-buffered steps at d=128, 128-key steps at
   // d=64 -- the fastest of the variants measured on B200 (tools/fmha_variants.py).  flags bit0 selects one thread per row (2 softmax
-  // warpgroups, setmaxnreg-enlarged register file), bit1 (d=128) the 128-key aliased steps; kept for A/B measurements.
+  // warpgroups, setmaxnreg-enlarged register file), bit1 (d=128) the 128-key aliased steps, bit2 a single MMA-issuing warp for both query tiles (measured slower: one thread cannot keep
+  // the pipe fed); kept for A/B measurements.
   const bool one = (a.flags & 1u) != 0;
-  if (a.head_dim == 64) return one ? launch_fmha<64, 128, 3, 1>(a, stream) : launch_fmha<64, 128, 3, 2>(a, stream);
+  // Share of the exponentials moved from the MUFU to the FMA pipe (Cody-Waite + polynomial), per 8 column pairs.  Measured on B200 with
+  // two threads per query row (4 softmax warpgroups): the softmax is bound by issue slots and dependent-latency chains rather than by
+  // the MUFU, so the default is 0 (all MUFU.EX2): +4 % at d=128 / 4096 keys, +9 % at d=64 / 13377 keys over the former 2 / 3 of 8; short
+  // key sequences (cross-attention, 512 keys) keep 2 of 8.  flags >> 3 = 1 + share selects a variant explicitly (A/B).
+  const unsigned poly_sel = a.flags >> 3;
+  if (a.head_dim == 64) {
+    if (one) return launch_fmha<64, 128, 3, 1>(a, stream);
+    if (poly_sel == 2u) return launch_fmha<64, 128, 1, 2>(a, stream);
+    if (poly_sel == 3u) return launch_fmha<64, 128, 2, 2>(a, stream);
+    if (poly_sel == 4u) return launch_fmha<64, 128, 3, 2>(a, stream);
+    return launch_fmha<64, 128, 0, 2>(a, stream);
+  }
   if (a.flags & 2u) return one ? launch_fmha<128, 128, 2, 1>(a, stream) : launch_fmha<128, 128, 2, 2>(a, stream);
-  return one ? launch_fmha<128, 64, 2, 1>(a, stream) : launch_fmha<128, 64, 2, 2>(a, stream);
+  if (one) return launch_fmha<128, 64, 2, 1>(a, stream);
+  if (poly_sel == 1u) return launch_fmha<128, 64, 0, 2>(a, stream);
+  if (poly_sel == 2u) return launch_fmha<128, 64, 1, 2>(a, stream);
+  if (poly_sel == 3u) return launch_fmha<128, 64, 2, 2>(a, stream);
+  if (poly_sel == 4u) return launch_fmha<128, 64, 3, 2>(a, stream);
+  return a.len_kv >= 2048 ? launch_fmha<128, 64, 0, 2>(a, stream) : launch_fmha<128, 64, 2, 2>(a, stream);
 }
 
 }  // namespace v3a
