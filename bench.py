@@ -39,6 +39,30 @@ VIEWS, IMG = 13, 448
 N_GAUSS = VIEWS * IMG * IMG
 
 
+def step_tflop(D, F, layers, L, Lt, text_dim=4096):
+    """Algorithmic TFLOP of one denoise step (cond + uncond forward), SURVEY §8(d) accounting: per block QKV + self-attention +
+    out + cross (q, text k/v, attention, out) + FFN; plus patch embedding, text / time embedders and the output head."""
+    block = 2 * L * D * 3 * D + 4 * L * L * D + 2 * L * D * D + (2 * L * D * D + 2 * Lt * D * 2 * D + 4 * L * Lt * D + 2 * L * D * D) + 4 * L * D * F
+    extra = 2 * L * 64 * D * 2 + 2 * Lt * (text_dim * D + D * D) + 2 * (256 * D + D * D + D * 6 * D)
+    return 2.0 * (layers * block + extra) / 1e12
+
+
+def configure(args):
+    """BASELINE configs: 1.3B / 13 views (headline, configs[1-2]) or 14B / 21 views (configs[3]); sets the module-level workload."""
+    global WORKLOAD, STEP_TFLOP, DECODER_TFLOP, VIEWS, N_GAUSS
+    VIEWS = args.views
+    N_GAUSS = VIEWS * IMG * IMG
+    T = (VIEWS - 1) // 4 + 1
+    L = T * 32 * 32
+    D, F, layers, params = (1536, 8960, 30, "1.419 B") if args.model == "1.3b" else (5120, 13824, 40, "14.29 B")
+    STEP_TFLOP = step_tflop(D, F, layers, L, 512)
+    DECODER_TFLOP = {13: 50.28, 21: 98.70}[VIEWS]  # SURVEY §8(a): 43.75 + 6.53 at 13 views, 88.16 + 10.54 at 21
+    name = "1.3B" if args.model == "1.3b" else "14B"
+    WORKLOAD = (f"VIST3A-{name} DiT 50-step denoise, 512x512x{VIEWS} views (latent [1,16,{T},64,64], L={L}, 512 text tokens), "
+                f"batch {args.prompts_per_gpu} per GPU")
+    return T, params
+
+
 def _peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -162,20 +186,20 @@ def run_reference(args):
 # --------------------------------------------------------------------------------------------------
 # our arm
 # --------------------------------------------------------------------------------------------------
-def build_models(device, with_decoder=True):
+def build_models(device, with_decoder=True, model_name="1.3b", voxelize=False):
     """Random-init weights of the named architectures, generated on the device (no checkpoint is reachable offline)."""
     from types import SimpleNamespace
 
     from vist3a_b200 import stitched_decoder as SD
     from vist3a_b200 import wan_dit as WD
 
-    cfg = WD.WAN_1_3B_CONFIG
+    cfg = WD.WAN_1_3B_CONFIG if model_name == "1.3b" else WD.WAN_14B_CONFIG
     sd = WD.random_state_dict(cfg, 0, device)
     model = WD.WanTransformer3DModelB200.from_state_dict(sd, cfg, device=device)
     del sd
     dec = None
     if with_decoder:
-        dcfg = SD.DecoderConfig()
+        dcfg = SD.DecoderConfig(voxelize=voxelize)
         sd = SD.random_state_dict(dcfg, 0, device)
         dec = SD.StitchVAE3DB200.from_state_dict(sd, dcfg, device=device)
         del sd
@@ -200,8 +224,9 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
     _lib.load()
-    cfg, model, dec = build_models(device, with_decoder=not args.no_decoder)
-    B, T, HW, Lt = args.prompts_per_gpu, 4, 64, 512
+    T_lat, n_params = configure(args)
+    cfg, model, dec = build_models(device, with_decoder=not args.no_decoder, model_name=args.model, voxelize=args.voxelize)
+    B, T, HW, Lt = args.prompts_per_gpu, T_lat, 64, 512
     g = torch.Generator().manual_seed(1000 + rank)  # every rank denoises its own prompt
     noise_h = torch.randn(B, 16, T, HW, HW, generator=g).pin_memory()
     tc_h = torch.randn(B, Lt, cfg.text_dim, generator=g).bfloat16()
@@ -328,7 +353,11 @@ def run_ours(args):
                              (", NCCL all-gather of all ranks' Gaussians" if world > 1 else "") + ", D2H of scene_scale",
                  "decoder_launches_per_forward": dec_launches // kd,
                  "latent": "denoised latent of the random-weight DiT, clamped to [-4, 4] before de-normalisation (real VAE latents are O(1))",
-                 "workload": "VIST3A-1.3B full stitched path: DiT -> conv3d_k5x3x3 stitch -> AnySplat enc_blocks_2 -> 3DGS, 512x512x13v"}
+                 "workload": f"VIST3A-{'1.3B' if args.model == '1.3b' else '14B'} full stitched path: DiT -> conv3d_k5x3x3 stitch -> AnySplat "
+                             f"enc_blocks_2 -> 3DGS, 512x512x{VIEWS}v"}
+        if args.voxelize:  # voxelised fusion (released AnySplat configs): fewer, fused Gaussians; Gaussians/s above still counts pixels decoded
+            gauss["voxelize"] = {"voxel_size": dec.cfg.voxel_size, "voxels_per_prompt": int(outs["o"].gaussians.means.shape[1]),
+                                 "voxelize_ratio": float(outs["o"].infos["voxelize_ratio"])}
         del outs
 
     # ---- per-kernel device timing of one eager step (roofline of the dominant kernel)
@@ -369,7 +398,7 @@ def run_ours(args):
 
     # ---- CPU baseline (rank 0, N=1 only): bounded sample of the oracle port on the host cores
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and args.model == "1.3b" and args.views == 13:
         nb = args.ref_blocks
         t = cpu_sample(nb, repeats=2)[-1]
         sps = 1.0 / (2.0 * 30.0 / nb * t)
@@ -384,8 +413,8 @@ def run_ours(args):
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
                 "data": "synthetic",
-                "config": {"workload": WORKLOAD, "weights": "random-init Wan-1.3B (1.419 B params)", "cfg": "cond+uncond batched B=2",
-                           "cuda_graph": not args.no_graph, "l2": "working set (2.8 GB weights + activations) >> 126 MB L2; no flush needed",
+                "config": {"workload": WORKLOAD, "weights": f"random-init Wan-{args.model.upper()} ({n_params} params)", "cfg": "cond+uncond batched B=2",
+                           "cuda_graph": not args.no_graph, "l2": "working set (bf16 weights of every layer + activations) >> 126 MB L2; no flush needed",
                            "prompts_per_gpu": B},
                 "roofline": roof, "cpu_baseline": cpu, "clocks": clk.summary(), "gaussians": gauss,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -412,6 +441,9 @@ def main():
     ap.add_argument("--prompts-per-gpu", type=int, default=1, help="prompts batched per GPU (BASELINE configs[4] sweep: 1/2/4/8)")
     ap.add_argument("--no-decoder", action="store_true", help="skip the Gaussians/s leg (decoder + gather)")
     ap.add_argument("--decoder-iters", type=int, default=3)
+    ap.add_argument("--model", default="1.3b", choices=["1.3b", "14b"], help="Wan DiT size (BASELINE configs[1-2] / configs[3])")
+    ap.add_argument("--views", type=int, default=13, choices=[13, 21], help="views per prompt (13: latent T=4, L=4096; 21: T=6, L=6144)")
+    ap.add_argument("--voxelize", action="store_true", help="decoder with voxelised Gaussian fusion (voxel_size 0.002)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
