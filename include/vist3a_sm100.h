@@ -249,6 +249,19 @@ int vist3a_im2col_nhwc(const float* x, float* A, int64_t ldA, int64_t n_img, int
  * replaces: "context_image = (rearrange(context_image, 'b c v h w -> b v c h w') + 1) / 2" (models/anysplat_stitched.py:172-174)
  *   and the zero padding of the 7x7 input_merger convolution. */
 int vist3a_rgb_to_nhwc4pad(const void* image, int32_t dtype, float* out, int64_t B, int64_t V, int64_t H, int64_t W, void* stream);
+/* the same for the un-stitched (image -> 3DGS) path: image [B, V, 3, H, W] already in [0, 1], copied unscaled
+ * (EncoderAnySplat.forward passes `image` to the Gaussian head as is, AS/model/encoder/anysplat.py:449-455) */
+int vist3a_rgb01_views_to_nhwc4pad(const void* image, int32_t dtype, float* out, int64_t B, int64_t V, int64_t H, int64_t W, void* stream);
+
+/* DINOv2 patch embedding (stride-p, p x p convolution, no overlap) as a GEMM operand:
+ *   image [n_img, 3, H, W] in [0, 1] (fp32 or bf16)  ->  A [n_img * (H/p) * (W/p), ldA] bf16,
+ *   A[(n, gy, gx), c*p*p + py*p + px] = (bf16(image[n, c, gy*p+py, gx*p+px]) - mean3[c]) / std3[c], columns >= 3 p^2 zero;
+ *   follow with vist3a_gemm against the flattened conv weight [embed_dim, 3 p^2] (zero-padded to ldA columns).
+ * mean3 / std3: HOST pointers to 3 floats (ImageNet statistics).
+ * replaces: Aggregator.forward normalisation (AS/model/encoder/vggt/models/aggregator.py:228) + PatchEmbed.proj
+ *   (AS/model/encoder/vggt/layers/patch_embed.py:65,68-81) of the un-stitched AnySplat encoder. */
+int vist3a_patch_embed_im2col(const void* image, int32_t dtype, void* A, int64_t ldA, int64_t n_img, int64_t H, int64_t W, int32_t patch,
+                              const float* mean3, const float* std3, void* stream);
 
 /* per-head LayerNorm(head_dim = 64) of q and k + 2-D rotary embedding, in place on a fused bf16 [rows, 3*heads*64] qkv buffer.
  *   token p = row % tokens_per_view; p < n_special: position (0,0); else (1 + (p-n_special)/grid_w, 1 + (p-n_special)%grid_w)

@@ -113,8 +113,14 @@ FULL = RefWidth()
 TINY = RefWidth(embed_dim=64, num_heads=1, dino_depth=4, cam_heads=2, dpt_features=256, dpt_out_channels=(32, 32, 64, 64), pos_grid=37)
 
 
+def load_teacher(width: RefWidth = FULL, seed: int = 0, sh_degree: int = 4, voxelize: bool = False, voxel_size: float = 0.002):
+    """Returns the reference's UN-STITCHED AnySplat encoder (`EncoderAnySplat`, AS/model/encoder/anysplat.py: DINOv2 patch embedding +
+    all DINO blocks + aggregator + heads; image [B, V, 3, H, W] in [0, 1] -> EncoderOutput), fp32, eval, seeded random init."""
+    return load_reference(width, seed=seed, sh_degree=sh_degree, voxelize=voxelize, voxel_size=voxel_size, _teacher=True)
+
+
 def load_reference(width: RefWidth = FULL, resolution: int = 512, seed: int = 0, sh_degree: int = 4, voxelize: bool = False,
-                   voxel_size: float = 0.002):
+                   voxel_size: float = 0.002, _teacher: bool = False):
     """Returns the reference StitchVAE3D (fp32, eval, checkpointing off) with seeded random init."""
     if not available():
         raise RuntimeError(f"{REFERENCE_ROOT} is not mounted here; the real reference can only be imported in the build container")
@@ -183,6 +189,10 @@ def load_reference(width: RefWidth = FULL, resolution: int = 512, seed: int = 0,
             gs_params_head_type="dpt_gs", pred_head_type="depth", voxelize=voxelize, intermediate_layer_idx=[4, 11, 17, 23])
         torch.manual_seed(seed)
         ff = anysplat_mod.AnySplat(cfg, dec_mod.DecoderSplattingCUDACfg("splatting_cuda", [1.0, 1.0, 1.0], False))
+        if _teacher:
+            enc = ff.encoder.float().eval()
+            enc.aggregator.use_checkpoint = False
+            return enc
         model = sm.StitchVAE3D(FakeVAE(), ff, torch.device("cpu"), "enc_blocks_2",
                                parse_conv_spec(f"conv3d_k5x3x3_o{W.embed_dim}_s1x2x2_p2x1x1"), resolution)
     finally:
@@ -205,7 +215,8 @@ def outputs_to_dict(out) -> dict:
     g = out.gaussians
     d = {"means": g.means, "covariances": g.covariances, "harmonics": g.harmonics, "opacities": g.opacities, "scales": g.scales,
          "rotations": g.rotations, "extrinsic": out.pred_context_pose["extrinsic"], "intrinsic": out.pred_context_pose["intrinsic"],
-         "depth": out.depth_dict["depth"], "last_pred_pose_enc": out.last_pred_pose_enc,
+         "depth": out.depth_dict["depth"],
+         "last_pred_pose_enc": out.last_pred_pose_enc if getattr(out, "last_pred_pose_enc", None) is not None else out.pred_pose_enc_list[-1],
          "scene_scale": out.infos["scene_scale"].reshape(1)}
     for i, p in enumerate(out.pred_pose_enc_list):
         d[f"pred_pose_enc_{i}"] = p

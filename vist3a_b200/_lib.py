@@ -46,6 +46,8 @@ EXPORTS = (
     "vist3a_fma_rows",
     "vist3a_bias_act_t",
     "vist3a_rgb_to_nhwc4pad",
+    "vist3a_rgb01_views_to_nhwc4pad",
+    "vist3a_patch_embed_im2col",
     "vist3a_pose_to_cameras",
     "vist3a_gaussian_epilogue",
     "vist3a_gaussian_adapter",
@@ -179,6 +181,8 @@ def load(build_if_missing: bool = False) -> C.CDLL:
     lib.vist3a_attention_small.argtypes = [vp, vp, i64, i64, i64, i64, f32, vp]
     lib.vist3a_fma_rows.argtypes = [vp, i64, vp, i64, vp, i64, vp, i64, i64, i64, vp]
     lib.vist3a_rgb_to_nhwc4pad.argtypes = [vp, i32, vp, i64, i64, i64, i64, vp]
+    lib.vist3a_rgb01_views_to_nhwc4pad.argtypes = [vp, i32, vp, i64, i64, i64, i64, vp]
+    lib.vist3a_patch_embed_im2col.argtypes = [vp, i32, vp, i64, i64, i64, i64, i32, C.POINTER(f32), C.POINTER(f32), vp]
     lib.vist3a_bias_act_t.argtypes = [vp, i64, vp, i32, vp, vp, i64, vp, i64, i64, i64, vp]
     lib.vist3a_pose_to_cameras.argtypes = [vp, vp, vp, vp, vp, vp, i64, i64, i64, vp]
     lib.vist3a_gaussian_epilogue.argtypes = [vp, i64, i64, vp, f32, vp, i64, vp, vp, vp, i64, i64, i64, i64, vp, vp, vp, vp, vp, vp,

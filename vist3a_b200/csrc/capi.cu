@@ -30,7 +30,8 @@ int depth_to_space_entry(const float*, float*, long long, long long, long long, 
 int attention_small_entry(const float*, float*, long long, long long, long long, long long, float, cudaStream_t);
 int bias_act_t_entry(const float*, long long, const float*, int, const float*, const float*, long long, float*, long long, long long,
                      long long, cudaStream_t);
-int rgb_to_nhwc4pad_entry(const void*, int, float*, long long, long long, long long, long long, cudaStream_t);
+int rgb_to_nhwc4pad_entry(const void*, int, float*, long long, long long, long long, long long, int, float, float, cudaStream_t);
+int patch_embed_im2col_entry(const void*, int, void*, long long, long long, long long, long long, int, const float*, const float*, cudaStream_t);
 int fma_rows_entry(float*, long long, const float*, long long, const float*, long long, const float*, long long, long long,
                    long long, cudaStream_t);
 int pose_to_cameras_entry(const float*, float*, float*, float*, float*, float*, long long, long long, long long, cudaStream_t);
@@ -257,7 +258,14 @@ int vist3a_bias_act_t(const float* ct, int64_t ldct, const float* bias, int32_t 
   return bias_act_t_entry(ct, ldct, bias, act, gate, residual, ldr, y, ldy, M, N, ST(stream));
 }
 int vist3a_rgb_to_nhwc4pad(const void* image, int32_t dtype, float* out, int64_t B, int64_t V, int64_t H, int64_t W, void* stream) {
-  return rgb_to_nhwc4pad_entry(image, dtype, out, B, V, H, W, ST(stream));
+  return rgb_to_nhwc4pad_entry(image, dtype, out, B, V, H, W, 0, 0.5f, 0.5f, ST(stream));
+}
+int vist3a_rgb01_views_to_nhwc4pad(const void* image, int32_t dtype, float* out, int64_t B, int64_t V, int64_t H, int64_t W, void* stream) {
+  return rgb_to_nhwc4pad_entry(image, dtype, out, B, V, H, W, 1, 1.0f, 0.0f, ST(stream));
+}
+int vist3a_patch_embed_im2col(const void* image, int32_t dtype, void* A, int64_t ldA, int64_t n_img, int64_t H, int64_t W, int32_t patch,
+                              const float* mean3, const float* std3, void* stream) {
+  return patch_embed_im2col_entry(image, dtype, A, ldA, n_img, H, W, patch, mean3, std3, ST(stream));
 }
 int vist3a_pose_to_cameras(const float* pose_raw, float* pose_act, float* extr, float* intr, float* c2w,
                            float* intr_norm, int64_t S, int64_t H, int64_t W, void* stream) {

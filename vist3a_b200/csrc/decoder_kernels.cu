@@ -76,10 +76,65 @@ int im2col_stitch_entry(const void* lat, int dt, void* A, long long B, long long
 }
 
 // ----------------------------------------------------------------------------------------
+// DINOv2 patch embedding as a GEMM: images [n_img, 3, H, W] in [0, 1] -> A [n_img * (H/p) * (W/p), ldA] bf16,
+//   A[(n, gy, gx), c*p*p + py*p + px] = (bf16(image[n, c, gy*p + py, gx*p + px]) - mean[c]) / std[c]    (columns >= 3 p^2 zero)
+// The stride-p, p x p convolution has no overlap, so its im2col is a permutation; one thread writes two consecutive k.
+// ----------------------------------------------------------------------------------------
+template <bool kF32>
+__global__ void __launch_bounds__(256) patch_embed_im2col_kernel(const void* __restrict__ img, __nv_bfloat16* __restrict__ A, long long ldA, int n_img,
+                                                                 int H, int W, int p, float m0, float m1, float m2, float s0, float s1, float s2) {
+  const int gh = H / p, gw = W / p;
+  const int K = 3 * p * p;
+  const long long pairs_per_row = ldA / 2;
+  const long long total = (long long)n_img * gh * gw * pairs_per_row;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const long long row = i / pairs_per_row;
+  const int k0 = (int)(i % pairs_per_row) * 2;
+  const int gx = (int)(row % gw), gy = (int)((row / gw) % gh);
+  const long long n = row / ((long long)gw * gh);
+  float v[2];
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    const int k = k0 + u;
+    float x = 0.f;
+    if (k < K) {
+      const int c = k / (p * p), r = k % (p * p), py = r / p, px = r % p;
+      const long long idx = ((n * 3 + c) * H + (gy * p + py)) * (long long)W + (gx * p + px);
+      // the reference casts the image to bf16 before normalising (anysplat.py:418: image.to(torch.bfloat16))
+      const float raw = kF32 ? __bfloat162float(__float2bfloat16_rn(reinterpret_cast<const float*>(img)[idx]))
+                             : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(img)[idx]);
+      const float m = c == 0 ? m0 : (c == 1 ? m1 : m2), sd = c == 0 ? s0 : (c == 1 ? s1 : s2);
+      x = __fdiv_rn(raw - m, sd);
+    }
+    v[u] = x;
+  }
+  *reinterpret_cast<uint32_t*>(A + row * ldA + k0) = pack_bf16(v[0], v[1]);
+}
+
+int patch_embed_im2col_entry(const void* img, int dt, void* A, long long ldA, long long n_img, long long H, long long W, int p, const float* mean,
+                             const float* std, cudaStream_t st) {
+  V3A_REQUIRE(img && A && mean && std && n_img > 0 && H > 0 && W > 0 && p > 0, VIST3A_ERR_INVALID, "patch_embed_im2col: bad arguments");
+  V3A_REQUIRE(H % p == 0 && W % p == 0, VIST3A_ERR_INVALID, "patch_embed_im2col: H and W must be multiples of the patch size %d", p);
+  V3A_REQUIRE(ldA % 8 == 0 && ldA >= 3ll * p * p, VIST3A_ERR_INVALID, "patch_embed_im2col: ldA must be a multiple of 8 and >= 3 p^2");
+  const long long total = n_img * (H / p) * (W / p) * (ldA / 2);
+  if (dt == VIST3A_DTYPE_F32)
+    patch_embed_im2col_kernel<true><<<grid_for(total, 256), 256, 0, st>>>(img, (__nv_bfloat16*)A, ldA, (int)n_img, (int)H, (int)W, p, mean[0], mean[1], mean[2],
+                                                                        std[0], std[1], std[2]);
+  else
+    patch_embed_im2col_kernel<false><<<grid_for(total, 256), 256, 0, st>>>(img, (__nv_bfloat16*)A, ldA, (int)n_img, (int)H, (int)W, p, mean[0], mean[1], mean[2],
+                                                                         std[0], std[1], std[2]);
+  V3A_CUDA_OK(cudaGetLastError());
+  launch_counter().fetch_add(1);
+  return VIST3A_OK;
+}
+
+// ----------------------------------------------------------------------------------------
 // RGB views [B,3,V,H,W] in [-1,1] -> zero-padded RGB0 NHWC image [B*V, H, W+8, 4] in [0,1] (3 zero pixels left, 5 right)
 // ----------------------------------------------------------------------------------------
 template <bool kF32>
-__global__ void __launch_bounds__(256) rgb_to_nhwc4pad_kernel(const void* __restrict__ img, float4* __restrict__ out, int B, int V, int H, int W) {
+__global__ void __launch_bounds__(256) rgb_to_nhwc4pad_kernel(const void* __restrict__ img, float4* __restrict__ out, int B, int V, int H, int W,
+                                                              int view_major, float scale, float offset) {
   const int Wp = W + 8;
   const long long total = (long long)B * V * H * Wp;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -92,23 +147,28 @@ __global__ void __launch_bounds__(256) rgb_to_nhwc4pad_kernel(const void* __rest
   const int x = xp - 3;
   if (x >= 0 && x < W) {
     const long long plane = (long long)H * W;
-    const long long base = (((long long)b * 3) * V + v) * plane + (long long)y * W + x;  // channel stride = V * plane
+    // [B,3,V,H,W]: channel stride V * plane;  [B,V,3,H,W] (view_major): channel stride plane
+    const long long base = (view_major ? ((long long)b * V + v) * 3 : ((long long)b * 3) * V + v) * plane + (long long)y * W + x;
+    const long long cstride = view_major ? plane : (long long)V * plane;
     float c[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-      const long long idx = base + (long long)k * V * plane;
+      const long long idx = base + (long long)k * cstride;
       c[k] = kF32 ? reinterpret_cast<const float*>(img)[idx] : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(img)[idx]);
     }
-    o = make_float4((c[0] + 1.0f) * 0.5f, (c[1] + 1.0f) * 0.5f, (c[2] + 1.0f) * 0.5f, 0.f);
+    o = make_float4(c[0] * scale + offset, c[1] * scale + offset, c[2] * scale + offset, 0.f);
   }
   out[i] = o;
 }
 
-int rgb_to_nhwc4pad_entry(const void* img, int dt, float* out, long long B, long long V, long long H, long long W, cudaStream_t st) {
+int rgb_to_nhwc4pad_entry(const void* img, int dt, float* out, long long B, long long V, long long H, long long W, int view_major, float scale,
+                          float offset, cudaStream_t st) {
   V3A_REQUIRE(img && out && B > 0 && V > 0 && H > 0 && W > 0, VIST3A_ERR_INVALID, "rgb_to_nhwc4pad: bad arguments");
   const long long total = B * V * H * (W + 8);
-  if (dt == VIST3A_DTYPE_F32) rgb_to_nhwc4pad_kernel<true><<<grid_for(total, 256), 256, 0, st>>>(img, (float4*)out, (int)B, (int)V, (int)H, (int)W);
-  else rgb_to_nhwc4pad_kernel<false><<<grid_for(total, 256), 256, 0, st>>>(img, (float4*)out, (int)B, (int)V, (int)H, (int)W);
+  if (dt == VIST3A_DTYPE_F32)
+    rgb_to_nhwc4pad_kernel<true><<<grid_for(total, 256), 256, 0, st>>>(img, (float4*)out, (int)B, (int)V, (int)H, (int)W, view_major, scale, offset);
+  else
+    rgb_to_nhwc4pad_kernel<false><<<grid_for(total, 256), 256, 0, st>>>(img, (float4*)out, (int)B, (int)V, (int)H, (int)W, view_major, scale, offset);
   V3A_CUDA_OK(cudaGetLastError());
   launch_counter().fetch_add(1);
   return VIST3A_OK;

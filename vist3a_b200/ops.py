@@ -322,6 +322,37 @@ def rgb_to_nhwc4pad(image: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def rgb01_views_to_nhwc4pad(image: torch.Tensor) -> torch.Tensor:
+    """image [B, V, 3, H, W] in [0, 1] -> zero-padded RGB0 image [B*V, H, W+8, 4] fp32 (un-stitched image -> 3DGS path)."""
+    _need_cuda(image)
+    image = image.contiguous()
+    B, V, Cc, H, W = image.shape
+    if Cc != 3:
+        raise ValueError("rgb01_views_to_nhwc4pad: expected 3 colour channels")
+    out = torch.empty((B * V, H, W + 8, 4), dtype=torch.float32, device=image.device)
+    L.check(L.load().vist3a_rgb01_views_to_nhwc4pad(image.data_ptr(), _dt(image), out.data_ptr(), B, V, H, W, _stream()))
+    return out
+
+
+# ImageNet statistics of AS/.../vggt/models/aggregator.py:29-30 as the reference model holds them: EncoderAnySplat casts the aggregator and its
+# buffers to bfloat16 (AS/model/encoder/anysplat.py:144), i.e. (0.485, 0.456, 0.406) / (0.229, 0.224, 0.225) rounded to bf16
+IMAGENET_MEAN, IMAGENET_STD = (0.484375, 0.455078125, 0.40625), (0.228515625, 0.2236328125, 0.224609375)
+
+
+def patch_embed_im2col(image: torch.Tensor, patch: int, k_pad: int) -> torch.Tensor:
+    """image [n, 3, H, W] in [0, 1] -> bf16 [n * (H/patch) * (W/patch), k_pad] operand of the patch-embedding GEMM
+    (ImageNet-normalised, k = c*p*p + py*p + px); see vist3a_patch_embed_im2col."""
+    _need_cuda(image)
+    image = image.contiguous()
+    n, Cc, H, W = image.shape
+    if Cc != 3:
+        raise ValueError("patch_embed_im2col: expected 3 colour channels")
+    A = torch.empty((n * (H // patch) * (W // patch), k_pad), dtype=torch.bfloat16, device=image.device)
+    mean, std = (C.c_float * 3)(*IMAGENET_MEAN), (C.c_float * 3)(*IMAGENET_STD)
+    L.check(L.load().vist3a_patch_embed_im2col(image.data_ptr(), _dt(image), A.data_ptr(), k_pad, n, H, W, patch, mean, std, _stream()))
+    return A
+
+
 def im2col_nhwc(x: torch.Tensor, kh: int, kw: int, stride: int, pad: int, k_pad: Optional[int] = None) -> torch.Tensor:
     """x NHWC fp32 -> [n*ho*wo, k_pad] fp32 with column (dy*kw+dx)*C + c (zero beyond kh*kw*C)."""
     _need_cuda(x)
@@ -561,7 +592,8 @@ class OpTimer:
                  "rmsnorm_rope_": io_cost("rmsnorm_rope"), "row_rinv": io_cost("rmsnorm_rope"), "modulation": io_cost("small"), "skinny_linear": io_cost("small"),
                  "timestep_features": io_cost("small"), "patchify": io_cost("small"), "unpatchify": io_cost("small"),
                  "cfg_combine": io_cost("small"), "axpby_n": io_cost("small"), "im2col_stitch": io_cost("im2col"),
-                 "im2col_nhwc": io_cost("im2col"), "rgb_to_nhwc4pad": io_cost("small"), "qknorm_rope2d_": io_cost("qknorm_rope2d"), "bilinear_nhwc": io_cost("bilinear"),
+                 "im2col_nhwc": io_cost("im2col"), "rgb_to_nhwc4pad": io_cost("small"), "rgb01_views_to_nhwc4pad": io_cost("small"),
+                 "patch_embed_im2col": io_cost("im2col"), "qknorm_rope2d_": io_cost("qknorm_rope2d"), "bilinear_nhwc": io_cost("bilinear"),
                  "depth_to_space": io_cost("depth_to_space"), "attention_small": io_cost("small"), "fma_rows": io_cost("small"),
                  "pose_to_cameras": io_cost("small"), "linear_tokens16": io_cost("linear_tokens16"), "gaussian_epilogue": io_cost("gaussian_epilogue")}
         for name, cost in table.items():

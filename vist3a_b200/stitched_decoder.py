@@ -79,6 +79,8 @@ class DecoderConfig:
     latent_channels: int = 16
     inter_layers: Tuple[int, ...] = (4, 11, 17, 23)
     resolution: int = 512  # video resolution; the VAE latent grid is resolution / 8
+    patch_embed: bool = False  # un-stitched AnySplat encoder: DINOv2 patch embedding (image input, `forward_images`) instead of the stitching
+                               # layer; dino_blocks then counts ALL DINO blocks (24 in the released model)
     voxelize: bool = False   # EncoderAnySplatCfg.voxelize (AS/model/encoder/anysplat.py:125; true in config/experiment/*.yaml)
     voxel_size: float = 0.002  # config/experiment/dl3dv.yaml:20
 
@@ -118,7 +120,12 @@ def param_shapes(cfg: DecoderConfig) -> Dict[str, Tuple[int, ...]]:
     """Parameter manifest of the stitched decoder under the reference's state-dict keys (what a real
     `anysplat_stitched.pth` + AnySplat checkpoint provide; tests check it against the oracle's manifest)."""
     C, C2, Fd, oc = cfg.embed_dim, 2 * cfg.embed_dim, cfg.dpt_features, cfg.dpt_out_channels
-    s: Dict[str, Tuple[int, ...]] = {"stitching_layer.weight": (C, cfg.latent_channels, 5, 3, 3), "stitching_layer.bias": (C,)}
+    s: Dict[str, Tuple[int, ...]] = {}
+    if cfg.patch_embed:   # AS/.../layers/patch_embed.py:65 (Conv2d k = s = patch)
+        s[E + "aggregator.patch_embed.patch_embed.proj.weight"] = (C, 3, cfg.patch, cfg.patch)
+        s[E + "aggregator.patch_embed.patch_embed.proj.bias"] = (C,)
+    else:
+        s["stitching_layer.weight"], s["stitching_layer.bias"] = (C, cfg.latent_channels, 5, 3, 3), (C,)
 
     def lin(name, n, k):
         s[name + ".weight"], s[name + ".bias"] = (n, k), (n,)
@@ -254,10 +261,16 @@ class StitchVAE3DB200(torch.nn.Module):
         def bf(t):
             return t.detach().float().to(dev, torch.bfloat16).contiguous()
 
-        self.stitching_layer = SimpleNamespace(weight=sd["stitching_layer.weight"], bias=sd["stitching_layer.bias"])
-        w["stitch.w"] = bf(sd["stitching_layer.weight"].reshape(C, -1))  # k = c*45 + kt*9 + ky*3 + kx
-        w["stitch.b"] = f32(sd["stitching_layer.bias"])
         pe = E + "aggregator.patch_embed."
+        if cfg.patch_embed:
+            pw = sd[pe + "patch_embed.proj.weight"].detach().float().reshape(C, -1)     # k = c*p*p + py*p + px
+            self._pe_k = (pw.shape[1] + 7) // 8 * 8                                      # 588 -> 592 (16-byte TMA row stride)
+            w["pe.w"] = bf(F.pad(pw, (0, self._pe_k - pw.shape[1])))
+            w["pe.b"] = f32(sd[pe + "patch_embed.proj.bias"])
+        else:
+            self.stitching_layer = SimpleNamespace(weight=sd["stitching_layer.weight"], bias=sd["stitching_layer.bias"])
+            w["stitch.w"] = bf(sd["stitching_layer.weight"].reshape(C, -1))  # k = c*45 + kt*9 + ky*3 + kx
+            w["stitch.b"] = f32(sd["stitching_layer.bias"])
         self._pos_embed = sd[pe + "pos_embed"].detach().float().cpu()
         self._cls = sd[pe + "cls_token"].detach().float().cpu().reshape(1, C)
         self._reg = sd[pe + "register_tokens"].detach().float().cpu().reshape(4, C)
@@ -389,11 +402,15 @@ class StitchVAE3DB200(torch.nn.Module):
     def _aggregate(self, latent: torch.Tensor, H: int, W: int) -> List[torch.Tensor]:
         cfg, w, dev = self.cfg, self.w, self.device
         C = cfg.embed_dim
-        B, _, T, lh, lw = latent.shape
-        V = (T - 1) * 4 + 1
-        gh, gw = lh // 2, lw // 2
-        if (gh, gw) != (H // cfg.patch, W // cfg.patch):
-            raise ValueError(f"latent grid {lh}x{lw} -> {gh}x{gw} tokens does not match the {H}x{W} image ({H // cfg.patch}x{W // cfg.patch} patches)")
+        if cfg.patch_embed:   # `latent` is the image batch [B, V, 3, H, W] in [0, 1]
+            B, V = latent.shape[:2]
+            gh, gw = H // cfg.patch, W // cfg.patch
+        else:
+            B, _, T, lh, lw = latent.shape
+            V = (T - 1) * 4 + 1
+            gh, gw = lh // 2, lw // 2
+            if (gh, gw) != (H // cfg.patch, W // cfg.patch):
+                raise ValueError(f"latent grid {lh}x{lw} -> {gh}x{gw} tokens does not match the {H}x{W} image ({H // cfg.patch}x{W // cfg.patch} patches)")
         npatch = gh * gw
         P = npatch + N_SPECIAL
         BV = B * V
@@ -406,8 +423,13 @@ class StitchVAE3DB200(torch.nn.Module):
         pmap = (npatch, P, N_SPECIAL)  # patch-token rows of the [BV*P] stream
         # --- stitching conv: upsample + replicate pad + im2col, then one GEMM (+bias +pos-embed) into the patch rows
         x = torch.empty((rows, C), dtype=torch.float32, device=dev)
-        a = ops.im2col_stitch(latent)
-        ops.gemm(a, w["stitch.w"], w["stitch.b"], out=x, residual=tb.pos, rmap=(npatch, 0, 0), cmap=pmap)
+        if cfg.patch_embed:
+            # DINOv2 patch embedding: normalise + im2col (a permutation: the 14x14 patches do not overlap), then one GEMM (+bias +pos-embed)
+            a = ops.patch_embed_im2col(latent.reshape(B * V, 3, H, W), cfg.patch, self._pe_k)
+            ops.gemm(a, w["pe.w"], w["pe.b"], out=x, residual=tb.pos, rmap=(npatch, 0, 0), cmap=pmap)
+        else:
+            a = ops.im2col_stitch(latent)
+            ops.gemm(a, w["stitch.w"], w["stitch.b"], out=x, residual=tb.pos, rmap=(npatch, 0, 0), cmap=pmap)
         del a
         x.view(BV, P, C)[:, :N_SPECIAL].copy_(tb.special)
         # --- DINOv2 blocks (eps 1e-6, no QK norm / RoPE), sequences = views
@@ -550,7 +572,9 @@ class StitchVAE3DB200(torch.nn.Module):
             raise NotImplementedError("the B200 decoder is an inference engine (train=False)")
         if not self.w:
             raise RuntimeError("weights not loaded: use StitchVAE3DB200.from_state_dict(...)")
-        cfg, w, dev = self.cfg, self.w, self.device
+        if self.cfg.patch_embed:
+            raise RuntimeError("this engine was built with DecoderConfig.patch_embed (un-stitched encoder): call forward_images(image)")
+        cfg, dev = self.cfg, self.device
         B, ci, V, H, W = feedforward_image.shape
         if latent.dtype not in (torch.float32, torch.bfloat16):
             latent = latent.float()
@@ -560,6 +584,27 @@ class StitchVAE3DB200(torch.nn.Module):
         lat_hw = cfg.resolution // 8
         if latent.shape[-2:] != (lat_hw, lat_hw):  # upsampling_layer also resizes H, W to resolution/8 (stitched_model.py:92-107)
             raise NotImplementedError(f"latent grid {tuple(latent.shape[-2:])} != resolution/8 = {lat_hw}: spatial resampling is not on the hot path")
+        return self._decode(latent, feedforward_image, B, V, H, W)
+
+    @torch.no_grad()
+    def forward_images(self, image: torch.Tensor) -> EncoderOutput:
+        """Un-stitched AnySplat encoder, image -> 3D Gaussians (drop-in for `EncoderAnySplat.forward(image)`,
+        AS/model/encoder/anysplat.py:337-610): image [B, V, 3, H, W] in [0, 1], H and W multiples of 14.  Needs an engine built
+        with DecoderConfig(patch_embed=True, dino_blocks=<all DINO blocks>) from a state dict that holds the patch-embedding conv."""
+        if not self.cfg.patch_embed:
+            raise RuntimeError("this engine was built for the stitched path: call forward_with_latent(latent, feedforward_image)")
+        if not self.w:
+            raise RuntimeError("weights not loaded: use StitchVAE3DB200.from_state_dict(...)")
+        B, V, ci, H, W = image.shape
+        if ci != 3 or H % self.cfg.patch or W % self.cfg.patch:
+            raise ValueError(f"image {tuple(image.shape)}: expected [B, V, 3, H, W] with H, W multiples of {self.cfg.patch}")
+        if image.dtype not in (torch.float32, torch.bfloat16):
+            image = image.float()
+        image = image.to(self.device).contiguous()
+        return self._decode(image, image, B, V, H, W)
+
+    def _decode(self, latent: torch.Tensor, feedforward_image: torch.Tensor, B: int, V: int, H: int, W: int) -> EncoderOutput:
+        cfg, w, dev = self.cfg, self.w, self.device
         gh, gw = H // cfg.patch, W // cfg.patch
         P = gh * gw + N_SPECIAL
         BV = B * V
@@ -578,7 +623,10 @@ class StitchVAE3DB200(torch.nn.Module):
         # --- Gaussian head
         if feedforward_image.dtype not in (torch.float32, torch.bfloat16):
             feedforward_image = feedforward_image.float()
-        rgb = ops.rgb_to_nhwc4pad(feedforward_image.to(dev))              # [BV, H, W+8, 4] in [0, 1], rows zero-padded
+        if cfg.patch_embed:
+            rgb = ops.rgb01_views_to_nhwc4pad(feedforward_image)          # image already in [0, 1], [B, V, 3, H, W]
+        else:
+            rgb = ops.rgb_to_nhwc4pad(feedforward_image.to(dev))          # [BV, H, W+8, 4] in [0, 1], rows zero-padded
         merged = torch.empty((BV * H * W, w["gh.merger.w"].shape[0]), dtype=torch.float32, device=dev)
         ops.gemm(rgb, w["gh.merger.w"], w["gh.merger.b"], act="relu", out=merged,
                  conv=dict(kh=7, kw=1, pad=3, pad_x=0, geom=(BV, H, W, 32), strides=(4, (W + 8) * 4, H * (W + 8) * 4)))
