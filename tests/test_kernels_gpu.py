@@ -85,6 +85,27 @@ def test_gemm_gate_residual_fp32_stream(ops):
     assert _rel_l2(outb.float(), refb.float()) < 4e-3
 
 
+@pytest.mark.parametrize("M,N,K,f32out", [(8192, 1536, 512, False), (8192, 1528, 256, True), (8192, 1536, 1536, False), (4000, 1400, 320, True)])
+def test_gemm_176_wide_tiles_match_256_wide(ops, M, N, K, f32out):
+    """N ~ 1536 on 74 CTA pairs: the launcher takes 176-wide column tiles (4 full waves instead of 2.6 of 256-wide ones); same results,
+    incl. the 16-column last chunk of a tile, the partial last tile, bias / gate / residual epilogues and both output types."""
+    g = torch.Generator(device="cuda").manual_seed(N + K)
+    a = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    w = (torch.randn(N, K, device="cuda", generator=g) / math.sqrt(K)).bfloat16()
+    bias = torch.randn(N, device="cuda", generator=g)
+    gate = torch.randn(2, N, device="cuda", generator=g)
+    res = torch.randn(M, N, device="cuda", generator=g)
+    res = res if f32out else res.bfloat16()
+    kw = dict(gate=gate, gate_bstride=N, rows_per_batch=M // 2, residual=res, round_linear=True, two_cta=True,
+              out_dtype=torch.float32 if f32out else torch.bfloat16)
+    o176 = ops.gemm(a, w, bias, **kw)
+    o256 = ops.gemm(a, w, bias, bn256=True, **kw)
+    assert torch.equal(o176, o256)   # same MMAs per element (K order identical), same epilogue arithmetic
+    lin = (a.float() @ w.float().t() + bias).bfloat16().float()
+    ref = res.float() + lin * gate.repeat_interleave(M // 2, 0)
+    assert _rel_l2(o176.float(), ref) < (2e-3 if f32out else 6e-3)
+
+
 @pytest.mark.parametrize("M,N,K", [(1024, 256, 512), (500, 136, 72), (4096, 32, 1152)])
 def test_gemm_tf32(ops, M, N, K):
     g = torch.Generator(device="cuda").manual_seed(3)

@@ -28,7 +28,9 @@ def launches(path, title):
         if len(r) < len(hdr):
             continue
         name = r[ix["Kernel Name"]].split("(")[0].replace("void ", "")[:80]
-        v = float(r[ix["Metric Value"]])
+        if r[ix["Metric Name"]] != "gpu__time_duration.sum":
+            continue
+        v = float(r[ix["Metric Value"]].replace(",", ""))
         u = r[ix["Metric Unit"]]
         v = v / 1e3 if u == "ns" else v * 1e3 if u == "ms" else v
         agg[name][0] += 1
@@ -67,13 +69,14 @@ def main():
     tag = sys.argv[1]
     os.makedirs(OUT, exist_ok=True)
     for stem, title in (("launches", "one eager denoise step of bench.py (cond+uncond DiT forward at L=4096, CFG, UniPC)"),
-                        ("launches_decoder", "one stitched-decoder forward (13 views x 448x448)")):
+                        ("launches_decoder", "one stitched-decoder forward (13 views x 448x448)"),
+                        ("launches_voxel", "one voxelised fusion of 2 609 152 points x 83 features (32 launches; radix passes beyond the key width exit at once)")):
         p = os.path.join(GP, f"{stem}_{tag}.csv")
         if os.path.exists(p):
             name = "launches_dit_step" if stem == "launches" else stem
             open(os.path.join(OUT, f"{tag}_{name}.txt"), "w").write(launches(p, title))
     tr = {}
-    for stem, key in (("fmha", "fmha_tcgen05"), ("fmha64", None), ("gemm", "gemm_tcgen05"), ("gemm_tf32conv", None), ("gauss", "gaussian_epilogue")):
+    for stem, key in (("fmha", "fmha_tcgen05"), ("fmha64", None), ("gemm", "gemm_tcgen05"), ("gemm_tf32conv", None), ("gauss", "gaussian_epilogue"), ("voxel", "voxel_reduce")):
         rep = os.path.join(GP, f"{stem}_{tag}.ncu-rep")
         if os.path.exists(rep):
             open(os.path.join(OUT, f"{tag}_ncu_{stem}.txt"), "w").write(ncu_text(rep))

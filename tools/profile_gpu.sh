@@ -17,4 +17,8 @@ ncu --set full --clock-control none --import-source on -k regex:gemm_tcgen05 -s 
     python tools/kernel_bench.py --only dit_ffn1 --iters 2 --no-torch --no-flush > gpurun_out/ncu_gemm_${tag}.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:gaussian_epilogue -c 1 -o gpurun_out/gauss_${tag} -f \
     python tools/decoder_profile.py --ncu-all > gpurun_out/ncu_gauss_${tag}.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:voxel_reduce -s 2 -c 1 -o gpurun_out/voxel_${tag} -f \
+    python tools/kernel_bench.py --only voxel --iters 2 --no-torch --no-flush > gpurun_out/ncu_voxel_${tag}.log 2>&1
+ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:'voxel|radix|seg_' -s 64 -c 32 --csv \
+    --log-file gpurun_out/launches_voxel_${tag}.csv python tools/kernel_bench.py --only voxel --no-torch --iters 2 > gpurun_out/launches_voxel_${tag}.log 2>&1
 ls -la gpurun_out/*_${tag}.ncu-rep gpurun_out/launches*_${tag}.csv

@@ -61,9 +61,11 @@ struct GemmCfg {
   static constexpr int B_BYTES = BN_LOCAL * 128;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 8 ? 8 : (200 * 1024) / STAGE_BYTES;
-  static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;  // two accumulator stages
+  static constexpr int TMEM_COLS = 2 * BN <= 32 ? 32 : 2 * BN <= 64 ? 64 : 2 * BN <= 128 ? 128 : 2 * BN <= 256 ? 256 : 512;  // two accumulator stages
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
-  static_assert(BN == 64 || BN == 128 || BN == 256, "BN");
+  // BN = 176 (pairs only): 9 column tiles of a 1536-wide output fill 4 waves of 74 CTA pairs to 97 % (6 tiles of 256: 3 waves at 86 %)
+  static_assert(BN == 64 || BN == 128 || BN == 256 || (BN == 176 && kCta == 2), "BN");
+  static_assert(BN % 16 == 0 && BN_LOCAL % 8 == 0, "MMA N granularity (16) / swizzle atom rows (8)");
   static_assert(TMEM_COLS <= 512, "TMEM");
 };
 
@@ -252,7 +254,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     // Two warps per TMEM lane quadrant: warp w reads lanes [32 (w%4), +32) and every other 32-column chunk.
     const uint32_t q = warp & 3u;
     const int half = (int)((warp - 4u) >> 2);
-    constexpr int NCHUNK = BN / 32;
+    constexpr int NCHUNK = (BN + 31) / 32;  // BN = 176: the last chunk holds 16 columns (the TMEM read runs into the other stage, unused)
     int as = 0;
     uint32_t aph = 0;
     for (int tile = worker; tile < num_tiles; tile += num_workers) {
@@ -293,7 +295,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         // prefetch the next chunk of this warp while this one is processed
         if (c + 2 < NCHUNK && n0 + 64 < shape.N) tmem_ld_x32(taddr + (uint32_t)((c + 2) * 32), r);
         if (row_ok) {
-          const int ncols = min(32, shape.N - n0);
+          const int ncols = min(min(32, shape.N - n0), n_tile + BN - n0);
           if (ep.bias) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
@@ -442,7 +444,17 @@ static int launch_gemm(const vist3a_gemm_args& a, cudaStream_t stream) {
 template <bool kTF32>
 static int dispatch_gemm(const vist3a_gemm_args& a, cudaStream_t stream) {
   const bool two = (a.flags & VIST3A_GEMM_FLAG_2CTA) && !(a.flags & VIST3A_GEMM_FLAG_1CTA) && a.M > 128;
-  if (a.N > 128) return two ? launch_gemm<256, 2, kTF32>(a, stream) : launch_gemm<256, 1, kTF32>(a, stream);
+  if (a.N > 128) {
+    if (two && !a.conv.enabled && !(a.flags & VIST3A_GEMM_FLAG_BN256)) {
+      // wave quantisation: cost ~ waves x tile width over the CTA pairs; take 176-wide tiles when they save more than 3 %.
+      // Measured on B200 (tools/kernel_bench.py, 8192 x 1536 outputs): +2.8 % at K = 1536, -1.3 % at K = 8960 -- a 176-wide tile pulls
+      // 77 B/clk/SM of operands through L2 instead of 62.5, which costs more than the fuller last wave returns on long K loops.
+      const long long pairs = num_sms() / 2, tm = (a.M + 255) / 256;
+      auto cost = [&](long long bn) { return ((tm * ((a.N + bn - 1) / bn) + pairs - 1) / pairs) * bn; };
+      if (a.K <= 2048 && cost(176) * 103 < cost(256) * 100) return launch_gemm<176, 2, kTF32>(a, stream);
+    }
+    return two ? launch_gemm<256, 2, kTF32>(a, stream) : launch_gemm<256, 1, kTF32>(a, stream);
+  }
   if (a.N > 64) return two ? launch_gemm<128, 2, kTF32>(a, stream) : launch_gemm<128, 1, kTF32>(a, stream);
   return launch_gemm<64, 1, kTF32>(a, stream);
 }
