@@ -87,8 +87,8 @@ def test_gemm_gate_residual_fp32_stream(ops):
 
 @pytest.mark.parametrize("M,N,K,f32out", [(8192, 1536, 512, False), (8192, 1528, 256, True), (8192, 1536, 1536, False), (4000, 1400, 320, True)])
 def test_gemm_176_wide_tiles_match_256_wide(ops, M, N, K, f32out):
-    """N ~ 1536 on 74 CTA pairs: the launcher takes 176-wide column tiles (4 full waves instead of 2.6 of 256-wide ones); same results,
-    incl. the 16-column last chunk of a tile, the partial last tile, bias / gate / residual epilogues and both output types."""
+    """N ~ 1536 on 74 CTA pairs: the 176-wide column tiles of the A/B flag (4 full waves instead of 2.6 of 256-wide ones) give the same
+    results, incl. the 16-column last chunk of a tile, the partial last tile, bias / gate / residual epilogues and both output types."""
     g = torch.Generator(device="cuda").manual_seed(N + K)
     a = torch.randn(M, K, device="cuda", generator=g).bfloat16()
     w = (torch.randn(N, K, device="cuda", generator=g) / math.sqrt(K)).bfloat16()
@@ -98,8 +98,8 @@ def test_gemm_176_wide_tiles_match_256_wide(ops, M, N, K, f32out):
     res = res if f32out else res.bfloat16()
     kw = dict(gate=gate, gate_bstride=N, rows_per_batch=M // 2, residual=res, round_linear=True, two_cta=True,
               out_dtype=torch.float32 if f32out else torch.bfloat16)
-    o176 = ops.gemm(a, w, bias, **kw)
-    o256 = ops.gemm(a, w, bias, bn256=True, **kw)
+    o176 = ops.gemm(a, w, bias, bn176=True, **kw)
+    o256 = ops.gemm(a, w, bias, **kw)
     assert torch.equal(o176, o256)   # same MMAs per element (K order identical), same epilogue arithmetic
     lin = (a.float() @ w.float().t() + bias).bfloat16().float()
     ref = res.float() + lin * gate.repeat_interleave(M // 2, 0)

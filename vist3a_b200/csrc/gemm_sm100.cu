@@ -39,7 +39,11 @@ struct GemmEpilogue {
   int act, post_act;
   int round_linear;
   int round_gate;
+  long long* trace;  // debug (v3a_debug_gemm_trace): 8 cycle counters per CTA, normally null
 };
+
+static long long* g_gemm_trace = nullptr;
+extern "C" void v3a_debug_gemm_trace(void* buf) { g_gemm_trace = reinterpret_cast<long long*>(buf); }
 
 constexpr int kConvTW = 16, kConvTH = 8;  // pixel patch of one 128-row A tile
 
@@ -62,8 +66,10 @@ struct GemmCfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 8 ? 8 : (200 * 1024) / STAGE_BYTES;
   static constexpr int TMEM_COLS = 2 * BN <= 32 ? 32 : 2 * BN <= 64 ? 64 : 2 * BN <= 128 ? 128 : 2 * BN <= 256 ? 256 : 512;  // two accumulator stages
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
-  // BN = 176 (pairs only): 9 column tiles of a 1536-wide output fill 4 waves of 74 CTA pairs to 97 % (6 tiles of 256: 3 waves at 86 %)
+  static constexpr int STAGING_BYTES = 8 * 32 * 128;   // per epilogue warp: 32 rows x 128 bytes
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + STAGING_BYTES;
+  static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
+  // BN = 176 (pairs only, A/B flag): 9 column tiles of a 1536-wide output fill 4 waves of 74 CTA pairs to 97 % (6 tiles of 256: 3 waves at 86 %)
   static_assert(BN == 64 || BN == 128 || BN == 256 || (BN == 176 && kCta == 2), "BN");
   static_assert(BN % 16 == 0 && BN_LOCAL % 8 == 0, "MMA N granularity (16) / swizzle atom rows (8)");
   static_assert(TMEM_COLS <= 512, "TMEM");
@@ -177,6 +183,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     // coordinates / descriptors stay in uniform registers (no per-instruction R2UR + elect waterfall).
     int s = 0;
     uint32_t ph = 0;
+    long long tr_wait = 0;
+    const long long tr_t0 = ep.trace ? clock64() : 0;
     for (int tile = worker; tile < num_tiles; tile += num_workers) {
       const int tm = tile % shape.tiles_m, tn = tile / shape.tiles_m;
       const int mt = tm * kCta + (int)rank;  // this CTA's 128-row tile
@@ -192,7 +200,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
       int cb = 0, dy = 0, dx = 0;
       for (int kb = 0; kb < num_kb; ++kb) {
-        mbar_wait(empty_bar(s), ph ^ 1u);
+        if (ep.trace) {
+          const long long t1 = clock64();
+          mbar_wait(empty_bar(s), ph ^ 1u);
+          tr_wait += clock64() - t1;
+        } else {
+          mbar_wait(empty_bar(s), ph ^ 1u);
+        }
         if (elect_one()) {
           if constexpr (kCta == 1) {
             mbar_expect_tx(full_bar(s), Cfg::STAGE_BYTES);
@@ -214,6 +228,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
       }
     }
+    if (ep.trace && lane == 0) {
+      ep.trace[blockIdx.x * 8 + 0] = clock64() - tr_t0;  // producer: total
+      ep.trace[blockIdx.x * 8 + 1] = tr_wait;            // producer: waiting for a free stage
+    }
   } else if (warp == 1) {
     // ------------------------------ MMA issuer (same scheme: uniform control flow, elected issue) -------------
     if (leader) {
@@ -222,12 +240,26 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       uint32_t ph = 0;
       int as = 0;
       uint32_t aph = 0;
+      long long tr_full = 0, tr_tempty = 0;
+      const long long tr_t0 = ep.trace ? clock64() : 0;
       for (int tile = worker; tile < num_tiles; tile += num_workers) {
-        mbar_wait(tempty_bar(as), aph ^ 1u);
+        if (ep.trace) {
+          const long long t1 = clock64();
+          mbar_wait(tempty_bar(as), aph ^ 1u);
+          tr_tempty += clock64() - t1;
+        } else {
+          mbar_wait(tempty_bar(as), aph ^ 1u);
+        }
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
         for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(full_bar(s), ph);
+          if (ep.trace) {
+            const long long t1 = clock64();
+            mbar_wait(full_bar(s), ph);
+            tr_full += clock64() - t1;
+          } else {
+            mbar_wait(full_bar(s), ph);
+          }
           tc_fence_after();
           if (elect_one()) {
             const uint64_t adesc = make_smem_desc_sw128(smem_a(s), 1024, 0);
@@ -248,15 +280,23 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
         if (++as == 2) { as = 0; aph ^= 1u; }
       }
+      if (ep.trace && lane == 0) {
+        ep.trace[blockIdx.x * 8 + 2] = clock64() - tr_t0;  // MMA warp: total
+        ep.trace[blockIdx.x * 8 + 3] = tr_full;            // MMA warp: waiting for operands (TMA)
+        ep.trace[blockIdx.x * 8 + 4] = tr_tempty;          // MMA warp: waiting for a free accumulator stage (epilogue)
+      }
     }
   } else if (warp >= 4) {
     // ------------------------------ epilogue ------------------------------
     // Two warps per TMEM lane quadrant: warp w reads lanes [32 (w%4), +32) and every other 32-column chunk.
     const uint32_t q = warp & 3u;
     const int half = (int)((warp - 4u) >> 2);
+    const uint32_t stage_base = bar_base + 256u + (warp - 4u) * 4096u;  // this warp's staging buffer
     constexpr int NCHUNK = (BN + 31) / 32;  // BN = 176: the last chunk holds 16 columns (the TMEM read runs into the other stage, unused)
     int as = 0;
     uint32_t aph = 0;
+    long long tr_tfull = 0;
+    const long long tr_t0 = ep.trace ? clock64() : 0;
     for (int tile = worker; tile < num_tiles; tile += num_workers) {
       const int tm = tile % shape.tiles_m, tn = tile / shape.tiles_m;
       const int mt = tm * kCta + (int)rank;
@@ -279,23 +319,52 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const float* gate_row = ep.gate ? ep.gate + b * ep.gate_bstride : nullptr;
       const long long crow = row_ok ? ep.cmap(row) : 0;
       const long long rrow = (row_ok && ep.residual) ? ep.rmap(row) : 0;
-      mbar_wait(tfull_bar(as), aph);
+      if (ep.trace) {
+        const long long t1 = clock64();
+        mbar_wait(tfull_bar(as), aph);
+        tr_tfull += clock64() - t1;
+      } else {
+        mbar_wait(tfull_bar(as), aph);
+      }
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((q * 32u) << 16) + (uint32_t)(as * BN);
+      // Chunk k of this warp.  bf16 output: the two warps of a lane quadrant take alternating PAIRS of adjacent 32-column chunks
+      // (0,1,4,5 | 2,3,6,7), so a warp stages 64 columns = one full 128-byte line per row before it writes; fp32 output (and BN = 64):
+      // one 32-column chunk at a time.
+      constexpr bool kPairs = NCHUNK >= 4;
+      auto chunk_of = [&](int k) { return kPairs ? (k >> 1) * 4 + half * 2 + (k & 1) : 2 * k + half; };
+      auto chunk_ok = [&](int k) { const int c = chunk_of(k); return c < NCHUNK && n_tile + c * 32 < shape.N; };
       uint32_t r[32];
-      if (n_tile + half * 32 < shape.N) tmem_ld_x32(taddr + (uint32_t)(half * 32), r);
+      if (chunk_ok(0)) tmem_ld_x32(taddr + (uint32_t)(chunk_of(0) * 32), r);
+      bool released = false;
+      int blk_n0 = 0, blk_bytes = 0;  // first column / valid bytes per row of the block being staged
 #pragma unroll 1
-      for (int c = half; c < NCHUNK; c += 2) {
-        const int n0 = n_tile + c * 32;
-        if (n0 >= shape.N) break;  // warp-uniform
+      for (int k = 0; chunk_ok(k); ++k) {
+        const int n0 = n_tile + chunk_of(k) * 32;
         tmem_ld_wait();
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-        // prefetch the next chunk of this warp while this one is processed
-        if (c + 2 < NCHUNK && n0 + 64 < shape.N) tmem_ld_x32(taddr + (uint32_t)((c + 2) * 32), r);
+        // prefetch the next chunk of this warp while this one is processed; after the last read the accumulator stage goes back to
+        // the MMA warp at once (the arithmetic and the stores below no longer need it)
+        const bool more = chunk_ok(k + 1);
+        if (more) {
+          tmem_ld_x32(taddr + (uint32_t)(chunk_of(k + 1) * 32), r);
+        } else {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if constexpr (kCta == 1) mbar_arrive(tempty_bar(as)); else mbar_arrive_cluster(tempty_bar(as), 0);
+          }
+          released = true;
+        }
+        const int ncols = min(min(32, shape.N - n0), n_tile + BN - n0);
+        const int es = ep.out_fp32 ? 4 : 2;
+        const bool first_of_block = ep.out_fp32 || !kPairs || (k & 1) == 0;
+        if (first_of_block) { blk_n0 = n0; blk_bytes = 0; }
+        const uint32_t srow = stage_base + lane * 128u;
+        const uint32_t byte0 = (uint32_t)blk_bytes;  // offset of this chunk inside the staged row (0 or 64)
         if (row_ok) {
-          const int ncols = min(min(32, shape.N - n0), n_tile + BN - n0);
           if (ep.bias) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
@@ -323,42 +392,73 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               for (int j = 0; j < 32; ++j) v[j] = bf16_round(v[j]);
             }
           }
+          // stage the finished values in this warp's 32 x 128-byte buffer (16-byte pieces XOR-swizzled by the row: conflict-free
+          // both for these per-row writes and for the row-contiguous reads below)
           if (ep.out_fp32) {
             if (ep.residual) add_row32<true>(v, ep.residual, rrow * ep.ldr + n0, ncols);
             if (ep.residual2) add_row32<true>(v, ep.residual2, crow * ep.ldc + n0, ncols);
             if (ep.post_act == VIST3A_ACT_RELU) act32<VIST3A_ACT_RELU>(v);
-            float* cp = reinterpret_cast<float*>(ep.C) + crow * ep.ldc + n0;
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
-              if (j < ncols) *reinterpret_cast<float4*>(cp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+              if (j < ncols) {
+                const uint32_t piece = (uint32_t)(j >> 2);
+                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(srow + ((piece ^ (lane & 7u)) << 4)), "f"(v[j]), "f"(v[j + 1]),
+                             "f"(v[j + 2]), "f"(v[j + 3])
+                             : "memory");
+              }
             }
           } else {
             if (ep.residual) add_row32<false>(v, ep.residual, rrow * ep.ldr + n0, ncols);
             if (ep.residual2) add_row32<false>(v, ep.residual2, crow * ep.ldc + n0, ncols);
             if (ep.post_act == VIST3A_ACT_RELU) act32<VIST3A_ACT_RELU>(v);
-            __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(ep.C) + crow * ep.ldc + n0;
 #pragma unroll
             for (int j = 0; j < 32; j += 8) {
               if (j < ncols) {
-                uint4 o;
-                o.x = pack_bf16(v[j], v[j + 1]);
-                o.y = pack_bf16(v[j + 2], v[j + 3]);
-                o.z = pack_bf16(v[j + 4], v[j + 5]);
-                o.w = pack_bf16(v[j + 6], v[j + 7]);
-                *reinterpret_cast<uint4*>(cp + j) = o;
+                const uint32_t piece = (byte0 >> 4) + (uint32_t)(j >> 3);
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow + ((piece ^ (lane & 7u)) << 4)), "r"(pack_bf16(v[j], v[j + 1])),
+                             "r"(pack_bf16(v[j + 2], v[j + 3])), "r"(pack_bf16(v[j + 4], v[j + 5])), "r"(pack_bf16(v[j + 6], v[j + 7]))
+                             : "memory");
               }
             }
           }
         }
+        blk_bytes += ncols * es;
+        // flush: rows of the block are written as contiguous runs -- lane l moves piece l % 8 of row l / 8 + 4 it (up to 4 full 128-byte
+        // lines per instruction instead of 32 scattered 16-byte pieces)
+        const bool flush = ep.out_fp32 || !kPairs || (k & 1) == 1 || !more;
+        if (flush) {
+          __syncwarp();
+          const uint32_t piece = lane & 7u;
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int rr = it * 4 + (int)(lane >> 3);
+            const long long crow_r = __shfl_sync(0xffffffffu, crow, rr);
+            const int ok_r = __shfl_sync(0xffffffffu, (int)row_ok, rr);
+            if (ok_r && (int)(piece << 4) < blk_bytes) {
+              uint4 val;
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                           : "=r"(val.x), "=r"(val.y), "=r"(val.z), "=r"(val.w)
+                           : "r"(stage_base + (uint32_t)rr * 128u + ((piece ^ ((uint32_t)rr & 7u)) << 4))
+                           : "memory");
+              char* dst = reinterpret_cast<char*>(ep.C) + (crow_r * ep.ldc + blk_n0) * es + (piece << 4);
+              *reinterpret_cast<uint4*>(dst) = val;
+            }
+          }
+          __syncwarp();
+        }
       }
-      tmem_ld_wait();
-      // release the accumulator stage to the MMA warp
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        if constexpr (kCta == 1) mbar_arrive(tempty_bar(as)); else mbar_arrive_cluster(tempty_bar(as), 0);
+      if (!released) {  // no chunk of this tile belongs to this warp: still hand the accumulator stage back
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if constexpr (kCta == 1) mbar_arrive(tempty_bar(as)); else mbar_arrive_cluster(tempty_bar(as), 0);
+        }
       }
       if (++as == 2) { as = 0; aph ^= 1u; }
+    }
+    if (ep.trace && warp == 4 && lane == 0) {
+      ep.trace[blockIdx.x * 8 + 5] = clock64() - tr_t0;  // epilogue warp 4: total
+      ep.trace[blockIdx.x * 8 + 6] = tr_tfull;           // epilogue warp 4: waiting for an accumulator
     }
   }
 
@@ -425,6 +525,7 @@ static int launch_gemm(const vist3a_gemm_args& a, cudaStream_t stream) {
   ep.rmap = {a.rmap.rpg, a.rmap.gstride, a.rmap.goff};
   ep.out_fp32 = a.out_dtype == VIST3A_DTYPE_F32;
   ep.act = a.act; ep.post_act = a.post_act; ep.round_linear = a.round_linear; ep.round_gate = a.round_gate;
+  ep.trace = g_gemm_trace;
 
   auto kern = gemm_tcgen05_kernel<BN, kCta, kTF32>;
   static bool attr_set = false;  // per template instantiation
@@ -445,13 +546,15 @@ template <bool kTF32>
 static int dispatch_gemm(const vist3a_gemm_args& a, cudaStream_t stream) {
   const bool two = (a.flags & VIST3A_GEMM_FLAG_2CTA) && !(a.flags & VIST3A_GEMM_FLAG_1CTA) && a.M > 128;
   if (a.N > 128) {
-    if (two && !a.conv.enabled && !(a.flags & VIST3A_GEMM_FLAG_BN256)) {
-      // wave quantisation: cost ~ waves x tile width over the CTA pairs; take 176-wide tiles when they save more than 3 %.
-      // Measured on B200 (tools/kernel_bench.py, 8192 x 1536 outputs): +2.8 % at K = 1536, -1.3 % at K = 8960 -- a 176-wide tile pulls
-      // 77 B/clk/SM of operands through L2 instead of 62.5, which costs more than the fuller last wave returns on long K loops.
+    if (two && !a.conv.enabled && (a.flags & VIST3A_GEMM_FLAG_BN176)) {
+      // Wave quantisation experiment (A/B flag, off by default): cost ~ waves x tile width over the CTA pairs; 176-wide tiles fill 4 waves
+      // of 74 pairs to 97 % on a 1536-wide output (256-wide: 3 waves at 86 %).  Measured on B200 (tools/kernel_bench.py, 8192 x 1536):
+      // 944 vs 993 TFLOP/s at K = 1536 and -1.3 % at K = 8960 -- a 176-wide tile pulls 77 B/clk/SM of operands through L2 instead of
+      // 62.5 and the MMA warp already waits for operands a third of its time (tools/gemm_trace.py), which costs more than the fuller
+      // last wave returns.
       const long long pairs = num_sms() / 2, tm = (a.M + 255) / 256;
       auto cost = [&](long long bn) { return ((tm * ((a.N + bn - 1) / bn) + pairs - 1) / pairs) * bn; };
-      if (a.K <= 2048 && cost(176) * 103 < cost(256) * 100) return launch_gemm<176, 2, kTF32>(a, stream);
+      if (cost(176) * 103 < cost(256) * 100) return launch_gemm<176, 2, kTF32>(a, stream);
     }
     return two ? launch_gemm<256, 2, kTF32>(a, stream) : launch_gemm<256, 1, kTF32>(a, stream);
   }
