@@ -364,6 +364,27 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         if (first_of_block) { blk_n0 = n0; blk_bytes = 0; }
         const uint32_t srow = stage_base + lane * 128u;
         const uint32_t byte0 = (uint32_t)blk_bytes;  // offset of this chunk inside the staged row (0 or 64)
+        if (ep.residual && first_of_block) {
+          // the residual rows of this block come in the same way the results go out: row-contiguous 16-byte pieces (full lines)
+          // into the staging buffer; every thread then picks its own row's values from shared memory
+          int blk_cols = ncols;
+          if (!ep.out_fp32 && kPairs && chunk_ok(k + 1)) blk_cols += min(min(32, shape.N - n0 - 32), n_tile + BN - n0 - 32);
+          const int rbytes = blk_cols * es;
+          const uint32_t piece = lane & 7u;
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int rr = it * 4 + (int)(lane >> 3);
+            const long long rrow_r = __shfl_sync(0xffffffffu, rrow, rr);
+            const int ok_r = __shfl_sync(0xffffffffu, (int)row_ok, rr);
+            if (ok_r && (int)(piece << 4) < rbytes) {
+              const uint4 val = *reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(ep.residual) + (rrow_r * ep.ldr + n0) * es + (piece << 4));
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage_base + (uint32_t)rr * 128u + ((piece ^ ((uint32_t)rr & 7u)) << 4)),
+                           "r"(val.x), "r"(val.y), "r"(val.z), "r"(val.w)
+                           : "memory");
+            }
+          }
+          __syncwarp();
+        }
         if (row_ok) {
           if (ep.bias) {
 #pragma unroll
@@ -395,7 +416,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           // stage the finished values in this warp's 32 x 128-byte buffer (16-byte pieces XOR-swizzled by the row: conflict-free
           // both for these per-row writes and for the row-contiguous reads below)
           if (ep.out_fp32) {
-            if (ep.residual) add_row32<true>(v, ep.residual, rrow * ep.ldr + n0, ncols);
+            if (ep.residual) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                if (j < ncols) {
+                  float4 x;
+                  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                               : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w)
+                               : "r"(srow + (((uint32_t)(j >> 2)) ^ (lane & 7u)) * 16u)
+                               : "memory");
+                  v[j] += x.x; v[j + 1] += x.y; v[j + 2] += x.z; v[j + 3] += x.w;
+                }
+              }
+            }
             if (ep.residual2) add_row32<true>(v, ep.residual2, crow * ep.ldc + n0, ncols);
             if (ep.post_act == VIST3A_ACT_RELU) act32<VIST3A_ACT_RELU>(v);
 #pragma unroll
@@ -408,7 +441,22 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               }
             }
           } else {
-            if (ep.residual) add_row32<false>(v, ep.residual, rrow * ep.ldr + n0, ncols);
+            if (ep.residual) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                if (j < ncols) {
+                  uint4 x;
+                  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                               : "=r"(x.x), "=r"(x.y), "=r"(x.z), "=r"(x.w)
+                               : "r"(srow + ((((byte0 >> 4) + (uint32_t)(j >> 3)) ^ (lane & 7u)) << 4))
+                               : "memory");
+                  v[j] += bf16_lo(x.x); v[j + 1] += bf16_hi(x.x);
+                  v[j + 2] += bf16_lo(x.y); v[j + 3] += bf16_hi(x.y);
+                  v[j + 4] += bf16_lo(x.z); v[j + 5] += bf16_hi(x.z);
+                  v[j + 6] += bf16_lo(x.w); v[j + 7] += bf16_hi(x.w);
+                }
+              }
+            }
             if (ep.residual2) add_row32<false>(v, ep.residual2, crow * ep.ldc + n0, ncols);
             if (ep.post_act == VIST3A_ACT_RELU) act32<VIST3A_ACT_RELU>(v);
 #pragma unroll
