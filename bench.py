@@ -165,6 +165,13 @@ def run_reference(args):
     if rank != 0:
         return
     nb = args.ref_blocks
+    # all the host threads this process may use: torchrun exports OMP_NUM_THREADS=1 to its workers, which would time a 1-thread CPU arm
+    try:
+        avail = len(os.sched_getaffinity(0))
+    except AttributeError:
+        avail = os.cpu_count() or 1
+    if torch.get_num_threads() < avail:
+        torch.set_num_threads(avail)
     cores = torch.get_num_threads()
     times = cpu_sample(nb, repeats=args.warmup + args.steps)[args.warmup:]
     # a denoise step = 2 forwards of 30 blocks; each timed sample is nb blocks of one forward
@@ -221,6 +228,10 @@ def run_ours(args):
         raise SystemExit("bench.py needs a B200: the product path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
+    # stdout carries exactly ONE JSON line: library chatter written to fd 1 (NCCL prints its version banner there) goes to stderr instead
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
     _lib.load()
@@ -422,7 +433,8 @@ def run_ours(args):
                 "gpu_launches": launches_eager if args.no_graph else (launches_per_step or 0) * args.steps,
                 "gpu_launches_note": "graph replays re-launch the captured kernels; count = kernels per step x steps" if not args.no_graph else "eager",
                 "tflops_model": STEP_TFLOP * value}
-        print(json.dumps(line), flush=True)
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 

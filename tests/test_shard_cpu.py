@@ -42,17 +42,29 @@ def test_pack_unpack_roundtrip(cov):
         assert torch.equal(v, getattr(g, k))
 
 
+def _gauss_packed(seed, b=2, n=19, d_sh=25):
+    """Gaussians whose fields are views of one field-major buffer, as the decoder produces them (ops.alloc_gaussian_fields)"""
+    from vist3a_b200.ops import alloc_gaussian_fields
+
+    o = alloc_gaussian_fields(b * n, d_sh, "cpu")
+    o["packed"].copy_(torch.randn(o["packed"].shape, generator=torch.Generator().manual_seed(seed)))
+    return Gaussians(means=o["means"].view(b, n, 3), covariances=o["covariances"].view(b, n, 3, 3), harmonics=o["harmonics"].view(b, n, 3, d_sh),
+                     opacities=o["opacities"].view(b, n), scales=o["scales"].view(b, n, 3), rotations=o["rotations"].view(b, n, 4), packed=o["packed"])
+
+
 def _worker(rank, world, port, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        mine = _gauss(100 + rank)
-        got = all_gather_gaussians(mine, with_covariances=True)
-        ok = len(got) == world
-        for r in range(world):
-            want = _gauss(100 + r)
-            for k, v in got[r].items():
-                ok = ok and torch.equal(v, getattr(want, k))
+        ok = True
+        for make, cov in ((_gauss, True), (_gauss_packed, True), (_gauss_packed, False)):   # record path / packed buffer path
+            got = all_gather_gaussians(make(100 + rank), with_covariances=cov)
+            ok = ok and len(got) == world
+            for r in range(world):
+                want = make(100 + r)
+                ok = ok and (("covariances" in got[r]) == cov)
+                for k, v in got[r].items():
+                    ok = ok and torch.equal(v, getattr(want, k))
         q.put((rank, ok))
     finally:
         dist.destroy_process_group()

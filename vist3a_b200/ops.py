@@ -459,6 +459,24 @@ def pose_to_cameras(pose_raw: torch.Tensor, H: int, W: int, cameras: bool = True
     return out
 
 
+GAUSSIAN_FIELDS = (("means", 3), ("scales", 3), ("rotations", 4), ("opacities", 1), ("harmonics", None), ("covariances", 9))
+
+
+def alloc_gaussian_fields(P: int, d_sh: int, device) -> dict:
+    """One flat fp32 buffer holding every per-Gaussian output field-major (means | scales | rotations | opacities | harmonics |
+    covariances, each field contiguous over the P Gaussians), plus the per-field views the kernels write.  The multi-GPU gather sends
+    the buffer as it is (vist3a_b200.t23d.all_gather_gaussians): no packing or unpacking copies."""
+    widths = [(k, 3 * d_sh if w is None else w) for k, w in GAUSSIAN_FIELDS]
+    flat = torch.empty((P * sum(w for _, w in widths),), dtype=torch.float32, device=device)
+    o, off = {"packed": flat}, 0
+    for k, w in widths:
+        o[k] = flat[off:off + P * w]
+        off += P * w
+    o["means"], o["scales"], o["rotations"] = o["means"].view(P, 3), o["scales"].view(P, 3), o["rotations"].view(P, 4)
+    o["harmonics"], o["covariances"] = o["harmonics"].view(P, 3, d_sh), o["covariances"].view(P, 3, 3)
+    return o
+
+
 def gaussian_epilogue(depth_feat: torch.Tensor, depth_w: torch.Tensor, depth_b: float, gs_raw: torch.Tensor, extr: torch.Tensor,
                       intr: torch.Tensor, sh_mask: torch.Tensor, S: int, H: int, W: int):
     """fused depth activation + unprojection + Gaussian adapter; see vist3a_gaussian_epilogue."""
@@ -467,10 +485,8 @@ def gaussian_epilogue(depth_feat: torch.Tensor, depth_w: torch.Tensor, depth_b: 
     d_sh = sh_mask.shape[0]
     dev = gs_raw.device
     f32 = torch.float32
-    o = dict(depth=torch.empty((P,), dtype=f32, device=dev), means=torch.empty((P, 3), dtype=f32, device=dev),
-             scales=torch.empty((P, 3), dtype=f32, device=dev), rotations=torch.empty((P, 4), dtype=f32, device=dev),
-             opacities=torch.empty((P,), dtype=f32, device=dev), harmonics=torch.empty((P, 3, d_sh), dtype=f32, device=dev),
-             covariances=torch.empty((P, 3, 3), dtype=f32, device=dev), scene_sum=torch.zeros((1,), dtype=f32, device=dev))
+    o = alloc_gaussian_fields(P, d_sh, dev)
+    o["depth"], o["scene_sum"] = torch.empty((P,), dtype=f32, device=dev), torch.zeros((1,), dtype=f32, device=dev)
     L.check(L.load().vist3a_gaussian_epilogue(depth_feat.data_ptr(), depth_feat.stride(0), depth_w.shape[0], depth_w.data_ptr(),
                                               float(depth_b), gs_raw.data_ptr(), gs_raw.stride(0), extr.data_ptr(), intr.data_ptr(),
                                               sh_mask.data_ptr(), d_sh, S, H, W, o["depth"].data_ptr(), o["means"].data_ptr(),
@@ -487,9 +503,7 @@ def gaussian_adapter(pts: torch.Tensor, feats: torch.Tensor, sh_mask: torch.Tens
     dev, f32 = pts.device, torch.float32
     if pts.dtype != f32 or feats.dtype != f32 or not pts.is_contiguous() or feats.stride(1) != 1:
         raise ValueError("gaussian_adapter: fp32 contiguous points and unit-stride fp32 feature rows expected")
-    o = dict(means=torch.empty((P, 3), dtype=f32, device=dev), scales=torch.empty((P, 3), dtype=f32, device=dev),
-             rotations=torch.empty((P, 4), dtype=f32, device=dev), opacities=torch.empty((P,), dtype=f32, device=dev),
-             harmonics=torch.empty((P, 3, d_sh), dtype=f32, device=dev), covariances=torch.empty((P, 3, 3), dtype=f32, device=dev))
+    o = alloc_gaussian_fields(P, d_sh, dev)
     if P > 0:
         L.check(L.load().vist3a_gaussian_adapter(pts.data_ptr(), feats.data_ptr(), feats.stride(0), sh_mask.data_ptr(), d_sh, P,
                                                  o["means"].data_ptr(), o["scales"].data_ptr(), o["rotations"].data_ptr(),

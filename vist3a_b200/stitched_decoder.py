@@ -50,6 +50,9 @@ class Gaussians:
     opacities: torch.Tensor      # [B, N]
     scales: torch.Tensor         # [B, N, 3]
     rotations: torch.Tensor      # [B, N, 4] (xyzw)
+    # not a reference field: the flat fp32 buffer all the fields above are views of (field-major: means | scales | rotations | opacities |
+    # harmonics | covariances, each over the B*N Gaussians) -- what the multi-GPU gather sends without packing (t23d.all_gather_gaussians)
+    packed: Optional[torch.Tensor] = None
 
 
 @dataclass
@@ -663,7 +666,7 @@ class StitchVAE3DB200(torch.nn.Module):
             del fused, vp, vf
         gauss = Gaussians(means=o["means"].view(B, N, 3), covariances=o["covariances"].view(B, N, 3, 3),
                           harmonics=o["harmonics"].view(B, N, 3, cfg.d_sh), opacities=o["opacities"].view(B, N),
-                          scales=o["scales"].view(B, N, 3), rotations=o["rotations"].view(B, N, 4))
+                          scales=o["scales"].view(B, N, 3), rotations=o["rotations"].view(B, N, 4), packed=o.get("packed"))
         scene_scale = (o["scene_sum"] / float(BV * H * W)).clamp_min(1e-8).reshape(())
         return EncoderOutput(
             gaussians=gauss,
