@@ -475,6 +475,12 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
         for (int cb = 0; cb < HC / 32; ++cb) {
           uint32_t pk[16];
+          if (cb * 32 >= valid) {  // (warp-uniform) a 32-column chunk past the last key: P = 0 without 32 exponentials per thread
+#pragma unroll
+            for (int k = 0; k < 16; ++k) pk[k] = 0u;
+            tmem_st_x16(p_addr + (uint32_t)(cb * 16), pk);
+            continue;
+          }
 #pragma unroll
           for (int k = 0; k < 16; ++k) {
             float y0, y1, e0, e1;
