@@ -354,6 +354,28 @@ int vist3a_voxel_fusion(const float* pts, const float* feats, int64_t ld_feats, 
                         int64_t n_points, float voxel_size, float* voxel_pts, float* voxel_feats, int32_t* inverse, int32_t* counts,
                         int64_t* n_voxels, void* workspace, int64_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * 3D-Gaussian rasteriser, forward (the consumer of the Gaussians: novel-view rendering)
+ * replaces: gsplat 1.4.0 `rasterization(means, quats, scales, opacities, sh, viewmat, K, W, H, sh_degree=4, render_mode="RGB+D",
+ *   packed=False, near_plane=1e-10, backgrounds, radius_clip=0.1, covars, rasterize_mode="classic")`, called once per view from
+ *   DecoderSplattingCUDA.rendering_fn (AS/model/decoder/decoder_splatting_cuda.py:43-125, call :92-112).  gsplat is absent from the
+ *   reference tree (requirements.txt:17); its published algorithm is restated (see csrc/gs_render.cu, oracle/gsplat_ref.py).
+ * Phase 1, vist3a_gs_project: per Gaussian camera-space projection (covariances [N,3,3] given), eps2d blur, conic, 3-sigma radius, culling,
+ *   degree <= 4 spherical-harmonic colour from harmonics [N, 3, d_sh] (the decoder's layout), 16x16-tile box, exclusive scan of the tile
+ *   counts.  viewmat (row-major 4x4 world->camera) and K (row-major 3x3, pixels) are HOST pointers.  *n_isect (device int64) receives the
+ *   number of (tile, Gaussian) intersections: read it after synchronising, then size phase 2's workspace.
+ * Phase 2, vist3a_gs_rasterize: intersection keys (tile id | depth bits), stable radix sort, per-tile ranges, front-to-back compositing.
+ *   background: HOST pointer to 3 floats.  Outputs rgb [H, W, 3] (unclamped, as gsplat), depth [H, W] (accumulated alpha-weighted depth,
+ *   "RGB+D"), alpha [H, W].
+ * Workspaces are caller-owned device memory, 256-byte aligned; the project workspace is an input of phase 2. */
+int64_t vist3a_gs_project_workspace_bytes(int64_t n_gaussians);
+int vist3a_gs_project(const float* means, const float* covariances, const float* opacities, const float* harmonics, int64_t d_sh, int32_t sh_degree,
+                      int64_t n_gaussians, const float* viewmat, const float* K, int64_t W, int64_t H, float near_plane, float far_plane,
+                      float radius_clip, float eps2d, void* workspace, int64_t workspace_bytes, int64_t* n_isect, void* stream);
+int64_t vist3a_gs_rasterize_workspace_bytes(int64_t n_isect, int64_t W, int64_t H);
+int vist3a_gs_rasterize(const void* project_workspace, int64_t n_gaussians, int64_t n_isect, int64_t W, int64_t H, const float* background,
+                        void* workspace, int64_t workspace_bytes, float* rgb, float* depth, float* alpha, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

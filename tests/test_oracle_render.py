@@ -1,0 +1,86 @@
+"""Known-answer tests of the rasteriser oracle (oracle/gsplat_ref.py).  gsplat 1.4.0 is absent and the reference holds no golden renders,
+so the oracle is PARITY UNPINNED against the package itself; what can be pinned analytically is pinned here: the spherical-harmonic basis
+against the closed forms, the projection of an on-axis isotropic Gaussian, the compositing rules (alpha cap, 1/255 cut, transmittance stop,
+background), tile culling and depth ordering."""
+import math
+
+import torch
+
+from oracle import gsplat_ref as G
+
+
+def test_sh_basis_matches_closed_forms_and_is_orthonormal():
+    g = torch.Generator().manual_seed(0)
+    d = torch.randn(200000, 3, generator=g, dtype=torch.float64)
+    d = d / d.norm(dim=-1, keepdim=True)
+    b = G.sh_basis(4, d)
+    x, y, z = d.unbind(-1)
+    assert torch.allclose(b[:, 6], 0.31539156525252005 * (3 * z * z - 1), atol=1e-12)           # Y_2^0
+    assert torch.allclose(b[:, 4], 1.0925484305920792 * x * y, atol=1e-12)                      # Y_2^-2
+    assert torch.allclose(b[:, 12], 0.3731763325901154 * z * (5 * z * z - 3), atol=1e-12)       # Y_3^0
+    assert torch.allclose(b[:, 20], 0.10578554691520431 * (35 * z ** 4 - 30 * z * z + 3), atol=1e-12)  # Y_4^0
+    gram = (b.T @ b) / d.shape[0] * 4 * math.pi                                                 # Monte-Carlo orthonormality over the sphere
+    assert float((gram - torch.eye(25, dtype=torch.float64)).abs().max()) < 0.03
+
+
+def _one(mean, s, opac=0.8, W=64, H=48, color=0.5, **kw):
+    means = torch.tensor([mean], dtype=torch.float32)
+    cov = torch.diag_embed(torch.tensor([[s * s] * 3], dtype=torch.float32))
+    harm = torch.zeros(1, 3, 25)
+    harm[:, :, 0] = color / 0.2820947917738781      # colour = 0.5 + `color`
+    V, K = G.look_at_camera(W, H, fov_deg=60.0)
+    return G.render(means, cov, torch.tensor([opac]), harm, V, K, W, H, **kw), K
+
+
+def test_on_axis_isotropic_gaussian():
+    W, H, s, zc, opac = 64, 48, 0.05, 2.0, 0.8
+    r, K = _one((0.0, 0.0, zc), s, opac, W, H, color=0.25)
+    f = float(K[0, 0])
+    var2d = (f * s / zc) ** 2 + 0.3                   # isotropic 3-D covariance on the axis: J S J^T = (f s / z)^2 I, + eps2d
+    for (py, px) in ((H // 2, W // 2), (H // 2 + 3, W // 2 - 2)):
+        dx, dy = W / 2 - (px + 0.5), H / 2 - (py + 0.5)
+        a = min(0.999, opac * math.exp(-0.5 * (dx * dx + dy * dy) / var2d))
+        assert abs(float(r["alpha"][py, px]) - a) < 1e-5
+        assert abs(float(r["rgb"][py, px, 0]) - 0.75 * a) < 1e-5      # colour 0.5 + 0.25, black background
+        assert abs(float(r["depth"][py, px]) - zc * a) < 1e-5
+    radius = math.ceil(3 * math.sqrt(var2d))
+    assert r["n_isect"] == (math.ceil((W / 2 + radius) / 16) - math.floor((W / 2 - radius) / 16)) * (math.ceil((H / 2 + radius) / 16) - math.floor((H / 2 - radius) / 16))
+
+
+def test_compositing_rules():
+    # background through the remaining transmittance; tiles the +-radius box does not touch see only the background
+    r, _ = _one((0.0, 0.0, 2.0), 0.02, 0.5, background=(0.2, 0.4, 0.6))
+    assert torch.allclose(r["rgb"][0, 0], torch.tensor([0.2, 0.4, 0.6])) and float(r["alpha"][0, 0]) == 0.0
+    c = r["alpha"][24, 32]
+    assert torch.allclose(r["rgb"][24, 32], 1.0 * c + (1 - c) * torch.tensor([0.2, 0.4, 0.6]), atol=1e-6)
+    # alpha is capped at 0.999 and contributions below 1/255 are dropped
+    r, _ = _one((0.0, 0.0, 2.0), 0.3, 1.5)        # opacity x exp(-sigma) > 1 near the centre
+    assert abs(float(r["alpha"].max()) - 0.999) < 1e-6
+    r, _ = _one((0.0, 0.0, 2.0), 0.3, 1.0 / 300.0)
+    assert float(r["alpha"].max()) == 0.0
+    # culling: behind the camera, beyond the image, sub-clip radius
+    assert _one((0.0, 0.0, -1.0), 0.05)[0]["n_isect"] == 0
+    assert _one((50.0, 0.0, 2.0), 0.05)[0]["n_isect"] == 0
+    assert _one((0.0, 0.0, 2.0), 0.05, radius_clip=100.0)[0]["n_isect"] == 0
+
+
+def test_depth_order_and_transmittance_stop():
+    W, H = 32, 32
+    V, K = G.look_at_camera(W, H)
+    cov = torch.diag_embed(torch.full((3, 3), 0.5 ** 2))
+    harm = torch.zeros(3, 3, 25)
+    for k, col in enumerate((1.0, 0.0, -0.5)):
+        harm[k, :, 0] = col / 0.2820947917738781
+    opac = torch.tensor([0.99, 0.99, 0.99])
+    near_first = G.render(torch.tensor([[0.0, 0, 2.0], [0.0, 0, 3.0], [0.0, 0, 4.0]]), cov, opac, harm, V, K, W, H)
+    far_first = G.render(torch.tensor([[0.0, 0, 4.0], [0.0, 0, 3.0], [0.0, 0, 2.0]]), cov, opac, harm, V, K, W, H)
+    cpx = (H // 2, W // 2)
+    f = float(K[0, 0])
+    a = [min(0.999, 0.99 * math.exp(-0.25 / ((f * 0.5 / z) ** 2 + 0.3))) for z in (2.0, 3.0, 4.0)]   # pixel centre is (0.5, 0.5) off the mean
+    # front Gaussian (colour 1.5), then colour 0.5 behind it with T = 1 - a0; the third would leave T (1 - a2) <= 1e-4: the loop stops WITHOUT adding it
+    t1 = 1 - a[0]
+    assert t1 * (1 - a[1]) > 1e-4 and t1 * (1 - a[1]) * (1 - a[2]) <= 1e-4
+    assert abs(float(near_first["rgb"][cpx][0]) - (1.5 * a[0] + 0.5 * a[1] * t1)) < 1e-5
+    assert abs(float(near_first["alpha"][cpx]) - (1 - t1 * (1 - a[1]))) < 1e-6
+    # order is by depth, not by index: with the far Gaussian listed first the result is the same scene
+    assert torch.allclose(far_first["rgb"], G.render(torch.tensor([[0.0, 0, 2.0], [0.0, 0, 3.0], [0.0, 0, 4.0]]), cov, opac, harm.flip(0), V, K, W, H)["rgb"])

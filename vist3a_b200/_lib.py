@@ -52,7 +52,11 @@ EXPORTS = (
     "vist3a_gaussian_epilogue",
     "vist3a_gaussian_adapter",
     "vist3a_voxel_fusion",
+    "vist3a_gs_project",
+    "vist3a_gs_rasterize",
     "vist3a_voxel_fusion_workspace_bytes",
+    "vist3a_gs_project_workspace_bytes",
+    "vist3a_gs_rasterize_workspace_bytes",
 )
 
 
@@ -156,10 +160,14 @@ def load(build_if_missing: bool = False) -> C.CDLL:
     lib.vist3a_launch_count.restype = C.c_int64
     lib.vist3a_set_pdl.restype = C.c_int
     lib.vist3a_set_pdl.argtypes = [C.c_int32]
-    for name in EXPORTS[4:-1]:
+    for name in EXPORTS[4:-3]:
         getattr(lib, name).restype = C.c_int
     lib.vist3a_voxel_fusion_workspace_bytes.restype = C.c_int64
     lib.vist3a_voxel_fusion_workspace_bytes.argtypes = [C.c_int64]
+    lib.vist3a_gs_project_workspace_bytes.restype = C.c_int64
+    lib.vist3a_gs_project_workspace_bytes.argtypes = [C.c_int64]
+    lib.vist3a_gs_rasterize_workspace_bytes.restype = C.c_int64
+    lib.vist3a_gs_rasterize_workspace_bytes.argtypes = [C.c_int64, C.c_int64, C.c_int64]
     lib.vist3a_gemm.argtypes = [C.POINTER(GemmArgs), C.c_void_p]
     lib.vist3a_fmha_fwd.argtypes = [C.POINTER(FmhaArgs), C.c_void_p]
     i64, i32, f32, vp, u32 = C.c_int64, C.c_int32, C.c_float, C.c_void_p, C.c_uint32
@@ -189,6 +197,9 @@ def load(build_if_missing: bool = False) -> C.CDLL:
                                              vp, vp, vp]
     lib.vist3a_gaussian_adapter.argtypes = [vp, vp, i64, vp, i64, i64, vp, vp, vp, vp, vp, vp, vp]
     lib.vist3a_voxel_fusion.argtypes = [vp, vp, i64, i64, vp, i64, i64, f32, vp, vp, vp, vp, vp, vp, i64, vp]
+    fp = C.POINTER(f32)
+    lib.vist3a_gs_project.argtypes = [vp, vp, vp, vp, i64, i32, i64, fp, fp, i64, i64, f32, f32, f32, f32, vp, i64, vp, vp]
+    lib.vist3a_gs_rasterize.argtypes = [vp, i64, i64, i64, i64, fp, vp, i64, vp, vp, vp, vp]
     _lib = lib
     return lib
 

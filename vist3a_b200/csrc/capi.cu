@@ -43,6 +43,11 @@ int gaussian_adapter_entry(const float*, const float*, long long, const float*, 
 long long voxel_fusion_workspace_bytes(long long);
 int voxel_fusion_entry(const float*, const float*, long long, long long, const float*, long long, long long, float, float*, float*, int*, int*,
                        long long*, void*, long long, cudaStream_t);
+long long gs_project_workspace_bytes(long long);
+long long gs_rasterize_workspace_bytes(long long, long long, long long);
+int gs_project_entry(const float*, const float*, const float*, const float*, long long, int, long long, const float*, const float*, long long, long long,
+                     float, float, float, float, void*, long long, long long*, cudaStream_t);
+int gs_rasterize_entry(const void*, long long, long long, long long, long long, const float*, void*, long long, float*, float*, float*, cudaStream_t);
 int timestep_features_entry(const float*, void*, int, long long, long long, cudaStream_t);
 int patchify_entry(const void*, int, void*, long long, long long, long long, long long, long long, cudaStream_t);
 int unpatchify_entry(const void*, int, long long, void*, int, long long, long long, long long, long long, long long,
@@ -291,6 +296,19 @@ int vist3a_voxel_fusion(const float* pts, const float* feats, int64_t ld_feats, 
                         int64_t* n_voxels, void* workspace, int64_t workspace_bytes, void* stream) {
   return voxel_fusion_entry(pts, feats, ld_feats, feat_dim, conf, conf_stride, n_points, voxel_size, voxel_pts, voxel_feats, inverse, counts,
                             reinterpret_cast<long long*>(n_voxels), workspace, workspace_bytes, ST(stream));
+}
+
+int64_t vist3a_gs_project_workspace_bytes(int64_t n_gaussians) { return gs_project_workspace_bytes(n_gaussians); }
+int vist3a_gs_project(const float* means, const float* covariances, const float* opacities, const float* harmonics, int64_t d_sh, int32_t sh_degree,
+                      int64_t n_gaussians, const float* viewmat, const float* K, int64_t W, int64_t H, float near_plane, float far_plane,
+                      float radius_clip, float eps2d, void* workspace, int64_t workspace_bytes, int64_t* n_isect, void* stream) {
+  return gs_project_entry(means, covariances, opacities, harmonics, d_sh, sh_degree, n_gaussians, viewmat, K, W, H, near_plane, far_plane, radius_clip,
+                          eps2d, workspace, workspace_bytes, reinterpret_cast<long long*>(n_isect), ST(stream));
+}
+int64_t vist3a_gs_rasterize_workspace_bytes(int64_t n_isect, int64_t W, int64_t H) { return gs_rasterize_workspace_bytes(n_isect, W, H); }
+int vist3a_gs_rasterize(const void* project_workspace, int64_t n_gaussians, int64_t n_isect, int64_t W, int64_t H, const float* background,
+                        void* workspace, int64_t workspace_bytes, float* rgb, float* depth, float* alpha, void* stream) {
+  return gs_rasterize_entry(project_workspace, n_gaussians, n_isect, W, H, background, workspace, workspace_bytes, rgb, depth, alpha, ST(stream));
 }
 
 }  // extern "C"

@@ -544,6 +544,36 @@ def voxel_fusion(pts: torch.Tensor, feats: torch.Tensor, conf: torch.Tensor, vox
     return out
 
 
+def gs_render(means: torch.Tensor, covariances: torch.Tensor, opacities: torch.Tensor, harmonics: torch.Tensor, viewmat, K, W: int, H: int, *,
+              sh_degree: int = 4, background=(0.0, 0.0, 0.0), near_plane: float = 1e-10, far_plane: float = 1e10, radius_clip: float = 0.1,
+              eps2d: float = 0.3):
+    """Rasterise N Gaussians into one view (see vist3a_gs_project / vist3a_gs_rasterize): means [N,3], covariances [N,3,3], opacities [N],
+    harmonics [N,3,d_sh] fp32 on the device; viewmat 4x4 world->camera and K 3x3 (pixels) as nested lists / CPU tensors.  Returns
+    dict(rgb [H,W,3] unclamped, depth [H,W], alpha [H,W], n_isect).  Reading the intersection count synchronises the stream."""
+    _need_cuda(means, covariances, opacities, harmonics)
+    f32, dev = torch.float32, means.device
+    N, d_sh = means.shape[0], harmonics.shape[-1]
+    for t_, shp in ((means, (N, 3)), (covariances, (N, 3, 3)), (opacities, (N,)), (harmonics, (N, 3, d_sh))):
+        if t_.dtype != f32 or not t_.is_contiguous() or tuple(t_.shape) != shp:
+            raise ValueError(f"gs_render: contiguous fp32 tensor of shape {shp} expected, got {tuple(t_.shape)} {t_.dtype}")
+    vm = (C.c_float * 16)(*[float(v) for v in torch.as_tensor(viewmat, dtype=f32).reshape(-1).tolist()])
+    kk = (C.c_float * 9)(*[float(v) for v in torch.as_tensor(K, dtype=f32).reshape(-1).tolist()])
+    bg = (C.c_float * 3)(*[float(v) for v in background])
+    lib = L.load()
+    pws = torch.empty((int(lib.vist3a_gs_project_workspace_bytes(N)),), dtype=torch.uint8, device=dev)
+    n_is = torch.zeros((1,), dtype=torch.int64, device=dev)
+    L.check(lib.vist3a_gs_project(means.data_ptr(), covariances.data_ptr(), opacities.data_ptr(), harmonics.data_ptr(), d_sh, int(sh_degree), N, vm, kk,
+                                  W, H, float(near_plane), float(far_plane), float(radius_clip), float(eps2d), pws.data_ptr(), pws.numel(),
+                                  n_is.data_ptr(), _stream()))
+    n_isect = int(n_is.item())
+    rws = torch.empty((int(lib.vist3a_gs_rasterize_workspace_bytes(n_isect, W, H)),), dtype=torch.uint8, device=dev)
+    out = dict(rgb=torch.empty((H, W, 3), dtype=f32, device=dev), depth=torch.empty((H, W), dtype=f32, device=dev),
+               alpha=torch.empty((H, W), dtype=f32, device=dev), n_isect=n_isect)
+    L.check(lib.vist3a_gs_rasterize(pws.data_ptr(), N, n_isect, W, H, bg, rws.data_ptr(), rws.numel(), out["rgb"].data_ptr(), out["depth"].data_ptr(),
+                                    out["alpha"].data_ptr(), _stream()))
+    return out
+
+
 # ------------------------------------------------------------------------------------------------
 # per-launch device timing (bench.py roofline): CUDA events recorded on the launching stream around
 # every call of the wrapped op, with its algorithmic FLOPs / bytes.
