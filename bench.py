@@ -366,6 +366,14 @@ def run_ours(args):
                  "latent": "denoised latent of the random-weight DiT, clamped to [-4, 4] before de-normalisation (real VAE latents are O(1))",
                  "workload": f"VIST3A-{'1.3B' if args.model == '1.3b' else '14B'} full stitched path: DiT -> conv3d_k5x3x3 stitch -> AnySplat "
                              f"enc_blocks_2 -> 3DGS, 512x512x{VIEWS}v"}
+        if args.render:    # consumer of the Gaussians: re-render the 13 context views from the predicted cameras (rasteriser forward)
+            from vist3a_b200.renderer import DecoderSplattingB200
+
+            rend = DecoderSplattingB200((1.0, 1.0, 1.0))
+            rend.render_context_views(outs["o"], (IMG, IMG))
+            ms_r = timed(lambda i: rend.render_context_views(outs["o"], (IMG, IMG)), 2) / 2
+            gauss["render"] = {"views": VIEWS, "image": f"{IMG}x{IMG}", "ms_per_view": ms_r / (B * VIEWS), "views_per_sec": world * B * VIEWS / (ms_r / 1e3),
+                               "what": "DecoderSplattingB200.rendering_fn over the predicted context cameras, all Gaussians of the prompt per view"}
         if args.voxelize:  # voxelised fusion (released AnySplat configs): fewer, fused Gaussians; Gaussians/s above still counts pixels decoded
             gauss["voxelize"] = {"voxel_size": dec.cfg.voxel_size, "voxels_per_prompt": int(outs["o"].gaussians.means.shape[1]),
                                  "voxelize_ratio": float(outs["o"].infos["voxelize_ratio"])}
@@ -456,6 +464,7 @@ def main():
     ap.add_argument("--model", default="1.3b", choices=["1.3b", "14b"], help="Wan DiT size (BASELINE configs[1-2] / configs[3])")
     ap.add_argument("--views", type=int, default=13, choices=[13, 21], help="views per prompt (13: latent T=4, L=4096; 21: T=6, L=6144)")
     ap.add_argument("--voxelize", action="store_true", help="decoder with voxelised Gaussian fusion (voxel_size 0.002)")
+    ap.add_argument("--render", action="store_true", help="also time the rasteriser on the decoded Gaussians (13 context views)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

@@ -56,3 +56,10 @@ class DecoderSplattingB200(torch.nn.Module):
         return DecoderOutput(color, depth, alpha)
 
     forward = rendering_fn
+
+    @torch.no_grad()
+    def render_context_views(self, output, image_shape=(448, 448)) -> DecoderOutput:
+        """Re-render the scene from the cameras the decoder predicted for its own context views (`EncoderOutput.pred_context_pose`:
+        camera-to-world extrinsics, normalised intrinsics) -- the first thing inference_t23d.py:139-155 does with the Gaussians."""
+        pose = output.pred_context_pose
+        return self.rendering_fn(output.gaussians, pose["extrinsic"], pose["intrinsic"], image_shape=image_shape)
