@@ -275,7 +275,11 @@ __global__ void __launch_bounds__(kTile* kTile) gs_rasterize_kernel(const float*
                                                                    int tiles_x, float bg0, float bg1, float bg2, float* __restrict__ rgb,
                                                                    float* __restrict__ depth, float* __restrict__ alpha) {
   const unsigned* vals = (*npasses & 1) ? vals_b : vals_a;
-  __shared__ float s_g[kTile * kTile][kGeom];
+  // batch of 256 Gaussians in shared memory as three float4 per Gaussian: the test of a Gaussian against a pixel needs the first two
+  // (position, opacity, conic); colour and depth are read only when it contributes
+  __shared__ float4 s_xyod[kTile * kTile];   // x, y, opacity, depth
+  __shared__ float4 s_con[kTile * kTile];    // conic a, b, c
+  __shared__ float4 s_rgb[kTile * kTile];
   const int tile = blockIdx.y * tiles_x + blockIdx.x;
   const int px_i = blockIdx.x * kTile + (threadIdx.x % kTile), py_i = blockIdx.y * kTile + (threadIdx.x / kTile);
   const float px = (float)px_i + 0.5f, py = (float)py_i + 0.5f;
@@ -288,16 +292,17 @@ __global__ void __launch_bounds__(kTile* kTile) gs_rasterize_kernel(const float*
     const unsigned j = base + threadIdx.x;
     if (j < r1) {
       const float* g = geom + (long long)vals[j] * kGeom;
-#pragma unroll
-      for (int k = 0; k < kGeom; ++k) s_g[threadIdx.x][k] = g[k];
+      s_xyod[threadIdx.x] = make_float4(g[0], g[1], g[6], g[2]);
+      s_con[threadIdx.x] = make_float4(g[3], g[4], g[5], 0.f);
+      s_rgb[threadIdx.x] = make_float4(g[7], g[8], g[9], 0.f);
     }
     __syncthreads();
     const int cnt = (int)min((unsigned)(kTile * kTile), r1 - base);
     for (int t = 0; t < cnt && !done; ++t) {
-      const float* g = s_g[t];
-      const float dx = g[0] - px, dy = g[1] - py;
-      const float sigma = 0.5f * (g[3] * dx * dx + g[5] * dy * dy) + g[4] * dx * dy;
-      const float a = fminf(0.999f, g[6] * __expf(-sigma));
+      const float4 xo = s_xyod[t], cn = s_con[t];
+      const float dx = xo.x - px, dy = xo.y - py;
+      const float sigma = 0.5f * (cn.x * dx * dx + cn.z * dy * dy) + cn.y * dx * dy;
+      const float a = fminf(0.999f, xo.z * __expf(-sigma));
       if (sigma < 0.f || a < 1.f / 255.f) continue;
       const float next_T = T * (1.f - a);
       if (next_T <= 1e-4f) {
@@ -305,7 +310,8 @@ __global__ void __launch_bounds__(kTile* kTile) gs_rasterize_kernel(const float*
         break;
       }
       const float vis = a * T;
-      acc0 += g[7] * vis; acc1 += g[8] * vis; acc2 += g[9] * vis; accd += g[2] * vis;
+      const float4 c = s_rgb[t];
+      acc0 += c.x * vis; acc1 += c.y * vis; acc2 += c.z * vis; accd += xo.w * vis;
       T = next_T;
     }
   }
