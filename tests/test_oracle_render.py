@@ -84,3 +84,63 @@ def test_depth_order_and_transmittance_stop():
     assert abs(float(near_first["alpha"][cpx]) - (1 - t1 * (1 - a[1]))) < 1e-6
     # order is by depth, not by index: with the far Gaussian listed first the result is the same scene
     assert torch.allclose(far_first["rgb"], G.render(torch.tensor([[0.0, 0, 2.0], [0.0, 0, 3.0], [0.0, 0, 4.0]]), cov, opac, harm.flip(0), V, K, W, H)["rgb"])
+
+
+def _poses(seed, B=2, V=4):
+    g = torch.Generator().manual_seed(seed)
+    q = torch.randn(B, V, 4, generator=g)
+    q = q / q.norm(dim=-1, keepdim=True)
+    w, x, y, z = q.unbind(-1)
+    R = torch.stack([1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y), 2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x),
+                     2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)], dim=-1).view(B, V, 3, 3)
+    E = torch.eye(4).repeat(B, V, 1, 1)
+    E[..., :3, :3] = R
+    E[..., :3, 3] = torch.randn(B, V, 3, generator=g)
+    K = torch.eye(3).repeat(B, V, 1, 1)
+    K[..., 0, 0] = 0.8 + 0.4 * torch.rand(B, V, generator=g)
+    K[..., 1, 1] = 0.8 + 0.4 * torch.rand(B, V, generator=g)
+    K[..., 0, 2] = K[..., 1, 2] = 0.5
+    return E, K
+
+
+def test_interpolated_camera_path_properties():
+    from vist3a_b200.renderer import interpolate_context_cameras
+
+    E, K = _poses(0)
+    ex, ix = interpolate_context_cameras(E, K, t=10)
+    assert ex.shape == (2, 33, 4, 4) and ix.shape == (2, 33, 3, 3)            # (V - 1)(t + 1) frames: 132 for 13 views
+    assert torch.equal(ex[:, 0], E[:, 0]) and torch.equal(ex[:, 11], E[:, 1]) and torch.equal(ix[:, 22], K[:, 2])
+    R = ex[..., :3, :3]
+    assert float((R @ R.transpose(-1, -2) - torch.eye(3)).abs().max()) < 1e-5   # projected back onto rotations
+    assert torch.allclose(ex[:, 5, :3, 3], (1 - 5 / 11) * E[:, 0, :3, 3] + 5 / 11 * E[:, 1, :3, 3], atol=1e-6)
+
+
+def test_interpolated_camera_path_matches_live_reference():
+    """the reference's own save_interpolated_video (AS/misc/image_io.py:111-228), run with a decoder stand-in that records the cameras"""
+    import importlib
+
+    import pytest
+
+    from oracle import ref_loader as RL
+
+    if not RL.available():
+        pytest.skip("/root/reference is only mounted in the build container")
+    RL.load_teacher(RL.TINY)   # installs the import stubs (skvideo, matplotlib, ...)
+    io = importlib.import_module("third_party_model.anysplat.src.misc.image_io")
+    from vist3a_b200.renderer import interpolate_context_cameras
+
+    class Stop(Exception):
+        pass
+
+    class Recorder:
+        def forward(self, gaussians, extr, intr, near, far, hw, cov_ignore=False):
+            self.extr, self.intr, self.near, self.far = extr, intr, near, far
+            raise Stop
+
+    E, K = _poses(3, B=1, V=5)
+    rec = Recorder()
+    with pytest.raises(Stop):
+        io.save_interpolated_video(E, K, 1, 448, 448, None, "/tmp", rec, t=10)
+    ex, ix = interpolate_context_cameras(E, K, t=10)
+    assert rec.extr.shape == ex.shape == (1, 44, 4, 4)
+    assert float((rec.extr - ex).abs().max()) < 2e-6 and float((rec.intr - ix).abs().max()) < 1e-6

@@ -96,3 +96,32 @@ def test_renderer_module_on_decoder_sized_scene():
                    rotations=torch.zeros(1, n, 4, device="cuda"))
     out2 = DecoderSplattingB200((1.0, 1.0, 1.0)).rendering_fn(gp, c2w[:, 1:2], Kn[None, None], image_shape=(H, W))
     assert float((out2.color[0, 0] - out.color[0, 1]).abs().max()) < 1e-3   # equal fp32 depths among 2.6 M Gaussians composite in index order
+
+
+def test_text_to_3d_tail_decoder_then_interpolated_video_frames():
+    """the tail of inference_t23d.py:133-155 on the tiny decoder: forward_with_latent -> Gaussians + predicted cameras -> the interpolated camera path
+    of save_interpolated_video -> frames; checked against the oracle renderer on the engine's own Gaussians for one interpolated camera"""
+    from oracle import decoder_ref as D
+    from oracle import gsplat_ref as G
+    from vist3a_b200.renderer import DecoderSplattingB200, interpolate_context_cameras
+    from vist3a_b200.stitched_decoder import DecoderConfig, StitchVAE3DB200
+
+    o = D.TINY
+    sd = D.init_state_dict(o, seed=3)
+    lat, img = D.synthetic_inputs(o, views_latent=2, latent_hw=8, image_hw=56, seed=5)
+    cfg = DecoderConfig(embed_dim=o.embed_dim, num_heads=o.num_heads, dino_blocks=o.dino_blocks, cam_heads=o.cam_heads, dpt_out_channels=o.dpt_out_channels, resolution=64)
+    out = StitchVAE3DB200.from_state_dict(sd, cfg, device="cuda:0").forward_with_latent(lat.cuda(), img.cuda())
+    rend = DecoderSplattingB200((1.0, 1.0, 1.0))
+    frames = rend.render_interpolated_views(out, image_shape=(56, 56), t=2)
+    assert frames.color.shape == (1, 12, 3, 56, 56) and frames.depth.shape == (1, 12, 56, 56)      # (5 - 1)(2 + 1) frames
+    assert bool(torch.isfinite(frames.color).all()) and float(frames.color.min()) >= 0 and float(frames.color.max()) <= 1
+    ex, ix = interpolate_context_cameras(out.pred_context_pose["extrinsic"].float().cpu(), out.pred_context_pose["intrinsic"].float().cpu(), 2)
+    k = 4                                                                                            # an interpolated (not a context) camera
+    K = ix[0, k].clone()
+    K[0] *= 56
+    K[1] *= 56
+    g = out.gaussians
+    want = G.render(g.means[0].cpu(), g.covariances[0].cpu(), g.opacities[0].cpu(), g.harmonics[0].cpu(), torch.linalg.inv(ex[0, k]), K, 56, 56,
+                    background=(1.0, 1.0, 1.0))
+    assert float((frames.color[0, k].permute(1, 2, 0).cpu() - want["rgb"].clamp(0, 1)).abs().max()) < 5e-4
+    assert float((frames.alpha[0, k].cpu() - want["alpha"]).abs().max()) < 5e-4

@@ -21,6 +21,30 @@ class DecoderOutput:   # AS/model/decoder/decoder.py: color [B,V,3,H,W], depth [
     lod_rendering: Optional[dict] = None
 
 
+def interpolate_context_cameras(extrinsics: torch.Tensor, intrinsics: torch.Tensor, t: int = 10):
+    """Camera path of the reference's result video (`save_interpolated_video`, AS/misc/image_io.py:111-183): between every pair of
+    neighbouring context views, the view itself plus t interpolated ones -- translation and intrinsics linearly, rotation as the linear
+    blend of the two matrices projected back onto SO(3) through its SVD (U V^T).  extrinsics [B,V,4,4] camera-to-world, intrinsics
+    [B,V,3,3] -> [B,(V-1)(t+1),4,4], [B,(V-1)(t+1),3,3]  (13 views, t = 10: 132 frames; the last context view is not part of the path,
+    as in the reference, which appends it only after the path has been concatenated, :176-181)."""
+    B, V = extrinsics.shape[:2]
+    ex, ix = [], []
+    for i in range(V - 1):
+        ex.append(extrinsics[:, i:i + 1])
+        ix.append(intrinsics[:, i:i + 1])
+        for j in range(1, t + 1):
+            a = j / (t + 1)
+            s, e = extrinsics[:, i], extrinsics[:, i + 1]
+            rot = (1 - a) * s[:, :3, :3] + a * e[:, :3, :3]
+            u, _, vh = torch.linalg.svd(rot)
+            m = torch.eye(4, device=extrinsics.device, dtype=extrinsics.dtype).unsqueeze(0).repeat(B, 1, 1)
+            m[:, :3, :3] = u @ vh
+            m[:, :3, 3] = (1 - a) * s[:, :3, 3] + a * e[:, :3, 3]
+            ex.append(m.unsqueeze(1))
+            ix.append(((1 - a) * intrinsics[:, i] + a * intrinsics[:, i + 1]).unsqueeze(1))
+    return torch.cat(ex, dim=1), torch.cat(ix, dim=1)
+
+
 class DecoderSplattingB200(torch.nn.Module):
     def __init__(self, background_color: Sequence[float] = (1.0, 1.0, 1.0)):
         super().__init__()
@@ -63,3 +87,11 @@ class DecoderSplattingB200(torch.nn.Module):
         camera-to-world extrinsics, normalised intrinsics) -- the first thing inference_t23d.py:139-155 does with the Gaussians."""
         pose = output.pred_context_pose
         return self.rendering_fn(output.gaussians, pose["extrinsic"], pose["intrinsic"], image_shape=image_shape)
+
+    @torch.no_grad()
+    def render_interpolated_views(self, output, image_shape=(448, 448), t: int = 10) -> DecoderOutput:
+        """The frames of the reference's gs.mp4 (`save_interpolated_video`, inference_t23d.py:146-155): the interpolated camera path through the
+        predicted context views (132 frames for 13 views), rendered from all Gaussians.  Colour clipped to [0, 1] as in :193."""
+        pose = output.pred_context_pose
+        ex, ix = interpolate_context_cameras(pose["extrinsic"].float().cpu(), pose["intrinsic"].float().cpu(), t)
+        return self.rendering_fn(output.gaussians, ex, ix, image_shape=image_shape)
