@@ -1,6 +1,7 @@
 // Stable LSD radix sort of (64-bit key, 32-bit value) pairs, 8-bit digits, shared by the voxelised fusion and the Gaussian rasteriser.
 // One pass = radix_hist_kernel (per-block digit histogram, digit-major table) -> radix_scan_kernel (one block per digit: exclusive scan
-// over the sort blocks + digit totals) -> radix_scatter_kernel (warp-private digit counters + match.any ranking: stable).  Buffers
+// over the sort blocks + digit totals) -> radix_scatter_kernel (warp-private digit counters + match.any ranking: stable; the tile is
+// reordered in shared memory so that digit runs leave as contiguous stores).  Buffers
 // ping-pong between (keys_a, vals_a) and (keys_b, vals_b) with the pass index; `*npasses` (device memory) says how many passes run --
 // launches for later passes return at once, so the host can enqueue the maximum without knowing the key width.  After the sort the data
 // sit in the a-buffers if *npasses is even, in the b-buffers otherwise.
@@ -81,6 +82,13 @@ __global__ void __launch_bounds__(256) radix_scan_kernel(unsigned* __restrict__ 
   if (threadIdx.x == 0) digit_total[blockIdx.x] = carry_s;
 }
 
+constexpr int kScatterSmem = kSortTile * 12 + (kSortThreads / 32) * 256 * 4 + 3 * 256 * 4 + 64;
+
+// Stable scatter of one 4096-key tile.  Ranking: warp w owns a contiguous slice of the tile and walks it in rounds of 32 keys; match.any
+// groups the lanes of a round by digit, the group's first lane bumps the warp-private digit counter, so a key's rank is (keys of that digit
+// earlier in the slice) -- no atomics, order preserved.  The tile is then laid out in digit order in shared memory and written from there:
+// neighbouring threads hold neighbouring keys of a digit run, i.e. the global stores of a run are contiguous (16 keys = 128 bytes on
+// average) instead of 4096 scattered 8- and 4-byte stores.
 __global__ void __launch_bounds__(kSortThreads) radix_scatter_kernel(const unsigned long long* __restrict__ keys_a, unsigned long long* __restrict__ keys_b_,
                                                                      const unsigned* __restrict__ vals_a, unsigned* __restrict__ vals_b_, long long N, int pass,
                                                                      const int* __restrict__ npasses, const unsigned* __restrict__ block_off, int nblocks,
@@ -92,29 +100,36 @@ __global__ void __launch_bounds__(kSortThreads) radix_scatter_kernel(const unsig
   const unsigned* vin = (pass & 1) ? vals_b_ : vals_a;
   unsigned* vout = (pass & 1) ? const_cast<unsigned*>(vals_a) : vals_b_;
   constexpr int NW = kSortThreads / 32;
-  __shared__ unsigned wcnt[NW][256];   // per-warp digit counters, then per-warp exclusive bases
-  __shared__ unsigned dbase[256];      // exclusive scan of the digit totals
-  __shared__ unsigned dwarp[8];
+  extern __shared__ __align__(16) unsigned char radix_smem[];
+  unsigned long long* s_keys = reinterpret_cast<unsigned long long*>(radix_smem);          // [4096] tile in digit order
+  unsigned* s_vals = reinterpret_cast<unsigned*>(radix_smem + kSortTile * 8);              // [4096]
+  unsigned(*wcnt)[256] = reinterpret_cast<unsigned(*)[256]>(radix_smem + kSortTile * 12);   // per-warp digit counters, then tile-local bases
+  unsigned* dbase = reinterpret_cast<unsigned*>(radix_smem + kSortTile * 12 + NW * 1024);   // exclusive scan of the digit totals
+  unsigned* gdel = dbase + 256;                                                             // global position - tile-local position, per digit
+  unsigned* lscan = gdel + 256;                                                             // scratch of the block scans
+  unsigned* dwarp = lscan + 256;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  {
-    const unsigned t = digit_total[threadIdx.x];
-    unsigned incl = t;
+  auto block_excl_scan = [&](unsigned v) {  // exclusive scan over the 256 threads (digits)
+    unsigned incl = v;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       const unsigned u = __shfl_up_sync(0xffffffffu, incl, o);
       if (lane >= o) incl += u;
     }
+    __syncthreads();   // dwarp free again
     if (lane == 31) dwarp[wid] = incl;
     __syncthreads();
     unsigned woff = 0;
 #pragma unroll
     for (int w = 0; w < 8; ++w) woff += (w < wid) ? dwarp[w] : 0u;
-    dbase[threadIdx.x] = woff + incl - t;
-  }
+    return woff + incl - v;
+  };
+  dbase[threadIdx.x] = block_excl_scan(digit_total[threadIdx.x]);
   for (int d = lane; d < 256; d += 32) wcnt[wid][d] = 0;
   __syncwarp();
   // warp w owns the contiguous slice [w * 512, (w + 1) * 512) of the block tile; 16 rounds of 32 keys in order
-  const long long wbase = (long long)blockIdx.x * kSortTile + (long long)wid * (kSortTile / NW);
+  const long long tile0 = (long long)blockIdx.x * kSortTile;
+  const long long wbase = tile0 + (long long)wid * (kSortTile / NW);
   const int shift = pass * 8;
   unsigned long long key[kSortItems];
   unsigned rank[kSortItems];
@@ -138,15 +153,22 @@ __global__ void __launch_bounds__(kSortThreads) radix_scatter_kernel(const unsig
     __syncwarp();
   }
   __syncthreads();
-  // per digit: exclusive scan over the warps, plus the block's global offset
+  // per digit (thread d): tile-local base of the digit, then of every warp inside it; and the shift to the global position
   {
     const int d = threadIdx.x;  // kSortThreads == 256 digits
-    unsigned run = dbase[d] + block_off[(long long)d * nblocks + blockIdx.x];
+    unsigned c[NW], tot = 0;
 #pragma unroll
     for (int w = 0; w < NW; ++w) {
-      const unsigned c = wcnt[w][d];
+      c[w] = wcnt[w][d];
+      tot += c[w];
+    }
+    const unsigned lbase = block_excl_scan(tot);
+    gdel[d] = dbase[d] + block_off[(long long)d * nblocks + blockIdx.x] - lbase;
+    unsigned run = lbase;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) {
       wcnt[w][d] = run;
-      run += c;
+      run += c[w];
     }
   }
   __syncthreads();
@@ -155,22 +177,38 @@ __global__ void __launch_bounds__(kSortThreads) radix_scatter_kernel(const unsig
     const long long i = wbase + r * 32 + lane;
     if (i < N) {
       const unsigned d = (unsigned)(key[r] >> shift) & 255u;
-      const unsigned pos = wcnt[wid][d] + rank[r];
-      kout[pos] = key[r];
-      vout[pos] = vin[i];
+      const unsigned lp = wcnt[wid][d] + rank[r];
+      s_keys[lp] = key[r];
+      s_vals[lp] = vin[i];
+    }
+  }
+  __syncthreads();
+  const int count = (int)min((long long)kSortTile, N - tile0);
+#pragma unroll 4
+  for (int k = 0; k < kSortItems; ++k) {
+    const int j = k * kSortThreads + threadIdx.x;
+    if (j < count) {
+      const unsigned long long kk = s_keys[j];
+      const unsigned pos = (unsigned)j + gdel[(unsigned)(kk >> shift) & 255u];
+      kout[pos] = kk;
+      vout[pos] = s_vals[j];
     }
   }
 }
-
 
 // enqueue `max_passes` passes; block_hist holds 256 * nblocks counters, digit_total 256
 inline void radix_sort_enqueue(unsigned long long* keys_a, unsigned long long* keys_b, unsigned* vals_a, unsigned* vals_b, long long n, int max_passes,
                                const int* npasses, unsigned* block_hist, unsigned* digit_total, cudaStream_t st) {
   const int nblocks = (int)((n + kSortTile - 1) / kSortTile);
+  static bool attr_set = false;  // one copy of the kernel (and of this flag) per translation unit
+  if (!attr_set) {
+    cudaFuncSetAttribute(radix_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kScatterSmem);
+    attr_set = true;
+  }
   for (int pass = 0; pass < max_passes; ++pass) {
     radix_hist_kernel<<<nblocks, kSortThreads, 0, st>>>(keys_a, keys_b, n, pass, npasses, block_hist, nblocks);
     radix_scan_kernel<<<256, 256, 0, st>>>(block_hist, nblocks, digit_total, pass, npasses);
-    radix_scatter_kernel<<<nblocks, kSortThreads, 0, st>>>(keys_a, keys_b, vals_a, vals_b, n, pass, npasses, block_hist, nblocks, digit_total);
+    radix_scatter_kernel<<<nblocks, kSortThreads, kScatterSmem, st>>>(keys_a, keys_b, vals_a, vals_b, n, pass, npasses, block_hist, nblocks, digit_total);
   }
 }
 
