@@ -264,6 +264,68 @@ __global__ void __launch_bounds__(256) qknorm_rope2d_kernel(__nv_bfloat16* __res
   }
 }
 
+// Same operation with ONE THREAD per (row, q|k, head): the 64 values of a head are 128 contiguous bytes (eight 16-byte loads), the
+// LayerNorm statistics and the rotate-half pairs (j, j+16) are thread-local -- no shuffles, 16-byte accesses, and a warp covers the 4 KB of
+// one row's q|k heads.  (The warp-per-head kernel above moves 4 bytes per lane and ran at 2.3 TB/s; kept for strides that are not
+// multiples of 8 elements.)
+__global__ void __launch_bounds__(128) qknorm_rope2d_head_kernel(__nv_bfloat16* __restrict__ qkv, long long ld, long long rows, int heads,
+                                                                 const float* __restrict__ qw, const float* __restrict__ qb, const float* __restrict__ kw,
+                                                                 const float* __restrict__ kb, float eps, const float* __restrict__ cos_tab,
+                                                                 const float* __restrict__ sin_tab, int tokens_per_view, int n_special, int grid_w) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= rows * 2 * heads) return;
+  const int head = (int)(t % heads);
+  const int which = (int)((t / heads) & 1);
+  const long long row = t / (2 * heads);
+  const int p = (int)(row % tokens_per_view);
+  int py = 0, px = 0;
+  if (p >= n_special) {
+    py = 1 + (p - n_special) / grid_w;
+    px = 1 + (p - n_special) % grid_w;
+  }
+  uint4* ptr = reinterpret_cast<uint4*>(qkv + row * ld + ((long long)which * heads + head) * 64);
+  const float* wgt = which == 0 ? qw : kw;
+  const float* bia = which == 0 ? qb : kb;
+  float x[64];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const uint4 u = ptr[k];
+    x[8 * k] = bf16_lo(u.x); x[8 * k + 1] = bf16_hi(u.x); x[8 * k + 2] = bf16_lo(u.y); x[8 * k + 3] = bf16_hi(u.y);
+    x[8 * k + 4] = bf16_lo(u.z); x[8 * k + 5] = bf16_hi(u.z); x[8 * k + 6] = bf16_lo(u.w); x[8 * k + 7] = bf16_hi(u.w);
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int e = 0; e < 64; ++e) s += x[e];
+  const float mean = s * (1.0f / 64.0f);
+  float ss = 0.f;
+#pragma unroll
+  for (int e = 0; e < 64; ++e) {
+    x[e] -= mean;
+    ss += x[e] * x[e];
+  }
+  const float rstd = rsqrtf(ss * (1.0f / 64.0f) + eps);
+#pragma unroll
+  for (int e = 0; e < 64; ++e) x[e] = x[e] * rstd * __ldg(wgt + e) + __ldg(bia + e);
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int pos = h == 0 ? py : px;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const float c = __ldg(cos_tab + pos * 16 + j), sn = __ldg(sin_tab + pos * 16 + j);
+      const float a = x[h * 32 + j], b = x[h * 32 + j + 16];
+      x[h * 32 + j] = a * c - b * sn;
+      x[h * 32 + j + 16] = b * c + a * sn;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    uint4 u;
+    u.x = pack_bf16(x[8 * k], x[8 * k + 1]); u.y = pack_bf16(x[8 * k + 2], x[8 * k + 3]);
+    u.z = pack_bf16(x[8 * k + 4], x[8 * k + 5]); u.w = pack_bf16(x[8 * k + 6], x[8 * k + 7]);
+    ptr[k] = u;
+  }
+}
+
 int qknorm_rope2d_entry(void* qkv, long long ld, long long rows, long long heads, const float* qw, const float* qb,
                         const float* kw, const float* kb, float eps, const float* cos_tab, const float* sin_tab,
                         long long max_pos, long long tpv, long long n_special, long long grid_w, cudaStream_t st) {
@@ -273,8 +335,12 @@ int qknorm_rope2d_entry(void* qkv, long long ld, long long rows, long long heads
   const long long npatch = tpv - n_special;
   const long long need = 1 + (npatch > 0 ? ((npatch - 1) / grid_w + 1 > grid_w ? (npatch - 1) / grid_w + 1 : grid_w) : 0);
   V3A_REQUIRE(max_pos >= need, VIST3A_ERR_INVALID, "qknorm_rope2d: rope table has %lld positions, %lld needed", max_pos, need);
-  qknorm_rope2d_kernel<<<grid_for(rows * heads, 8), 256, 0, st>>>((__nv_bfloat16*)qkv, ld, rows, (int)heads, qw, qb, kw, kb, eps,
-                                                                  cos_tab, sin_tab, (int)tpv, (int)n_special, (int)grid_w);
+  if (ld % 8 == 0 && ((uintptr_t)qkv & 15) == 0)
+    qknorm_rope2d_head_kernel<<<grid_for(rows * 2 * heads, 128), 128, 0, st>>>((__nv_bfloat16*)qkv, ld, rows, (int)heads, qw, qb, kw, kb, eps, cos_tab,
+                                                                              sin_tab, (int)tpv, (int)n_special, (int)grid_w);
+  else
+    qknorm_rope2d_kernel<<<grid_for(rows * heads, 8), 256, 0, st>>>((__nv_bfloat16*)qkv, ld, rows, (int)heads, qw, qb, kw, kb, eps,
+                                                                    cos_tab, sin_tab, (int)tpv, (int)n_special, (int)grid_w);
   V3A_CUDA_OK(cudaGetLastError());
   launch_counter().fetch_add(1);
   return VIST3A_OK;
