@@ -34,7 +34,7 @@ extern "C" {
 #define VIST3A_DTYPE_F32 1
 
 const char* vist3a_last_error(void);
-int vist3a_abi_version(void); /* 4 */
+int vist3a_abi_version(void); /* 5 */
 /* number of kernels this library has launched from the calling process (all threads) */
 int64_t vist3a_launch_count(void);
 /* Programmatic dependent launch (PDL) of the hot kernels (GEMM, attention, LayerNorm, RMSNorm+RoPE, row_rinv): each is launched
@@ -298,10 +298,14 @@ int vist3a_fma_rows(float* out, int64_t ldo, const float* a, int64_t lda, const 
 /* transposed epilogue of a swapped-operand skinny linear.  For M <= 16 tokens the weight matrix is the streamed (A) operand
  * of vist3a_gemm:  ct[n, m] = sum_k W[n, k] x[m, k]  (ct is [N, ldct >= 16] fp32); this finishes
  *   y[m, n] = residual[m, n] + gate[n] * act(ct[n, m] + bias[n])        (bias / gate / residual optional)
+ * splits = S > 1: split-K by reshaping, so that a 2048-row weight matrix fills the GPU instead of 16 CTAs -- the caller ran the GEMM on
+ *   W viewed as [N*S, K/S] (row n*S + s = the s-th K-slice of row n: the same memory) against x viewed as [16*S, K/S]; the partial sums
+ *   of output (n, m) are the diagonal blocks ct[n*S + s, m*S + s], summed here (the off-diagonal products are wasted tensor work on a
+ *   weight-bandwidth-bound operation).
  * replaces: bias, activation, LayerScale and residual add of the nn.Linear layers inside the camera-head trunk
  *   (AS/.../heads/camera_head.py:87-170; Block.forward AS/.../layers/block.py:81-107 at 13 tokens). */
 int vist3a_bias_act_t(const float* ct, int64_t ldct, const float* bias, int32_t act, const float* gate, const float* residual,
-                      int64_t ldr, float* y, int64_t ldy, int64_t M, int64_t N, void* stream);
+                      int64_t ldr, float* y, int64_t ldy, int64_t M, int64_t N, int32_t splits, void* stream);
 
 /* camera head output: activate pose encodings (relu on the 2 FoV entries) and build cameras.
  *   pose_raw [S, 9] -> pose_act [S, 9]; extr [S, 3, 4] world->cam; intr [S, 3, 3] in pixels;

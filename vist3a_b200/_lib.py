@@ -191,7 +191,7 @@ def load(build_if_missing: bool = False) -> C.CDLL:
     lib.vist3a_rgb_to_nhwc4pad.argtypes = [vp, i32, vp, i64, i64, i64, i64, vp]
     lib.vist3a_rgb01_views_to_nhwc4pad.argtypes = [vp, i32, vp, i64, i64, i64, i64, vp]
     lib.vist3a_patch_embed_im2col.argtypes = [vp, i32, vp, i64, i64, i64, i64, i32, C.POINTER(f32), C.POINTER(f32), vp]
-    lib.vist3a_bias_act_t.argtypes = [vp, i64, vp, i32, vp, vp, i64, vp, i64, i64, i64, vp]
+    lib.vist3a_bias_act_t.argtypes = [vp, i64, vp, i32, vp, vp, i64, vp, i64, i64, i64, i32, vp]
     lib.vist3a_pose_to_cameras.argtypes = [vp, vp, vp, vp, vp, vp, i64, i64, i64, vp]
     lib.vist3a_gaussian_epilogue.argtypes = [vp, i64, i64, vp, f32, vp, i64, vp, vp, vp, i64, i64, i64, i64, vp, vp, vp, vp, vp, vp,
                                              vp, vp, vp]

@@ -29,7 +29,7 @@ int bilinear_nhwc_entry(const float*, float*, long long, long long, long long, l
 int depth_to_space_entry(const float*, float*, long long, long long, long long, long long, int, cudaStream_t);
 int attention_small_entry(const float*, float*, long long, long long, long long, long long, float, cudaStream_t);
 int bias_act_t_entry(const float*, long long, const float*, int, const float*, const float*, long long, float*, long long, long long,
-                     long long, cudaStream_t);
+                     long long, int, cudaStream_t);
 int rgb_to_nhwc4pad_entry(const void*, int, float*, long long, long long, long long, long long, int, float, float, cudaStream_t);
 int patch_embed_im2col_entry(const void*, int, void*, long long, long long, long long, long long, int, const float*, const float*, cudaStream_t);
 int fma_rows_entry(float*, long long, const float*, long long, const float*, long long, const float*, long long, long long,
@@ -165,7 +165,7 @@ using namespace v3a;
 extern "C" {
 
 const char* vist3a_last_error(void) { return last_error_buf(); }
-int vist3a_abi_version(void) { return 4; }
+int vist3a_abi_version(void) { return 5; }
 int64_t vist3a_launch_count(void) { return (int64_t)launch_counter().load(); }
 int vist3a_set_pdl(int32_t enable) { return set_pdl(enable); }
 
@@ -259,8 +259,8 @@ int vist3a_fma_rows(float* out, int64_t ldo, const float* a, int64_t lda, const 
   return fma_rows_entry(out, ldo, a, lda, b, ldb, c, ldc, rows, dim, ST(stream));
 }
 int vist3a_bias_act_t(const float* ct, int64_t ldct, const float* bias, int32_t act, const float* gate, const float* residual,
-                      int64_t ldr, float* y, int64_t ldy, int64_t M, int64_t N, void* stream) {
-  return bias_act_t_entry(ct, ldct, bias, act, gate, residual, ldr, y, ldy, M, N, ST(stream));
+                      int64_t ldr, float* y, int64_t ldy, int64_t M, int64_t N, int32_t splits, void* stream) {
+  return bias_act_t_entry(ct, ldct, bias, act, gate, residual, ldr, y, ldy, M, N, splits, ST(stream));
 }
 int vist3a_rgb_to_nhwc4pad(const void* image, int32_t dtype, float* out, int64_t B, int64_t V, int64_t H, int64_t W, void* stream) {
   return rgb_to_nhwc4pad_entry(image, dtype, out, B, V, H, W, 0, 0.5f, 0.5f, ST(stream));

@@ -519,11 +519,13 @@ __device__ __forceinline__ float act_apply_f(float v, int act) {
 }
 __global__ void __launch_bounds__(256) bias_act_t_kernel(const float* __restrict__ ct, long long ldct, const float* __restrict__ bias,
                                                          int act, const float* __restrict__ gate, const float* __restrict__ res,
-                                                         long long ldr, float* __restrict__ y, long long ldy, int M, int N) {
+                                                         long long ldr, float* __restrict__ y, long long ldy, int M, int N, int splits) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)M * N) return;
   const int n = (int)(i % N), m = (int)(i / N);  // consecutive threads -> consecutive n: coalesced y / bias / gate / residual
-  float v = ct[(long long)n * ldct + m] + (bias ? bias[n] : 0.f);
+  // split-K by reshaping (see vist3a_bias_act_t): partial s of output (n, m) sits at row n * splits + s, column m * splits + s
+  float v = bias ? bias[n] : 0.f;
+  for (int sp = 0; sp < splits; ++sp) v += ct[((long long)n * splits + sp) * ldct + (long long)m * splits + sp];
   v = act_apply_f(v, act);
   if (gate) v *= gate[n];
   if (res) v += res[(long long)m * ldr + n];
@@ -531,10 +533,11 @@ __global__ void __launch_bounds__(256) bias_act_t_kernel(const float* __restrict
 }
 
 int bias_act_t_entry(const float* ct, long long ldct, const float* bias, int act, const float* gate, const float* res, long long ldr,
-                     float* y, long long ldy, long long M, long long N, cudaStream_t st) {
-  V3A_REQUIRE(ct && y && M > 0 && N > 0 && ldct >= M && ldy >= N, VIST3A_ERR_INVALID, "bias_act_t: bad arguments");
+                     float* y, long long ldy, long long M, long long N, int splits, cudaStream_t st) {
+  V3A_REQUIRE(ct && y && M > 0 && N > 0 && ldct >= M * (splits > 0 ? splits : 1) && ldy >= N, VIST3A_ERR_INVALID, "bias_act_t: bad arguments");
   V3A_REQUIRE(!res || ldr >= N, VIST3A_ERR_INVALID, "bias_act_t: residual stride");
-  bias_act_t_kernel<<<grid_for(M * N, 256), 256, 0, st>>>(ct, ldct, bias, act, gate, res, ldr, y, ldy, (int)M, (int)N);
+  V3A_REQUIRE(splits >= 1 && splits <= 64, VIST3A_ERR_INVALID, "bias_act_t: splits must be in [1, 64]");
+  bias_act_t_kernel<<<grid_for(M * N, 256), 256, 0, st>>>(ct, ldct, bias, act, gate, res, ldr, y, ldy, (int)M, (int)N, splits);
   V3A_CUDA_OK(cudaGetLastError());
   launch_counter().fetch_add(1);
   return VIST3A_OK;

@@ -434,12 +434,21 @@ def linear_tokens16(x16: torch.Tensor, M: int, w: torch.Tensor, bias: Optional[t
     TP = x16.shape[0]
     if TP not in (16, 32) or not x16.is_contiguous() or M > TP:
         raise ValueError("linear_tokens16: x16 must be a contiguous [16 or 32, K] buffer holding M <= rows token rows")
-    N = w.shape[0]
-    ct = gemm(w, x16, out_dtype=torch.float32, two_cta=False)  # [N, TP] = W x^T
+    N, K = w.shape
+    # split-K by reshaping: W [N, K] is the same memory as [N*S, K/S] (row n*S + s = K-slice s of row n), x16 the same as [TP*S, K/S]; the
+    # GEMM then has N*S/128 CTAs streaming weights instead of N/128 (16 for a 2048-row matrix on 148 SMs) and bias_act_t sums the
+    # diagonal blocks ct[n*S + s, m*S + s].  S: smallest power of two that gives >= 96 CTAs, K/S a multiple of 32 floats, TP*S <= 256.
+    S = 1
+    while w.is_contiguous() and (N * S) // 128 < 96 and S < 8 and (K // (2 * S)) % 32 == 0 and TP * 2 * S <= 256:
+        S *= 2
+    if S > 1:
+        ct = gemm(w.view(N * S, K // S), x16.view(TP * S, K // S), out_dtype=torch.float32, two_cta=False)   # [N*S, TP*S]
+    else:
+        ct = gemm(w, x16, out_dtype=torch.float32, two_cta=False)  # [N, TP] = W x^T
     if out is None:
         out = torch.zeros((TP, N), dtype=torch.float32, device=x16.device)
     L.check(L.load().vist3a_bias_act_t(ct.data_ptr(), ct.stride(0), _ptr(bias), ACT[act], _ptr(gate), _ptr(residual),
-                                       residual.stride(0) if residual is not None else 0, out.data_ptr(), out.stride(0), M, N,
+                                       residual.stride(0) if residual is not None else 0, out.data_ptr(), out.stride(0), M, N, S,
                                        _stream()))
     return out
 
