@@ -341,6 +341,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll 1
       for (int k = 0; chunk_ok(k); ++k) {
         const int n0 = n_tile + chunk_of(k) * 32;
+        // bias of this chunk: issued before the wait for the accumulator so that its (L2) latency overlaps the TMEM read
+        // (ncu: the FADDs consuming a just-issued bias load were the hottest stall of the epilogue)
+        float4 bvv[8];
+        if (ep.bias) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) bvv[j] = (n0 + 4 * j < shape.N) ? __ldg(reinterpret_cast<const float4*>(ep.bias + n0) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
         tmem_ld_wait();
         float v[32];
 #pragma unroll
@@ -389,10 +396,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           if (ep.bias) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
-              if (j < ncols) {
-                const float4 bv = __ldg(reinterpret_cast<const float4*>(ep.bias + n0 + j));
-                v[j] += bv.x; v[j + 1] += bv.y; v[j + 2] += bv.z; v[j + 3] += bv.w;
-              }
+              const float4 bv = bvv[j >> 2];
+              v[j] += bv.x; v[j + 1] += bv.y; v[j + 2] += bv.z; v[j + 3] += bv.w;
             }
           }
           if (ep.act != VIST3A_ACT_NONE) apply_act32(v, ep.act);
