@@ -33,6 +33,7 @@ struct FmhaParams {
   float scale_log2;  // scale * log2(e)
   const float* row_scale;  // optional per-(batch, query row) positive factor on the logits
   int single_issuer;       // one MMA-issuing warp for both query tiles (flags bit 2)
+  int direct_store;        // per-thread output stores instead of shared memory + bulk tensor store (flags bit 6, A/B)
   long long* trace;        // debug: 32 clock64 stamps / phase sums per CTA (v3a_debug_fmha_trace), normally null
 };
 
@@ -526,6 +527,26 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       tc_fence_after();
       if (warp == 4 && lane == 0) FMHA_TRACE(9);
       const float inv_l = 1.0f / l_run;
+      if (p.direct_store) {  // A/B (flags bit 6): per-thread row stores
+        __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(p.O) + (long long)batch * p.o_bs + (long long)row * p.o_rs + (long long)head * p.o_hs + h * OC;
+#pragma unroll
+        for (int cb = 0; cb < OC / 32; ++cb) {
+          uint32_t o[32];
+          tmem_ld_x32(o_addr + (uint32_t)(cb * 32), o);
+          tmem_ld_wait();
+          if (row < p.len_q) {
+#pragma unroll
+            for (int k = 0; k < 32; k += 8) {
+              uint4 w;
+              w.x = pack_bf16(__uint_as_float(o[k]) * inv_l, __uint_as_float(o[k + 1]) * inv_l);
+              w.y = pack_bf16(__uint_as_float(o[k + 2]) * inv_l, __uint_as_float(o[k + 3]) * inv_l);
+              w.z = pack_bf16(__uint_as_float(o[k + 4]) * inv_l, __uint_as_float(o[k + 5]) * inv_l);
+              w.w = pack_bf16(__uint_as_float(o[k + 6]) * inv_l, __uint_as_float(o[k + 7]) * inv_l);
+              *reinterpret_cast<uint4*>(orow + cb * 32 + k) = w;
+            }
+          }
+        }
+      } else {
       // O / l -> bf16 -> this tile's Q buffer (free: every MMA has completed) in the 128B-swizzled box layout, then ONE bulk tensor store
       // per 64-column slab.  (Per-thread row stores are uncoalesced -- 32 rows per instruction -- and cost ~7000 cycles per CTA.)
       // Rows past len_q are clipped by the TMA unit.
@@ -556,6 +577,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           tma_store_4d(&tmO, smem_q(i) + sl * Cfg::Q_SLAB_BYTES, sl * 64, head, q0 + i * Cfg::BQ, batch);
         tma_store_commit();
         tma_store_wait_read<0>();  // the buffer must stay intact until the TMA unit has read it (the CTA exits next)
+      }
       }
       if (warp == 4 && lane == 0) FMHA_TRACE(10);
     }
@@ -596,6 +618,7 @@ static int launch_fmha(const vist3a_fmha_args& a, cudaStream_t stream) {
   p.row_scale = a.q_row_scale;
   p.trace = g_fmha_trace;
   p.single_issuer = (a.flags & 4u) ? 1 : 0;
+  p.direct_store = (a.flags & 64u) ? 1 : 0;
   auto kern = fmha_fwd_kernel<D, BKV_, POLY_, SPLIT_>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -633,7 +656,7 @@ int fmha_entry(const vist3a_fmha_args* args, cudaStream_t stream) {
   // two threads per query row (4 softmax warpgroups): the softmax is bound by issue slots and dependent-latency chains rather than by
   // the MUFU, so the default is 0 (all MUFU.EX2): +4 % at d=128 / 4096 keys, +9 % at d=64 / 13377 keys over the former 2 / 3 of 8; short
   // key sequences (cross-attention, 512 keys) keep 2 of 8.  flags >> 3 = 1 + share selects a variant explicitly (A/B).
-  const unsigned poly_sel = a.flags >> 3;
+  const unsigned poly_sel = (a.flags >> 3) & 7u;
   if (a.head_dim == 64) {
     if (one) return launch_fmha<64, 128, 3, 1>(a, stream);
     if (poly_sel == 2u) return launch_fmha<64, 128, 1, 2>(a, stream);
