@@ -65,6 +65,12 @@ def _worker(rank, world, port, q):
                 ok = ok and (("covariances" in got[r]) == cov)
                 for k, v in got[r].items():
                     ok = ok and torch.equal(v, getattr(want, k))
+        # ragged: voxelised fusion leaves a different number of Gaussians on every rank
+        got = all_gather_gaussians(_gauss(200 + rank, n=11 + 5 * rank), with_covariances=True)
+        for r in range(world):
+            want = _gauss(200 + r, n=11 + 5 * r)
+            for k, v in got[r].items():
+                ok = ok and v.shape == getattr(want, k).shape and torch.equal(v, getattr(want, k))
         q.put((rank, ok))
     finally:
         dist.destroy_process_group()

@@ -108,10 +108,28 @@ def all_gather_gaussians(g: Gaussians, group=None, with_covariances: bool = Fals
     the received segments are viewed, not copied (2.1 ms for 2 x 0.99 GB over NVLink; packing records with torch.cat and re-splitting them
     cost 35 ms).  Gaussians built elsewhere (no `packed`) take the record path."""
     import torch.distributed as dist
+    import torch.nn.functional as F
 
     world = dist.get_world_size(group)
     B, N = g.opacities.shape
     d_sh = g.harmonics.shape[-1]
+    # voxelised fusion makes the Gaussian count data dependent: agree on the counts first (one tiny collective); ranks with fewer Gaussians
+    # pad to the largest count with the reference's fill values (points -1e4, opacity 0: models/anysplat_stitched.py:448-455) and every
+    # returned dict is cut back to its rank's own count
+    counts = torch.tensor([N], dtype=torch.int64, device=g.opacities.device)
+    all_counts = torch.empty((world,), dtype=torch.int64, device=counts.device)
+    dist.all_gather_into_tensor(all_counts, counts, group=group)
+    all_counts = [int(c) for c in all_counts.tolist()]
+    nmax = max(all_counts)
+    if min(all_counts) != nmax:
+        pad = nmax - N
+
+        def padn(t, value=0.0):
+            return F.pad(t, (0, 0) * (t.dim() - 2) + (0, pad), value=value) if pad else t
+
+        g = Gaussians(means=padn(g.means, -1e4), covariances=padn(g.covariances), harmonics=padn(g.harmonics), opacities=padn(g.opacities),
+                      scales=padn(g.scales), rotations=padn(g.rotations))
+        N = nmax
     if g.packed is not None:
         per = B * N * (11 + 3 * d_sh + (9 if with_covariances else 0))   # covariances are the last field: leave them out by length
         src = g.packed[:per]
@@ -121,4 +139,5 @@ def all_gather_gaussians(g: Gaussians, group=None, with_covariances: bool = Fals
     rec = pack_gaussians(g, with_covariances)
     out = torch.empty((world * B,) + tuple(rec.shape[1:]), dtype=rec.dtype, device=rec.device)  # rank-major concatenation
     dist.all_gather_into_tensor(out, rec, group=group)
-    return [unpack_gaussians(out[r * B:(r + 1) * B], d_sh, with_covariances) for r in range(world)]
+    res = [unpack_gaussians(out[r * B:(r + 1) * B], d_sh, with_covariances) for r in range(world)]
+    return [{k: v[:, :all_counts[r]] for k, v in d.items()} for r, d in enumerate(res)]
