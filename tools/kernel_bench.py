@@ -50,8 +50,8 @@ def main():
         bias = torch.randn(N, device="cuda")
         out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
         r = {"name": name, "M": M, "N": N, "K": K}
-        for tag, two, b176 in (("2cta", True, False), ("2cta_bn176", True, True), ("1cta", False, False)):
-            ms = timeit(lambda: ops.gemm(x, w, bias, out=out, two_cta=two, bn176=b176), a.iters, flush=flush)
+        for tag, two, b176, mc in (("2cta", True, False, False), ("2cta_mc", True, False, True), ("2cta_bn176", True, True, False), ("1cta", False, False, False)):
+            ms = timeit(lambda: ops.gemm(x, w, bias, out=out, two_cta=two, bn176=b176, multicast=mc), a.iters, flush=flush)
             r[tag + "_ms"] = round(ms, 4)
             r[tag + "_tflops"] = round(2 * M * N * K / ms / 1e9, 1)
         if not a.no_torch:

@@ -50,6 +50,7 @@ constexpr int kConvTW = 16, kConvTH = 8;  // pixel patch of one 128-row A tile
 struct GemmShape {
   int M, N, K;
   int tiles_m, tiles_n;  // tiles_m counts 128*kCta-row tiles
+  int mc;                // clusters of two CTA pairs on neighbouring column tiles, the shared A rows multicast between them (kCta == 2 only)
   // conv mode
   int conv, kh, kw, pad_y, pad_x, n_img, h, w, c_in, h_out, w_out, tiles_x, tiles_y, cblocks;
 };
@@ -126,7 +127,7 @@ constexpr int kGemmThreads = 384;  // warps 0-3: TMA / MMA / TMEM alloc / idle; 
 
 template <int BN, int kCta, bool kTF32>
 __global__ void __launch_bounds__(kGemmThreads, 1)
-gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmA64,
                     const GemmShape shape, const GemmEpilogue ep) {
   using Cfg = GemmCfg<BN, kCta, kTF32>;
   constexpr int STAGES = Cfg::STAGES;
@@ -144,7 +145,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
   const uint32_t warp = warp_id_sync();
   const uint32_t lane = lane_id();
-  const uint32_t rank = (kCta == 2) ? cluster_ctarank() : 0u;
+  // Multicast mode (shape.mc): the cluster holds TWO pairs working on column tiles 2 tnp and 2 tnp + 1 of the same 256 rows.  Every CTA
+  // fetches one 64-row half of its 128 A rows and multicasts it to its twin in the other pair (same rank inside the pair), so the A
+  // operand crosses L2 -> SM once per cluster instead of once per pair (-25 % operand traffic per flop).
+  const uint32_t crank = (kCta == 2) ? cluster_ctarank() : 0u;
+  const uint32_t rank = crank & 1u;       // rank inside the CTA pair
+  const uint32_t pr = crank >> 1;         // pair inside the cluster (0 unless shape.mc)
+  const int csize = (kCta == 2 && shape.mc) ? 4 : kCta;
   const bool leader = (rank == 0);
 
   if (warp == 0 && lane == 0) {
@@ -154,7 +161,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
+      mbar_init(empty_bar(s), shape.mc ? 2 : 1);  // multicast: a slot is free once BOTH pairs of the cluster have consumed it
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
@@ -173,9 +180,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   pdl_wait();
 
   const int num_kb = shape.conv ? shape.kh * shape.kw * shape.cblocks : (shape.K + Cfg::BK - 1) / Cfg::BK;
-  const int num_tiles = shape.tiles_m * shape.tiles_n;
-  const int worker = blockIdx.x / kCta;
-  const int num_workers = gridDim.x / kCta;
+  const int num_tiles = shape.mc ? shape.tiles_m * (shape.tiles_n / 2) : shape.tiles_m * shape.tiles_n;
+  const int worker = blockIdx.x / csize;
+  const int num_workers = gridDim.x / csize;
+  auto tile_n_of = [&](int tile) { return shape.mc ? 2 * (tile / shape.tiles_m) + (int)pr : tile / shape.tiles_m; };
 
   if (warp == 0) {
     // ------------------------------ TMA producer ------------------------------
@@ -186,7 +194,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     long long tr_wait = 0;
     const long long tr_t0 = ep.trace ? clock64() : 0;
     for (int tile = worker; tile < num_tiles; tile += num_workers) {
-      const int tm = tile % shape.tiles_m, tn = tile / shape.tiles_m;
+      const int tm = tile % shape.tiles_m, tn = tile_n_of(tile);
       const int mt = tm * kCta + (int)rank;  // this CTA's 128-row tile
       const int m0 = mt * Cfg::BM;
       const int n0 = tn * BN + (int)rank * Cfg::BN_LOCAL;
@@ -216,6 +224,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           } else {
             if (leader) mbar_expect_tx(full_bar(s), 2 * Cfg::STAGE_BYTES);
             if (shape.conv) tma_load_4d_2sm(smem_a(s), &tmA, full_bar(s), cb * Cfg::BK, x0 + dx, y0 + dy, img);
+            else if (shape.mc)
+              tma_load_2d_2sm_mc(smem_a(s) + pr * (Cfg::A_BYTES / 2), &tmA64, full_bar(s), kb * Cfg::BK, m0 + (int)pr * (Cfg::BM / 2),
+                                 (uint16_t)((1u << rank) | (1u << (rank + 2))));
             else tma_load_2d_2sm(smem_a(s), &tmA, full_bar(s), kb * Cfg::BK, m0);
             tma_load_2d_2sm(smem_b(s), &tmB, full_bar(s), kb * Cfg::BK, n0);
           }
@@ -270,9 +281,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               if constexpr (kTF32) umma_tf32_ss<kCta>(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) ? 1u : 0u);
               else umma_f16_ss<kCta>(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) ? 1u : 0u);
             }
-            if constexpr (kCta == 1) umma_commit(empty_bar(s)); else umma_commit_2sm_mc(empty_bar(s), 3);
+            if constexpr (kCta == 1) umma_commit(empty_bar(s)); else umma_commit_2sm_mc(empty_bar(s), shape.mc ? 15 : 3);
             if (kb == num_kb - 1) {
-              if constexpr (kCta == 1) umma_commit(tfull_bar(as)); else umma_commit_2sm_mc(tfull_bar(as), 3);
+              if constexpr (kCta == 1) umma_commit(tfull_bar(as)); else umma_commit_2sm_mc(tfull_bar(as), (uint16_t)(3u << (2 * pr)));
             }
           }
           __syncwarp();
@@ -298,7 +309,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     long long tr_tfull = 0;
     const long long tr_t0 = ep.trace ? clock64() : 0;
     for (int tile = worker; tile < num_tiles; tile += num_workers) {
-      const int tm = tile % shape.tiles_m, tn = tile / shape.tiles_m;
+      const int tm = tile % shape.tiles_m, tn = tile_n_of(tile);
       const int mt = tm * kCta + (int)rank;
       const int r_in_tile = (int)(q * 32u + lane);
       long long row;
@@ -361,7 +372,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           tc_fence_before();
           __syncwarp();
           if (lane == 0) {
-            if constexpr (kCta == 1) mbar_arrive(tempty_bar(as)); else mbar_arrive_cluster(tempty_bar(as), 0);
+            if constexpr (kCta == 1) mbar_arrive(tempty_bar(as)); else mbar_arrive_cluster(tempty_bar(as), 2 * pr);
           }
           released = true;
         }
@@ -504,7 +515,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         tc_fence_before();
         __syncwarp();
         if (lane == 0) {
-          if constexpr (kCta == 1) mbar_arrive(tempty_bar(as)); else mbar_arrive_cluster(tempty_bar(as), 0);
+          if constexpr (kCta == 1) mbar_arrive(tempty_bar(as)); else mbar_arrive_cluster(tempty_bar(as), 2 * pr);
         }
       }
       if (++as == 2) { as = 0; aph ^= 1u; }
@@ -531,7 +542,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 template <int BN, int kCta, bool kTF32>
 static int launch_gemm(const vist3a_gemm_args& a, cudaStream_t stream) {
   using Cfg = GemmCfg<BN, kCta, kTF32>;
-  CUtensorMap tmA, tmB;
+  CUtensorMap tmA, tmB, tmA64;
   GemmShape shape = {};
   shape.M = (int)a.M; shape.N = (int)a.N; shape.K = (int)a.K;
   if (a.conv.enabled) {
@@ -560,6 +571,9 @@ static int launch_gemm(const vist3a_gemm_args& a, cudaStream_t stream) {
     uint32_t box[2] = {(uint32_t)Cfg::BK, (uint32_t)Cfg::BM};
     int rc = encode_tensor_map(&tmA, a.A, Cfg::ES, kTF32, 2, dims, strides, box, true);
     if (rc) return rc;
+    uint32_t box64[2] = {(uint32_t)Cfg::BK, (uint32_t)Cfg::BM / 2};
+    rc = encode_tensor_map(&tmA64, a.A, Cfg::ES, kTF32, 2, dims, strides, box64, true);
+    if (rc) return rc;
   }
   {
     uint64_t dims[2] = {(uint64_t)a.K, (uint64_t)a.N};
@@ -586,11 +600,32 @@ static int launch_gemm(const vist3a_gemm_args& a, cudaStream_t stream) {
     V3A_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set = true;
   }
-  const int tiles = shape.tiles_m * shape.tiles_n;
-  int workers = num_sms() / kCta;
+  if (a.conv.enabled) tmA64 = tmA;
+  shape.mc = (kCta == 2 && BN == 256 && !a.conv.enabled && (a.flags & VIST3A_GEMM_FLAG_MULTICAST) && shape.tiles_n % 2 == 0) ? 1 : 0;
+  const int csize = shape.mc ? 4 : kCta;
+  const int tiles = shape.mc ? shape.tiles_m * (shape.tiles_n / 2) : shape.tiles_m * shape.tiles_n;
+  int workers = num_sms() / csize;
+  if (shape.mc) {
+    // clusters of 4 must sit inside one GPC: fewer than num_sms / 4 may be resident at once, and a persistent kernel must not launch more
+    static int max_clusters = 0;
+    if (max_clusters == 0) {
+      cudaLaunchConfig_t qc = {};
+      qc.gridDim = dim3((unsigned)(workers * 4));
+      qc.blockDim = dim3(kGemmThreads);
+      qc.dynamicSmemBytes = Cfg::SMEM_BYTES;
+      cudaLaunchAttribute qa[1];
+      qa[0].id = cudaLaunchAttributeClusterDimension;
+      qa[0].val.clusterDim.x = 4; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
+      qc.attrs = qa; qc.numAttrs = 1;
+      int n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, kern, &qc) != cudaSuccess || n <= 0) n = workers;
+      max_clusters = n;
+    }
+    if (workers > max_clusters) workers = max_clusters;
+  }
   if (workers > tiles) workers = tiles;
-  V3A_CUDA_OK(launch_kernel(kern, dim3((unsigned)(workers * kCta)), dim3(kGemmThreads), Cfg::SMEM_BYTES, stream, /*pdl=*/true, kCta,
-                            tmA, tmB, shape, ep));
+  V3A_CUDA_OK(launch_kernel(kern, dim3((unsigned)(workers * csize)), dim3(kGemmThreads), Cfg::SMEM_BYTES, stream, /*pdl=*/true, csize,
+                            tmA, tmB, tmA64, shape, ep));
   launch_counter().fetch_add(1);
   return VIST3A_OK;
 }

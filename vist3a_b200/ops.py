@@ -51,7 +51,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
          gate: Optional[torch.Tensor] = None, gate_bstride: int = 0, rows_per_batch: int = 0,
          residual: Optional[torch.Tensor] = None, round_linear: bool = False, round_gate: bool = False,
          two_cta: Optional[bool] = None, residual2: Optional[torch.Tensor] = None, post_act=None,
-         cmap: Optional[tuple] = None, rmap: Optional[tuple] = None, conv: Optional[dict] = None, bn176: bool = False) -> torch.Tensor:
+         cmap: Optional[tuple] = None, rmap: Optional[tuple] = None, conv: Optional[dict] = None, bn176: bool = False, multicast: bool = False) -> torch.Tensor:
     """out[M,N] = epilogue(a[M,K] @ w[N,K]^T); see vist3a_gemm in include/vist3a_sm100.h.
     cmap / rmap = (rows_per_group, group_stride, group_offset) row maps of out(+residual2) / residual;
     conv = dict(kh, kw, pad) with `a` an NHWC [n, h, w, c] tensor: implicit-GEMM convolution (stride 1).  Optional conv keys
@@ -121,7 +121,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
     args.round_linear, args.round_gate = int(round_linear), int(round_gate)
     if two_cta is None:
         two_cta = M >= 2048
-    args.flags = (L.GEMM_FLAG_2CTA if two_cta else L.GEMM_FLAG_1CTA) | (L.GEMM_FLAG_BN176 if bn176 else 0)
+    args.flags = (L.GEMM_FLAG_2CTA if two_cta else L.GEMM_FLAG_1CTA) | (L.GEMM_FLAG_BN176 if bn176 else 0) | (L.GEMM_FLAG_MULTICAST if multicast else 0)
     L.check(L.load().vist3a_gemm(C.byref(args), _stream()))
     return out
 
