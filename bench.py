@@ -418,11 +418,13 @@ def run_ours(args):
     # ---- CPU baseline (rank 0, N=1 only): bounded sample of the oracle port on the host cores
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline and args.model == "1.3b" and args.views == 13:
-        nb = args.ref_blocks
-        t = cpu_sample(nb, repeats=2)[-1]
+        nb = max(1, min(30, args.cpu_blocks))
+        cpu_sample(1)  # spins the thread pool up
+        t = cpu_sample(nb)[-1]
         sps = 1.0 / (2.0 * 30.0 / nb * t)
         cpu = {"value": sps, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-               "sample": f"{nb} of 30 full-size fp32 blocks of one cond forward (oracle/wan_dit_ref.py), {t:.2f} s; steps/s = 1/(2*30/{nb}*t)"}
+               "sample": f"{nb} of 30 full-size fp32 blocks of one cond forward incl. embed/head (oracle/wan_dit_ref.py), {t:.2f} s; "
+                         f"a step is two such forwards: steps/s = 1/(2*30/{nb}*t)"}
         if gauss is not None:
             dt, n, what = cpu_decoder_sample()
             gauss["cpu_baseline"] = {"decoder_gaussians_per_sec": n / dt, "cores": torch.get_num_threads(), "kind": "port",
@@ -457,7 +459,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ncu-step", action="store_true", help="profile exactly one eager denoise step (for ncu --profile-from-start off)")
     ap.add_argument("--detail", action="store_true", help="print per-shape kernel timings of one eager step to stderr")
-    ap.add_argument("--ref-blocks", type=int, default=2, help="full-size blocks per CPU sample")
+    ap.add_argument("--ref-blocks", type=int, default=2, help="full-size blocks per timed step of --impl reference")
+    ap.add_argument("--cpu-blocks", type=int, default=30, help="full-size blocks of the cpu_baseline leg (30 = one whole forward, ~10 s on 16 cores)")
     ap.add_argument("--prompts-per-gpu", type=int, default=1, help="prompts batched per GPU (BASELINE configs[4] sweep: 1/2/4/8)")
     ap.add_argument("--no-decoder", action="store_true", help="skip the Gaussians/s leg (decoder + gather)")
     ap.add_argument("--decoder-iters", type=int, default=3)
