@@ -393,6 +393,8 @@ int gs_project_entry(const float* means, const float* covars, const float* opac,
   V3A_REQUIRE(W > 0 && H > 0 && W <= 16 * 65535 && H <= 16 * 65535, VIST3A_ERR_INVALID, "gs_project: bad image size");
   V3A_REQUIRE(sh_degree >= 0 && sh_degree <= 4 && d_sh >= (sh_degree + 1) * (sh_degree + 1), VIST3A_ERR_INVALID,
               "gs_project: sh_degree must be in [0, 4] and d_sh >= (sh_degree + 1)^2 (got %d, %lld)", sh_degree, d_sh);
+  // the sort key holds the float bits of the depth, which order like the value only for depth >= 0
+  V3A_REQUIRE(near_plane >= 0.f && far_plane > near_plane, VIST3A_ERR_INVALID, "gs_project: need 0 <= near_plane < far_plane");
   V3A_REQUIRE(((uintptr_t)workspace & 255) == 0, VIST3A_ERR_INVALID, "gs_project: workspace must be 256-byte aligned");
   const ProjWs w = carve_proj(workspace, N);
   V3A_REQUIRE(workspace_bytes >= w.bytes, VIST3A_ERR_INVALID, "gs_project: workspace of %lld bytes needed, %lld given", w.bytes, workspace_bytes);
