@@ -221,3 +221,64 @@ def outputs_to_dict(out) -> dict:
     for i, p in enumerate(out.pred_pose_enc_list):
         d[f"pred_pose_enc_{i}"] = p
     return {k: v.detach().float().contiguous() for k, v in d.items()}
+
+
+class LiveWanVAE:
+    """The reference's vendored Wan-2.1 VAE (`utils/wan_utils.py:96-1180`) on CPU: its own `WanEncoder3d` / `WanDecoder3d` / `WanCausalConv3d`
+    modules and its own chunked, cache-carrying `_encode` / `_decode` loops (:1021-1048, :1078-1117), run unmodified.  Only the diffusers
+    base classes of `AutoencoderKLWan` (ModelMixin / ConfigMixin: config + checkpoint I/O, no arithmetic) are absent, so the two loops are
+    called as plain functions on this holder; `get_activation("silu")` is served as `nn.SiLU()` (what diffusers returns)."""
+
+    def __init__(self, base_dim=96, z_dim=16, dim_mult=(1, 2, 4, 4), num_res_blocks=2, temperal_downsample=(False, True, True), seed=0):
+        if not available():
+            raise RuntimeError(f"{REFERENCE_ROOT} is not mounted here; the real reference can only be imported in the build container")
+        for n in _STUBS:
+            _make_stub(n)
+        act = sys.modules["diffusers.models.activations"]
+        if "_vist3a_oracle" not in act.__dict__:   # (the stub modules answer every attribute, so no hasattr)
+            def get_activation(name):
+                assert name == "silu", name
+                return torch.nn.SiLU()
+            act.get_activation, act._vist3a_oracle = get_activation, True
+        if REFERENCE_ROOT not in sys.path:
+            sys.path.insert(0, REFERENCE_ROOT)
+        import importlib
+
+        wu = importlib.import_module("utils.wan_utils")
+        if wu.get_activation is not act.__dict__["get_activation"]:   # module imported earlier with the inert stub
+            wu.get_activation = act.__dict__["get_activation"]
+        self._wu = wu
+        self.z_dim = z_dim
+        self.temperal_downsample = list(temperal_downsample)
+        self.temperal_upsample = self.temperal_downsample[::-1]
+        torch.manual_seed(seed)
+        self.encoder = wu.WanEncoder3d(base_dim, z_dim * 2, list(dim_mult), num_res_blocks, [], self.temperal_downsample, 0.0).float().eval()
+        self.quant_conv = wu.WanCausalConv3d(z_dim * 2, z_dim * 2, 1).float().eval()
+        self.post_quant_conv = wu.WanCausalConv3d(z_dim, z_dim, 1).float().eval()
+        self.decoder = wu.WanDecoder3d(base_dim, z_dim, list(dim_mult), num_res_blocks, [], self.temperal_upsample, 0.0).float().eval()
+        self._parts = {"encoder": self.encoder, "quant_conv": self.quant_conv, "post_quant_conv": self.post_quant_conv, "decoder": self.decoder}
+
+    # the two helpers `_encode` / `_decode` call on self
+    def _count_conv3d(self, model):
+        return self._wu.AutoencoderKLWan._count_conv3d(self, model)
+
+    def _create_cache_state(self, model):
+        return self._wu.AutoencoderKLWan._create_cache_state(self, model)
+
+    @torch.no_grad()
+    def encode_moments(self, x: torch.Tensor) -> torch.Tensor:
+        """[B, 3, T, H, W] in [-1, 1] -> [B, 2 z_dim, 1 + (T - 1) / 4, H / 8, W / 8] (mean | logvar), the tensor `encode` wraps in
+        DiagonalGaussianDistribution (:1068-1072)"""
+        return self._wu.AutoencoderKLWan._encode(self, x)
+
+    @torch.no_grad()
+    def decode(self, z: torch.Tensor) -> torch.Tensor:
+        """[B, z_dim, T', h, w] -> [B, 3, 1 + 4 (T' - 1), 8 h, 8 w], clamped to [-1, 1] (:1078-1117)"""
+        return self._wu.AutoencoderKLWan._decode(self, z, return_dict=False)[0]
+
+    def state_dict(self) -> dict:
+        return {f"{p}.{k}": v.detach().clone() for p, m in self._parts.items() for k, v in m.state_dict().items()}
+
+    def load_state_dict(self, sd: dict):
+        for p, m in self._parts.items():
+            m.load_state_dict({k[len(p) + 1:]: v for k, v in sd.items() if k.startswith(p + ".")}, strict=True)
