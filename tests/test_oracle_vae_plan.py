@@ -32,3 +32,17 @@ def test_time_interleave_order():
     ref = torch.stack((ref[:, 0], ref[:, 1]), 3).reshape(1, C, 2 * T, H, W)  # the reference's three lines
     out = y.reshape(T, H, W, 2, C).permute(0, 3, 1, 2, 4).reshape(2 * T, H, W, C)
     assert torch.equal(out.permute(3, 0, 1, 2)[None], ref)
+
+
+@pytest.mark.parametrize("seed,frames,hw", [(4, 1, 16), (5, 5, 16), (6, 13, 24)])
+def test_planned_encode_equals_the_oracle(seed, frames, hw):
+    """stride-2 gathers (ZeroPad2d((0,1,0,1)) + conv; whole-clip temporal down-sampling) and the conv_out / quant_conv fold"""
+    cfg = V.TINY_VAE
+    sd = V.init_state_dict(cfg, seed=seed)
+    clip = V.synthetic_clip(frames, hw, seed=seed)
+    ref = V.encode_moments(sd, cfg, clip)
+    out = PL.encode_plan(sd, cfg, clip)
+    assert out.shape == ref.shape
+    assert (out - ref).abs().max().item() <= 2e-5
+    b = PL.encode_plan(sd, cfg, clip, round_bf16=True)
+    assert (b - ref).abs().max().item() <= 0.1 * max(1.0, ref.abs().max().item())
