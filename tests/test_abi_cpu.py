@@ -91,3 +91,58 @@ def test_weight_manifests_match_the_oracles():
     assert SD.param_shapes(SD.DecoderConfig()) == D.param_shapes(D.FULL)
     assert WD.param_shapes(WD.WAN_1_3B_CONFIG) == R.param_shapes(R.WAN_1_3B)
     assert WD.param_shapes(WD.WAN_14B_CONFIG) == R.param_shapes(R.WAN_14B)
+
+
+def test_argument_validation_precedes_any_device_work(lib):
+    """Every entry point validates sizes / alignment / geometry before it touches CUDA or dereferences a pointer, so the checks can be
+    exercised on a GPU-less host with placeholder addresses; a call that passes validation then fails on the missing device."""
+    import ctypes as C
+
+    h = lib.load()
+    no_gpu = not torch.cuda.is_available()   # with a device present the placeholder addresses must never reach a launch
+    P = 0x1000        # placeholder, 256-byte aligned, never dereferenced
+    cam = (C.c_float * 16)(1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1)
+    K = (C.c_float * 9)(100, 0, 32, 0, 100, 32, 0, 0, 1)
+
+    def err():
+        return h.vist3a_last_error().decode()
+
+    # workspace sizes are pure host arithmetic
+    n = 1000
+    vb = h.vist3a_voxel_fusion_workspace_bytes(n)
+    assert vb >= n * (8 + 8 + 4 + 4 + 4 + 4) and h.vist3a_voxel_fusion_workspace_bytes(0) == 0
+    pb = h.vist3a_gs_project_workspace_bytes(n)
+    assert pb >= n * (40 + 8 + 4 + 4)
+    assert h.vist3a_gs_rasterize_workspace_bytes(5000, 64, 64) > 5000 * 24
+
+    # voxel fusion
+    args = dict(pts=P, feats=P, ld=83, C_=83, conf=P, cs=1, N=n, vs=0.002, vp=P, vf=P, inv=None, cnt=None, nv=P, ws=P, wsb=vb, st=None)
+    call = lambda a: h.vist3a_voxel_fusion(a["pts"], a["feats"], a["ld"], a["C_"], a["conf"], a["cs"], a["N"], a["vs"], a["vp"], a["vf"],
+                                           a["inv"], a["cnt"], a["nv"], a["ws"], a["wsb"], a["st"])
+    assert call({**args, "pts": None}) == lib.ERR_INVALID and "null" in err()
+    assert call({**args, "N": 0}) == lib.ERR_INVALID and "N must be" in err()
+    assert call({**args, "C_": 126, "ld": 126}) == lib.ERR_INVALID and "feature dim" in err()
+    assert call({**args, "vs": 0.0}) == lib.ERR_INVALID and "voxel_size" in err()
+    assert call({**args, "ws": P + 16}) == lib.ERR_INVALID and "aligned" in err()
+    assert call({**args, "wsb": vb - 1}) == lib.ERR_INVALID and "workspace of" in err()
+    assert not no_gpu or call(args) in (lib.ERR_ARCH, lib.ERR_CUDA)        # valid arguments: only the device is missing
+
+    # rasteriser, phase 1
+    pargs = dict(m=P, c=P, o=P, h=P, dsh=25, deg=4, N=n, vm=cam, K=K, W=64, H=64, near=1e-10, far=1e10, rc=0.1, eps=0.3, ws=P, wsb=pb, ni=P, st=None)
+    pcall = lambda a: h.vist3a_gs_project(a["m"], a["c"], a["o"], a["h"], a["dsh"], a["deg"], a["N"], a["vm"], a["K"], a["W"], a["H"], a["near"],
+                                          a["far"], a["rc"], a["eps"], a["ws"], a["wsb"], a["ni"], a["st"])
+    assert pcall({**pargs, "deg": 5}) == lib.ERR_INVALID and "sh_degree" in err()
+    assert pcall({**pargs, "dsh": 16}) == lib.ERR_INVALID and "sh_degree" in err()
+    assert pcall({**pargs, "near": -1.0}) == lib.ERR_INVALID and "near_plane" in err()
+    assert pcall({**pargs, "far": 0.0}) == lib.ERR_INVALID and "near_plane" in err()
+    assert pcall({**pargs, "W": 0}) == lib.ERR_INVALID and "image size" in err()
+    assert pcall({**pargs, "wsb": pb - 1}) == lib.ERR_INVALID and "workspace of" in err()
+    assert not no_gpu or pcall(pargs) in (lib.ERR_ARCH, lib.ERR_CUDA)
+
+    # rasteriser, phase 2
+    bg = (C.c_float * 3)(0, 0, 0)
+    rb = h.vist3a_gs_rasterize_workspace_bytes(5000, 64, 64)
+    assert h.vist3a_gs_rasterize(P, n, 5000, 64, 64, bg, P, rb - 1, P, P, P, None) == lib.ERR_INVALID and "workspace of" in err()
+    assert h.vist3a_gs_rasterize(P, n, 1 << 32, 64, 64, bg, P, rb, P, P, P, None) == lib.ERR_INVALID and "2^32" in err()
+    assert not no_gpu or h.vist3a_gs_rasterize(P, n, 5000, 64, 64, bg, P, rb, P, P, P, None) in (lib.ERR_ARCH, lib.ERR_CUDA)
+    assert not no_gpu or h.vist3a_launch_count() == 0
