@@ -146,3 +146,61 @@ def test_argument_validation_precedes_any_device_work(lib):
     assert h.vist3a_gs_rasterize(P, n, 1 << 32, 64, 64, bg, P, rb, P, P, P, None) == lib.ERR_INVALID and "2^32" in err()
     assert not no_gpu or h.vist3a_gs_rasterize(P, n, 5000, 64, 64, bg, P, rb, P, P, P, None) in (lib.ERR_ARCH, lib.ERR_CUDA)
     assert not no_gpu or h.vist3a_launch_count() == 0
+
+
+def test_gemm_and_attention_argument_validation(lib):
+    """the two tensor-core entry points reject bad geometry with a message, before any tensor map is encoded or kernel launched"""
+    h = lib.load()
+    P = 0x1000
+
+    def err():
+        return h.vist3a_last_error().decode()
+
+    def gemm(**kw):
+        a = lib.GemmArgs()
+        a.A = a.W = a.C = P
+        a.M, a.N, a.K = 256, 128, 64
+        a.lda = a.ldw = 64
+        a.ldc = 128
+        a.in_dtype = a.out_dtype = 0       # bf16
+        for k, v in kw.items():
+            if k.startswith("conv_"):
+                setattr(a.conv, k[5:], v)
+            else:
+                setattr(a, k, v)
+        return h.vist3a_gemm(C.byref(a), None)
+
+    assert gemm(A=None) == lib.ERR_INVALID and "null" in err()
+    assert gemm(K=0) == lib.ERR_INVALID and "positive" in err()
+    assert gemm(ldw=60) == lib.ERR_INVALID and "ldw" in err()
+    assert gemm(lda=63) == lib.ERR_INVALID and "lda" in err()
+    assert gemm(ldc=120) == lib.ERR_INVALID and "ldc" in err()
+    assert gemm(A=P + 8) == lib.ERR_INVALID and "aligned" in err()
+    assert gemm(in_dtype=7) == lib.ERR_INVALID and "in_dtype" in err()
+    assert gemm(post_act=1) == lib.ERR_UNSUPPORTED and "post_act" in err()
+    # implicit-GEMM convolution: K and M must agree with the geometry, channels with the 64-element K block
+    conv = dict(conv_enabled=1, conv_kh=3, conv_kw=3, conv_pad_y=1, conv_pad_x=1, conv_n_img=1, conv_h=16, conv_w=16, conv_c_in=64, K=9 * 64, ldw=9 * 64)
+    assert gemm(**{**conv, "conv_c_in": 32, "K": 9 * 32, "ldw": 9 * 32}) == lib.ERR_UNSUPPORTED and "c_in" in err()
+    assert gemm(**{**conv, "K": 8 * 64, "ldw": 9 * 64}) == lib.ERR_INVALID and "kh*kw*c_in" in err()
+    assert gemm(**{**conv, "M": 255}) == lib.ERR_INVALID and "n_img*h_out*w_out" in err()
+
+    def fmha(**kw):
+        a = lib.FmhaArgs()
+        a.Q = a.K = a.V = a.O = P
+        a.batch, a.heads, a.len_q, a.len_kv, a.head_dim = 1, 2, 128, 128, 128
+        for f in ("q", "k", "v", "o"):
+            setattr(a, f + "_bs", 128 * 256)
+            setattr(a, f + "_rs", 256)
+            setattr(a, f + "_hs", 128)
+        a.scale = 0.088
+        for k, v in kw.items():
+            setattr(a, k, v)
+        return h.vist3a_fmha_fwd(C.byref(a), None)
+
+    assert fmha(Q=None) == lib.ERR_INVALID and "null" in err()
+    assert fmha(head_dim=96) == lib.ERR_UNSUPPORTED and "head_dim" in err()
+    assert fmha(len_kv=0) == lib.ERR_INVALID
+    assert fmha(k_rs=250) == lib.ERR_INVALID and "strides" in err()
+    assert fmha(V=P + 4) == lib.ERR_INVALID
+    if not torch.cuda.is_available():
+        assert gemm() in (lib.ERR_ARCH, lib.ERR_CUDA) and fmha() in (lib.ERR_ARCH, lib.ERR_CUDA)
