@@ -90,3 +90,33 @@ def test_all_gather_gaussians_gloo_world2():
     for p in procs:
         p.join(timeout=60)
     assert sorted(res) == [(0, True), (1, True)]
+
+
+def test_views_from_vae_mirrors_the_reference_resize():
+    """inference_t23d.py:114-123: decode, then trilinear (align_corners=False) resize of H x W only"""
+    import torch.nn.functional as F
+
+    from vist3a_b200.t23d import views_from_vae
+
+    class FakeVAE(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.w = torch.nn.Parameter(torch.ones(1, dtype=torch.float64))
+            self.seen = None
+
+        def decode(self, z, return_dict=True):
+            assert return_dict is False
+            self.seen = z.dtype
+            t = 1 + 4 * (z.shape[2] - 1)
+            g = torch.Generator().manual_seed(0)
+            return (torch.rand(z.shape[0], 3, t, 8 * z.shape[3], 8 * z.shape[4], generator=g, dtype=z.dtype) * 2 - 1,)
+
+    vae = FakeVAE()
+    lat = torch.randn(1, 16, 2, 4, 4)
+    out = views_from_vae(vae, lat, size=28)
+    assert vae.seen == torch.float64 and out.dtype == torch.float32 and out.shape == (1, 3, 5, 28, 28)
+    ref = F.interpolate(vae.decode(lat.double(), return_dict=False)[0].float(), (5, 28, 28), mode="trilinear", align_corners=False)
+    assert torch.equal(out, ref)
+    # the frame axis is not interpolated: every output frame depends on its own input frame only
+    per_frame = F.interpolate(vae.decode(lat.double(), return_dict=False)[0].float()[:, :, 2], (28, 28), mode="bilinear", align_corners=False)
+    assert torch.allclose(out[:, :, 2], per_frame, atol=1e-6)

@@ -9,7 +9,7 @@ collective inside a prompt.  The one exchange step is the gather of the final Ga
 (`all_gather_gaussians`): means, scales, rotations, opacities, harmonics (+ covariances) of every rank.
 
 Text encoding (UMT5) and the Wan VAE decode that produces `feedforward_image` are outside the hot path
-(SURVEY §8f): the caller passes text embeddings and the decoded views.
+(SURVEY §8f): the caller passes text embeddings and either the decoded views or its VAE module (`views_from_vae`).
 """
 from __future__ import annotations
 
@@ -65,9 +65,26 @@ class TextTo3DGS:
 
     @torch.no_grad()
     def generate(self, noise: torch.Tensor, text_cond: torch.Tensor, text_uncond: torch.Tensor,
-                 feedforward_image: torch.Tensor) -> EncoderOutput:
+                 feedforward_image: Optional[torch.Tensor] = None, *, vae=None) -> EncoderOutput:
+        """One prompt.  `feedforward_image` [1, 3, V, 448, 448] in [-1, 1] are the decoded views the Gaussian head reads; when it is not
+        given, `vae` (the caller's `pipe.vae`: any object with diffusers' `decode(latents, return_dict=False)`) decodes the de-normalised
+        latent and the frames are resized as the reference does (inference_t23d.py:114-123) -- the VAE itself is outside this engine."""
         latent = self.denoise(noise, text_cond, text_uncond)
+        if feedforward_image is None:
+            if vae is None:
+                raise ValueError("generate: pass feedforward_image, or vae= to decode the views from the latent")
+            feedforward_image = views_from_vae(vae, latent)
         return self.dec.forward_with_latent(latent, feedforward_image, train=False)
+
+
+def views_from_vae(vae, latent: torch.Tensor, size: int = 448) -> torch.Tensor:
+    """inference_t23d.py:114-123: `samples = pipe.vae.decode(latents, return_dict=False)[0]`, then a trilinear (align_corners=False)
+    resize of the frames to size x size with the frame count kept.  Host plumbing around the caller's VAE module."""
+    import torch.nn.functional as F
+
+    p = next(iter(vae.parameters()), None) if hasattr(vae, "parameters") else None
+    samples = vae.decode(latent if p is None else latent.to(p.dtype), return_dict=False)[0]
+    return F.interpolate(samples.float(), (samples.shape[2], size, size), mode="trilinear", align_corners=False)
 
 
 def pack_gaussians(g: Gaussians, with_covariances: bool = False) -> torch.Tensor:
