@@ -144,3 +144,56 @@ def test_interpolated_camera_path_matches_live_reference():
     ex, ix = interpolate_context_cameras(E, K, t=10)
     assert rec.extr.shape == ex.shape == (1, 44, 4, 4)
     assert float((rec.extr - ex).abs().max()) < 2e-6 and float((rec.intr - ix).abs().max()) < 1e-6
+
+
+def test_projection_is_the_linearised_pinhole_camera():
+    """Independent of gsplat: inside the frustum the 2-D covariance must be Jac(pi) Sigma Jac(pi)^T with pi the pinhole projection
+    (autograd Jacobian, world -> pixel), + eps2d on the diagonal; the conic its inverse; the radius ceil(3 sqrt(largest eigenvalue))."""
+    torch.manual_seed(0)
+    W = H = 96
+    Vm, K = G.look_at_camera(W, H, fov_deg=60.0, shift=(0.1, -0.05, 0.0), yaw_deg=12.0)
+    Vm, K = Vm.double(), K.double()
+    means, covars, _, _ = G.random_scene(64, seed=3, spread=0.5, scale=(0.02, 0.08), sh_degree=0)
+    means, covars = means.double(), covars.double()
+    out = G.project(means, covars, Vm, K, W, H)
+
+    def pix(p):
+        c = Vm[:3, :3] @ p + Vm[:3, 3]
+        return torch.stack([K[0, 0] * c[0] / c[2] + K[0, 2], K[1, 1] * c[1] / c[2] + K[1, 2]])
+
+    checked = 0
+    for i in range(means.shape[0]):
+        m2 = pix(means[i])
+        if not bool(out["valid"][i]) or not (0 < m2[0] < W and 0 < m2[1] < H):
+            continue          # outside the image the reference clamps the Jacobian's (x/z, y/z): not the plain linearisation
+        J = torch.autograd.functional.jacobian(pix, means[i])
+        c2 = J @ covars[i] @ J.T + 0.3 * torch.eye(2, dtype=torch.float64)
+        a, b, c = out["conic"][i]
+        conic = torch.stack([torch.stack([a, b]), torch.stack([b, c])])
+        assert torch.allclose(conic @ c2, torch.eye(2, dtype=torch.float64), atol=1e-6)
+        assert torch.allclose(out["means2d"][i], m2, atol=1e-6)
+        ev = torch.linalg.eigvalsh(c2)[-1]
+        assert abs(float(out["radius"][i]) - float(torch.ceil(3.0 * torch.sqrt(ev)))) <= (1.0 if abs(float(3.0 * torch.sqrt(ev)) % 1.0) < 1e-6 else 0.0)
+        checked += 1
+    assert checked >= 20
+
+
+def test_projected_covariance_against_sampling():
+    """Monte-Carlo: points drawn from a small 3-D Gaussian and projected exactly have the linearised 2-D covariance (to sampling error)"""
+    g = torch.Generator().manual_seed(5)
+    W = H = 128
+    Vm, K = G.look_at_camera(W, H, fov_deg=50.0)
+    Vm, K = Vm.double(), K.double()
+    A = torch.randn(3, 3, generator=g, dtype=torch.float64) * 0.01
+    cov = (A @ A.T + 1e-5 * torch.eye(3, dtype=torch.float64))
+    mean = torch.tensor([0.15, -0.1, 2.0], dtype=torch.float64)
+    out = G.project(mean[None], cov[None], Vm, K, W, H, eps2d=0.0, radius_clip=0.0)
+    assert bool(out["valid"][0])
+    a, b, c = out["conic"][0]
+    c2 = torch.linalg.inv(torch.stack([torch.stack([a, b]), torch.stack([b, c])]))
+    pts = mean + torch.randn(400_000, 3, generator=g, dtype=torch.float64) @ torch.linalg.cholesky(cov).T
+    cam = pts @ Vm[:3, :3].T + Vm[:3, 3]
+    uv = torch.stack([K[0, 0] * cam[:, 0] / cam[:, 2] + K[0, 2], K[1, 1] * cam[:, 1] / cam[:, 2] + K[1, 2]], dim=-1)
+    emp = torch.cov(uv.T)
+    assert torch.allclose(emp, c2, rtol=0.02, atol=0.02 * float(c2.diagonal().max()))
+    assert torch.allclose(uv.mean(0), out["means2d"][0], atol=0.02 * float(c2.diagonal().max().sqrt()) + 1e-3)
