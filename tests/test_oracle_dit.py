@@ -30,6 +30,21 @@ def test_rope_split_and_identity_at_origin():
     assert not torch.allclose(fr[1, 43:], torch.ones(21, dtype=torch.complex128))
 
 
+def test_rope_logits_depend_on_relative_position_only():
+    """the defining property of rotary embeddings, per axis group: <rot(q, p), rot(k, p')> is a function of p - p' (t, h, w offsets)"""
+    cfg = R.WAN_1_3B
+    f, h, w = 3, 4, 5
+    fr = R.rope_freqs(cfg, f, h, w)                                   # [f*h*w, 64]
+    g = torch.Generator().manual_seed(0)
+    q = torch.view_as_complex(torch.randn(64, 2, generator=g, dtype=torch.float64))
+    k = torch.view_as_complex(torch.randn(64, 2, generator=g, dtype=torch.float64))
+    L = ((q * fr)[:, None, :] * (k * fr).conj()[None, :, :]).sum(-1).real.view(f, h, w, f, h, w)   # real dot product of the rotated pairs
+    assert torch.allclose(L[:-1, :, :, :-1], L[1:, :, :, 1:], atol=1e-9)             # shift both along t
+    assert torch.allclose(L[:, :-1, :, :, :-1], L[:, 1:, :, :, 1:], atol=1e-9)       # along h
+    assert torch.allclose(L[:, :, :-1, :, :, :-1], L[:, :, 1:, :, :, 1:], atol=1e-9)  # along w
+    assert not torch.allclose(L[0, 0, 0, 0, 0, 0], L[0, 0, 0, 1, 2, 3])
+
+
 def test_zero_gates_make_block_residual_only():
     cfg = R.WAN_TINY
     sd = R.init_state_dict(cfg, seed=3, bias_std=0.02)
