@@ -120,7 +120,8 @@ def load_teacher(width: RefWidth = FULL, seed: int = 0, sh_degree: int = 4, voxe
 
 
 def load_reference(width: RefWidth = FULL, resolution: int = 512, seed: int = 0, sh_degree: int = 4, voxelize: bool = False,
-                   voxel_size: float = 0.002, _teacher: bool = False):
+                   voxel_size: float = 0.002, _teacher: bool = False, render_conf: bool = False, opacity_conf: bool = False,
+                   conf_threshold: float = 0.1):
     """Returns the reference StitchVAE3D (fp32, eval, checkpointing off) with seeded random init."""
     if not available():
         raise RuntimeError(f"{REFERENCE_ROOT} is not mounted here; the real reference can only be imported in the build container")
@@ -186,7 +187,8 @@ def load_reference(width: RefWidth = FULL, resolution: int = 512, seed: int = 0,
             num_monocular_samples=32, backbone=None, visualizer=None,
             gaussian_adapter=ga_mod.GaussianAdapterCfg(0.5, 15.0, sh_degree), apply_bounds_shim=True,
             opacity_mapping=enc_mod.OpacityMappingCfg(0.0, 0.0, 1), gaussians_per_pixel=1, num_surfaces=1,
-            gs_params_head_type="dpt_gs", pred_head_type="depth", voxelize=voxelize, intermediate_layer_idx=[4, 11, 17, 23])
+            gs_params_head_type="dpt_gs", pred_head_type="depth", voxelize=voxelize, intermediate_layer_idx=[4, 11, 17, 23],
+            render_conf=render_conf, opacity_conf=opacity_conf, conf_threshold=conf_threshold)
         torch.manual_seed(seed)
         ff = anysplat_mod.AnySplat(cfg, dec_mod.DecoderSplattingCUDACfg("splatting_cuda", [1.0, 1.0, 1.0], False))
         if _teacher:

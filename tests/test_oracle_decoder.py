@@ -129,3 +129,28 @@ def test_unproject_identity_camera():
     p = D.unproject(depth, extr, intr)
     assert torch.allclose(p[0, 2, 3], torch.tensor([0.0, 0.0, 2.0]))
     assert torch.allclose(p[0, 0, 0], torch.tensor([-2.0, -2.0, 2.0]))
+
+
+@pytest.mark.skipif(not RL.available(), reason="/root/reference is only mounted in the build container")
+@pytest.mark.parametrize("render_conf,opacity_conf,thr", [(True, False, 0.1), (True, True, 0.3), (False, True, 0.1)])
+def test_confidence_quantile_branches_match_live_reference(render_conf, opacity_conf, thr):
+    """render_conf / opacity_conf (models/anysplat_stitched.py:381-387, 443-467; off in every released config): quantile of the depth
+    confidence, ordered compaction of the surviving pixels, opacity damping -- bit-exact against the reference's own forward"""
+    model = RL.load_reference(RL.TINY, resolution=64, seed=11, render_conf=render_conf, opacity_conf=opacity_conf, conf_threshold=thr)
+    sd = RL.decoder_state_dict(model)
+    lat, img = D.synthetic_inputs(D.TINY, views_latent=2, latent_hw=8, image_hw=56, seed=1)
+    with torch.no_grad():
+        ref = RL.outputs_to_dict(model.forward_with_latent(lat, feedforward_image=img))
+    out = D.decoder_forward(sd, D.TINY, lat, img, resolution=64, render_conf=render_conf, opacity_conf=opacity_conf, conf_threshold=thr)
+    n_all = img.shape[2] * img.shape[3] * img.shape[4]
+    n = int(out["valid_counts"][0])
+    assert ref["means"].shape[1] == n
+    if render_conf:
+        assert abs(n - (1 - thr) * n_all) <= 2          # the quantile cuts the lowest `thr` share of the pixels
+    else:
+        assert n == n_all
+    for k, v in ref.items():
+        _cmp(k, out[k], v)
+    if opacity_conf:
+        plain = D.decoder_forward(sd, D.TINY, lat, img, resolution=64, render_conf=render_conf, conf_threshold=thr)
+        assert torch.all(out["opacities"] <= plain["opacities"]) and torch.any(out["opacities"] < plain["opacities"])
