@@ -120,3 +120,41 @@ def test_views_from_vae_mirrors_the_reference_resize():
     # the frame axis is not interpolated: every output frame depends on its own input frame only
     per_frame = F.interpolate(vae.decode(lat.double(), return_dict=False)[0].float()[:, :, 2], (28, 28), mode="bilinear", align_corners=False)
     assert torch.allclose(out[:, :, 2], per_frame, atol=1e-6)
+
+
+def test_stitched_forward_mirrors_the_reference_surface():
+    """StitchVAE3D.forward (models/stitched_model.py:140-163) = VAE encode + sample, then forward_with_latent; the engine takes the caller's
+    VAE module and refuses without one (the Wan VAE is not part of it)."""
+    import pytest
+
+    from vist3a_b200.stitched_decoder import DecoderConfig, StitchVAE3DB200
+
+    m = StitchVAE3DB200(DecoderConfig(), device="cpu")
+    with pytest.raises(NotImplementedError, match="diffusion_vae"):
+        m.forward(torch.zeros(1, 3, 5, 16, 16), torch.zeros(1, 3, 5, 14, 14))
+
+    class Dist:
+        def __init__(self, z):
+            self.z = z
+
+        def sample(self):
+            return self.z
+
+    class FakeVAE:
+        def encode(self, images):
+            self.seen = images
+            b, _, t, h, w = images.shape
+            return type("Out", (), {"latent_dist": Dist(torch.full((b, 16, 1 + (t - 1) // 4, h // 8, w // 8), 0.25))})()
+
+    got = {}
+
+    def fake_fwl(latent, feedforward_image, train=False):
+        got.update(latent=latent, image=feedforward_image, train=train)
+        return "decoded"
+
+    m.diffusion_vae = FakeVAE()
+    m.forward_with_latent = fake_fwl
+    clip, views = torch.rand(2, 3, 5, 16, 16), torch.rand(2, 3, 5, 14, 14)
+    assert m.forward(clip, views) == "decoded"
+    assert m.diffusion_vae.seen is clip and got["image"] is views and got["train"] is False
+    assert got["latent"].shape == (2, 16, 2, 2, 2) and float(got["latent"].mean()) == 0.25

@@ -237,6 +237,7 @@ class StitchVAE3DB200(torch.nn.Module):
         self._tables = {}
         self.keep_voxel_inputs = False
         self.voxel_inputs = None
+        self.diffusion_vae = None        # optional: the caller's Wan VAE module, only used by forward(images, ...)
         if config.embed_dim // config.num_heads != 64:
             raise NotImplementedError("the QK-norm + 2-D RoPE kernel implements the aggregator's 64-wide heads")
 
@@ -678,5 +679,14 @@ class StitchVAE3DB200(torch.nn.Module):
             last_pred_pose_enc=pose_list[-1],
         )
 
-    def forward(self, *a, **k):
-        raise NotImplementedError("StitchVAE3D.forward (VAE encode of images) is outside the text-to-3D hot path; call forward_with_latent")
+    def forward(self, images: torch.Tensor, feedforward_image: torch.Tensor, train: bool = False) -> EncoderOutput:
+        """StitchVAE3D.forward (models/stitched_model.py:140-163): `diffusion_vae.encode(images).latent_dist.sample()` (images [B, 3, T, H, W]
+        in [-1, 1]) and then the stitched path on that latent.  The VAE is the caller's module (`self.diffusion_vae = pipe.vae`; the Wan VAE
+        is not part of this engine yet); without one the call is refused."""
+        vae = getattr(self, "diffusion_vae", None)
+        if vae is None:
+            raise NotImplementedError("StitchVAE3D.forward needs the Wan VAE encoder, which is outside this engine: set `.diffusion_vae` to the "
+                                      "caller's VAE module, or call forward_with_latent(latent, feedforward_image)")
+        with torch.no_grad():
+            latent = vae.encode(images).latent_dist.sample()
+        return self.forward_with_latent(latent, feedforward_image, train=train)
