@@ -204,3 +204,31 @@ def test_gemm_and_attention_argument_validation(lib):
     assert fmha(V=P + 4) == lib.ERR_INVALID
     if not torch.cuda.is_available():
         assert gemm() in (lib.ERR_ARCH, lib.ERR_CUDA) and fmha() in (lib.ERR_ARCH, lib.ERR_CUDA)
+
+
+def test_every_compute_entry_point_rejects_zeroed_arguments(lib):
+    """robustness of the boundary: NULL pointers / zero sizes come back as VIST3A_ERR_INVALID with a message from every compute entry point
+    (no crash, no launch) -- the reference's FFI-less Python would raise here; a C caller gets a status code"""
+    h = lib.load()
+    skip = {"vist3a_last_error", "vist3a_abi_version", "vist3a_launch_count", "vist3a_set_pdl", "vist3a_voxel_fusion_workspace_bytes",
+            "vist3a_gs_project_workspace_bytes", "vist3a_gs_rasterize_workspace_bytes"}
+    n0 = h.vist3a_launch_count()
+    checked = 0
+    for name in lib.EXPORTS:
+        if name in skip:
+            continue
+        fn = getattr(h, name)
+        assert fn.argtypes is not None, name
+        args = []
+        for t in fn.argtypes:
+            if t in (C.c_void_p, C.c_char_p) or (hasattr(t, "_type_") and not isinstance(t._type_, str)):
+                args.append(None)
+            elif t in (C.c_float, C.c_double):
+                args.append(0.0)
+            else:
+                args.append(0)
+        assert fn(*args) == lib.ERR_INVALID, name
+        msg = h.vist3a_last_error().decode()
+        assert ":" in msg, (name, msg)            # "<entry point>: <what is wrong>"
+        checked += 1
+    assert checked == len(lib.EXPORTS) - len(skip) and h.vist3a_launch_count() == n0
