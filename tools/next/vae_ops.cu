@@ -1,4 +1,4 @@
-// DRAFT (never run on a GPU; see tools/next/README.md): HBM-bound helper kernels of the planned Wan-VAE device path.
+// DRAFT (see tools/next/README.md: checked once on a B200, untimed): HBM-bound helper kernels of the planned Wan-VAE device path.
 // Per-operation references: oracle/wan_vae_plan.py (rmsnorm_silu, attention's softmax, the time interleave of `upsample`).
 // Reference layers: utils/wan_utils.py:150-184 (WanRMS_norm), :428-475 (WanAttentionBlock), :304-306 (temporal interleave).
 #include <cuda_bf16.h>
