@@ -42,3 +42,18 @@ def test_upsample_conv_on_the_low_resolution_map():
     # per parity only a 2x2 block of the low-resolution neighbourhood carries weight
     blocks = wt.reshape(2, 2, co, 3, 3, ci).abs().sum(dim=(2, 5)) > 0
     assert all(int(blocks[ph, pw].sum()) == 4 for ph in range(2) for pw in range(2))
+
+
+def test_padded_input_channels():
+    """96-channel activations stored 128 wide: the padded tap-major weight reproduces the convolution on the padded layout"""
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(3, 5, 6, 96, generator=g, dtype=torch.float64)
+    w = torch.randn(8, 96, 3, 3, 3, generator=g, dtype=torch.float64)
+    ref = _gather(x, 3, 3, 3) @ conv3d_weight_to_taps(w).t()
+    xp = F.pad(x, (0, 32))                                             # pixel stride 128, channels 96..127 zero
+    wt = conv3d_weight_to_taps(w, c_in_pad=128)
+    assert wt.shape == (8, 27 * 128)
+    assert torch.allclose(_gather(xp, 3, 3, 3) @ wt.t(), ref, atol=1e-12)
+    # garbage in the padding channels is harmless as long as it is finite: it meets zero weights
+    xp[..., 96:] = 7.0
+    assert torch.allclose(_gather(xp, 3, 3, 3) @ wt.t(), ref, atol=1e-12)

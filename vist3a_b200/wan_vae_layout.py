@@ -11,14 +11,22 @@ from __future__ import annotations
 import torch
 
 
-def conv3d_weight_to_taps(w: torch.Tensor) -> torch.Tensor:
-    """[C_out, C_in, kt, kh, kw] (nn.Conv3d) or [C_out, C_in, kh, kw] (nn.Conv2d, kt = 1) -> [C_out, kt*kh*kw*C_in], tap-major K"""
+def conv3d_weight_to_taps(w: torch.Tensor, c_in_pad: int | None = None) -> torch.Tensor:
+    """[C_out, C_in, kt, kh, kw] (nn.Conv3d) or [C_out, C_in, kh, kw] (nn.Conv2d, kt = 1) -> [C_out, kt*kh*kw*C_in], tap-major K.
+    `c_in_pad` > C_in appends zero input channels per tap: activations kept with a wider pixel stride (e.g. the 96-channel layers stored
+    128 wide so that a tap is a whole number of 64-channel k-blocks) read their padding as zeros times zero weights."""
     if w.dim() == 4:
         w = w.unsqueeze(2)
     if w.dim() != 5:
         raise ValueError("conv3d_weight_to_taps: expected a Conv3d / Conv2d weight")
     co, ci, kt, kh, kw = w.shape
-    return w.permute(0, 2, 3, 4, 1).reshape(co, kt * kh * kw * ci).contiguous()
+    wt = w.permute(0, 2, 3, 4, 1)
+    if c_in_pad is not None:
+        if c_in_pad < ci:
+            raise ValueError("conv3d_weight_to_taps: c_in_pad is smaller than C_in")
+        wt = torch.nn.functional.pad(wt, (0, c_in_pad - ci))
+        ci = c_in_pad
+    return wt.reshape(co, kt * kh * kw * ci).contiguous()
 
 
 def upsample_conv_weight_to_parity(w: torch.Tensor, bias: torch.Tensor | None = None):
