@@ -110,3 +110,18 @@ def test_posterior_and_latent_statistics():
     assert torch.allclose(V.denormalise_latents(one).flatten(), torch.tensor(V.LATENTS_MEAN) + torch.tensor(V.LATENTS_STD), rtol=1e-6)
     f = V.frames_to_feedforward(torch.rand(1, 3, 2, 16, 16), hw=14)
     assert f.shape == (1, 3, 2, 14, 14)
+
+
+@pytest.mark.slow
+@pytest.mark.skipif(not RL.available(), reason="/root/reference is not mounted (build container only)")
+def test_against_live_reference_full_width():
+    """the released widths (base 96, z 16, 126.9 M parameters) on a 5-frame 32 x 32 clip, ~15 s on 8 cores"""
+    cfg = V.WAN_VAE
+    live = RL.LiveWanVAE(seed=0)
+    sd = V.init_state_dict(cfg, seed=9)
+    live.load_state_dict(sd)
+    clip = V.synthetic_clip(5, 32, seed=1)
+    m_ref = live.encode_moments(clip)
+    assert (V.encode_moments(sd, cfg, clip) - m_ref).abs().max().item() <= TOL
+    z = V.posterior(m_ref)
+    assert (V.decode(sd, cfg, z) - live.decode(z)).abs().max().item() <= TOL
