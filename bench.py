@@ -71,6 +71,21 @@ def _peaks():
     return {"hbm_gbs": 6650.0, "bf16_burst": 1590.0, "bf16_sustained": 1400.0, "src": "fallback"}
 
 
+def _attention_roofline(detail, pk):
+    """north_star: "achieved fraction of the attention-GEMM roofline" -- the fmha launches of one step by shape (self / cross attention):
+    algorithmic 4*B*H*Lq*Lk*d FLOPs over their CUDA-event time, against the sustained and burst measured bf16 peaks"""
+    out = {}
+    for k, v in detail.items():
+        if not k.startswith("fmha_tcgen05|") or not v["flops"]:
+            continue
+        dims = k.split("|")[1].split("x")
+        name = "self" if dims[2] == dims[3] else "cross"
+        tf = v["flops"] / (v["ms"] / 1e3) / 1e12
+        out[name] = {"shape_BxHxLqxLkxD": k.split("|")[1], "launches": v["launches"], "ms": round(v["ms"], 4), "achieved": tf, "unit": "TFLOP/s",
+                     "frac": tf / pk["bf16_sustained"], "frac_of_burst": tf / pk["bf16_burst"]}
+    return out
+
+
 def _ncu_traffic(kernel):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed `ncu --set full`
     capture (profiles/ncu_traffic.json, written by tools/ncu_summary.py --traffic); None when no capture is committed."""
@@ -142,51 +157,169 @@ def cpu_sample(nb: int, repeats: int = 1):
     return times
 
 
-def cpu_decoder_sample():
-    """One forward of the decoder oracle (full widths: 1024-dim tokens, 22 + 48 blocks, DPT heads) on a reduced
-    view count / resolution (5 views x 224x224 -> 250 880 Gaussians); returns (seconds, Gaussians, description)."""
-    import torch
-
+def cpu_decoder_sample(full: bool = True):
+    """One forward of the decoder oracle (full widths: 1024-dim tokens, 22 + 48 blocks, DPT heads) on the host cores.  full: the BASELINE
+    size, 13 views x 448x448 -> 2 609 152 Gaussians ("one full-size forward", ~1-2 min); else 5 views x 224x224 (1/10.4 of
+    it).  Returns (seconds, Gaussians, description)."""
     from oracle import decoder_ref as D
 
     sd = D.init_state_dict(D.FULL, seed=1, round_bf16=False)
-    lat, img = D.synthetic_inputs(D.FULL, views_latent=2, latent_hw=32, image_hw=224, seed=2)
+    if full:
+        lat, img = D.synthetic_inputs(D.FULL, views_latent=4, latent_hw=64, image_hw=448, seed=2)
+        res, what = 512, "13 views x 448x448 (2 609 152 Gaussians: the whole BASELINE decoder workload, one forward)"
+    else:
+        lat, img = D.synthetic_inputs(D.FULL, views_latent=2, latent_hw=32, image_hw=224, seed=2)
+        res, what = 256, "5 views x 224x224 (250 880 Gaussians; 1/10.4 of the 13 x 448x448 workload)"
     t0 = time.perf_counter()
-    out = D.decoder_forward(sd, D.FULL, lat, img, resolution=256)
+    out = D.decoder_forward(sd, D.FULL, lat, img, resolution=res)
     dt = time.perf_counter() - t0
     n = out["means"].shape[1]
-    return dt, n, "oracle/decoder_ref.py fp32, full-width model, 5 views x 224x224 (250 880 Gaussians; 1/10.4 of the 13 x 448x448 workload)"
+    return dt, n, "oracle/decoder_ref.py fp32, full-width model, " + what
 
 
-def run_reference(args):
+def cpu_full_steps(n_steps: int, warmup: int):
+    """The reference's CPU path for one denoise step, run as it is -- no extrapolation: cond forward + uncond forward of the whole 30-block
+    1.3B DiT at L = 4096 / 512 text tokens (two sequential B = 1 calls, as WanPipeline issues them), CFG combine, UniPC update; oracle
+    restatement (oracle/wan_dit_ref.py + oracle/unipc_ref.py), fp32, all host threads.  Returns the seconds of each timed step."""
     import torch
 
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
-    nb = args.ref_blocks
-    # all the host threads this process may use: torchrun exports OMP_NUM_THREADS=1 to its workers, which would time a 1-thread CPU arm
+    from oracle import unipc_ref as U
+    from oracle import wan_dit_ref as R
+
+    cfg = R.WAN_1_3B
+    sd = R.init_state_dict(cfg, seed=0, round_bf16=False)
+    lat, txt_c = R.synthetic_inputs(cfg, frames=4, hw=64, text_len=512, text_valid=200, seed=0)
+    _, txt_u = R.synthetic_inputs(cfg, frames=4, hw=64, text_len=512, text_valid=60, seed=1)
+    txt_c, txt_u = txt_c.float(), txt_u.float()
+    sch = U.UniPCFlowRef(flow_shift=5.0)
+    sch.set_timesteps(50)
+    x = lat.float()
+    times = []
+    for i in range(warmup + n_steps):
+        if sch.step_index >= 50:       # a new prompt every 50 steps
+            sch.set_timesteps(50)
+            x = lat.float()
+        t0 = time.perf_counter()
+        t = sch.timesteps[sch.step_index].expand(1)
+        c = R.wan_forward(sd, cfg, x, t, txt_c, cast_fp32=False)
+        u = R.wan_forward(sd, cfg, x, t, txt_u, cast_fp32=False)
+        x = sch.step(u + 6.0 * (c - u), x)
+        times.append(time.perf_counter() - t0)
+    return times[warmup:]
+
+
+def _host_threads():
+    """all the host threads this process may use: torchrun exports OMP_NUM_THREADS=1 to its workers, which would time a 1-thread CPU arm"""
+    import torch
+
     try:
         avail = len(os.sched_getaffinity(0))
     except AttributeError:
         avail = os.cpu_count() or 1
     if torch.get_num_threads() < avail:
         torch.set_num_threads(avail)
-    cores = torch.get_num_threads()
-    times = cpu_sample(nb, repeats=args.warmup + args.steps)[args.warmup:]
-    # a denoise step = 2 forwards of 30 blocks; each timed sample is nb blocks of one forward
-    est_step = [2.0 * 30.0 / nb * t for t in times]
+    return torch.get_num_threads()
+
+
+def run_reference(args):
+    """`--impl reference`: the reference's own CPU implementation of the path on the box's host cores.  The DiT lives in un-vendored
+    diffusers (kind "port": the oracle restatement).  Every timed step is one WHOLE denoise step (two 30-block forwards + CFG + UniPC,
+    ~14 s on 16 cores): ms_per_step is what was measured, nothing is extrapolated.  `--ref-blocks < 30` (opt-in, for smoke runs only)
+    shortens the forwards and says so in `sample`."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = _host_threads()
+    nb = max(1, min(30, args.ref_blocks))
+    if nb == 30:
+        times = cpu_full_steps(args.steps, args.warmup)
+        est_step = times
+        sample = ("every timed step is one whole denoise step of the 1.3B DiT (cond + uncond 30-block forwards at L=4096, Lt=512, fp32, "
+                  "CFG combine, UniPC update): measured, not extrapolated")
+    else:
+        times = cpu_sample(nb, repeats=args.warmup + args.steps)[args.warmup:]
+        est_step = [2.0 * 30.0 / nb * t for t in times]
+        sample = (f"SMOKE MODE (--ref-blocks {nb}): each step times {nb} of 30 blocks of ONE forward and extrapolates, steps/s = 1 / (2 * 30/{nb} * t); "
+                  "not a measurement of the full step")
     sps = 1.0 / statistics.mean(est_step)
-    sample = (f"each step times {nb} of 30 full-size 1.3B blocks (L=4096, Lt=512, fp32) of ONE cond forward incl. embed/head; "
-              f"steps/s = 1 / (2 * 30/{nb} * t_sample)")
+    gauss = None
+    if not args.no_decoder:
+        dt, n, what = cpu_decoder_sample(full=not args.cpu_decoder_reduced)
+        gauss = {"decoder_gaussians_per_sec": n / dt, "unit": "Gaussians/s", "cores": cores, "kind": "port", "sample": what + f", {dt:.1f} s"}
     line = {"impl": "reference", "metric": METRIC, "value": sps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * statistics.mean(est_step), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD},
             "cpu_baseline": {"value": sps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": sps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gaussians": None if args.no_decoder else (lambda r: {"decoder_gaussians_per_sec": r[1] / r[0], "unit": "Gaussians/s", "cores": cores,
-                                                                 "kind": "port", "sample": r[2] + f", {r[0]:.1f} s"})(cpu_decoder_sample()),
+            "gaussians": gauss,
             "note": "reference DiT lives in un-vendored diffusers==0.33.1; timed arm is the oracle restatement (oracle/wan_dit_ref.py)"}
+    print(json.dumps(line), flush=True)
+
+
+def run_torch(args):
+    """`--impl torch`: same-box GPU comparator ("torch 2.11's cuBLAS/SDPA/cuDNN executing the same graph").  The DiT graph of
+    the oracle restatement with bf16 weights under CUDA autocast -- i.e. what the reference does on a GPU (fp16 pipeline under bf16
+    autocast, inference_t23d.py:73,87): F.linear -> cuBLAS, F.scaled_dot_product_attention -> flash / cuDNN, LayerNorm in fp32 -- two
+    sequential B = 1 forwards per step as WanPipeline issues them, CFG + UniPC in torch.  None of this repo's kernels run here."""
+    import torch
+
+    from oracle import unipc_ref as U
+    from oracle import wan_dit_ref as R
+
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    configure(args)
+    cfg = R.WAN_1_3B if args.model == "1.3b" else R.WAN_14B
+    g = torch.Generator(device=dev).manual_seed(0)
+    sd = {}
+    for k, shp in R.param_shapes(cfg).items():   # the benchmark's init (SURVEY §8d), generated on the device
+        if k.endswith("scale_shift_table"):
+            sd[k] = torch.randn(shp, device=dev, generator=g) / cfg.inner_dim ** 0.5
+        elif "norm" in k and k.endswith(".weight"):
+            sd[k] = torch.ones(shp, device=dev)
+        elif k.endswith(".bias"):
+            sd[k] = torch.zeros(shp, device=dev, dtype=torch.bfloat16)
+        else:
+            sd[k] = (torch.randn(shp, device=dev, generator=g) * 0.02).bfloat16()
+    T = (args.views - 1) // 4 + 1
+    lat, txt_c = R.synthetic_inputs(cfg, frames=T, hw=64, text_len=512, text_valid=200, seed=0)
+    _, txt_u = R.synthetic_inputs(cfg, frames=T, hw=64, text_len=512, text_valid=60, seed=1)
+    lat, txt_c, txt_u = lat.to(dev), txt_c.to(dev), txt_u.to(dev)
+    sch = U.UniPCFlowRef(flow_shift=5.0)
+    sch.set_timesteps(50)          # the scheduler's scalars stay 0-dim CPU tensors (they combine with CUDA tensors as scalars)
+    state = {"x": lat.float()}
+
+    def step(i):
+        if sch.step_index >= 50:
+            sch.set_timesteps(50)
+            state["x"] = lat.float()
+        t = sch.timesteps[sch.step_index].to(dev).expand(1)
+        x = state["x"].bfloat16()
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            c = R.wan_forward(sd, cfg, x, t, txt_c, cast_fp32=False)
+            u = R.wan_forward(sd, cfg, x, t, txt_u, cast_fp32=False)
+        state["x"] = sch.step((u.float() + 6.0 * (c.float() - u.float())), state["x"])
+
+    with torch.no_grad():
+        for i in range(max(args.warmup, 3)):
+            step(i)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with ClockSampler(dev.index or 0) as clk:
+            e0.record()
+            for i in range(args.steps):
+                step(i)
+            e1.record()
+            torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    line = {"impl": "torch", "metric": METRIC, "value": 1e3 / ms, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "what": "torch eager: oracle DiT graph, bf16 weights under CUDA autocast (cuBLAS GEMMs, torch SDPA, fp32 LayerNorm), "
+                                                      "cond and uncond as two sequential B=1 forwards, CFG + UniPC in torch; comparator only"},
+            "tflops_model": STEP_TFLOP * 1e3 / ms, "clocks": clk.summary(), "torch": torch.__version__}
     print(json.dumps(line), flush=True)
 
 
@@ -366,6 +499,24 @@ def run_ours(args):
                  "latent": "denoised latent of the random-weight DiT, clamped to [-4, 4] before de-normalisation (real VAE latents are O(1))",
                  "workload": f"VIST3A-{'1.3B' if args.model == '1.3b' else '14B'} full stitched path: DiT -> conv3d_k5x3x3 stitch -> AnySplat "
                              f"enc_blocks_2 -> 3DGS, 512x512x{VIEWS}v"}
+        # roofline of the decoder's dominant kernel class: CUDA events around every call of one forward
+        with ops.OpTimer() as tmd:
+            dec.forward_with_latent(lat, img)
+        sd_ = tmd.summary()
+        totd = sum(v["ms"] for v in sd_.values())
+        topd = max((k for k in sd_ if sd_[k]["flops"] > 0), key=lambda k: sd_[k]["ms"])
+        pkd = _peaks()
+        dd = sd_[topd]
+        achd = dd["flops"] / (dd["ms"] / 1e3) / 1e12
+        gauss["roofline"] = {"bound": "tensor", "kernel": topd, "achieved": achd, "peak": pkd["bf16_sustained"], "unit": "TFLOP/s",
+                             "frac": achd / pkd["bf16_sustained"], "frac_of_burst": achd / pkd["bf16_burst"], "peak_src": pkd["src"] + " (sustained)",
+                             "traffic": _ncu_traffic(topd + "|decoder"), "launches_per_forward": dd["launches"], "avg_launch_ms": dd["ms"] / dd["launches"],
+                             "share_of_forward": dd["ms"] / ms_dec, "share_of_eager_kernel_sum": dd["ms"] / totd,
+                             "forward_model_tflops": B * DECODER_TFLOP / (ms_dec / 1e3),
+                             "forward_frac_of_sustained": B * DECODER_TFLOP / (ms_dec / 1e3) / pkd["bf16_sustained"],
+                             "by_kernel": {k: {"ms": round(v["ms"], 4), "launches": v["launches"],
+                                               "tflops": (v["flops"] / (v["ms"] / 1e3) / 1e12) if v["flops"] else None,
+                                               "gbs": v["bytes"] / (v["ms"] / 1e3) / 1e9} for k, v in sd_.items()}}
         if args.render:    # consumer of the Gaussians: re-render the 13 context views from the predicted cameras (rasteriser forward)
             from vist3a_b200.renderer import DecoderSplattingB200
 
@@ -409,7 +560,9 @@ def run_ours(args):
         roof = {"bound": "tensor", "kernel": top, "achieved": ach, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
                 "frac": ach / pk["bf16_sustained"], "frac_of_burst": ach / pk["bf16_burst"], "peak_src": pk["src"] + " (sustained: kernel timed inside a long step)",
                 "traffic": _ncu_traffic(top), "launches_per_step": d["launches"], "avg_launch_ms": d["ms"] / d["launches"],
-                "share_of_step": d["ms"] / tot,
+                "share_of_step": d["ms"] / ms_step, "share_of_eager_kernel_sum": d["ms"] / tot,
+                "share_note": "kernel time from CUDA events around every call of one EAGER step; share_of_step divides it by the CUDA-graphed step time",
+                "attention": _attention_roofline(tm.summary(detail=True), pk),
                 "step_model_tflops": B * STEP_TFLOP / (ms_step / 1e3), "step_frac_of_sustained": B * STEP_TFLOP / (ms_step / 1e3) / pk["bf16_sustained"],
                 "by_kernel": {k: {"ms": round(v["ms"], 4), "launches": v["launches"],
                                   "tflops": (v["flops"] / (v["ms"] / 1e3) / 1e12) if v["flops"] else None,
@@ -423,11 +576,11 @@ def run_ours(args):
             cpu_sample(1)  # spins the thread pool up
             t = cpu_sample(nb)[-1]
             sps = 1.0 / (2.0 * 30.0 / nb * t)
-            cpu = {"value": sps, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            cpu = {"value": sps, "unit": UNIT, "cores": _host_threads(), "kind": "port",
                    "sample": f"{nb} of 30 full-size fp32 blocks of one cond forward incl. embed/head (oracle/wan_dit_ref.py), {t:.2f} s; "
                              f"a step is two such forwards: steps/s = 1/(2*30/{nb}*t)"}
             if gauss is not None:
-                dt, n, what = cpu_decoder_sample()
+                dt, n, what = cpu_decoder_sample(full=not args.cpu_decoder_reduced)
                 gauss["cpu_baseline"] = {"decoder_gaussians_per_sec": n / dt, "cores": torch.get_num_threads(), "kind": "port",
                                          "sample": what + f", {dt:.1f} s"}
         except Exception as e:  # noqa: BLE001
@@ -457,12 +610,14 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "torch"])
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ncu-step", action="store_true", help="profile exactly one eager denoise step (for ncu --profile-from-start off)")
     ap.add_argument("--detail", action="store_true", help="print per-shape kernel timings of one eager step to stderr")
-    ap.add_argument("--ref-blocks", type=int, default=2, help="full-size blocks per timed step of --impl reference")
+    ap.add_argument("--ref-blocks", type=int, default=30, help="--impl reference: 30 (default) = every timed step is a whole measured step; "
+                    "< 30 = smoke mode (shortened forwards, extrapolated, flagged in the line)")
+    ap.add_argument("--cpu-decoder-reduced", action="store_true", help="decoder CPU leg at 5 views x 224x224 instead of the full 13 x 448x448 forward")
     ap.add_argument("--cpu-blocks", type=int, default=30, help="full-size blocks of the cpu_baseline leg (30 = one whole forward, ~10 s on 16 cores)")
     ap.add_argument("--prompts-per-gpu", type=int, default=1, help="prompts batched per GPU (BASELINE configs[4] sweep: 1/2/4/8)")
     ap.add_argument("--no-decoder", action="store_true", help="skip the Gaussians/s leg (decoder + gather)")
@@ -476,6 +631,8 @@ def main():
         args.warmup = 3
     if args.impl == "reference":
         run_reference(args)
+    elif args.impl == "torch":
+        run_torch(args)
     else:
         run_ours(args)
 

@@ -154,15 +154,15 @@ def fold_lora(sd: Dict[str, torch.Tensor], lora: Dict[str, torch.Tensor], lora_a
 # ------------------------------------------------------------------------------------------------
 # forward
 # ------------------------------------------------------------------------------------------------
-def rope_freqs(cfg: WanConfig, f: int, h: int, w: int) -> torch.Tensor:
+def rope_freqs(cfg: WanConfig, f: int, h: int, w: int, device=None) -> torch.Tensor:
     """complex128 [f*h*w, head_dim/2] (WanRotaryPosEmbed): head_dim split t/h/w = 44/42/42 at d=128."""
     hd = cfg.attention_head_dim
     h_dim = w_dim = 2 * (hd // 6)
     t_dim = hd - h_dim - w_dim
     tabs = []
     for dim in (t_dim, h_dim, w_dim):
-        fr = 1.0 / (10000.0 ** (torch.arange(0, dim, 2, dtype=torch.float64)[: dim // 2] / dim))
-        ang = torch.outer(torch.arange(cfg.rope_max_seq_len, dtype=torch.float64), fr)
+        fr = 1.0 / (10000.0 ** (torch.arange(0, dim, 2, dtype=torch.float64, device=device)[: dim // 2] / dim))
+        ang = torch.outer(torch.arange(cfg.rope_max_seq_len, dtype=torch.float64, device=device), fr)
         tabs.append(torch.polar(torch.ones_like(ang), ang))
     ft = tabs[0][:f].view(f, 1, 1, -1).expand(f, h, w, -1)
     fh = tabs[1][:h].view(1, h, 1, -1).expand(f, h, w, -1)
@@ -173,7 +173,7 @@ def rope_freqs(cfg: WanConfig, f: int, h: int, w: int) -> torch.Tensor:
 def timestep_embedding(t: torch.Tensor, dim: int) -> torch.Tensor:
     """Timesteps(num_channels=dim, flip_sin_to_cos=True, downscale_freq_shift=0)."""
     half = dim // 2
-    exponent = -math.log(10000.0) * torch.arange(half, dtype=torch.float32) / half
+    exponent = -math.log(10000.0) * torch.arange(half, dtype=torch.float32, device=t.device) / half
     emb = t.float()[:, None] * torch.exp(exponent)[None]
     return torch.cat([emb.cos(), emb.sin()], dim=-1)
 
@@ -239,14 +239,18 @@ def block_forward(sd, i: int, cfg: WanConfig, x, txt, tproj, freqs):
 
 @torch.no_grad()
 def wan_forward(sd: Dict[str, torch.Tensor], cfg: WanConfig, hidden_states: torch.Tensor, timestep: torch.Tensor,
-                encoder_hidden_states: torch.Tensor, num_layers: Optional[int] = None) -> torch.Tensor:
-    """WanTransformer3DModel.forward(hidden_states [B,C,T,H,W], timestep [B], encoder_hidden_states [B,Lt,text_dim])."""
-    sd = {k: v.float() for k, v in sd.items()}
+                encoder_hidden_states: torch.Tensor, num_layers: Optional[int] = None, cast_fp32: bool = True) -> torch.Tensor:
+    """WanTransformer3DModel.forward(hidden_states [B,C,T,H,W], timestep [B], encoder_hidden_states [B,Lt,text_dim]).
+    cast_fp32=False runs on the tensors as given (any device / dtype): bench.py's `--impl torch` comparator executes this same graph with
+    bf16 weights under CUDA autocast, i.e. through torch's cuBLAS / SDPA kernels."""
+    if cast_fp32:
+        sd = {k: v.float() for k, v in sd.items()}
     B, C, T, H, W = hidden_states.shape
     pt, ph, pw = cfg.patch_size
     f, h, w = T // pt, H // ph, W // pw
-    freqs = rope_freqs(cfg, f, h, w)
-    x = F.conv3d(hidden_states.float(), sd["patch_embedding.weight"], sd["patch_embedding.bias"], stride=cfg.patch_size)
+    freqs = rope_freqs(cfg, f, h, w, device=hidden_states.device)
+    x = F.conv3d(hidden_states.float() if cast_fp32 else hidden_states.to(sd["patch_embedding.weight"].dtype), sd["patch_embedding.weight"],
+                 sd["patch_embedding.bias"], stride=cfg.patch_size)
     x = x.flatten(2).transpose(1, 2)  # [B, L, D], token order (t, h, w)
     temb, tproj, txt = condition_embed(sd, cfg, timestep, encoder_hidden_states)
     for i in range(cfg.num_layers if num_layers is None else num_layers):

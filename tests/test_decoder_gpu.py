@@ -19,7 +19,13 @@ pytestmark = pytest.mark.gpu
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "decoder_tiny.pt")
 GAUSS = ("means", "covariances", "harmonics", "opacities", "scales", "rotations")
-REL_TOL = 2e-2
+# per-field bounds on the rel-L2 error vs the fp32 oracle = 3 x the error measured on the B200 (scales / opacities 2-4e-4,
+# depth 2-7e-4 [bounded at north_star's 1e-3], covariances 1e-3, rotations / harmonics 2-3e-3, pose 3-4e-3); camera-conditioned fields
+# (means, scene scale, c2w) are bounded by FLOOR_MULT x the reference's own GPU-autocast error where that is larger
+BOUNDS = {"scales": 1e-3, "opacities": 1e-3, "depth": 1e-3, "covariances": 3e-3, "rotations": 9e-3, "harmonics": 9e-3,
+          "last_pred_pose_enc": 1.2e-2, "pred_pose_enc_0": 1.2e-2, "pred_pose_enc_3": 1.2e-2, "intrinsic": 1.2e-2, "extrinsic": 1.2e-2,
+          "means": 2e-2, "scene_scale": 2e-2}
+REL_TOL = 2e-2   # fields without an entry above
 FLOOR_MULT = 2.0
 KEYS = GAUSS + ("depth", "extrinsic", "intrinsic", "last_pred_pose_enc", "scene_scale")
 
@@ -35,8 +41,8 @@ def _autocast_floor(D, sd, ocfg, lat, img, resolution, ref):
 def _check(tag, errs, floor):
     print(tag, "ours ", {k: f"{v:.2e}" for k, v in errs.items()})
     print(tag, "floor", {k: f"{v:.2e}" for k, v in floor.items()})
-    bad = {k: (v, floor.get(k.replace("oracle_", ""))) for k, v in errs.items()
-           if not v < max(REL_TOL, FLOOR_MULT * floor.get(k.replace("oracle_", ""), 0.0))}
+    bad = {k: (v, BOUNDS.get(k.replace("oracle_", ""), REL_TOL), floor.get(k.replace("oracle_", ""))) for k, v in errs.items()
+           if not v < max(BOUNDS.get(k.replace("oracle_", ""), REL_TOL), FLOOR_MULT * floor.get(k.replace("oracle_", ""), 0.0))}
     assert not bad, bad
 
 
@@ -164,3 +170,72 @@ def test_decoder_properties_at_13_views():
     mw = g.means.view(13, -1, 3)[:, ::1009].cpu()
     cam = torch.einsum("sij,snj->sni", extr[0, :, :, :3], mw) + extr[0, :, None, :, 3]
     assert torch.allclose(cam[..., 2], d, rtol=2e-3, atol=1e-4)
+
+
+def test_latent_grid_is_resampled_to_resolution_over_8():
+    """upsampling_layer (stitched_model.py:92-107) resizes T *and* H, W: a latent whose grid is not resolution/8 is interpolated
+    (trilinear, align_corners=True) before the stitching conv"""
+    from oracle import decoder_ref as D
+
+    sd = D.init_state_dict(D.TINY, seed=3)
+    lat, img = D.synthetic_inputs(D.TINY, views_latent=2, latent_hw=12, image_hw=56, seed=9)   # 12x12 grid -> 8x8 (resolution 64)
+    ref = D.decoder_forward(sd, D.TINY, lat, img, resolution=64)
+    out = _as_dict(_engine(sd, D.TINY, 64).forward_with_latent(lat.cuda(), img.cuda()))
+    errs = {k: _rel(out[k], ref[k]) for k in KEYS}
+    _check("resampled-latent", errs, _autocast_floor(D, sd, D.TINY, lat, img, 64, ref))
+
+
+def test_load_stitching_model_builds_the_same_engine(tmp_path):
+    """load_stitching_model(args) (nvs_eval.py:21-63 mirror): an UN-stitched AnySplat state dict (4 DINO blocks + patch-embedding conv) +
+    anysplat_stitched.pth (LoRA factors in the stitched numbering, stitching layer, tokens) -> same outputs as the engine built from the
+    already folded stitched state dict; and the attributes the reference's drivers read exist"""
+    import types
+
+    from oracle import decoder_ref as D
+    from vist3a_b200.loader import load_stitching_model
+    from vist3a_b200.renderer import DecoderSplattingB200
+
+    sd = D.init_state_dict(D.TINY, seed=3)
+    pe = "stitched_3d_model.encoder.aggregator.patch_embed."
+    g = torch.Generator().manual_seed(1)
+    A, Bm = torch.randn(4, 64, generator=g) * 0.1, torch.randn(192, 4, generator=g) * 0.1
+    # the AnySplat checkpoint as the hub holds it: keys `encoder.*`, DINO blocks numbered from the patch embedding (2 extra in front)
+    ff = {}
+    for k, v in sd.items():
+        if not k.startswith("stitched_3d_model.encoder."):
+            continue
+        k2 = k[len("stitched_3d_model."):]
+        if k.startswith(pe + "blocks."):
+            idx, tail = k[len(pe + "blocks."):].split(".", 1)
+            k2 = f"encoder.aggregator.patch_embed.blocks.{int(idx) + 2}.{tail}"
+            if idx == "0":
+                for extra in (0, 1):
+                    ff[f"encoder.aggregator.patch_embed.blocks.{extra}.{tail}"] = torch.zeros_like(v)
+        ff[k2] = v
+    ff["encoder.aggregator.patch_embed.patch_embed.proj.weight"] = torch.zeros(64, 3, 14, 14)
+    ff["encoder.aggregator.patch_embed.patch_embed.proj.bias"] = torch.zeros(64)
+    base_qkv = ff["encoder.aggregator.patch_embed.blocks.3.attn.qkv.weight"]      # = stitched blocks.1
+    ck = {"lora": {"encoder.aggregator.patch_embed.blocks.1.attn.qkv.lora_A": A, "encoder.aggregator.patch_embed.blocks.1.attn.qkv.lora_B": Bm},
+          "stitching_layer": {"weight": sd["stitching_layer.weight"], "bias": sd["stitching_layer.bias"]},
+          "cls_token": sd[pe + "cls_token"], "register_tokens": sd[pe + "register_tokens"], "mask_token": sd[pe + "mask_token"]}
+    path = tmp_path / "anysplat_stitched.pth"
+    torch.save(ck, path)
+    args = types.SimpleNamespace(feedforward_model="anysplat", video_model="wan", stitching_layer_location="enc_blocks_2",
+                                 stitching_layer_config="conv3d_k5x3x3_o64_s1x2x2_p2x1x1", resolution=64, initialization_weight_path=None,
+                                 lora_config="r4,a8,d0.05,f0", checkpoint_path=str(path))
+    m = load_stitching_model(args, feedforward_state_dict=ff, device="cuda:0",
+                             config_overrides=dict(num_heads=1, cam_heads=2, dpt_out_channels=(32, 32, 64, 64)))
+    assert m.cfg.dino_blocks == 2 and m.cfg.embed_dim == 64
+    assert isinstance(m.stitched_3d_model.decoder, DecoderSplattingB200)
+    assert m.stitching_layer.weight.shape == (64, 16, 5, 3, 3) and m.stitching_layer.bias.shape == (64,)
+    assert m.stitched_3d_model.encoder.aggregator.patch_embed.cls_token.shape == (1, 1, 64)
+    assert m.stitched_3d_model.encoder.aggregator.patch_embed.register_tokens.shape == (1, 4, 64)
+    sd2 = dict(sd)
+    sd2[pe + "blocks.1.attn.qkv.weight"] = base_qkv + (8.0 / 4.0) * (Bm @ A)
+    lat, img = D.synthetic_inputs(D.TINY, views_latent=2, latent_hw=8, image_hw=56, seed=5)
+    want = _as_dict(_engine(sd2, D.TINY, 64).forward_with_latent(lat.cuda(), img.cuda()))
+    got = _as_dict(m.forward_with_latent(lat.cuda(), img.cuda()))
+    for k in KEYS:
+        assert torch.equal(got[k], want[k]), k
+    plain = _as_dict(_engine(sd, D.TINY, 64).forward_with_latent(lat.cuda(), img.cuda()))
+    assert _rel(plain["harmonics"], want["harmonics"]) > 1e-4      # the adapter changed the model

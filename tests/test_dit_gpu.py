@@ -3,8 +3,10 @@ fp32 CPU oracle (oracle/wan_dit_ref.py) on identical seeded weights, latents and
 
 Stated bf16 tolerance: the engine keeps the reference's CUDA-autocast dtype policy (bf16 GEMM
 operands / residual stream / attention probabilities), so against an all-fp32 oracle the output
-differs by accumulated bf16 rounding: rel-L2 <= 2e-2 for the model output, and no worse than
-1.5x the error of the same oracle graph executed by torch in bf16 autocast on this GPU.
+differs by accumulated bf16 rounding: rel-L2 <= 2e-2 for the model output (3 x the 4.6e-3 - 6e-3 measured
+on the B200 for these cases), and no worse than 1.5x the error of the same oracle graph executed by
+torch in bf16 autocast on this GPU (3.2e-3 - 3.8e-3).  The full 30-layer BASELINE forward and the 50-step
+trajectory are in tests/test_parity_full_gpu.py.
 """
 import pytest
 import torch
@@ -22,37 +24,11 @@ def _rel(a, b):
 
 
 def _torch_bf16_forward(sd, cfg, lat, t, txt, num_layers=None):
-    """the oracle graph run by torch on the GPU under bf16 autocast = the reference's own execution mode"""
+    """the oracle graph run by torch on the GPU under bf16 autocast = the reference's own execution mode (wan_forward upcasts the weights
+    to fp32; F.linear / conv / SDPA under autocast then run in bf16 as in the reference)"""
     sdg = {k: v.cuda() for k, v in sd.items()}
-    R_rope = R.rope_freqs
-
-    def rope_cuda(cfg_, f, h, w):
-        return R_rope(cfg_, f, h, w).cuda()
-
-    R.rope_freqs = rope_cuda
-    try:
-        with torch.autocast("cuda", dtype=torch.bfloat16):
-            return _autocast_forward(sdg, cfg, lat.cuda(), t.cuda(), txt.cuda(), num_layers)
-    finally:
-        R.rope_freqs = R_rope
-
-
-def _autocast_forward(sd, cfg, lat, t, txt, num_layers):
-    # wan_forward upcasts weights to fp32; F.linear/conv/sdpa under autocast then run in bf16 as in the reference
-    orig = R.timestep_embedding
-
-    def te(tt, dim):
-        half = dim // 2
-        import math
-        e = -math.log(10000.0) * torch.arange(half, dtype=torch.float32, device=tt.device) / half
-        emb = tt.float()[:, None] * torch.exp(e)[None]
-        return torch.cat([emb.cos(), emb.sin()], -1)
-
-    R.timestep_embedding = te
-    try:
-        return R.wan_forward(sd, cfg, lat, t, txt, num_layers=num_layers).float()
-    finally:
-        R.timestep_embedding = orig
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        return R.wan_forward(sdg, cfg, lat.cuda(), t.cuda(), txt.cuda(), num_layers=num_layers).float()
 
 
 def _engine(sd, cfg, lora=None):

@@ -96,3 +96,100 @@ def test_apply_stitched_checkpoint_layout():
     q = "stitched_3d_model.encoder.aggregator.frame_blocks.0.attn.qkv."
     assert torch.equal(out[q + "weight"], torch.full((12, 4), 2 * 16.0)) and torch.equal(out[q + "bias"], torch.full((12,), 3.0))
     assert float(out["stitching_layer.weight"].sum()) == 4 * 16 * 45 and float(out["stitched_3d_model.encoder.aggregator.patch_embed.cls_token"].sum()) == 4
+
+
+# ------------------------------------------------------------------------------------------------
+# load_stitching_model(args) mirror: the two argument mini-grammars and the block renumbering
+# ------------------------------------------------------------------------------------------------
+def test_conv_spec_and_lora_grammars_match_the_reference():
+    import pytest
+
+    from vist3a_b200 import loader as LD
+
+    spec = LD.parse_conv_spec("conv3d_k5x3x3_o1024_s1x2x2_p2x1x1")
+    assert (spec.dim, spec.out_channels, spec.kernel_size, spec.stride, spec.padding, spec.dilation) == (3, 1024, (5, 3, 3), (1, 2, 2), (2, 1, 1), 1)
+    assert LD.parse_conv_spec("conv2d_k3_o64") == LD.ConvSpec(2, 64, 3, 1, 0, 1)
+    with pytest.raises(ValueError):
+        LD.parse_conv_spec("conv4d_k3_o8")
+    lc = LD.parse_lora_mode("r8,a16,d0.05,f0")
+    assert (lc.r, lc.alpha, lc.dropout, lc.fan_in_fan_out, lc.bias) == (8, 16, 0.05, False, "lora_only")
+    lc = LD.parse_lora_mode("r4,a32,bnone,tqkv|proj,enc,fix_head")
+    assert (lc.r, lc.alpha, lc.bias, lc.target_modules, lc.finetune_encoder, lc.freeze_head) == (4, 32, "none", ("qkv", "proj"), True, True)
+    with pytest.raises(ValueError):
+        LD.parse_lora_mode("r8,zz")
+    with pytest.raises(ValueError):
+        LD.parse_lora_mode("bsome")
+    # against the reference's own parsers where the reference tree is mounted (build container)
+    import os
+    import sys
+
+    if os.path.isdir("/root/reference/models"):
+        sys.path.insert(0, "/root/reference")
+        try:
+            from models.stitching_layer_builder import parse_conv_spec as ref_conv
+            from utils.lora_util.utils import parse_lora_mode as ref_lora
+        except Exception:
+            return
+        finally:
+            sys.path.remove("/root/reference")
+        for txt in ("conv3d_k5x3x3_o1024_s1x2x2_p2x1x1", "conv2d_k3_o64", "conv1d_k7_o8_s2_p3_d2", "conv3d_k3x3x3_o32_s2_p1"):
+            a, b = LD.parse_conv_spec(txt), ref_conv(txt)
+            assert (a.dim, a.out_channels, a.kernel_size, a.stride, a.padding, a.dilation) == (b.dim, b.out_channels, b.kernel_size, b.stride, b.padding, b.dilation)
+        for txt in ("r8,a16,d0.05,f0", "r4,a32,bnone,tqkv|proj,enc,fix_head", "r16,a1,f1,ball"):
+            a, b = LD.parse_lora_mode(txt), ref_lora(txt)
+            for f in ("r", "alpha", "dropout", "bias", "target_modules", "fan_in_fan_out", "finetune_encoder", "freeze_head"):
+                assert getattr(a, f) == getattr(b, f), (txt, f)
+
+
+def test_unstitched_checkpoint_is_renumbered_or_refused():
+    import pytest
+
+    from vist3a_b200.checkpoint import apply_stitched_checkpoint, renumber_stitched_blocks
+
+    pe = "stitched_3d_model.encoder.aggregator.patch_embed."
+    sd = {pe + "patch_embed.proj.weight": torch.zeros(8, 3, 14, 14), pe + "patch_embed.proj.bias": torch.zeros(8), pe + "cls_token": torch.zeros(1, 1, 8)}
+    for i in range(6):
+        sd[pe + f"blocks.{i}.attn.qkv.weight"] = torch.full((24, 8), float(i))
+    ck = {"lora": {"encoder.aggregator.patch_embed.blocks.0.attn.qkv.lora_A": torch.ones(2, 8),
+                   "encoder.aggregator.patch_embed.blocks.0.attn.qkv.lora_B": torch.ones(24, 2)},
+          "stitching_layer": {"weight": torch.zeros(8, 16, 5, 3, 3), "bias": torch.zeros(8)}}
+    with pytest.raises(ValueError):          # 24-block numbering + patch-embedding conv: refused without the stitch index
+        apply_stitched_checkpoint(sd, ck, lora_alpha=2, lora_r=2)
+    rn = renumber_stitched_blocks(sd, 2)
+    assert pe + "patch_embed.proj.weight" not in rn and pe + "blocks.4.attn.qkv.weight" not in rn
+    assert float(rn[pe + "blocks.0.attn.qkv.weight"][0, 0]) == 2.0 and float(rn[pe + "blocks.3.attn.qkv.weight"][0, 0]) == 5.0
+    out = apply_stitched_checkpoint(sd, ck, lora_alpha=2, lora_r=2, stitched_layer_index=2)
+    # the LoRA delta of stitched blocks.0 lands on ORIGINAL block 2: 2 + (alpha / r) * (B @ A) = 2 + 2
+    assert float(out[pe + "blocks.0.attn.qkv.weight"][0, 0]) == 4.0 and float(out[pe + "blocks.1.attn.qkv.weight"][0, 0]) == 3.0
+
+
+def test_load_stitching_model_argument_errors():
+    import types
+
+    import pytest
+
+    from vist3a_b200 import loader as LD
+
+    args = types.SimpleNamespace(feedforward_model="dust3r", video_model="wan", stitching_layer_location="enc_blocks_2",
+                                 stitching_layer_config="conv3d_k5x3x3_o1024_s1x2x2_p2x1x1", resolution=512, initialization_weight_path=None,
+                                 lora_config="r8,a16,d0.05,f0", checkpoint_path=None)
+    with pytest.raises(NotImplementedError):
+        LD.load_stitching_model(args, feedforward_state_dict={})
+    args.feedforward_model = "anysplat"
+    args.video_model = "cogvideo"
+    with pytest.raises(NotImplementedError):
+        LD.load_stitching_model(args, feedforward_state_dict={})
+    args.video_model = "wan"
+    args.stitching_layer_location = "dec_blocks_1"
+    with pytest.raises(NotImplementedError):
+        LD.load_stitching_model(args, feedforward_state_dict={})
+    args.stitching_layer_location = "enc_blocks_2"
+    args.stitching_layer_config = "conv3d_k3x3x3_o1024_s1x2x2_p1x1x1"
+    with pytest.raises(NotImplementedError):
+        LD.load_stitching_model(args, feedforward_state_dict={})
+    args.stitching_layer_config = "not_a_conv"
+    with pytest.raises(ValueError):
+        LD.load_stitching_model(args, feedforward_state_dict={})
+    args.stitching_layer_config = "conv3d_k5x3x3_o1024_s1x2x2_p2x1x1"
+    with pytest.raises(FileNotFoundError):    # no network path: the AnySplat weights must be local
+        LD.load_stitching_model(args)

@@ -37,8 +37,9 @@ struct FmhaParams {
   long long* trace;        // debug: 32 clock64 stamps / phase sums per CTA (v3a_debug_fmha_trace), normally null
 };
 
-static long long* g_fmha_trace = nullptr;
-extern "C" void v3a_debug_fmha_trace(void* buf) { g_fmha_trace = reinterpret_cast<long long*>(buf); }
+// debug hook (tools/fmha_trace.py), off unless armed: process-wide by design, read once per launch
+static std::atomic<long long*> g_fmha_trace{nullptr};
+extern "C" void v3a_debug_fmha_trace(void* buf) { g_fmha_trace.store(reinterpret_cast<long long*>(buf)); }
 #define FMHA_TRACE_ADD(slot, val)                                                                                     \
   do {                                                                                                                \
     if (p.trace) p.trace[((long long)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 32 + (slot)] = (val); \
@@ -616,15 +617,12 @@ static int launch_fmha(const vist3a_fmha_args& a, cudaStream_t stream) {
   p.len_q = (int)a.len_q; p.len_kv = (int)a.len_kv;
   p.scale_log2 = a.scale * 1.4426950408889634f;
   p.row_scale = a.q_row_scale;
-  p.trace = g_fmha_trace;
+  p.trace = g_fmha_trace.load(std::memory_order_relaxed);
   p.single_issuer = (a.flags & 4u) ? 1 : 0;
   p.direct_store = (a.flags & 64u) ? 1 : 0;
   auto kern = fmha_fwd_kernel<D, BKV_, POLY_, SPLIT_>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    V3A_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    attr_set = true;
-  }
+  static std::atomic<unsigned long long> attr_done{0};  // per template instantiation, one bit per device
+  V3A_CUDA_OK(ensure_dynamic_smem(kern, Cfg::SMEM_BYTES, attr_done));
   const long long rows_per_cta = Cfg::BQ * Cfg::QT;
   dim3 grid((unsigned)((a.len_q + rows_per_cta - 1) / rows_per_cta), (unsigned)a.heads, (unsigned)a.batch);
   V3A_CUDA_OK(launch_kernel(kern, grid, dim3(Cfg::THREADS), Cfg::SMEM_BYTES, stream, /*pdl=*/true, 1, tmQ, tmK, tmV, tmO, p));

@@ -42,8 +42,9 @@ struct GemmEpilogue {
   long long* trace;  // debug (v3a_debug_gemm_trace): 8 cycle counters per CTA, normally null
 };
 
-static long long* g_gemm_trace = nullptr;
-extern "C" void v3a_debug_gemm_trace(void* buf) { g_gemm_trace = reinterpret_cast<long long*>(buf); }
+// debug hook (tools/gemm_trace.py), off unless armed: process-wide by design, read once per launch
+static std::atomic<long long*> g_gemm_trace{nullptr};
+extern "C" void v3a_debug_gemm_trace(void* buf) { g_gemm_trace.store(reinterpret_cast<long long*>(buf)); }
 
 constexpr int kConvTW = 16, kConvTH = 8;  // pixel patch of one 128-row A tile
 
@@ -592,14 +593,11 @@ static int launch_gemm(const vist3a_gemm_args& a, cudaStream_t stream) {
   ep.rmap = {a.rmap.rpg, a.rmap.gstride, a.rmap.goff};
   ep.out_fp32 = a.out_dtype == VIST3A_DTYPE_F32;
   ep.act = a.act; ep.post_act = a.post_act; ep.round_linear = a.round_linear; ep.round_gate = a.round_gate;
-  ep.trace = g_gemm_trace;
+  ep.trace = g_gemm_trace.load(std::memory_order_relaxed);
 
   auto kern = gemm_tcgen05_kernel<BN, kCta, kTF32>;
-  static bool attr_set = false;  // per template instantiation
-  if (!attr_set) {
-    V3A_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    attr_set = true;
-  }
+  static std::atomic<unsigned long long> attr_done{0};  // per template instantiation, one bit per device
+  V3A_CUDA_OK(ensure_dynamic_smem(kern, Cfg::SMEM_BYTES, attr_done));
   if (a.conv.enabled) tmA64 = tmA;
   shape.mc = (kCta == 2 && BN == 256 && !a.conv.enabled && (a.flags & VIST3A_GEMM_FLAG_MULTICAST) && shape.tiles_n % 2 == 0) ? 1 : 0;
   const int csize = shape.mc ? 4 : kCta;

@@ -445,7 +445,7 @@ int gs_rasterize_entry(const void* proj_workspace, long long N, long long n_isec
   launches += 1;
   if (n_isect > 0) {
     gs_emit_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(pw.geom, pw.bbox, pw.touched, pw.offsets, N, tiles_x, w.keys_a, w.vals_a);
-    radix_sort_enqueue(w.keys_a, w.keys_b, w.vals_a, w.vals_b, n_isect, passes, w.npasses, w.block_hist, w.digit_total, st);
+    V3A_CUDA_OK(radix_sort_enqueue(w.keys_a, w.keys_b, w.vals_a, w.vals_b, n_isect, passes, w.npasses, w.block_hist, w.digit_total, st));
     gs_tile_ranges_kernel<<<(unsigned)((n_isect + 255) / 256), 256, 0, st>>>(w.keys_a, w.keys_b, w.npasses, n_isect, w.tile_start, w.tile_end);
     launches += 2 + 3 * passes;
   }

@@ -56,6 +56,20 @@ inline cudaError_t launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, 
   return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
 
+// Opt a kernel in to `bytes` of dynamic shared memory.  The attribute is per device (context), so the "already done" record is a
+// per-device bit (devices >= 64: set every time); concurrent first calls from several threads set it twice, which is harmless.
+template <typename K>
+inline cudaError_t ensure_dynamic_smem(K kern, int bytes, std::atomic<unsigned long long>& done) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  const unsigned long long bit = dev < 64 ? (1ull << dev) : 0ull;
+  if (bit && (done.load(std::memory_order_acquire) & bit)) return cudaSuccess;
+  e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess && bit) done.fetch_or(bit, std::memory_order_release);
+  return e;
+}
+
 #define V3A_CUDA_OK(expr)                                                                             \
   do {                                                                                                \
     cudaError_t _e = (expr);                                                                          \

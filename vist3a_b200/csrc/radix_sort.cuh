@@ -7,6 +7,7 @@
 // sit in the a-buffers if *npasses is even, in the b-buffers otherwise.
 #pragma once
 #include "common.cuh"
+#include "host_util.cuh"
 
 namespace v3a {
 namespace {
@@ -197,19 +198,17 @@ __global__ void __launch_bounds__(kSortThreads) radix_scatter_kernel(const unsig
 }
 
 // enqueue `max_passes` passes; block_hist holds 256 * nblocks counters, digit_total 256
-inline void radix_sort_enqueue(unsigned long long* keys_a, unsigned long long* keys_b, unsigned* vals_a, unsigned* vals_b, long long n, int max_passes,
+inline cudaError_t radix_sort_enqueue(unsigned long long* keys_a, unsigned long long* keys_b, unsigned* vals_a, unsigned* vals_b, long long n, int max_passes,
                                const int* npasses, unsigned* block_hist, unsigned* digit_total, cudaStream_t st) {
   const int nblocks = (int)((n + kSortTile - 1) / kSortTile);
-  static bool attr_set = false;  // one copy of the kernel (and of this flag) per translation unit
-  if (!attr_set) {
-    cudaFuncSetAttribute(radix_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kScatterSmem);
-    attr_set = true;
-  }
+  static std::atomic<unsigned long long> attr_done{0};  // one copy of the kernel (and of this record) per translation unit; one bit per device
+  if (ensure_dynamic_smem(radix_scatter_kernel, kScatterSmem, attr_done) != cudaSuccess) return cudaGetLastError();
   for (int pass = 0; pass < max_passes; ++pass) {
     radix_hist_kernel<<<nblocks, kSortThreads, 0, st>>>(keys_a, keys_b, n, pass, npasses, block_hist, nblocks);
     radix_scan_kernel<<<256, 256, 0, st>>>(block_hist, nblocks, digit_total, pass, npasses);
     radix_scatter_kernel<<<nblocks, kSortThreads, kScatterSmem, st>>>(keys_a, keys_b, vals_a, vals_b, n, pass, npasses, block_hist, nblocks, digit_total);
   }
+  return cudaSuccess;
 }
 
 }  // namespace

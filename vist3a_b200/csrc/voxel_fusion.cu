@@ -412,7 +412,7 @@ int voxel_fusion_entry(const float* pts, const float* feats, long long ld_feats,
   voxel_key_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(pts, N, voxel_size, w.header, w.keys_a, w.vals_a);
   launches += 4;
   // passes >= ceil(bits / 8) return immediately (device-side count: no host round trip)
-  radix_sort_enqueue(w.keys_a, w.keys_b, w.vals_a, w.vals_b, N, 8, &w.header->npasses, w.block_hist, w.digit_total, st);
+  V3A_CUDA_OK(radix_sort_enqueue(w.keys_a, w.keys_b, w.vals_a, w.vals_b, N, 8, &w.header->npasses, w.block_hist, w.digit_total, st));
   launches += 24;
   seg_count_kernel<<<w.nscan, 256, 0, st>>>(w.keys_a, w.keys_b, N, w.header, w.partial);
   seg_scan_partials_kernel<<<1, 1024, 0, st>>>(w.partial, w.nscan, w.header, n_voxels, w.seg_start, N);

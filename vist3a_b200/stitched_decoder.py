@@ -86,6 +86,11 @@ class DecoderConfig:
                                # layer; dino_blocks then counts ALL DINO blocks (24 in the released model)
     voxelize: bool = False   # EncoderAnySplatCfg.voxelize (AS/model/encoder/anysplat.py:125; true in config/experiment/*.yaml)
     voxel_size: float = 0.002  # config/experiment/dl3dv.yaml:20
+    # confidence-quantile branches (EncoderAnySplatCfg.render_conf / opacity_conf / conf_threshold, AS/model/encoder/anysplat.py:83-125;
+    # models/anysplat_stitched.py:381-387, 443-467; off in every released config)
+    render_conf: bool = False
+    opacity_conf: bool = False
+    conf_threshold: float = 0.1
 
     @property
     def d_sh(self):
@@ -266,6 +271,10 @@ class StitchVAE3DB200(torch.nn.Module):
             return t.detach().float().to(dev, torch.bfloat16).contiguous()
 
         pe = E + "aggregator.patch_embed."
+        if not cfg.patch_embed and (pe + "patch_embed.proj.weight" in sd or pe + f"blocks.{cfg.dino_blocks}.norm1.weight" in sd):
+            # an un-stitched AnySplat checkpoint numbers its DINO blocks 0..23; the stitched model's blocks.i are original blocks.(i + k)
+            raise ValueError(f"load_weights: the state dict holds patch_embed.patch_embed.proj / blocks.{cfg.dino_blocks}: it carries the UN-stitched "
+                             "block numbering; renumber it with vist3a_b200.checkpoint.renumber_stitched_blocks(sd, k) (k of enc_blocks_k) first")
         if cfg.patch_embed:
             pw = sd[pe + "patch_embed.proj.weight"].detach().float().reshape(C, -1)     # k = c*p*p + py*p + px
             self._pe_k = (pw.shape[1] + 7) // 8 * 8                                      # 588 -> 592 (16-byte TMA row stride)
@@ -354,6 +363,14 @@ class StitchVAE3DB200(torch.nn.Module):
         w["rope.cos"], w["rope.sin"] = f32(ang.cos()), f32(ang.sin())
         self.w = w
         self._tables = {}
+        # attributes the reference's drivers read off the model: `.stitched_3d_model.decoder` (the renderer handed to
+        # save_interpolated_video, inference_t23d.py:154), `.stitching_layer.{weight,bias}` and the patch-embed tokens
+        # (nvs_eval.py:51-61; model_stitching_training.py:33-72 saves exactly these)
+        from .renderer import DecoderSplattingB200
+
+        pe_ns = SimpleNamespace(cls_token=sd[pe + "cls_token"], register_tokens=sd[pe + "register_tokens"], mask_token=sd.get(pe + "mask_token"))
+        self.stitched_3d_model = SimpleNamespace(decoder=DecoderSplattingB200((1.0, 1.0, 1.0)),
+                                                 encoder=SimpleNamespace(aggregator=SimpleNamespace(patch_embed=pe_ns), cfg=cfg))
 
     def weight_bytes(self) -> int:
         return sum(t.numel() * t.element_size() for t in self.w.values())
@@ -586,8 +603,16 @@ class StitchVAE3DB200(torch.nn.Module):
         if latent.shape[0] != B or (latent.shape[2] - 1) * 4 + 1 != V:
             raise ValueError(f"latent {tuple(latent.shape)} does not match {V} views x batch {B}")
         lat_hw = cfg.resolution // 8
-        if latent.shape[-2:] != (lat_hw, lat_hw):  # upsampling_layer also resizes H, W to resolution/8 (stitched_model.py:92-107)
-            raise NotImplementedError(f"latent grid {tuple(latent.shape[-2:])} != resolution/8 = {lat_hw}: spatial resampling is not on the hot path")
+        if latent.shape[-2:] != (lat_hw, lat_hw):
+            # upsampling_layer also resizes H, W to resolution/8 (stitched_model.py:92-107: one trilinear, align_corners=True interpolation
+            # to [4(T-1)+1, res/8, res/8]).  Trilinear interpolation is separable: the spatial part runs here (bilinear kernel on the
+            # [B*T, h, w, 16] view of the latent), the temporal part stays fused in the stitching conv's operand gather.
+            Bl, Cl, Tl, hl, wl = latent.shape
+            x = latent.float().permute(0, 2, 3, 4, 1).reshape(Bl * Tl, hl, wl, Cl).contiguous()
+            if Cl % 8:
+                raise NotImplementedError(f"spatial resampling of a {Cl}-channel latent (the bilinear kernel moves 8-channel groups)")
+            x = ops.bilinear_nhwc(x, lat_hw, lat_hw)
+            latent = x.view(Bl, Tl, lat_hw, lat_hw, Cl).permute(0, 4, 1, 2, 3).contiguous()
         return self._decode(latent, feedforward_image, B, V, H, W)
 
     @torch.no_grad()

@@ -217,11 +217,23 @@ class WanTransformer3DModelB200(torch.nn.Module):
             ops.rmsnorm_rope_(kv[i][:, :D], w[k + "nk2q2"], c.attention_head_dim, eps=c.eps)
         return SimpleNamespace(kv=kv, B=B, Lt=Lt)
 
+    TEXT_CACHE_SLOTS = 4  # cond + uncond of the current prompt stay cached while WanPipeline alternates them (2 calls per step)
+
     def _text_state(self, enc: torch.Tensor):
-        key = (enc.data_ptr(), tuple(enc.shape), enc._version, enc.dtype)
-        if self._text_cache is None or self._text_cache[0] != key:
-            self._text_cache = (key, self.encode_text(enc))
-        return self._text_cache[1]
+        """Per-prompt text state, cached on the IDENTITY of the embedding tensor (the entry keeps a reference to it, so the caching
+        allocator cannot hand its address to another prompt's embeddings) plus its in-place version counter; least recently used of
+        TEXT_CACHE_SLOTS entries is dropped."""
+        cache = self._text_cache if self._text_cache is not None else []
+        for n, (t, ver, st) in enumerate(cache):
+            if t is enc and ver == enc._version:
+                if n:
+                    cache.insert(0, cache.pop(n))
+                return st
+        st = self.encode_text(enc)
+        cache.insert(0, (enc, enc._version, st))
+        del cache[self.TEXT_CACHE_SLOTS:]
+        self._text_cache = cache
+        return st
 
     # ------------------------------------------------------------------ forward
     def _workspace(self, B, L):
@@ -239,7 +251,7 @@ class WanTransformer3DModelB200(torch.nn.Module):
                 mod2=torch.empty((B, 2, D), dtype=torch.float32, device=dev),
                 po=torch.empty((M, self.w["out.w"].shape[0]), dtype=bf, device=dev),
                 rq=torch.empty((M,), dtype=torch.float32, device=dev))
-            self._ws = {key: ws}  # one live shape at a time
+            self._ws[key] = ws  # every shape stays alive: a captured CUDA graph (DenoiseEngine) holds the pointers of its workspace
         return ws
 
     @torch.no_grad()
