@@ -87,7 +87,9 @@ typedef struct vist3a_conv {
   int32_t enabled;
   int32_t kh, kw, pad_y, pad_x;
   int32_t n_img, h, w, c_in; /* stride-1 conv: h_out = h + 2*pad_y - kh + 1, w_out = w + 2*pad_x - kw + 1 */
-  int32_t reserved;
+  int32_t kt;                /* 0 / 1: 2-D conv.  > 1: causal temporal taps over the image (= frame) index: output frame t reads frames
+                                t + dt - (kt - 1), dt = 0..kt-1, frames before the first are zero (WanCausalConv3d, utils/wan_utils.py:96-147);
+                                K = kt*kh*kw*c_in, taps ordered (dt, dy, dx).  One clip per call (the frame shift must not cross clips). */
   int64_t pix_stride, row_stride, img_stride;
 } vist3a_conv;
 

@@ -220,29 +220,34 @@ def condition_embed(sd, cfg: WanConfig, timestep: torch.Tensor, text: torch.Tens
     return temb, tproj, txt
 
 
-def block_forward(sd, i: int, cfg: WanConfig, x, txt, tproj, freqs):
-    """WanTransformerBlock.forward (AdaLN-zero; chunk order shift, scale, gate, c_shift, c_scale, c_gate)."""
+def block_forward(sd, i: int, cfg: WanConfig, x, txt, tproj, freqs, stream_dtype=None):
+    """WanTransformerBlock.forward (AdaLN-zero; chunk order shift, scale, gate, c_shift, c_scale, c_gate).
+    stream_dtype: the dtype the residual stream is kept in.  diffusers computes every gated residual add in fp32 and casts the sum back
+    with `.type_as(hidden_states)`, so a bf16 pipeline carries a bf16 stream; None = no rounding (the fp32 oracle)."""
     p = f"blocks.{i}."
+    cast = (lambda t: t.to(stream_dtype)) if stream_dtype is not None else (lambda t: t)
     sh1, sc1, g1, sh2, sc2, g2 = (sd[p + "scale_shift_table"].float() + tproj.float()).chunk(6, dim=1)
-    h = _ln(x, eps=cfg.eps) * (1 + sc1) + sh1
-    x = x + _attention(sd, p + "attn1.", h, h, cfg, freqs) * g1
+    h = cast(_ln(x, eps=cfg.eps) * (1 + sc1) + sh1)
+    x = cast(x.float() + _attention(sd, p + "attn1.", h, h, cfg, freqs) * g1) if stream_dtype is not None else x + _attention(sd, p + "attn1.", h, h, cfg, freqs) * g1
     if cfg.cross_attn_norm:
-        h = _ln(x, sd[p + "norm2.weight"], sd[p + "norm2.bias"], cfg.eps)
+        h = cast(_ln(x, sd[p + "norm2.weight"], sd[p + "norm2.bias"], cfg.eps))
     else:
         h = x
-    x = x + _attention(sd, p + "attn2.", h, txt, cfg, None)
-    h = _ln(x, eps=cfg.eps) * (1 + sc2) + sh2
+    x = cast(x + _attention(sd, p + "attn2.", h, txt, cfg, None))
+    h = cast(_ln(x, eps=cfg.eps) * (1 + sc2) + sh2)
     f = F.linear(F.gelu(F.linear(h, sd[p + "ffn.net.0.proj.weight"], sd[p + "ffn.net.0.proj.bias"]), approximate="tanh"),
                  sd[p + "ffn.net.2.weight"], sd[p + "ffn.net.2.bias"])
-    return x + f * g2
+    return cast(x.float() + f.float() * g2) if stream_dtype is not None else x + f * g2
 
 
 @torch.no_grad()
 def wan_forward(sd: Dict[str, torch.Tensor], cfg: WanConfig, hidden_states: torch.Tensor, timestep: torch.Tensor,
-                encoder_hidden_states: torch.Tensor, num_layers: Optional[int] = None, cast_fp32: bool = True) -> torch.Tensor:
+                encoder_hidden_states: torch.Tensor, num_layers: Optional[int] = None, cast_fp32: bool = True,
+                stream_dtype=None) -> torch.Tensor:
     """WanTransformer3DModel.forward(hidden_states [B,C,T,H,W], timestep [B], encoder_hidden_states [B,Lt,text_dim]).
     cast_fp32=False runs on the tensors as given (any device / dtype): bench.py's `--impl torch` comparator executes this same graph with
-    bf16 weights under CUDA autocast, i.e. through torch's cuBLAS / SDPA kernels."""
+    bf16 weights under CUDA autocast, i.e. through torch's cuBLAS / SDPA kernels.  stream_dtype=torch.bfloat16 additionally keeps the
+    residual stream in bf16 between blocks, as a bf16 diffusers pipeline does (see block_forward)."""
     if cast_fp32:
         sd = {k: v.float() for k, v in sd.items()}
     B, C, T, H, W = hidden_states.shape
@@ -253,8 +258,10 @@ def wan_forward(sd: Dict[str, torch.Tensor], cfg: WanConfig, hidden_states: torc
                  sd["patch_embedding.bias"], stride=cfg.patch_size)
     x = x.flatten(2).transpose(1, 2)  # [B, L, D], token order (t, h, w)
     temb, tproj, txt = condition_embed(sd, cfg, timestep, encoder_hidden_states)
+    if stream_dtype is not None:
+        x = x.to(stream_dtype)
     for i in range(cfg.num_layers if num_layers is None else num_layers):
-        x = block_forward(sd, i, cfg, x, txt, tproj, freqs)
+        x = block_forward(sd, i, cfg, x, txt, tproj, freqs, stream_dtype)
     shift, scale = (sd["scale_shift_table"] + temb[:, None]).chunk(2, dim=1)
     x = _ln(x, eps=cfg.eps) * (1 + scale) + shift
     x = F.linear(x, sd["proj_out.weight"], sd["proj_out.bias"])

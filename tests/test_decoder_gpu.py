@@ -235,7 +235,7 @@ def test_load_stitching_model_builds_the_same_engine(tmp_path):
     lat, img = D.synthetic_inputs(D.TINY, views_latent=2, latent_hw=8, image_hw=56, seed=5)
     want = _as_dict(_engine(sd2, D.TINY, 64).forward_with_latent(lat.cuda(), img.cuda()))
     got = _as_dict(m.forward_with_latent(lat.cuda(), img.cuda()))
-    for k in KEYS:
-        assert torch.equal(got[k], want[k]), k
+    for k in KEYS:   # same weights, same kernels: identical (the scene scale is an atomic float sum: equal up to summation order)
+        assert torch.equal(got[k], want[k]) if k != "scene_scale" else _rel(got[k], want[k]) < 1e-5, k
     plain = _as_dict(_engine(sd, D.TINY, 64).forward_with_latent(lat.cuda(), img.cuda()))
     assert _rel(plain["harmonics"], want["harmonics"]) > 1e-4      # the adapter changed the model

@@ -45,13 +45,18 @@ def test_dit_1p3b_all_30_layers_baseline_shape():
     # the reference's own execution mode on this GPU: the same graph by torch under bf16 autocast (cuBLAS / SDPA)
     sdg = {k: (v.cuda().bfloat16() if v.dim() > 1 and "scale_shift_table" not in k else v.cuda()) for k, v in sd.items()}
     with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
-        auto = R.wan_forward(sdg, cfg, lat.cuda(), t.cuda(), txt.cuda(), cast_fp32=False).float()
-    e_ours, e_torch = _rel(out, ref), _rel(auto, ref)
-    print(f"1.3B x 30 layers, L=4096, Lt=512: rel-L2 vs fp32 oracle: ours {e_ours:.3e}, torch-bf16-autocast {e_torch:.3e}")
+        # (a) as the reference runs it: bf16 pipeline, the residual stream rounded to bf16 after every gated add (`.type_as(hidden_states)`)
+        auto = R.wan_forward(sdg, cfg, lat.cuda(), t.cuda(), txt.cuda(), cast_fp32=False, stream_dtype=torch.bfloat16).float()
+        # (b) the same graph with an fp32 residual stream (what type promotion gives when nothing casts back): a lower bound on bf16 error
+        auto32 = R.wan_forward(sdg, cfg, lat.cuda(), t.cuda(), txt.cuda(), cast_fp32=False).float()
+    e_ours, e_torch, e_torch32 = _rel(out, ref), _rel(auto, ref), _rel(auto32, ref)
+    print(f"1.3B x 30 layers, L=4096, Lt=512: rel-L2 vs fp32 oracle: ours {e_ours:.3e}, torch-bf16 (bf16 stream, the reference's policy) {e_torch:.3e}, "
+          f"torch-bf16 (fp32 stream) {e_torch32:.3e}")
     assert out.shape == (1, 16, 4, 64, 64) and bool(torch.isfinite(out).all())
-    # bound: bf16 rounding of the residual stream accumulates over 30 layers (measured 2-layer 5e-3); stay within 1.5 x torch's own
-    # bf16 execution of the graph and below 3e-2 absolute
-    assert e_ours < 3e-2
+    # bound: the engine keeps diffusers' dtype policy -- a bf16 residual stream, rounded after each of the 90 residual adds -- so its
+    # error against the fp32 oracle is that policy's (measured on the B200: ours 1.37e-2; fp32-stream torch 4.7e-3).  Stay within 1.5 x
+    # the error of torch executing the same policy, and below 3 x measured in absolute terms
+    assert e_ours < 4e-2
     assert e_ours < 1.5 * e_torch + 1e-3
 
 
@@ -80,7 +85,7 @@ def test_50_step_trajectory_reduced_depth():
     e = _rel(out, ref)
     print(f"50-step trajectory (2 layers, L=512): rel-L2 {e:.3e}")
     assert bool(torch.isfinite(out).all())
-    assert e < 5e-2   # guidance 6 amplifies the per-step bf16 error ~6x (8-step tiny trajectory: 1e-2)
+    assert e < 1.5e-2   # 3 x the 4.1e-3 measured on the B200 (guidance 6 amplifies the per-step bf16 error)
 
 
 # --------------------------------------------------------------------------------------------------------------------------------
@@ -120,8 +125,11 @@ def test_fmha_global_lengths(L):
 # --------------------------------------------------------------------------------------------------------------------------------
 # per-field bounds = 3 x the rel-L2 error measured on the B200 against the fp32 oracle at this size; the fields of
 # the first group do not pass through the predicted cameras and meet north_star's 1e-3
-BOUNDS_13V = {"scales": 1e-3, "opacities": 1e-3, "depth": 1e-3, "covariances": 3e-3, "rotations": 8e-3, "harmonics": 8e-3,
-              "last_pred_pose_enc": 1.2e-2, "intrinsic": 1.2e-2, "extrinsic": 1.2e-2, "means": 9e-2, "scene_scale": 9e-2}
+# measured (B200, r2): scales 4.1e-4, opacities 2.3e-4, depth 7.9e-4, covariances 1.2e-3, rotations 1.9e-3, harmonics 1.9e-3, pose 3.0e-3,
+# intrinsic 2.2e-3, extrinsic 6.1e-3, means 7.9e-3, scene scale 8.7e-4; the reference's own GPU numerics (floor): 3.0e-4, 1.7e-4, 5.3e-4,
+# 1.5e-3, 2.8e-3, 1.2e-3, 4.2e-3, 2.4e-3, 8.6e-3, 1.2e-2, 3.8e-5
+BOUNDS_13V = {"scales": 1e-3, "opacities": 1e-3, "depth": 1e-3, "covariances": 3.6e-3, "rotations": 6e-3, "harmonics": 6e-3,
+              "last_pred_pose_enc": 9e-3, "intrinsic": 7e-3, "extrinsic": 1.8e-2, "means": 2.4e-2, "scene_scale": 3e-3}
 FLOOR_MULT = 2.0
 
 

@@ -66,7 +66,7 @@ class RowMap(C.Structure):
 
 class Conv(C.Structure):
     _fields_ = [("enabled", C.c_int32), ("kh", C.c_int32), ("kw", C.c_int32), ("pad_y", C.c_int32), ("pad_x", C.c_int32),
-                ("n_img", C.c_int32), ("h", C.c_int32), ("w", C.c_int32), ("c_in", C.c_int32), ("reserved", C.c_int32),
+                ("n_img", C.c_int32), ("h", C.c_int32), ("w", C.c_int32), ("c_in", C.c_int32), ("kt", C.c_int32),
                 ("pix_stride", C.c_int64), ("row_stride", C.c_int64), ("img_stride", C.c_int64)]
 
 

@@ -1,0 +1,402 @@
+// tcgen05 fused attention forward on CTA PAIRS (cta_group::2), head_dim 128:  O = softmax(Q K^T * scale) V, non-causal, no mask.
+//
+// Why pairs.  The single-CTA kernel (fmha_sm100.cu) issues S = Q K^T as SS-mode MMAs of 128 x 64 x 16: every MMA re-reads its 4 KB Q slice
+// and a 2 KB K slice from shared memory = 192 B/clk against the 128 B/clk an SM's shared memory delivers, so the QK half of the tensor work
+// runs at 2/3 speed (traced floor: 1280 cycles per 1024 cycles of tensor work).  With cta_group::2 one MMA covers 256 query rows x 128 keys:
+// each CTA supplies its OWN 128 query rows (4 KB per MMA) and only HALF of the key tile (64 keys, 2 KB) for 64 cycles of tensor time
+// = 96 B/clk, and P V (A = P from tensor memory, B = half of V's head-dim columns: 2 KB per MMA) needs 32 B/clk.  TMA traffic halves too
+// (each CTA loads half of every K and V tile: 32 KB per 128-key step).
+//
+// One cluster of two CTAs per (batch, head, 256 query rows); CTA r owns query rows [128 r, 128 r + 128).
+//   warp 0        TMA producer (both CTAs): own Q tile once; per 128-key step the CTA's half of K (keys [64 r, 64 r + 64), all of d) and its half
+//                 of V (all 128 keys, head-dim columns [64 r, 64 r + 64)); "full" barriers live in the leader CTA (2-SM TMA completion)
+//   warp 1        MMA issuer, leader CTA only: S(j) = Q K(j)^T into TMEM score buffer j % 2, O += P(j) V(j) (P read from TMEM), for both CTAs;
+//                 completion is multicast to both CTAs' barriers (tcgen05.commit ... multicast::cluster)
+//   warp 2        TMEM allocator (cta_group::2, 512 columns)
+//   warps 4..     softmax, SPLIT threads per query row (thread = TMEM lane x column slice): tcgen05.ld S, row max (slices exchange through
+//                 shared memory + a named barrier), lazy rescale of O, exp2, bf16 P -> tcgen05.st over the S buffer it came from, arrive on
+//                 the LEADER's p_full barrier (remote arrive from the peer CTA)
+// TMEM map per CTA (512 columns): S0 | P0 [0,128)   S1 | P1 [128,256)   O [256,384).  S is double-buffered: Q K(j+2)^T is queued behind
+// P(j) V(j) in the in-order tensor pipe (it overwrites the buffer P(j) lives in), so the next score tile is ready when the softmax warps
+// finish the current one and the tensor pipe never waits for a "buffer free" handshake.
+#include "common.cuh"
+#include "fmha_math.cuh"
+#include "host_util.cuh"
+
+namespace v3a {
+
+struct FmhaPairParams {
+  int len_q, len_kv;
+  float scale_log2;        // scale * log2(e)
+  const float* row_scale;  // optional per-(batch, query row) positive factor on the logits
+};
+
+template <int SPLIT_, int POLY_>
+struct FmhaPairCfg {
+  static constexpr int D = 128, BQ = 128, BKV = 128;
+  static constexpr int SPLIT = SPLIT_;                 // softmax threads per query row
+  static constexpr int POLY = POLY_;                   // of every 8 column pairs, this many take exp2 on the FMA pipe
+  static constexpr int HC = BKV / SPLIT;               // score columns per softmax thread and step
+  static constexpr int OC = D / SPLIT;                 // O columns per softmax thread (rescale, epilogue)
+  static constexpr int THREADS = 128 + 128 * SPLIT;
+  static constexpr int Q_SLAB_BYTES = BQ * 128;        // 64 head-dim columns (128 B) x 128 rows
+  static constexpr int Q_TILE_BYTES = 2 * Q_SLAB_BYTES;
+  static constexpr int K_SLAB_BYTES = (BKV / 2) * 128; // this CTA's 64 keys x 64 head-dim columns
+  static constexpr int K_HALF_BYTES = 2 * K_SLAB_BYTES;  // 16 KB
+  static constexpr int V_HALF_BYTES = BKV * 128;       // 128 keys x this CTA's 64 head-dim columns = 16 KB
+  static constexpr int ST = 4;                         // ring stages of K and of V
+  static constexpr int NBARS = 1 + 4 * ST + 6;         // q_full | k_full, k_empty, v_full, v_empty | s_full[2], p_full[2], pv_done[2]
+  static constexpr int XCH_BYTES = 2 * SPLIT * 128 * 4;  // [step parity][slice][row] fp32
+  static constexpr int SMEM_BYTES = Q_TILE_BYTES + ST * (K_HALF_BYTES + V_HALF_BYTES) + 1024 + 8 * NBARS + 16 + XCH_BYTES;
+  static constexpr uint32_t TM_S = 0, S_STRIDE = 128, TM_O = 256;
+  static_assert(SPLIT == 2 || SPLIT == 4, "SPLIT");
+  static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
+};
+
+template <int SPLIT_, int POLY_>
+__global__ void __launch_bounds__(128 + 128 * SPLIT_, 1)
+fmha_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
+                 const __grid_constant__ CUtensorMap tmO, const FmhaPairParams p) {
+  using Cfg = FmhaPairCfg<SPLIT_, POLY_>;
+  constexpr int SPLIT = Cfg::SPLIT, HC = Cfg::HC, OC = Cfg::OC, ST = Cfg::ST, BKV = Cfg::BKV, D = Cfg::D;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t smem_q = smem_base;
+  auto smem_k = [&](int s) { return smem_base + Cfg::Q_TILE_BYTES + Cfg::K_HALF_BYTES * s; };
+  auto smem_v = [&](int s) { return smem_base + Cfg::Q_TILE_BYTES + Cfg::K_HALF_BYTES * ST + Cfg::V_HALF_BYTES * s; };
+  const uint32_t bar_base = smem_base + Cfg::Q_TILE_BYTES + ST * (Cfg::K_HALF_BYTES + Cfg::V_HALF_BYTES);
+  const uint32_t q_full = bar_base;
+  auto k_full = [&](int s) { return bar_base + 8u * (1 + s); };
+  auto k_empty = [&](int s) { return bar_base + 8u * (1 + ST + s); };
+  auto v_full = [&](int s) { return bar_base + 8u * (1 + 2 * ST + s); };
+  auto v_empty = [&](int s) { return bar_base + 8u * (1 + 3 * ST + s); };
+  auto s_full = [&](int b) { return bar_base + 8u * (1 + 4 * ST + b); };
+  auto p_full = [&](int b) { return bar_base + 8u * (1 + 4 * ST + 2 + b); };
+  auto pv_done = [&](int b) { return bar_base + 8u * (1 + 4 * ST + 4 + b); };
+  const uint32_t tmem_slot = bar_base + 8u * Cfg::NBARS;
+  const uint32_t xch_base = tmem_slot + 16u;
+
+  const uint32_t warp = warp_id_sync();
+  const uint32_t lane = lane_id();
+  const uint32_t rank = cluster_ctarank();          // 0 = leader
+  const bool leader = rank == 0;
+  const int q0 = (int)(blockIdx.x >> 1) * (2 * Cfg::BQ) + (int)rank * Cfg::BQ;   // first query row of this CTA
+  const int head = blockIdx.y, batch = blockIdx.z;
+  const int n_kv = (p.len_kv + BKV - 1) / BKV;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    tma_prefetch_desc(&tmO);
+  }
+  if (warp == 1 && lane == 0) {
+    mbar_init(q_full, 1);
+    for (int s = 0; s < ST; ++s) {
+      mbar_init(k_full(s), 1);
+      mbar_init(k_empty(s), 1);
+      mbar_init(v_full(s), 1);
+      mbar_init(v_empty(s), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(s_full(b), 1);
+      mbar_init(p_full(b), 2 * 4 * SPLIT);   // one arrival per softmax warp of BOTH CTAs (only the leader's copy is used)
+      mbar_init(pv_done(b), 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<2>(tmem_slot, 512);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  pdl_launch_dependents();
+  pdl_wait();  // PDL: q / k / v written by the previous kernel are read (and O written) only after this point
+
+  if (warp == 0) {
+    // ------------------------------ TMA producer (warp-uniform control flow, one elected lane issues) ------------------------------
+    if (elect_one()) {
+      if (leader) mbar_expect_tx(q_full, 2u * Cfg::Q_TILE_BYTES);
+#pragma unroll
+      for (int sl = 0; sl < 2; ++sl) tma_load_4d_2sm(smem_q + sl * Cfg::Q_SLAB_BYTES, &tmQ, q_full, sl * 64, head, q0, batch);
+    }
+    __syncwarp();
+    int s = 0;
+    uint32_t ph = 0;
+    for (int j = 0; j < n_kv; ++j) {
+      mbar_wait(k_empty(s), ph ^ 1u);
+      if (elect_one()) {
+        if (leader) mbar_expect_tx(k_full(s), 2u * Cfg::K_HALF_BYTES);
+#pragma unroll
+        for (int sl = 0; sl < 2; ++sl)
+          tma_load_4d_2sm(smem_k(s) + sl * Cfg::K_SLAB_BYTES, &tmK, k_full(s), sl * 64, head, j * BKV + (int)rank * (BKV / 2), batch);
+      }
+      __syncwarp();
+      mbar_wait(v_empty(s), ph ^ 1u);
+      if (elect_one()) {
+        if (leader) mbar_expect_tx(v_full(s), 2u * Cfg::V_HALF_BYTES);
+        tma_load_4d_2sm(smem_v(s), &tmV, v_full(s), (int)rank * 64, head, j * BKV, batch);
+      }
+      __syncwarp();
+      if (++s == ST) { s = 0; ph ^= 1u; }
+    }
+  } else if (warp == 1) {
+    // ------------------------------ MMA issue (leader CTA; the whole warp runs the control flow, one elected lane issues) ----------
+    if (leader) {
+      constexpr uint32_t idesc_qk = make_idesc(kFmtBF16, 256, BKV, 0, 0);
+      constexpr uint32_t idesc_pv = make_idesc(kFmtBF16, 256, D, 0, 1);   // B (V) is MN-major
+      int qs = 0, vs = 0;
+      uint32_t qph = 0, vph = 0;
+      auto issue_qk = [&](int j) {
+        mbar_wait(k_full(qs), qph);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t d_tmem = tmem_base + Cfg::TM_S + (uint32_t)(j & 1) * Cfg::S_STRIDE;
+          const uint64_t qdesc = make_smem_desc_sw128(smem_q, 1024, 0);
+          const uint64_t kdesc = make_smem_desc_sw128(smem_k(qs), 1024, 0);
+#pragma unroll
+          for (int kk = 0; kk < D / 16; ++kk) {
+            // +32 B along the head dim inside a swizzle atom = +2 in the (addr >> 4) field; next 64-column slab = + SLAB_BYTES
+            const uint64_t ao = (uint64_t)(((kk >> 2) * Cfg::Q_SLAB_BYTES + (kk & 3) * 32) >> 4);
+            const uint64_t bo = (uint64_t)(((kk >> 2) * Cfg::K_SLAB_BYTES + (kk & 3) * 32) >> 4);
+            umma_f16_ss<2>(d_tmem, qdesc + ao, kdesc + bo, idesc_qk, kk ? 1u : 0u);
+          }
+          umma_commit_2sm_mc(s_full(j & 1), 3);
+          umma_commit_2sm_mc(k_empty(qs), 3);
+        }
+        __syncwarp();
+        if (++qs == ST) { qs = 0; qph ^= 1u; }
+      };
+      auto issue_pv = [&](int j) {
+        mbar_wait(v_full(vs), vph);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t p_tmem = tmem_base + Cfg::TM_S + (uint32_t)(j & 1) * Cfg::S_STRIDE;
+          // this CTA's V half: key rows at a 128 B pitch (K dimension of the MMA), 64 head-dim columns = one swizzle row (MN dimension)
+          const uint64_t vdesc = make_smem_desc_sw128(smem_v(vs), 1024, Cfg::V_HALF_BYTES);
+#pragma unroll
+          for (int kk = 0; kk < BKV / 16; ++kk)
+            umma_f16_ts_2sm(tmem_base + Cfg::TM_O, p_tmem + (uint32_t)(kk * 8), vdesc + (uint64_t)((kk * 2048) >> 4), idesc_pv, (j | kk) ? 1u : 0u);
+          umma_commit_2sm_mc(pv_done(j & 1), 3);
+          umma_commit_2sm_mc(v_empty(vs), 3);
+        }
+        __syncwarp();
+        if (++vs == ST) { vs = 0; vph ^= 1u; }
+      };
+      mbar_wait(q_full, 0);
+      issue_qk(0);
+      if (n_kv > 1) issue_qk(1);
+      for (int j = 0; j < n_kv; ++j) {
+        mbar_wait_cluster(p_full(j & 1), (uint32_t)(j >> 1) & 1u);   // P(j) of both CTAs is in tensor memory
+        tc_fence_after();
+        issue_pv(j);
+        if (j + 2 < n_kv) issue_qk(j + 2);   // overwrites S(j) | P(j): ordered behind P(j) V(j) by the in-order tensor pipe
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------ softmax / correction / epilogue (both CTAs) ------------------------------
+    const int h = (int)(warp - 4u) >> 2;             // column slice of this warp
+    const uint32_t wq = warp & 3u;                   // TMEM lane quadrant this warp may access
+    const int rit = (int)(wq * 32u + lane);          // row in this CTA's tile
+    const uint32_t lane_base = tmem_base + ((wq * 32u) << 16);
+    const int row = q0 + rit;
+    const uint32_t o_addr = lane_base + Cfg::TM_O + (uint32_t)(h * OC);
+    auto xch = [&](int par, int slice) { return xch_base + 4u * (uint32_t)((par * SPLIT + slice) * 128 + rit); };
+    const uint32_t quad_bar = 1u + wq;               // named barrier of the SPLIT warps that own these 32 rows
+    float m_run = -INFINITY;                         // running (possibly stale) row max of raw scores
+    float l_run = 0.0f;                              // running sum of exp2((s - m_run) * c) over this thread's columns
+    const float c = (p.row_scale && row < p.len_q) ? p.scale_log2 * p.row_scale[(long long)batch * p.len_q + row] : p.scale_log2;
+    const uint64_t cc2 = pack2(c, c);
+    for (int j = 0; j < n_kv; ++j) {
+      const int b = j & 1;
+      mbar_wait(s_full(b), (uint32_t)(j >> 1) & 1u);
+      tc_fence_after();
+      uint32_t r[HC];
+      const uint32_t s_addr = lane_base + Cfg::TM_S + (uint32_t)b * Cfg::S_STRIDE + (uint32_t)(h * HC);
+#pragma unroll
+      for (int cb = 0; cb < HC / 32; ++cb) tmem_ld_x32(s_addr + (uint32_t)(cb * 32), r + cb * 32);
+      tmem_ld_wait();
+      const int valid = p.len_kv - j * BKV - h * HC;   // columns of this thread that hold existing keys
+      if (valid < HC) {
+#pragma unroll
+        for (int k = 0; k < HC; ++k)
+          if (k >= valid) r[k] = 0xff800000u;  // -inf
+      }
+      float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+      for (int k = 0; k < HC; k += 8) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) mx[u] = fmaxf(fmaxf(mx[u], __uint_as_float(r[k + 2 * u])), __uint_as_float(r[k + 2 * u + 1]));
+      }
+      float m_tile = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+      // the slices of a row exchange their partial max; the barrier also orders every slice's S loads before anybody's P stores into
+      // the columns they were read from (P aliases the first 64 columns of the score buffer)
+      asm volatile("st.shared.f32 [%0], %1;" ::"r"(xch(b, h)), "f"(m_tile) : "memory");
+      asm volatile("bar.sync %0, %1;" ::"r"(quad_bar), "n"(32 * SPLIT) : "memory");
+#pragma unroll
+      for (int o = 1; o < SPLIT; ++o) {
+        float other;
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(other) : "r"(xch(b, (h + o) % SPLIT)) : "memory");
+        m_tile = fmaxf(m_tile, other);
+      }
+      const float m_new = fmaxf(m_run, m_tile);
+      if (j == 0) {
+        m_run = m_new;
+      } else {
+        const bool need = (m_new - m_run) * c > 8.0f;
+        if (__any_sync(0xffffffffu, need)) {
+          // O is accumulated by P(j-1) V(j-1): it must have finished before the rows are rescaled
+          mbar_wait(pv_done((j - 1) & 1), (uint32_t)((j - 1) >> 1) & 1u);
+          tc_fence_after();
+          const float f = need ? ex2_approx((m_run - m_new) * c) : 1.0f;
+          if (need) m_run = m_new;
+          l_run *= f;
+#pragma unroll 1
+          for (int cb = 0; cb < OC / 16; ++cb) {   // 16 columns at a time: the score row stays live in registers
+            uint32_t o[16];
+            tmem_ld_x16(o_addr + (uint32_t)(cb * 16), o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int k = 0; k < 16; ++k) o[k] = __float_as_uint(__uint_as_float(o[k]) * f);
+            tmem_st_x16(o_addr + (uint32_t)(cb * 16), o);
+          }
+          tmem_st_wait();
+        }
+      }
+      const float nmc = -m_run * c;
+      const uint64_t mc2 = pack2(nmc, nmc);
+      uint64_t sum2[2] = {0ull, 0ull};   // packed (even, odd) column partial sums
+      const uint32_t p_addr = lane_base + Cfg::TM_S + (uint32_t)b * Cfg::S_STRIDE + (uint32_t)(h * (HC / 2));
+#pragma unroll
+      for (int cb = 0; cb < HC / 32; ++cb) {
+        uint32_t pk[16];
+        if (cb * 32 >= valid) {   // (warp-uniform) a 32-column chunk past the last key: P = 0 without its exponentials
+#pragma unroll
+          for (int k = 0; k < 16; ++k) pk[k] = 0u;
+          tmem_st_x16(p_addr + (uint32_t)(cb * 16), pk);
+          continue;
+        }
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          float y0, y1, e0, e1;
+          unpack2(fma2(pack2(__uint_as_float(r[cb * 32 + 2 * k]), __uint_as_float(r[cb * 32 + 2 * k + 1])), cc2, mc2), y0, y1);
+          if ((k & 7) < Cfg::POLY) {
+            exp2_poly2(y0, y1, e0, e1);
+          } else {
+            e0 = ex2_approx(y0);
+            e1 = ex2_approx(y1);
+          }
+          sum2[k & 1] = add2(sum2[k & 1], pack2(e0, e1));
+          pk[k] = pack_bf16(e0, e1);
+        }
+        tmem_st_x16(p_addr + (uint32_t)(cb * 16), pk);
+      }
+      {
+        float s0, s1, s2, s3;
+        unpack2(sum2[0], s0, s1);
+        unpack2(sum2[1], s2, s3);
+        l_run += (s0 + s1) + (s2 + s3);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (leader) mbar_arrive(p_full(b)); else mbar_arrive_cluster(p_full(b), 0);
+      }
+    }
+    // ---- epilogue: O / l -> bf16 -> shared memory (this CTA's Q buffer: every MMA has completed) -> one bulk tensor store per slab ----
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(xch(n_kv & 1, h)), "f"(l_run) : "memory");
+    asm volatile("bar.sync %0, %1;" ::"r"(quad_bar), "n"(32 * SPLIT) : "memory");
+#pragma unroll
+    for (int o = 1; o < SPLIT; ++o) {
+      float other;
+      asm volatile("ld.shared.f32 %0, [%1];" : "=f"(other) : "r"(xch(n_kv & 1, (h + o) % SPLIT)) : "memory");
+      l_run += other;
+    }
+    mbar_wait(pv_done((n_kv - 1) & 1), (uint32_t)((n_kv - 1) >> 1) & 1u);   // the commit covers every earlier MMA too
+    tc_fence_after();
+    const float inv_l = 1.0f / l_run;
+#pragma unroll
+    for (int cb = 0; cb < OC / 32; ++cb) {
+      uint32_t o[32];
+      tmem_ld_x32(o_addr + (uint32_t)(cb * 32), o);
+      tmem_ld_wait();
+      const int col0 = h * OC + cb * 32;   // first of 32 consecutive output columns
+      const uint32_t srow = smem_q + (uint32_t)((col0 >> 6) * Cfg::Q_SLAB_BYTES + rit * 128);
+#pragma unroll
+      for (int k = 0; k < 32; k += 8) {
+        const uint32_t chunk = (uint32_t)(((col0 & 63) + k) >> 3);
+        const uint32_t dst = srow + ((chunk ^ ((uint32_t)rit & 7u)) << 4);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst),
+                     "r"(pack_bf16(__uint_as_float(o[k]) * inv_l, __uint_as_float(o[k + 1]) * inv_l)),
+                     "r"(pack_bf16(__uint_as_float(o[k + 2]) * inv_l, __uint_as_float(o[k + 3]) * inv_l)),
+                     "r"(pack_bf16(__uint_as_float(o[k + 4]) * inv_l, __uint_as_float(o[k + 5]) * inv_l)),
+                     "r"(pack_bf16(__uint_as_float(o[k + 6]) * inv_l, __uint_as_float(o[k + 7]) * inv_l))
+                     : "memory");
+      }
+    }
+    fence_proxy_async_smem();
+    asm volatile("bar.sync %0, %1;" ::"r"(5u), "n"(128 * SPLIT) : "memory");   // all softmax threads of this CTA
+    if (warp == 4 && lane == 0) {
+#pragma unroll
+      for (int sl = 0; sl < 2; ++sl) tma_store_4d(&tmO, smem_q + sl * Cfg::Q_SLAB_BYTES, sl * 64, head, q0, batch);   // rows >= len_q are clipped
+      tma_store_commit();
+      tma_store_wait_read<0>();   // the buffer must stay intact until the TMA unit has read it
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();   // the peer's tensor memory / shared memory is in use until both CTAs are done
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<2>(tmem_base, 512);
+  }
+}
+
+static int make_map4(CUtensorMap* tm, const void* ptr, long long B, long long H, long long L, long long D, long long bs, long long rs,
+                     long long hs, uint32_t box_rows) {
+  // dims (fastest first): head_dim, heads, rows, batch; box = 64 head-dim columns (128 B: one swizzle row) x box_rows rows
+  uint64_t dims[4] = {(uint64_t)D, (uint64_t)H, (uint64_t)L, (uint64_t)B};
+  uint64_t strides[3] = {(uint64_t)hs * 2, (uint64_t)rs * 2, (uint64_t)bs * 2};
+  uint32_t box[4] = {64, 1, box_rows, 1};
+  return encode_tensor_map(tm, ptr, 2, false, 4, dims, strides, box, true);
+}
+
+template <int SPLIT_, int POLY_>
+static int launch_fmha_pair(const vist3a_fmha_args& a, cudaStream_t stream) {
+  using Cfg = FmhaPairCfg<SPLIT_, POLY_>;
+  CUtensorMap tmQ, tmK, tmV, tmO;
+  int rc;
+  if ((rc = make_map4(&tmQ, a.Q, a.batch, a.heads, a.len_q, 128, a.q_bs, a.q_rs, a.q_hs, Cfg::BQ))) return rc;
+  if ((rc = make_map4(&tmK, a.K, a.batch, a.heads, a.len_kv, 128, a.k_bs, a.k_rs, a.k_hs, Cfg::BKV / 2))) return rc;
+  if ((rc = make_map4(&tmV, a.V, a.batch, a.heads, a.len_kv, 128, a.v_bs, a.v_rs, a.v_hs, Cfg::BKV))) return rc;
+  if ((rc = make_map4(&tmO, a.O, a.batch, a.heads, a.len_q, 128, a.o_bs, a.o_rs, a.o_hs, Cfg::BQ))) return rc;
+  FmhaPairParams p;
+  p.len_q = (int)a.len_q;
+  p.len_kv = (int)a.len_kv;
+  p.scale_log2 = a.scale * 1.4426950408889634f;
+  p.row_scale = a.q_row_scale;
+  auto kern = fmha_pair_kernel<SPLIT_, POLY_>;
+  static std::atomic<unsigned long long> attr_done{0};
+  V3A_CUDA_OK(ensure_dynamic_smem(kern, Cfg::SMEM_BYTES, attr_done));
+  const long long rows_per_cluster = 2 * Cfg::BQ;
+  dim3 grid((unsigned)(2 * ((a.len_q + rows_per_cluster - 1) / rows_per_cluster)), (unsigned)a.heads, (unsigned)a.batch);
+  V3A_CUDA_OK(launch_kernel(kern, grid, dim3(Cfg::THREADS), Cfg::SMEM_BYTES, stream, /*pdl=*/true, 2, tmQ, tmK, tmV, tmO, p));
+  launch_counter().fetch_add(1);
+  return VIST3A_OK;
+}
+
+// head_dim 128 on CTA pairs; `variant`: 0 = default (4 threads per row, all MUFU), 1 = 2 threads per row, 2 / 3 = 1 / 2 of 8 column pairs
+// on the FMA pipe (4 threads per row)
+int fmha_pair_entry(const vist3a_fmha_args& a, int variant, cudaStream_t stream) {
+  switch (variant) {
+    case 1: return launch_fmha_pair<2, 0>(a, stream);
+    case 2: return launch_fmha_pair<4, 1>(a, stream);
+    case 3: return launch_fmha_pair<4, 2>(a, stream);
+    case 4: return launch_fmha_pair<2, 2>(a, stream);
+    default: return launch_fmha_pair<4, 0>(a, stream);
+  }
+}
+
+}  // namespace v3a

@@ -22,6 +22,7 @@
 // TMEM map, 256 columns per query tile:  d=128: S0|P0 [0,64)  S1|P1 [64,128)  O [128,256)
 //                                        d=64:  S [0,128)  P [128,192)  O [192,256)
 #include "common.cuh"
+#include "fmha_math.cuh"
 #include "host_util.cuh"
 
 namespace v3a {
@@ -80,50 +81,6 @@ struct FmhaCfg {
   static_assert(TM_O + D <= TILE_COLS, "TMEM budget");
 };
 
-
-__device__ __forceinline__ float ex2_approx(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
-  uint64_t r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-  return r;
-}
-__device__ __forceinline__ void unpack2(uint64_t v, float& lo, float& hi) {
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
-}
-__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {  // packed 2 x fp32 FADD2
-  uint64_t d;
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-  return d;
-}
-__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {  // packed 2 x fp32 FFMA2
-  uint64_t d;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-  return d;
-}
-// exp2 of two values on the FMA / ALU pipes: y = n + f (n integer, |f| <= 0.5), 2^f by a degree-3 minimax polynomial
-// (max rel. error 1.0e-4), 2^n by adding n to the exponent field.  y is clamped to >= -126.
-__device__ __forceinline__ void exp2_poly2(float y0, float y1, float& e0, float& e1) {
-  const uint64_t one = pack2(1.0f, 1.0f);
-  const uint64_t magic = pack2(12582912.0f, 12582912.0f);      // 1.5 * 2^23: rounds to nearest integer
-  const uint64_t nmagic = pack2(-12582912.0f, -12582912.0f);
-  const uint64_t neg1 = pack2(-1.0f, -1.0f);
-  const uint64_t yy = pack2(fmaxf(y0, -126.0f), fmaxf(y1, -126.0f));
-  const uint64_t t = fma2(yy, one, magic);
-  const uint64_t n = fma2(t, one, nmagic);
-  const uint64_t f = fma2(n, neg1, yy);
-  uint64_t q = fma2(f, pack2(0.055008664727211f, 0.055008664727211f), pack2(0.24221056699752808f, 0.24221056699752808f));
-  q = fma2(q, f, pack2(0.6932829022407532f, 0.6932829022407532f));
-  q = fma2(q, f, one);
-  float t0, t1, q0, q1;
-  unpack2(t, t0, t1);
-  unpack2(q, q0, q1);
-  e0 = __int_as_float(__float_as_int(q0) + (__float_as_int(t0) << 23));
-  e1 = __int_as_float(__float_as_int(q1) + (__float_as_int(t1) << 23));
-}
 
 template <int D, int BKV_, int POLY_, int SPLIT_>
 __global__ void __launch_bounds__(128 + 256 * SPLIT_, 1)
@@ -630,6 +587,8 @@ static int launch_fmha(const vist3a_fmha_args& a, cudaStream_t stream) {
   return VIST3A_OK;
 }
 
+int fmha_pair_entry(const vist3a_fmha_args& a, int variant, cudaStream_t stream);   // fmha_pair_sm100.cu
+
 int fmha_entry(const vist3a_fmha_args* args, cudaStream_t stream) {
   V3A_REQUIRE(args != nullptr, VIST3A_ERR_INVALID, "fmha: null args");
   const vist3a_fmha_args& a = *args;
@@ -649,6 +608,8 @@ int fmha_entry(const vist3a_fmha_args* args, cudaStream_t stream) {
   // d=64 -- the fastest of the variants measured on B200 (tools/fmha_variants.py).  flags bit0 selects one thread per row (2 softmax
   // warpgroups, setmaxnreg-enlarged register file), bit1 (d=128) the 128-key aliased steps, bit2 a single MMA-issuing warp for both query tiles (measured slower: one thread cannot keep
   // the pipe fed); kept for A/B measurements.
+  // head_dim 128: the CTA-pair kernel (fmha_pair_sm100.cu); flags bit 8 selects it, bits 9-11 its variant (A/B measurements)
+  if (a.head_dim == 128 && (a.flags & 256u)) return fmha_pair_entry(a, (int)((a.flags >> 9) & 7u), stream);
   const bool one = (a.flags & 1u) != 0;
   // Share of the exponentials moved from the MUFU to the FMA pipe (Cody-Waite + polynomial), per 8 column pairs.  Measured on B200 with
   // two threads per query row (4 softmax warpgroups): the softmax is bound by issue slots and dependent-latency chains rather than by

@@ -54,6 +54,7 @@ struct GemmShape {
   int mc;                // clusters of two CTA pairs on neighbouring column tiles, the shared A rows multicast between them (kCta == 2 only)
   // conv mode
   int conv, kh, kw, pad_y, pad_x, n_img, h, w, c_in, h_out, w_out, tiles_x, tiles_y, cblocks;
+  int kt;                // causal temporal taps (>= 1): the image coordinate of tap dt is img + dt - (kt - 1); negative = zero fill
 };
 
 template <int BN, int kCta, bool kTF32>
@@ -72,7 +73,9 @@ struct GemmCfg {
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + STAGING_BYTES;
   static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
   // BN = 176 (pairs only, A/B flag): 9 column tiles of a 1536-wide output fill 4 waves of 74 CTA pairs to 97 % (6 tiles of 256: 3 waves at 86 %)
-  static_assert(BN == 64 || BN == 128 || BN == 256 || (BN == 176 && kCta == 2), "BN");
+  // BN = 96 / 192: output widths that are multiples of 96 but not of 128 (the Wan VAE's 96 / 192 / 384-channel layers, the 84-wide Gaussian
+  // head): a 128 / 256-wide tile would spend a quarter of its MMA columns on padding
+  static_assert(BN == 64 || BN == 96 || BN == 128 || BN == 192 || BN == 256 || (BN == 176 && kCta == 2), "BN");
   static_assert(BN % 16 == 0 && BN_LOCAL % 8 == 0, "MMA N granularity (16) / swizzle atom rows (8)");
   static_assert(TMEM_COLS <= 512, "TMEM");
 };
@@ -180,7 +183,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   pdl_launch_dependents();
   pdl_wait();
 
-  const int num_kb = shape.conv ? shape.kh * shape.kw * shape.cblocks : (shape.K + Cfg::BK - 1) / Cfg::BK;
+  const int num_kb = shape.conv ? shape.kt * shape.kh * shape.kw * shape.cblocks : (shape.K + Cfg::BK - 1) / Cfg::BK;
   const int num_tiles = shape.mc ? shape.tiles_m * (shape.tiles_n / 2) : shape.tiles_m * shape.tiles_n;
   const int worker = blockIdx.x / csize;
   const int num_workers = gridDim.x / csize;
@@ -202,12 +205,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       int img = 0, y0 = 0, x0 = 0;
       if (shape.conv) {
         const int per_img = shape.tiles_x * shape.tiles_y;
-        img = mt / per_img;
+        img = mt / per_img - (shape.kt - 1);
         const int t2 = mt % per_img;
         y0 = (t2 / shape.tiles_x) * kConvTH - shape.pad_y;
         x0 = (t2 % shape.tiles_x) * kConvTW - shape.pad_x;
       }
-      int cb = 0, dy = 0, dx = 0;
+      int cb = 0, dy = 0, dx = 0, dt = 0;
       for (int kb = 0; kb < num_kb; ++kb) {
         if (ep.trace) {
           const long long t1 = clock64();
@@ -219,12 +222,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         if (elect_one()) {
           if constexpr (kCta == 1) {
             mbar_expect_tx(full_bar(s), Cfg::STAGE_BYTES);
-            if (shape.conv) tma_load_4d(smem_a(s), &tmA, full_bar(s), cb * Cfg::BK, x0 + dx, y0 + dy, img);
+            if (shape.conv) tma_load_4d(smem_a(s), &tmA, full_bar(s), cb * Cfg::BK, x0 + dx, y0 + dy, img + dt);
             else tma_load_2d(smem_a(s), &tmA, full_bar(s), kb * Cfg::BK, m0);
             tma_load_2d(smem_b(s), &tmB, full_bar(s), kb * Cfg::BK, n0);
           } else {
             if (leader) mbar_expect_tx(full_bar(s), 2 * Cfg::STAGE_BYTES);
-            if (shape.conv) tma_load_4d_2sm(smem_a(s), &tmA, full_bar(s), cb * Cfg::BK, x0 + dx, y0 + dy, img);
+            if (shape.conv) tma_load_4d_2sm(smem_a(s), &tmA, full_bar(s), cb * Cfg::BK, x0 + dx, y0 + dy, img + dt);
             else if (shape.mc)
               tma_load_2d_2sm_mc(smem_a(s) + pr * (Cfg::A_BYTES / 2), &tmA64, full_bar(s), kb * Cfg::BK, m0 + (int)pr * (Cfg::BM / 2),
                                  (uint16_t)((1u << rank) | (1u << (rank + 2))));
@@ -236,7 +239,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         if (++s == STAGES) { s = 0; ph ^= 1u; }
         if (shape.conv && ++cb == shape.cblocks) {
           cb = 0;
-          if (++dx == shape.kw) { dx = 0; ++dy; }
+          if (++dx == shape.kw) {
+            dx = 0;
+            if (++dy == shape.kh) { dy = 0; ++dt; }
+          }
         }
       }
     }
@@ -549,7 +555,7 @@ static int launch_gemm(const vist3a_gemm_args& a, cudaStream_t stream) {
   if (a.conv.enabled) {
     const vist3a_conv& c = a.conv;
     shape.conv = 1; shape.kh = c.kh; shape.kw = c.kw; shape.pad_y = c.pad_y; shape.pad_x = c.pad_x;
-    shape.n_img = c.n_img; shape.h = c.h; shape.w = c.w; shape.c_in = c.c_in;
+    shape.n_img = c.n_img; shape.h = c.h; shape.w = c.w; shape.c_in = c.c_in; shape.kt = c.kt > 1 ? c.kt : 1;
     shape.h_out = c.h + 2 * c.pad_y - c.kh + 1;
     shape.w_out = c.w + 2 * c.pad_x - c.kw + 1;
     shape.tiles_x = (shape.w_out + kConvTW - 1) / kConvTW;
@@ -642,9 +648,12 @@ static int dispatch_gemm(const vist3a_gemm_args& a, cudaStream_t stream) {
       auto cost = [&](long long bn) { return ((tm * ((a.N + bn - 1) / bn) + pairs - 1) / pairs) * bn; };
       if (cost(176) * 103 < cost(256) * 100) return launch_gemm<176, 2, kTF32>(a, stream);
     }
+    // 192-wide tiles when they cover N with strictly fewer padded columns than 256-wide ones (N = 192, 384, 1152, ...)
+    if ((a.N + 191) / 192 * 192 < (a.N + 255) / 256 * 256) return two ? launch_gemm<192, 2, kTF32>(a, stream) : launch_gemm<192, 1, kTF32>(a, stream);
     return two ? launch_gemm<256, 2, kTF32>(a, stream) : launch_gemm<256, 1, kTF32>(a, stream);
   }
-  if (a.N > 64) return two ? launch_gemm<128, 2, kTF32>(a, stream) : launch_gemm<128, 1, kTF32>(a, stream);
+  if (a.N > 96) return two ? launch_gemm<128, 2, kTF32>(a, stream) : launch_gemm<128, 1, kTF32>(a, stream);
+  if (a.N > 64) return two ? launch_gemm<96, 2, kTF32>(a, stream) : launch_gemm<96, 1, kTF32>(a, stream);
   return launch_gemm<64, 1, kTF32>(a, stream);
 }
 
@@ -669,7 +678,8 @@ int gemm_entry(const vist3a_gemm_args* args, cudaStream_t stream) {
     V3A_REQUIRE(c.pix_stride >= 0 && c.row_stride >= 0 && c.img_stride >= 0 && (c.pix_stride * es) % 16 == 0 && (c.row_stride * es) % 16 == 0 &&
                     (c.img_stride * es) % 16 == 0, VIST3A_ERR_INVALID, "gemm(conv): pixel / row / image strides must be multiples of 16 bytes");
     V3A_REQUIRE(c.c_in % bk == 0, VIST3A_ERR_UNSUPPORTED, "gemm(conv): c_in (%d) must be a multiple of %d", c.c_in, bk);
-    V3A_REQUIRE(a.K == (int64_t)c.kh * c.kw * c.c_in, VIST3A_ERR_INVALID, "gemm(conv): K must equal kh*kw*c_in");
+    V3A_REQUIRE(c.kt >= 0 && c.kt <= 8, VIST3A_ERR_INVALID, "gemm(conv): kt must be in [0, 8]");
+    V3A_REQUIRE(a.K == (int64_t)(c.kt > 1 ? c.kt : 1) * c.kh * c.kw * c.c_in, VIST3A_ERR_INVALID, "gemm(conv): K must equal kt*kh*kw*c_in");
     const long long ho = c.h + 2 * c.pad_y - c.kh + 1, wo = c.w + 2 * c.pad_x - c.kw + 1;
     V3A_REQUIRE(ho > 0 && wo > 0 && a.M == (int64_t)c.n_img * ho * wo, VIST3A_ERR_INVALID, "gemm(conv): M must equal n_img*h_out*w_out");
   } else {

@@ -67,7 +67,8 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
         kh, kw, pad = conv["kh"], conv["kw"], conv["pad"]
         pad_x = conv.get("pad_x", pad)
         h_out, w_out = h_in + 2 * pad - kh + 1, w_in + 2 * pad_x - kw + 1
-        M, K = n_img * h_out * w_out, kh * kw * c_in
+        kt = int(conv.get("kt", 1))   # > 1: causal temporal taps over the image (frame) index, one clip per call
+        M, K = n_img * h_out * w_out, kt * kh * kw * c_in
         a2 = a
     else:
         a2 = _rows2d(a)
@@ -110,6 +111,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
     if conv is not None:
         args.conv.enabled, args.conv.kh, args.conv.kw, args.conv.pad_y, args.conv.pad_x = 1, kh, kw, pad, pad_x
         args.conv.n_img, args.conv.h, args.conv.w, args.conv.c_in = n_img, h_in, w_in, c_in
+        args.conv.kt = kt
         if "strides" in conv:
             args.conv.pix_stride, args.conv.row_stride, args.conv.img_stride = conv["strides"]
     args.post_act = ACT[post_act]
