@@ -67,9 +67,10 @@ struct GemmCfg {
   static constexpr int A_BYTES = BM * 128;
   static constexpr int B_BYTES = BN_LOCAL * 128;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 8 ? 8 : (200 * 1024) / STAGE_BYTES;
-  static constexpr int TMEM_COLS = 2 * BN <= 32 ? 32 : 2 * BN <= 64 ? 64 : 2 * BN <= 128 ? 128 : 2 * BN <= 256 ? 256 : 512;  // two accumulator stages
   static constexpr int STAGING_BYTES = 8 * 32 * 128;   // per epilogue warp: 32 rows x 128 bytes
+  static constexpr int RING_BUDGET = 227 * 1024 - 1024 /*align slack*/ - 256 /*barriers*/ - STAGING_BYTES;
+  static constexpr int STAGES = RING_BUDGET / STAGE_BYTES > 8 ? 8 : RING_BUDGET / STAGE_BYTES;
+  static constexpr int TMEM_COLS = 2 * BN <= 32 ? 32 : 2 * BN <= 64 ? 64 : 2 * BN <= 128 ? 128 : 2 * BN <= 256 ? 256 : 512;  // two accumulator stages
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + STAGING_BYTES;
   static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
   // BN = 176 (pairs only, A/B flag): 9 column tiles of a 1536-wide output fill 4 waves of 74 CTA pairs to 97 % (6 tiles of 256: 3 waves at 86 %)
