@@ -476,14 +476,32 @@ def run_ours(args):
             gather_step(0)
             ms_gather = timed(gather_step, 3) / 3
             outs.pop("all", None)
-        # end to end per prompt: H2D of the decoded views, 50 denoise steps, decode, gather, D2H of one scalar (scene scale)
+        # Wan VAE decode between the denoiser and the stitched decoder (inference_t23d.py:114-123): random-init weights of the released
+        # architecture; its 13 x 512 x 512 frames, resized to 448 x 448, are the decoder's feedforward_image in the end-to-end prompt
+        vae, ms_vae = None, None
+        if not args.no_vae:
+            from vist3a_b200.t23d import views_from_vae
+            from vist3a_b200.wan_vae import WanVAEDecoderB200, random_state_dict as vae_random_state_dict
+
+            vae = WanVAEDecoderB200.from_state_dict(vae_random_state_dict(device), None, device)
+            for i in range(2):
+                views_from_vae(vae, lat)
+            ms_vae = timed(lambda i: views_from_vae(vae, lat), kd) / kd
+
+        # end to end per prompt: H2D of text + noise, 50 denoise steps, de-normalise, VAE decode + resize (or H2D of given views), stitched
+        # decode, gather, D2H of one scalar (scene scale)
         def e2e_prompt(i):
-            img.copy_(img_h, non_blocking=True)
             eng.set_text(tc_h, tu_h)
             eng.set_noise(noise_h)
             for k in range(nsteps):
                 eng.step(k)
-            o = dec.forward_with_latent(eng.x.clamp(-4, 4) * std + mean, img)
+            lat_i = eng.x.clamp(-4, 4) * std + mean
+            if vae is not None:
+                views = views_from_vae(vae, lat_i)
+            else:
+                img.copy_(img_h, non_blocking=True)
+                views = img
+            o = dec.forward_with_latent(lat_i, views)
             if world > 1:
                 all_gather_gaussians(o.gaussians)
             o.infos["scene_scale"].cpu()
@@ -493,7 +511,9 @@ def run_ours(args):
                  "decoder_gaussians_per_sec": world * B * N_GAUSS / (ms_dec / 1e3), "decoder_ms": ms_dec,
                  "decoder_tflops": B * DECODER_TFLOP / (ms_dec / 1e3), "gather_ms": ms_gather,
                  "e2e_gaussians_per_sec": world * B * N_GAUSS / (ms_prompt / 1e3), "e2e_prompt_ms": ms_prompt,
-                 "e2e_what": "one prompt per GPU: H2D views, text projections, 50 CFG denoise steps, de-normalise, decode" +
+                 "vae_decode_ms": ms_vae, "vae_what": None if vae is None else "WanVAEDecoderB200: latent [1,16,T,64,64] -> frames 512x512 (29.5 TFLOP at 13 views) + resize to 448x448",
+                 "e2e_what": "one prompt per GPU: H2D text + noise, text projections, 50 CFG denoise steps, de-normalise, " +
+                             ("Wan VAE decode + 448 resize, " if vae is not None else "H2D views, ") + "stitched decode" +
                              (", NCCL all-gather of all ranks' Gaussians" if world > 1 else "") + ", D2H of scene_scale",
                  "decoder_launches_per_forward": dec_launches // kd,
                  "latent": "denoised latent of the random-weight DiT, clamped to [-4, 4] before de-normalisation (real VAE latents are O(1))",
@@ -622,6 +642,7 @@ def main():
     ap.add_argument("--prompts-per-gpu", type=int, default=1, help="prompts batched per GPU (BASELINE configs[4] sweep: 1/2/4/8)")
     ap.add_argument("--no-decoder", action="store_true", help="skip the Gaussians/s leg (decoder + gather)")
     ap.add_argument("--decoder-iters", type=int, default=3)
+    ap.add_argument("--no-vae", action="store_true", help="end-to-end prompt without the Wan VAE decode (views copied from the host instead)")
     ap.add_argument("--model", default="1.3b", choices=["1.3b", "14b"], help="Wan DiT size (BASELINE configs[1-2] / configs[3])")
     ap.add_argument("--views", type=int, default=13, choices=[13, 21], help="views per prompt (13: latent T=4, L=4096; 21: T=6, L=6144)")
     ap.add_argument("--voxelize", action="store_true", help="decoder with voxelised Gaussian fusion (voxel_size 0.002)")

@@ -34,7 +34,7 @@ extern "C" {
 #define VIST3A_DTYPE_F32 1
 
 const char* vist3a_last_error(void);
-int vist3a_abi_version(void); /* 5 */
+int vist3a_abi_version(void); /* 6 */
 /* number of kernels this library has launched from the calling process (all threads) */
 int64_t vist3a_launch_count(void);
 /* Programmatic dependent launch (PDL) of the hot kernels (GEMM, attention, LayerNorm, RMSNorm+RoPE, row_rinv): each is launched
@@ -382,6 +382,36 @@ int vist3a_gs_project(const float* means, const float* covariances, const float*
 int64_t vist3a_gs_rasterize_workspace_bytes(int64_t n_isect, int64_t W, int64_t H);
 int vist3a_gs_rasterize(const void* project_workspace, int64_t n_gaussians, int64_t n_isect, int64_t W, int64_t H, const float* background,
                         void* workspace, int64_t workspace_bytes, float* rgb, float* depth, float* alpha, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Wan-2.1 VAE decode (pipe.vae.decode between the denoiser and the stitched decoder, inference_t23d.py:104-114; arithmetic vendored at
+ * utils/wan_utils.py:96-1180).  Activations are NDHWC bf16, one clip [T, H, W, ld]; every convolution is vist3a_gemm in conv mode
+ * (`kt` temporal taps = WanCausalConv3d :96-147).  These are the HBM-bound passes between the convolutions.
+ * ------------------------------------------------------------------------------------------ */
+/* y[r, c] = silu?(x[r, c] / max(||x[r, :C]||_2, 1e-12) * sqrt(C) * gamma[c]), c < C; y[r, C:ldy] = 0 (zero padding channels of the next
+ * convolution's operand).  replaces: WanRMS_norm (:150-184, channel_first images) + nn.SiLU of WanResidualBlock (:366-372, :395-399) and
+ * the un-activated norm of WanAttentionBlock (:449). */
+int vist3a_vae_rmsnorm(const void* x, int64_t ldx, const float* gamma, void* y, int64_t ldy, int64_t rows, int64_t C, int32_t silu, void* stream);
+/* p[r, :] = softmax(scale * s[r, :]) in bf16 from fp32 logits.  replaces: the softmax inside F.scaled_dot_product_attention of
+ * WanAttentionBlock (:463-467: one head of width C over the H*W positions of a frame). */
+int vist3a_softmax_rows(const float* s, void* p, int64_t rows, int64_t L, float scale, void* stream);
+/* out[2t + half, p, :] = y[t, p, half*C : (half+1)*C]  (y [T, P, 2C] -> out [2T, P, C], bf16).  replaces: the channel-halves-to-time
+ * interleave of WanResample "upsample3d" (:304-306). */
+int vist3a_time_interleave(const void* y, void* out, int64_t T, int64_t P, int64_t C, void* stream);
+/* out[c, r] = in[r, c]  (bf16 [R, C] with row stride ld_in -> [C, R]): V^T operand of the mid-block attention's P V GEMM */
+int vist3a_transpose_bf16(const void* in, int64_t ld_in, void* out, int64_t R, int64_t C, void* stream);
+/* depth-to-space (k = 2) of the parity-decomposed up-sampling convolution: in [n*h*w, 4*C] (col = (py*2 + px)*C + c) -> NHWC bf16
+ * [n, 2h, 2w, ldo] (channels [0, C)).  replaces: WanUpsample (nearest-exact 2x) + Conv2d 3x3 output layout (:226-238). */
+int vist3a_depth_to_space2_bf16(const void* in, void* out, int64_t n_img, int64_t h, int64_t w, int64_t C, int64_t ldo, void* stream);
+/* latent [C, T*h*w] (fp32 or bf16) -> NDHWC bf16 [T*h*w, ld], channels [C, ld) zero: operand of post_quant_conv / decoder.conv_in */
+int vist3a_latent_to_ndhwc(const void* z, int32_t z_dtype, void* out, int64_t C, int64_t THW, int64_t ld, void* stream);
+/* conv_out result [T*H*W, ld] fp32 (channels 0..2) -> frames [3, T*H*W] fp32 clamped to [-1, 1] (AutoencoderKLWan._decode :1115) */
+int vist3a_vae_frames_out(const float* y, int64_t ld, float* out, int64_t THW, void* stream);
+
+/* planar bilinear resize, half-pixel centres: in [planes, h_in, w_in] fp32 -> out [planes, h_out, w_out].  replaces: F.interpolate(samples,
+ * (T, 448, 448), mode="trilinear", align_corners=False) of the decoded frames (inference_t23d.py:116-123; the frame count is kept, so the
+ * temporal weights are the identity). */
+int vist3a_resize_planes(const float* in, float* out, int64_t planes, int64_t h_in, int64_t w_in, int64_t h_out, int64_t w_out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -34,7 +34,7 @@ def test_library_exports_every_declared_symbol(lib):
     missing = [n for n in names if not hasattr(h, n)]
     assert not missing, missing
     assert sorted(lib.EXPORTS) == names            # the Python binding lists exactly the header's entry points
-    assert h.vist3a_abi_version() == 5
+    assert h.vist3a_abi_version() == 6
     assert h.vist3a_launch_count() == 0            # nothing was launched by loading / symbol lookup
 
 

@@ -1,0 +1,101 @@
+"""GPU parity of the Wan-2.1 VAE decode (vist3a_b200.wan_vae.WanVAEDecoderB200, every op through the C ABI) against the pinned fp32 oracle
+(oracle/wan_vae_ref.py, itself checked against the reference's own modules and chunked decode loop, tests/test_oracle_vae.py) and
+against the golden vectors the REAL reference produced (tests/golden/wan_vae_tiny.pt).
+
+Stated tolerance: the engine keeps bf16 activations between layers and bf16 tensor-core operands with fp32 accumulation (the reference
+runs its VAE in fp16/bf16 too: inference_t23d.py:73 loads the pipeline in half precision); the oracle is fp32.  The decoder is ~30
+convolutions deep with an RMS norm in front of each, so rounding does not accumulate multiplicatively: bound rel-L2 < 2e-2 on the frames
+before clamping effects, max |err| < 0.1 on outputs in [-1, 1] (measured values are printed and recorded in DESIGN.md §2).
+"""
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "wan_vae_tiny.pt")
+
+
+def _rel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def _engine(sd, cfg):
+    from vist3a_b200.wan_vae import WanVAEDecoderB200
+
+    return WanVAEDecoderB200.from_state_dict(sd, dict(base_dim=cfg.base_dim, z_dim=cfg.z_dim, dim_mult=cfg.dim_mult, num_res_blocks=cfg.num_res_blocks,
+                                                      temporal_downsample=cfg.temporal_downsample), device="cuda:0")
+
+
+def test_tiny_vae_decode_matches_reference_golden():
+    from oracle import wan_vae_ref as V
+    from vist3a_b200 import _lib
+
+    g = torch.load(GOLDEN, weights_only=False)
+    cfg = V.TINY_VAE
+    for name, c in g["cases"].items():
+        sd = V.init_state_dict(cfg, seed=c["weight_seed"])
+        n0 = _lib.launch_count()
+        m = _engine(sd, cfg)
+        out = m.decode(c["latent"].cuda(), return_dict=False)[0]
+        torch.cuda.synchronize()
+        assert _lib.launch_count() - n0 > 80
+        want = c["decoded"]
+        assert out.shape == want.shape and out.dtype == torch.float32
+        rel, mx = _rel(out, want), float((out.cpu() - want).abs().max())
+        print(f"tiny VAE {name}: rel-L2 {rel:.3e}, max |err| {mx:.3e}")
+        assert rel < 2e-2 and mx < 0.1
+
+
+@pytest.mark.parametrize("frames,hw", [(1, 8), (2, 8), (3, 16)])
+def test_released_width_vae_decode_matches_oracle(frames, hw):
+    """Wan-2.1 widths (96 / 192 / 384 channels, z = 16): the 96-channel layers stored 128 wide, 192-wide tiles, temporal taps, parity-decomposed
+    up-sampling convolutions, mid-block attention; latent [1, 16, frames, hw, hw] -> [1, 3, 1 + 4 (frames - 1), 8 hw, 8 hw]"""
+    from oracle import wan_vae_ref as V
+
+    cfg = V.WAN_VAE
+    sd = V.init_state_dict(cfg, seed=3)
+    gen = torch.Generator().manual_seed(frames * 100 + hw)
+    z = torch.randn(1, cfg.z_dim, frames, hw, hw, generator=gen)
+    want = V.decode(sd, cfg, z)
+    out = _engine(sd, cfg).decode(z.cuda(), return_dict=False)[0]
+    assert out.shape == want.shape == (1, 3, 1 + 4 * (frames - 1), 8 * hw, 8 * hw)
+    rel, mx = _rel(out, want), float((out.cpu() - want).abs().max())
+    print(f"Wan VAE widths, latent {frames}x{hw}x{hw}: rel-L2 {rel:.3e}, max |err| {mx:.3e}")
+    assert bool(torch.isfinite(out).all()) and rel < 2e-2 and mx < 0.1
+
+
+def test_vae_decode_baseline_size_properties():
+    """BASELINE clip: latent [1, 16, 4, 64, 64] -> 13 frames x 512 x 512.  Size-independent properties: range, causality (frame t depends only
+    on latent frames <= ceil(t / 4)), batch independence; and the oracle on a crop-equivalent small problem is covered above."""
+    from oracle import wan_vae_ref as V
+
+    cfg = V.WAN_VAE
+    sd = V.init_state_dict(cfg, seed=3)
+    m = _engine(sd, cfg)
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    z = torch.randn(1, 16, 4, 64, 64, device="cuda", generator=gen)
+    out = m.decode(z, return_dict=False)[0]
+    assert out.shape == (1, 3, 13, 512, 512) and bool(torch.isfinite(out).all())
+    assert float(out.min()) >= -1.0 and float(out.max()) <= 1.0
+    z2 = z.clone()
+    z2[:, :, 3] = torch.randn(1, 16, 64, 64, device="cuda", generator=gen)      # change the LAST latent frame only
+    out2 = m.decode(z2, return_dict=False)[0]
+    assert torch.equal(out[:, :, :9], out2[:, :, :9])                              # frames 0..8 come from latent frames 0..2 (causal convolutions)
+    assert not torch.equal(out[:, :, 9:], out2[:, :, 9:])
+    both = m.decode(torch.cat([z, z2], 0), return_dict=False)[0]
+    assert torch.equal(both[0], out[0]) and torch.equal(both[1], out2[0])
+
+
+@pytest.mark.parametrize("shape,size", [((1, 3, 5, 64, 64), 56), ((2, 3, 2, 40, 72), 448), ((1, 3, 3, 512, 512), 448)])
+def test_resize_planes_matches_trilinear_interpolate(shape, size):
+    """inference_t23d.py:116-123: F.interpolate(samples, (T, 448, 448), mode="trilinear", align_corners=False)"""
+    from vist3a_b200 import ops
+
+    g = torch.Generator(device="cuda").manual_seed(sum(shape))
+    x = torch.rand(shape, device="cuda", generator=g) * 2 - 1
+    want = torch.nn.functional.interpolate(x, (shape[2], size, size), mode="trilinear", align_corners=False)
+    got = ops.resize_planes(x, size, size)
+    assert got.shape == want.shape
+    assert float((got - want).abs().max()) < 2e-6

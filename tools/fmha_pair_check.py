@@ -30,7 +30,7 @@ def timeit(fn, iters, flush):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--variants", default="0,1,2,3,4")
+    ap.add_argument("--variants", default="0,1,2,3,4,5,6,7")
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--no-time", action="store_true")
     a = ap.parse_args()

@@ -54,6 +54,14 @@ EXPORTS = (
     "vist3a_voxel_fusion",
     "vist3a_gs_project",
     "vist3a_gs_rasterize",
+    "vist3a_vae_rmsnorm",
+    "vist3a_softmax_rows",
+    "vist3a_time_interleave",
+    "vist3a_transpose_bf16",
+    "vist3a_depth_to_space2_bf16",
+    "vist3a_latent_to_ndhwc",
+    "vist3a_vae_frames_out",
+    "vist3a_resize_planes",
     "vist3a_voxel_fusion_workspace_bytes",
     "vist3a_gs_project_workspace_bytes",
     "vist3a_gs_rasterize_workspace_bytes",
@@ -200,6 +208,14 @@ def load(build_if_missing: bool = False) -> C.CDLL:
     fp = C.POINTER(f32)
     lib.vist3a_gs_project.argtypes = [vp, vp, vp, vp, i64, i32, i64, fp, fp, i64, i64, f32, f32, f32, f32, vp, i64, vp, vp]
     lib.vist3a_gs_rasterize.argtypes = [vp, i64, i64, i64, i64, fp, vp, i64, vp, vp, vp, vp]
+    lib.vist3a_vae_rmsnorm.argtypes = [vp, i64, vp, vp, i64, i64, i64, i32, vp]
+    lib.vist3a_softmax_rows.argtypes = [vp, vp, i64, i64, f32, vp]
+    lib.vist3a_time_interleave.argtypes = [vp, vp, i64, i64, i64, vp]
+    lib.vist3a_transpose_bf16.argtypes = [vp, i64, vp, i64, i64, vp]
+    lib.vist3a_depth_to_space2_bf16.argtypes = [vp, vp, i64, i64, i64, i64, i64, vp]
+    lib.vist3a_latent_to_ndhwc.argtypes = [vp, i32, vp, i64, i64, i64, vp]
+    lib.vist3a_vae_frames_out.argtypes = [vp, i64, vp, i64, vp]
+    lib.vist3a_resize_planes.argtypes = [vp, vp, i64, i64, i64, i64, i64, vp]
     _lib = lib
     return lib
 

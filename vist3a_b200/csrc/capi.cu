@@ -54,6 +54,14 @@ int unpatchify_entry(const void*, int, long long, void*, int, long long, long lo
                      cudaStream_t);
 int cfg_combine_entry(const void*, const void*, int, float, float*, long long, cudaStream_t);
 int axpby_entry(float*, int, const float* const*, const float*, long long, cudaStream_t);
+int vae_rmsnorm_entry(const void*, long long, const float*, void*, long long, long long, long long, int, cudaStream_t);
+int softmax_rows_entry(const float*, void*, long long, long long, float, cudaStream_t);
+int time_interleave_entry(const void*, void*, long long, long long, long long, cudaStream_t);
+int transpose_bf16_entry(const void*, long long, void*, long long, long long, cudaStream_t);
+int depth_to_space2_bf16_entry(const void*, void*, long long, long long, long long, long long, long long, cudaStream_t);
+int latent_to_ndhwc_entry(const void*, int, void*, long long, long long, long long, cudaStream_t);
+int vae_frames_out_entry(const float*, long long, float*, long long, cudaStream_t);
+int resize_planes_entry(const float*, float*, long long, long long, long long, long long, long long, cudaStream_t);
 
 char* last_error_buf() {
   static thread_local char buf[512] = {0};
@@ -165,12 +173,28 @@ using namespace v3a;
 extern "C" {
 
 const char* vist3a_last_error(void) { return last_error_buf(); }
-int vist3a_abi_version(void) { return 5; }
+int vist3a_abi_version(void) { return 6; }
 int64_t vist3a_launch_count(void) { return (int64_t)launch_counter().load(); }
 int vist3a_set_pdl(int32_t enable) { return set_pdl(enable); }
 
 int vist3a_gemm(const vist3a_gemm_args* args, void* stream) { return gemm_entry(args, ST(stream)); }
 int vist3a_fmha_fwd(const vist3a_fmha_args* args, void* stream) { return fmha_entry(args, ST(stream)); }
+int vist3a_vae_rmsnorm(const void* x, int64_t ldx, const float* gamma, void* y, int64_t ldy, int64_t rows, int64_t C, int32_t silu, void* stream) {
+  return vae_rmsnorm_entry(x, ldx, gamma, y, ldy, rows, C, silu, ST(stream));
+}
+int vist3a_softmax_rows(const float* s, void* p, int64_t rows, int64_t L, float scale, void* stream) { return softmax_rows_entry(s, p, rows, L, scale, ST(stream)); }
+int vist3a_time_interleave(const void* y, void* out, int64_t T, int64_t P, int64_t C, void* stream) { return time_interleave_entry(y, out, T, P, C, ST(stream)); }
+int vist3a_transpose_bf16(const void* in, int64_t ld_in, void* out, int64_t R, int64_t C, void* stream) { return transpose_bf16_entry(in, ld_in, out, R, C, ST(stream)); }
+int vist3a_depth_to_space2_bf16(const void* in, void* out, int64_t n_img, int64_t h, int64_t w, int64_t C, int64_t ldo, void* stream) {
+  return depth_to_space2_bf16_entry(in, out, n_img, h, w, C, ldo, ST(stream));
+}
+int vist3a_latent_to_ndhwc(const void* z, int32_t z_dtype, void* out, int64_t C, int64_t THW, int64_t ld, void* stream) {
+  return latent_to_ndhwc_entry(z, z_dtype, out, C, THW, ld, ST(stream));
+}
+int vist3a_vae_frames_out(const float* y, int64_t ld, float* out, int64_t THW, void* stream) { return vae_frames_out_entry(y, ld, out, THW, ST(stream)); }
+int vist3a_resize_planes(const float* in, float* out, int64_t planes, int64_t h_in, int64_t w_in, int64_t h_out, int64_t w_out, void* stream) {
+  return resize_planes_entry(in, out, planes, h_in, w_in, h_out, w_out, ST(stream));
+}
 
 int vist3a_layernorm(const void* x, int32_t x_dtype, int64_t ldx, void* out, int32_t out_dtype, int64_t ldo,
                      int64_t rows, int64_t dim, int64_t rows_per_batch, const float* mul, int64_t mul_bstride,

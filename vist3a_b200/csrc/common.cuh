@@ -80,6 +80,16 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t cta) 
       "r"(cta)
       : "memory");
 }
+// remote arrive with CTA-scope release (what CUTLASS' ClusterBarrier::arrive(cta_id) issues): enough when the data handed over lives in tensor
+// memory and is ordered by tcgen05 fences; mbar_arrive_cluster's release.cluster compiles to MEMBAR.ALL.GPU + CCTL.IVALL + ERRBAR
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}" ::"r"(bar),
+      "r"(cta)
+      : "memory");
+}
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(

@@ -16,9 +16,14 @@
 //   warps 4..     softmax, SPLIT threads per query row (thread = TMEM lane x column slice): tcgen05.ld S, row max (slices exchange through
 //                 shared memory + a named barrier), lazy rescale of O, exp2, bf16 P -> tcgen05.st over the S buffer it came from, arrive on
 //                 the LEADER's p_full barrier (remote arrive from the peer CTA)
-// TMEM map per CTA (512 columns): S0 | P0 [0,128)   S1 | P1 [128,256)   O [256,384).  S is double-buffered: Q K(j+2)^T is queued behind
-// P(j) V(j) in the in-order tensor pipe (it overwrites the buffer P(j) lives in), so the next score tile is ready when the softmax warps
-// finish the current one and the tensor pipe never waits for a "buffer free" handshake.
+// Two shapes of the same kernel (template QT = query tiles per CTA):
+//   QT = 1   one 128-row tile per CTA, S double-buffered.  TMEM: S0 | P0 [0,128)  S1 | P1 [128,256)  O [256,384).  Q K(j+2)^T is queued behind
+//            P(j) V(j) in the in-order tensor pipe (it overwrites the buffer P(j) lives in).  All softmax warps of the CTA work on the same score
+//            tile in lockstep, so the MUFU idles while they load / reduce / store (measured: 36 % tensor pipe) -- kept for A/B.
+//   QT = 2   two 128-row tiles per CTA (512 query rows per cluster), each with its own softmax warps, S single-buffered per tile
+//            (TMEM per tile: S | P [0,128)  O [128,256)): while tile A's warps exponentiate, the tensor pipe runs tile B's P V and next Q K^T
+//            and tile B's warps are in their load / max / store phases -- the two tiles keep MUFU and tensor pipe busy alternately, and every
+//            K / V tile is used for 512 query rows.
 #include "common.cuh"
 #include "fmha_math.cuh"
 #include "host_util.cuh"
@@ -29,50 +34,66 @@ struct FmhaPairParams {
   int len_q, len_kv;
   float scale_log2;        // scale * log2(e)
   const float* row_scale;  // optional per-(batch, query row) positive factor on the logits
+  long long* trace;        // debug (v3a_debug_fmha_pair_trace): clock64 stamps of CTA (0,0,0), normally null
 };
 
-template <int SPLIT_, int POLY_>
+// debug hook (tools/fmha_pair_trace.py), off unless armed: [step][tile][8] stamps of the leader CTA of cluster 0:
+//   0 MMA warp sees P ready   1 MMA warp has issued P V + next Q K^T   2 softmax sees S ready   3 S in registers   4 row max exchanged
+//   5 exponentials done       6 P stored + arrived
+static std::atomic<long long*> g_pair_trace{nullptr};
+extern "C" void v3a_debug_fmha_pair_trace(void* buf) { g_pair_trace.store(reinterpret_cast<long long*>(buf)); }
+#define PAIR_TRACE(j, i, slot)                                                                         \
+  do {                                                                                                 \
+    if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (j) < 64) p.trace[((j) * 2 + (i)) * 8 + (slot)] = clock64(); \
+  } while (0)
+
+template <int QT_, int SPLIT_, int POLY_>
 struct FmhaPairCfg {
   static constexpr int D = 128, BQ = 128, BKV = 128;
+  static constexpr int QT = QT_;                       // 128-row query tiles per CTA
+  static constexpr int NSB = QT == 1 ? 2 : 1;          // score buffers per tile
   static constexpr int SPLIT = SPLIT_;                 // softmax threads per query row
   static constexpr int POLY = POLY_;                   // of every 8 column pairs, this many take exp2 on the FMA pipe
   static constexpr int HC = BKV / SPLIT;               // score columns per softmax thread and step
   static constexpr int OC = D / SPLIT;                 // O columns per softmax thread (rescale, epilogue)
-  static constexpr int THREADS = 128 + 128 * SPLIT;
+  static constexpr int THREADS = 128 + QT * 128 * SPLIT;
   static constexpr int Q_SLAB_BYTES = BQ * 128;        // 64 head-dim columns (128 B) x 128 rows
   static constexpr int Q_TILE_BYTES = 2 * Q_SLAB_BYTES;
   static constexpr int K_SLAB_BYTES = (BKV / 2) * 128; // this CTA's 64 keys x 64 head-dim columns
   static constexpr int K_HALF_BYTES = 2 * K_SLAB_BYTES;  // 16 KB
   static constexpr int V_HALF_BYTES = BKV * 128;       // 128 keys x this CTA's 64 head-dim columns = 16 KB
   static constexpr int ST = 4;                         // ring stages of K and of V
-  static constexpr int NBARS = 1 + 4 * ST + 6;         // q_full | k_full, k_empty, v_full, v_empty | s_full[2], p_full[2], pv_done[2]
-  static constexpr int XCH_BYTES = 2 * SPLIT * 128 * 4;  // [step parity][slice][row] fp32
-  static constexpr int SMEM_BYTES = Q_TILE_BYTES + ST * (K_HALF_BYTES + V_HALF_BYTES) + 1024 + 8 * NBARS + 16 + XCH_BYTES;
-  static constexpr uint32_t TM_S = 0, S_STRIDE = 128, TM_O = 256;
-  static_assert(SPLIT == 2 || SPLIT == 4, "SPLIT");
+  static constexpr int NH = SPLIT == 1 ? 2 : 1;        // P(j) is handed to the MMA warp in NH key halves (one thread per row: after 64 keys each)
+  static constexpr int NBARS = 1 + 4 * ST + 8 * QT;    // q_full | k_full, k_empty, v_full, v_empty | per tile: s_full[2], p_full[2][2], pv_done[2]
+  static constexpr int XCH_BYTES = 2 * QT * SPLIT * 128 * 4;  // [step parity][tile][slice][row] fp32
+  static constexpr int SMEM_BYTES = QT * Q_TILE_BYTES + ST * (K_HALF_BYTES + V_HALF_BYTES) + 1024 + 8 * NBARS + 16 + XCH_BYTES;
+  static constexpr uint32_t TILE_COLS = 256, TM_S = 0, S_STRIDE = 128, TM_O = NSB * 128;
+  static_assert(SPLIT == 1 || SPLIT == 2 || SPLIT == 4, "SPLIT");
+  static_assert(QT == 1 || (QT == 2 && SPLIT <= 2), "two tiles per CTA run one or two threads per row (384 / 640 threads)");
   static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 };
 
-template <int SPLIT_, int POLY_>
-__global__ void __launch_bounds__(128 + 128 * SPLIT_, 1)
+template <int QT_, int SPLIT_, int POLY_>
+__global__ void __launch_bounds__(128 + QT_ * 128 * SPLIT_, 1)
 fmha_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                  const __grid_constant__ CUtensorMap tmO, const FmhaPairParams p) {
-  using Cfg = FmhaPairCfg<SPLIT_, POLY_>;
-  constexpr int SPLIT = Cfg::SPLIT, HC = Cfg::HC, OC = Cfg::OC, ST = Cfg::ST, BKV = Cfg::BKV, D = Cfg::D;
+  using Cfg = FmhaPairCfg<QT_, SPLIT_, POLY_>;
+  constexpr int QT = Cfg::QT, NSB = Cfg::NSB, NH = Cfg::NH, SPLIT = Cfg::SPLIT, HC = Cfg::HC, OC = Cfg::OC, ST = Cfg::ST, BKV = Cfg::BKV, D = Cfg::D;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t smem_q = smem_base;
-  auto smem_k = [&](int s) { return smem_base + Cfg::Q_TILE_BYTES + Cfg::K_HALF_BYTES * s; };
-  auto smem_v = [&](int s) { return smem_base + Cfg::Q_TILE_BYTES + Cfg::K_HALF_BYTES * ST + Cfg::V_HALF_BYTES * s; };
-  const uint32_t bar_base = smem_base + Cfg::Q_TILE_BYTES + ST * (Cfg::K_HALF_BYTES + Cfg::V_HALF_BYTES);
+  auto smem_q = [&](int i) { return smem_base + Cfg::Q_TILE_BYTES * i; };
+  auto smem_k = [&](int s) { return smem_base + QT * Cfg::Q_TILE_BYTES + Cfg::K_HALF_BYTES * s; };
+  auto smem_v = [&](int s) { return smem_base + QT * Cfg::Q_TILE_BYTES + Cfg::K_HALF_BYTES * ST + Cfg::V_HALF_BYTES * s; };
+  const uint32_t bar_base = smem_base + QT * Cfg::Q_TILE_BYTES + ST * (Cfg::K_HALF_BYTES + Cfg::V_HALF_BYTES);
   const uint32_t q_full = bar_base;
   auto k_full = [&](int s) { return bar_base + 8u * (1 + s); };
   auto k_empty = [&](int s) { return bar_base + 8u * (1 + ST + s); };
   auto v_full = [&](int s) { return bar_base + 8u * (1 + 2 * ST + s); };
   auto v_empty = [&](int s) { return bar_base + 8u * (1 + 3 * ST + s); };
-  auto s_full = [&](int b) { return bar_base + 8u * (1 + 4 * ST + b); };
-  auto p_full = [&](int b) { return bar_base + 8u * (1 + 4 * ST + 2 + b); };
-  auto pv_done = [&](int b) { return bar_base + 8u * (1 + 4 * ST + 4 + b); };
+  // per tile i; every barrier exists twice (b = step parity): a waiter is never two completions behind the barrier it polls
+  auto s_full = [&](int i, int b) { return bar_base + 8u * (1 + 4 * ST + 8 * i + b); };
+  auto p_full = [&](int i, int b, int hh) { return bar_base + 8u * (1 + 4 * ST + 8 * i + 2 + 2 * b + hh); };
+  auto pv_done = [&](int i, int b) { return bar_base + 8u * (1 + 4 * ST + 8 * i + 6 + b); };
   const uint32_t tmem_slot = bar_base + 8u * Cfg::NBARS;
   const uint32_t xch_base = tmem_slot + 16u;
 
@@ -80,7 +101,8 @@ fmha_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   const uint32_t lane = lane_id();
   const uint32_t rank = cluster_ctarank();          // 0 = leader
   const bool leader = rank == 0;
-  const int q0 = (int)(blockIdx.x >> 1) * (2 * Cfg::BQ) + (int)rank * Cfg::BQ;   // first query row of this CTA
+  // the cluster owns 256 * QT consecutive query rows: tile i of the pair = rows [256 i, 256 i + 256), this CTA's half = [128 rank, +128)
+  auto q0_of = [&](int i) { return (int)(blockIdx.x >> 1) * (2 * QT * Cfg::BQ) + (2 * i + (int)rank) * Cfg::BQ; };
   const int head = blockIdx.y, batch = blockIdx.z;
   const int n_kv = (p.len_kv + BKV - 1) / BKV;
 
@@ -98,10 +120,12 @@ fmha_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       mbar_init(v_full(s), 1);
       mbar_init(v_empty(s), 1);
     }
-    for (int b = 0; b < 2; ++b) {
-      mbar_init(s_full(b), 1);
-      mbar_init(p_full(b), 2 * 4 * SPLIT);   // one arrival per softmax warp of BOTH CTAs (only the leader's copy is used)
-      mbar_init(pv_done(b), 1);
+    for (int i = 0; i < QT; ++i) {
+      for (int b = 0; b < 2; ++b) {
+        mbar_init(s_full(i, b), 1);
+        for (int hh = 0; hh < 2; ++hh) mbar_init(p_full(i, b, hh), 2 * 4 * SPLIT);   // one arrival per softmax warp of the tile in BOTH CTAs (leader's copy)
+        mbar_init(pv_done(i, b), 1);
+      }
     }
     fence_barrier_init();
   }
@@ -117,9 +141,12 @@ fmha_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   if (warp == 0) {
     // ------------------------------ TMA producer (warp-uniform control flow, one elected lane issues) ------------------------------
     if (elect_one()) {
-      if (leader) mbar_expect_tx(q_full, 2u * Cfg::Q_TILE_BYTES);
+      if (leader) mbar_expect_tx(q_full, 2u * QT * Cfg::Q_TILE_BYTES);
 #pragma unroll
-      for (int sl = 0; sl < 2; ++sl) tma_load_4d_2sm(smem_q + sl * Cfg::Q_SLAB_BYTES, &tmQ, q_full, sl * 64, head, q0, batch);
+      for (int i = 0; i < QT; ++i) {
+#pragma unroll
+        for (int sl = 0; sl < 2; ++sl) tma_load_4d_2sm(smem_q(i) + sl * Cfg::Q_SLAB_BYTES, &tmQ, q_full, sl * 64, head, q0_of(i), batch);
+      }
     }
     __syncwarp();
     int s = 0;
@@ -148,12 +175,13 @@ fmha_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       constexpr uint32_t idesc_pv = make_idesc(kFmtBF16, 256, D, 0, 1);   // B (V) is MN-major
       int qs = 0, vs = 0;
       uint32_t qph = 0, vph = 0;
-      auto issue_qk = [&](int j) {
-        mbar_wait(k_full(qs), qph);
+      // S_i(j) = Q_i K(j)^T for tile i; all tiles use key tile j back to back: the first waits for it, the last releases its ring slot
+      auto issue_qk = [&](int i, int j) {
+        if (i == 0) mbar_wait(k_full(qs), qph);
         tc_fence_after();
         if (elect_one()) {
-          const uint32_t d_tmem = tmem_base + Cfg::TM_S + (uint32_t)(j & 1) * Cfg::S_STRIDE;
-          const uint64_t qdesc = make_smem_desc_sw128(smem_q, 1024, 0);
+          const uint32_t d_tmem = tmem_base + (uint32_t)i * Cfg::TILE_COLS + Cfg::TM_S + (uint32_t)(j % NSB) * Cfg::S_STRIDE;
+          const uint64_t qdesc = make_smem_desc_sw128(smem_q(i), 1024, 0);
           const uint64_t kdesc = make_smem_desc_sw128(smem_k(qs), 1024, 0);
 #pragma unroll
           for (int kk = 0; kk < D / 16; ++kk) {
@@ -162,61 +190,82 @@ fmha_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             const uint64_t bo = (uint64_t)(((kk >> 2) * Cfg::K_SLAB_BYTES + (kk & 3) * 32) >> 4);
             umma_f16_ss<2>(d_tmem, qdesc + ao, kdesc + bo, idesc_qk, kk ? 1u : 0u);
           }
-          umma_commit_2sm_mc(s_full(j & 1), 3);
-          umma_commit_2sm_mc(k_empty(qs), 3);
+          umma_commit_2sm_mc(s_full(i, j & 1), 3);
+          if (i == QT - 1) umma_commit_2sm_mc(k_empty(qs), 3);
         }
         __syncwarp();
-        if (++qs == ST) { qs = 0; qph ^= 1u; }
+        if (i == QT - 1) { if (++qs == ST) { qs = 0; qph ^= 1u; } }
       };
-      auto issue_pv = [&](int j) {
-        mbar_wait(v_full(vs), vph);
+      auto issue_pv = [&](int i, int j, int hh) {   // hh: key half of P(j) (NH == 1: the whole tile)
+        if (i == 0 && hh == 0) mbar_wait(v_full(vs), vph);
         tc_fence_after();
         if (elect_one()) {
-          const uint32_t p_tmem = tmem_base + Cfg::TM_S + (uint32_t)(j & 1) * Cfg::S_STRIDE;
+          const uint32_t t_base = tmem_base + (uint32_t)i * Cfg::TILE_COLS;
+          const uint32_t p_tmem = t_base + Cfg::TM_S + (uint32_t)(j % NSB) * Cfg::S_STRIDE;
           // this CTA's V half: key rows at a 128 B pitch (K dimension of the MMA), 64 head-dim columns = one swizzle row (MN dimension)
           const uint64_t vdesc = make_smem_desc_sw128(smem_v(vs), 1024, Cfg::V_HALF_BYTES);
+          constexpr int KH = BKV / 16 / NH;
 #pragma unroll
-          for (int kk = 0; kk < BKV / 16; ++kk)
-            umma_f16_ts_2sm(tmem_base + Cfg::TM_O, p_tmem + (uint32_t)(kk * 8), vdesc + (uint64_t)((kk * 2048) >> 4), idesc_pv, (j | kk) ? 1u : 0u);
-          umma_commit_2sm_mc(pv_done(j & 1), 3);
-          umma_commit_2sm_mc(v_empty(vs), 3);
+          for (int k2 = 0; k2 < KH; ++k2) {
+            const int kk = hh * KH + k2;
+            umma_f16_ts_2sm(t_base + Cfg::TM_O, p_tmem + (uint32_t)(kk * 8), vdesc + (uint64_t)((kk * 2048) >> 4), idesc_pv, (j | kk) ? 1u : 0u);
+          }
+          if (hh == NH - 1) {
+            umma_commit_2sm_mc(pv_done(i, j & 1), 3);
+            if (i == QT - 1) umma_commit_2sm_mc(v_empty(vs), 3);
+          }
         }
         __syncwarp();
-        if (++vs == ST) { vs = 0; vph ^= 1u; }
+        if (i == QT - 1 && hh == NH - 1) { if (++vs == ST) { vs = 0; vph ^= 1u; } }
       };
       mbar_wait(q_full, 0);
-      issue_qk(0);
-      if (n_kv > 1) issue_qk(1);
+      for (int j = 0; j < NSB && j < n_kv; ++j) {
+#pragma unroll
+        for (int i = 0; i < QT; ++i) issue_qk(i, j);
+      }
       for (int j = 0; j < n_kv; ++j) {
-        mbar_wait_cluster(p_full(j & 1), (uint32_t)(j >> 1) & 1u);   // P(j) of both CTAs is in tensor memory
-        tc_fence_after();
-        issue_pv(j);
-        if (j + 2 < n_kv) issue_qk(j + 2);   // overwrites S(j) | P(j): ordered behind P(j) V(j) by the in-order tensor pipe
+#pragma unroll
+        for (int i = 0; i < QT; ++i) {
+#pragma unroll
+          for (int hh = 0; hh < NH; ++hh) {
+            mbar_wait(p_full(i, j & 1, hh), (uint32_t)(j >> 1) & 1u);   // (this half of) P_i(j) of both CTAs is in tensor memory
+            tc_fence_after();
+            if (lane == 0 && hh == 0) PAIR_TRACE(j, i, 0);
+            issue_pv(i, j, hh);
+          }
+          if (j + NSB < n_kv) issue_qk(i, j + NSB);   // overwrites S_i(j) | P_i(j): ordered behind P_i(j) V(j) by the in-order tensor pipe
+          if (lane == 0) PAIR_TRACE(j, i, 1);
+        }
       }
     }
   } else if (warp >= 4) {
     // ------------------------------ softmax / correction / epilogue (both CTAs) ------------------------------
-    const int h = (int)(warp - 4u) >> 2;             // column slice of this warp
+    const int i = (int)(warp - 4u) / (4 * SPLIT);    // query tile of this warp
+    const int h = ((int)(warp - 4u) >> 2) % SPLIT;   // column slice of this warp
     const uint32_t wq = warp & 3u;                   // TMEM lane quadrant this warp may access
     const int rit = (int)(wq * 32u + lane);          // row in this CTA's tile
-    const uint32_t lane_base = tmem_base + ((wq * 32u) << 16);
+    const uint32_t lane_base = tmem_base + ((wq * 32u) << 16) + (uint32_t)i * Cfg::TILE_COLS;
+    const int q0 = q0_of(i);
     const int row = q0 + rit;
     const uint32_t o_addr = lane_base + Cfg::TM_O + (uint32_t)(h * OC);
-    auto xch = [&](int par, int slice) { return xch_base + 4u * (uint32_t)((par * SPLIT + slice) * 128 + rit); };
-    const uint32_t quad_bar = 1u + wq;               // named barrier of the SPLIT warps that own these 32 rows
+    auto xch = [&](int par, int slice) { return xch_base + 4u * (uint32_t)(((par * QT + i) * SPLIT + slice) * 128 + rit); };
+    const uint32_t quad_bar = 1u + (uint32_t)i * 4u + wq;   // named barrier of the SPLIT warps that own these 32 rows
     float m_run = -INFINITY;                         // running (possibly stale) row max of raw scores
     float l_run = 0.0f;                              // running sum of exp2((s - m_run) * c) over this thread's columns
     const float c = (p.row_scale && row < p.len_q) ? p.scale_log2 * p.row_scale[(long long)batch * p.len_q + row] : p.scale_log2;
     const uint64_t cc2 = pack2(c, c);
     for (int j = 0; j < n_kv; ++j) {
-      const int b = j & 1;
-      mbar_wait(s_full(b), (uint32_t)(j >> 1) & 1u);
+      const int b = j & 1, sb = j % NSB;
+      mbar_wait(s_full(i, b), (uint32_t)(j >> 1) & 1u);
       tc_fence_after();
+      const bool tr = h == 0 && wq == 0 && lane == 0;
+      if (tr) PAIR_TRACE(j, i, 2);
       uint32_t r[HC];
-      const uint32_t s_addr = lane_base + Cfg::TM_S + (uint32_t)b * Cfg::S_STRIDE + (uint32_t)(h * HC);
+      const uint32_t s_addr = lane_base + Cfg::TM_S + (uint32_t)sb * Cfg::S_STRIDE + (uint32_t)(h * HC);
 #pragma unroll
       for (int cb = 0; cb < HC / 32; ++cb) tmem_ld_x32(s_addr + (uint32_t)(cb * 32), r + cb * 32);
       tmem_ld_wait();
+      if (tr) PAIR_TRACE(j, i, 3);
       const int valid = p.len_kv - j * BKV - h * HC;   // columns of this thread that hold existing keys
       if (valid < HC) {
 #pragma unroll
@@ -232,22 +281,25 @@ fmha_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       float m_tile = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
       // the slices of a row exchange their partial max; the barrier also orders every slice's S loads before anybody's P stores into
       // the columns they were read from (P aliases the first 64 columns of the score buffer)
-      asm volatile("st.shared.f32 [%0], %1;" ::"r"(xch(b, h)), "f"(m_tile) : "memory");
-      asm volatile("bar.sync %0, %1;" ::"r"(quad_bar), "n"(32 * SPLIT) : "memory");
+      if constexpr (SPLIT > 1) {
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(xch(b, h)), "f"(m_tile) : "memory");
+        asm volatile("bar.sync %0, %1;" ::"r"(quad_bar), "n"(32 * SPLIT) : "memory");
 #pragma unroll
-      for (int o = 1; o < SPLIT; ++o) {
-        float other;
-        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(other) : "r"(xch(b, (h + o) % SPLIT)) : "memory");
-        m_tile = fmaxf(m_tile, other);
+        for (int o = 1; o < SPLIT; ++o) {
+          float other;
+          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(other) : "r"(xch(b, (h + o) % SPLIT)) : "memory");
+          m_tile = fmaxf(m_tile, other);
+        }
       }
       const float m_new = fmaxf(m_run, m_tile);
+      if (tr) PAIR_TRACE(j, i, 4);
       if (j == 0) {
         m_run = m_new;
       } else {
         const bool need = (m_new - m_run) * c > 8.0f;
         if (__any_sync(0xffffffffu, need)) {
           // O is accumulated by P(j-1) V(j-1): it must have finished before the rows are rescaled
-          mbar_wait(pv_done((j - 1) & 1), (uint32_t)((j - 1) >> 1) & 1u);
+          mbar_wait(pv_done(i, (j - 1) & 1), (uint32_t)((j - 1) >> 1) & 1u);
           tc_fence_after();
           const float f = need ? ex2_approx((m_run - m_new) * c) : 1.0f;
           if (need) m_run = m_new;
@@ -267,30 +319,39 @@ fmha_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       const float nmc = -m_run * c;
       const uint64_t mc2 = pack2(nmc, nmc);
       uint64_t sum2[2] = {0ull, 0ull};   // packed (even, odd) column partial sums
-      const uint32_t p_addr = lane_base + Cfg::TM_S + (uint32_t)b * Cfg::S_STRIDE + (uint32_t)(h * (HC / 2));
+      const uint32_t p_addr = lane_base + Cfg::TM_S + (uint32_t)sb * Cfg::S_STRIDE + (uint32_t)(h * (HC / 2));
 #pragma unroll
       for (int cb = 0; cb < HC / 32; ++cb) {
         uint32_t pk[16];
         if (cb * 32 >= valid) {   // (warp-uniform) a 32-column chunk past the last key: P = 0 without its exponentials
 #pragma unroll
           for (int k = 0; k < 16; ++k) pk[k] = 0u;
-          tmem_st_x16(p_addr + (uint32_t)(cb * 16), pk);
-          continue;
-        }
+        } else {
 #pragma unroll
-        for (int k = 0; k < 16; ++k) {
-          float y0, y1, e0, e1;
-          unpack2(fma2(pack2(__uint_as_float(r[cb * 32 + 2 * k]), __uint_as_float(r[cb * 32 + 2 * k + 1])), cc2, mc2), y0, y1);
-          if ((k & 7) < Cfg::POLY) {
-            exp2_poly2(y0, y1, e0, e1);
-          } else {
-            e0 = ex2_approx(y0);
-            e1 = ex2_approx(y1);
+          for (int k = 0; k < 16; ++k) {
+            float y0, y1, e0, e1;
+            unpack2(fma2(pack2(__uint_as_float(r[cb * 32 + 2 * k]), __uint_as_float(r[cb * 32 + 2 * k + 1])), cc2, mc2), y0, y1);
+            if ((k & 7) < Cfg::POLY) {
+              exp2_poly2(y0, y1, e0, e1);
+            } else {
+              e0 = ex2_approx(y0);
+              e1 = ex2_approx(y1);
+            }
+            sum2[k & 1] = add2(sum2[k & 1], pack2(e0, e1));
+            pk[k] = pack_bf16(e0, e1);
           }
-          sum2[k & 1] = add2(sum2[k & 1], pack2(e0, e1));
-          pk[k] = pack_bf16(e0, e1);
         }
         tmem_st_x16(p_addr + (uint32_t)(cb * 16), pk);
+        if constexpr (SPLIT == 1) {
+          if (cb == 1) {   // the first 64 keys of P(j) are complete: the tensor pipe starts on them while the other 64 are exponentiated
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              if (leader) mbar_arrive(p_full(i, b, 0)); else mbar_arrive_remote(p_full(i, b, 0), 0);
+            }
+          }
+        }
       }
       {
         float s0, s1, s2, s3;
@@ -298,23 +359,29 @@ fmha_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         unpack2(sum2[1], s2, s3);
         l_run += (s0 + s1) + (s2 + s3);
       }
+      if (tr) PAIR_TRACE(j, i, 5);
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
+      if (tr) PAIR_TRACE(j, i, 6);
       if (lane == 0) {
-        if (leader) mbar_arrive(p_full(b)); else mbar_arrive_cluster(p_full(b), 0);
+        // (CTA-scope release: the data handed over is in tensor memory, ordered by the tcgen05 fences; a cluster-scope release costs a
+        //  MEMBAR.GPU + L1 invalidate per step -- measured 9 % of all warp samples)
+        if (leader) mbar_arrive(p_full(i, b, NH - 1)); else mbar_arrive_remote(p_full(i, b, NH - 1), 0);
       }
     }
     // ---- epilogue: O / l -> bf16 -> shared memory (this CTA's Q buffer: every MMA has completed) -> one bulk tensor store per slab ----
-    asm volatile("st.shared.f32 [%0], %1;" ::"r"(xch(n_kv & 1, h)), "f"(l_run) : "memory");
-    asm volatile("bar.sync %0, %1;" ::"r"(quad_bar), "n"(32 * SPLIT) : "memory");
+    if constexpr (SPLIT > 1) {
+      asm volatile("st.shared.f32 [%0], %1;" ::"r"(xch(n_kv & 1, h)), "f"(l_run) : "memory");
+      asm volatile("bar.sync %0, %1;" ::"r"(quad_bar), "n"(32 * SPLIT) : "memory");
 #pragma unroll
-    for (int o = 1; o < SPLIT; ++o) {
-      float other;
-      asm volatile("ld.shared.f32 %0, [%1];" : "=f"(other) : "r"(xch(n_kv & 1, (h + o) % SPLIT)) : "memory");
-      l_run += other;
+      for (int o = 1; o < SPLIT; ++o) {
+        float other;
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(other) : "r"(xch(n_kv & 1, (h + o) % SPLIT)) : "memory");
+        l_run += other;
+      }
     }
-    mbar_wait(pv_done((n_kv - 1) & 1), (uint32_t)((n_kv - 1) >> 1) & 1u);   // the commit covers every earlier MMA too
+    mbar_wait(pv_done(i, (n_kv - 1) & 1), (uint32_t)((n_kv - 1) >> 1) & 1u);   // the commit covers every earlier MMA too
     tc_fence_after();
     const float inv_l = 1.0f / l_run;
 #pragma unroll
@@ -323,7 +390,7 @@ fmha_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       tmem_ld_x32(o_addr + (uint32_t)(cb * 32), o);
       tmem_ld_wait();
       const int col0 = h * OC + cb * 32;   // first of 32 consecutive output columns
-      const uint32_t srow = smem_q + (uint32_t)((col0 >> 6) * Cfg::Q_SLAB_BYTES + rit * 128);
+      const uint32_t srow = smem_q(i) + (uint32_t)((col0 >> 6) * Cfg::Q_SLAB_BYTES + rit * 128);
 #pragma unroll
       for (int k = 0; k < 32; k += 8) {
         const uint32_t chunk = (uint32_t)(((col0 & 63) + k) >> 3);
@@ -337,10 +404,10 @@ fmha_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       }
     }
     fence_proxy_async_smem();
-    asm volatile("bar.sync %0, %1;" ::"r"(5u), "n"(128 * SPLIT) : "memory");   // all softmax threads of this CTA
-    if (warp == 4 && lane == 0) {
+    asm volatile("bar.sync %0, %1;" ::"r"(9u + (uint32_t)i), "n"(128 * SPLIT) : "memory");   // all softmax threads of this tile
+    if (h == 0 && rit == 0) {
 #pragma unroll
-      for (int sl = 0; sl < 2; ++sl) tma_store_4d(&tmO, smem_q + sl * Cfg::Q_SLAB_BYTES, sl * 64, head, q0, batch);   // rows >= len_q are clipped
+      for (int sl = 0; sl < 2; ++sl) tma_store_4d(&tmO, smem_q(i) + sl * Cfg::Q_SLAB_BYTES, sl * 64, head, q0, batch);   // rows >= len_q are clipped
       tma_store_commit();
       tma_store_wait_read<0>();   // the buffer must stay intact until the TMA unit has read it
     }
@@ -363,9 +430,9 @@ static int make_map4(CUtensorMap* tm, const void* ptr, long long B, long long H,
   return encode_tensor_map(tm, ptr, 2, false, 4, dims, strides, box, true);
 }
 
-template <int SPLIT_, int POLY_>
+template <int QT_, int SPLIT_, int POLY_>
 static int launch_fmha_pair(const vist3a_fmha_args& a, cudaStream_t stream) {
-  using Cfg = FmhaPairCfg<SPLIT_, POLY_>;
+  using Cfg = FmhaPairCfg<QT_, SPLIT_, POLY_>;
   CUtensorMap tmQ, tmK, tmV, tmO;
   int rc;
   if ((rc = make_map4(&tmQ, a.Q, a.batch, a.heads, a.len_q, 128, a.q_bs, a.q_rs, a.q_hs, Cfg::BQ))) return rc;
@@ -377,25 +444,30 @@ static int launch_fmha_pair(const vist3a_fmha_args& a, cudaStream_t stream) {
   p.len_kv = (int)a.len_kv;
   p.scale_log2 = a.scale * 1.4426950408889634f;
   p.row_scale = a.q_row_scale;
-  auto kern = fmha_pair_kernel<SPLIT_, POLY_>;
+  p.trace = g_pair_trace.load(std::memory_order_relaxed);
+  auto kern = fmha_pair_kernel<QT_, SPLIT_, POLY_>;
   static std::atomic<unsigned long long> attr_done{0};
   V3A_CUDA_OK(ensure_dynamic_smem(kern, Cfg::SMEM_BYTES, attr_done));
-  const long long rows_per_cluster = 2 * Cfg::BQ;
+  const long long rows_per_cluster = 2 * Cfg::QT * Cfg::BQ;
   dim3 grid((unsigned)(2 * ((a.len_q + rows_per_cluster - 1) / rows_per_cluster)), (unsigned)a.heads, (unsigned)a.batch);
   V3A_CUDA_OK(launch_kernel(kern, grid, dim3(Cfg::THREADS), Cfg::SMEM_BYTES, stream, /*pdl=*/true, 2, tmQ, tmK, tmV, tmO, p));
   launch_counter().fetch_add(1);
   return VIST3A_OK;
 }
 
-// head_dim 128 on CTA pairs; `variant`: 0 = default (4 threads per row, all MUFU), 1 = 2 threads per row, 2 / 3 = 1 / 2 of 8 column pairs
-// on the FMA pipe (4 threads per row)
+// head_dim 128 on CTA pairs; `variant` (A/B measurements): 0 = default: two query tiles per CTA, one thread per query row, P handed over in
+// two key halves, all exponentials on the MUFU; 1 / 2 = the same with 1 / 2 of every 8 column pairs on the FMA pipe; 3 = two tiles, two
+// threads per row; 4 = two tiles, two threads per row, 2 of 8 on the FMA pipe; 5 = one tile per CTA, 4 threads per row
 int fmha_pair_entry(const vist3a_fmha_args& a, int variant, cudaStream_t stream) {
   switch (variant) {
-    case 1: return launch_fmha_pair<2, 0>(a, stream);
-    case 2: return launch_fmha_pair<4, 1>(a, stream);
-    case 3: return launch_fmha_pair<4, 2>(a, stream);
-    case 4: return launch_fmha_pair<2, 2>(a, stream);
-    default: return launch_fmha_pair<4, 0>(a, stream);
+    case 1: return launch_fmha_pair<2, 1, 1>(a, stream);
+    case 2: return launch_fmha_pair<2, 1, 2>(a, stream);
+    case 3: return launch_fmha_pair<2, 2, 0>(a, stream);
+    case 4: return launch_fmha_pair<2, 2, 2>(a, stream);
+    case 5: return launch_fmha_pair<2, 1, 3>(a, stream);
+    case 6: return launch_fmha_pair<2, 1, 4>(a, stream);
+    case 7: return launch_fmha_pair<2, 2, 3>(a, stream);
+    default: return launch_fmha_pair<2, 1, 0>(a, stream);
   }
 }
 

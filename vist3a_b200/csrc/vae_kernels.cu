@@ -20,50 +20,70 @@ __device__ __forceinline__ uint32_t pack2bf(float lo, float hi) {
   return *reinterpret_cast<const uint32_t*>(&v);
 }
 
-// y[r, c] = silu?( x[r, c] / max(||x[r, :C]||, 1e-12) * sqrt(C) * gamma[c] ) for c < C, 0 for C <= c < ldy.  One warp per row: lane l owns
-// the 16-byte chunks l, l + 32 (C = 96 / 192 / 384 -> 12 / 24 / 48 chunks): one read and one write of the row.
-template <bool kSilu>
+// y[r, c] = silu?( x[r, c] / max(||x[r, :C]||, 1e-12) * sqrt(C) * gamma[c] ) for c < C, 0 for C <= c < ldy.  LPR lanes per row (16 for rows of
+// up to 128 channels: two rows per warp, every lane busy on the 96-channel layers that carry most of the bytes; 32 otherwise), each lane
+// owns the 16-byte chunks l, l + LPR, ...; two row groups per warp iteration are in flight (loads of the second issued before the
+// reduction of the first): one read and one write of every row.
+template <bool kSilu, int LPR>
 __global__ void __launch_bounds__(256) vae_rmsnorm_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, const float* __restrict__ gamma,
                                                           __nv_bfloat16* __restrict__ y, long long ldy, long long rows, int C) {
-  const int lane = threadIdx.x & 31;
+  constexpr int RPW = 32 / LPR;                        // rows per warp and pass
+  constexpr int NCH = LPR == 16 ? 1 : 2;               // chunks per lane (ld <= 128 with 16 lanes; <= 512 with 32)
+  const int lane = threadIdx.x & 31, sub = lane % LPR, rsel = lane / LPR;
   const int chunks = C / 8, ychunks = (int)(ldy / 8);
   const float root_c = sqrtf((float)C);
-  for (long long r = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); r < rows; r += (long long)gridDim.x * 8) {
-    const uint4* xr = reinterpret_cast<const uint4*>(x + r * ldx);
-    uint4 v[2];
-    float ss = 0.f;
+  const long long warp0 = (long long)blockIdx.x * 8 + (threadIdx.x >> 5), nwarps = (long long)gridDim.x * 8;
+  for (long long r0 = warp0 * (2 * RPW); r0 < rows; r0 += nwarps * (2 * RPW)) {
+    uint4 v[2][NCH];
+    float ss[2] = {0.f, 0.f};
 #pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      const int ch = lane + 32 * k;
-      v[k] = ch < chunks ? xr[ch] : make_uint4(0u, 0u, 0u, 0u);
-      const uint32_t w[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
+    for (int g = 0; g < 2; ++g) {
+      const long long r = r0 + g * RPW + rsel;
+      const uint4* xr = reinterpret_cast<const uint4*>(x + r * ldx);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) ss += bf16_lo(w[j]) * bf16_lo(w[j]) + bf16_hi(w[j]) * bf16_hi(w[j]);
+      for (int k = 0; k < NCH; ++k) {
+        const int ch = sub + LPR * k;
+        v[g][k] = (r < rows && ch < chunks) ? xr[ch] : make_uint4(0u, 0u, 0u, 0u);
+      }
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-    const float scale = root_c / fmaxf(sqrtf(ss), 1e-12f);
-    uint4* yr = reinterpret_cast<uint4*>(y + r * ldy);
+    for (int g = 0; g < 2; ++g) {
 #pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      const int ch = lane + 32 * k;
-      if (ch < chunks) {
-        const float4 g0 = *reinterpret_cast<const float4*>(gamma + ch * 8), g1 = *reinterpret_cast<const float4*>(gamma + ch * 8 + 4);
-        const uint32_t w[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
-        const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-        uint32_t o4[4];
+      for (int k = 0; k < NCH; ++k) {
+        const uint32_t w[4] = {v[g][k].x, v[g][k].y, v[g][k].z, v[g][k].w};
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          float a = bf16_lo(w[j]) * scale * g[2 * j], b = bf16_hi(w[j]) * scale * g[2 * j + 1];
-          if (kSilu) {
-            a = __fdividef(a, 1.f + __expf(-a));
-            b = __fdividef(b, 1.f + __expf(-b));
+        for (int j = 0; j < 4; ++j) ss[g] += bf16_lo(w[j]) * bf16_lo(w[j]) + bf16_hi(w[j]) * bf16_hi(w[j]);
+      }
+#pragma unroll
+      for (int o = LPR / 2; o > 0; o >>= 1) ss[g] += __shfl_xor_sync(0xffffffffu, ss[g], o);
+    }
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+      const long long r = r0 + g * RPW + rsel;
+      if (r >= rows) continue;
+      const float scale = root_c / fmaxf(sqrtf(ss[g]), 1e-12f);
+      uint4* yr = reinterpret_cast<uint4*>(y + r * ldy);
+#pragma unroll
+      for (int k = 0; k < NCH; ++k) {
+        const int ch = sub + LPR * k;
+        if (ch < chunks) {
+          const float4 g0 = *reinterpret_cast<const float4*>(gamma + ch * 8), g1 = *reinterpret_cast<const float4*>(gamma + ch * 8 + 4);
+          const uint32_t w[4] = {v[g][k].x, v[g][k].y, v[g][k].z, v[g][k].w};
+          const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+          uint32_t o4[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float a = bf16_lo(w[j]) * scale * gm[2 * j], b = bf16_hi(w[j]) * scale * gm[2 * j + 1];
+            if (kSilu) {
+              a = __fdividef(a, 1.f + __expf(-a));
+              b = __fdividef(b, 1.f + __expf(-b));
+            }
+            o4[j] = pack2bf(a, b);
           }
-          o4[j] = pack2bf(a, b);
+          yr[ch] = make_uint4(o4[0], o4[1], o4[2], o4[3]);
+        } else if (ch < ychunks) {
+          yr[ch] = make_uint4(0u, 0u, 0u, 0u);   // padding channels of a convolution input stay zero
         }
-        yr[ch] = make_uint4(o4[0], o4[1], o4[2], o4[3]);
-      } else if (ch < ychunks) {
-        yr[ch] = make_uint4(0u, 0u, 0u, 0u);   // padding channels of a convolution input stay zero
       }
     }
   }
@@ -181,6 +201,25 @@ __global__ void __launch_bounds__(256) frames_out_kernel(const float* __restrict
   }
 }
 
+// planar bilinear resize with half-pixel centres (F.interpolate(mode="trilinear", align_corners=False) with the frame count kept is a
+// per-frame bilinear resize): in [planes, hi, wi] -> out [planes, ho, wo]; source index = scale * (dst + 0.5) - 0.5 clamped at 0
+// (ATen area_pixel_compute_source_index), neighbours clamped at the border
+__global__ void __launch_bounds__(256) resize_planes_kernel(const float* __restrict__ in, float* __restrict__ out, long long planes, int hi, int wi, int ho,
+                                                            int wo, float sy, float sx) {
+  const long long total = planes * ho * wo;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(i % wo), y = (int)((i / wo) % ho);
+    const long long pl = i / ((long long)wo * ho);
+    const float fy = fmaxf(sy * ((float)y + 0.5f) - 0.5f, 0.f), fx = fmaxf(sx * ((float)x + 0.5f) - 0.5f, 0.f);
+    const int y0 = min((int)fy, hi - 1), x0 = min((int)fx, wi - 1);
+    const int y1 = min(y0 + 1, hi - 1), x1 = min(x0 + 1, wi - 1);
+    const float ly = fy - (float)y0, lx = fx - (float)x0;
+    const float* b = in + pl * hi * wi;
+    const float v00 = b[(long long)y0 * wi + x0], v01 = b[(long long)y0 * wi + x1], v10 = b[(long long)y1 * wi + x0], v11 = b[(long long)y1 * wi + x1];
+    out[i] = (1.f - ly) * ((1.f - lx) * v00 + lx * v01) + ly * ((1.f - lx) * v10 + lx * v11);
+  }
+}
+
 inline unsigned blocks_for(long long n, int per_block, int cap) {
   const long long b = (n + per_block - 1) / per_block;
   return (unsigned)(b < cap ? (b > 0 ? b : 1) : cap);
@@ -192,9 +231,17 @@ int vae_rmsnorm_entry(const void* x, long long ldx, const float* gamma, void* y,
   V3A_REQUIRE(x && gamma && y && rows > 0 && C > 0 && C % 8 == 0 && C <= 512, VIST3A_ERR_INVALID, "vae_rmsnorm: C must be a multiple of 8, <= 512");
   V3A_REQUIRE(ldx >= C && ldy >= C && ldx % 8 == 0 && ldy % 8 == 0 && ldy <= 512, VIST3A_ERR_INVALID, "vae_rmsnorm: row strides must be multiples of 8 elements, >= C");
   V3A_REQUIRE((((uintptr_t)x | (uintptr_t)y | (uintptr_t)gamma) & 15) == 0, VIST3A_ERR_INVALID, "vae_rmsnorm: pointers must be 16-byte aligned");
-  const unsigned grid = blocks_for(rows, 8, num_sms() * 16);
-  if (silu) vae_rmsnorm_kernel<true><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, ldx, gamma, (__nv_bfloat16*)y, ldy, rows, (int)C);
-  else vae_rmsnorm_kernel<false><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, ldx, gamma, (__nv_bfloat16*)y, ldy, rows, (int)C);
+  const bool narrow = ldy <= 128 && C <= 128;         // 16 lanes per row
+  const unsigned grid = blocks_for(rows, narrow ? 32 : 16, num_sms() * 16);
+  const __nv_bfloat16* xb = (const __nv_bfloat16*)x;
+  __nv_bfloat16* yb = (__nv_bfloat16*)y;
+  if (silu) {
+    if (narrow) vae_rmsnorm_kernel<true, 16><<<grid, 256, 0, st>>>(xb, ldx, gamma, yb, ldy, rows, (int)C);
+    else vae_rmsnorm_kernel<true, 32><<<grid, 256, 0, st>>>(xb, ldx, gamma, yb, ldy, rows, (int)C);
+  } else {
+    if (narrow) vae_rmsnorm_kernel<false, 16><<<grid, 256, 0, st>>>(xb, ldx, gamma, yb, ldy, rows, (int)C);
+    else vae_rmsnorm_kernel<false, 32><<<grid, 256, 0, st>>>(xb, ldx, gamma, yb, ldy, rows, (int)C);
+  }
   V3A_CUDA_OK(cudaGetLastError());
   launch_counter().fetch_add(1);
   return VIST3A_OK;
@@ -239,6 +286,15 @@ int latent_to_ndhwc_entry(const void* z, int dtype, void* out, long long C, long
   const unsigned grid = blocks_for(THW * ld, 256, num_sms() * 8);
   if (dtype == VIST3A_DTYPE_F32) latent_to_ndhwc_kernel<true><<<grid, 256, 0, st>>>(z, (__nv_bfloat16*)out, (int)C, THW, (int)ld);
   else latent_to_ndhwc_kernel<false><<<grid, 256, 0, st>>>(z, (__nv_bfloat16*)out, (int)C, THW, (int)ld);
+  V3A_CUDA_OK(cudaGetLastError());
+  launch_counter().fetch_add(1);
+  return VIST3A_OK;
+}
+
+int resize_planes_entry(const float* in, float* out, long long planes, long long hi, long long wi, long long ho, long long wo, cudaStream_t st) {
+  V3A_REQUIRE(in && out && planes > 0 && hi > 0 && wi > 0 && ho > 0 && wo > 0, VIST3A_ERR_INVALID, "resize_planes: bad shape");
+  resize_planes_kernel<<<blocks_for(planes * ho * wo, 256, num_sms() * 16), 256, 0, st>>>(in, out, planes, (int)hi, (int)wi, (int)ho, (int)wo, (float)hi / (float)ho,
+                                                                                           (float)wi / (float)wo);
   V3A_CUDA_OK(cudaGetLastError());
   launch_counter().fetch_add(1);
   return VIST3A_OK;

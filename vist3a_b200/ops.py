@@ -620,6 +620,7 @@ class OpTimer:
                 cv = kw["conv"]
                 n_, h_, w_, _ = cv.get("geom", a.shape)
                 M = n_ * (h_ + 2 * cv["pad"] - cv["kh"] + 1) * (w_ + 2 * cv.get("pad_x", cv["pad"]) - cv["kw"] + 1)
+                N = out.shape[-1] if out.dim() == 2 else N
             by = M * K * a.element_size() + N * K * w.element_size() + M * N * out.element_size()
             ep = ("+" + kw["act"] if kw.get("act") else "") + ("+gate" if kw.get("gate") is not None else "") + (
                 "+res" if kw.get("residual") is not None else "")
@@ -650,7 +651,10 @@ class OpTimer:
                  "im2col_nhwc": io_cost("im2col"), "rgb_to_nhwc4pad": io_cost("small"), "rgb01_views_to_nhwc4pad": io_cost("small"),
                  "patch_embed_im2col": io_cost("im2col"), "qknorm_rope2d_": io_cost("qknorm_rope2d"), "bilinear_nhwc": io_cost("bilinear"),
                  "depth_to_space": io_cost("depth_to_space"), "attention_small": io_cost("small"), "fma_rows": io_cost("small"),
-                 "pose_to_cameras": io_cost("small"), "linear_tokens16": io_cost("linear_tokens16"), "gaussian_epilogue": io_cost("gaussian_epilogue")}
+                 "pose_to_cameras": io_cost("small"), "linear_tokens16": io_cost("linear_tokens16"), "gaussian_epilogue": io_cost("gaussian_epilogue"),
+                 "vae_rmsnorm": io_cost("vae_rmsnorm"), "softmax_rows": io_cost("softmax_rows"), "time_interleave": io_cost("vae_layout"),
+                 "transpose_bf16": io_cost("vae_layout"), "depth_to_space2_bf16": io_cost("vae_layout"), "latent_to_ndhwc": io_cost("small"),
+                 "vae_frames_out": io_cost("vae_layout"), "resize_planes": io_cost("vae_layout")}
         for name, cost in table.items():
             self._saved[name] = getattr(mod, name)
             setattr(mod, name, self._wrap(name, self._saved[name], cost))
@@ -675,3 +679,91 @@ class OpTimer:
             d["flops"] += fl
             d["bytes"] += by
         return agg
+
+
+# ------------------------------------------------------------------------------------------------
+# Wan VAE decode kernels (NDHWC bf16 activations; see vist3a_b200/wan_vae.py)
+# ------------------------------------------------------------------------------------------------
+def vae_rmsnorm(x: torch.Tensor, gamma: torch.Tensor, C: int, *, silu: bool = True, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x [..., ldx] bf16 (channels [0, C) valid) -> [..., ldy] bf16: RMS norm over the C channels * gamma (+ SiLU); channels [C, ldy) = 0."""
+    _need_cuda(x, gamma, out)
+    if x.dtype != torch.bfloat16 or not x.is_contiguous() or gamma.dtype != torch.float32:
+        raise TypeError("vae_rmsnorm: contiguous bfloat16 activations and a float32 gamma expected")
+    ldx = x.shape[-1]
+    if out is None:
+        out = torch.empty_like(x)
+    rows = x.numel() // ldx
+    L.check(L.load().vist3a_vae_rmsnorm(x.data_ptr(), ldx, gamma.data_ptr(), out.data_ptr(), out.shape[-1], rows, C, int(silu), _stream()))
+    return out
+
+
+def softmax_rows(s: torch.Tensor, scale: float, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """softmax(scale * s) per row: fp32 [rows, L] -> bf16 [rows, L]."""
+    _need_cuda(s, out)
+    if s.dim() != 2 or s.dtype != torch.float32 or not s.is_contiguous():
+        raise TypeError("softmax_rows: contiguous float32 [rows, L] expected")
+    if out is None:
+        out = torch.empty(s.shape, dtype=torch.bfloat16, device=s.device)
+    L.check(L.load().vist3a_softmax_rows(s.data_ptr(), out.data_ptr(), s.shape[0], s.shape[1], float(scale), _stream()))
+    return out
+
+
+def time_interleave(y: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+    """y [T, H, W, 2C] bf16 -> out [2T, H, W, C]: out[2t + half] = y[t, ..., half*C:(half+1)*C]."""
+    _need_cuda(y, out)
+    T, H, W, C2 = y.shape
+    if not y.is_contiguous() or not out.is_contiguous() or out.shape != (2 * T, H, W, C2 // 2) or y.dtype != torch.bfloat16 or out.dtype != torch.bfloat16:
+        raise ValueError("time_interleave: y [T, H, W, 2C] and out [2T, H, W, C] contiguous bfloat16 expected")
+    L.check(L.load().vist3a_time_interleave(y.data_ptr(), out.data_ptr(), T, H * W, C2 // 2, _stream()))
+    return out
+
+
+def transpose_bf16(x: torch.Tensor) -> torch.Tensor:
+    """[R, C] bf16 (unit inner stride, any row stride) -> contiguous [C, R]."""
+    _need_cuda(x)
+    if x.dim() != 2 or x.dtype != torch.bfloat16 or x.stride(1) != 1:
+        raise TypeError("transpose_bf16: 2-D bfloat16 with unit inner stride expected")
+    out = torch.empty((x.shape[1], x.shape[0]), dtype=torch.bfloat16, device=x.device)
+    L.check(L.load().vist3a_transpose_bf16(x.data_ptr(), x.stride(0), out.data_ptr(), x.shape[0], x.shape[1], _stream()))
+    return out
+
+
+def depth_to_space2_bf16(y: torch.Tensor, n: int, h: int, w: int, C: int, ldo: int) -> torch.Tensor:
+    """[n*h*w, 4*C] bf16 (col (py*2+px)*C + c) -> NHWC [n, 2h, 2w, ldo] (channels [0, C) written)."""
+    _need_cuda(y)
+    if y.dtype != torch.bfloat16 or not y.is_contiguous() or y.shape != (n * h * w, 4 * C):
+        raise ValueError("depth_to_space2_bf16: contiguous bfloat16 [n*h*w, 4*C] expected")
+    out = torch.empty((n, 2 * h, 2 * w, ldo), dtype=torch.bfloat16, device=y.device)
+    L.check(L.load().vist3a_depth_to_space2_bf16(y.data_ptr(), out.data_ptr(), n, h, w, C, ldo, _stream()))
+    return out
+
+
+def latent_to_ndhwc(z: torch.Tensor, ld: int) -> torch.Tensor:
+    """z [C, T, h, w] (fp32 / bf16) -> [T, h, w, ld] bf16 with channels [C, ld) zero."""
+    _need_cuda(z)
+    z = z.contiguous()
+    Cc, T, h, w = z.shape
+    out = torch.empty((T, h, w, ld), dtype=torch.bfloat16, device=z.device)
+    L.check(L.load().vist3a_latent_to_ndhwc(z.data_ptr(), _dt(z), out.data_ptr(), Cc, T * h * w, ld, _stream()))
+    return out
+
+
+def vae_frames_out(y: torch.Tensor, T: int, H: int, W: int) -> torch.Tensor:
+    """conv_out result [T*H*W, ld] fp32 -> frames [3, T, H, W] fp32 clamped to [-1, 1]."""
+    _need_cuda(y)
+    if y.dtype != torch.float32 or not y.is_contiguous() or y.shape[0] != T * H * W:
+        raise ValueError("vae_frames_out: contiguous float32 [T*H*W, ld] expected")
+    out = torch.empty((3, T, H, W), dtype=torch.float32, device=y.device)
+    L.check(L.load().vist3a_vae_frames_out(y.data_ptr(), y.shape[1], out.data_ptr(), T * H * W, _stream()))
+    return out
+
+
+def resize_planes(x: torch.Tensor, h_out: int, w_out: int) -> torch.Tensor:
+    """[..., H, W] fp32 -> [..., h_out, w_out]: bilinear, half-pixel centres (align_corners=False), every leading index a plane."""
+    _need_cuda(x)
+    if x.dtype != torch.float32 or not x.is_contiguous():
+        raise TypeError("resize_planes: contiguous float32 expected")
+    out = torch.empty(tuple(x.shape[:-2]) + (h_out, w_out), dtype=torch.float32, device=x.device)
+    planes = x.numel() // (x.shape[-1] * x.shape[-2])
+    L.check(L.load().vist3a_resize_planes(x.data_ptr(), out.data_ptr(), planes, x.shape[-2], x.shape[-1], h_out, w_out, _stream()))
+    return out

@@ -79,9 +79,15 @@ class TextTo3DGS:
 
 def views_from_vae(vae, latent: torch.Tensor, size: int = 448) -> torch.Tensor:
     """inference_t23d.py:114-123: `samples = pipe.vae.decode(latents, return_dict=False)[0]`, then a trilinear (align_corners=False)
-    resize of the frames to size x size with the frame count kept.  Host plumbing around the caller's VAE module."""
+    resize of the frames to size x size with the frame count kept.  With the engine's own decoder (`WanVAEDecoderB200`) both steps run on
+    the sm_100a kernels; any other object is treated as the caller's VAE module (diffusers' `decode(latents, return_dict=False)`)."""
     import torch.nn.functional as F
 
+    from .wan_vae import WanVAEDecoderB200
+
+    if isinstance(vae, WanVAEDecoderB200):
+        samples = vae.decode(latent, return_dict=False)[0]                # [B, 3, T, 8h, 8w] fp32 in [-1, 1]
+        return ops.resize_planes(samples, size, size)
     p = next(iter(vae.parameters()), None) if hasattr(vae, "parameters") else None
     samples = vae.decode(latent if p is None else latent.to(p.dtype), return_dict=False)[0]
     return F.interpolate(samples.float(), (samples.shape[2], size, size), mode="trilinear", align_corners=False)
