@@ -34,7 +34,7 @@ extern "C" {
 #define VIST3A_DTYPE_F32 1
 
 const char* vist3a_last_error(void);
-int vist3a_abi_version(void); /* 6 */
+int vist3a_abi_version(void); /* 7 */
 /* number of kernels this library has launched from the calling process (all threads) */
 int64_t vist3a_launch_count(void);
 /* Programmatic dependent launch (PDL) of the hot kernels (GEMM, attention, LayerNorm, RMSNorm+RoPE, row_rinv): each is launched
@@ -394,12 +394,12 @@ int vist3a_gs_rasterize(const void* project_workspace, int64_t n_gaussians, int6
 int vist3a_vae_rmsnorm(const void* x, int64_t ldx, const float* gamma, void* y, int64_t ldy, int64_t rows, int64_t C, int32_t silu, void* stream);
 /* p[r, :] = softmax(scale * s[r, :]) in bf16 from fp32 logits.  replaces: the softmax inside F.scaled_dot_product_attention of
  * WanAttentionBlock (:463-467: one head of width C over the H*W positions of a frame). */
-int vist3a_softmax_rows(const float* s, void* p, int64_t rows, int64_t L, float scale, void* stream);
+int vist3a_softmax_rows(const float* s, void* p, int64_t rows, int64_t L, int64_t ldp, float scale, void* stream);
 /* out[2t + half, p, :] = y[t, p, half*C : (half+1)*C]  (y [T, P, 2C] -> out [2T, P, C], bf16).  replaces: the channel-halves-to-time
  * interleave of WanResample "upsample3d" (:304-306). */
 int vist3a_time_interleave(const void* y, void* out, int64_t T, int64_t P, int64_t C, void* stream);
 /* out[c, r] = in[r, c]  (bf16 [R, C] with row stride ld_in -> [C, R]): V^T operand of the mid-block attention's P V GEMM */
-int vist3a_transpose_bf16(const void* in, int64_t ld_in, void* out, int64_t R, int64_t C, void* stream);
+int vist3a_transpose_bf16(const void* in, int64_t ld_in, void* out, int64_t ld_out, int64_t R, int64_t C, void* stream);
 /* depth-to-space (k = 2) of the parity-decomposed up-sampling convolution: in [n*h*w, 4*C] (col = (py*2 + px)*C + c) -> NHWC bf16
  * [n, 2h, 2w, ldo] (channels [0, C)).  replaces: WanUpsample (nearest-exact 2x) + Conv2d 3x3 output layout (:226-238). */
 int vist3a_depth_to_space2_bf16(const void* in, void* out, int64_t n_img, int64_t h, int64_t w, int64_t C, int64_t ldo, void* stream);
@@ -412,6 +412,26 @@ int vist3a_vae_frames_out(const float* y, int64_t ld, float* out, int64_t THW, v
  * (T, 448, 448), mode="trilinear", align_corners=False) of the decoded frames (inference_t23d.py:116-123; the frame count is kept, so the
  * temporal weights are the identity). */
 int vist3a_resize_planes(const float* in, float* out, int64_t planes, int64_t h_in, int64_t w_in, int64_t h_out, int64_t w_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Confidence-quantile branches of the stitched decoder (EncoderAnySplatCfg.render_conf / opacity_conf; models/anysplat_stitched.py:381-387,
+ * 442-455, 463-467).  HBM-bound index work on caller-owned workspaces (256-byte aligned device memory).
+ * ------------------------------------------------------------------------------------------ */
+/* conf[p] = 1 + exp(dot(feat[p, 0:C], w) + bias): the depth head's confidence channel ("expp1", AS/.../heads/head_act.py:102-103) from the
+ * 32-wide feature rows in front of its last 1x1 convolution */
+int vist3a_depth_conf(const float* feat, int64_t ld, int64_t C, const float* w, float bias, float* conf, int64_t n_pixels, void* stream);
+/* *out (device float) = torch.quantile(x, q) over n floats, interpolation "linear" (rank q (n - 1) in fp32; torch.lerp between the two order
+ * statistics): stable radix sort of order-preserving keys.  replaces: torch.quantile(depth_conf.flatten(0, 1), conf_threshold) (:382-384, :464) */
+int64_t vist3a_quantile_workspace_bytes(int64_t n);
+int vist3a_quantile_f32(const float* x, int64_t n, float q, float* out, void* workspace, int64_t workspace_bytes, void* stream);
+/* ordered compaction: rows i with conf[i] > *threshold (all rows if use_threshold == 0), in index order -> out_feats [count, C] (from feats rows
+ * of stride ld_feats), out_pts [count, 3], out_damp [count] = sigmoid(conf[i] - *threshold) (may be NULL); *count (device int64) = kept rows.
+ * replaces: `anchor_feats[b_i].permute(0, 2, 3, 1)[conf_valid_mask[b_i]]`, `pts_all[b_i][conf_valid_mask[b_i]]` (:442-446) and
+ * `torch.sigmoid(depth_conf - shift)[conf_valid_mask]` (:465-467). */
+int64_t vist3a_compact_rows_workspace_bytes(int64_t n);
+int vist3a_compact_rows(const float* conf, const float* threshold, int32_t use_threshold, int64_t n, const float* feats, int64_t ld_feats, int64_t C,
+                        const float* pts, float* out_feats, float* out_pts, float* out_damp, int64_t* count, void* workspace, int64_t workspace_bytes,
+                        void* stream);
 
 #ifdef __cplusplus
 }

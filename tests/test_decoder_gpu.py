@@ -239,3 +239,77 @@ def test_load_stitching_model_builds_the_same_engine(tmp_path):
         assert torch.equal(got[k], want[k]) if k != "scene_scale" else _rel(got[k], want[k]) < 1e-5, k
     plain = _as_dict(_engine(sd, D.TINY, 64).forward_with_latent(lat.cuda(), img.cuda()))
     assert _rel(plain["harmonics"], want["harmonics"]) > 1e-4      # the adapter changed the model
+
+
+# ------------------------------------------------------------------------------------------------
+# confidence-quantile branches (render_conf / opacity_conf; models/anysplat_stitched.py:381-387, 442-455, 463-467)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,q", [(1, 0.5), (7, 0.1), (4097, 0.1), (100_000, 0.3), (652_288, 0.1), (2_609_152, 0.999)])
+def test_quantile_is_bit_exact_against_torch(n, q):
+    """index / order-statistic work: bit-exact against torch.quantile (CPU, fp32, linear interpolation) incl. ties and negatives"""
+    from vist3a_b200 import ops
+
+    g = torch.Generator().manual_seed(n)
+    x = 1.0 + torch.randn(n, generator=g).exp()
+    x[::5] = x[0]                                   # ties
+    if n > 3:
+        x[1], x[2] = -3.5, 0.0
+    got = ops.quantile(x.cuda(), q).cpu()
+    want = torch.quantile(x, q)
+    assert got.item() == want.item(), (got.item(), want.item())
+
+
+@pytest.mark.parametrize("n,C,use_thr", [(1, 4, True), (2047, 83, True), (2049, 83, True), (70_001, 83, True), (70_001, 12, False), (652_288, 83, True)])
+def test_compact_rows_is_bit_exact_against_boolean_mask(n, C, use_thr):
+    from vist3a_b200 import ops
+
+    g = torch.Generator().manual_seed(n + C)
+    conf = 1.0 + torch.randn(n, generator=g).exp()
+    thr = torch.quantile(conf, 0.4).reshape(1) if n > 1 else torch.tensor([0.0])
+    feats = torch.randn(n, C + 5, generator=g)     # strided rows (the engine's raw Gaussian rows are wider than C)
+    pts = torch.randn(n, 3, generator=g)
+    k = ops.compact_rows(conf.cuda(), thr.cuda(), feats.cuda()[:, :C], pts.cuda(), feat_dim=C, use_threshold=use_thr, want_damp=True)
+    mask = conf > thr if use_thr else torch.ones(n, dtype=torch.bool)
+    assert k["count"] == int(mask.sum())
+    assert torch.equal(k["feats"].cpu(), feats[:, :C][mask])
+    assert torch.equal(k["pts"].cpu(), pts[mask])
+    torch.testing.assert_close(k["damp"].cpu(), torch.sigmoid(conf - thr)[mask], rtol=2e-6, atol=1e-7)
+
+
+@pytest.mark.parametrize("render_conf,opacity_conf,thr", [(True, False, 0.1), (True, True, 0.3), (False, True, 0.1)])
+def test_confidence_branches_against_oracle(render_conf, opacity_conf, thr):
+    """The engine's confidence map differs from the fp32 oracle's by its bf16/TF32 numerics, so pixels within that error of the
+    quantile may flip: the kept set is compared as a set (>= 99 % agreement, count within 1 %), the kept Gaussians bit-exactly against
+    the engine's own un-thresholded output at the kept pixels, and the damped opacities against the oracle on the common pixels."""
+    import dataclasses
+
+    from oracle import decoder_ref as D
+
+    sd = D.init_state_dict(D.TINY, seed=11)
+    lat, img = D.synthetic_inputs(D.TINY, views_latent=2, latent_hw=8, image_hw=56, seed=5)
+    ref = D.decoder_forward(sd, D.TINY, lat, img, resolution=64, render_conf=render_conf, opacity_conf=opacity_conf, conf_threshold=thr)
+    m = _engine(sd, D.TINY, 64)
+    plain = m.forward_with_latent(lat.cuda(), img.cuda())
+    m.cfg = dataclasses.replace(m.cfg, render_conf=render_conf, opacity_conf=opacity_conf, conf_threshold=thr)
+    out = m.forward_with_latent(lat.cuda(), img.cuda())
+    mask = out.depth_dict["conf_valid_mask"].flatten().cpu()
+    ref_mask = ref["conf_valid_mask"].flatten()
+    n_kept = out.gaussians.means.shape[1]
+    assert n_kept == int(mask.sum()) == out.infos["valid_counts"][0]
+    if render_conf:
+        assert float((mask == ref_mask).float().mean()) > 0.99
+        assert abs(n_kept - int(ref_mask.sum())) <= 0.01 * ref_mask.numel()
+        assert abs(n_kept / mask.numel() - (1 - thr)) < 0.01
+    else:
+        assert bool(mask.all()) and n_kept == mask.numel()
+    for k in ("means", "scales", "rotations", "harmonics", "covariances"):
+        assert torch.equal(getattr(out.gaussians, k)[0].cpu(), getattr(plain.gaussians, k)[0].cpu()[mask]), k
+    if not opacity_conf:
+        assert torch.equal(out.gaussians.opacities[0].cpu(), plain.gaussians.opacities[0].cpu()[mask])
+    else:
+        # common pixels: position of each kept pixel in either compaction
+        both = mask & ref_mask
+        ours = out.gaussians.opacities[0].cpu()[both[mask]]
+        want = ref["opacities"][0][both[ref_mask]]
+        assert _rel(ours, want) < 5e-3
+        assert bool((out.gaussians.opacities[0].cpu() <= plain.gaussians.opacities[0].cpu()[mask]).all())

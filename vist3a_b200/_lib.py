@@ -62,9 +62,14 @@ EXPORTS = (
     "vist3a_latent_to_ndhwc",
     "vist3a_vae_frames_out",
     "vist3a_resize_planes",
+    "vist3a_depth_conf",
+    "vist3a_quantile_f32",
+    "vist3a_compact_rows",
     "vist3a_voxel_fusion_workspace_bytes",
     "vist3a_gs_project_workspace_bytes",
     "vist3a_gs_rasterize_workspace_bytes",
+    "vist3a_quantile_workspace_bytes",
+    "vist3a_compact_rows_workspace_bytes",
 )
 
 
@@ -168,7 +173,7 @@ def load(build_if_missing: bool = False) -> C.CDLL:
     lib.vist3a_launch_count.restype = C.c_int64
     lib.vist3a_set_pdl.restype = C.c_int
     lib.vist3a_set_pdl.argtypes = [C.c_int32]
-    for name in EXPORTS[4:-3]:
+    for name in EXPORTS[4:-5]:
         getattr(lib, name).restype = C.c_int
     lib.vist3a_voxel_fusion_workspace_bytes.restype = C.c_int64
     lib.vist3a_voxel_fusion_workspace_bytes.argtypes = [C.c_int64]
@@ -209,13 +214,20 @@ def load(build_if_missing: bool = False) -> C.CDLL:
     lib.vist3a_gs_project.argtypes = [vp, vp, vp, vp, i64, i32, i64, fp, fp, i64, i64, f32, f32, f32, f32, vp, i64, vp, vp]
     lib.vist3a_gs_rasterize.argtypes = [vp, i64, i64, i64, i64, fp, vp, i64, vp, vp, vp, vp]
     lib.vist3a_vae_rmsnorm.argtypes = [vp, i64, vp, vp, i64, i64, i64, i32, vp]
-    lib.vist3a_softmax_rows.argtypes = [vp, vp, i64, i64, f32, vp]
+    lib.vist3a_softmax_rows.argtypes = [vp, vp, i64, i64, i64, f32, vp]
     lib.vist3a_time_interleave.argtypes = [vp, vp, i64, i64, i64, vp]
-    lib.vist3a_transpose_bf16.argtypes = [vp, i64, vp, i64, i64, vp]
+    lib.vist3a_transpose_bf16.argtypes = [vp, i64, vp, i64, i64, i64, vp]
     lib.vist3a_depth_to_space2_bf16.argtypes = [vp, vp, i64, i64, i64, i64, i64, vp]
     lib.vist3a_latent_to_ndhwc.argtypes = [vp, i32, vp, i64, i64, i64, vp]
     lib.vist3a_vae_frames_out.argtypes = [vp, i64, vp, i64, vp]
     lib.vist3a_resize_planes.argtypes = [vp, vp, i64, i64, i64, i64, i64, vp]
+    lib.vist3a_depth_conf.argtypes = [vp, i64, i64, vp, f32, vp, i64, vp]
+    lib.vist3a_quantile_workspace_bytes.restype = C.c_int64
+    lib.vist3a_quantile_workspace_bytes.argtypes = [i64]
+    lib.vist3a_quantile_f32.argtypes = [vp, i64, f32, vp, vp, i64, vp]
+    lib.vist3a_compact_rows_workspace_bytes.restype = C.c_int64
+    lib.vist3a_compact_rows_workspace_bytes.argtypes = [i64]
+    lib.vist3a_compact_rows.argtypes = [vp, vp, i32, i64, vp, i64, i64, vp, vp, vp, vp, vp, vp, i64, vp]
     _lib = lib
     return lib
 

@@ -55,13 +55,19 @@ int unpatchify_entry(const void*, int, long long, void*, int, long long, long lo
 int cfg_combine_entry(const void*, const void*, int, float, float*, long long, cudaStream_t);
 int axpby_entry(float*, int, const float* const*, const float*, long long, cudaStream_t);
 int vae_rmsnorm_entry(const void*, long long, const float*, void*, long long, long long, long long, int, cudaStream_t);
-int softmax_rows_entry(const float*, void*, long long, long long, float, cudaStream_t);
+int softmax_rows_entry(const float*, void*, long long, long long, long long, float, cudaStream_t);
 int time_interleave_entry(const void*, void*, long long, long long, long long, cudaStream_t);
-int transpose_bf16_entry(const void*, long long, void*, long long, long long, cudaStream_t);
+int transpose_bf16_entry(const void*, long long, void*, long long, long long, long long, cudaStream_t);
 int depth_to_space2_bf16_entry(const void*, void*, long long, long long, long long, long long, long long, cudaStream_t);
 int latent_to_ndhwc_entry(const void*, int, void*, long long, long long, long long, cudaStream_t);
 int vae_frames_out_entry(const float*, long long, float*, long long, cudaStream_t);
 int resize_planes_entry(const float*, float*, long long, long long, long long, long long, long long, cudaStream_t);
+int depth_conf_entry(const float*, long long, long long, const float*, float, float*, long long, cudaStream_t);
+long long quantile_workspace_bytes(long long);
+int quantile_entry(const float*, long long, float, float*, void*, long long, cudaStream_t);
+long long compact_rows_workspace_bytes(long long);
+int compact_rows_entry(const float*, const float*, int, long long, const float*, long long, long long, const float*, float*, float*, float*, long long*, void*,
+                       long long, cudaStream_t);
 
 char* last_error_buf() {
   static thread_local char buf[512] = {0};
@@ -173,7 +179,7 @@ using namespace v3a;
 extern "C" {
 
 const char* vist3a_last_error(void) { return last_error_buf(); }
-int vist3a_abi_version(void) { return 6; }
+int vist3a_abi_version(void) { return 7; }
 int64_t vist3a_launch_count(void) { return (int64_t)launch_counter().load(); }
 int vist3a_set_pdl(int32_t enable) { return set_pdl(enable); }
 
@@ -182,9 +188,13 @@ int vist3a_fmha_fwd(const vist3a_fmha_args* args, void* stream) { return fmha_en
 int vist3a_vae_rmsnorm(const void* x, int64_t ldx, const float* gamma, void* y, int64_t ldy, int64_t rows, int64_t C, int32_t silu, void* stream) {
   return vae_rmsnorm_entry(x, ldx, gamma, y, ldy, rows, C, silu, ST(stream));
 }
-int vist3a_softmax_rows(const float* s, void* p, int64_t rows, int64_t L, float scale, void* stream) { return softmax_rows_entry(s, p, rows, L, scale, ST(stream)); }
+int vist3a_softmax_rows(const float* s, void* p, int64_t rows, int64_t L, int64_t ldp, float scale, void* stream) {
+  return softmax_rows_entry(s, p, rows, L, ldp, scale, ST(stream));
+}
 int vist3a_time_interleave(const void* y, void* out, int64_t T, int64_t P, int64_t C, void* stream) { return time_interleave_entry(y, out, T, P, C, ST(stream)); }
-int vist3a_transpose_bf16(const void* in, int64_t ld_in, void* out, int64_t R, int64_t C, void* stream) { return transpose_bf16_entry(in, ld_in, out, R, C, ST(stream)); }
+int vist3a_transpose_bf16(const void* in, int64_t ld_in, void* out, int64_t ld_out, int64_t R, int64_t C, void* stream) {
+  return transpose_bf16_entry(in, ld_in, out, ld_out, R, C, ST(stream));
+}
 int vist3a_depth_to_space2_bf16(const void* in, void* out, int64_t n_img, int64_t h, int64_t w, int64_t C, int64_t ldo, void* stream) {
   return depth_to_space2_bf16_entry(in, out, n_img, h, w, C, ldo, ST(stream));
 }
@@ -192,6 +202,20 @@ int vist3a_latent_to_ndhwc(const void* z, int32_t z_dtype, void* out, int64_t C,
   return latent_to_ndhwc_entry(z, z_dtype, out, C, THW, ld, ST(stream));
 }
 int vist3a_vae_frames_out(const float* y, int64_t ld, float* out, int64_t THW, void* stream) { return vae_frames_out_entry(y, ld, out, THW, ST(stream)); }
+int vist3a_depth_conf(const float* feat, int64_t ld, int64_t C, const float* w, float bias, float* conf, int64_t n_pixels, void* stream) {
+  return depth_conf_entry(feat, ld, C, w, bias, conf, n_pixels, ST(stream));
+}
+int64_t vist3a_quantile_workspace_bytes(int64_t n) { return quantile_workspace_bytes(n); }
+int vist3a_quantile_f32(const float* x, int64_t n, float q, float* out, void* workspace, int64_t workspace_bytes, void* stream) {
+  return quantile_entry(x, n, q, out, workspace, workspace_bytes, ST(stream));
+}
+int64_t vist3a_compact_rows_workspace_bytes(int64_t n) { return compact_rows_workspace_bytes(n); }
+int vist3a_compact_rows(const float* conf, const float* threshold, int32_t use_threshold, int64_t n, const float* feats, int64_t ld_feats, int64_t C,
+                        const float* pts, float* out_feats, float* out_pts, float* out_damp, int64_t* count, void* workspace, int64_t workspace_bytes,
+                        void* stream) {
+  return compact_rows_entry(conf, threshold, use_threshold, n, feats, ld_feats, C, pts, out_feats, out_pts, out_damp, (long long*)count, workspace,
+                            workspace_bytes, ST(stream));
+}
 int vist3a_resize_planes(const float* in, float* out, int64_t planes, int64_t h_in, int64_t w_in, int64_t h_out, int64_t w_out, void* stream) {
   return resize_planes_entry(in, out, planes, h_in, w_in, h_out, w_out, ST(stream));
 }

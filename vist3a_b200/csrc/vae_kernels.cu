@@ -91,9 +91,9 @@ __global__ void __launch_bounds__(256) vae_rmsnorm_kernel(const __nv_bfloat16* _
 
 // p[r, :] = softmax(scale * s[r, :]) as bf16; s fp32 [rows, L] (the logits GEMM writes fp32), L % 4 == 0.  One block per row; the row is
 // read twice (online max + sum, then the normalised write): 4096 x 4096 fp32 per frame = 64 MB, L2 resident between the passes.
-__global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restrict__ s, __nv_bfloat16* __restrict__ p, int L, float scale) {
+__global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restrict__ s, __nv_bfloat16* __restrict__ p, int L, long long ldp, float scale) {
   const float* sr = s + (long long)blockIdx.x * L;
-  __nv_bfloat16* pr = p + (long long)blockIdx.x * L;
+  __nv_bfloat16* pr = p + (long long)blockIdx.x * ldp;
   float m = -INFINITY, sum = 0.f;
   for (int i = threadIdx.x * 4; i < L; i += 256 * 4) {
     const float4 v = *reinterpret_cast<const float4*>(sr + i);
@@ -143,9 +143,9 @@ __global__ void __launch_bounds__(256) time_interleave_kernel(const __nv_bfloat1
   }
 }
 
-// [R, C] (row stride ld_in) -> [C, R] (bf16), 32 x 32 tiles through shared memory: V^T for the P V GEMM of the mid-block attention
+// [R, C] (row stride ld_in) -> [C, R] (row stride ld_out; bf16), 32 x 32 tiles through shared memory: V^T for the P V GEMM of the mid-block attention
 __global__ void __launch_bounds__(256) transpose_bf16_kernel(const __nv_bfloat16* __restrict__ in, long long ld_in, __nv_bfloat16* __restrict__ out,
-                                                             long long R, int C) {
+                                                             long long ld_out, long long R, int C) {
   __shared__ __nv_bfloat16 tile[32][33];
   const long long r0 = (long long)blockIdx.x * 32;
   const int c0 = blockIdx.y * 32;
@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(256) transpose_bf16_kernel(const __nv_bfloat16
   for (int j = threadIdx.x >> 5; j < 32; j += 8) {
     const int c = c0 + j;
     const long long r = r0 + (threadIdx.x & 31);
-    if (r < R && c < C) out[(long long)c * R + r] = tile[threadIdx.x & 31][j];
+    if (r < R && c < C) out[(long long)c * ld_out + r] = tile[threadIdx.x & 31][j];
   }
 }
 
@@ -247,9 +247,10 @@ int vae_rmsnorm_entry(const void* x, long long ldx, const float* gamma, void* y,
   return VIST3A_OK;
 }
 
-int softmax_rows_entry(const float* s, void* p, long long rows, long long L, float scale, cudaStream_t st) {
-  V3A_REQUIRE(s && p && rows > 0 && rows <= 0x7fffffff && L > 0 && L % 4 == 0 && L <= 0x7fffffff, VIST3A_ERR_INVALID, "softmax_rows: L must be a positive multiple of 4");
-  softmax_rows_kernel<<<(unsigned)rows, 256, 0, st>>>(s, (__nv_bfloat16*)p, (int)L, scale);
+int softmax_rows_entry(const float* s, void* p, long long rows, long long L, long long ldp, float scale, cudaStream_t st) {
+  V3A_REQUIRE(s && p && rows > 0 && rows <= 0x7fffffff && L > 0 && L % 4 == 0 && L <= 0x7fffffff && ldp >= L && ldp % 4 == 0, VIST3A_ERR_INVALID,
+              "softmax_rows: L and the output row stride must be positive multiples of 4, stride >= L");
+  softmax_rows_kernel<<<(unsigned)rows, 256, 0, st>>>(s, (__nv_bfloat16*)p, (int)L, ldp, scale);
   V3A_CUDA_OK(cudaGetLastError());
   launch_counter().fetch_add(1);
   return VIST3A_OK;
@@ -263,9 +264,9 @@ int time_interleave_entry(const void* y, void* out, long long T, long long P, lo
   return VIST3A_OK;
 }
 
-int transpose_bf16_entry(const void* in, long long ld_in, void* out, long long R, long long C, cudaStream_t st) {
-  V3A_REQUIRE(in && out && R > 0 && C > 0 && ld_in >= C && (R + 31) / 32 <= 0x7fffffff && (C + 31) / 32 <= 65535, VIST3A_ERR_INVALID, "transpose_bf16: bad shape");
-  transpose_bf16_kernel<<<dim3((unsigned)((R + 31) / 32), (unsigned)((C + 31) / 32)), 256, 0, st>>>((const __nv_bfloat16*)in, ld_in, (__nv_bfloat16*)out, R, (int)C);
+int transpose_bf16_entry(const void* in, long long ld_in, void* out, long long ld_out, long long R, long long C, cudaStream_t st) {
+  V3A_REQUIRE(in && out && R > 0 && C > 0 && ld_in >= C && ld_out >= R && (R + 31) / 32 <= 0x7fffffff && (C + 31) / 32 <= 65535, VIST3A_ERR_INVALID, "transpose_bf16: bad shape");
+  transpose_bf16_kernel<<<dim3((unsigned)((R + 31) / 32), (unsigned)((C + 31) / 32)), 256, 0, st>>>((const __nv_bfloat16*)in, ld_in, (__nv_bfloat16*)out, ld_out, R, (int)C);
   V3A_CUDA_OK(cudaGetLastError());
   launch_counter().fetch_add(1);
   return VIST3A_OK;

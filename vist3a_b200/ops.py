@@ -698,13 +698,15 @@ def vae_rmsnorm(x: torch.Tensor, gamma: torch.Tensor, C: int, *, silu: bool = Tr
 
 
 def softmax_rows(s: torch.Tensor, scale: float, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """softmax(scale * s) per row: fp32 [rows, L] -> bf16 [rows, L]."""
+    """softmax(scale * s) per row: fp32 [rows, L] -> bf16 [rows, L] (`out` may have a padded row stride)."""
     _need_cuda(s, out)
     if s.dim() != 2 or s.dtype != torch.float32 or not s.is_contiguous():
         raise TypeError("softmax_rows: contiguous float32 [rows, L] expected")
     if out is None:
         out = torch.empty(s.shape, dtype=torch.bfloat16, device=s.device)
-    L.check(L.load().vist3a_softmax_rows(s.data_ptr(), out.data_ptr(), s.shape[0], s.shape[1], float(scale), _stream()))
+    if out.shape != s.shape or out.dtype != torch.bfloat16 or out.stride(1) != 1:
+        raise TypeError("softmax_rows: out must be bfloat16 [rows, L] with unit inner stride")
+    L.check(L.load().vist3a_softmax_rows(s.data_ptr(), out.data_ptr(), s.shape[0], s.shape[1], out.stride(0), float(scale), _stream()))
     return out
 
 
@@ -719,12 +721,13 @@ def time_interleave(y: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
 
 
 def transpose_bf16(x: torch.Tensor) -> torch.Tensor:
-    """[R, C] bf16 (unit inner stride, any row stride) -> contiguous [C, R]."""
+    """[R, C] bf16 (unit inner stride, any row stride) -> [C, R] with the row stride rounded up to 8 elements (a 16-byte TMA stride)."""
     _need_cuda(x)
     if x.dim() != 2 or x.dtype != torch.bfloat16 or x.stride(1) != 1:
         raise TypeError("transpose_bf16: 2-D bfloat16 with unit inner stride expected")
-    out = torch.empty((x.shape[1], x.shape[0]), dtype=torch.bfloat16, device=x.device)
-    L.check(L.load().vist3a_transpose_bf16(x.data_ptr(), x.stride(0), out.data_ptr(), x.shape[0], x.shape[1], _stream()))
+    R = x.shape[0]
+    out = torch.empty((x.shape[1], (R + 7) // 8 * 8), dtype=torch.bfloat16, device=x.device)[:, :R]
+    L.check(L.load().vist3a_transpose_bf16(x.data_ptr(), x.stride(0), out.data_ptr(), out.stride(0), R, x.shape[1], _stream()))
     return out
 
 
@@ -767,3 +770,50 @@ def resize_planes(x: torch.Tensor, h_out: int, w_out: int) -> torch.Tensor:
     planes = x.numel() // (x.shape[-1] * x.shape[-2])
     L.check(L.load().vist3a_resize_planes(x.data_ptr(), out.data_ptr(), planes, x.shape[-2], x.shape[-1], h_out, w_out, _stream()))
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# confidence-quantile branches of the stitched decoder (render_conf / opacity_conf)
+# ------------------------------------------------------------------------------------------------
+def depth_conf(feat: torch.Tensor, w: torch.Tensor, bias: float) -> torch.Tensor:
+    """conf[p] = 1 + exp(feat[p] . w + bias): feat [P, C] fp32 rows (unit inner stride) -> [P] fp32."""
+    _need_cuda(feat, w)
+    if feat.dim() != 2 or feat.dtype != torch.float32 or feat.stride(1) != 1 or w.dtype != torch.float32:
+        raise TypeError("depth_conf: float32 [P, C] rows and a float32 weight vector expected")
+    out = torch.empty((feat.shape[0],), dtype=torch.float32, device=feat.device)
+    L.check(L.load().vist3a_depth_conf(feat.data_ptr(), feat.stride(0), feat.shape[1], w.data_ptr(), float(bias), out.data_ptr(), feat.shape[0], _stream()))
+    return out
+
+
+def quantile(x: torch.Tensor, q: float) -> torch.Tensor:
+    """torch.quantile(x.flatten(), q) (linear interpolation) as a 1-element device tensor; no host synchronisation."""
+    _need_cuda(x)
+    if x.dtype != torch.float32 or not x.is_contiguous():
+        raise TypeError("quantile: contiguous float32 expected")
+    lib = L.load()
+    n = x.numel()
+    ws = torch.empty((int(lib.vist3a_quantile_workspace_bytes(n)),), dtype=torch.uint8, device=x.device)
+    out = torch.empty((1,), dtype=torch.float32, device=x.device)
+    L.check(lib.vist3a_quantile_f32(x.data_ptr(), n, float(q), out.data_ptr(), ws.data_ptr(), ws.numel(), _stream()))
+    return out
+
+
+def compact_rows(conf: torch.Tensor, threshold: torch.Tensor, feats: torch.Tensor, pts: torch.Tensor, *, feat_dim: int, use_threshold: bool = True,
+                 want_damp: bool = False):
+    """Rows with conf > threshold (all rows if not use_threshold), in order: dict(feats [M, C], pts [M, 3], damp [M] or None, count = M).
+    Reading M synchronises the stream (the output size is data dependent, as the boolean-mask gather is in the reference)."""
+    _need_cuda(conf, threshold, feats, pts)
+    n = conf.shape[0]
+    f32, dev = torch.float32, conf.device
+    if conf.dtype != f32 or not conf.is_contiguous() or feats.dtype != f32 or feats.stride(1) != 1 or pts.dtype != f32 or not pts.is_contiguous() or feats.shape[0] != n:
+        raise ValueError("compact_rows: fp32 contiguous conf / points and unit-stride fp32 feature rows expected")
+    lib = L.load()
+    ws = torch.empty((int(lib.vist3a_compact_rows_workspace_bytes(n)),), dtype=torch.uint8, device=dev)
+    of = torch.empty((n, feat_dim), dtype=f32, device=dev)
+    op = torch.empty((n, 3), dtype=f32, device=dev)
+    od = torch.empty((n,), dtype=f32, device=dev) if want_damp else None
+    cnt = torch.zeros((1,), dtype=torch.int64, device=dev)
+    L.check(lib.vist3a_compact_rows(conf.data_ptr(), threshold.data_ptr(), int(use_threshold), n, feats.data_ptr(), feats.stride(0), feat_dim, pts.data_ptr(),
+                                    of.data_ptr(), op.data_ptr(), _ptr(od), cnt.data_ptr(), ws.data_ptr(), ws.numel(), _stream()))
+    m = int(cnt.item())
+    return dict(feats=of[:m], pts=op[:m], damp=None if od is None else od[:m], count=m)

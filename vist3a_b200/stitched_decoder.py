@@ -342,8 +342,10 @@ class StitchVAE3DB200(torch.nn.Module):
                         w[tag + f"rf{r}.u{u}c{c}.b"] = f32(sd[p + f"resConfUnit{u}.conv{c}.bias"])
             w[tag + "oc1.w"], w[tag + "oc1.b"] = f32(_conv_w(sd[head + "scratch.output_conv1.weight"])), f32(sd[head + "scratch.output_conv1.bias"])
             w[tag + "oc2a.w"], w[tag + "oc2a.b"] = f32(_conv_w(sd[head + "scratch.output_conv2.0.weight"])), f32(sd[head + "scratch.output_conv2.0.bias"])
-        w["dh.oc2b.w"] = f32(sd[E + "depth_head.scratch.output_conv2.2.weight"][0].flatten())  # depth channel only
+        w["dh.oc2b.w"] = f32(sd[E + "depth_head.scratch.output_conv2.2.weight"][0].flatten())  # depth channel
         self._depth_b = float(sd[E + "depth_head.scratch.output_conv2.2.bias"][0])
+        w["dh.conf.w"] = f32(sd[E + "depth_head.scratch.output_conv2.2.weight"][1].flatten())  # confidence channel (render_conf / opacity_conf only)
+        self._conf_b = float(sd[E + "depth_head.scratch.output_conv2.2.bias"][1])
         g = E + "gaussian_param_head."
         w["gh.oc2b.w"] = f32(sd[g + "scratch.output_conv2.2.weight"].flatten(1))
         w["gh.oc2b.b"] = f32(sd[g + "scratch.output_conv2.2.bias"])
@@ -671,7 +673,38 @@ class StitchVAE3DB200(torch.nn.Module):
         # --- fused depth activation + unprojection + Gaussian adapter
         o = ops.gaussian_epilogue(dfeat.view(BV * H * W, -1), w["dh.oc2b.w"], self._depth_b, raw, cams["extr"], cams["intr"], w["sh_mask"], BV, H, W)
         N = V * H * W
-        if cfg.voxelize:
+        conf_mask, valid_counts = None, None
+        if (cfg.render_conf or cfg.opacity_conf) and cfg.voxelize:
+            raise NotImplementedError("render_conf / opacity_conf together with voxelize: the reference indexes the damping factor with the pixel mask "
+                                      "against voxel-sized tensors (anysplat_stitched.py:463-467), which only works with voxelize off")
+        if cfg.render_conf or cfg.opacity_conf:
+            # confidence-quantile branches (anysplat_stitched.py:381-387, 442-455, 463-467): the quantile is taken over ALL pixels of the call;
+            # the kept pixels of every batch element are compacted in (view, row, column) order and padded to the largest count
+            if cfg.opacity_conf and B != 1:
+                raise ValueError("opacity_conf: the reference's broadcast (anysplat_stitched.py:465-467) only works for one batch element")
+            Cr = cfg.raw_gs_dim
+            conf = ops.depth_conf(dfeat.view(BV * H * W, -1), w["dh.conf.w"], self._conf_b)
+            qv = ops.quantile(conf, cfg.conf_threshold)
+            rawb, ptsb, confb = raw.view(B, N, -1), o["means"].view(B, N, 3), conf.view(B, N)
+            kept = [ops.compact_rows(confb[b], qv, rawb[b], ptsb[b], feat_dim=Cr, use_threshold=cfg.render_conf, want_damp=cfg.opacity_conf) for b in range(B)]
+            valid_counts = [k["count"] for k in kept]
+            conf_mask = (conf.view(B, V, H, W) > qv) if cfg.render_conf else None
+            N = max(valid_counts)
+            if B == 1:
+                vp, vf = kept[0]["pts"], kept[0]["feats"]
+            else:
+                vp = torch.full((B, N, 3), -1e4, dtype=torch.float32, device=dev)
+                vf = torch.full((B, N, Cr), -1e10, dtype=torch.float32, device=dev)
+                for b, k in enumerate(kept):
+                    vp[b, :k["count"]] = k["pts"]
+                    vf[b, :k["count"]] = k["feats"]
+            depth_out = o["depth"]
+            o = ops.gaussian_adapter(vp.reshape(B * N, 3), vf.reshape(B * N, Cr), w["sh_mask"]) | dict(depth=depth_out, scene_sum=o["scene_sum"])
+            if cfg.opacity_conf:   # opacity * sigmoid(depth_conf - quantile) of the kept pixels
+                op = o["opacities"].view(1, -1)
+                ops.fma_rows(op, kept[0]["damp"].view(1, -1), torch.zeros_like(op), out=op)
+            del kept, vp, vf
+        elif cfg.voxelize:
             # voxelised fusion per batch element, padded to the largest voxel count (anysplat_stitched.py:419-455), then the adapter
             Cr = cfg.raw_gs_dim
             rawb, ptsb = raw.view(B, N, -1), o["means"].view(B, N, 3)
@@ -698,8 +731,9 @@ class StitchVAE3DB200(torch.nn.Module):
             gaussians=gauss,
             pred_pose_enc_list=pose_list,
             pred_context_pose=dict(extrinsic=cams["c2w"].view(B, V, 4, 4), intrinsic=cams["intr_norm"].view(B, V, 3, 3)),
-            depth_dict=dict(depth=o["depth"].view(B, V, H, W, 1), conf_valid_mask=torch.ones((B, V, H, W), dtype=torch.bool, device=dev)),
-            infos=dict(scene_scale=scene_scale, voxelize_ratio=float(N) / (H * W * V)),
+            depth_dict=dict(depth=o["depth"].view(B, V, H, W, 1),
+                            conf_valid_mask=conf_mask if conf_mask is not None else torch.ones((B, V, H, W), dtype=torch.bool, device=dev)),
+            infos=dict(scene_scale=scene_scale, voxelize_ratio=float(N) / (H * W * V), **({"valid_counts": valid_counts} if valid_counts is not None else {})),
             distill_infos=None,
             last_pred_pose_enc=pose_list[-1],
         )

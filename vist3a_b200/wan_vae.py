@@ -157,8 +157,9 @@ class WanVAEDecoderB200(torch.nn.Module):
         z = self.config.z_dim
         # post_quant_conv (1x1x1 over the z latent channels) as a GEMM over the 64-wide zero-padded latent rows
         pq = sd["post_quant_conv.weight"].detach().float().reshape(z, z)
-        w["post_quant_conv.w"] = F.pad(pq, (0, _ld(z) - z)).to(dev, torch.bfloat16).contiguous()
-        w["post_quant_conv.b"] = sd["post_quant_conv.bias"].detach().float().to(dev).contiguous()
+        z8 = (z + 7) // 8 * 8                                                # output rows padded to the GEMM's 8-column granularity (zero rows)
+        w["post_quant_conv.w"] = F.pad(pq, (0, _ld(z) - z, 0, z8 - z)).to(dev, torch.bfloat16).contiguous()
+        w["post_quant_conv.b"] = F.pad(sd["post_quant_conv.bias"].detach().float(), (0, z8 - z)).to(dev).contiguous()
         conv("decoder.conv_in")
         for r in (0, 1):
             res(f"decoder.mid_block.resnets.{r}")
@@ -221,7 +222,7 @@ class WanVAEDecoderB200(torch.nn.Module):
         qkv = ops.gemm(n.view(-1, ld)[:, :C], w[p + ".to_qkv.w"], w[p + ".to_qkv.b"])          # [T*HW, 3C] bf16
         att = torch.empty((T * HW, C), dtype=torch.bfloat16, device=x.device)
         logits = torch.empty((HW, HW), dtype=torch.float32, device=x.device)
-        probs = torch.empty((HW, HW), dtype=torch.bfloat16, device=x.device)
+        probs = torch.empty((HW, (HW + 7) // 8 * 8), dtype=torch.bfloat16, device=x.device)[:, :HW]   # row stride: a 16-byte multiple (TMA)
         for t in range(T):
             f = qkv[t * HW:(t + 1) * HW]
             ops.gemm(f[:, :C], f[:, C:2 * C], out=logits)                                       # q k^T
@@ -259,7 +260,7 @@ class WanVAEDecoderB200(torch.nn.Module):
         x = ops.latent_to_ndhwc(z.to(self._dev), _ld(zc))                                        # [T', h, w, 64]
         T, h, wd, ldz = x.shape
         pq = torch.zeros((T, h, wd, ldz), dtype=torch.bfloat16, device=self._dev)                # padding channels stay zero (conv_in operand)
-        ops.gemm(x.view(-1, ldz), w["post_quant_conv.w"], w["post_quant_conv.b"], out=pq.view(-1, ldz)[:, :zc])
+        ops.gemm(x.view(-1, ldz), w["post_quant_conv.w"], w["post_quant_conv.b"], out=pq.view(-1, ldz)[:, :w["post_quant_conv.w"].shape[0]])
         ups, c0 = decoder_layout(cfg)
         x = self._conv(pq, "decoder.conv_in", zc)
         x = self._res_block(x, "decoder.mid_block.resnets.0", c0, c0)
