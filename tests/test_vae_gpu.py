@@ -40,7 +40,7 @@ def test_tiny_vae_decode_matches_reference_golden():
         m = _engine(sd, cfg)
         out = m.decode(c["latent"].cuda(), return_dict=False)[0]
         torch.cuda.synchronize()
-        assert _lib.launch_count() - n0 > 80
+        assert _lib.launch_count() - n0 > 60
         want = c["decoded"]
         assert out.shape == want.shape and out.dtype == torch.float32
         rel, mx = _rel(out, want), float((out.cpu() - want).abs().max())

@@ -35,6 +35,7 @@ struct FmhaPairParams {
   float scale_log2;        // scale * log2(e)
   const float* row_scale;  // optional per-(batch, query row) positive factor on the logits
   long long* trace;        // debug (v3a_debug_fmha_pair_trace): clock64 stamps of CTA (0,0,0), normally null
+  uint32_t zero;           // 0 (a value ptxas cannot fold: scheduling aid of the speculative softmax)
 };
 
 // debug hook (tools/fmha_pair_trace.py), off unless armed: [step][tile][8] stamps of the leader CTA of cluster 0:
@@ -47,7 +48,7 @@ extern "C" void v3a_debug_fmha_pair_trace(void* buf) { g_pair_trace.store(reinte
     if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (j) < 64) p.trace[((j) * 2 + (i)) * 8 + (slot)] = clock64(); \
   } while (0)
 
-template <int QT_, int SPLIT_, int POLY_>
+template <int QT_, int SPLIT_, int POLY_, int FAST_ = 0>
 struct FmhaPairCfg {
   static constexpr int D = 128, BQ = 128, BKV = 128;
   static constexpr int QT = QT_;                       // 128-row query tiles per CTA
@@ -64,7 +65,9 @@ struct FmhaPairCfg {
   static constexpr int V_HALF_BYTES = BKV * 128;       // 128 keys x this CTA's 64 head-dim columns = 16 KB
   static constexpr int ST = 4;                         // ring stages of K and of V
   static constexpr int NH = SPLIT == 1 ? 2 : 1;        // P(j) is handed to the MMA warp in NH key halves (one thread per row: after 64 keys each)
-  static constexpr int NBARS = 1 + 4 * ST + 8 * QT;    // q_full | k_full, k_empty, v_full, v_empty | per tile: s_full[2], p_full[2][2], pv_done[2]
+  static constexpr int NBARS = 1 + 4 * ST + 8 * QT + 2 * QT;   // q_full | k_full, k_empty, v_full, v_empty | per tile: s_full[2], p_full[2][2], pv_done[2] | pvh_done[2]
+  static constexpr bool FAST = FAST_ != 0;             // speculative (stale-maximum) softmax in 64-column half-steps (fmha_math.cuh), one thread per row
+  static_assert(!FAST || (SPLIT_ == 1 && QT_ == 2), "the speculative softmax runs one thread per row on two tiles per CTA");
   static constexpr int XCH_BYTES = 2 * QT * SPLIT * 128 * 4;  // [step parity][tile][slice][row] fp32
   static constexpr int SMEM_BYTES = QT * Q_TILE_BYTES + ST * (K_HALF_BYTES + V_HALF_BYTES) + 1024 + 8 * NBARS + 16 + XCH_BYTES;
   static constexpr uint32_t TILE_COLS = 256, TM_S = 0, S_STRIDE = 128, TM_O = NSB * 128;
@@ -73,11 +76,11 @@ struct FmhaPairCfg {
   static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 };
 
-template <int QT_, int SPLIT_, int POLY_>
+template <int QT_, int SPLIT_, int POLY_, int FAST_ = 0>
 __global__ void __launch_bounds__(128 + QT_ * 128 * SPLIT_, 1)
 fmha_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                  const __grid_constant__ CUtensorMap tmO, const FmhaPairParams p) {
-  using Cfg = FmhaPairCfg<QT_, SPLIT_, POLY_>;
+  using Cfg = FmhaPairCfg<QT_, SPLIT_, POLY_, FAST_>;
   constexpr int QT = Cfg::QT, NSB = Cfg::NSB, NH = Cfg::NH, SPLIT = Cfg::SPLIT, HC = Cfg::HC, OC = Cfg::OC, ST = Cfg::ST, BKV = Cfg::BKV, D = Cfg::D;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -94,6 +97,7 @@ fmha_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   auto s_full = [&](int i, int b) { return bar_base + 8u * (1 + 4 * ST + 8 * i + b); };
   auto p_full = [&](int i, int b, int hh) { return bar_base + 8u * (1 + 4 * ST + 8 * i + 2 + 2 * b + hh); };
   auto pv_done = [&](int i, int b) { return bar_base + 8u * (1 + 4 * ST + 8 * i + 6 + b); };
+  auto pvh_done = [&](int i, int b) { return bar_base + 8u * (1 + 4 * ST + 8 * QT + 2 * i + b); };   // first key half of P_i(j) V(j) has completed
   const uint32_t tmem_slot = bar_base + 8u * Cfg::NBARS;
   const uint32_t xch_base = tmem_slot + 16u;
 
@@ -125,6 +129,7 @@ fmha_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         mbar_init(s_full(i, b), 1);
         for (int hh = 0; hh < 2; ++hh) mbar_init(p_full(i, b, hh), 2 * 4 * SPLIT);   // one arrival per softmax warp of the tile in BOTH CTAs (leader's copy)
         mbar_init(pv_done(i, b), 1);
+        mbar_init(pvh_done(i, b), 1);
       }
     }
     fence_barrier_init();
@@ -213,6 +218,8 @@ fmha_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           if (hh == NH - 1) {
             umma_commit_2sm_mc(pv_done(i, j & 1), 3);
             if (i == QT - 1) umma_commit_2sm_mc(v_empty(vs), 3);
+          } else if (Cfg::FAST) {
+            umma_commit_2sm_mc(pvh_done(i, j & 1), 3);
           }
         }
         __syncwarp();
@@ -254,6 +261,91 @@ fmha_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     float l_run = 0.0f;                              // running sum of exp2((s - m_run) * c) over this thread's columns
     const float c = (p.row_scale && row < p.len_q) ? p.scale_log2 * p.row_scale[(long long)batch * p.len_q + row] : p.scale_log2;
     const uint64_t cc2 = pack2(c, c);
+    if constexpr (Cfg::FAST) {
+      // ---- speculative softmax: 64-column half-steps against the stale running maximum; each half of P(j) is handed to the tensor pipe as
+      //      soon as it is stored (fmha_sm100.cu runs the same scheme on one CTA) ----
+      float nmc = 0.0f;
+      uint64_t mc2 = 0ull;
+      for (int j = 0; j < n_kv; ++j) {
+        const int b = j & 1;
+        mbar_wait(s_full(i, b), (uint32_t)(j >> 1) & 1u);
+        tc_fence_after();
+        const bool tr = wq == 0 && lane == 0;
+        if (tr) PAIR_TRACE(j, i, 2);
+        const uint32_t p_addr = lane_base + Cfg::TM_S;
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          uint32_t r[64];
+          tmem_ld_x32(p_addr + (uint32_t)(hh * 64), r);
+          tmem_ld_x32(p_addr + (uint32_t)(hh * 64) + 32u, r + 32);
+          tmem_ld_wait();
+          if (tr && hh == 0) PAIR_TRACE(j, i, 3);
+          const int valid = p.len_kv - j * BKV - hh * 64;
+          if (valid < 64) {
+#pragma unroll
+            for (int k = 0; k < 64; ++k)
+              if (k >= valid) r[k] = 0xff800000u;  // -inf
+          }
+          if (j == 0 && hh == 0) {   // first scores of the row: the reference maximum is their maximum
+            float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+            for (int k = 0; k < 64; k += 8) {
+#pragma unroll
+              for (int u = 0; u < 4; ++u) mx[u] = fmaxf(fmaxf(mx[u], __uint_as_float(r[k + 2 * u])), __uint_as_float(r[k + 2 * u + 1]));
+            }
+            m_run = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+            nmc = -m_run * c;
+            mc2 = pack2(nmc, nmc);
+          }
+          uint32_t pk[32];
+          uint64_t hsum[2] = {0ull, 0ull};
+          const float m_half = exp_half64<Cfg::POLY>(r, cc2, mc2, hsum, pk, p.zero);
+          const bool need = (m_half - m_run) * c > 8.0f;
+          if (__any_sync(0xffffffffu, need)) {
+            // (rare) the stale maximum is too small for some row of this warp: rescale what has been accumulated, redo the half-step
+            const float f = need ? ex2_approx((m_run - m_half) * c) : 1.0f;
+            if (need) m_run = m_half;
+            l_run *= f;
+            if (j >= 1 || hh > 0) {
+              // O holds P(0..j-1) V [+ the first half of P(j) V, handed over already]: those products must have completed; the second half
+              // of P(j) V is not issued before this warp arrives on p_full, so O is quiescent afterwards
+              if (j >= 1) mbar_wait(pv_done(i, (j - 1) & 1), (uint32_t)((j - 1) >> 1) & 1u);
+              if (hh > 0) mbar_wait(pvh_done(i, b), (uint32_t)(j >> 1) & 1u);
+              tc_fence_after();
+#pragma unroll 1
+              for (int cb = 0; cb < D / 16; ++cb) {
+                uint32_t o[16];
+                tmem_ld_x16(o_addr + (uint32_t)(cb * 16), o);
+                tmem_ld_wait();
+#pragma unroll
+                for (int k = 0; k < 16; ++k) o[k] = __float_as_uint(__uint_as_float(o[k]) * f);
+                tmem_st_x16(o_addr + (uint32_t)(cb * 16), o);
+              }
+              tmem_st_wait();
+            }
+            nmc = -m_run * c;
+            mc2 = pack2(nmc, nmc);
+            hsum[0] = hsum[1] = 0ull;
+            exp_half64_exact(r, cc2, mc2, hsum, pk);
+          }
+          {
+            float s0, s1, s2, s3;
+            unpack2(hsum[0], s0, s1);
+            unpack2(hsum[1], s2, s3);
+            l_run += (s0 + s1) + (s2 + s3);
+          }
+          if (tr && hh == 1) PAIR_TRACE(j, i, 5);
+          tmem_st_x32(p_addr + (uint32_t)(hh * 32), pk);
+          tmem_st_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (tr && hh == 1) PAIR_TRACE(j, i, 6);
+          if (lane == 0) {
+            if (leader) mbar_arrive(p_full(i, b, hh)); else mbar_arrive_remote(p_full(i, b, hh), 0);
+          }
+        }
+      }
+    } else
     for (int j = 0; j < n_kv; ++j) {
       const int b = j & 1, sb = j % NSB;
       mbar_wait(s_full(i, b), (uint32_t)(j >> 1) & 1u);
@@ -430,9 +522,9 @@ static int make_map4(CUtensorMap* tm, const void* ptr, long long B, long long H,
   return encode_tensor_map(tm, ptr, 2, false, 4, dims, strides, box, true);
 }
 
-template <int QT_, int SPLIT_, int POLY_>
+template <int QT_, int SPLIT_, int POLY_, int FAST_ = 0>
 static int launch_fmha_pair(const vist3a_fmha_args& a, cudaStream_t stream) {
-  using Cfg = FmhaPairCfg<QT_, SPLIT_, POLY_>;
+  using Cfg = FmhaPairCfg<QT_, SPLIT_, POLY_, FAST_>;
   CUtensorMap tmQ, tmK, tmV, tmO;
   int rc;
   if ((rc = make_map4(&tmQ, a.Q, a.batch, a.heads, a.len_q, 128, a.q_bs, a.q_rs, a.q_hs, Cfg::BQ))) return rc;
@@ -445,7 +537,8 @@ static int launch_fmha_pair(const vist3a_fmha_args& a, cudaStream_t stream) {
   p.scale_log2 = a.scale * 1.4426950408889634f;
   p.row_scale = a.q_row_scale;
   p.trace = g_pair_trace.load(std::memory_order_relaxed);
-  auto kern = fmha_pair_kernel<QT_, SPLIT_, POLY_>;
+  p.zero = 0u;
+  auto kern = fmha_pair_kernel<QT_, SPLIT_, POLY_, FAST_>;
   static std::atomic<unsigned long long> attr_done{0};
   V3A_CUDA_OK(ensure_dynamic_smem(kern, Cfg::SMEM_BYTES, attr_done));
   const long long rows_per_cluster = 2 * Cfg::QT * Cfg::BQ;
@@ -456,17 +549,17 @@ static int launch_fmha_pair(const vist3a_fmha_args& a, cudaStream_t stream) {
 }
 
 // head_dim 128 on CTA pairs; `variant` (A/B measurements): 0 = default: two query tiles per CTA, one thread per query row, P handed over in
-// two key halves, all exponentials on the MUFU; 1 / 2 = the same with 1 / 2 of every 8 column pairs on the FMA pipe; 3 = two tiles, two
-// threads per row; 4 = two tiles, two threads per row, 2 of 8 on the FMA pipe; 5 = one tile per CTA, 4 threads per row
+// two key halves, all exponentials on the MUFU; 1 / 2 = the same with 1 / 2 of every 8 column pairs on the FMA pipe; 3 = speculative
+// softmax (stale maximum, 64-column half-steps), all MUFU; 4 = the same with 2 of 8 on the FMA pipe; 5 / 6 = default with 3 / 4 of 8; 7 = speculative, 3 of 8
 int fmha_pair_entry(const vist3a_fmha_args& a, int variant, cudaStream_t stream) {
   switch (variant) {
     case 1: return launch_fmha_pair<2, 1, 1>(a, stream);
     case 2: return launch_fmha_pair<2, 1, 2>(a, stream);
-    case 3: return launch_fmha_pair<2, 2, 0>(a, stream);
-    case 4: return launch_fmha_pair<2, 2, 2>(a, stream);
+    case 3: return launch_fmha_pair<2, 1, 0, 1>(a, stream);
+    case 4: return launch_fmha_pair<2, 1, 2, 1>(a, stream);
     case 5: return launch_fmha_pair<2, 1, 3>(a, stream);
     case 6: return launch_fmha_pair<2, 1, 4>(a, stream);
-    case 7: return launch_fmha_pair<2, 2, 3>(a, stream);
+    case 7: return launch_fmha_pair<2, 1, 3, 1>(a, stream);
     default: return launch_fmha_pair<2, 1, 0>(a, stream);
   }
 }

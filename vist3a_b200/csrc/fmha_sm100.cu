@@ -36,6 +36,8 @@ struct FmhaParams {
   int single_issuer;       // one MMA-issuing warp for both query tiles (flags bit 2)
   int direct_store;        // per-thread output stores instead of shared memory + bulk tensor store (flags bit 6, A/B)
   long long* trace;        // debug: 32 clock64 stamps / phase sums per CTA (v3a_debug_fmha_trace), normally null
+  uint32_t zero;           // 0 (a value ptxas cannot fold: scheduling aid of the speculative softmax)
+  int skip_softmax;        // debug (flags bit 12): the softmax warps only hand the barriers on (garbage output): tensor-side ceiling
 };
 
 // debug hook (tools/fmha_trace.py), off unless armed: process-wide by design, read once per launch
@@ -50,7 +52,7 @@ extern "C" void v3a_debug_fmha_trace(void* buf) { g_fmha_trace.store(reinterpret
     if (p.trace) p.trace[((long long)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 32 + (slot)] = clock64(); \
   } while (0)
 
-template <int D, int BKV_, int POLY_, int SPLIT_>
+template <int D, int BKV_, int POLY_, int SPLIT_, int FAST_ = 0>
 struct FmhaCfg {
   static constexpr int BQ = 128, QT = 2;             // two query tiles per CTA
   static constexpr int BKV = BKV_;                   // keys per step
@@ -62,7 +64,7 @@ struct FmhaCfg {
   static constexpr int Q_TILE_BYTES = SLABS * Q_SLAB_BYTES;
   static constexpr int KV_TILE_BYTES = SLABS * KV_SLAB_BYTES;   // 16 KB either way
   static constexpr int KV_STAGES = KV_TILE_BYTES > 16384 ? 2 : 4;
-  static constexpr int PT = NSB + 1 + 4;             // barriers per query tile: s_full[NSB], s_free, p_full[2], pv_done[2]
+  static constexpr int PT = NSB + 1 + 4 + 4;         // barriers per query tile: s_full[NSB], s_free, p_full[2], pv_done[2], p_half[2], pvh_done[2]
   static constexpr int NBARS = 1 + 4 * KV_STAGES + 2 * PT;
   static constexpr int SPLIT = SPLIT_;               // threads per query row (softmax warpgroups per tile)
   static constexpr int THREADS = 128 + 256 * SPLIT;
@@ -78,15 +80,20 @@ struct FmhaCfg {
   static constexpr uint32_t TM_O = ALIAS ? 128 : 192;
   static_assert(D == 128 || BKV == 128, "d=64 runs 128-key steps");
   static constexpr int POLY = POLY_;                     // of every 8 column pairs, this many use the FMA-pipe exp2
+  static constexpr bool FAST = FAST_ != 0;               // speculative (stale-maximum) softmax in 64-column half-steps, one thread per row
+  // aliased 128-key steps (S single-buffered: softmax -> P V -> next Q K^T is a serial chain per tile): the first 64 keys of P(j) are handed
+  // to the tensor pipe while the other 64 are still being exponentiated
+  static constexpr bool HANDOFF = FAST && ALIAS && BKV_ == 128;
+  static_assert(!FAST || SPLIT_ == 1, "the speculative softmax runs one thread per query row");
   static_assert(TM_O + D <= TILE_COLS, "TMEM budget");
 };
 
 
-template <int D, int BKV_, int POLY_, int SPLIT_>
+template <int D, int BKV_, int POLY_, int SPLIT_, int FAST_ = 0>
 __global__ void __launch_bounds__(128 + 256 * SPLIT_, 1)
 fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO, const FmhaParams p) {
-  using Cfg = FmhaCfg<D, BKV_, POLY_, SPLIT_>;
+  using Cfg = FmhaCfg<D, BKV_, POLY_, SPLIT_, FAST_>;
   constexpr int SPLIT = Cfg::SPLIT;
   constexpr int HC = Cfg::HC;
   constexpr int ST = Cfg::KV_STAGES;
@@ -109,6 +116,8 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   auto s_free = [&](int i) { return bar_base + 8u * (1 + 4 * ST + i * Cfg::PT + NSB); };
   auto p_full = [&](int i, int b) { return bar_base + 8u * (1 + 4 * ST + i * Cfg::PT + NSB + 1 + b); };
   auto pv_done = [&](int i, int b) { return bar_base + 8u * (1 + 4 * ST + i * Cfg::PT + NSB + 3 + b); };
+  auto p_half = [&](int i, int b) { return bar_base + 8u * (1 + 4 * ST + i * Cfg::PT + NSB + 5 + b); };
+  auto pvh_done = [&](int i, int b) { return bar_base + 8u * (1 + 4 * ST + i * Cfg::PT + NSB + 7 + b); };   // first half of P(j) V(j) has completed
   const uint32_t tmem_slot = bar_base + 8u * Cfg::NBARS;
   const uint32_t xch_base = tmem_slot + 16u;  // float [2 parities][2 tiles][2 halves][128 rows]
 
@@ -148,6 +157,8 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       for (int b = 0; b < 2; ++b) {
         mbar_init(p_full(i, b), 4 * SPLIT);
         mbar_init(pv_done(i, b), 1);
+        mbar_init(p_half(i, b), 4 * SPLIT);
+        mbar_init(pvh_done(i, b), 1);
       }
     }
     fence_barrier_init();
@@ -222,19 +233,28 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
         __syncwarp();
       };
-      auto issue_pv = [&](int i, int j, int s, uint32_t ph) {
-        mbar_wait(v_full(s), ph);
+      // part: -1 = the whole P(j) V(j); 0 / 1 = its first / second 64 keys (HANDOFF: the halves of P arrive separately)
+      auto issue_pv = [&](int i, int j, int s, uint32_t ph, int part = -1) {
+        if (part <= 0) mbar_wait(v_full(s), ph);
         tc_fence_after();
         if (elect_one()) {
           const uint32_t t_base = tmem_base + (uint32_t)i * Cfg::TILE_COLS;
           const uint32_t p_tmem = t_base + Cfg::TM_P + (uint32_t)(j & 1) * Cfg::P_STRIDE;
           // V tile: kv rows at a 128 B pitch (K dimension), 64-wide head-dim slabs LBO apart (MN dimension)
           const uint64_t bdesc = make_smem_desc_sw128(smem_v(s), 1024, Cfg::KV_SLAB_BYTES);
+          constexpr int KS = BKV / 16;
+          const int k_lo = part == 1 ? KS / 2 : 0, k_hi = part == 0 ? KS / 2 : KS;
 #pragma unroll
-          for (int kk = 0; kk < BKV / 16; ++kk)
-            umma_f16_ts(t_base + Cfg::TM_O, p_tmem + (uint32_t)(kk * 8), bdesc + (uint64_t)((kk * 2048) >> 4), idesc_pv, (j | kk) ? 1u : 0u);
-          umma_commit(pv_done(i, j & 1));
-          umma_commit(v_empty(s));
+          for (int kk = 0; kk < KS; ++kk) {
+            if (kk >= k_lo && kk < k_hi)
+              umma_f16_ts(t_base + Cfg::TM_O, p_tmem + (uint32_t)(kk * 8), bdesc + (uint64_t)((kk * 2048) >> 4), idesc_pv, (j | kk) ? 1u : 0u);
+          }
+          if (part != 0) {
+            umma_commit(pv_done(i, j & 1));
+            umma_commit(v_empty(s));
+          } else {
+            umma_commit(pvh_done(i, j & 1));
+          }
         }
         __syncwarp();
       };
@@ -318,10 +338,17 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             issue_qk(i, j + 1, qs, qph);
             adv(qs, qph);
           }
+          if constexpr (Cfg::HANDOFF) {
+            mbar_wait(p_half(i, j & 1), (uint32_t)(j >> 1) & 1u);
+            tc_fence_after();
+            if (trm) { const long long t2 = clock64(); mm_wait += t2 - mt; mt = t2; }
+            issue_pv(i, j, vs, vph, 0);
+            if (trm) { const long long t2 = clock64(); mm_issue += t2 - mt; mt = t2; }
+          }
           mbar_wait(p_full(i, j & 1), (uint32_t)(j >> 1) & 1u);
           tc_fence_after();
           if (trm) { const long long t2 = clock64(); mm_wait += t2 - mt; mt = t2; }
-          issue_pv(i, j, vs, vph);
+          issue_pv(i, j, vs, vph, Cfg::HANDOFF ? 1 : -1);
           adv(vs, vph);
           if (Cfg::ALIAS && more) {  // overwrites S(j)|P(j): ordered behind P(j) V by the in-order tensor pipe
             issue_qk(i, j + NSB, qs, qph);
@@ -358,6 +385,141 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const uint64_t cc2 = pack2(c, c);
       const bool tr = p.trace != nullptr && warp == 4;
       long long ph_wait = 0, ph_ld = 0, ph_max = 0, ph_exp = 0, ph_st = 0, tt = 0;
+      if constexpr (Cfg::FAST) {
+        // ---- speculative softmax: 64-column half-steps against the stale running maximum (fmha_math.cuh: exp_half64) ----
+        constexpr int NHALF = BKV / 64;
+        float nmc = 0.0f;
+        uint64_t mc2 = 0ull;
+        for (int j = 0; j < n_kv; ++j) {
+          const int sb = j % NSB;
+          if (tr) tt = clock64();
+          mbar_wait(s_full(i, sb), (uint32_t)(j / NSB) & 1u);
+          tc_fence_after();
+          if (tr) { const long long t2 = clock64(); ph_wait += t2 - tt; tt = t2; }
+          if (j == 0 && warp == 4 && lane == 0) FMHA_TRACE(6);
+          const uint32_t p_addr = tile_base + Cfg::TM_P + (uint32_t)(j & 1) * Cfg::P_STRIDE;
+          if (p.skip_softmax) {   // debug: no score loads, no exponentials -- the barriers alone
+            if (!Cfg::ALIAS) { __syncwarp(); if (lane == 0) mbar_arrive(s_free(i)); }
+            if (!Cfg::ALIAS && j >= 1) mbar_wait(pv_done(i, (j - 1) & 1), (uint32_t)((j - 1) >> 1) & 1u);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              if (Cfg::HANDOFF) mbar_arrive(p_half(i, j & 1));
+              mbar_arrive(p_full(i, j & 1));
+            }
+            l_run = 1.0f;
+            continue;
+          }
+#pragma unroll
+          for (int hh = 0; hh < NHALF; ++hh) {
+            uint32_t r[64];
+            const uint32_t s_addr = tile_base + Cfg::TM_S + (uint32_t)sb * Cfg::S_STRIDE + (uint32_t)(hh * 64);
+            tmem_ld_x32(s_addr, r);
+            tmem_ld_x32(s_addr + 32u, r + 32);
+            tmem_ld_wait();
+            if (tr) { const long long t2 = clock64(); ph_ld += t2 - tt; tt = t2; }
+            if (!Cfg::ALIAS && hh == NHALF - 1) {   // the whole score tile is in registers: Q K^T of the next step may overwrite it
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(s_free(i));
+            }
+            const int valid = p.len_kv - j * BKV - hh * 64;   // columns of this half that hold existing keys
+            if (valid < 64) {
+#pragma unroll
+              for (int k = 0; k < 64; ++k)
+                if (k >= valid) r[k] = 0xff800000u;  // -inf
+            }
+            if (j == 0 && hh == 0) {   // first scores of the row: the reference maximum is their maximum
+              float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+              for (int k = 0; k < 64; k += 8) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) mx[u] = fmaxf(fmaxf(mx[u], __uint_as_float(r[k + 2 * u])), __uint_as_float(r[k + 2 * u + 1]));
+              }
+              m_run = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+              nmc = -m_run * c;
+              mc2 = pack2(nmc, nmc);
+            }
+            uint32_t pk[32];
+            uint64_t hsum[2] = {0ull, 0ull};
+            const float m_half = exp_half64<Cfg::POLY>(r, cc2, mc2, hsum, pk, p.zero);
+            float hs;
+            {
+              float s0, s1, s2, s3;
+              unpack2(hsum[0], s0, s1);
+              unpack2(hsum[1], s2, s3);
+              hs = (s0 + s1) + (s2 + s3);
+            }
+            {
+              const bool need = (m_half - m_run) * c > 8.0f;
+              if (__any_sync(0xffffffffu, need)) {
+                // (rare) the stale maximum is too small for some row of this warp: rescale what has been accumulated, redo the half-step
+                const float f = need ? ex2_approx((m_run - m_half) * c) : 1.0f;
+                if (need) m_run = m_half;
+                l_run *= f;
+                if (j >= 1 || (Cfg::HANDOFF && hh > 0)) {   // O holds P(0..j-1) V: P(j-1) V must have finished before the rows are rescaled
+                  if (j >= 1) mbar_wait(pv_done(i, (j - 1) & 1), (uint32_t)((j - 1) >> 1) & 1u);
+                  // (the first half of P(j) has been handed over: its product is being added to O -- wait for it; the second half is not
+                  //  issued before this warp arrives on p_full, so O is quiescent afterwards)
+                  if (Cfg::HANDOFF && hh > 0) mbar_wait(pvh_done(i, j & 1), (uint32_t)(j >> 1) & 1u);
+                  tc_fence_after();
+#pragma unroll 1
+                  for (int cb = 0; cb < D / 16; ++cb) {
+                    uint32_t o[16];
+                    tmem_ld_x16(o_addr + (uint32_t)(cb * 16), o);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) o[k] = __float_as_uint(__uint_as_float(o[k]) * f);
+                    tmem_st_x16(o_addr + (uint32_t)(cb * 16), o);
+                  }
+                }
+                if (hh > 0 && !Cfg::HANDOFF) {   // the first half of P(j) is in tensor memory, taken against the old maximum
+                  tmem_st_wait();
+#pragma unroll 1
+                  for (int cb = 0; cb < 2; ++cb) {
+                    uint32_t q[16];
+                    tmem_ld_x16(p_addr + (uint32_t)(cb * 16), q);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) q[k] = pack_bf16(bf16_lo(q[k]) * f, bf16_hi(q[k]) * f);
+                    tmem_st_x16(p_addr + (uint32_t)(cb * 16), q);
+                  }
+                }
+                tmem_st_wait();
+                nmc = -m_run * c;
+                mc2 = pack2(nmc, nmc);
+                hsum[0] = hsum[1] = 0ull;
+                exp_half64_exact(r, cc2, mc2, hsum, pk);
+                float s0, s1, s2, s3;
+                unpack2(hsum[0], s0, s1);
+                unpack2(hsum[1], s2, s3);
+                hs = (s0 + s1) + (s2 + s3);
+              }
+            }
+            l_run += hs;
+            if (tr) { const long long t2 = clock64(); ph_exp += t2 - tt; tt = t2; }
+            // d=64: the single P buffer is read by P(j-1) V.  (d=128: the commit behind s_full of this step covers the last reader of
+            // the buffer S(j) | P(j) lives in.)
+            if (!Cfg::ALIAS && hh == 0 && j >= 1) {
+              mbar_wait(pv_done(i, (j - 1) & 1), (uint32_t)((j - 1) >> 1) & 1u);
+              tc_fence_after();
+            }
+            tmem_st_x32(p_addr + (uint32_t)(hh * 32), pk);
+            if (Cfg::HANDOFF && hh == 0) {
+              tmem_st_wait();
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(p_half(i, j & 1));
+            }
+          }
+          tmem_st_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(p_full(i, j & 1));
+          if (tr) { const long long t2 = clock64(); ph_st += t2 - tt; tt = t2; }
+          if (j == 0 && warp == 4 && lane == 0) FMHA_TRACE(7);
+        }
+      } else
       for (int j = 0; j < n_kv; ++j) {
         const int sb = j % NSB;
         if (tr) tt = clock64();
@@ -560,9 +722,9 @@ static int make_qkv_map(CUtensorMap* tm, const void* ptr, long long B, long long
   return encode_tensor_map(tm, ptr, 2, false, 4, dims, strides, box, true);
 }
 
-template <int D, int BKV_, int POLY_, int SPLIT_>
+template <int D, int BKV_, int POLY_, int SPLIT_, int FAST_ = 0>
 static int launch_fmha(const vist3a_fmha_args& a, cudaStream_t stream) {
-  using Cfg = FmhaCfg<D, BKV_, POLY_, SPLIT_>;
+  using Cfg = FmhaCfg<D, BKV_, POLY_, SPLIT_, FAST_>;
   CUtensorMap tmQ, tmK, tmV, tmO;
   int rc;
   if ((rc = make_qkv_map(&tmQ, a.Q, a.batch, a.heads, a.len_q, D, a.q_bs, a.q_rs, a.q_hs, Cfg::BQ))) return rc;
@@ -575,9 +737,11 @@ static int launch_fmha(const vist3a_fmha_args& a, cudaStream_t stream) {
   p.scale_log2 = a.scale * 1.4426950408889634f;
   p.row_scale = a.q_row_scale;
   p.trace = g_fmha_trace.load(std::memory_order_relaxed);
+  p.zero = 0u;
+  p.skip_softmax = (a.flags & 4096u) ? 1 : 0;
   p.single_issuer = (a.flags & 4u) ? 1 : 0;
   p.direct_store = (a.flags & 64u) ? 1 : 0;
-  auto kern = fmha_fwd_kernel<D, BKV_, POLY_, SPLIT_>;
+  auto kern = fmha_fwd_kernel<D, BKV_, POLY_, SPLIT_, FAST_>;
   static std::atomic<unsigned long long> attr_done{0};  // per template instantiation, one bit per device
   V3A_CUDA_OK(ensure_dynamic_smem(kern, Cfg::SMEM_BYTES, attr_done));
   const long long rows_per_cta = Cfg::BQ * Cfg::QT;
@@ -611,6 +775,43 @@ int fmha_entry(const vist3a_fmha_args* args, cudaStream_t stream) {
   // head_dim 128: the CTA-pair kernel (fmha_pair_sm100.cu); flags bit 8 selects it, bits 9-11 its variant (A/B measurements)
   if (a.head_dim == 128 && (a.flags & 256u)) return fmha_pair_entry(a, (int)((a.flags >> 9) & 7u), stream);
   const bool one = (a.flags & 1u) != 0;
+  // Default (flags == 0), from same-process A/B runs on B200 (tools/fmha_variants.py, tools/fmha_pair_check.py; profiles/README.md): the speculative
+  // softmax (stale running maximum, 64-column half-steps, one thread per row, 2-3 of 8 exponentials on the FMA pipe) everywhere; at head_dim 128
+  // and >= 1024 keys on CTA pairs (+4.5 % over the single-CTA kernel at 4096 keys), below that on one CTA (+7 % at 512 keys).  flags bit 13
+  // selects the former default (two threads per row, exact running maximum) for A/B.
+  if (a.flags == 0u) {
+    if (a.head_dim == 64) return launch_fmha<64, 128, 2, 1, 1>(a, stream);
+    if (a.len_kv >= 1024) return fmha_pair_entry(a, 7, stream);
+    return launch_fmha<128, 64, 2, 1, 1>(a, stream);
+  }
+  if (a.flags & 128u) {   // speculative softmax, one thread per row; bits 3-5 = FMA-pipe exponentials per 8 column pairs
+    const unsigned np = (a.flags >> 3) & 7u;
+    if (a.head_dim == 64) {
+      switch (np) {
+        case 0: return launch_fmha<64, 128, 0, 1, 1>(a, stream);
+        case 1: return launch_fmha<64, 128, 1, 1, 1>(a, stream);
+        case 2: return launch_fmha<64, 128, 2, 1, 1>(a, stream);
+        case 3: return launch_fmha<64, 128, 3, 1, 1>(a, stream);
+        default: return launch_fmha<64, 128, 4, 1, 1>(a, stream);
+      }
+    }
+    if (a.flags & 2u) {   // aliased 128-key steps, P handed over in two halves
+      switch (np) {
+        case 0: return launch_fmha<128, 128, 0, 1, 1>(a, stream);
+        case 1: return launch_fmha<128, 128, 1, 1, 1>(a, stream);
+        case 2: return launch_fmha<128, 128, 2, 1, 1>(a, stream);
+        case 3: return launch_fmha<128, 128, 3, 1, 1>(a, stream);
+        default: return launch_fmha<128, 128, 4, 1, 1>(a, stream);
+      }
+    }
+    switch (np) {
+      case 0: return launch_fmha<128, 64, 0, 1, 1>(a, stream);
+      case 1: return launch_fmha<128, 64, 1, 1, 1>(a, stream);
+      case 2: return launch_fmha<128, 64, 2, 1, 1>(a, stream);
+      case 3: return launch_fmha<128, 64, 3, 1, 1>(a, stream);
+      default: return launch_fmha<128, 64, 4, 1, 1>(a, stream);
+    }
+  }
   // Share of the exponentials moved from the MUFU to the FMA pipe (Cody-Waite + polynomial), per 8 column pairs.  Measured on B200 with
   // two threads per query row (4 softmax warpgroups): the softmax is bound by issue slots and dependent-latency chains rather than by
   // the MUFU, so the default is 0 (all MUFU.EX2): +4 % at d=128 / 4096 keys, +9 % at d=64 / 13377 keys over the former 2 / 3 of 8; short

@@ -5,6 +5,7 @@ libvist3a_sm100.so and returns the (pre-allocated or new) output tensor.  No op 
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional
 
 import torch
@@ -128,6 +129,10 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
     return out
 
 
+# A/B switch for measurements and numerics studies (tools/): flags used when the caller passes none (e.g. 8192 = the former default variants)
+_FMHA_DEFAULT_FLAGS = int(os.environ.get("VIST3A_FMHA_FLAGS", "0"), 0)
+
+
 def fmha(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, scale: Optional[float] = None,
          out: Optional[torch.Tensor] = None, flags: int = 0, q_row_scale: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Non-causal attention.  q [B, Lq, H, D], k/v [B, Lkv, H, D] (any strides with unit inner stride,
@@ -151,7 +156,7 @@ def fmha(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, scale: Optional[f
     a.v_bs, a.v_rs, a.v_hs = v.stride(0), v.stride(1), v.stride(2)
     a.o_bs, a.o_rs, a.o_hs = out.stride(0), out.stride(1), out.stride(2)
     a.scale = float(scale if scale is not None else D ** -0.5)
-    a.flags = flags
+    a.flags = flags if flags else _FMHA_DEFAULT_FLAGS
     if q_row_scale is not None:
         if q_row_scale.dtype != torch.float32 or not q_row_scale.is_contiguous() or q_row_scale.numel() != B * Lq or not q_row_scale.is_cuda:
             raise TypeError("fmha: q_row_scale must be a contiguous CUDA float32 tensor of B*Lq elements")
