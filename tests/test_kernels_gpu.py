@@ -158,6 +158,27 @@ def test_fmha(ops, B, H, Lq, Lk, D):
     assert _rel_l2(out.float(), ref) < 8e-3
 
 
+# every selectable attention variant (vist3a_fmha_args.flags; A/B measurements in tools/fmha_variants.py, tools/fmha_pair_check.py) computes the
+# same function: 0 = default dispatch, 8192 = the former default (two threads per row, exact running maximum), 128 | np << 3 = speculative
+# softmax with one thread per row, | 2 = aliased 128-key steps with the half hand-off of P, 16384 = speculative with two threads per row,
+# 256 | v << 9 = CTA-pair kernel variant v (head_dim 128)
+@pytest.mark.parametrize("flags", [0, 8192, 128, 128 | 16, 128 | 2 | 16, 16384, 256, 256 | (4 << 9), 256 | (7 << 9)])
+@pytest.mark.parametrize("B,H,Lq,Lk,D", [(2, 3, 300, 333, 128), (1, 2, 257, 129, 128), (2, 3, 1029, 1029, 64), (1, 4, 640, 1100, 64)])
+def test_fmha_variants_agree_with_sdpa(ops, flags, B, H, Lq, Lk, D):
+    if D == 64 and (flags & (256 | 2)):
+        pytest.skip("CTA-pair kernel and aliased 128-key steps exist for head_dim 128 only")
+    g = torch.Generator(device="cuda").manual_seed(B + Lq + D)
+    q = torch.randn(B, Lq, H, D, device="cuda", generator=g).bfloat16()
+    k = torch.randn(B, Lk, H, D, device="cuda", generator=g).bfloat16()
+    v = torch.randn(B, Lk, H, D, device="cuda", generator=g).bfloat16()
+    q[:, : Lq // 2] *= 4   # large logits on half the rows
+    k[:, Lk // 2:] *= 2    # ... growing along the keys: the running maximum moves by more than the lazy-rescale threshold
+    ref = torch.nn.functional.scaled_dot_product_attention(q.float().transpose(1, 2), k.float().transpose(1, 2), v.float().transpose(1, 2)).transpose(1, 2)
+    out = ops.fmha(q, k, v, flags=flags)
+    assert torch.isfinite(out).all()
+    assert _rel_l2(out.float(), ref) < 6e-3, flags
+
+
 def test_fmha_large_scores(ops):
     # rows whose max moves by > 2^8 between kv tiles exercise the lazy-rescale path
     g = torch.Generator(device="cuda").manual_seed(5)

@@ -84,7 +84,9 @@ __device__ __forceinline__ void exp2_poly2_b(float y0, float y1, float bound, fl
 // half-step first and leaves a MUFU-only tail (measured: 570 static cycles per half-step against 384 of MUFU time); to stagger them, the clamp
 // bound of group g's polynomial pairs is made to depend on a MUFU result from the middle of group g - 1 (bound | (e & zero): one LOP3), so
 // that every group's FMA-pipe work lands in the issue slots between the MUFU instructions of its own neighbourhood.
-template <int NP>
+// TRACK = false drops the maximum (returns -inf): the caller then tests the half-step's row sum instead (a sum above 2^8 or a non-finite one
+// means that some exponent was above the lazy-rescale threshold, or several were close to it)
+template <int NP, bool TRACK = true>
 __device__ __forceinline__ float exp_half64(const uint32_t* r, uint64_t cc2, uint64_t mc2, uint64_t* hsum, uint32_t* pk, uint32_t zero) {
   float mx0 = -INFINITY, mx1 = -INFINITY;
   uint32_t dep = 0u;
@@ -94,8 +96,10 @@ __device__ __forceinline__ float exp_half64(const uint32_t* r, uint64_t cc2, uin
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       const float s0 = __uint_as_float(r[g * 16 + 2 * k]), s1 = __uint_as_float(r[g * 16 + 2 * k + 1]);
-      if (k & 1) mx1 = fmaxf(fmaxf(mx1, s0), s1);
-      else mx0 = fmaxf(fmaxf(mx0, s0), s1);
+      if (TRACK) {
+        if (k & 1) mx1 = fmaxf(fmaxf(mx1, s0), s1);
+        else mx0 = fmaxf(fmaxf(mx0, s0), s1);
+      }
       float y0, y1, e0, e1;
       unpack2(fma2(pack2(s0, s1), cc2, mc2), y0, y1);
       if (exp_pair_is_poly<NP>(k)) {

@@ -69,7 +69,7 @@ struct FmhaCfg {
   static constexpr int SPLIT = SPLIT_;               // threads per query row (softmax warpgroups per tile)
   static constexpr int THREADS = 128 + 256 * SPLIT;
   static constexpr int HC = BKV / SPLIT;             // score columns per softmax thread and step
-  static constexpr int XCH_BYTES = 2 * QT * 2 * 128 * 4;  // row-max / row-sum exchange between the two threads of a row
+  static constexpr int XCH_BYTES = 4 * QT * 2 * 128 * 4;  // row-max / row-sum / slow-path flag exchange between the two threads of a row: [slot][tile][half][row]
   static constexpr int SMEM_BYTES = Q_TILE_BYTES * QT + KV_TILE_BYTES * 2 * KV_STAGES + 1024 + 8 * NBARS + 16 + XCH_BYTES;
   static_assert(SPLIT == 1 || SPLIT == 2, "SPLIT");
   static constexpr uint32_t TILE_COLS = 256;
@@ -83,11 +83,19 @@ struct FmhaCfg {
   static constexpr bool FAST = FAST_ != 0;               // speculative (stale-maximum) softmax in 64-column half-steps, one thread per row
   // aliased 128-key steps (S single-buffered: softmax -> P V -> next Q K^T is a serial chain per tile): the first 64 keys of P(j) are handed
   // to the tensor pipe while the other 64 are still being exponentiated
-  static constexpr bool HANDOFF = FAST && ALIAS && BKV_ == 128;
-  static_assert(!FAST || SPLIT_ == 1, "the speculative softmax runs one thread per query row");
+  static constexpr bool HANDOFF = FAST_ == 1 && ALIAS && BKV_ == 128;
+  // FAST_ == 1: one thread per query row, two 64-column half-steps per 128 keys in sequence; FAST_ == 2: two threads per row, one 64-column half
+  // each (128-key steps only), which agree on the rare slow path through shared memory and a 64-thread named barrier AFTER the exponentials
+  static_assert(FAST_ == 0 || (FAST_ == 1 && SPLIT_ == 1) || (FAST_ == 2 && SPLIT_ == 2 && BKV_ == 128), "speculative softmax variants");
   static_assert(TM_O + D <= TILE_COLS, "TMEM budget");
 };
 
+
+// registers per softmax thread of the two-threads-per-row speculative variant (96 = the launch-time allocation, no setmaxnreg)
+#ifndef V3A_FAST2_REGS
+#define V3A_FAST2_REGS 96
+#endif
+constexpr int kFast2Regs = V3A_FAST2_REGS;
 
 template <int D, int BKV_, int POLY_, int SPLIT_, int FAST_ = 0>
 __global__ void __launch_bounds__(128 + 256 * SPLIT_, 1)
@@ -176,6 +184,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
   if (warp < 4) {
     if constexpr (SPLIT == 1) asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+    if constexpr (FAST_ == 2 && kFast2Regs != 96) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
     // (SPLIT == 2: 20 warps at the launch-time 96 registers; see the note at the softmax branch)
     if (warp == 0) {
       // ------------------------------ TMA producer (warp-uniform control flow, one elected lane issues) ---------
@@ -361,6 +370,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     }
   } else {
     if constexpr (SPLIT == 1) asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
+    if constexpr (FAST_ == 2 && kFast2Regs != 96) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kFast2Regs));
     // SPLIT == 2 keeps the launch-time allocation (96 registers x 640 threads): setmaxnreg.inc above 96 deadlocked on B200 --
     // the per-warp register allocation is coarser than the PTX granularity of 8, and 16 warps x 4096 registers is the whole file.
     // ------------------------------ softmax / correction / epilogue ------------------------------
@@ -385,7 +395,134 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const uint64_t cc2 = pack2(c, c);
       const bool tr = p.trace != nullptr && warp == 4;
       long long ph_wait = 0, ph_ld = 0, ph_max = 0, ph_exp = 0, ph_st = 0, tt = 0;
-      if constexpr (Cfg::FAST) {
+      if constexpr (FAST_ == 2) {
+        // ---- speculative softmax, two threads per row: thread (row, h) owns score columns [64 h, 64 h + 64) of every 128-key step.  The
+        //      exponentials run against the stale maximum with no exchange in front of them; afterwards the two threads of a row exchange ONE
+        //      flag (row sum of the half above 2^8 or not finite) and only then store P, so that a flagged step can still reload its scores from
+        //      tensor memory, agree on the row maximum, rescale O / the row sums once and redo the exponentials exactly. ----
+        float nmc = 0.0f;
+        uint64_t mc2 = 0ull;
+        auto max64 = [&](const uint32_t* r) {
+          float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+          for (int k = 0; k < 64; k += 8) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) mx[u] = fmaxf(fmaxf(mx[u], __uint_as_float(r[k + 2 * u])), __uint_as_float(r[k + 2 * u + 1]));
+          }
+          return fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+        };
+        auto exchange = [&](int slot, float mine) {   // value of the other thread of this row (both call it at the same point)
+          asm volatile("st.shared.f32 [%0], %1;" ::"r"(xch(slot, h)), "f"(mine) : "memory");
+          asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+          float other;
+          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(other) : "r"(xch(slot, h ^ 1)) : "memory");
+          return other;
+        };
+        for (int j = 0; j < n_kv; ++j) {
+          const int sb = j % NSB;
+          if (tr) tt = clock64();
+          mbar_wait(s_full(i, sb), (uint32_t)(j / NSB) & 1u);
+          tc_fence_after();
+          if (tr) { const long long t2 = clock64(); ph_wait += t2 - tt; tt = t2; }
+          if (j == 0 && warp == 4 && lane == 0) FMHA_TRACE(6);
+          const uint32_t s_addr = tile_base + Cfg::TM_S + (uint32_t)sb * Cfg::S_STRIDE + (uint32_t)(h * 64);
+          const uint32_t p_addr = tile_base + Cfg::TM_P + (uint32_t)(j & 1) * Cfg::P_STRIDE + (uint32_t)(h * 32);
+          const int valid = p.len_kv - j * BKV - h * 64;   // columns of this thread that hold existing keys
+          uint32_t pk[32];
+          uint64_t hsum[2] = {0ull, 0ull};
+          {
+            uint32_t r[64];
+            tmem_ld_x32(s_addr, r);
+            tmem_ld_x32(s_addr + 32u, r + 32);
+            tmem_ld_wait();
+            if (tr) { const long long t2 = clock64(); ph_ld += t2 - tt; tt = t2; }
+            if (valid < 64) {
+#pragma unroll
+              for (int k = 0; k < 64; ++k)
+                if (k >= valid) r[k] = 0xff800000u;  // -inf
+            }
+            if (j == 0) {   // first scores of the row: the reference maximum is the maximum over both halves
+              const float mine = max64(r);
+              m_run = fmaxf(mine, exchange(2, mine));
+              nmc = -m_run * c;
+              mc2 = pack2(nmc, nmc);
+            }
+            exp_half64<Cfg::POLY, false>(r, cc2, mc2, hsum, pk, p.zero);
+          }
+          float hs;
+          {
+            float s0, s1, s2, s3;
+            unpack2(hsum[0], s0, s1);
+            unpack2(hsum[1], s2, s3);
+            hs = (s0 + s1) + (s2 + s3);
+          }
+          if (tr) { const long long t2 = clock64(); ph_exp += t2 - tt; tt = t2; }
+          const float flag = (hs <= 256.0f) ? 0.0f : 1.0f;
+          const float flag_other = exchange(j & 1, flag);
+          if (__any_sync(0xffffffffu, (flag + flag_other) != 0.0f)) {
+            // (rare) exact path for the rows of this warp pair: the scores are still in tensor memory (P is stored below, and Q K^T of the next
+            // step waits for s_free / for P V of this step)
+            uint32_t r[64];
+            tmem_ld_x32(s_addr, r);
+            tmem_ld_x32(s_addr + 32u, r + 32);
+            tmem_ld_wait();
+            if (valid < 64) {
+#pragma unroll
+              for (int k = 0; k < 64; ++k)
+                if (k >= valid) r[k] = 0xff800000u;  // -inf
+            }
+            const float mine = max64(r);
+            const float m_new = fmaxf(m_run, fmaxf(mine, exchange(3, mine)));
+            const bool need = (m_new - m_run) * c > 8.0f;
+            if (__any_sync(0xffffffffu, need)) {
+              const float f = need ? ex2_approx((m_run - m_new) * c) : 1.0f;
+              if (need) m_run = m_new;
+              l_run *= f;
+              if (j >= 1) {   // O holds P(0..j-1) V: P(j-1) V must have finished before the rows are rescaled (each thread its column half)
+                mbar_wait(pv_done(i, (j - 1) & 1), (uint32_t)((j - 1) >> 1) & 1u);
+                tc_fence_after();
+#pragma unroll 1
+                for (int cb = 0; cb < OC / 16; ++cb) {
+                  uint32_t o[16];
+                  tmem_ld_x16(o_addr + (uint32_t)(cb * 16), o);
+                  tmem_ld_wait();
+#pragma unroll
+                  for (int k = 0; k < 16; ++k) o[k] = __float_as_uint(__uint_as_float(o[k]) * f);
+                  tmem_st_x16(o_addr + (uint32_t)(cb * 16), o);
+                }
+                tmem_st_wait();
+              }
+              nmc = -m_run * c;
+              mc2 = pack2(nmc, nmc);
+            }
+            // (always redone here, also when no row needed the rescale: the fast path's P need not stay live across this branch)
+            hsum[0] = hsum[1] = 0ull;
+            exp_half64_exact(r, cc2, mc2, hsum, pk);
+            float s0, s1, s2, s3;
+            unpack2(hsum[0], s0, s1);
+            unpack2(hsum[1], s2, s3);
+            hs = (s0 + s1) + (s2 + s3);
+          }
+          l_run += hs;
+          if (!Cfg::ALIAS) {
+            // every thread of the row is done with S(j): Q K^T of the next step may overwrite it.  The single P buffer is read by P(j-1) V.
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(s_free(i));
+            if (j >= 1) {
+              mbar_wait(pv_done(i, (j - 1) & 1), (uint32_t)((j - 1) >> 1) & 1u);
+              tc_fence_after();
+            }
+          }
+          tmem_st_x32(p_addr, pk);
+          tmem_st_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(p_full(i, j & 1));
+          if (tr) { const long long t2 = clock64(); ph_st += t2 - tt; tt = t2; }
+          if (j == 0 && warp == 4 && lane == 0) FMHA_TRACE(7);
+        }
+      } else if constexpr (Cfg::FAST) {
         // ---- speculative softmax: 64-column half-steps against the stale running maximum (fmha_math.cuh: exp_half64) ----
         constexpr int NHALF = BKV / 64;
         float nmc = 0.0f;
@@ -783,6 +920,22 @@ int fmha_entry(const vist3a_fmha_args* args, cudaStream_t stream) {
     if (a.head_dim == 64) return launch_fmha<64, 128, 2, 1, 1>(a, stream);
     if (a.len_kv >= 1024) return fmha_pair_entry(a, 7, stream);
     return launch_fmha<128, 64, 2, 1, 1>(a, stream);
+  }
+  if (a.flags & 16384u) {   // speculative softmax, two threads per row (128-key steps); bits 3-5 = FMA-pipe exponentials per 8 column pairs
+    const unsigned np = (a.flags >> 3) & 7u;
+    if (a.head_dim == 64) {
+      switch (np) {
+        case 0: return launch_fmha<64, 128, 0, 2, 2>(a, stream);
+        case 1: return launch_fmha<64, 128, 1, 2, 2>(a, stream);
+        case 2: return launch_fmha<64, 128, 2, 2, 2>(a, stream);
+        default: return launch_fmha<64, 128, 3, 2, 2>(a, stream);
+      }
+    }
+    switch (np) {
+      case 0: return launch_fmha<128, 128, 0, 2, 2>(a, stream);
+      case 2: return launch_fmha<128, 128, 2, 2, 2>(a, stream);
+      default: return launch_fmha<128, 128, 3, 2, 2>(a, stream);
+    }
   }
   if (a.flags & 128u) {   // speculative softmax, one thread per row; bits 3-5 = FMA-pipe exponentials per 8 column pairs
     const unsigned np = (a.flags >> 3) & 7u;
