@@ -352,7 +352,7 @@ def run_ours(args):
 
     from vist3a_b200 import _lib, ops
     from vist3a_b200.pipeline import DenoiseEngine
-    from vist3a_b200.t23d import WAN_LATENTS_MEAN, WAN_LATENTS_STD, all_gather_gaussians
+    from vist3a_b200.t23d import WAN_LATENTS_MEAN, WAN_LATENTS_STD, all_gather_gaussians, all_gather_gaussians_async
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -471,7 +471,7 @@ def run_ours(args):
         ms_gather = 0.0
         if world > 1:
             def gather_step(i):
-                outs["all"] = all_gather_gaussians(outs["o"].gaussians)
+                outs["all"] = all_gather_gaussians(outs["o"].gaussians, fixed_count=not args.voxelize)
 
             gather_step(0)
             ms_gather = timed(gather_step, 3) / 3
@@ -490,31 +490,48 @@ def run_ours(args):
 
         # end to end per prompt: H2D of text + noise, 50 denoise steps, de-normalise, VAE decode + resize (or H2D of given views), stitched
         # decode, gather, D2H of one scalar (scene scale)
-        def e2e_prompt(i):
-            eng.set_text(tc_h, tu_h)
-            eng.set_noise(noise_h)
-            for k in range(nsteps):
-                eng.step(k)
-            lat_i = eng.x.clamp(-4, 4) * std + mean
-            if vae is not None:
-                views = views_from_vae(vae, lat_i)
-            else:
-                img.copy_(img_h, non_blocking=True)
-                views = img
-            o = dec.forward_with_latent(lat_i, views)
-            if world > 1:
-                all_gather_gaussians(o.gaussians)
-            o.infos["scene_scale"].cpu()
+        # With several GPUs the all-gather of prompt p is issued asynchronously and waited for after prompt p + 1 has been queued, so it runs
+        # under that prompt's denoising (t23d.generate_sharded does the same): two prompts per rank are timed and the time per prompt reported.
+        n_e2e = 2 if world > 1 else 1
 
-        ms_prompt = timed(e2e_prompt, 1)
+        def e2e_prompts(i):
+            pending = None
+            for _ in range(n_e2e):
+                eng.set_text(tc_h, tu_h)
+                eng.set_noise(noise_h)
+                for k in range(nsteps):
+                    eng.step(k)
+                lat_i = eng.x.clamp(-4, 4) * std + mean
+                if vae is not None:
+                    views = views_from_vae(vae, lat_i)
+                else:
+                    img.copy_(img_h, non_blocking=True)
+                    views = img
+                o = dec.forward_with_latent(lat_i, views)
+                h = all_gather_gaussians_async(o.gaussians, fixed_count=not args.voxelize) if world > 1 else None
+                if pending is not None:
+                    pending[1].wait()
+                    pending[0].infos["scene_scale"].cpu()
+                pending = (o, h)
+            if pending[1] is not None:
+                pending[1].wait()
+            pending[0].infos["scene_scale"].cpu()
+
+        ms_prompt = timed(e2e_prompts, 1) / n_e2e
+        gather_bytes = (world - 1) * B * N_GAUSS * (11 + 3 * 25) * 4 if world > 1 else 0   # received per GPU (own segment stays local)
         gauss = {"n_per_prompt": N_GAUSS, "unit": "Gaussians/s",
                  "decoder_gaussians_per_sec": world * B * N_GAUSS / (ms_dec / 1e3), "decoder_ms": ms_dec,
                  "decoder_tflops": B * DECODER_TFLOP / (ms_dec / 1e3), "gather_ms": ms_gather,
+                 "gather": None if world == 1 else {"ms_inline": ms_gather, "bytes_received_per_gpu": gather_bytes,
+                                                    "GBps_per_gpu": gather_bytes / (ms_gather / 1e3) / 1e9,
+                                                    "frac_of_nvlink5_900GBps": gather_bytes / (ms_gather / 1e3) / 900e9,
+                                                    "what": "one all_gather_into_tensor of the field-major Gaussian buffers (no count collective: fixed N); in the "
+                                                            "end-to-end prompt it is asynchronous and overlaps the next prompt's denoising"},
                  "e2e_gaussians_per_sec": world * B * N_GAUSS / (ms_prompt / 1e3), "e2e_prompt_ms": ms_prompt,
                  "vae_decode_ms": ms_vae, "vae_what": None if vae is None else "WanVAEDecoderB200: latent [1,16,T,64,64] -> frames 512x512 (29.5 TFLOP at 13 views) + resize to 448x448",
-                 "e2e_what": "one prompt per GPU: H2D text + noise, text projections, 50 CFG denoise steps, de-normalise, " +
+                 "e2e_what": ("one prompt per GPU" if world == 1 else "two prompts per GPU, time per prompt") + ": H2D text + noise, text projections, 50 CFG denoise steps, de-normalise, " +
                              ("Wan VAE decode + 448 resize, " if vae is not None else "H2D views, ") + "stitched decode" +
-                             (", NCCL all-gather of all ranks' Gaussians" if world > 1 else "") + ", D2H of scene_scale",
+                             (", asynchronous NCCL all-gather of all ranks' Gaussians (under the next prompt's denoising)" if world > 1 else "") + ", D2H of scene_scale",
                  "decoder_launches_per_forward": dec_launches // kd,
                  "latent": "denoised latent of the random-weight DiT, clamped to [-4, 4] before de-normalisation (real VAE latents are O(1))",
                  "workload": f"VIST3A-{'1.3B' if args.model == '1.3b' else '14B'} full stitched path: DiT -> conv3d_k5x3x3 stitch -> AnySplat "

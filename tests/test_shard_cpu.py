@@ -9,7 +9,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from vist3a_b200.stitched_decoder import Gaussians
-from vist3a_b200.t23d import all_gather_gaussians, pack_gaussians, shard_prompts, unpack_gaussians
+from vist3a_b200.t23d import all_gather_gaussians, all_gather_gaussians_async, pack_gaussians, shard_prompts, unpack_gaussians
 
 
 def _gauss(seed, n=37, d_sh=25):
@@ -71,6 +71,15 @@ def _worker(rank, world, port, q):
             want = _gauss(200 + r, n=11 + 5 * r)
             for k, v in got[r].items():
                 ok = ok and v.shape == getattr(want, k).shape and torch.equal(v, getattr(want, k))
+        # fixed count (no count collective, no host read) and two gathers in flight at once, waited in order
+        h1 = all_gather_gaussians_async(_gauss_packed(300 + rank), with_covariances=False, fixed_count=True)
+        h2 = all_gather_gaussians_async(_gauss(400 + rank), with_covariances=True, fixed_count=True)
+        for h, make, base in ((h1, _gauss_packed, 300), (h2, _gauss, 400)):
+            got = h.wait()
+            for r in range(world):
+                want = make(base + r)
+                for k, v in got[r].items():
+                    ok = ok and torch.equal(v, getattr(want, k))
         q.put((rank, ok))
     finally:
         dist.destroy_process_group()

@@ -122,45 +122,94 @@ def _field_views(flat: torch.Tensor, B: int, N: int, d_sh: int, with_covariances
     return out
 
 
-def all_gather_gaussians(g: Gaussians, group=None, with_covariances: bool = False) -> List[Dict[str, torch.Tensor]]:
+class GaussianGather:
+    """An all-gather of Gaussians in flight (`all_gather_gaussians_async`).  `wait()` makes the CURRENT stream wait for the collective (the host is
+    not blocked on NCCL) and returns one dict of tensors per rank; the handle keeps the send and receive buffers alive until then."""
+
+    def __init__(self, work, finish, keep):
+        self._work, self._finish, self._keep = work, finish, keep
+
+    def wait(self) -> List[Dict[str, torch.Tensor]]:
+        if self._work is not None:
+            self._work.wait()
+            self._work = None
+        return self._finish()
+
+
+def all_gather_gaussians_async(g: Gaussians, group=None, with_covariances: bool = False, fixed_count: bool = False) -> GaussianGather:
     """The single exchange step of the multi-GPU path: every rank contributes the Gaussians of its prompt and
     receives everybody's.  One `all_gather_into_tensor` of a fixed-size buffer (N = V*H*W per prompt when voxelisation is off), NCCL
-    over NVLink on GPUs, gloo on CPU in the tests.  Returns one dict per rank.
+    over NVLink on GPUs, gloo on CPU in the tests.  The collective is issued asynchronously (`async_op=True`: on NCCL it runs on the
+    process group's own stream behind the work already queued on the current one), so the caller can queue the next prompt's denoising
+    before calling `wait()` -- the gather then hides under it.
 
     The decoder writes its outputs field-major into ONE flat buffer (`Gaussians.packed`), so the collective sends that buffer as it is and
     the received segments are viewed, not copied (2.1 ms for 2 x 0.99 GB over NVLink; packing records with torch.cat and re-splitting them
-    cost 35 ms).  Gaussians built elsewhere (no `packed`) take the record path."""
+    cost 35 ms).  Gaussians built elsewhere (no `packed`) take the record path.
+
+    fixed_count: every rank holds the same number of Gaussians (voxelised fusion and the confidence branches are off: N = V*H*W).  Otherwise
+    the counts are agreed on first -- one tiny collective and a host read, which synchronises the stream."""
     import torch.distributed as dist
     import torch.nn.functional as F
 
     world = dist.get_world_size(group)
     B, N = g.opacities.shape
     d_sh = g.harmonics.shape[-1]
-    # voxelised fusion makes the Gaussian count data dependent: agree on the counts first (one tiny collective); ranks with fewer Gaussians
-    # pad to the largest count with the reference's fill values (points -1e4, opacity 0: models/anysplat_stitched.py:448-455) and every
-    # returned dict is cut back to its rank's own count
-    counts = torch.tensor([N], dtype=torch.int64, device=g.opacities.device)
-    all_counts = torch.empty((world,), dtype=torch.int64, device=counts.device)
-    dist.all_gather_into_tensor(all_counts, counts, group=group)
-    all_counts = [int(c) for c in all_counts.tolist()]
-    nmax = max(all_counts)
-    if min(all_counts) != nmax:
-        pad = nmax - N
+    all_counts = None
+    if not fixed_count:
+        # voxelised fusion makes the Gaussian count data dependent: agree on the counts first (one tiny collective); ranks with fewer Gaussians
+        # pad to the largest count with the reference's fill values (points -1e4, opacity 0: models/anysplat_stitched.py:448-455) and every
+        # returned dict is cut back to its rank's own count
+        counts = torch.tensor([N], dtype=torch.int64, device=g.opacities.device)
+        gathered = torch.empty((world,), dtype=torch.int64, device=counts.device)
+        dist.all_gather_into_tensor(gathered, counts, group=group)
+        all_counts = [int(c) for c in gathered.tolist()]
+        nmax = max(all_counts)
+        if min(all_counts) != nmax:
+            pad = nmax - N
 
-        def padn(t, value=0.0):
-            return F.pad(t, (0, 0) * (t.dim() - 2) + (0, pad), value=value) if pad else t
+            def padn(t, value=0.0):
+                return F.pad(t, (0, 0) * (t.dim() - 2) + (0, pad), value=value) if pad else t
 
-        g = Gaussians(means=padn(g.means, -1e4), covariances=padn(g.covariances), harmonics=padn(g.harmonics), opacities=padn(g.opacities),
-                      scales=padn(g.scales), rotations=padn(g.rotations))
-        N = nmax
+            g = Gaussians(means=padn(g.means, -1e4), covariances=padn(g.covariances), harmonics=padn(g.harmonics), opacities=padn(g.opacities),
+                          scales=padn(g.scales), rotations=padn(g.rotations))
+            N = nmax
     if g.packed is not None:
         per = B * N * (11 + 3 * d_sh + (9 if with_covariances else 0))   # covariances are the last field: leave them out by length
         src = g.packed[:per]
         out = torch.empty((world * per,), dtype=src.dtype, device=src.device)
-        dist.all_gather_into_tensor(out, src, group=group)
-        return [_field_views(out[r * per:(r + 1) * per], B, N, d_sh, with_covariances) for r in range(world)]
+        work = dist.all_gather_into_tensor(out, src, group=group, async_op=True)
+        return GaussianGather(work, lambda: [_field_views(out[r * per:(r + 1) * per], B, N, d_sh, with_covariances) for r in range(world)], (g, src, out))
     rec = pack_gaussians(g, with_covariances)
     out = torch.empty((world * B,) + tuple(rec.shape[1:]), dtype=rec.dtype, device=rec.device)  # rank-major concatenation
-    dist.all_gather_into_tensor(out, rec, group=group)
-    res = [unpack_gaussians(out[r * B:(r + 1) * B], d_sh, with_covariances) for r in range(world)]
-    return [{k: v[:, :all_counts[r]] for k, v in d.items()} for r, d in enumerate(res)]
+    work = dist.all_gather_into_tensor(out, rec, group=group, async_op=True)
+
+    def finish():
+        res = [unpack_gaussians(out[r * B:(r + 1) * B], d_sh, with_covariances) for r in range(world)]
+        return res if all_counts is None else [{k: v[:, :all_counts[r]] for k, v in d.items()} for r, d in enumerate(res)]
+
+    return GaussianGather(work, finish, (rec, out))
+
+
+def all_gather_gaussians(g: Gaussians, group=None, with_covariances: bool = False, fixed_count: bool = False) -> List[Dict[str, torch.Tensor]]:
+    """`all_gather_gaussians_async(...).wait()`: the gather in line with the caller's stream."""
+    return all_gather_gaussians_async(g, group, with_covariances, fixed_count).wait()
+
+
+def generate_sharded(engine: "TextTo3DGS", items, *, group=None, with_covariances: bool = False):
+    """The prompts of THIS rank (`shard_prompts`), each followed by the exchange of its Gaussians with the other ranks, pipelined: the
+    all-gather of prompt p is in flight while prompt p + 1 is denoised and decoded.  `items` yields (noise, text_cond, text_uncond,
+    feedforward_image or None [, vae]); yields (EncoderOutput of this rank, [dict of Gaussian tensors per rank]) per prompt.  Every rank must
+    bring the same number of prompts (the exchange is a collective)."""
+    cfg = engine.dec.cfg
+    fixed = not (cfg.voxelize or cfg.render_conf or cfg.opacity_conf)
+    pending = None
+    for it in items:
+        noise, tc, tu, img = it[:4]
+        out = engine.generate(noise, tc, tu, img, vae=it[4] if len(it) > 4 else None)
+        handle = all_gather_gaussians_async(out.gaussians, group, with_covariances, fixed_count=fixed)
+        if pending is not None:
+            yield pending[0], pending[1].wait()
+        pending = (out, handle)
+    if pending is not None:
+        yield pending[0], pending[1].wait()
