@@ -14,7 +14,9 @@ def main():
     lib = _lib.load()
     lib.v3a_debug_gemm_trace.argtypes = [ctypes.c_void_p]
     shapes = [("dit_qkv", 8192, 4608, 1536, None), ("dit_o", 8192, 1536, 1536, None), ("dit_ffn1", 8192, 8960, 1536, "gelu_tanh"),
-              ("dit_ffn2", 8192, 1536, 8960, None), ("dec_proj_f32res", 13377, 1024, 1024, "res"), ("dec_fc1", 13377, 4096, 1024, "gelu")]
+              ("dit_ffn2", 8192, 1536, 8960, None), ("dec_proj_f32res", 13377, 1024, 1024, "res"), ("dec_fc1", 13377, 4096, 1024, "gelu"),
+              ("dec_proj_plain", 13377, 1024, 1024, None), ("dec_proj_f32", 13377, 1024, 1024, "f32"), ("dit_o_f32res", 8192, 1536, 1536, "res"),
+              ("dit_o_f32", 8192, 1536, 1536, "f32")]
     for name, M, N, K, ep in shapes:
         x = torch.randn(M, K, device="cuda").bfloat16()
         w = (torch.randn(N, K, device="cuda") / K ** 0.5).bfloat16()
@@ -23,9 +25,11 @@ def main():
         if ep == "res":
             res = torch.randn(M, N, device="cuda")
             kw = dict(residual=res, out=res, gate=torch.ones(N, device="cuda"), round_linear=True)
+        elif ep == "f32":
+            kw = dict(out=torch.empty(M, N, device="cuda"))
         elif ep:
             kw = dict(act=ep)
-        for two in (True, False):
+        for two in (True,):
             for _ in range(3):
                 ops.gemm(x, w, bias, two_cta=two, **kw)
             tr = torch.zeros(148, 8, dtype=torch.int64, device="cuda")
