@@ -64,6 +64,7 @@ int vist3a_set_pdl(int32_t enable);
 #define VIST3A_GEMM_FLAG_2CTA 1u       /* use cta_group::2 pairs (256-row tiles) */
 #define VIST3A_GEMM_FLAG_1CTA 2u       /* force single-CTA tiles */
 #define VIST3A_GEMM_FLAG_MULTICAST 8u  /* pairs only, even number of 256-wide column tiles: clusters of two pairs share the A rows by TMA multicast */
+#define VIST3A_GEMM_FLAG_STAGED_F32 16u /* A/B: fp32 output through the shared-memory staging buffer instead of 256-bit per-thread accesses */
 #define VIST3A_GEMM_FLAG_BN176 4u      /* A/B: 176-wide column tiles for CTA pairs where they fill the waves better (measured slower) */
 
 /* row -> memory-row mapping of C / residual:  mem_row = (row / rpg) * gstride + goff + row % rpg   (rpg == 0: identity).
@@ -394,10 +395,10 @@ int vist3a_gs_rasterize(const void* project_workspace, int64_t n_gaussians, int6
 int vist3a_vae_rmsnorm(const void* x, int64_t ldx, const float* gamma, void* y, int64_t ldy, int64_t rows, int64_t C, int32_t silu, void* stream);
 /* p[r, :] = softmax(scale * s[r, :]) in bf16 from fp32 logits.  replaces: the softmax inside F.scaled_dot_product_attention of
  * WanAttentionBlock (:463-467: one head of width C over the H*W positions of a frame). */
-int vist3a_softmax_rows(const float* s, void* p, int64_t rows, int64_t L, int64_t ldp, float scale, void* stream);
+int vist3a_softmax_rows(const float* s, void* p, int64_t rows, int64_t L, int64_t valid, int64_t ldp, float scale, void* stream);
 /* out[2t + half, p, :] = y[t, p, half*C : (half+1)*C]  (y [T, P, 2C] -> out [2T, P, C], bf16).  replaces: the channel-halves-to-time
  * interleave of WanResample "upsample3d" (:304-306). */
-int vist3a_time_interleave(const void* y, void* out, int64_t T, int64_t P, int64_t C, void* stream);
+int vist3a_time_interleave(const void* y, int64_t ldy, void* out, int64_t ldo, int64_t T, int64_t P, int64_t C, void* stream);
 /* out[c, r] = in[r, c]  (bf16 [R, C] with row stride ld_in -> [C, R]): V^T operand of the mid-block attention's P V GEMM */
 int vist3a_transpose_bf16(const void* in, int64_t ld_in, void* out, int64_t ld_out, int64_t R, int64_t C, void* stream);
 /* depth-to-space (k = 2) of the parity-decomposed up-sampling convolution: in [n*h*w, 4*C] (col = (py*2 + px)*C + c) -> NHWC bf16

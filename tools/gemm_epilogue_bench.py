@@ -40,7 +40,9 @@ for name, M, N, K in (("dec_proj", 13377, 1024, 1024), ("dec_fc2", 13377, 1024, 
                     ("fp32+bias", lambda: ops.gemm(a, w, bias, out=o32)),
                     ("fp32+bias+res", lambda: ops.gemm(a, w, bias, residual=res32, out=o32)),
                     ("fp32+bias+gate+res", lambda: ops.gemm(a, w, bias, gate=gate, residual=res32, out=o32)),
-                    ("fp32+bias+gate+res_inplace", lambda: ops.gemm(a, w, bias, gate=gate, residual=o32, out=o32))):
+                    ("fp32+bias+gate+res_inplace", lambda: ops.gemm(a, w, bias, gate=gate, residual=o32, out=o32)),
+                    ("STAGED fp32", lambda: ops.gemm(a, w, out=o32, staged_f32=True)),
+                    ("STAGED fp32+bias+gate+res", lambda: ops.gemm(a, w, bias, gate=gate, residual=res32, out=o32, staged_f32=True))):
         ms = timeit(fn)
         rows[tag] = {"us": round(ms * 1e3, 1), "tflops": round(2.0 * M * N * K / ms / 1e9, 1)}
     print(json.dumps({"name": name, "M": M, "N": N, "K": K, **rows}), flush=True)

@@ -95,6 +95,22 @@ def main():
     small = rn(13, 256, 256, 128, dtype=torch.float32)
     add("bilinear_256_to_448", lambda: ops.bilinear_nhwc(small, 448, 448))
 
+    # ---- Wan VAE decode: causal 3x3x3 convolution as the temporal-tap conv mode (bf16, 192 channels at 256 x 256), RMS norm + SiLU, row softmax
+    va = rn(7, 256, 256, 192)
+    wv, bv = rn(192, 27 * 192, scale=(27 * 192) ** -0.5), rn(192, dtype=torch.float32)
+    ov = torch.empty(7 * 256 * 256, 192, device=dev, dtype=bf)
+    add("gemm_vae_conv3x3x3_bf16", lambda: ops.gemm(va, wv, bv, conv=dict(kh=3, kw=3, pad=1, kt=3), out=ov))
+    vx = rn(13, 512, 512, 128)
+    vg = rn(96, dtype=torch.float32)
+    vo = torch.empty_like(vx)
+    add("vae_rmsnorm_silu", lambda: ops.vae_rmsnorm(vx, vg, 96, out=vo))
+    lg = rn(4096, 4096, dtype=torch.float32)
+    pr = torch.empty(4096, 4096, device=dev, dtype=bf)
+    add("softmax_rows", lambda: ops.softmax_rows(lg, 384 ** -0.5, out=pr))
+    # ---- Gaussian epilogue of the decoder and the confidence-quantile select
+    conf = 1.0 + torch.randn(2609152, device=dev, generator=g).exp()
+    add("quantile_radix_select", lambda: ops.quantile(conf, 0.1))
+
     for name, fn in targets:   # warm-up outside the profiled range (function attributes, descriptors)
         fn()
     torch.cuda.synchronize()

@@ -15,6 +15,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--iters", type=int, default=5)
     ap.add_argument("--detail", action="store_true")
+    ap.add_argument("--ncu", action="store_true", help="one warm decode between cudaProfilerStart/Stop (ncu --profile-from-start off)")
     a = ap.parse_args()
     m = WanVAEDecoderB200.from_state_dict(random_state_dict(), None, "cuda")
     g = torch.Generator(device="cuda").manual_seed(1)
@@ -22,6 +23,12 @@ def main():
     for _ in range(2):
         out = m.decode(z, return_dict=False)[0]
     torch.cuda.synchronize()
+    if a.ncu:
+        torch.cuda.profiler.start()
+        m.decode(z, return_dict=False)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        return
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s.record()
     for _ in range(a.iters):

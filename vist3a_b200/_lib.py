@@ -17,7 +17,7 @@ OK = 0
 ERR_INVALID, ERR_ARCH, ERR_CUDA, ERR_UNSUPPORTED = -1, -2, -3, -4
 DTYPE_BF16, DTYPE_F32 = 0, 1
 ACT_NONE, ACT_GELU_TANH, ACT_GELU_ERF, ACT_SILU, ACT_RELU = 0, 1, 2, 3, 4
-GEMM_FLAG_2CTA, GEMM_FLAG_1CTA, GEMM_FLAG_BN176, GEMM_FLAG_MULTICAST = 1, 2, 4, 8
+GEMM_FLAG_2CTA, GEMM_FLAG_1CTA, GEMM_FLAG_BN176, GEMM_FLAG_MULTICAST, GEMM_FLAG_STAGED_F32 = 1, 2, 4, 8, 16
 
 # every symbol include/vist3a_sm100.h declares (tests check the built library exports all of them)
 EXPORTS = (
@@ -214,8 +214,8 @@ def load(build_if_missing: bool = False) -> C.CDLL:
     lib.vist3a_gs_project.argtypes = [vp, vp, vp, vp, i64, i32, i64, fp, fp, i64, i64, f32, f32, f32, f32, vp, i64, vp, vp]
     lib.vist3a_gs_rasterize.argtypes = [vp, i64, i64, i64, i64, fp, vp, i64, vp, vp, vp, vp]
     lib.vist3a_vae_rmsnorm.argtypes = [vp, i64, vp, vp, i64, i64, i64, i32, vp]
-    lib.vist3a_softmax_rows.argtypes = [vp, vp, i64, i64, i64, f32, vp]
-    lib.vist3a_time_interleave.argtypes = [vp, vp, i64, i64, i64, vp]
+    lib.vist3a_softmax_rows.argtypes = [vp, vp, i64, i64, i64, i64, f32, vp]
+    lib.vist3a_time_interleave.argtypes = [vp, i64, vp, i64, i64, i64, i64, vp]
     lib.vist3a_transpose_bf16.argtypes = [vp, i64, vp, i64, i64, i64, vp]
     lib.vist3a_depth_to_space2_bf16.argtypes = [vp, vp, i64, i64, i64, i64, i64, vp]
     lib.vist3a_latent_to_ndhwc.argtypes = [vp, i32, vp, i64, i64, i64, vp]

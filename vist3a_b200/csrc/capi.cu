@@ -55,8 +55,8 @@ int unpatchify_entry(const void*, int, long long, void*, int, long long, long lo
 int cfg_combine_entry(const void*, const void*, int, float, float*, long long, cudaStream_t);
 int axpby_entry(float*, int, const float* const*, const float*, long long, cudaStream_t);
 int vae_rmsnorm_entry(const void*, long long, const float*, void*, long long, long long, long long, int, cudaStream_t);
-int softmax_rows_entry(const float*, void*, long long, long long, long long, float, cudaStream_t);
-int time_interleave_entry(const void*, void*, long long, long long, long long, cudaStream_t);
+int softmax_rows_entry(const float*, void*, long long, long long, long long, long long, float, cudaStream_t);
+int time_interleave_entry(const void*, long long, void*, long long, long long, long long, long long, cudaStream_t);
 int transpose_bf16_entry(const void*, long long, void*, long long, long long, long long, cudaStream_t);
 int depth_to_space2_bf16_entry(const void*, void*, long long, long long, long long, long long, long long, cudaStream_t);
 int latent_to_ndhwc_entry(const void*, int, void*, long long, long long, long long, cudaStream_t);
@@ -188,10 +188,12 @@ int vist3a_fmha_fwd(const vist3a_fmha_args* args, void* stream) { return fmha_en
 int vist3a_vae_rmsnorm(const void* x, int64_t ldx, const float* gamma, void* y, int64_t ldy, int64_t rows, int64_t C, int32_t silu, void* stream) {
   return vae_rmsnorm_entry(x, ldx, gamma, y, ldy, rows, C, silu, ST(stream));
 }
-int vist3a_softmax_rows(const float* s, void* p, int64_t rows, int64_t L, int64_t ldp, float scale, void* stream) {
-  return softmax_rows_entry(s, p, rows, L, ldp, scale, ST(stream));
+int vist3a_softmax_rows(const float* s, void* p, int64_t rows, int64_t L, int64_t valid, int64_t ldp, float scale, void* stream) {
+  return softmax_rows_entry(s, p, rows, L, valid, ldp, scale, ST(stream));
 }
-int vist3a_time_interleave(const void* y, void* out, int64_t T, int64_t P, int64_t C, void* stream) { return time_interleave_entry(y, out, T, P, C, ST(stream)); }
+int vist3a_time_interleave(const void* y, int64_t ldy, void* out, int64_t ldo, int64_t T, int64_t P, int64_t C, void* stream) {
+  return time_interleave_entry(y, ldy, out, ldo, T, P, C, ST(stream));
+}
 int vist3a_transpose_bf16(const void* in, int64_t ld_in, void* out, int64_t ld_out, int64_t R, int64_t C, void* stream) {
   return transpose_bf16_entry(in, ld_in, out, ld_out, R, C, ST(stream));
 }

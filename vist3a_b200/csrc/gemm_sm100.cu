@@ -130,7 +130,9 @@ __device__ __forceinline__ void add_row32(float (&v)[32], const void* base, long
 
 constexpr int kGemmThreads = 384;  // warps 0-3: TMA / MMA / TMEM alloc / idle; warps 4-11: epilogue
 
-template <int BN, int kCta, bool kTF32>
+// kDirect: fp32 output written (and an fp32 residual read) by 256-bit per-thread accesses in the accumulator's row layout, no staging buffer.
+// A separate instantiation, so that its registers do not weigh on the staged path (a spill there goes to L2: the kernel leaves no L1).
+template <int BN, int kCta, bool kTF32, bool kDirect = false>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmA64,
                     const GemmShape shape, const GemmEpilogue ep) {
@@ -357,6 +359,80 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       if (chunk_ok(0)) tmem_ld_x32(taddr + (uint32_t)(chunk_of(0) * 32), r);
       bool released = false;
       int blk_n0 = 0, blk_bytes = 0;  // first column / valid bytes per row of the block being staged
+      if constexpr (kDirect) {
+        // ---- fp32 output without staging: every thread owns 32 consecutive columns of its row = 4 sectors of 32 bytes, which LDG.256 /
+        //      STG.256 move whole.  The staging that coalesces 16-byte pieces into lines costs 512 KB of shared-memory traffic per
+        //      128 x 256 tile with a residual, on top of what the main loop moves through the same 128 B/clk port.
+        (void)blk_n0; (void)blk_bytes;
+#pragma unroll 1
+        for (int k = 0; chunk_ok(k); ++k) {
+          const int n0 = n_tile + chunk_of(k) * 32;
+          float4 bvv[8];
+          if (ep.bias) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) bvv[j] = __ldg(reinterpret_cast<const float4*>(ep.bias + n0) + j);
+          }
+          const float* rp = (ep.residual && row_ok) ? reinterpret_cast<const float*>(ep.residual) + rrow * ep.ldr + n0 : nullptr;
+          float rs[32];
+          if (rp) {   // issued before the wait for the accumulator
+#pragma unroll
+            for (int j = 0; j < 32; j += 8)
+              asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                           : "=f"(rs[j]), "=f"(rs[j + 1]), "=f"(rs[j + 2]), "=f"(rs[j + 3]), "=f"(rs[j + 4]), "=f"(rs[j + 5]), "=f"(rs[j + 6]), "=f"(rs[j + 7])
+                           : "l"(rp + j));
+          }
+          tmem_ld_wait();
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          if (chunk_ok(k + 1)) {
+            tmem_ld_x32(taddr + (uint32_t)(chunk_of(k + 1) * 32), r);
+          } else {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              if constexpr (kCta == 1) mbar_arrive(tempty_bar(as)); else mbar_arrive_cluster(tempty_bar(as), 2 * pr);
+            }
+            released = true;
+          }
+          if (row_ok) {
+            if (ep.bias) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                const float4 bv = bvv[j >> 2];
+                v[j] += bv.x; v[j + 1] += bv.y; v[j + 2] += bv.z; v[j + 3] += bv.w;
+              }
+            }
+            if (ep.act != VIST3A_ACT_NONE) apply_act32(v, ep.act);
+            if (ep.round_linear) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = bf16_round(v[j]);
+            }
+            if (gate_row) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                const float4 g = __ldg(reinterpret_cast<const float4*>(gate_row + n0 + j));
+                v[j] *= g.x; v[j + 1] *= g.y; v[j + 2] *= g.z; v[j + 3] *= g.w;
+              }
+              if (ep.round_gate) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = bf16_round(v[j]);
+              }
+            }
+            if (rp) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] += rs[j];
+            }
+            if (ep.post_act == VIST3A_ACT_RELU) act32<VIST3A_ACT_RELU>(v);
+            float* cp = reinterpret_cast<float*>(ep.C) + crow * ep.ldc + n0;
+#pragma unroll
+            for (int j = 0; j < 32; j += 8)
+              asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(cp + j), "f"(v[j]), "f"(v[j + 1]), "f"(v[j + 2]), "f"(v[j + 3]),
+                           "f"(v[j + 4]), "f"(v[j + 5]), "f"(v[j + 6]), "f"(v[j + 7])
+                           : "memory");
+          }
+        }
+      } else
 #pragma unroll 1
       for (int k = 0; chunk_ok(k); ++k) {
         const int n0 = n_tile + chunk_of(k) * 32;
@@ -602,9 +678,12 @@ static int launch_gemm(const vist3a_gemm_args& a, cudaStream_t stream) {
   ep.act = a.act; ep.post_act = a.post_act; ep.round_linear = a.round_linear; ep.round_gate = a.round_gate;
   ep.trace = g_gemm_trace.load(std::memory_order_relaxed);
 
-  auto kern = gemm_tcgen05_kernel<BN, kCta, kTF32>;
-  static std::atomic<unsigned long long> attr_done{0};  // per template instantiation, one bit per device
-  V3A_CUDA_OK(ensure_dynamic_smem(kern, Cfg::SMEM_BYTES, attr_done));
+  // fp32 output through 256-bit per-thread accesses when the layout allows it (whole 32-column chunks, 32-byte aligned rows)
+  const bool direct = ep.out_fp32 && !(a.flags & VIST3A_GEMM_FLAG_STAGED_F32) && a.N % 32 == 0 && a.ldc % 8 == 0 && ((uintptr_t)a.C & 31) == 0 &&
+                      (!a.residual || (a.ldr % 8 == 0 && ((uintptr_t)a.residual & 31) == 0)) && !a.residual2;
+  auto kern = direct ? gemm_tcgen05_kernel<BN, kCta, kTF32, true> : gemm_tcgen05_kernel<BN, kCta, kTF32, false>;
+  static std::atomic<unsigned long long> attr_done[2];  // per template instantiation (staged / direct), one bit per device
+  V3A_CUDA_OK(ensure_dynamic_smem(kern, Cfg::SMEM_BYTES, attr_done[direct ? 1 : 0]));
   if (a.conv.enabled) tmA64 = tmA;
   shape.mc = (kCta == 2 && BN == 256 && !a.conv.enabled && (a.flags & VIST3A_GEMM_FLAG_MULTICAST) && shape.tiles_n % 2 == 0) ? 1 : 0;
   const int csize = shape.mc ? 4 : kCta;

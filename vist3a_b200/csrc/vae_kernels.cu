@@ -91,13 +91,25 @@ __global__ void __launch_bounds__(256) vae_rmsnorm_kernel(const __nv_bfloat16* _
 
 // p[r, :] = softmax(scale * s[r, :]) as bf16; s fp32 [rows, L] (the logits GEMM writes fp32), L % 4 == 0.  One block per row; the row is
 // read twice (online max + sum, then the normalised write): 4096 x 4096 fp32 per frame = 64 MB, L2 resident between the passes.
-__global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restrict__ s, __nv_bfloat16* __restrict__ p, int L, long long ldp, float scale) {
+__global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restrict__ s, __nv_bfloat16* __restrict__ p, int L, int valid, long long ldp, float scale) {
   const float* sr = s + (long long)blockIdx.x * L;
   __nv_bfloat16* pr = p + (long long)blockIdx.x * ldp;
   float m = -INFINITY, sum = 0.f;
+  // columns [valid, L) are padding (ragged H*W padded to the GEMM's granularity): they count as -inf and come out as P = 0
+  auto masked = [&](int i) {
+    float4 v = *reinterpret_cast<const float4*>(sr + i);
+    if (i + 3 >= valid) {
+      if (i >= valid) v.x = -INFINITY;
+      if (i + 1 >= valid) v.y = -INFINITY;
+      if (i + 2 >= valid) v.z = -INFINITY;
+      v.w = -INFINITY;
+    }
+    return v;
+  };
   for (int i = threadIdx.x * 4; i < L; i += 256 * 4) {
-    const float4 v = *reinterpret_cast<const float4*>(sr + i);
+    const float4 v = masked(i);
     const float mx = fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)) * scale;
+    if (mx == -INFINITY) continue;
     if (mx > m) {
       sum *= __expf(m - mx);   // m = -inf at first: exp(-inf) = 0, sum is 0 anyway
       m = mx;
@@ -122,7 +134,7 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restri
   for (int w = 0; w < 8; ++w) S += (sm[w] == -INFINITY) ? 0.f : ssum[w] * __expf(sm[w] - M);
   const float inv = 1.f / S;
   for (int i = threadIdx.x * 4; i < L; i += 256 * 4) {
-    const float4 v = *reinterpret_cast<const float4*>(sr + i);
+    const float4 v = masked(i);
     uint2 o;
     o.x = pack2bf(__expf(v.x * scale - M) * inv, __expf(v.y * scale - M) * inv);
     o.y = pack2bf(__expf(v.z * scale - M) * inv, __expf(v.w * scale - M) * inv);
@@ -131,15 +143,15 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restri
 }
 
 // temporal up-sampling: y [T, P, 2C] (time_conv output, P = H*W pixels) -> out [2T, P, C]: out[2t + half, p, :] = y[t, p, half*C : half*C + C]
-__global__ void __launch_bounds__(256) time_interleave_kernel(const __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restrict__ out, long long T,
-                                                              long long P, int C) {
+__global__ void __launch_bounds__(256) time_interleave_kernel(const __nv_bfloat16* __restrict__ y, long long ldy, __nv_bfloat16* __restrict__ out,
+                                                              long long ldo, long long T, long long P, int C) {
   const int cv = C / 8;   // 16-byte chunks per output row
   const long long total = 2 * T * P * cv;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int c = (int)(i % cv);
     const long long row = i / cv, p = row % P, t2 = row / P;
     const long long t = t2 >> 1, half = t2 & 1;
-    reinterpret_cast<uint4*>(out)[i] = reinterpret_cast<const uint4*>(y)[((t * P + p) * 2 + half) * cv + c];
+    *reinterpret_cast<uint4*>(out + row * ldo + c * 8) = *reinterpret_cast<const uint4*>(y + (t * P + p) * ldy + half * C + c * 8);
   }
 }
 
@@ -247,18 +259,20 @@ int vae_rmsnorm_entry(const void* x, long long ldx, const float* gamma, void* y,
   return VIST3A_OK;
 }
 
-int softmax_rows_entry(const float* s, void* p, long long rows, long long L, long long ldp, float scale, cudaStream_t st) {
-  V3A_REQUIRE(s && p && rows > 0 && rows <= 0x7fffffff && L > 0 && L % 4 == 0 && L <= 0x7fffffff && ldp >= L && ldp % 4 == 0, VIST3A_ERR_INVALID,
-              "softmax_rows: L and the output row stride must be positive multiples of 4, stride >= L");
-  softmax_rows_kernel<<<(unsigned)rows, 256, 0, st>>>(s, (__nv_bfloat16*)p, (int)L, ldp, scale);
+int softmax_rows_entry(const float* s, void* p, long long rows, long long L, long long valid, long long ldp, float scale, cudaStream_t st) {
+  V3A_REQUIRE(s && p && rows > 0 && rows <= 0x7fffffff && L > 0 && L % 4 == 0 && L <= 0x7fffffff && ldp >= L && ldp % 4 == 0 && valid > 0 && valid <= L,
+              VIST3A_ERR_INVALID, "softmax_rows: L and the output row stride must be positive multiples of 4, stride >= L, 0 < valid <= L");
+  softmax_rows_kernel<<<(unsigned)rows, 256, 0, st>>>(s, (__nv_bfloat16*)p, (int)L, (int)valid, ldp, scale);
   V3A_CUDA_OK(cudaGetLastError());
   launch_counter().fetch_add(1);
   return VIST3A_OK;
 }
 
-int time_interleave_entry(const void* y, void* out, long long T, long long P, long long C, cudaStream_t st) {
-  V3A_REQUIRE(y && out && T > 0 && P > 0 && C > 0 && C % 8 == 0, VIST3A_ERR_INVALID, "time_interleave: C must be a multiple of 8");
-  time_interleave_kernel<<<blocks_for(2 * T * P * (C / 8), 256, num_sms() * 8), 256, 0, st>>>((const __nv_bfloat16*)y, (__nv_bfloat16*)out, T, P, (int)C);
+int time_interleave_entry(const void* y, long long ldy, void* out, long long ldo, long long T, long long P, long long C, cudaStream_t st) {
+  V3A_REQUIRE(y && out && T > 0 && P > 0 && C > 0 && C % 8 == 0 && ldy >= 2 * C && ldo >= C && ldy % 8 == 0 && ldo % 8 == 0, VIST3A_ERR_INVALID,
+              "time_interleave: C and the row strides must be multiples of 8, ldy >= 2C, ldo >= C");
+  time_interleave_kernel<<<blocks_for(2 * T * P * (C / 8), 256, num_sms() * 8), 256, 0, st>>>((const __nv_bfloat16*)y, ldy, (__nv_bfloat16*)out, ldo, T, P,
+                                                                                             (int)C);
   V3A_CUDA_OK(cudaGetLastError());
   launch_counter().fetch_add(1);
   return VIST3A_OK;

@@ -52,7 +52,8 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
          gate: Optional[torch.Tensor] = None, gate_bstride: int = 0, rows_per_batch: int = 0,
          residual: Optional[torch.Tensor] = None, round_linear: bool = False, round_gate: bool = False,
          two_cta: Optional[bool] = None, residual2: Optional[torch.Tensor] = None, post_act=None,
-         cmap: Optional[tuple] = None, rmap: Optional[tuple] = None, conv: Optional[dict] = None, bn176: bool = False, multicast: bool = False) -> torch.Tensor:
+         cmap: Optional[tuple] = None, rmap: Optional[tuple] = None, conv: Optional[dict] = None, bn176: bool = False, multicast: bool = False,
+         staged_f32: bool = False) -> torch.Tensor:
     """out[M,N] = epilogue(a[M,K] @ w[N,K]^T); see vist3a_gemm in include/vist3a_sm100.h.
     cmap / rmap = (rows_per_group, group_stride, group_offset) row maps of out(+residual2) / residual;
     conv = dict(kh, kw, pad) with `a` an NHWC [n, h, w, c] tensor: implicit-GEMM convolution (stride 1).  Optional conv keys
@@ -124,7 +125,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
     args.round_linear, args.round_gate = int(round_linear), int(round_gate)
     if two_cta is None:
         two_cta = M >= 2048
-    args.flags = (L.GEMM_FLAG_2CTA if two_cta else L.GEMM_FLAG_1CTA) | (L.GEMM_FLAG_BN176 if bn176 else 0) | (L.GEMM_FLAG_MULTICAST if multicast else 0)
+    args.flags = (L.GEMM_FLAG_2CTA if two_cta else L.GEMM_FLAG_1CTA) | (L.GEMM_FLAG_BN176 if bn176 else 0) | (L.GEMM_FLAG_MULTICAST if multicast else 0) | (L.GEMM_FLAG_STAGED_F32 if staged_f32 else 0)
     L.check(L.load().vist3a_gemm(C.byref(args), _stream()))
     return out
 
@@ -702,8 +703,8 @@ def vae_rmsnorm(x: torch.Tensor, gamma: torch.Tensor, C: int, *, silu: bool = Tr
     return out
 
 
-def softmax_rows(s: torch.Tensor, scale: float, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """softmax(scale * s) per row: fp32 [rows, L] -> bf16 [rows, L] (`out` may have a padded row stride)."""
+def softmax_rows(s: torch.Tensor, scale: float, out: Optional[torch.Tensor] = None, valid: Optional[int] = None) -> torch.Tensor:
+    """softmax(scale * s) per row: fp32 [rows, L] -> bf16 [rows, L] (`out` may have a padded row stride); columns >= valid are padding (P = 0)."""
     _need_cuda(s, out)
     if s.dim() != 2 or s.dtype != torch.float32 or not s.is_contiguous():
         raise TypeError("softmax_rows: contiguous float32 [rows, L] expected")
@@ -711,17 +712,21 @@ def softmax_rows(s: torch.Tensor, scale: float, out: Optional[torch.Tensor] = No
         out = torch.empty(s.shape, dtype=torch.bfloat16, device=s.device)
     if out.shape != s.shape or out.dtype != torch.bfloat16 or out.stride(1) != 1:
         raise TypeError("softmax_rows: out must be bfloat16 [rows, L] with unit inner stride")
-    L.check(L.load().vist3a_softmax_rows(s.data_ptr(), out.data_ptr(), s.shape[0], s.shape[1], out.stride(0), float(scale), _stream()))
+    L.check(L.load().vist3a_softmax_rows(s.data_ptr(), out.data_ptr(), s.shape[0], s.shape[1], s.shape[1] if valid is None else int(valid), out.stride(0),
+                                        float(scale), _stream()))
     return out
 
 
-def time_interleave(y: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
-    """y [T, H, W, 2C] bf16 -> out [2T, H, W, C]: out[2t + half] = y[t, ..., half*C:(half+1)*C]."""
+def time_interleave(y: torch.Tensor, out: torch.Tensor, C: Optional[int] = None) -> torch.Tensor:
+    """y [T, H, W, ldy] bf16 (channels [0, 2C) valid) -> out [2T, H, W, ldo] (channels [0, C) written): out[2t + half] = y[t, ..., half*C:(half+1)*C].
+    C defaults to ldy / 2 (dense rows)."""
     _need_cuda(y, out)
-    T, H, W, C2 = y.shape
-    if not y.is_contiguous() or not out.is_contiguous() or out.shape != (2 * T, H, W, C2 // 2) or y.dtype != torch.bfloat16 or out.dtype != torch.bfloat16:
-        raise ValueError("time_interleave: y [T, H, W, 2C] and out [2T, H, W, C] contiguous bfloat16 expected")
-    L.check(L.load().vist3a_time_interleave(y.data_ptr(), out.data_ptr(), T, H * W, C2 // 2, _stream()))
+    T, H, W, ldy = y.shape
+    C = ldy // 2 if C is None else C
+    if (not y.is_contiguous() or not out.is_contiguous() or out.shape[:3] != (2 * T, H, W) or out.shape[3] < C or ldy < 2 * C
+            or y.dtype != torch.bfloat16 or out.dtype != torch.bfloat16):
+        raise ValueError("time_interleave: y [T, H, W, >= 2C] and out [2T, H, W, >= C] contiguous bfloat16 expected")
+    L.check(L.load().vist3a_time_interleave(y.data_ptr(), ldy, out.data_ptr(), out.shape[3], T, H * W, C, _stream()))
     return out
 
 

@@ -219,15 +219,19 @@ class WanVAEDecoderB200(torch.nn.Module):
         T, H, W, ld = x.shape
         HW = H * W
         n = ops.vae_rmsnorm(x, w[p + ".norm.gamma"], C, silu=False)
-        qkv = ops.gemm(n.view(-1, ld)[:, :C], w[p + ".to_qkv.w"], w[p + ".to_qkv.b"])          # [T*HW, 3C] bf16
+        # ragged H*W (not a multiple of 8: the GEMM's N / 16-byte row granularity): keys and values are read HW8 >= HW rows deep -- the rows
+        # behind a frame belong to the next frame, behind the last frame to 8 zero rows -- and the softmax masks the padding columns (P = 0)
+        HW8 = (HW + 7) // 8 * 8
+        qkv = (torch.empty if HW8 == HW else torch.zeros)((T * HW + HW8 - HW, 3 * C), dtype=torch.bfloat16, device=x.device)
+        ops.gemm(n.view(-1, ld)[:, :C], w[p + ".to_qkv.w"], w[p + ".to_qkv.b"], out=qkv[:T * HW])  # [T*HW, 3C] bf16
         att = torch.empty((T * HW, C), dtype=torch.bfloat16, device=x.device)
-        logits = torch.empty((HW, HW), dtype=torch.float32, device=x.device)
-        probs = torch.empty((HW, (HW + 7) // 8 * 8), dtype=torch.bfloat16, device=x.device)[:, :HW]   # row stride: a 16-byte multiple (TMA)
+        logits = torch.empty((HW, HW8), dtype=torch.float32, device=x.device)
+        probs = torch.empty((HW, HW8), dtype=torch.bfloat16, device=x.device)
         for t in range(T):
-            f = qkv[t * HW:(t + 1) * HW]
-            ops.gemm(f[:, :C], f[:, C:2 * C], out=logits)                                       # q k^T
-            ops.softmax_rows(logits, C ** -0.5, out=probs)
-            ops.gemm(probs, ops.transpose_bf16(f[:, 2 * C:]), out=att[t * HW:(t + 1) * HW])     # P v
+            f = qkv[t * HW:t * HW + HW8]
+            ops.gemm(f[:HW, :C], f[:, C:2 * C], out=logits)                                      # q k^T
+            ops.softmax_rows(logits, C ** -0.5, out=probs, valid=HW)
+            ops.gemm(probs, ops.transpose_bf16(f[:, 2 * C:]), out=att[t * HW:(t + 1) * HW])      # P v
         out = torch.empty_like(x)
         ops.gemm(att, w[p + ".proj.w"], w[p + ".proj.b"], residual=x.view(-1, ld)[:, :C], out=out.view(-1, ld)[:, :C])
         return out
@@ -239,9 +243,9 @@ class WanVAEDecoderB200(torch.nn.Module):
         T, H, W, ld = x.shape
         if temporal and T > 1:
             y = self._conv(x[1:], p + ".time_conv", C)                                          # [T-1, H, W, 2C]
-            xn = torch.empty((2 * T - 1, H, W, ld), dtype=torch.bfloat16, device=x.device)
+            xn = (torch.empty if ld == C else torch.zeros)((2 * T - 1, H, W, ld), dtype=torch.bfloat16, device=x.device)   # padding channels: finite (they meet zero weights)
             xn[0].copy_(x[0])
-            ops.time_interleave(y, xn[1:])
+            ops.time_interleave(y, xn[1:], C)
             x, T = xn, 2 * T - 1
         wt, b = w[p + ".resample.w"], w[p + ".resample.b"]
         co = wt.shape[0] // 4
