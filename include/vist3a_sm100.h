@@ -64,7 +64,7 @@ int vist3a_set_pdl(int32_t enable);
 #define VIST3A_GEMM_FLAG_2CTA 1u       /* use cta_group::2 pairs (256-row tiles) */
 #define VIST3A_GEMM_FLAG_1CTA 2u       /* force single-CTA tiles */
 #define VIST3A_GEMM_FLAG_MULTICAST 8u  /* pairs only, even number of 256-wide column tiles: clusters of two pairs share the A rows by TMA multicast */
-#define VIST3A_GEMM_FLAG_STAGED_F32 16u /* A/B: fp32 output through the shared-memory staging buffer instead of 256-bit per-thread accesses */
+#define VIST3A_GEMM_FLAG_STAGED 16u    /* A/B: output / residual through the shared-memory staging buffer instead of 256-bit per-thread accesses */
 #define VIST3A_GEMM_FLAG_BN176 4u      /* A/B: 176-wide column tiles for CTA pairs where they fill the waves better (measured slower) */
 
 /* row -> memory-row mapping of C / residual:  mem_row = (row / rpg) * gstride + goff + row % rpg   (rpg == 0: identity).

@@ -24,7 +24,7 @@ def timeit(fn, iters=15):
     return ts[len(ts) // 2]
 
 
-for name, M, N, K in (("dec_proj", 13377, 1024, 1024), ("dec_fc2", 13377, 1024, 4096), ("dit_o", 8192, 1536, 1536), ("dit_ffn2", 8192, 1536, 8960)):
+for name, M, N, K in (("dec_proj", 13377, 1024, 1024), ("dec_fc2", 13377, 1024, 4096), ("dit_o", 8192, 1536, 1536), ("dit_ffn2", 8192, 1536, 8960), ("dit_qkv", 8192, 4608, 1536), ("dit_ffn1", 8192, 8960, 1536)):
     a = torch.randn(M, K, device="cuda").bfloat16()
     w = torch.randn(N, K, device="cuda").bfloat16() * 0.05
     bias = torch.randn(N, device="cuda")
@@ -41,8 +41,11 @@ for name, M, N, K in (("dec_proj", 13377, 1024, 1024), ("dec_fc2", 13377, 1024, 
                     ("fp32+bias+res", lambda: ops.gemm(a, w, bias, residual=res32, out=o32)),
                     ("fp32+bias+gate+res", lambda: ops.gemm(a, w, bias, gate=gate, residual=res32, out=o32)),
                     ("fp32+bias+gate+res_inplace", lambda: ops.gemm(a, w, bias, gate=gate, residual=o32, out=o32)),
-                    ("STAGED fp32", lambda: ops.gemm(a, w, out=o32, staged_f32=True)),
-                    ("STAGED fp32+bias+gate+res", lambda: ops.gemm(a, w, bias, gate=gate, residual=res32, out=o32, staged_f32=True))):
+                    ("STAGED bf16", lambda: ops.gemm(a, w, out=o16, staged=True)),
+                    ("STAGED bf16+bias+res16", lambda: ops.gemm(a, w, bias, residual=res16, out=o16, staged=True)),
+                    ("STAGED fp32", lambda: ops.gemm(a, w, out=o32, staged=True)),
+                    ("STAGED fp32+bias+gate+res", lambda: ops.gemm(a, w, bias, gate=gate, residual=res32, out=o32, staged=True)),
+                    ("bf16 (again)", lambda: ops.gemm(a, w, out=o16))):
         ms = timeit(fn)
         rows[tag] = {"us": round(ms * 1e3, 1), "tflops": round(2.0 * M * N * K / ms / 1e9, 1)}
     print(json.dumps({"name": name, "M": M, "N": N, "K": K, **rows}), flush=True)

@@ -17,7 +17,7 @@ OK = 0
 ERR_INVALID, ERR_ARCH, ERR_CUDA, ERR_UNSUPPORTED = -1, -2, -3, -4
 DTYPE_BF16, DTYPE_F32 = 0, 1
 ACT_NONE, ACT_GELU_TANH, ACT_GELU_ERF, ACT_SILU, ACT_RELU = 0, 1, 2, 3, 4
-GEMM_FLAG_2CTA, GEMM_FLAG_1CTA, GEMM_FLAG_BN176, GEMM_FLAG_MULTICAST, GEMM_FLAG_STAGED_F32 = 1, 2, 4, 8, 16
+GEMM_FLAG_2CTA, GEMM_FLAG_1CTA, GEMM_FLAG_BN176, GEMM_FLAG_MULTICAST, GEMM_FLAG_STAGED = 1, 2, 4, 8, 16
 
 # every symbol include/vist3a_sm100.h declares (tests check the built library exports all of them)
 EXPORTS = (

@@ -372,14 +372,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
             for (int j = 0; j < 8; ++j) bvv[j] = __ldg(reinterpret_cast<const float4*>(ep.bias + n0) + j);
           }
-          const float* rp = (ep.residual && row_ok) ? reinterpret_cast<const float*>(ep.residual) + rrow * ep.ldr + n0 : nullptr;
-          float rs[32];
+          const char* rp = (ep.residual && row_ok) ? reinterpret_cast<const char*>(ep.residual) + (rrow * ep.ldr + n0) * (ep.out_fp32 ? 4 : 2) : nullptr;
+          uint32_t rs[32];   // fp32: 32 values; bf16: 16 packed pairs
           if (rp) {   // issued before the wait for the accumulator
 #pragma unroll
-            for (int j = 0; j < 32; j += 8)
-              asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                           : "=f"(rs[j]), "=f"(rs[j + 1]), "=f"(rs[j + 2]), "=f"(rs[j + 3]), "=f"(rs[j + 4]), "=f"(rs[j + 5]), "=f"(rs[j + 6]), "=f"(rs[j + 7])
-                           : "l"(rp + j));
+            for (int j = 0; j < 32; j += 8) {
+              if (ep.out_fp32 || j < 16)
+                asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                             : "=r"(rs[j]), "=r"(rs[j + 1]), "=r"(rs[j + 2]), "=r"(rs[j + 3]), "=r"(rs[j + 4]), "=r"(rs[j + 5]), "=r"(rs[j + 6]), "=r"(rs[j + 7])
+                             : "l"(rp + 4 * j));
+            }
           }
           tmem_ld_wait();
           float v[32];
@@ -420,16 +422,31 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               }
             }
             if (rp) {
+              if (ep.out_fp32) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] += rs[j];
+                for (int j = 0; j < 32; ++j) v[j] += __uint_as_float(rs[j]);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) { v[2 * j] += bf16_lo(rs[j]); v[2 * j + 1] += bf16_hi(rs[j]); }
+              }
             }
             if (ep.post_act == VIST3A_ACT_RELU) act32<VIST3A_ACT_RELU>(v);
-            float* cp = reinterpret_cast<float*>(ep.C) + crow * ep.ldc + n0;
+            if (ep.out_fp32) {
+              float* cp = reinterpret_cast<float*>(ep.C) + crow * ep.ldc + n0;
 #pragma unroll
-            for (int j = 0; j < 32; j += 8)
-              asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(cp + j), "f"(v[j]), "f"(v[j + 1]), "f"(v[j + 2]), "f"(v[j + 3]),
-                           "f"(v[j + 4]), "f"(v[j + 5]), "f"(v[j + 6]), "f"(v[j + 7])
-                           : "memory");
+              for (int j = 0; j < 32; j += 8)
+                asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(cp + j), "f"(v[j]), "f"(v[j + 1]), "f"(v[j + 2]), "f"(v[j + 3]),
+                             "f"(v[j + 4]), "f"(v[j + 5]), "f"(v[j + 6]), "f"(v[j + 7])
+                             : "memory");
+            } else {
+              __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(ep.C) + crow * ep.ldc + n0;
+#pragma unroll
+              for (int j = 0; j < 32; j += 16)
+                asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(cp + j), "r"(pack_bf16(v[j], v[j + 1])), "r"(pack_bf16(v[j + 2], v[j + 3])),
+                             "r"(pack_bf16(v[j + 4], v[j + 5])), "r"(pack_bf16(v[j + 6], v[j + 7])), "r"(pack_bf16(v[j + 8], v[j + 9])),
+                             "r"(pack_bf16(v[j + 10], v[j + 11])), "r"(pack_bf16(v[j + 12], v[j + 13])), "r"(pack_bf16(v[j + 14], v[j + 15]))
+                             : "memory");
+            }
           }
         }
       } else
@@ -679,8 +696,12 @@ static int launch_gemm(const vist3a_gemm_args& a, cudaStream_t stream) {
   ep.trace = g_gemm_trace.load(std::memory_order_relaxed);
 
   // fp32 output through 256-bit per-thread accesses when the layout allows it (whole 32-column chunks, 32-byte aligned rows)
-  const bool direct = ep.out_fp32 && !(a.flags & VIST3A_GEMM_FLAG_STAGED_F32) && a.N % 32 == 0 && a.ldc % 8 == 0 && ((uintptr_t)a.C & 31) == 0 &&
-                      (!a.residual || (a.ldr % 8 == 0 && ((uintptr_t)a.residual & 31) == 0)) && !a.residual2;
+  const long long al = ep.out_fp32 ? 8 : 16;   // elements per 32 bytes
+  const bool direct_ok = BN % 32 == 0 /* (176-wide tiles end in a 16-column chunk) */ && a.N % 32 == 0 && a.ldc % al == 0 && ((uintptr_t)a.C & 31) == 0 &&
+                         (!a.residual || (a.ldr % al == 0 && ((uintptr_t)a.residual & 31) == 0)) && !a.residual2;
+  // direct by default -- same-process A/B (tools/gemm_epilogue_bench.py): fp32 + gate + residual -12 % on the K <= 1536 projections, bf16 + bf16
+  // residual -11..-13 %, plain bf16 -2..-3 % on QKV / FFN1; VIST3A_GEMM_FLAG_STAGED forces the staging-buffer epilogue
+  const bool direct = direct_ok && !(a.flags & VIST3A_GEMM_FLAG_STAGED);
   auto kern = direct ? gemm_tcgen05_kernel<BN, kCta, kTF32, true> : gemm_tcgen05_kernel<BN, kCta, kTF32, false>;
   static std::atomic<unsigned long long> attr_done[2];  // per template instantiation (staged / direct), one bit per device
   V3A_CUDA_OK(ensure_dynamic_smem(kern, Cfg::SMEM_BYTES, attr_done[direct ? 1 : 0]));

@@ -53,7 +53,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
          residual: Optional[torch.Tensor] = None, round_linear: bool = False, round_gate: bool = False,
          two_cta: Optional[bool] = None, residual2: Optional[torch.Tensor] = None, post_act=None,
          cmap: Optional[tuple] = None, rmap: Optional[tuple] = None, conv: Optional[dict] = None, bn176: bool = False, multicast: bool = False,
-         staged_f32: bool = False) -> torch.Tensor:
+         staged: bool = False) -> torch.Tensor:
     """out[M,N] = epilogue(a[M,K] @ w[N,K]^T); see vist3a_gemm in include/vist3a_sm100.h.
     cmap / rmap = (rows_per_group, group_stride, group_offset) row maps of out(+residual2) / residual;
     conv = dict(kh, kw, pad) with `a` an NHWC [n, h, w, c] tensor: implicit-GEMM convolution (stride 1).  Optional conv keys
@@ -125,7 +125,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
     args.round_linear, args.round_gate = int(round_linear), int(round_gate)
     if two_cta is None:
         two_cta = M >= 2048
-    args.flags = (L.GEMM_FLAG_2CTA if two_cta else L.GEMM_FLAG_1CTA) | (L.GEMM_FLAG_BN176 if bn176 else 0) | (L.GEMM_FLAG_MULTICAST if multicast else 0) | (L.GEMM_FLAG_STAGED_F32 if staged_f32 else 0)
+    args.flags = (L.GEMM_FLAG_2CTA if two_cta else L.GEMM_FLAG_1CTA) | (L.GEMM_FLAG_BN176 if bn176 else 0) | (L.GEMM_FLAG_MULTICAST if multicast else 0) | (L.GEMM_FLAG_STAGED if staged else 0)
     L.check(L.load().vist3a_gemm(C.byref(args), _stream()))
     return out
 
