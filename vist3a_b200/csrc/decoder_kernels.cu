@@ -286,12 +286,17 @@ __global__ void __launch_bounds__(128) qknorm_rope2d_head_kernel(__nv_bfloat16* 
   uint4* ptr = reinterpret_cast<uint4*>(qkv + row * ld + ((long long)which * heads + head) * 64);
   const float* wgt = which == 0 ? qw : kw;
   const float* bia = which == 0 ? qb : kb;
+  // 256-bit accesses: a lane's 128 bytes are 4 whole 32-byte sectors (with 16-byte pieces every warp instruction fetched 32 sectors for
+  // half their bytes)
   float x[64];
 #pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    const uint4 u = ptr[k];
-    x[8 * k] = bf16_lo(u.x); x[8 * k + 1] = bf16_hi(u.x); x[8 * k + 2] = bf16_lo(u.y); x[8 * k + 3] = bf16_hi(u.y);
-    x[8 * k + 4] = bf16_lo(u.z); x[8 * k + 5] = bf16_hi(u.z); x[8 * k + 6] = bf16_lo(u.w); x[8 * k + 7] = bf16_hi(u.w);
+  for (int k = 0; k < 4; ++k) {
+    uint32_t u[8];
+    asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7])
+                 : "l"(ptr + 2 * k));
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { x[16 * k + 2 * e] = bf16_lo(u[e]); x[16 * k + 2 * e + 1] = bf16_hi(u[e]); }
   }
   float s = 0.f;
 #pragma unroll
@@ -318,12 +323,12 @@ __global__ void __launch_bounds__(128) qknorm_rope2d_head_kernel(__nv_bfloat16* 
     }
   }
 #pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    uint4 u;
-    u.x = pack_bf16(x[8 * k], x[8 * k + 1]); u.y = pack_bf16(x[8 * k + 2], x[8 * k + 3]);
-    u.z = pack_bf16(x[8 * k + 4], x[8 * k + 5]); u.w = pack_bf16(x[8 * k + 6], x[8 * k + 7]);
-    ptr[k] = u;
-  }
+  for (int k = 0; k < 4; ++k)
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(ptr + 2 * k), "r"(pack_bf16(x[16 * k], x[16 * k + 1])),
+                 "r"(pack_bf16(x[16 * k + 2], x[16 * k + 3])), "r"(pack_bf16(x[16 * k + 4], x[16 * k + 5])), "r"(pack_bf16(x[16 * k + 6], x[16 * k + 7])),
+                 "r"(pack_bf16(x[16 * k + 8], x[16 * k + 9])), "r"(pack_bf16(x[16 * k + 10], x[16 * k + 11])),
+                 "r"(pack_bf16(x[16 * k + 12], x[16 * k + 13])), "r"(pack_bf16(x[16 * k + 14], x[16 * k + 15]))
+                 : "memory");
 }
 
 int qknorm_rope2d_entry(void* qkv, long long ld, long long rows, long long heads, const float* qw, const float* qb,
@@ -335,7 +340,7 @@ int qknorm_rope2d_entry(void* qkv, long long ld, long long rows, long long heads
   const long long npatch = tpv - n_special;
   const long long need = 1 + (npatch > 0 ? ((npatch - 1) / grid_w + 1 > grid_w ? (npatch - 1) / grid_w + 1 : grid_w) : 0);
   V3A_REQUIRE(max_pos >= need, VIST3A_ERR_INVALID, "qknorm_rope2d: rope table has %lld positions, %lld needed", max_pos, need);
-  if (ld % 8 == 0 && ((uintptr_t)qkv & 15) == 0)
+  if (ld % 16 == 0 && ((uintptr_t)qkv & 31) == 0)
     qknorm_rope2d_head_kernel<<<grid_for(rows * 2 * heads, 128), 128, 0, st>>>((__nv_bfloat16*)qkv, ld, rows, (int)heads, qw, qb, kw, kb, eps, cos_tab,
                                                                               sin_tab, (int)tpv, (int)n_special, (int)grid_w);
   else
@@ -349,17 +354,17 @@ int qknorm_rope2d_entry(void* qkv, long long ld, long long rows, long long heads
 // ----------------------------------------------------------------------------------------
 // bilinear resize (align_corners=True), NHWC fp32, 4 channels per thread
 // ----------------------------------------------------------------------------------------
+// grid: x = chunks of 256 (pixel, 4-channel group) pairs along one output row, y = output row, z = image -- 32-bit index arithmetic only (the first
+// version decomposed one flat 64-bit index per thread: three 64-bit divisions made the kernel issue-bound at 2.2 TB/s, ncu: 78 % issue slots)
 __global__ void __launch_bounds__(256) bilinear_nhwc_kernel(const float* __restrict__ in, float* __restrict__ out, int n_img,
                                                             int hi, int wi, int ho, int wo, int C, const float* __restrict__ add,
                                                             const float* __restrict__ pos_x, const float* __restrict__ pos_y,
                                                             float sy, float sx) {
-  const int c4 = C / 4;
-  const long long total = (long long)n_img * ho * wo * c4;
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  const int c = (int)(i % c4) * 4;
-  long long pix = i / c4;
-  const int x = (int)(pix % wo), y = (int)((pix / wo) % ho), n = (int)(pix / ((long long)wo * ho));
+  const int c4 = C >> 2;
+  const int t = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+  if (t >= wo * c4) return;
+  const int x = t / c4, c = (t - x * c4) * 4;
+  const int y = (int)blockIdx.y, n = (int)blockIdx.z;
   // PyTorch area_pixel_compute_source_index(align_corners=True): src = scale * dst
   const float fy = sy * (float)y, fx = sx * (float)x;
   int y0 = (int)fy, x0 = (int)fx;
@@ -369,17 +374,20 @@ __global__ void __launch_bounds__(256) bilinear_nhwc_kernel(const float* __restr
   const float ly = fy - (float)y0, lx = fx - (float)x0;
   const float hy = 1.0f - ly, hx = 1.0f - lx;
   const float* base = in + (long long)n * hi * wi * C + c;
-  const float4 v00 = *reinterpret_cast<const float4*>(base + ((long long)y0 * wi + x0) * C);
-  const float4 v01 = *reinterpret_cast<const float4*>(base + ((long long)y0 * wi + x1) * C);
-  const float4 v10 = *reinterpret_cast<const float4*>(base + ((long long)y1 * wi + x0) * C);
-  const float4 v11 = *reinterpret_cast<const float4*>(base + ((long long)y1 * wi + x1) * C);
+  const float* r0 = base + (long long)y0 * wi * C;
+  const float* r1 = base + (long long)y1 * wi * C;
+  const float4 v00 = *reinterpret_cast<const float4*>(r0 + x0 * C);
+  const float4 v01 = *reinterpret_cast<const float4*>(r0 + x1 * C);
+  const float4 v10 = *reinterpret_cast<const float4*>(r1 + x0 * C);
+  const float4 v11 = *reinterpret_cast<const float4*>(r1 + x1 * C);
   float4 o;
   o.x = hy * (hx * v00.x + lx * v01.x) + ly * (hx * v10.x + lx * v11.x);
   o.y = hy * (hx * v00.y + lx * v01.y) + ly * (hx * v10.y + lx * v11.y);
   o.z = hy * (hx * v00.z + lx * v01.z) + ly * (hx * v10.z + lx * v11.z);
   o.w = hy * (hx * v00.w + lx * v01.w) + ly * (hx * v10.w + lx * v11.w);
+  const long long off = (((long long)n * ho + y) * wo + x) * C + c;
   if (add) {
-    const float4 a = *reinterpret_cast<const float4*>(add + pix * C + c);
+    const float4 a = *reinterpret_cast<const float4*>(add + off);
     o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
   }
   if (pos_x) {
@@ -388,7 +396,7 @@ __global__ void __launch_bounds__(256) bilinear_nhwc_kernel(const float* __restr
                                : *reinterpret_cast<const float4*>(pos_y + (long long)y * half + (c - half));
     o.x += pe.x; o.y += pe.y; o.z += pe.z; o.w += pe.w;
   }
-  *reinterpret_cast<float4*>(out + pix * C + c) = o;
+  *reinterpret_cast<float4*>(out + off) = o;
 }
 
 int bilinear_nhwc_entry(const float* in, float* out, long long n_img, long long hi, long long wi, long long ho, long long wo,
@@ -398,9 +406,9 @@ int bilinear_nhwc_entry(const float* in, float* out, long long n_img, long long 
   V3A_REQUIRE((pos_x == nullptr) == (pos_y == nullptr), VIST3A_ERR_INVALID, "bilinear_nhwc: pos_x/pos_y must both be given");
   const float sy = ho > 1 ? (float)(hi - 1) / (float)(ho - 1) : 0.f;
   const float sx = wo > 1 ? (float)(wi - 1) / (float)(wo - 1) : 0.f;
-  const long long total = n_img * ho * wo * (C / 4);
-  bilinear_nhwc_kernel<<<grid_for(total, 256), 256, 0, st>>>(in, out, (int)n_img, (int)hi, (int)wi, (int)ho, (int)wo, (int)C, add,
-                                                             pos_x, pos_y, sy, sx);
+  V3A_REQUIRE(ho <= 65535 && n_img <= 65535 && wo * (C / 4) < (1ll << 31), VIST3A_ERR_INVALID, "bilinear_nhwc: output rows / images exceed the grid limits");
+  const dim3 grid((unsigned)((wo * (C / 4) + 255) / 256), (unsigned)ho, (unsigned)n_img);
+  bilinear_nhwc_kernel<<<grid, 256, 0, st>>>(in, out, (int)n_img, (int)hi, (int)wi, (int)ho, (int)wo, (int)C, add, pos_x, pos_y, sy, sx);
   V3A_CUDA_OK(cudaGetLastError());
   launch_counter().fetch_add(1);
   return VIST3A_OK;

@@ -83,10 +83,10 @@ struct FmhaCfg {
   static constexpr bool FAST = FAST_ != 0;               // speculative (stale-maximum) softmax in 64-column half-steps, one thread per row
   // aliased 128-key steps (S single-buffered: softmax -> P V -> next Q K^T is a serial chain per tile): the first 64 keys of P(j) are handed
   // to the tensor pipe while the other 64 are still being exponentiated
-  static constexpr bool HANDOFF = FAST_ == 1 && ALIAS && BKV_ == 128;
+  static constexpr bool HANDOFF = (FAST_ == 1 || FAST_ == 3) && ALIAS && BKV_ == 128;
   // FAST_ == 1: one thread per query row, two 64-column half-steps per 128 keys in sequence; FAST_ == 2: two threads per row, one 64-column half
   // each (128-key steps only), which agree on the rare slow path through shared memory and a 64-thread named barrier AFTER the exponentials
-  static_assert(FAST_ == 0 || (FAST_ == 1 && SPLIT_ == 1) || (FAST_ == 2 && SPLIT_ == 2 && BKV_ == 128), "speculative softmax variants");
+  static_assert(FAST_ == 0 || ((FAST_ == 1 || FAST_ == 3) && SPLIT_ == 1) || (FAST_ == 2 && SPLIT_ == 2 && BKV_ == 128), "speculative softmax variants");
   static_assert(TM_O + D <= TILE_COLS, "TMEM budget");
 };
 
@@ -96,6 +96,7 @@ struct FmhaCfg {
 #define V3A_FAST2_REGS 96
 #endif
 constexpr int kFast2Regs = V3A_FAST2_REGS;
+
 
 template <int D, int BKV_, int POLY_, int SPLIT_, int FAST_ = 0>
 __global__ void __launch_bounds__(128 + 256 * SPLIT_, 1)
@@ -547,18 +548,37 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             l_run = 1.0f;
             continue;
           }
+          // d=64 (128-key steps, S not aliased): both halves of the score row are pulled into registers at once -- one TMEM round trip per step
+          // instead of two, and Q K^T of the next step may overwrite S right away
+          constexpr bool kPreload = !Cfg::ALIAS && NHALF == 2 && FAST_ == 3;   // A/B variant (flags bit 15): measured slower than two loads per step
+          uint32_t rr[kPreload ? NHALF : 1][64];
+          if constexpr (kPreload) {
 #pragma unroll
-          for (int hh = 0; hh < NHALF; ++hh) {
-            uint32_t r[64];
-            const uint32_t s_addr = tile_base + Cfg::TM_S + (uint32_t)sb * Cfg::S_STRIDE + (uint32_t)(hh * 64);
-            tmem_ld_x32(s_addr, r);
-            tmem_ld_x32(s_addr + 32u, r + 32);
+            for (int hh = 0; hh < NHALF; ++hh) {
+              const uint32_t s_addr = tile_base + Cfg::TM_S + (uint32_t)sb * Cfg::S_STRIDE + (uint32_t)(hh * 64);
+              tmem_ld_x32(s_addr, rr[hh]);
+              tmem_ld_x32(s_addr + 32u, rr[hh] + 32);
+            }
             tmem_ld_wait();
             if (tr) { const long long t2 = clock64(); ph_ld += t2 - tt; tt = t2; }
-            if (!Cfg::ALIAS && hh == NHALF - 1) {   // the whole score tile is in registers: Q K^T of the next step may overwrite it
-              tc_fence_before();
-              __syncwarp();
-              if (lane == 0) mbar_arrive(s_free(i));
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(s_free(i));
+          }
+#pragma unroll
+          for (int hh = 0; hh < NHALF; ++hh) {
+            uint32_t (&r)[64] = rr[kPreload ? hh : 0];
+            if constexpr (!kPreload) {
+              const uint32_t s_addr = tile_base + Cfg::TM_S + (uint32_t)sb * Cfg::S_STRIDE + (uint32_t)(hh * 64);
+              tmem_ld_x32(s_addr, r);
+              tmem_ld_x32(s_addr + 32u, r + 32);
+              tmem_ld_wait();
+              if (tr) { const long long t2 = clock64(); ph_ld += t2 - tt; tt = t2; }
+              if (!Cfg::ALIAS && hh == NHALF - 1) {   // the whole score tile is in registers: Q K^T of the next step may overwrite it
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(s_free(i));
+              }
             }
             const int valid = p.len_kv - j * BKV - hh * 64;   // columns of this half that hold existing keys
             if (valid < 64) {
@@ -914,10 +934,12 @@ int fmha_entry(const vist3a_fmha_args* args, cudaStream_t stream) {
   const bool one = (a.flags & 1u) != 0;
   // Default (flags == 0), from same-process A/B runs on B200 (tools/fmha_variants.py, tools/fmha_pair_check.py; profiles/README.md): the speculative
   // softmax (stale running maximum, 64-column half-steps, one thread per row, 2-3 of 8 exponentials on the FMA pipe) everywhere; at head_dim 128
-  // and >= 1024 keys on CTA pairs (+4.5 % over the single-CTA kernel at 4096 keys), below that on one CTA (+7 % at 512 keys).  flags bit 13
+  // and >= 1024 keys on CTA pairs (+4.4 % over the former default at 4096 keys), below that on one CTA (equal at 512 keys; +5 % on the decoder's
+  // 1029-key frame attention, +1..3 % on its 13 377-key global attention).  flags bit 13
   // selects the former default (two threads per row, exact running maximum) for A/B.
   if (a.flags == 0u) {
-    if (a.head_dim == 64) return launch_fmha<64, 128, 2, 1, 1>(a, stream);
+    // (head_dim 64, long key sequences -- the decoder's global attention: two threads per row, +1.7 % at 13 377 keys; -6 % at 1029)
+    if (a.head_dim == 64) return a.len_kv >= 4096 ? launch_fmha<64, 128, 0, 2, 2>(a, stream) : launch_fmha<64, 128, 2, 1, 1>(a, stream);
     if (a.len_kv >= 1024) return fmha_pair_entry(a, 7, stream);
     return launch_fmha<128, 64, 2, 1, 1>(a, stream);
   }
@@ -940,6 +962,7 @@ int fmha_entry(const vist3a_fmha_args* args, cudaStream_t stream) {
   if (a.flags & 128u) {   // speculative softmax, one thread per row; bits 3-5 = FMA-pipe exponentials per 8 column pairs
     const unsigned np = (a.flags >> 3) & 7u;
     if (a.head_dim == 64) {
+      if (a.flags & 32768u) return launch_fmha<64, 128, 2, 1, 3>(a, stream);   // both score halves of a step loaded at once
       switch (np) {
         case 0: return launch_fmha<64, 128, 0, 1, 1>(a, stream);
         case 1: return launch_fmha<64, 128, 1, 1, 1>(a, stream);
