@@ -91,7 +91,9 @@ struct FmhaCfg {
 };
 
 
-// registers per softmax thread of the two-threads-per-row speculative variant (96 = the launch-time allocation, no setmaxnreg)
+// registers per softmax thread of the two-threads-per-row speculative variant (96 = the launch-time allocation, no setmaxnreg).  setmaxnreg
+// redistributes only what the CTA was given at launch (640 x 96): raising 16 warps to 112 needs 8192 registers, shrinking the 4 utility warps
+// to 40 frees 7168 -- that dead-locks; 104 works but the utility warps then spill in their per-step loops: 630 vs 693 TFLOP/s at 13 377 keys.
 #ifndef V3A_FAST2_REGS
 #define V3A_FAST2_REGS 96
 #endif
