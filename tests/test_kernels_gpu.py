@@ -161,8 +161,8 @@ def test_fmha(ops, B, H, Lq, Lk, D):
 # every selectable attention variant (vist3a_fmha_args.flags; A/B measurements in tools/fmha_variants.py, tools/fmha_pair_check.py) computes the
 # same function: 0 = default dispatch, 8192 = the former default (two threads per row, exact running maximum), 128 | np << 3 = speculative
 # softmax with one thread per row, | 2 = aliased 128-key steps with the half hand-off of P, 16384 = speculative with two threads per row,
-# 256 | v << 9 = CTA-pair kernel variant v (head_dim 128)
-@pytest.mark.parametrize("flags", [0, 8192, 128, 128 | 16, 128 | 2 | 16, 16384, 256, 256 | (4 << 9), 256 | (7 << 9)])
+# 65536 | np << 3 = ONE query tile per CTA with two threads per row, 256 | v << 9 = CTA-pair kernel variant v (head_dim 128)
+@pytest.mark.parametrize("flags", [0, 8192, 128, 128 | 16, 128 | 2 | 16, 16384, 65536, 65536 | 16, 256, 256 | (4 << 9), 256 | (7 << 9)])
 @pytest.mark.parametrize("B,H,Lq,Lk,D", [(2, 3, 300, 333, 128), (1, 2, 257, 129, 128), (2, 3, 1029, 1029, 64), (1, 4, 640, 1100, 64)])
 def test_fmha_variants_agree_with_sdpa(ops, flags, B, H, Lq, Lk, D):
     if D == 64 and (flags & (256 | 2)):

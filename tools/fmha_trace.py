@@ -21,7 +21,8 @@ def main():
     o = torch.empty_like(q)
     for _ in range(3):
         ops.fmha(q, k, v, out=o, flags=flags)
-    ctas = B * H * ((Lq + 255) // 256)
+    rows_per_cta = 128 if flags & 65536 else 256
+    ctas = B * H * ((Lq + rows_per_cta - 1) // rows_per_cta)
     tr = torch.zeros(ctas, 32, dtype=torch.int64, device="cuda")
     lib.v3a_debug_fmha_trace.argtypes = [ctypes.c_void_p]
     lib.v3a_debug_fmha_trace(tr.data_ptr())
@@ -34,7 +35,7 @@ def main():
     for i, n in enumerate(NAMES):
         col = rel[:, i]
         print(f"  {n:12s} {col.median().item():10.0f} {col.quantile(0.9).item():10.0f}")
-    steps = (Lk + 63) // 64 if D == 128 else (Lk + 127) // 128
+    steps = (Lk + 63) // 64 if (D == 128 and not (flags & (2 | 16384 | 65536))) else (Lk + 127) // 128
     for i, n in ((16, "softmax: wait S"), (17, "softmax: tmem ld"), (18, "softmax: max+xchg+rescale"), (19, "softmax: exp+pack+st issue"),
                  (20, "softmax: st wait+arrive"), (21, "mma warp: wait P"), (22, "mma warp: issue PV+QK")):
         col = t[:, i].double() / steps

@@ -52,12 +52,15 @@ extern "C" void v3a_debug_fmha_trace(void* buf) { g_fmha_trace.store(reinterpret
     if (p.trace) p.trace[((long long)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 32 + (slot)] = clock64(); \
   } while (0)
 
-template <int D, int BKV_, int POLY_, int SPLIT_, int FAST_ = 0>
+// QT_ = 1 (round 2): ONE 128-row query tile per CTA with two softmax threads per row.  Tensor memory then has room for double-buffered
+// 128-key score tiles at d=128 (S0|P0 [0,128)  S1|P1 [128,256)  O [256,384)), so Q K^T of step j+1 runs under the softmax of step j without
+// the 64-key steps whose SS-mode MMAs are shared-memory bound, and 384 threads leave 168+ registers to the softmax threads.
+template <int D, int BKV_, int POLY_, int SPLIT_, int FAST_ = 0, int QT_ = 2>
 struct FmhaCfg {
-  static constexpr int BQ = 128, QT = 2;             // two query tiles per CTA
+  static constexpr int BQ = 128, QT = QT_;           // query tiles per CTA
   static constexpr int BKV = BKV_;                   // keys per step
   static constexpr bool ALIAS = (D == 128);          // P(j) overwrites S(j)
-  static constexpr int NSB = (ALIAS && BKV == 64) ? 2 : 1;  // score buffers per query tile
+  static constexpr int NSB = (ALIAS && (BKV == 64 || QT == 1)) ? 2 : 1;  // score buffers per query tile
   static constexpr int SLABS = D / 64;               // 64-element (128-byte) column slabs
   static constexpr int Q_SLAB_BYTES = BQ * 128;
   static constexpr int KV_SLAB_BYTES = BKV * 128;
@@ -67,17 +70,19 @@ struct FmhaCfg {
   static constexpr int PT = NSB + 1 + 4 + 4;         // barriers per query tile: s_full[NSB], s_free, p_full[2], pv_done[2], p_half[2], pvh_done[2]
   static constexpr int NBARS = 1 + 4 * KV_STAGES + 2 * PT;
   static constexpr int SPLIT = SPLIT_;               // threads per query row (softmax warpgroups per tile)
-  static constexpr int THREADS = 128 + 256 * SPLIT;
+  static constexpr int THREADS = 128 + 128 * QT * SPLIT;
   static constexpr int HC = BKV / SPLIT;             // score columns per softmax thread and step
-  static constexpr int XCH_BYTES = 4 * QT * 2 * 128 * 4;  // row-max / row-sum / slow-path flag exchange between the two threads of a row: [slot][tile][half][row]
+  static constexpr int XCH_BYTES = 4 * 2 * 2 * 128 * 4;    // row-max / row-sum / slow-path flag exchange between the two threads of a row: [slot][tile][half][row]
   static constexpr int SMEM_BYTES = Q_TILE_BYTES * QT + KV_TILE_BYTES * 2 * KV_STAGES + 1024 + 8 * NBARS + 16 + XCH_BYTES;
   static_assert(SPLIT == 1 || SPLIT == 2, "SPLIT");
-  static constexpr uint32_t TILE_COLS = 256;
+  static constexpr uint32_t TILE_COLS = QT == 1 ? 512 : 256;
   static constexpr uint32_t TM_S = 0;
-  static constexpr uint32_t S_STRIDE = 64;           // between the NSB score buffers (ALIAS only)
+  static constexpr uint32_t S_STRIDE = BKV;          // between the NSB score buffers (ALIAS only)
   static constexpr uint32_t TM_P = ALIAS ? 0 : 128;
-  static constexpr uint32_t P_STRIDE = (NSB == 2) ? 64 : 0;
-  static constexpr uint32_t TM_O = ALIAS ? 128 : 192;
+  static constexpr uint32_t P_STRIDE = (NSB == 2) ? BKV : 0;
+  static constexpr uint32_t TM_O = ALIAS ? NSB * BKV : 192;
+  static_assert(QT == 1 || QT == 2, "QT");
+  static_assert(QT == 2 || (SPLIT_ == 2 && BKV_ == 128), "one tile per CTA: two threads per row, 128-key steps");
   static_assert(D == 128 || BKV == 128, "d=64 runs 128-key steps");
   static constexpr int POLY = POLY_;                     // of every 8 column pairs, this many use the FMA-pipe exp2
   static constexpr bool FAST = FAST_ != 0;               // speculative (stale-maximum) softmax in 64-column half-steps, one thread per row
@@ -100,11 +105,11 @@ struct FmhaCfg {
 constexpr int kFast2Regs = V3A_FAST2_REGS;
 
 
-template <int D, int BKV_, int POLY_, int SPLIT_, int FAST_ = 0>
-__global__ void __launch_bounds__(128 + 256 * SPLIT_, 1)
+template <int D, int BKV_, int POLY_, int SPLIT_, int FAST_ = 0, int QT_ = 2>
+__global__ void __launch_bounds__(128 + 128 * QT_ * SPLIT_, 1)
 fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO, const FmhaParams p) {
-  using Cfg = FmhaCfg<D, BKV_, POLY_, SPLIT_, FAST_>;
+  using Cfg = FmhaCfg<D, BKV_, POLY_, SPLIT_, FAST_, QT_>;
   constexpr int SPLIT = Cfg::SPLIT;
   constexpr int HC = Cfg::HC;
   constexpr int ST = Cfg::KV_STAGES;
@@ -138,7 +143,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const int head = blockIdx.y;
   const int batch = blockIdx.z;
   const int n_kv = (p.len_kv + BKV - 1) / BKV;
-  const int nq = (q0 + Cfg::BQ < p.len_q) ? 2 : 1;  // query tiles of this CTA that hold at least one row
+  const int nq = (Cfg::QT == 2 && q0 + Cfg::BQ < p.len_q) ? 2 : 1;  // query tiles of this CTA that hold at least one row
   if (threadIdx.x == 0) {
     FMHA_TRACE(0);
     if (p.trace) {
@@ -186,8 +191,8 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   if (threadIdx.x == 0) FMHA_TRACE(2);
 
   if (warp < 4) {
-    if constexpr (SPLIT == 1) asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
-    if constexpr (FAST_ == 2 && kFast2Regs != 96) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    if constexpr (Cfg::THREADS == 384) asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+    if constexpr (FAST_ == 2 && Cfg::THREADS == 640 && kFast2Regs != 96) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
     // (SPLIT == 2: 20 warps at the launch-time 96 registers; see the note at the softmax branch)
     if (warp == 0) {
       // ------------------------------ TMA producer (warp-uniform control flow, one elected lane issues) ---------
@@ -372,8 +377,8 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
     }
   } else {
-    if constexpr (SPLIT == 1) asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
-    if constexpr (FAST_ == 2 && kFast2Regs != 96) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kFast2Regs));
+    if constexpr (Cfg::THREADS == 384) asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
+    if constexpr (FAST_ == 2 && Cfg::THREADS == 640 && kFast2Regs != 96) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kFast2Regs));
     // SPLIT == 2 keeps the launch-time allocation (96 registers x 640 threads): setmaxnreg.inc above 96 deadlocked on B200 --
     // the per-warp register allocation is coarser than the PTX granularity of 8, and 16 warps x 4096 registers is the whole file.
     // ------------------------------ softmax / correction / epilogue ------------------------------
@@ -881,9 +886,9 @@ static int make_qkv_map(CUtensorMap* tm, const void* ptr, long long B, long long
   return encode_tensor_map(tm, ptr, 2, false, 4, dims, strides, box, true);
 }
 
-template <int D, int BKV_, int POLY_, int SPLIT_, int FAST_ = 0>
+template <int D, int BKV_, int POLY_, int SPLIT_, int FAST_ = 0, int QT_ = 2>
 static int launch_fmha(const vist3a_fmha_args& a, cudaStream_t stream) {
-  using Cfg = FmhaCfg<D, BKV_, POLY_, SPLIT_, FAST_>;
+  using Cfg = FmhaCfg<D, BKV_, POLY_, SPLIT_, FAST_, QT_>;
   CUtensorMap tmQ, tmK, tmV, tmO;
   int rc;
   if ((rc = make_qkv_map(&tmQ, a.Q, a.batch, a.heads, a.len_q, D, a.q_bs, a.q_rs, a.q_hs, Cfg::BQ))) return rc;
@@ -900,7 +905,7 @@ static int launch_fmha(const vist3a_fmha_args& a, cudaStream_t stream) {
   p.skip_softmax = (a.flags & 4096u) ? 1 : 0;
   p.single_issuer = (a.flags & 4u) ? 1 : 0;
   p.direct_store = (a.flags & 64u) ? 1 : 0;
-  auto kern = fmha_fwd_kernel<D, BKV_, POLY_, SPLIT_, FAST_>;
+  auto kern = fmha_fwd_kernel<D, BKV_, POLY_, SPLIT_, FAST_, QT_>;
   static std::atomic<unsigned long long> attr_done{0};  // per template instantiation, one bit per device
   V3A_CUDA_OK(ensure_dynamic_smem(kern, Cfg::SMEM_BYTES, attr_done));
   const long long rows_per_cta = Cfg::BQ * Cfg::QT;
@@ -944,6 +949,23 @@ int fmha_entry(const vist3a_fmha_args* args, cudaStream_t stream) {
     if (a.head_dim == 64) return a.len_kv >= 4096 ? launch_fmha<64, 128, 0, 2, 2>(a, stream) : launch_fmha<64, 128, 2, 1, 1>(a, stream);
     if (a.len_kv >= 1024) return fmha_pair_entry(a, 7, stream);
     return launch_fmha<128, 64, 2, 1, 1>(a, stream);
+  }
+  if (a.flags & 65536u) {   // ONE query tile per CTA, speculative softmax with two threads per row; bits 3-5 = FMA-pipe exponentials per 8 pairs
+    const unsigned np = (a.flags >> 3) & 7u;
+    if (a.head_dim == 64) {
+      switch (np) {
+        case 0: return launch_fmha<64, 128, 0, 2, 2, 1>(a, stream);
+        case 1: return launch_fmha<64, 128, 1, 2, 2, 1>(a, stream);
+        case 2: return launch_fmha<64, 128, 2, 2, 2, 1>(a, stream);
+        default: return launch_fmha<64, 128, 3, 2, 2, 1>(a, stream);
+      }
+    }
+    switch (np) {
+      case 0: return launch_fmha<128, 128, 0, 2, 2, 1>(a, stream);
+      case 1: return launch_fmha<128, 128, 1, 2, 2, 1>(a, stream);
+      case 2: return launch_fmha<128, 128, 2, 2, 2, 1>(a, stream);
+      default: return launch_fmha<128, 128, 3, 2, 2, 1>(a, stream);
+    }
   }
   if (a.flags & 16384u) {   // speculative softmax, two threads per row (128-key steps); bits 3-5 = FMA-pipe exponentials per 8 column pairs
     const unsigned np = (a.flags >> 3) & 7u;
