@@ -16,16 +16,29 @@ from vist3a_b200 import ops  # noqa: E402
 
 
 def timeit(fn, iters=30):
+    """device time per call inside a CUDA graph of `iters` calls (eager timing of these 10-20 us kernels measures the host's launch
+    overhead: python + ctypes cost about as much per call as the kernel runs)"""
     for _ in range(5):
         fn()
     torch.cuda.synchronize()
+    st = torch.cuda.Stream()
+    st.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(st):
+        fn()
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr, stream=st):
+            for _ in range(iters):
+                fn()
+    torch.cuda.synchronize()
+    gr.replay()
+    torch.cuda.synchronize()
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s.record()
-    for _ in range(iters):
-        fn()
+    for _ in range(5):
+        gr.replay()
     e.record()
     torch.cuda.synchronize()
-    return s.elapsed_time(e) / iters * 1e3
+    return s.elapsed_time(e) / (5 * iters) * 1e3
 
 
 g = torch.Generator(device="cuda").manual_seed(0)
