@@ -941,11 +941,11 @@ int fmha_entry(const vist3a_fmha_args* args, cudaStream_t stream) {
   const bool one = (a.flags & 1u) != 0;
   // Default (flags == 0), from same-process A/B runs on B200 (tools/fmha_variants.py, tools/fmha_pair_check.py; profiles/README.md): the speculative
   // softmax (stale running maximum, 64-column half-steps, one thread per row, 2-3 of 8 exponentials on the FMA pipe) everywhere; at head_dim 128
-  // and >= 1024 keys on CTA pairs (+4.4 % over the former default at 4096 keys), below that on one CTA (equal at 512 keys; +5 % on the decoder's
-  // 1029-key frame attention, +1..3 % on its 13 377-key global attention).  flags bit 13
+  // and >= 1024 keys on CTA pairs (+5.5 % over the former default at 4096 keys, device time in a CUDA graph), below that on one CTA (+1.7 % at 512
+  // keys; +5.5 % on the decoder's 1029-key frame attention, +2.7 % on its 13 377-key global attention).  flags bit 13
   // selects the former default (two threads per row, exact running maximum) for A/B.
   if (a.flags == 0u) {
-    // (head_dim 64, long key sequences -- the decoder's global attention: two threads per row, +1.7 % at 13 377 keys; -6 % at 1029)
+    // (head_dim 64, long key sequences -- the decoder's global attention: two threads per row, +2 % over one thread per row at 13 377 keys; -7 % at 1029)
     if (a.head_dim == 64) return a.len_kv >= 4096 ? launch_fmha<64, 128, 0, 2, 2>(a, stream) : launch_fmha<64, 128, 2, 1, 1>(a, stream);
     if (a.len_kv >= 1024) return fmha_pair_entry(a, 7, stream);
     return launch_fmha<128, 64, 2, 1, 1>(a, stream);
