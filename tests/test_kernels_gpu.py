@@ -106,6 +106,28 @@ def test_gemm_176_wide_tiles_match_256_wide(ops, M, N, K, f32out):
     assert _rel_l2(o176.float(), ref) < (2e-3 if f32out else 6e-3)
 
 
+@pytest.mark.parametrize("M,N,K,f32", [(8192, 1536, 1536, False), (8192, 4608, 512, False), (8192, 1536, 1024, True), (13377, 1024, 512, True)])
+def test_gemm_multicast_and_staged_variants_are_bit_identical(ops, M, N, K, f32):
+    """A-operand multicast between two CTA pairs (VIST3A_GEMM_FLAG_MULTICAST: the DiT block GEMMs use it) and the staged epilogue (A/B flag) run
+    the same MMAs in the same K order and the same epilogue arithmetic as the default path: results are bit-identical, with and without the
+    gate + residual epilogue, for both output types (256-bit direct stores vs the staging buffer)."""
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    a = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    w = (torch.randn(N, K, device="cuda", generator=g) / math.sqrt(K)).bfloat16()
+    bias = torch.randn(N, device="cuda", generator=g)
+    gate = torch.randn(2, N, device="cuda", generator=g)
+    res = torch.randn(M, N, device="cuda", generator=g)
+    res = res if f32 else res.bfloat16()
+    dt = torch.float32 if f32 else torch.bfloat16
+    for kw in (dict(), dict(gate=gate, gate_bstride=N, rows_per_batch=(M + 1) // 2, residual=res, round_linear=True), dict(act="gelu_tanh")):
+        base = ops.gemm(a, w, bias, out_dtype=dt, two_cta=True, **kw)
+        assert torch.equal(ops.gemm(a, w, bias, out_dtype=dt, two_cta=True, multicast=True, **kw), base)
+        assert torch.equal(ops.gemm(a, w, bias, out_dtype=dt, two_cta=True, staged=True, **kw), base)
+        assert torch.equal(ops.gemm(a, w, bias, out_dtype=dt, two_cta=True, staged=True, multicast=True, **kw), base)
+    lin = (a.float() @ w.float().t() + bias)
+    assert _rel_l2(ops.gemm(a, w, bias, out_dtype=dt, two_cta=True, multicast=True).float(), lin) < 4e-3
+
+
 @pytest.mark.parametrize("M,N,K", [(1024, 256, 512), (500, 136, 72), (4096, 32, 1152)])
 def test_gemm_tf32(ops, M, N, K):
     g = torch.Generator(device="cuda").manual_seed(3)

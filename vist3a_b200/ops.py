@@ -125,11 +125,13 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
     args.round_linear, args.round_gate = int(round_linear), int(round_gate)
     if two_cta is None:
         two_cta = M >= 2048
-    args.flags = (L.GEMM_FLAG_2CTA if two_cta else L.GEMM_FLAG_1CTA) | (L.GEMM_FLAG_BN176 if bn176 else 0) | (L.GEMM_FLAG_MULTICAST if multicast else 0) | (L.GEMM_FLAG_STAGED if staged else 0)
+    args.flags = ((L.GEMM_FLAG_2CTA if two_cta else L.GEMM_FLAG_1CTA) | (L.GEMM_FLAG_BN176 if bn176 else 0) | (L.GEMM_FLAG_MULTICAST if multicast else 0)
+                  | (L.GEMM_FLAG_STAGED if staged else 0) | _GEMM_EXTRA_FLAGS)
     L.check(L.load().vist3a_gemm(C.byref(args), _stream()))
     return out
 
 
+_GEMM_EXTRA_FLAGS = int(os.environ.get("VIST3A_GEMM_FLAGS", "0"), 0)   # A/B switch (tools/): OR-ed into every GEMM call's flags (8 = multicast, 16 = staged epilogue)
 # A/B switch for measurements and numerics studies (tools/): flags used when the caller passes none (e.g. 8192 = the former default variants)
 _FMHA_DEFAULT_FLAGS = int(os.environ.get("VIST3A_FMHA_FLAGS", "0"), 0)
 

@@ -302,29 +302,31 @@ class WanTransformer3DModelB200(torch.nn.Module):
             # --- self-attention
             ops.layernorm(x, mul=mod[:, 1], add=mod[:, 0], mul_bstride=6 * D, add_bstride=6 * D, rows_per_batch=L,
                           eps=c.eps, out=ws.h)
-            ops.gemm(ws.h, w[k + "qkv.w"], w[k + "qkv.b"], out=ws.qkv)
+            # (multicast=True: clusters of two CTA pairs share the activation rows by TMA multicast where the tile grid allows it -- slower in
+            #  isolation, -0.8 % on the power-capped step: 27.93 -> 27.69 ms in an alternating same-box A/B, tools/runs/gpu_r3n.sh)
+            ops.gemm(ws.h, w[k + "qkv.w"], w[k + "qkv.b"], out=ws.qkv, multicast=True)
             ops.rmsnorm_rope_(ws.qkv[:, :2 * D], w[k + "nqk1"], hd, eps=c.eps, cos=cos, sin=sin, nseg=2)
             qkv5 = ws.qkv.view(B, L, 3, H_, hd)
             ops.fmha(qkv5[:, :, 0], qkv5[:, :, 1], qkv5[:, :, 2], out=ws.att.view(B, L, H_, hd))
             ops.gemm(ws.att, w[k + "o1.w"], w[k + "o1.b"], gate=mod[:, 2], gate_bstride=6 * D, rows_per_batch=L,
-                     residual=x, out=x, round_linear=True)
+                     residual=x, out=x, round_linear=True, multicast=True)
             # --- cross-attention
             if c.cross_attn_norm:
                 ops.layernorm(x, mul=w[k + "n2.w"], add=w[k + "n2.b"], eps=c.eps, out=ws.h)
                 hq = ws.h
             else:
                 hq = x
-            ops.gemm(hq, w[k + "q2.w"], w[k + "q2.b"], out=ws.q2)
+            ops.gemm(hq, w[k + "q2.w"], w[k + "q2.b"], out=ws.q2, multicast=True)
             ops.row_rinv(ws.q2, eps=c.eps, out=ws.rq)
             kv5 = ts.kv[i].view(B, ts.Lt, 2, H_, hd)
             ops.fmha(ws.q2.view(B, L, H_, hd), kv5[:, :, 0], kv5[:, :, 1], out=ws.att.view(B, L, H_, hd), q_row_scale=ws.rq)
-            ops.gemm(ws.att, w[k + "o2.w"], w[k + "o2.b"], residual=x, out=x, round_linear=True)
+            ops.gemm(ws.att, w[k + "o2.w"], w[k + "o2.b"], residual=x, out=x, round_linear=True, multicast=True)
             # --- feed-forward
             ops.layernorm(x, mul=mod[:, 4], add=mod[:, 3], mul_bstride=6 * D, add_bstride=6 * D, rows_per_batch=L,
                           eps=c.eps, out=ws.h)
-            ops.gemm(ws.h, w[k + "f1.w"], w[k + "f1.b"], act="gelu_tanh", out=ws.ffn)
+            ops.gemm(ws.h, w[k + "f1.w"], w[k + "f1.b"], act="gelu_tanh", out=ws.ffn, multicast=True)
             ops.gemm(ws.ffn, w[k + "f2.w"], w[k + "f2.b"], gate=mod[:, 5], gate_bstride=6 * D, rows_per_batch=L,
-                     residual=x, out=x, round_linear=True)
+                     residual=x, out=x, round_linear=True, multicast=True)
 
         # output head: mod2 = [shift, 1+scale] from table + temb
         ops.modulation(w["out.table"], temb, nvec=2, broadcast=True, one_plus_mask=0b10, out=ws.mod2)
