@@ -201,6 +201,27 @@ def test_fmha_variants_agree_with_sdpa(ops, flags, B, H, Lq, Lk, D):
     assert _rel_l2(out.float(), ref) < 6e-3, flags
 
 
+@pytest.mark.parametrize("flags", [0, 8192, 128 | 16, 16384, 16384 | 16, 65536 | 16, 65536 | 24, 256 | (7 << 9)])
+@pytest.mark.parametrize("D", [64, 128])
+def test_fmha_outlier_keys_late_in_the_sequence(ops, flags, D):
+    """A few keys far down the sequence whose scores exceed everything before them by more than 2^127 (after scaling): the speculative softmax
+    has already exponentiated them against the stale maximum -- on the MUFU that is +inf, on the FMA-pipe path a clamped 2^127 -- and must take
+    its exact path (rescale O and the row sum, redo the half-step); columns chosen to hit MUFU and polynomial positions alike."""
+    if D == 64 and (flags & 256):
+        pytest.skip("CTA-pair kernel: head_dim 128 only")
+    g = torch.Generator(device="cuda").manual_seed(D + flags)
+    B, H, Lq, Lk = 1, 2, 300, 700
+    q = torch.randn(B, Lq, H, D, device="cuda", generator=g).bfloat16()
+    k = torch.randn(B, Lk, H, D, device="cuda", generator=g).bfloat16()
+    v = torch.randn(B, Lk, H, D, device="cuda", generator=g).bfloat16()
+    for j in (Lk - 3, Lk - 10, Lk - 21, Lk - 150, 400, 401, 402, 403):
+        k[:, j] *= 300.0
+    ref = torch.nn.functional.scaled_dot_product_attention(q.float().transpose(1, 2), k.float().transpose(1, 2), v.float().transpose(1, 2)).transpose(1, 2)
+    out = ops.fmha(q, k, v, flags=flags)
+    assert torch.isfinite(out).all()
+    assert _rel_l2(out.float(), ref) < 6e-3, flags
+
+
 def test_fmha_large_scores(ops):
     # rows whose max moves by > 2^8 between kv tiles exercise the lazy-rescale path
     g = torch.Generator(device="cuda").manual_seed(5)

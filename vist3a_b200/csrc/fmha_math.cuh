@@ -62,7 +62,11 @@ __device__ __forceinline__ constexpr bool exp_pair_is_poly(int k) {
   return NP >= 4 ? (k & 1) : NP == 3 ? (k == 1 || k == 4 || k == 7) : NP == 2 ? (k == 2 || k == 6) : NP == 1 ? (k == 4) : false;
 }
 // exp2 of two values on the FMA pipe with the lower clamp bound passed in (see exp_half64 for why it is a register)
+template <bool kClampHigh = false>
 __device__ __forceinline__ void exp2_poly2_b(float y0, float y1, float bound, float& e0, float& e1) {
+  // kClampHigh: callers that detect an exponent above the lazy-rescale threshold from the row SUM (no running maximum) need the polynomial path
+  // to return something huge for y > 127 instead of a wrapped exponent field (2^127 sends the sum over any threshold; the MUFU path gives +inf)
+  if (kClampHigh) { y0 = fminf(y0, 127.0f); y1 = fminf(y1, 127.0f); }
   const uint64_t one = pack2(1.0f, 1.0f);
   const uint64_t magic = pack2(12582912.0f, 12582912.0f);      // 1.5 * 2^23: rounds to nearest integer
   const uint64_t nmagic = pack2(-12582912.0f, -12582912.0f);
@@ -103,7 +107,7 @@ __device__ __forceinline__ float exp_half64(const uint32_t* r, uint64_t cc2, uin
       float y0, y1, e0, e1;
       unpack2(fma2(pack2(s0, s1), cc2, mc2), y0, y1);
       if (exp_pair_is_poly<NP>(k)) {
-        exp2_poly2_b(y0, y1, bound, e0, e1);
+        exp2_poly2_b<!TRACK>(y0, y1, bound, e0, e1);
       } else {
         e0 = ex2_approx(y0);
         e1 = ex2_approx(y1);
@@ -137,7 +141,7 @@ __device__ __forceinline__ void exp_half64_v2(const uint32_t* r, uint64_t cc2, u
         float& e0 = e[g & 1][2 * k];
         float& e1 = e[g & 1][2 * k + 1];
         if (exp_pair_is_poly<NP>(k)) {
-          exp2_poly2_b(y0, y1, bound, e0, e1);
+          exp2_poly2_b<true>(y0, y1, bound, e0, e1);
         } else {
           e0 = ex2_approx(y0);
           e1 = ex2_approx(y1);
