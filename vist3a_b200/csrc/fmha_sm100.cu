@@ -948,6 +948,7 @@ int fmha_entry(const vist3a_fmha_args* args, cudaStream_t stream) {
     // (head_dim 64, long key sequences -- the decoder's global attention: two threads per row, +2 % over one thread per row at 13 377 keys; -7 % at 1029)
     if (a.head_dim == 64) return a.len_kv >= 4096 ? launch_fmha<64, 128, 0, 2, 2>(a, stream) : launch_fmha<64, 128, 2, 1, 1>(a, stream);
     if (a.len_kv >= 1024) return fmha_pair_entry(a, 7, stream);
+    if (a.len_kv >= 512) return fmha_pair_entry(a, 4, stream);   // cross-attention (512 text tokens): 676 vs 659 TFLOP/s on one CTA
     return launch_fmha<128, 64, 2, 1, 1>(a, stream);
   }
   if (a.flags & 65536u) {   // ONE query tile per CTA, speculative softmax with two threads per row; bits 3-5 = FMA-pipe exponentials per 8 pairs
