@@ -34,7 +34,7 @@ extern "C" {
 #define VIST3A_DTYPE_F32 1
 
 const char* vist3a_last_error(void);
-int vist3a_abi_version(void); /* 7 */
+int vist3a_abi_version(void); /* 8 */
 /* number of kernels this library has launched from the calling process (all threads) */
 int64_t vist3a_launch_count(void);
 /* Programmatic dependent launch (PDL) of the hot kernels (GEMM, attention, LayerNorm, RMSNorm+RoPE, row_rinv): each is launched
@@ -141,9 +141,16 @@ typedef struct vist3a_fmha_args {
   uint32_t flags; /* 0 = tuned default; kernel-variant selectors for A/B measurements only (results identical up to rounding):
                      bit0 one thread per query row, bit1 128-key steps (d=128), bit2 single MMA-issuing warp, bits 3.. = 1 + FMA-pipe exp2 share */
   const float* q_row_scale; /* optional [batch * len_q] fp32: extra positive factor on the logits of query row (b, i), all heads */
+  void* workspace;          /* optional scratch (128-byte aligned), see vist3a_fmha_workspace_bytes; NULL / too small: the call still succeeds */
+  int64_t workspace_bytes;
 } vist3a_fmha_args;
 
 int vist3a_fmha_fwd(const vist3a_fmha_args* args, void* stream);
+/* Scratch the call would use for these arguments (>= 0; < 0: a VIST3A_ERR_* code).  head_dim 128 on CTA pairs: when the grid's last wave would
+ * leave most SMs idle, the query blocks of that wave are cut along the KEYS into chunks that fill the machine (flash-decoding style partial
+ * results: bf16 O + fp32 (max, sum) per row, 264 B per query row and chunk) and a merge kernel follows; without workspace the kernel runs
+ * unsplit (same result up to rounding).  No reference counterpart: torch SDPA owns its scratch. */
+int64_t vist3a_fmha_workspace_bytes(const vist3a_fmha_args* args);
 
 /* ------------------------------------------------------------------------------------------
  * LayerNorm with optional modulation:  out[r,:] = LN(x[r,:]) * mul[b,:] + add[b,:],  b = r / rows_per_batch

@@ -34,7 +34,7 @@ def test_library_exports_every_declared_symbol(lib):
     missing = [n for n in names if not hasattr(h, n)]
     assert not missing, missing
     assert sorted(lib.EXPORTS) == names            # the Python binding lists exactly the header's entry points
-    assert h.vist3a_abi_version() == 7
+    assert h.vist3a_abi_version() == 8
     assert h.vist3a_launch_count() == 0            # nothing was launched by loading / symbol lookup
 
 
@@ -212,7 +212,7 @@ def test_every_compute_entry_point_rejects_zeroed_arguments(lib):
     h = lib.load()
     skip = {"vist3a_last_error", "vist3a_abi_version", "vist3a_launch_count", "vist3a_set_pdl", "vist3a_voxel_fusion_workspace_bytes",
             "vist3a_gs_project_workspace_bytes", "vist3a_gs_rasterize_workspace_bytes", "vist3a_quantile_workspace_bytes",
-            "vist3a_compact_rows_workspace_bytes"}
+            "vist3a_compact_rows_workspace_bytes", "vist3a_fmha_workspace_bytes"}
     n0 = h.vist3a_launch_count()
     checked = 0
     for name in lib.EXPORTS:

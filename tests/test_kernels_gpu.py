@@ -222,6 +222,33 @@ def test_fmha_outlier_keys_late_in_the_sequence(ops, flags, D):
     assert _rel_l2(out.float(), ref) < 6e-3, flags
 
 
+@pytest.mark.parametrize("shape", [(1, 2, 600, 2048), (1, 15, 1024, 4096), (2, 3, 700, 2000), (1, 12, 2048, 4096)])
+@pytest.mark.parametrize("flags", [0, 1 << 18, 2 << 18, 3 << 18, 256 | (3 << 9), 256 | (2 << 18)])
+def test_fmha_key_split_last_wave(ops, shape, flags):
+    """head_dim 128 on CTA pairs: the query blocks of the grid's last, partly filled wave are cut along the keys (chunk clusters write partial
+    results, a merge kernel follows).  Shapes that split into equal chunks, into a mix of k and k + 1 chunks, with a ragged last key tile, with
+    per-row logit scales and with the largest logits in the LAST chunk; flags force 1 / 2 / 3 short waves and the non-speculative kernels.
+    Compared with fp32 SDPA and with the unsplit kernel (flags bit 17)."""
+    from vist3a_b200 import _lib
+    B, H, Lq, Lk = shape
+    g = torch.Generator(device="cuda").manual_seed(Lq + Lk + flags)
+    q = torch.randn(B, Lq, H, 128, device="cuda", generator=g).bfloat16()
+    k = torch.randn(B, Lk, H, 128, device="cuda", generator=g).bfloat16()
+    v = torch.randn(B, Lk, H, 128, device="cuda", generator=g).bfloat16()
+    q[:, : Lq // 2] *= 3
+    k[:, Lk - 100:] *= 2
+    rs = (torch.rand(B * Lq, device="cuda", generator=g) + 0.5).float()
+    ref = torch.nn.functional.scaled_dot_product_attention((q.float() * rs.view(B, Lq, 1, 1)).transpose(1, 2), k.float().transpose(1, 2),
+                                                           v.float().transpose(1, 2)).transpose(1, 2)
+    n0 = _lib.launch_count()
+    out = ops.fmha(q, k, v, flags=flags, q_row_scale=rs)
+    assert _lib.launch_count() - n0 == 2, "attention kernel + merge kernel expected (the shape is chosen to split)"
+    whole = ops.fmha(q, k, v, flags=flags | (1 << 17), q_row_scale=rs)
+    assert torch.isfinite(out).all()
+    assert _rel_l2(out.float(), ref) < 6e-3
+    assert _rel_l2(out.float(), whole.float()) < 4e-3
+
+
 def test_fmha_large_scores(ops):
     # rows whose max moves by > 2^8 between kv tiles exercise the lazy-rescale path
     g = torch.Generator(device="cuda").manual_seed(5)

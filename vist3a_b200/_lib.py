@@ -27,6 +27,7 @@ EXPORTS = (
     "vist3a_set_pdl",
     "vist3a_gemm",
     "vist3a_fmha_fwd",
+    "vist3a_fmha_workspace_bytes",
     "vist3a_layernorm",
     "vist3a_rmsnorm_rope",
     "vist3a_row_rinv",
@@ -140,6 +141,8 @@ class FmhaArgs(C.Structure):
         ("scale", C.c_float),
         ("flags", C.c_uint32),
         ("q_row_scale", C.c_void_p),
+        ("workspace", C.c_void_p),
+        ("workspace_bytes", C.c_int64),
     ]
 
 
@@ -183,6 +186,8 @@ def load(build_if_missing: bool = False) -> C.CDLL:
     lib.vist3a_gs_rasterize_workspace_bytes.argtypes = [C.c_int64, C.c_int64, C.c_int64]
     lib.vist3a_gemm.argtypes = [C.POINTER(GemmArgs), C.c_void_p]
     lib.vist3a_fmha_fwd.argtypes = [C.POINTER(FmhaArgs), C.c_void_p]
+    lib.vist3a_fmha_workspace_bytes.argtypes = [C.POINTER(FmhaArgs)]
+    lib.vist3a_fmha_workspace_bytes.restype = C.c_int64
     i64, i32, f32, vp, u32 = C.c_int64, C.c_int32, C.c_float, C.c_void_p, C.c_uint32
     lib.vist3a_layernorm.argtypes = [vp, i32, i64, vp, i32, i64, i64, i64, i64, vp, i64, vp, i64, f32, i32, C.POINTER(RowMap), C.POINTER(RowMap), vp]
     lib.vist3a_rmsnorm_rope.argtypes = [vp, i64, i64, i64, i64, vp, f32, vp, vp, i64, i64, i64, vp]

@@ -10,7 +10,7 @@ namespace v3a {
 
 // entry points implemented next to their kernels
 int gemm_entry(const vist3a_gemm_args*, cudaStream_t);
-int fmha_entry(const vist3a_fmha_args*, cudaStream_t);
+int fmha_entry(const vist3a_fmha_args*, cudaStream_t, long long* ws_query);
 int layernorm_entry(const void*, int, long long, void*, int, long long, long long, long long, long long, const float*,
                     long long, const float*, long long, float, int, const vist3a_rowmap*, const vist3a_rowmap*, cudaStream_t);
 int rmsnorm_rope_entry(void*, long long, long long, long long, long long, const float*, float, const float*,
@@ -179,12 +179,17 @@ using namespace v3a;
 extern "C" {
 
 const char* vist3a_last_error(void) { return last_error_buf(); }
-int vist3a_abi_version(void) { return 7; }
+int vist3a_abi_version(void) { return 8; }
 int64_t vist3a_launch_count(void) { return (int64_t)launch_counter().load(); }
 int vist3a_set_pdl(int32_t enable) { return set_pdl(enable); }
 
 int vist3a_gemm(const vist3a_gemm_args* args, void* stream) { return gemm_entry(args, ST(stream)); }
-int vist3a_fmha_fwd(const vist3a_fmha_args* args, void* stream) { return fmha_entry(args, ST(stream)); }
+int vist3a_fmha_fwd(const vist3a_fmha_args* args, void* stream) { return fmha_entry(args, ST(stream), nullptr); }
+int64_t vist3a_fmha_workspace_bytes(const vist3a_fmha_args* args) {
+  long long bytes = 0;
+  const int rc = fmha_entry(args, nullptr, &bytes);
+  return rc ? (int64_t)rc : (int64_t)bytes;
+}
 int vist3a_vae_rmsnorm(const void* x, int64_t ldx, const float* gamma, void* y, int64_t ldy, int64_t rows, int64_t C, int32_t silu, void* stream) {
   return vae_rmsnorm_entry(x, ldx, gamma, y, ldy, rows, C, silu, ST(stream));
 }

@@ -36,6 +36,13 @@ struct FmhaPairParams {
   const float* row_scale;  // optional per-(batch, query row) positive factor on the logits
   long long* trace;        // debug (v3a_debug_fmha_pair_trace): clock64 stamps of CTA (0,0,0), normally null
   uint32_t zero;           // 0 (a value ptxas cannot fold: scheduling aid of the speculative softmax)
+  // Work decomposition (1-D grid, cluster c = blockIdx.x / 2).  A unit = (batch, head, block of 256 QT query rows), q-block fastest.  Clusters
+  // [0, n_full) process one unit each over all keys.  The units behind them -- the last, partly filled wave of the grid -- are cut along
+  // the KEYS: the first split_a of them into split_k chunks, the others into split_k + 1, one cluster per chunk; a chunk cluster writes its
+  // normalised partial O (bf16) and per row (reference maximum * c, row sum) to the workspace and fmha_pair_combine_kernel merges them.
+  int q_blocks, heads;
+  int n_full, split_a, split_k;
+  float* ws_ml;            // [chunk][256 QT rows][2] fp32 (behind the partial O tiles the workspace tensor map tmW addresses)
 };
 
 // debug hook (tools/fmha_pair_trace.py), off unless armed: [step][tile][8] stamps of the leader CTA of cluster 0:
@@ -46,6 +53,14 @@ extern "C" void v3a_debug_fmha_pair_trace(void* buf) { g_pair_trace.store(reinte
 #define PAIR_TRACE(j, i, slot)                                                                         \
   do {                                                                                                 \
     if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (j) < 64) p.trace[((j) * 2 + (i)) * 8 + (slot)] = clock64(); \
+  } while (0)
+
+// second part of the debug buffer, [cluster][8] at offset 1024: %globaltimer (ns) of every cluster's leader CTA at
+//   0 kernel entry   1 set-up done (barriers, tensor memory, cluster sync, PDL wait)   2 tile 0 sees its first S   3 tile 0 has handed over its
+//   last P   4 last P V complete   5 tile 0's output stored   6 after the final cluster sync   7 SM id
+#define PAIR_STAMP(slot)                                                                                    \
+  do {                                                                                                      \
+    if (p.trace && rank == 0) p.trace[1024 + (long long)(blockIdx.x >> 1) * 8 + (slot)] = (long long)globaltimer_ns(); \
   } while (0)
 
 template <int QT_, int SPLIT_, int POLY_, int FAST_ = 0>
@@ -79,7 +94,7 @@ struct FmhaPairCfg {
 template <int QT_, int SPLIT_, int POLY_, int FAST_ = 0>
 __global__ void __launch_bounds__(128 + QT_ * 128 * SPLIT_, 1)
 fmha_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
-                 const __grid_constant__ CUtensorMap tmO, const FmhaPairParams p) {
+                 const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmW, const FmhaPairParams p) {
   using Cfg = FmhaPairCfg<QT_, SPLIT_, POLY_, FAST_>;
   constexpr int QT = Cfg::QT, NSB = Cfg::NSB, NH = Cfg::NH, SPLIT = Cfg::SPLIT, HC = Cfg::HC, OC = Cfg::OC, ST = Cfg::ST, BKV = Cfg::BKV, D = Cfg::D;
   extern __shared__ uint8_t smem_raw[];
@@ -106,11 +121,35 @@ fmha_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   const uint32_t rank = cluster_ctarank();          // 0 = leader
   const bool leader = rank == 0;
   // the cluster owns 256 * QT consecutive query rows: tile i of the pair = rows [256 i, 256 i + 256), this CTA's half = [128 rank, +128)
-  auto q0_of = [&](int i) { return (int)(blockIdx.x >> 1) * (2 * QT * Cfg::BQ) + (2 * i + (int)rank) * Cfg::BQ; };
-  const int head = blockIdx.y, batch = blockIdx.z;
-  const int n_kv = (p.len_kv + BKV - 1) / BKV;
+  int unit = (int)(blockIdx.x >> 1);
+  int kv0 = 0, n_kv = (p.len_kv + BKV - 1) / BKV;   // first 128-key step and number of steps of this cluster
+  const int part = unit - p.n_full;                 // >= 0: chunk cluster number (its slot in the workspace)
+  if (part >= 0) {
+    int k = p.split_k, u, ci;
+    const int na = p.split_a * p.split_k;
+    if (part < na) {
+      u = part / k;
+      ci = part - u * k;
+    } else {
+      ++k;
+      u = (part - na) / k;
+      ci = (part - na) - u * k;
+      u += p.split_a;
+    }
+    unit = p.n_full + u;
+    kv0 = ci * n_kv / k;
+    n_kv = (ci + 1) * n_kv / k - kv0;
+  }
+  const int qb = unit % p.q_blocks, head = (unit / p.q_blocks) % p.heads, batch = unit / (p.q_blocks * p.heads);
+  auto q0_of = [&](int i) { return qb * (2 * QT * Cfg::BQ) + (2 * i + (int)rank) * Cfg::BQ; };
 
   if (warp == 0 && lane == 0) {
+    PAIR_STAMP(0);
+    if (p.trace && rank == 0) {
+      uint32_t smid;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      p.trace[1024 + (long long)(blockIdx.x >> 1) * 8 + 7] = smid;
+    }
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
@@ -145,6 +184,7 @@ fmha_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 
   if (warp == 0) {
     // ------------------------------ TMA producer (warp-uniform control flow, one elected lane issues) ------------------------------
+    if (lane == 0) PAIR_STAMP(1);
     if (elect_one()) {
       if (leader) mbar_expect_tx(q_full, 2u * QT * Cfg::Q_TILE_BYTES);
 #pragma unroll
@@ -162,13 +202,13 @@ fmha_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         if (leader) mbar_expect_tx(k_full(s), 2u * Cfg::K_HALF_BYTES);
 #pragma unroll
         for (int sl = 0; sl < 2; ++sl)
-          tma_load_4d_2sm(smem_k(s) + sl * Cfg::K_SLAB_BYTES, &tmK, k_full(s), sl * 64, head, j * BKV + (int)rank * (BKV / 2), batch);
+          tma_load_4d_2sm(smem_k(s) + sl * Cfg::K_SLAB_BYTES, &tmK, k_full(s), sl * 64, head, (kv0 + j) * BKV + (int)rank * (BKV / 2), batch);
       }
       __syncwarp();
       mbar_wait(v_empty(s), ph ^ 1u);
       if (elect_one()) {
         if (leader) mbar_expect_tx(v_full(s), 2u * Cfg::V_HALF_BYTES);
-        tma_load_4d_2sm(smem_v(s), &tmV, v_full(s), (int)rank * 64, head, j * BKV, batch);
+        tma_load_4d_2sm(smem_v(s), &tmV, v_full(s), (int)rank * 64, head, (kv0 + j) * BKV, batch);
       }
       __syncwarp();
       if (++s == ST) { s = 0; ph ^= 1u; }
@@ -272,6 +312,7 @@ fmha_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         tc_fence_after();
         const bool tr = wq == 0 && lane == 0;
         if (tr) PAIR_TRACE(j, i, 2);
+        if (tr && i == 0 && j == 0) PAIR_STAMP(2);
         const uint32_t p_addr = lane_base + Cfg::TM_S;
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {
@@ -280,7 +321,7 @@ fmha_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           tmem_ld_x32(p_addr + (uint32_t)(hh * 64) + 32u, r + 32);
           tmem_ld_wait();
           if (tr && hh == 0) PAIR_TRACE(j, i, 3);
-          const int valid = p.len_kv - j * BKV - hh * 64;
+          const int valid = p.len_kv - (kv0 + j) * BKV - hh * 64;
           if (valid < 64) {
 #pragma unroll
             for (int k = 0; k < 64; ++k)
@@ -358,7 +399,7 @@ fmha_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       for (int cb = 0; cb < HC / 32; ++cb) tmem_ld_x32(s_addr + (uint32_t)(cb * 32), r + cb * 32);
       tmem_ld_wait();
       if (tr) PAIR_TRACE(j, i, 3);
-      const int valid = p.len_kv - j * BKV - h * HC;   // columns of this thread that hold existing keys
+      const int valid = p.len_kv - (kv0 + j) * BKV - h * HC;   // columns of this thread that hold existing keys
       if (valid < HC) {
 #pragma unroll
         for (int k = 0; k < HC; ++k)
@@ -463,6 +504,7 @@ fmha_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       }
     }
     // ---- epilogue: O / l -> bf16 -> shared memory (this CTA's Q buffer: every MMA has completed) -> one bulk tensor store per slab ----
+    if (i == 0 && h == 0 && rit == 0) PAIR_STAMP(3);
     if constexpr (SPLIT > 1) {
       asm volatile("st.shared.f32 [%0], %1;" ::"r"(xch(n_kv & 1, h)), "f"(l_run) : "memory");
       asm volatile("bar.sync %0, %1;" ::"r"(quad_bar), "n"(32 * SPLIT) : "memory");
@@ -475,6 +517,7 @@ fmha_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     }
     mbar_wait(pv_done(i, (n_kv - 1) & 1), (uint32_t)((n_kv - 1) >> 1) & 1u);   // the commit covers every earlier MMA too
     tc_fence_after();
+    if (i == 0 && h == 0 && rit == 0) PAIR_STAMP(4);
     const float inv_l = 1.0f / l_run;
 #pragma unroll
     for (int cb = 0; cb < OC / 32; ++cb) {
@@ -497,16 +540,28 @@ fmha_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     }
     fence_proxy_async_smem();
     asm volatile("bar.sync %0, %1;" ::"r"(9u + (uint32_t)i), "n"(128 * SPLIT) : "memory");   // all softmax threads of this tile
+    if (part >= 0 && h == 0) {   // chunk cluster: what the merge needs to weigh this partial result (row sums are complete in every slice)
+      const int wrow = part * (2 * QT * Cfg::BQ) + (2 * i + (int)rank) * Cfg::BQ + rit;
+      *reinterpret_cast<float2*>(p.ws_ml + 2ll * wrow) = make_float2(m_run * c, l_run);
+    }
     if (h == 0 && rit == 0) {
+      if (part >= 0) {
 #pragma unroll
-      for (int sl = 0; sl < 2; ++sl) tma_store_4d(&tmO, smem_q(i) + sl * Cfg::Q_SLAB_BYTES, sl * 64, head, q0, batch);   // rows >= len_q are clipped
+        for (int sl = 0; sl < 2; ++sl)
+          tma_store_4d(&tmW, smem_q(i) + sl * Cfg::Q_SLAB_BYTES, sl * 64, 0, part * (2 * QT * Cfg::BQ) + (2 * i + (int)rank) * Cfg::BQ, 0);
+      } else {
+#pragma unroll
+        for (int sl = 0; sl < 2; ++sl) tma_store_4d(&tmO, smem_q(i) + sl * Cfg::Q_SLAB_BYTES, sl * 64, head, q0, batch);   // rows >= len_q are clipped
+      }
       tma_store_commit();
       tma_store_wait_read<0>();   // the buffer must stay intact until the TMA unit has read it
+      if (i == 0) PAIR_STAMP(5);
     }
   }
 
   tc_fence_before();
   cluster_sync_all();   // the peer's tensor memory / shared memory is in use until both CTAs are done
+  if (warp == 0 && lane == 0) PAIR_STAMP(6);
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc<2>(tmem_base, 512);
@@ -522,10 +577,144 @@ static int make_map4(CUtensorMap* tm, const void* ptr, long long B, long long H,
   return encode_tensor_map(tm, ptr, 2, false, 4, dims, strides, box, true);
 }
 
+// ---- merge of the key chunks of the split units: one warp per query row ------------------------------------------------------------------
+// O[row] = sum_k w_k O_k[row] / sum_k w_k,  w_k = l_k 2^(m_k - max_k m_k)   (m_k = the chunk's reference maximum in the log2 domain, l_k its row sum)
+struct FmhaPairCombineParams {
+  const __nv_bfloat16* ws_o;   // [chunk][rows_per_unit][128] normalised partial O
+  const float* ws_ml;          // [chunk][rows_per_unit][2]
+  __nv_bfloat16* O;
+  long long o_bs, o_rs, o_hs;
+  int len_q, q_blocks, heads, rows_per_unit;
+  int n_full, split_a, split_k, n_split_units;
+};
+__global__ void __launch_bounds__(256) fmha_pair_combine_kernel(const FmhaPairCombineParams p) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int w = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = (int)(threadIdx.x & 31u);
+  const int u = w / p.rows_per_unit, r = w - u * p.rows_per_unit;
+  if (u >= p.n_split_units) return;
+  const int unit = p.n_full + u;
+  const int qb = unit % p.q_blocks, head = (unit / p.q_blocks) % p.heads, batch = unit / (p.q_blocks * p.heads);
+  const int row = qb * p.rows_per_unit + r;
+  if (row >= p.len_q) return;
+  const int k = u < p.split_a ? p.split_k : p.split_k + 1;
+  const int first = u < p.split_a ? u * p.split_k : p.split_a * p.split_k + (u - p.split_a) * (p.split_k + 1);
+  float mx = -INFINITY;
+  for (int ci = 0; ci < k; ++ci) mx = fmaxf(mx, p.ws_ml[2ll * ((long long)(first + ci) * p.rows_per_unit + r)]);
+  float acc[4] = {0.f, 0.f, 0.f, 0.f}, wsum = 0.f;
+  for (int ci = 0; ci < k; ++ci) {
+    const long long wrow = (long long)(first + ci) * p.rows_per_unit + r;
+    const float2 ml = *reinterpret_cast<const float2*>(p.ws_ml + 2 * wrow);
+    const float wk = ml.y * ex2_approx(ml.x - mx);
+    const uint2 v = *reinterpret_cast<const uint2*>(p.ws_o + wrow * 128 + lane * 4);
+    wsum += wk;
+    acc[0] = fmaf(wk, __uint_as_float(v.x << 16), acc[0]);
+    acc[1] = fmaf(wk, __uint_as_float(v.x & 0xffff0000u), acc[1]);
+    acc[2] = fmaf(wk, __uint_as_float(v.y << 16), acc[2]);
+    acc[3] = fmaf(wk, __uint_as_float(v.y & 0xffff0000u), acc[3]);
+  }
+  const float inv = 1.0f / wsum;
+  uint2 o;
+  o.x = pack_bf16(acc[0] * inv, acc[1] * inv);
+  o.y = pack_bf16(acc[2] * inv, acc[3] * inv);
+  *reinterpret_cast<uint2*>(p.O + (long long)batch * p.o_bs + (long long)row * p.o_rs + (long long)head * p.o_hs + lane * 4) = o;
+}
+
+// Key split of the last wave.  `slots` clusters run at a time; units % slots units are left for a wave that would keep most SMs idle for a
+// whole pass over the keys.  They are cut into slots * r chunks (r = 1..3 short waves), the variant with the smallest estimated time wins;
+// a chunk costs its steps plus kChunkOverhead steps (prologue, pipeline fill, epilogue), the merge kMergeCost steps.
+struct PairSplitPlan {
+  int n_full, split_a, split_k, n_chunks, n_split_units;
+};
+static PairSplitPlan plan_pair_split(long long units, int n_kv, int slots, unsigned force_rounds) {
+  constexpr int kMinSteps = 4, kChunkOverhead = 3, kMergeCost = 2;
+  PairSplitPlan none{(int)units, 0, 1, 0, 0};
+  if (slots <= 0 || units > (1ll << 24)) return none;
+  const int rem = (int)(units % slots);
+  if (rem == 0) return none;
+  const int cap = n_kv / kMinSteps;      // most chunks a unit may be cut into
+  if (cap < 2) return none;
+  PairSplitPlan best = none;
+  int best_cost = n_kv + kChunkOverhead;
+  for (int r = 1; r <= 3; ++r) {
+    if (force_rounds && (int)force_rounds != r) continue;
+    const int total = slots * r;
+    int base = total / rem;
+    if (base < 1) continue;
+    int extra = total - base * rem;      // units that get base + 1 chunks
+    if (base >= cap) { base = cap; extra = 0; }
+    if (base < 2 && extra == 0) continue;
+    const int longest = (n_kv + base - 1) / base;
+    const int cost = r * (longest + kChunkOverhead) + kMergeCost;
+    if (cost < best_cost || force_rounds) {
+      best_cost = cost;
+      best = PairSplitPlan{(int)(units - rem), rem - extra, base, (rem - extra) * base + extra * (base + 1), rem};
+    }
+  }
+  return best;
+}
+static constexpr long long kPairChunkBytes(int rows_per_unit) { return (long long)rows_per_unit * (128 * 2 + 2 * 4); }
+
 template <int QT_, int SPLIT_, int POLY_, int FAST_ = 0>
-static int launch_fmha_pair(const vist3a_fmha_args& a, cudaStream_t stream) {
+static int pair_slots(int* slots) {
+  // clusters of this kernel the device runs at a time (cached per device)
   using Cfg = FmhaPairCfg<QT_, SPLIT_, POLY_, FAST_>;
-  CUtensorMap tmQ, tmK, tmV, tmO;
+  static std::atomic<int> cache[64];
+  int dev = 0;
+  V3A_CUDA_OK(cudaGetDevice(&dev));
+  int v = dev < 64 ? cache[dev].load(std::memory_order_acquire) : 0;
+  if (v <= 0) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * 1024);
+    cfg.blockDim = dim3(Cfg::THREADS);
+    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, fmha_pair_kernel<QT_, SPLIT_, POLY_, FAST_>, &cfg) != cudaSuccess || n <= 0) {
+      (void)cudaGetLastError();
+      int sms = 0;
+      V3A_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+      n = sms / 2;
+    }
+    v = n;
+    if (dev < 64) cache[dev].store(v, std::memory_order_release);
+  }
+  *slots = v;
+  return VIST3A_OK;
+}
+
+// flags bit 17: no key split; bits 18-19: force the number of short waves (A/B measurements)
+template <int QT_, int SPLIT_, int POLY_, int FAST_ = 0>
+static int launch_fmha_pair(const vist3a_fmha_args& a, cudaStream_t stream, long long* ws_query) {
+  using Cfg = FmhaPairCfg<QT_, SPLIT_, POLY_, FAST_>;
+  auto kern = fmha_pair_kernel<QT_, SPLIT_, POLY_, FAST_>;
+  static std::atomic<unsigned long long> attr_done{0};
+  V3A_CUDA_OK(ensure_dynamic_smem(kern, Cfg::SMEM_BYTES, attr_done));
+  const int rows_per_unit = 2 * Cfg::QT * Cfg::BQ;
+  const long long q_blocks = (a.len_q + rows_per_unit - 1) / rows_per_unit;
+  const long long units = q_blocks * a.heads * a.batch;
+  V3A_REQUIRE(units < (1ll << 29), VIST3A_ERR_INVALID, "fmha: too many query blocks");
+  const int n_kv = (int)((a.len_kv + Cfg::BKV - 1) / Cfg::BKV);
+  PairSplitPlan plan{(int)units, 0, 1, 0, 0};
+  if (!(a.flags & (1u << 17))) {
+    int slots = 0, rc = pair_slots<QT_, SPLIT_, POLY_, FAST_>(&slots);
+    if (rc) return rc;
+    plan = plan_pair_split(units, n_kv, slots, (a.flags >> 18) & 3u);
+  }
+  const long long ws_bytes = (long long)plan.n_chunks * kPairChunkBytes(rows_per_unit);
+  if (ws_query) {
+    *ws_query = ws_bytes;
+    return VIST3A_OK;
+  }
+  if (plan.n_chunks && (a.workspace == nullptr || a.workspace_bytes < ws_bytes || ((uintptr_t)a.workspace & 127) != 0))
+    plan = PairSplitPlan{(int)units, 0, 1, 0, 0};   // no (usable) workspace: every unit over all keys
+  CUtensorMap tmQ, tmK, tmV, tmO, tmW;
   int rc;
   if ((rc = make_map4(&tmQ, a.Q, a.batch, a.heads, a.len_q, 128, a.q_bs, a.q_rs, a.q_hs, Cfg::BQ))) return rc;
   if ((rc = make_map4(&tmK, a.K, a.batch, a.heads, a.len_kv, 128, a.k_bs, a.k_rs, a.k_hs, Cfg::BKV / 2))) return rc;
@@ -538,29 +727,59 @@ static int launch_fmha_pair(const vist3a_fmha_args& a, cudaStream_t stream) {
   p.row_scale = a.q_row_scale;
   p.trace = g_pair_trace.load(std::memory_order_relaxed);
   p.zero = 0u;
-  auto kern = fmha_pair_kernel<QT_, SPLIT_, POLY_, FAST_>;
-  static std::atomic<unsigned long long> attr_done{0};
-  V3A_CUDA_OK(ensure_dynamic_smem(kern, Cfg::SMEM_BYTES, attr_done));
-  const long long rows_per_cluster = 2 * Cfg::QT * Cfg::BQ;
-  dim3 grid((unsigned)(2 * ((a.len_q + rows_per_cluster - 1) / rows_per_cluster)), (unsigned)a.heads, (unsigned)a.batch);
-  V3A_CUDA_OK(launch_kernel(kern, grid, dim3(Cfg::THREADS), Cfg::SMEM_BYTES, stream, /*pdl=*/true, 2, tmQ, tmK, tmV, tmO, p));
+  p.q_blocks = (int)q_blocks;
+  p.heads = (int)a.heads;
+  p.n_full = plan.n_full;
+  p.split_a = plan.split_a;
+  p.split_k = plan.split_k;
+  p.ws_ml = nullptr;
+  if (plan.n_chunks) {
+    const long long wrows = (long long)plan.n_chunks * rows_per_unit;
+    if ((rc = make_map4(&tmW, a.workspace, 1, 1, wrows, 128, wrows * 128, 128, 128, Cfg::BQ))) return rc;
+    p.ws_ml = reinterpret_cast<float*>(static_cast<char*>(a.workspace) + wrows * 128 * 2);
+  } else {
+    tmW = tmO;
+  }
+  dim3 grid((unsigned)(2 * (plan.n_full + plan.n_chunks)));
+  V3A_CUDA_OK(launch_kernel(kern, grid, dim3(Cfg::THREADS), Cfg::SMEM_BYTES, stream, /*pdl=*/true, 2, tmQ, tmK, tmV, tmO, tmW, p));
   launch_counter().fetch_add(1);
+  if (plan.n_chunks) {
+    FmhaPairCombineParams c;
+    c.ws_o = static_cast<const __nv_bfloat16*>(a.workspace);
+    c.ws_ml = p.ws_ml;
+    c.O = static_cast<__nv_bfloat16*>(a.O);
+    c.o_bs = a.o_bs;
+    c.o_rs = a.o_rs;
+    c.o_hs = a.o_hs;
+    c.len_q = (int)a.len_q;
+    c.q_blocks = (int)q_blocks;
+    c.heads = (int)a.heads;
+    c.rows_per_unit = rows_per_unit;
+    c.n_full = plan.n_full;
+    c.split_a = plan.split_a;
+    c.split_k = plan.split_k;
+    c.n_split_units = plan.n_split_units;
+    const long long warps = (long long)plan.n_split_units * rows_per_unit;
+    V3A_CUDA_OK(launch_kernel(fmha_pair_combine_kernel, dim3((unsigned)((warps + 7) / 8)), dim3(256), 0, stream, /*pdl=*/true, 1, c));
+    launch_counter().fetch_add(1);
+  }
   return VIST3A_OK;
 }
 
 // head_dim 128 on CTA pairs; `variant` (A/B measurements): 0 = default: two query tiles per CTA, one thread per query row, P handed over in
 // two key halves, all exponentials on the MUFU; 1 / 2 = the same with 1 / 2 of every 8 column pairs on the FMA pipe; 3 = speculative
 // softmax (stale maximum, 64-column half-steps), all MUFU; 4 = the same with 2 of 8 on the FMA pipe; 5 / 6 = default with 3 / 4 of 8; 7 = speculative, 3 of 8
-int fmha_pair_entry(const vist3a_fmha_args& a, int variant, cudaStream_t stream) {
+// ws_query != nullptr: no launch, *ws_query = workspace bytes the key split of this problem would use (0: no split)
+int fmha_pair_entry(const vist3a_fmha_args& a, int variant, cudaStream_t stream, long long* ws_query) {
   switch (variant) {
-    case 1: return launch_fmha_pair<2, 1, 1>(a, stream);
-    case 2: return launch_fmha_pair<2, 1, 2>(a, stream);
-    case 3: return launch_fmha_pair<2, 1, 0, 1>(a, stream);
-    case 4: return launch_fmha_pair<2, 1, 2, 1>(a, stream);
-    case 5: return launch_fmha_pair<2, 1, 3>(a, stream);
-    case 6: return launch_fmha_pair<2, 1, 4>(a, stream);
-    case 7: return launch_fmha_pair<2, 1, 3, 1>(a, stream);
-    default: return launch_fmha_pair<2, 1, 0>(a, stream);
+    case 1: return launch_fmha_pair<2, 1, 1>(a, stream, ws_query);
+    case 2: return launch_fmha_pair<2, 1, 2>(a, stream, ws_query);
+    case 3: return launch_fmha_pair<2, 1, 0, 1>(a, stream, ws_query);
+    case 4: return launch_fmha_pair<2, 1, 2, 1>(a, stream, ws_query);
+    case 5: return launch_fmha_pair<2, 1, 3>(a, stream, ws_query);
+    case 6: return launch_fmha_pair<2, 1, 4>(a, stream, ws_query);
+    case 7: return launch_fmha_pair<2, 1, 3, 1>(a, stream, ws_query);
+    default: return launch_fmha_pair<2, 1, 0>(a, stream, ws_query);
   }
 }
 

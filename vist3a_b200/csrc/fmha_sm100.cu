@@ -915,9 +915,11 @@ static int launch_fmha(const vist3a_fmha_args& a, cudaStream_t stream) {
   return VIST3A_OK;
 }
 
-int fmha_pair_entry(const vist3a_fmha_args& a, int variant, cudaStream_t stream);   // fmha_pair_sm100.cu
+int fmha_pair_entry(const vist3a_fmha_args& a, int variant, cudaStream_t stream, long long* ws_query);   // fmha_pair_sm100.cu
 
-int fmha_entry(const vist3a_fmha_args* args, cudaStream_t stream) {
+// ws_query != nullptr: nothing is launched; *ws_query = bytes of workspace the selected kernel would use for this problem (0: none)
+int fmha_entry(const vist3a_fmha_args* args, cudaStream_t stream, long long* ws_query) {
+  if (ws_query) *ws_query = 0;
   V3A_REQUIRE(args != nullptr, VIST3A_ERR_INVALID, "fmha: null args");
   const vist3a_fmha_args& a = *args;
   V3A_REQUIRE(a.Q && a.K && a.V && a.O, VIST3A_ERR_INVALID, "fmha: null Q/K/V/O");
@@ -937,20 +939,23 @@ int fmha_entry(const vist3a_fmha_args* args, cudaStream_t stream) {
   // warpgroups, setmaxnreg-enlarged register file), bit1 (d=128) the 128-key aliased steps, bit2 a single MMA-issuing warp for both query tiles (measured slower: one thread cannot keep
   // the pipe fed); kept for A/B measurements.
   // head_dim 128: the CTA-pair kernel (fmha_pair_sm100.cu); flags bit 8 selects it, bits 9-11 its variant (A/B measurements)
-  if (a.head_dim == 128 && (a.flags & 256u)) return fmha_pair_entry(a, (int)((a.flags >> 9) & 7u), stream);
+  if (a.head_dim == 128 && (a.flags & 256u)) return fmha_pair_entry(a, (int)((a.flags >> 9) & 7u), stream, ws_query);
   const bool one = (a.flags & 1u) != 0;
   // Default (flags == 0), from same-process A/B runs on B200 (tools/fmha_variants.py, tools/fmha_pair_check.py; profiles/README.md): the speculative
   // softmax (stale running maximum, 64-column half-steps, one thread per row, 2-3 of 8 exponentials on the FMA pipe) everywhere; at head_dim 128
   // and >= 1024 keys on CTA pairs (+5.5 % over the former default at 4096 keys, device time in a CUDA graph), below that on one CTA (+1.7 % at 512
   // keys; +5.5 % on the decoder's 1029-key frame attention, +2.7 % on its 13 377-key global attention).  flags bit 13
   // selects the former default (two threads per row, exact running maximum) for A/B.
-  if (a.flags == 0u) {
+  // (flags bits 17-19 steer the key split of the pair kernel's last wave and do not select a kernel)
+  if ((a.flags & ~(7u << 17)) == 0u) {
+    if (ws_query && (a.head_dim == 64 || a.len_kv < 512)) return VIST3A_OK;
     // (head_dim 64, long key sequences -- the decoder's global attention: two threads per row, +2 % over one thread per row at 13 377 keys; -7 % at 1029)
     if (a.head_dim == 64) return a.len_kv >= 4096 ? launch_fmha<64, 128, 0, 2, 2>(a, stream) : launch_fmha<64, 128, 2, 1, 1>(a, stream);
-    if (a.len_kv >= 1024) return fmha_pair_entry(a, 7, stream);
-    if (a.len_kv >= 512) return fmha_pair_entry(a, 4, stream);   // cross-attention (512 text tokens): 676 vs 659 TFLOP/s on one CTA
+    if (a.len_kv >= 1024) return fmha_pair_entry(a, 7, stream, ws_query);
+    if (a.len_kv >= 512) return fmha_pair_entry(a, 4, stream, ws_query);   // cross-attention (512 text tokens): 676 vs 659 TFLOP/s on one CTA
     return launch_fmha<128, 64, 2, 1, 1>(a, stream);
   }
+  if (ws_query) return VIST3A_OK;   // the single-CTA variants below use no workspace
   if (a.flags & 65536u) {   // ONE query tile per CTA, speculative softmax with two threads per row; bits 3-5 = FMA-pipe exponentials per 8 pairs
     const unsigned np = (a.flags >> 3) & 7u;
     if (a.head_dim == 64) {

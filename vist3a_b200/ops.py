@@ -136,6 +136,10 @@ _GEMM_EXTRA_FLAGS = int(os.environ.get("VIST3A_GEMM_FLAGS", "0"), 0)   # A/B swi
 _FMHA_DEFAULT_FLAGS = int(os.environ.get("VIST3A_FMHA_FLAGS", "0"), 0)
 
 
+_FMHA_WS_BYTES: dict = {}
+_FMHA_WS: dict = {}
+
+
 def fmha(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, scale: Optional[float] = None,
          out: Optional[torch.Tensor] = None, flags: int = 0, q_row_scale: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Non-causal attention.  q [B, Lq, H, D], k/v [B, Lkv, H, D] (any strides with unit inner stride,
@@ -164,7 +168,24 @@ def fmha(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, scale: Optional[f
         if q_row_scale.dtype != torch.float32 or not q_row_scale.is_contiguous() or q_row_scale.numel() != B * Lq or not q_row_scale.is_cuda:
             raise TypeError("fmha: q_row_scale must be a contiguous CUDA float32 tensor of B*Lq elements")
         a.q_row_scale = q_row_scale.data_ptr()
-    L.check(L.load().vist3a_fmha_fwd(C.byref(a), _stream()))
+    st = _stream()
+    if D == 128 and Lk >= 512:
+        # scratch of the key-split last wave (vist3a_fmha_workspace_bytes): one buffer per (device, stream), reused by every call on that stream
+        key = (q.device.index, B, H, Lq, Lk, a.flags)
+        need = _FMHA_WS_BYTES.get(key)
+        if need is None:
+            need = int(L.load().vist3a_fmha_workspace_bytes(C.byref(a)))
+            if need < 0:
+                L.check(need)
+            _FMHA_WS_BYTES[key] = need
+        if need:
+            skey = (q.device.index, st or 0)
+            ws = _FMHA_WS.get(skey)
+            if ws is None or ws.numel() < need:
+                ws = torch.empty(need, dtype=torch.uint8, device=q.device)
+                _FMHA_WS[skey] = ws
+            a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
+    L.check(L.load().vist3a_fmha_fwd(C.byref(a), st))
     return out
 
 
