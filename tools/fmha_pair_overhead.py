@@ -27,10 +27,10 @@ torch.cuda.synchronize()
 lib.v3a_debug_fmha_pair_trace(None)
 t = buf.cpu()[1024:].view(NCL, 8)
 cl = [r.tolist() for r in t if int(r[0])]
-t0 = min(r[0] for r in cl)
-print(f"flags {flags:#x}: {len(cl)} clusters, kernel span {(max(r[6] for r in cl) - t0) / 1000:.1f} us")
-names = ["entry->setup", "setup->first S", "first S->last P", "last P->PV done", "PV done->stored", "stored->exit", "total"]
-cols = [[r[1] - r[0], r[2] - r[1], r[3] - r[2], r[4] - r[3], r[5] - r[4], r[6] - r[5], r[6] - r[0]] for r in cl]
+t0 = min(r[6] for r in cl)
+print(f"flags {flags:#x}: {len(cl)} items, kernel span (first entry -> last store) {(max(r[5] for r in cl) - t0) / 1000:.1f} us")
+names = ["item start->Q requested", "Q requested->first S", "first S->last P", "last P->PV done", "PV done->stored", "total"]
+cols = [[r[1] - r[0], r[2] - r[1], r[3] - r[2], r[4] - r[3], r[5] - r[4], r[5] - r[0]] for r in cl]
 for n, c in zip(names, zip(*cols)):
     print(f"  {n:18s} median {statistics.median(c) / 1000:7.2f} us   min {min(c) / 1000:7.2f}   max {max(c) / 1000:7.2f}")
 by_sm = {}
@@ -39,11 +39,8 @@ for r in cl:
 gaps = []
 for sm, rs in by_sm.items():
     rs.sort(key=lambda r: r[0])
-    gaps += [b[0] - a[6] for a, b in zip(rs, rs[1:])]
+    gaps += [b[2] - a[4] for a, b in zip(rs, rs[1:])]
 if gaps:
-    print(f"  gap exit -> next cluster's entry on the same SM: median {statistics.median(gaps) / 1000:.2f} us  min {min(gaps) / 1000:.2f}  max {max(gaps) / 1000:.2f}  ({len(by_sm)} leader SMs)")
+    print(f"  tensor pipe idle between items on the same SM (last P V done -> next item's first S): median {statistics.median(gaps) / 1000:.2f} us  min {min(gaps) / 1000:.2f}  max {max(gaps) / 1000:.2f}  ({len(by_sm)} leader SMs)")
 starts = sorted(r[0] - t0 for r in cl)
-print("  entry times of the first wave (us):", [round(x / 1000, 1) for x in starts[:len(by_sm)][::12]])
-print("  per-wave entry (us):", [round(x / 1000, 1) for x in starts[::len(by_sm)]])
-for w in range(0, len(cl), len(by_sm)):
-    pass
+print("  item start times (us), every", len(by_sm), "th:", [round(x / 1000, 1) for x in starts[::len(by_sm)]])

@@ -31,15 +31,19 @@ def main():
             rec[name] = round(float((o.float() - ref).norm() / ref.norm()), 5)
         out["check"].append(rec)
         print(json.dumps(rec), flush=True)
-    for name, B, H, Lq, Lk in (("dit_self_1.3b", 2, 12, 4096, 4096), ("dit_self_14b", 2, 40, 4096, 4096), ("b1", 1, 12, 4096, 4096), ("dit_cross", 2, 12, 4096, 512),
+    if "--no-time" in sys.argv:
+        return
+    # persistent clusters + key split (0) | one cluster per item (bit 20) | no key split (bit 17) | neither: the round-2 kernel's decomposition
+    variants = (("persist+split", 0), ("split", 1 << 20), ("persist", NOSPLIT), ("neither", NOSPLIT | (1 << 20)), ("r1", 1 << 18), ("r3", 3 << 18))
+    for name, B, H, Lq, Lk in (("dit_self_1.3b", 2, 12, 4096, 4096), ("dit_cross", 2, 12, 4096, 512), ("dit_self_14b", 2, 40, 4096, 4096), ("b1", 1, 12, 4096, 4096),
                                ("small", 1, 12, 1024, 4096)):
         q = torch.randn(B, Lq, H, 128, device="cuda").bfloat16()
         k = torch.randn(B, Lk, H, 128, device="cuda").bfloat16()
         v = torch.randn(B, Lk, H, 128, device="cuda").bfloat16()
         o = torch.empty_like(q)
         rec = {"shape": name}
-        for rnd in range(2):
-            for vn, fl in (("split", 0), ("nosplit", NOSPLIT), ("r1", 1 << 18), ("r2", 2 << 18), ("r3", 3 << 18)):
+        for rnd in range(4):
+            for vn, fl in variants:
                 ms = timeit(lambda: ops.fmha(q, k, v, out=o, flags=fl))
                 rec.setdefault(vn, []).append(round(4 * B * H * Lq * Lk * 128 / ms / 1e9, 1))
         print(json.dumps(rec), flush=True)

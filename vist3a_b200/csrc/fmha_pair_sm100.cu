@@ -42,6 +42,7 @@ struct FmhaPairParams {
   // normalised partial O (bf16) and per row (reference maximum * c, row sum) to the workspace and fmha_pair_combine_kernel merges them.
   int q_blocks, heads;
   int n_full, split_a, split_k;
+  int n_items;             // n_full + number of chunks: cluster c works on items c, c + gridDim.x / 2, ... (persistent clusters, one per SM pair)
   float* ws_ml;            // [chunk][256 QT rows][2] fp32 (behind the partial O tiles the workspace tensor map tmW addresses)
 };
 
@@ -52,15 +53,15 @@ static std::atomic<long long*> g_pair_trace{nullptr};
 extern "C" void v3a_debug_fmha_pair_trace(void* buf) { g_pair_trace.store(reinterpret_cast<long long*>(buf)); }
 #define PAIR_TRACE(j, i, slot)                                                                         \
   do {                                                                                                 \
-    if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (j) < 64) p.trace[((j) * 2 + (i)) * 8 + (slot)] = clock64(); \
+    if (p.trace && blockIdx.x == 0 && item == item0 && (j) < 64) p.trace[((j) * 2 + (i)) * 8 + (slot)] = clock64(); \
   } while (0)
 
-// second part of the debug buffer, [cluster][8] at offset 1024: %globaltimer (ns) of every cluster's leader CTA at
-//   0 kernel entry   1 set-up done (barriers, tensor memory, cluster sync, PDL wait)   2 tile 0 sees its first S   3 tile 0 has handed over its
-//   last P   4 last P V complete   5 tile 0's output stored   6 after the final cluster sync   7 SM id
+// second part of the debug buffer, [item][8] at offset 1024: %globaltimer (ns) in the leader CTA of the cluster that works on the item:
+//   0 producer turns to the item   1 Q requested (the previous item's output has left the Q buffers)   2 tile 0 sees its first S
+//   3 tile 0 has handed over its last P   4 last P V complete   5 tile 0's output stored   6 kernel entry of the cluster   7 SM id
 #define PAIR_STAMP(slot)                                                                                    \
   do {                                                                                                      \
-    if (p.trace && rank == 0) p.trace[1024 + (long long)(blockIdx.x >> 1) * 8 + (slot)] = (long long)globaltimer_ns(); \
+    if (p.trace && rank == 0) p.trace[1024 + (long long)item * 8 + (slot)] = (long long)globaltimer_ns();   \
   } while (0)
 
 template <int QT_, int SPLIT_, int POLY_, int FAST_ = 0>
@@ -80,7 +81,7 @@ struct FmhaPairCfg {
   static constexpr int V_HALF_BYTES = BKV * 128;       // 128 keys x this CTA's 64 head-dim columns = 16 KB
   static constexpr int ST = 4;                         // ring stages of K and of V
   static constexpr int NH = SPLIT == 1 ? 2 : 1;        // P(j) is handed to the MMA warp in NH key halves (one thread per row: after 64 keys each)
-  static constexpr int NBARS = 1 + 4 * ST + 8 * QT + 2 * QT;   // q_full | k_full, k_empty, v_full, v_empty | per tile: s_full[2], p_full[2][2], pv_done[2] | pvh_done[2]
+  static constexpr int NBARS = 1 + 4 * ST + 8 * QT + 2 * QT + 1;   // q_full | k_full, k_empty, v_full, v_empty | per tile: s_full[2], p_full[2][2], pv_done[2] | pvh_done[2] | q_free
   static constexpr bool FAST = FAST_ != 0;             // speculative (stale-maximum) softmax in 64-column half-steps (fmha_math.cuh), one thread per row
   static_assert(!FAST || (SPLIT_ == 1 && QT_ == 2), "the speculative softmax runs one thread per row on two tiles per CTA");
   static constexpr int XCH_BYTES = 2 * QT * SPLIT * 128 * 4;  // [step parity][tile][slice][row] fp32
@@ -113,6 +114,7 @@ fmha_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   auto p_full = [&](int i, int b, int hh) { return bar_base + 8u * (1 + 4 * ST + 8 * i + 2 + 2 * b + hh); };
   auto pv_done = [&](int i, int b) { return bar_base + 8u * (1 + 4 * ST + 8 * i + 6 + b); };
   auto pvh_done = [&](int i, int b) { return bar_base + 8u * (1 + 4 * ST + 8 * QT + 2 * i + b); };   // first key half of P_i(j) V(j) has completed
+  const uint32_t q_free = bar_base + 8u * (1 + 4 * ST + 10 * QT);   // this CTA's tiles have stored the item's output (the Q buffers double as staging)
   const uint32_t tmem_slot = bar_base + 8u * Cfg::NBARS;
   const uint32_t xch_base = tmem_slot + 16u;
 
@@ -120,35 +122,54 @@ fmha_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   const uint32_t lane = lane_id();
   const uint32_t rank = cluster_ctarank();          // 0 = leader
   const bool leader = rank == 0;
-  // the cluster owns 256 * QT consecutive query rows: tile i of the pair = rows [256 i, 256 i + 256), this CTA's half = [128 rank, +128)
-  int unit = (int)(blockIdx.x >> 1);
-  int kv0 = 0, n_kv = (p.len_kv + BKV - 1) / BKV;   // first 128-key step and number of steps of this cluster
-  const int part = unit - p.n_full;                 // >= 0: chunk cluster number (its slot in the workspace)
-  if (part >= 0) {
-    int k = p.split_k, u, ci;
-    const int na = p.split_a * p.split_k;
-    if (part < na) {
-      u = part / k;
-      ci = part - u * k;
-    } else {
-      ++k;
-      u = (part - na) / k;
-      ci = (part - na) - u * k;
-      u += p.split_a;
+  // Persistent clusters: cluster c works on items c, c + G, c + 2 G, ... (G clusters in the grid).  Items [0, n_full) are whole units, the
+  // others key chunks (FmhaPairParams).  A unit owns 256 * QT consecutive query rows: tile i of the pair = rows [256 i, 256 i + 256), this
+  // CTA's half = [128 rank, +128).
+  const int n_kv_all = (p.len_kv + BKV - 1) / BKV;
+  const int item0 = (int)(blockIdx.x >> 1), item_step = (int)(gridDim.x >> 1);
+  struct Item {
+    int qb, head, batch;
+    int kv0, n_kv;   // first 128-key step and number of steps
+    int part;        // >= 0: chunk number (its slot in the workspace)
+  };
+  auto get_item = [&](int item) {
+    Item w;
+    int unit = item;
+    w.kv0 = 0;
+    w.n_kv = n_kv_all;
+    w.part = item - p.n_full;
+    if (w.part >= 0) {
+      int k = p.split_k, u, ci;
+      const int na = p.split_a * p.split_k;
+      if (w.part < na) {
+        u = w.part / k;
+        ci = w.part - u * k;
+      } else {
+        ++k;
+        u = (w.part - na) / k;
+        ci = (w.part - na) - u * k;
+        u += p.split_a;
+      }
+      unit = p.n_full + u;
+      w.kv0 = ci * n_kv_all / k;
+      w.n_kv = (ci + 1) * n_kv_all / k - w.kv0;
     }
-    unit = p.n_full + u;
-    kv0 = ci * n_kv / k;
-    n_kv = (ci + 1) * n_kv / k - kv0;
-  }
-  const int qb = unit % p.q_blocks, head = (unit / p.q_blocks) % p.heads, batch = unit / (p.q_blocks * p.heads);
-  auto q0_of = [&](int i) { return qb * (2 * QT * Cfg::BQ) + (2 * i + (int)rank) * Cfg::BQ; };
+    w.qb = unit % p.q_blocks;
+    w.head = (unit / p.q_blocks) % p.heads;
+    w.batch = unit / (p.q_blocks * p.heads);
+    return w;
+  };
+  auto q0_of = [&](const Item& w, int i) { return w.qb * (2 * QT * Cfg::BQ) + (2 * i + (int)rank) * Cfg::BQ; };
 
   if (warp == 0 && lane == 0) {
-    PAIR_STAMP(0);
     if (p.trace && rank == 0) {
       uint32_t smid;
       asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-      p.trace[1024 + (long long)(blockIdx.x >> 1) * 8 + 7] = smid;
+      const long long now = (long long)globaltimer_ns();
+      for (int item = item0; item < p.n_items; item += item_step) {
+        p.trace[1024 + (long long)item * 8 + 6] = now;
+        p.trace[1024 + (long long)item * 8 + 7] = smid;
+      }
     }
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmK);
@@ -157,6 +178,7 @@ fmha_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   }
   if (warp == 1 && lane == 0) {
     mbar_init(q_full, 1);
+    mbar_init(q_free, QT);
     for (int s = 0; s < ST; ++s) {
       mbar_init(k_full(s), 1);
       mbar_init(k_empty(s), 1);
@@ -184,34 +206,39 @@ fmha_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 
   if (warp == 0) {
     // ------------------------------ TMA producer (warp-uniform control flow, one elected lane issues) ------------------------------
-    if (lane == 0) PAIR_STAMP(1);
-    if (elect_one()) {
-      if (leader) mbar_expect_tx(q_full, 2u * QT * Cfg::Q_TILE_BYTES);
-#pragma unroll
-      for (int i = 0; i < QT; ++i) {
-#pragma unroll
-        for (int sl = 0; sl < 2; ++sl) tma_load_4d_2sm(smem_q(i) + sl * Cfg::Q_SLAB_BYTES, &tmQ, q_full, sl * 64, head, q0_of(i), batch);
-      }
-    }
-    __syncwarp();
-    int s = 0;
+    int s = 0, n_it = 0;
     uint32_t ph = 0;
-    for (int j = 0; j < n_kv; ++j) {
-      mbar_wait(k_empty(s), ph ^ 1u);
+    for (int item = item0; item < p.n_items; item += item_step, ++n_it) {
+      const Item w = get_item(item);
+      if (lane == 0) PAIR_STAMP(0);
+      if (n_it > 0) mbar_wait(q_free, (uint32_t)(n_it - 1) & 1u);   // the previous item's output has been read out of the Q buffers
       if (elect_one()) {
-        if (leader) mbar_expect_tx(k_full(s), 2u * Cfg::K_HALF_BYTES);
+        if (leader) mbar_expect_tx(q_full, 2u * QT * Cfg::Q_TILE_BYTES);
 #pragma unroll
-        for (int sl = 0; sl < 2; ++sl)
-          tma_load_4d_2sm(smem_k(s) + sl * Cfg::K_SLAB_BYTES, &tmK, k_full(s), sl * 64, head, (kv0 + j) * BKV + (int)rank * (BKV / 2), batch);
+        for (int i = 0; i < QT; ++i) {
+#pragma unroll
+          for (int sl = 0; sl < 2; ++sl) tma_load_4d_2sm(smem_q(i) + sl * Cfg::Q_SLAB_BYTES, &tmQ, q_full, sl * 64, w.head, q0_of(w, i), w.batch);
+        }
       }
       __syncwarp();
-      mbar_wait(v_empty(s), ph ^ 1u);
-      if (elect_one()) {
-        if (leader) mbar_expect_tx(v_full(s), 2u * Cfg::V_HALF_BYTES);
-        tma_load_4d_2sm(smem_v(s), &tmV, v_full(s), (int)rank * 64, head, (kv0 + j) * BKV, batch);
+      if (lane == 0) PAIR_STAMP(1);
+      for (int j = 0; j < w.n_kv; ++j) {
+        mbar_wait(k_empty(s), ph ^ 1u);
+        if (elect_one()) {
+          if (leader) mbar_expect_tx(k_full(s), 2u * Cfg::K_HALF_BYTES);
+#pragma unroll
+          for (int sl = 0; sl < 2; ++sl)
+            tma_load_4d_2sm(smem_k(s) + sl * Cfg::K_SLAB_BYTES, &tmK, k_full(s), sl * 64, w.head, (w.kv0 + j) * BKV + (int)rank * (BKV / 2), w.batch);
+        }
+        __syncwarp();
+        mbar_wait(v_empty(s), ph ^ 1u);
+        if (elect_one()) {
+          if (leader) mbar_expect_tx(v_full(s), 2u * Cfg::V_HALF_BYTES);
+          tma_load_4d_2sm(smem_v(s), &tmV, v_full(s), (int)rank * 64, w.head, (w.kv0 + j) * BKV, w.batch);
+        }
+        __syncwarp();
+        if (++s == ST) { s = 0; ph ^= 1u; }
       }
-      __syncwarp();
-      if (++s == ST) { s = 0; ph ^= 1u; }
     }
   } else if (warp == 1) {
     // ------------------------------ MMA issue (leader CTA; the whole warp runs the control flow, one elected lane issues) ----------
@@ -221,11 +248,12 @@ fmha_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       int qs = 0, vs = 0;
       uint32_t qph = 0, vph = 0;
       // S_i(j) = Q_i K(j)^T for tile i; all tiles use key tile j back to back: the first waits for it, the last releases its ring slot
-      auto issue_qk = [&](int i, int j) {
+      // g = number of the step counted over all items of this cluster: score buffer and barrier parities follow it
+      auto issue_qk = [&](int i, int g) {
         if (i == 0) mbar_wait(k_full(qs), qph);
         tc_fence_after();
         if (elect_one()) {
-          const uint32_t d_tmem = tmem_base + (uint32_t)i * Cfg::TILE_COLS + Cfg::TM_S + (uint32_t)(j % NSB) * Cfg::S_STRIDE;
+          const uint32_t d_tmem = tmem_base + (uint32_t)i * Cfg::TILE_COLS + Cfg::TM_S + (uint32_t)(g % NSB) * Cfg::S_STRIDE;
           const uint64_t qdesc = make_smem_desc_sw128(smem_q(i), 1024, 0);
           const uint64_t kdesc = make_smem_desc_sw128(smem_k(qs), 1024, 0);
 #pragma unroll
@@ -235,18 +263,18 @@ fmha_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             const uint64_t bo = (uint64_t)(((kk >> 2) * Cfg::K_SLAB_BYTES + (kk & 3) * 32) >> 4);
             umma_f16_ss<2>(d_tmem, qdesc + ao, kdesc + bo, idesc_qk, kk ? 1u : 0u);
           }
-          umma_commit_2sm_mc(s_full(i, j & 1), 3);
+          umma_commit_2sm_mc(s_full(i, g & 1), 3);
           if (i == QT - 1) umma_commit_2sm_mc(k_empty(qs), 3);
         }
         __syncwarp();
         if (i == QT - 1) { if (++qs == ST) { qs = 0; qph ^= 1u; } }
       };
-      auto issue_pv = [&](int i, int j, int hh) {   // hh: key half of P(j) (NH == 1: the whole tile)
+      auto issue_pv = [&](int i, int j, int g, int hh) {   // j: step within the item; hh: key half of P(j) (NH == 1: the whole tile)
         if (i == 0 && hh == 0) mbar_wait(v_full(vs), vph);
         tc_fence_after();
         if (elect_one()) {
           const uint32_t t_base = tmem_base + (uint32_t)i * Cfg::TILE_COLS;
-          const uint32_t p_tmem = t_base + Cfg::TM_S + (uint32_t)(j % NSB) * Cfg::S_STRIDE;
+          const uint32_t p_tmem = t_base + Cfg::TM_S + (uint32_t)(g % NSB) * Cfg::S_STRIDE;
           // this CTA's V half: key rows at a 128 B pitch (K dimension of the MMA), 64 head-dim columns = one swizzle row (MN dimension)
           const uint64_t vdesc = make_smem_desc_sw128(smem_v(vs), 1024, Cfg::V_HALF_BYTES);
           constexpr int KH = BKV / 16 / NH;
@@ -256,33 +284,40 @@ fmha_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             umma_f16_ts_2sm(t_base + Cfg::TM_O, p_tmem + (uint32_t)(kk * 8), vdesc + (uint64_t)((kk * 2048) >> 4), idesc_pv, (j | kk) ? 1u : 0u);
           }
           if (hh == NH - 1) {
-            umma_commit_2sm_mc(pv_done(i, j & 1), 3);
+            umma_commit_2sm_mc(pv_done(i, g & 1), 3);
             if (i == QT - 1) umma_commit_2sm_mc(v_empty(vs), 3);
           } else if (Cfg::FAST) {
-            umma_commit_2sm_mc(pvh_done(i, j & 1), 3);
+            umma_commit_2sm_mc(pvh_done(i, g & 1), 3);
           }
         }
         __syncwarp();
         if (i == QT - 1 && hh == NH - 1) { if (++vs == ST) { vs = 0; vph ^= 1u; } }
       };
-      mbar_wait(q_full, 0);
-      for (int j = 0; j < NSB && j < n_kv; ++j) {
+      int g0 = 0, n_it = 0;
+      for (int item = item0; item < p.n_items; item += item_step, ++n_it) {
+        const Item w = get_item(item);
+        // Q of this item is in shared memory: both CTAs have read the previous item's O out of tensor memory and stored it
+        mbar_wait(q_full, (uint32_t)n_it & 1u);
+        for (int j = 0; j < NSB && j < w.n_kv; ++j) {
 #pragma unroll
-        for (int i = 0; i < QT; ++i) issue_qk(i, j);
-      }
-      for (int j = 0; j < n_kv; ++j) {
-#pragma unroll
-        for (int i = 0; i < QT; ++i) {
-#pragma unroll
-          for (int hh = 0; hh < NH; ++hh) {
-            mbar_wait(p_full(i, j & 1, hh), (uint32_t)(j >> 1) & 1u);   // (this half of) P_i(j) of both CTAs is in tensor memory
-            tc_fence_after();
-            if (lane == 0 && hh == 0) PAIR_TRACE(j, i, 0);
-            issue_pv(i, j, hh);
-          }
-          if (j + NSB < n_kv) issue_qk(i, j + NSB);   // overwrites S_i(j) | P_i(j): ordered behind P_i(j) V(j) by the in-order tensor pipe
-          if (lane == 0) PAIR_TRACE(j, i, 1);
+          for (int i = 0; i < QT; ++i) issue_qk(i, g0 + j);
         }
+        for (int j = 0; j < w.n_kv; ++j) {
+          const int g = g0 + j;
+#pragma unroll
+          for (int i = 0; i < QT; ++i) {
+#pragma unroll
+            for (int hh = 0; hh < NH; ++hh) {
+              mbar_wait(p_full(i, g & 1, hh), (uint32_t)(g >> 1) & 1u);   // (this half of) P_i(j) of both CTAs is in tensor memory
+              tc_fence_after();
+              if (lane == 0 && hh == 0) PAIR_TRACE(j, i, 0);
+              issue_pv(i, j, g, hh);
+            }
+            if (j + NSB < w.n_kv) issue_qk(i, g + NSB);   // overwrites S_i(j) | P_i(j): ordered behind P_i(j) V(j) by the in-order tensor pipe
+            if (lane == 0) PAIR_TRACE(j, i, 1);
+          }
+        }
+        g0 += w.n_kv;
       }
     }
   } else if (warp >= 4) {
@@ -292,23 +327,32 @@ fmha_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     const uint32_t wq = warp & 3u;                   // TMEM lane quadrant this warp may access
     const int rit = (int)(wq * 32u + lane);          // row in this CTA's tile
     const uint32_t lane_base = tmem_base + ((wq * 32u) << 16) + (uint32_t)i * Cfg::TILE_COLS;
-    const int q0 = q0_of(i);
-    const int row = q0 + rit;
     const uint32_t o_addr = lane_base + Cfg::TM_O + (uint32_t)(h * OC);
     auto xch = [&](int par, int slice) { return xch_base + 4u * (uint32_t)(((par * QT + i) * SPLIT + slice) * 128 + rit); };
     const uint32_t quad_bar = 1u + (uint32_t)i * 4u + wq;   // named barrier of the SPLIT warps that own these 32 rows
+    int g = 0;                                         // step counted over all items of this cluster (barrier parities)
+    for (int item = item0; item < p.n_items; item += item_step) {
+    // (only what the key loop needs stays live across it; the epilogue decodes the item again)
+    int n_kv, kvalid;                                // steps of this item; keys from its first step to the end of the sequence
+    float c;
+    {
+      const Item w = get_item(item);
+      n_kv = w.n_kv;
+      kvalid = p.len_kv - w.kv0 * BKV;
+      const int row = q0_of(w, i) + rit;
+      c = (p.row_scale && row < p.len_q) ? p.scale_log2 * p.row_scale[(long long)w.batch * p.len_q + row] : p.scale_log2;
+    }
     float m_run = -INFINITY;                         // running (possibly stale) row max of raw scores
     float l_run = 0.0f;                              // running sum of exp2((s - m_run) * c) over this thread's columns
-    const float c = (p.row_scale && row < p.len_q) ? p.scale_log2 * p.row_scale[(long long)batch * p.len_q + row] : p.scale_log2;
     const uint64_t cc2 = pack2(c, c);
     if constexpr (Cfg::FAST) {
       // ---- speculative softmax: 64-column half-steps against the stale running maximum; each half of P(j) is handed to the tensor pipe as
       //      soon as it is stored (fmha_sm100.cu runs the same scheme on one CTA) ----
       float nmc = 0.0f;
       uint64_t mc2 = 0ull;
-      for (int j = 0; j < n_kv; ++j) {
-        const int b = j & 1;
-        mbar_wait(s_full(i, b), (uint32_t)(j >> 1) & 1u);
+      for (int j = 0; j < n_kv; ++j, ++g) {
+        const int b = g & 1;
+        mbar_wait(s_full(i, b), (uint32_t)(g >> 1) & 1u);
         tc_fence_after();
         const bool tr = wq == 0 && lane == 0;
         if (tr) PAIR_TRACE(j, i, 2);
@@ -321,7 +365,7 @@ fmha_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           tmem_ld_x32(p_addr + (uint32_t)(hh * 64) + 32u, r + 32);
           tmem_ld_wait();
           if (tr && hh == 0) PAIR_TRACE(j, i, 3);
-          const int valid = p.len_kv - (kv0 + j) * BKV - hh * 64;
+          const int valid = kvalid - j * BKV - hh * 64;
           if (valid < 64) {
 #pragma unroll
             for (int k = 0; k < 64; ++k)
@@ -350,8 +394,8 @@ fmha_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             if (j >= 1 || hh > 0) {
               // O holds P(0..j-1) V [+ the first half of P(j) V, handed over already]: those products must have completed; the second half
               // of P(j) V is not issued before this warp arrives on p_full, so O is quiescent afterwards
-              if (j >= 1) mbar_wait(pv_done(i, (j - 1) & 1), (uint32_t)((j - 1) >> 1) & 1u);
-              if (hh > 0) mbar_wait(pvh_done(i, b), (uint32_t)(j >> 1) & 1u);
+              if (j >= 1) mbar_wait(pv_done(i, (g - 1) & 1), (uint32_t)((g - 1) >> 1) & 1u);
+              if (hh > 0) mbar_wait(pvh_done(i, b), (uint32_t)(g >> 1) & 1u);
               tc_fence_after();
 #pragma unroll 1
               for (int cb = 0; cb < D / 16; ++cb) {
@@ -387,9 +431,9 @@ fmha_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         }
       }
     } else
-    for (int j = 0; j < n_kv; ++j) {
-      const int b = j & 1, sb = j % NSB;
-      mbar_wait(s_full(i, b), (uint32_t)(j >> 1) & 1u);
+    for (int j = 0; j < n_kv; ++j, ++g) {
+      const int b = g & 1, sb = g % NSB;
+      mbar_wait(s_full(i, b), (uint32_t)(g >> 1) & 1u);
       tc_fence_after();
       const bool tr = h == 0 && wq == 0 && lane == 0;
       if (tr) PAIR_TRACE(j, i, 2);
@@ -399,7 +443,7 @@ fmha_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       for (int cb = 0; cb < HC / 32; ++cb) tmem_ld_x32(s_addr + (uint32_t)(cb * 32), r + cb * 32);
       tmem_ld_wait();
       if (tr) PAIR_TRACE(j, i, 3);
-      const int valid = p.len_kv - (kv0 + j) * BKV - h * HC;   // columns of this thread that hold existing keys
+      const int valid = kvalid - j * BKV - h * HC;   // columns of this thread that hold existing keys
       if (valid < HC) {
 #pragma unroll
         for (int k = 0; k < HC; ++k)
@@ -432,7 +476,7 @@ fmha_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         const bool need = (m_new - m_run) * c > 8.0f;
         if (__any_sync(0xffffffffu, need)) {
           // O is accumulated by P(j-1) V(j-1): it must have finished before the rows are rescaled
-          mbar_wait(pv_done(i, (j - 1) & 1), (uint32_t)((j - 1) >> 1) & 1u);
+          mbar_wait(pv_done(i, (g - 1) & 1), (uint32_t)((g - 1) >> 1) & 1u);
           tc_fence_after();
           const float f = need ? ex2_approx((m_run - m_new) * c) : 1.0f;
           if (need) m_run = m_new;
@@ -506,16 +550,16 @@ fmha_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     // ---- epilogue: O / l -> bf16 -> shared memory (this CTA's Q buffer: every MMA has completed) -> one bulk tensor store per slab ----
     if (i == 0 && h == 0 && rit == 0) PAIR_STAMP(3);
     if constexpr (SPLIT > 1) {
-      asm volatile("st.shared.f32 [%0], %1;" ::"r"(xch(n_kv & 1, h)), "f"(l_run) : "memory");
+      asm volatile("st.shared.f32 [%0], %1;" ::"r"(xch(g & 1, h)), "f"(l_run) : "memory");
       asm volatile("bar.sync %0, %1;" ::"r"(quad_bar), "n"(32 * SPLIT) : "memory");
 #pragma unroll
       for (int o = 1; o < SPLIT; ++o) {
         float other;
-        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(other) : "r"(xch(n_kv & 1, (h + o) % SPLIT)) : "memory");
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(other) : "r"(xch(g & 1, (h + o) % SPLIT)) : "memory");
         l_run += other;
       }
     }
-    mbar_wait(pv_done(i, (n_kv - 1) & 1), (uint32_t)((n_kv - 1) >> 1) & 1u);   // the commit covers every earlier MMA too
+    mbar_wait(pv_done(i, (g - 1) & 1), (uint32_t)((g - 1) >> 1) & 1u);   // the commit covers every earlier MMA too
     tc_fence_after();
     if (i == 0 && h == 0 && rit == 0) PAIR_STAMP(4);
     const float inv_l = 1.0f / l_run;
@@ -540,6 +584,10 @@ fmha_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     }
     fence_proxy_async_smem();
     asm volatile("bar.sync %0, %1;" ::"r"(9u + (uint32_t)i), "n"(128 * SPLIT) : "memory");   // all softmax threads of this tile
+    int item_e = item;
+    asm volatile("" : "+r"(item_e));   // (decoded again rather than kept in registers across the key loop)
+    const Item w = get_item(item_e);
+    const int part = w.part, head = w.head, batch = w.batch, q0 = q0_of(w, i);
     if (part >= 0 && h == 0) {   // chunk cluster: what the merge needs to weigh this partial result (row sums are complete in every slice)
       const int wrow = part * (2 * QT * Cfg::BQ) + (2 * i + (int)rank) * Cfg::BQ + rit;
       *reinterpret_cast<float2*>(p.ws_ml + 2ll * wrow) = make_float2(m_run * c, l_run);
@@ -556,12 +604,13 @@ fmha_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       tma_store_commit();
       tma_store_wait_read<0>();   // the buffer must stay intact until the TMA unit has read it
       if (i == 0) PAIR_STAMP(5);
+      mbar_arrive(q_free);        // the producer may load the next item's Q over it
     }
+    }   // items
   }
 
   tc_fence_before();
   cluster_sync_all();   // the peer's tensor memory / shared memory is in use until both CTAs are done
-  if (warp == 0 && lane == 0) PAIR_STAMP(6);
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc<2>(tmem_base, 512);
@@ -689,7 +738,7 @@ static int pair_slots(int* slots) {
   return VIST3A_OK;
 }
 
-// flags bit 17: no key split; bits 18-19: force the number of short waves (A/B measurements)
+// flags bit 17: no key split; bits 18-19: force the number of short waves; bit 20: one cluster per item instead of persistent clusters (A/B measurements)
 template <int QT_, int SPLIT_, int POLY_, int FAST_ = 0>
 static int launch_fmha_pair(const vist3a_fmha_args& a, cudaStream_t stream, long long* ws_query) {
   using Cfg = FmhaPairCfg<QT_, SPLIT_, POLY_, FAST_>;
@@ -702,11 +751,9 @@ static int launch_fmha_pair(const vist3a_fmha_args& a, cudaStream_t stream, long
   V3A_REQUIRE(units < (1ll << 29), VIST3A_ERR_INVALID, "fmha: too many query blocks");
   const int n_kv = (int)((a.len_kv + Cfg::BKV - 1) / Cfg::BKV);
   PairSplitPlan plan{(int)units, 0, 1, 0, 0};
-  if (!(a.flags & (1u << 17))) {
-    int slots = 0, rc = pair_slots<QT_, SPLIT_, POLY_, FAST_>(&slots);
-    if (rc) return rc;
-    plan = plan_pair_split(units, n_kv, slots, (a.flags >> 18) & 3u);
-  }
+  int slots = 0, rc = pair_slots<QT_, SPLIT_, POLY_, FAST_>(&slots);
+  if (rc) return rc;
+  if (!(a.flags & (1u << 17))) plan = plan_pair_split(units, n_kv, slots, (a.flags >> 18) & 3u);
   const long long ws_bytes = (long long)plan.n_chunks * kPairChunkBytes(rows_per_unit);
   if (ws_query) {
     *ws_query = ws_bytes;
@@ -715,7 +762,6 @@ static int launch_fmha_pair(const vist3a_fmha_args& a, cudaStream_t stream, long
   if (plan.n_chunks && (a.workspace == nullptr || a.workspace_bytes < ws_bytes || ((uintptr_t)a.workspace & 127) != 0))
     plan = PairSplitPlan{(int)units, 0, 1, 0, 0};   // no (usable) workspace: every unit over all keys
   CUtensorMap tmQ, tmK, tmV, tmO, tmW;
-  int rc;
   if ((rc = make_map4(&tmQ, a.Q, a.batch, a.heads, a.len_q, 128, a.q_bs, a.q_rs, a.q_hs, Cfg::BQ))) return rc;
   if ((rc = make_map4(&tmK, a.K, a.batch, a.heads, a.len_kv, 128, a.k_bs, a.k_rs, a.k_hs, Cfg::BKV / 2))) return rc;
   if ((rc = make_map4(&tmV, a.V, a.batch, a.heads, a.len_kv, 128, a.v_bs, a.v_rs, a.v_hs, Cfg::BKV))) return rc;
@@ -732,6 +778,7 @@ static int launch_fmha_pair(const vist3a_fmha_args& a, cudaStream_t stream, long
   p.n_full = plan.n_full;
   p.split_a = plan.split_a;
   p.split_k = plan.split_k;
+  p.n_items = plan.n_full + plan.n_chunks;
   p.ws_ml = nullptr;
   if (plan.n_chunks) {
     const long long wrows = (long long)plan.n_chunks * rows_per_unit;
@@ -740,7 +787,8 @@ static int launch_fmha_pair(const vist3a_fmha_args& a, cudaStream_t stream, long
   } else {
     tmW = tmO;
   }
-  dim3 grid((unsigned)(2 * (plan.n_full + plan.n_chunks)));
+  // persistent clusters, one per SM pair, each working through every slots-th item (flags bit 20: one cluster per item, scheduled by the hardware)
+  dim3 grid((unsigned)(2 * ((a.flags & (1u << 20)) ? p.n_items : std::min(slots, p.n_items))));
   V3A_CUDA_OK(launch_kernel(kern, grid, dim3(Cfg::THREADS), Cfg::SMEM_BYTES, stream, /*pdl=*/true, 2, tmQ, tmK, tmV, tmO, tmW, p));
   launch_counter().fetch_add(1);
   if (plan.n_chunks) {
