@@ -81,11 +81,15 @@ struct FmhaPairCfg {
   static constexpr int V_HALF_BYTES = BKV * 128;       // 128 keys x this CTA's 64 head-dim columns = 16 KB
   static constexpr int ST = 4;                         // ring stages of K and of V
   static constexpr int NH = SPLIT == 1 ? 2 : 1;        // P(j) is handed to the MMA warp in NH key halves (one thread per row: after 64 keys each)
-  static constexpr int NBARS = 1 + 4 * ST + 8 * QT + 2 * QT + 1;   // q_full | k_full, k_empty, v_full, v_empty | per tile: s_full[2], p_full[2][2], pv_done[2] | pvh_done[2] | q_free
+  // OSTAGE: the output leaves through its own 32 KB staging buffer (shared by the CTA's two tiles, which finish half a step apart) instead of
+  // the Q buffers, so that the next item's Q is loaded and its first Q K^T issued while the epilogue of the current item runs
+  static constexpr bool OSTAGE = QT_ == 2 && SPLIT_ == 1;
+  static constexpr int NBARS = 1 + 4 * ST + 8 * QT + 2 * QT + 1 + 2;   // q_full | k_full, k_empty, v_full, v_empty | per tile: s_full[2], p_full[2][2], pv_done[2] | pvh_done[2] | q_free | ostage_done[2]
   static constexpr bool FAST = FAST_ != 0;             // speculative (stale-maximum) softmax in 64-column half-steps (fmha_math.cuh), one thread per row
   static_assert(!FAST || (SPLIT_ == 1 && QT_ == 2), "the speculative softmax runs one thread per row on two tiles per CTA");
-  static constexpr int XCH_BYTES = 2 * QT * SPLIT * 128 * 4;  // [step parity][tile][slice][row] fp32
-  static constexpr int SMEM_BYTES = QT * Q_TILE_BYTES + ST * (K_HALF_BYTES + V_HALF_BYTES) + 1024 + 8 * NBARS + 16 + XCH_BYTES;
+  static constexpr int XCH_BYTES = SPLIT == 1 ? 0 : 2 * QT * SPLIT * 128 * 4;  // [step parity][tile][slice][row] fp32 (slices of a row exchange max / sum)
+  static constexpr int OSTAGE_BYTES = OSTAGE ? Q_TILE_BYTES : 0;
+  static constexpr int SMEM_BYTES = QT * Q_TILE_BYTES + ST * (K_HALF_BYTES + V_HALF_BYTES) + OSTAGE_BYTES + 1024 + 8 * NBARS + 16 + XCH_BYTES;
   static constexpr uint32_t TILE_COLS = 256, TM_S = 0, S_STRIDE = 128, TM_O = NSB * 128;
   static_assert(SPLIT == 1 || SPLIT == 2 || SPLIT == 4, "SPLIT");
   static_assert(QT == 1 || (QT == 2 && SPLIT <= 2), "two tiles per CTA run one or two threads per row (384 / 640 threads)");
@@ -103,7 +107,8 @@ fmha_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   auto smem_q = [&](int i) { return smem_base + Cfg::Q_TILE_BYTES * i; };
   auto smem_k = [&](int s) { return smem_base + QT * Cfg::Q_TILE_BYTES + Cfg::K_HALF_BYTES * s; };
   auto smem_v = [&](int s) { return smem_base + QT * Cfg::Q_TILE_BYTES + Cfg::K_HALF_BYTES * ST + Cfg::V_HALF_BYTES * s; };
-  const uint32_t bar_base = smem_base + QT * Cfg::Q_TILE_BYTES + ST * (Cfg::K_HALF_BYTES + Cfg::V_HALF_BYTES);
+  const uint32_t smem_ostage = smem_base + QT * Cfg::Q_TILE_BYTES + ST * (Cfg::K_HALF_BYTES + Cfg::V_HALF_BYTES);
+  const uint32_t bar_base = smem_ostage + Cfg::OSTAGE_BYTES;
   const uint32_t q_full = bar_base;
   auto k_full = [&](int s) { return bar_base + 8u * (1 + s); };
   auto k_empty = [&](int s) { return bar_base + 8u * (1 + ST + s); };
@@ -115,6 +120,7 @@ fmha_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   auto pv_done = [&](int i, int b) { return bar_base + 8u * (1 + 4 * ST + 8 * i + 6 + b); };
   auto pvh_done = [&](int i, int b) { return bar_base + 8u * (1 + 4 * ST + 8 * QT + 2 * i + b); };   // first key half of P_i(j) V(j) has completed
   const uint32_t q_free = bar_base + 8u * (1 + 4 * ST + 10 * QT);   // this CTA's tiles have stored the item's output (the Q buffers double as staging)
+  auto ostage_done = [&](int i) { return bar_base + 8u * (2 + 4 * ST + 10 * QT + i); };   // tile i's output has been read out of the staging buffer
   const uint32_t tmem_slot = bar_base + 8u * Cfg::NBARS;
   const uint32_t xch_base = tmem_slot + 16u;
 
@@ -179,6 +185,7 @@ fmha_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   if (warp == 1 && lane == 0) {
     mbar_init(q_full, 1);
     mbar_init(q_free, QT);
+    for (int i = 0; i < 2; ++i) mbar_init(ostage_done(i), 1);
     for (int s = 0; s < ST; ++s) {
       mbar_init(k_full(s), 1);
       mbar_init(k_empty(s), 1);
@@ -206,12 +213,21 @@ fmha_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 
   if (warp == 0) {
     // ------------------------------ TMA producer (warp-uniform control flow, one elected lane issues) ------------------------------
-    int s = 0, n_it = 0;
-    uint32_t ph = 0;
+    int s = 0, n_it = 0, s_last = 0;
+    uint32_t ph = 0, ph_last = 0;   // (s_last, ph_last): ring slot and phase of the previous item's last key tile
     for (int item = item0; item < p.n_items; item += item_step, ++n_it) {
       const Item w = get_item(item);
       if (lane == 0) PAIR_STAMP(0);
-      if (n_it > 0) mbar_wait(q_free, (uint32_t)(n_it - 1) & 1u);   // the previous item's output has been read out of the Q buffers
+      if (n_it > 0) {
+        if constexpr (Cfg::OSTAGE) {
+          // the Q buffers are free once the previous item's last Q K^T has completed: the event that releases the ring slot of its key tile.
+          // (Not s_full: this warp runs up to ST steps = two phases of that barrier ahead of the MMAs, which a parity wait cannot tell apart.)
+          mbar_wait(k_empty(s_last), ph_last);
+        } else {
+          mbar_wait(q_free, (uint32_t)(n_it - 1) & 1u);   // the previous item's output has been read out of the Q buffers
+        }
+      }
+
       if (elect_one()) {
         if (leader) mbar_expect_tx(q_full, 2u * QT * Cfg::Q_TILE_BYTES);
 #pragma unroll
@@ -237,6 +253,8 @@ fmha_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           tma_load_4d_2sm(smem_v(s), &tmV, v_full(s), (int)rank * 64, w.head, (w.kv0 + j) * BKV, w.batch);
         }
         __syncwarp();
+        s_last = s;
+        ph_last = ph;
         if (++s == ST) { s = 0; ph ^= 1u; }
       }
     }
@@ -296,11 +314,14 @@ fmha_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       int g0 = 0, n_it = 0;
       for (int item = item0; item < p.n_items; item += item_step, ++n_it) {
         const Item w = get_item(item);
-        // Q of this item is in shared memory: both CTAs have read the previous item's O out of tensor memory and stored it
-        mbar_wait(q_full, (uint32_t)n_it & 1u);
-        for (int j = 0; j < NSB && j < w.n_kv; ++j) {
+        const bool has_next = item + item_step < p.n_items;
+        if (!Cfg::OSTAGE || n_it == 0) {
+          // Q of this item is in shared memory (without the staging buffer: both CTAs have stored the previous item's output from there)
+          mbar_wait(q_full, (uint32_t)n_it & 1u);
+          for (int j = 0; j < NSB && j < w.n_kv; ++j) {
 #pragma unroll
-          for (int i = 0; i < QT; ++i) issue_qk(i, g0 + j);
+            for (int i = 0; i < QT; ++i) issue_qk(i, g0 + j);
+          }
         }
         for (int j = 0; j < w.n_kv; ++j) {
           const int g = g0 + j;
@@ -313,7 +334,14 @@ fmha_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
               if (lane == 0 && hh == 0) PAIR_TRACE(j, i, 0);
               issue_pv(i, j, g, hh);
             }
-            if (j + NSB < w.n_kv) issue_qk(i, g + NSB);   // overwrites S_i(j) | P_i(j): ordered behind P_i(j) V(j) by the in-order tensor pipe
+            if (j + NSB < w.n_kv) {
+              issue_qk(i, g + NSB);   // overwrites S_i(j) | P_i(j): ordered behind P_i(j) V(j) by the in-order tensor pipe
+            } else if (Cfg::OSTAGE && has_next) {
+              // first Q K^T of the NEXT item, behind this item's last P V.  Its P V (which starts O afresh) waits for P like any other, and the
+              // softmax warps hand that P over only after they have read this item's O out of tensor memory
+              if (i == 0) mbar_wait(q_full, (uint32_t)(n_it + 1) & 1u);
+              issue_qk(i, g + 1);
+            }
             if (lane == 0) PAIR_TRACE(j, i, 1);
           }
         }
@@ -563,13 +591,20 @@ fmha_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     tc_fence_after();
     if (i == 0 && h == 0 && rit == 0) PAIR_STAMP(4);
     const float inv_l = 1.0f / l_run;
+    const uint32_t stage = Cfg::OSTAGE ? smem_ostage : smem_q(i);
+    if constexpr (Cfg::OSTAGE) {
+      // the two tiles take turns on the staging buffer: tile 1 after tile 0 of the same item, tile 0 after tile 1 of the previous item
+      const int n_done = (item - item0) / item_step;
+      if (i == 1) mbar_wait(ostage_done(0), (uint32_t)n_done & 1u);
+      else if (n_done > 0) mbar_wait(ostage_done(1), (uint32_t)(n_done - 1) & 1u);
+    }
 #pragma unroll
     for (int cb = 0; cb < OC / 32; ++cb) {
       uint32_t o[32];
       tmem_ld_x32(o_addr + (uint32_t)(cb * 32), o);
       tmem_ld_wait();
       const int col0 = h * OC + cb * 32;   // first of 32 consecutive output columns
-      const uint32_t srow = smem_q(i) + (uint32_t)((col0 >> 6) * Cfg::Q_SLAB_BYTES + rit * 128);
+      const uint32_t srow = stage + (uint32_t)((col0 >> 6) * Cfg::Q_SLAB_BYTES + rit * 128);
 #pragma unroll
       for (int k = 0; k < 32; k += 8) {
         const uint32_t chunk = (uint32_t)(((col0 & 63) + k) >> 3);
@@ -596,15 +631,16 @@ fmha_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       if (part >= 0) {
 #pragma unroll
         for (int sl = 0; sl < 2; ++sl)
-          tma_store_4d(&tmW, smem_q(i) + sl * Cfg::Q_SLAB_BYTES, sl * 64, 0, part * (2 * QT * Cfg::BQ) + (2 * i + (int)rank) * Cfg::BQ, 0);
+          tma_store_4d(&tmW, stage + sl * Cfg::Q_SLAB_BYTES, sl * 64, 0, part * (2 * QT * Cfg::BQ) + (2 * i + (int)rank) * Cfg::BQ, 0);
       } else {
 #pragma unroll
-        for (int sl = 0; sl < 2; ++sl) tma_store_4d(&tmO, smem_q(i) + sl * Cfg::Q_SLAB_BYTES, sl * 64, head, q0, batch);   // rows >= len_q are clipped
+        for (int sl = 0; sl < 2; ++sl) tma_store_4d(&tmO, stage + sl * Cfg::Q_SLAB_BYTES, sl * 64, head, q0, batch);   // rows >= len_q are clipped
       }
       tma_store_commit();
       tma_store_wait_read<0>();   // the buffer must stay intact until the TMA unit has read it
       if (i == 0) PAIR_STAMP(5);
-      mbar_arrive(q_free);        // the producer may load the next item's Q over it
+      if constexpr (Cfg::OSTAGE) mbar_arrive(ostage_done(i));   // the other tile may stage its output
+      else mbar_arrive(q_free);                                 // the producer may load the next item's Q over it
     }
     }   // items
   }
