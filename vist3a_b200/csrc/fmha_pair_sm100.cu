@@ -618,7 +618,12 @@ fmha_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       }
     }
     fence_proxy_async_smem();
-    asm volatile("bar.sync %0, %1;" ::"r"(9u + (uint32_t)i), "n"(128 * SPLIT) : "memory");   // all softmax threads of this tile
+    if constexpr (Cfg::OSTAGE) {
+      // warp 3 stores the staged tile (below): the softmax threads only signal it and turn to the next item
+      asm volatile("bar.arrive %0, %1;" ::"r"(9u + (uint32_t)i), "n"(128 * SPLIT + 32) : "memory");
+    } else {
+      asm volatile("bar.sync %0, %1;" ::"r"(9u + (uint32_t)i), "n"(128 * SPLIT) : "memory");   // all softmax threads of this tile
+    }
     int item_e = item;
     asm volatile("" : "+r"(item_e));   // (decoded again rather than kept in registers across the key loop)
     const Item w = get_item(item_e);
@@ -627,7 +632,7 @@ fmha_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       const int wrow = part * (2 * QT * Cfg::BQ) + (2 * i + (int)rank) * Cfg::BQ + rit;
       *reinterpret_cast<float2*>(p.ws_ml + 2ll * wrow) = make_float2(m_run * c, l_run);
     }
-    if (h == 0 && rit == 0) {
+    if (!Cfg::OSTAGE && h == 0 && rit == 0) {
       if (part >= 0) {
 #pragma unroll
         for (int sl = 0; sl < 2; ++sl)
@@ -639,10 +644,34 @@ fmha_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       tma_store_commit();
       tma_store_wait_read<0>();   // the buffer must stay intact until the TMA unit has read it
       if (i == 0) PAIR_STAMP(5);
-      if constexpr (Cfg::OSTAGE) mbar_arrive(ostage_done(i));   // the other tile may stage its output
-      else mbar_arrive(q_free);                                 // the producer may load the next item's Q over it
+      mbar_arrive(q_free);        // the producer may load the next item's Q over it
     }
     }   // items
+  } else if (warp == 3 && Cfg::OSTAGE) {
+    // ------------------------------ output store (both CTAs): staging buffer -> global memory, tile 0 and tile 1 of every item in turn ------
+    for (int item = item0; item < p.n_items; item += item_step) {
+      const Item w = get_item(item);
+#pragma unroll 1
+      for (int i = 0; i < QT; ++i) {
+        asm volatile("bar.sync %0, %1;" ::"r"(9u + (uint32_t)i), "n"(128 * SPLIT + 32) : "memory");   // tile i's softmax threads have staged their rows
+        if (lane == 0) {
+          if (w.part >= 0) {
+#pragma unroll
+            for (int sl = 0; sl < 2; ++sl)
+              tma_store_4d(&tmW, smem_ostage + sl * Cfg::Q_SLAB_BYTES, sl * 64, 0, w.part * (2 * QT * Cfg::BQ) + (2 * i + (int)rank) * Cfg::BQ, 0);
+          } else {
+#pragma unroll
+            for (int sl = 0; sl < 2; ++sl)
+              tma_store_4d(&tmO, smem_ostage + sl * Cfg::Q_SLAB_BYTES, sl * 64, w.head, q0_of(w, i), w.batch);   // rows >= len_q are clipped
+          }
+          tma_store_commit();
+          tma_store_wait_read<0>();   // the buffer must stay intact until the TMA unit has read it
+          if (i == 0) PAIR_STAMP(5);
+          mbar_arrive(ostage_done(i));   // the other tile may stage its output
+        }
+        __syncwarp();
+      }
+    }
   }
 
   tc_fence_before();
