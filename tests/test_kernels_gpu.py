@@ -249,6 +249,33 @@ def test_fmha_key_split_last_wave(ops, shape, flags):
     assert _rel_l2(out.float(), whole.float()) < 4e-3
 
 
+@pytest.mark.parametrize("shape", [(2, 3, 1029, 1029, 64), (1, 2, 261, 700, 128), (1, 2, 264, 300, 64), (3, 5, 513, 1029, 64), (1, 16, 4101, 4200, 64)])
+def test_fmha_tail_rows(ops, shape):
+    """len_q a few rows more than a multiple of the CTA's 256 query rows (the decoder's frames: 1029 tokens).  Opt-in variant (flags bit 21,
+    measured no faster than the default, see fmha_sm100.cu): the tensor-core CTAs cover the multiple, extra CTAs of the same launch compute the
+    last 1..8 rows on the CUDA cores.  With per-row logit scales; against fp32 SDPA, the tail rows on their own, and against the default."""
+    B, H, Lq, Lk, D = shape
+    g = torch.Generator(device="cuda").manual_seed(Lq + Lk + D)
+    q = torch.randn(B, Lq, H, D, device="cuda", generator=g).bfloat16()
+    k = torch.randn(B, Lk, H, D, device="cuda", generator=g).bfloat16()
+    v = torch.randn(B, Lk, H, D, device="cuda", generator=g).bfloat16()
+    q[:, -3:] *= 3
+    rs = (torch.rand(B * Lq, device="cuda", generator=g) + 0.5).float()
+    ref = torch.nn.functional.scaled_dot_product_attention((q.float() * rs.view(B, Lq, 1, 1)).transpose(1, 2), k.float().transpose(1, 2),
+                                                           v.float().transpose(1, 2)).transpose(1, 2)
+    out = torch.full((B, Lq + 2, H, D), 7.0, device="cuda", dtype=torch.bfloat16)   # two guard rows behind the output
+    ops.fmha(q, k, v, out=out[:, :Lq], flags=1 << 21, q_row_scale=rs)
+    default = ops.fmha(q, k, v, q_row_scale=rs)
+    assert (out[:, Lq:] == 7.0).all(), "rows behind len_q were written"
+    o = out[:, :Lq].float()
+    t = Lq % 256
+    assert _rel_l2(o, ref) < 6e-3
+    if D == 64:
+        assert _rel_l2(o[:, -t:], ref[:, -t:]) < 4e-3          # the CUDA-core rows (fp32 P: only the bf16 rounding of the output)
+    assert _rel_l2(o[:, :-t], default.float()[:, :-t]) == 0.0  # the tensor-core rows do not change
+    assert _rel_l2(o[:, -t:], default.float()[:, -t:]) < 6e-3
+
+
 def test_fmha_large_scores(ops):
     # rows whose max moves by > 2^8 between kv tiles exercise the lazy-rescale path
     g = torch.Generator(device="cuda").manual_seed(5)

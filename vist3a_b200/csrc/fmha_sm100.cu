@@ -38,6 +38,12 @@ struct FmhaParams {
   long long* trace;        // debug: 32 clock64 stamps / phase sums per CTA (v3a_debug_fmha_trace), normally null
   uint32_t zero;           // 0 (a value ptxas cannot fold: scheduling aid of the speculative softmax)
   int skip_softmax;        // debug (flags bit 12): the softmax warps only hand the barriers on (garbage output): tensor-side ceiling
+  // Tail rows.  When len_q is a few rows more than a multiple of the CTA's 256 query rows (the decoder's frames: 1029 = 4 * 256 + 5 tokens),
+  // a whole CTA would run every key step for them.  The tensor-core CTAs then cover len_q - tail_rows rows (len_q above is that number)
+  // and the grid gets extra z-slices whose CTAs compute the tail rows of one (batch, head) each on the CUDA cores (fmha_tail_rows).
+  int tail_rows, batch, heads;
+  const __nv_bfloat16 *Qg, *Kg, *Vg;
+  long long q_bs, q_rs, q_hs, k_bs, k_rs, k_hs, v_bs, v_rs, v_hs;
 };
 
 // debug hook (tools/fmha_trace.py), off unless armed: process-wide by design, read once per launch
@@ -51,6 +57,201 @@ extern "C" void v3a_debug_fmha_trace(void* buf) { g_fmha_trace.store(reinterpret
   do {                                                                                                                \
     if (p.trace) p.trace[((long long)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 32 + (slot)] = clock64(); \
   } while (0)
+
+// The last tail_rows (<= 8) query rows of one (batch, head), head_dim 64, on the CUDA cores in fp32.  The CTA has one thread block's worth of
+// latency hiding (the kernel's shared-memory request allows one CTA per SM), so nothing here may wait on global memory more than twice: the
+// whole K of the head, then the whole V, come in by TMA through the kernel's own tensor maps (128-key boxes, 128-byte swizzle: a thread that
+// walks "its" key row reads conflict-free), everything else runs from shared memory.
+//   smem (1024-aligned): K | V [nbox][128 keys][128 B]  (later: per-warp partial outputs)  |  scores / P [tail_rows][Lp] fp32  |  q [8][64] fp32
+//                        |  per-warp row max [8][32], row sum [8][32]  |  mbarrier
+constexpr int kTailMax = 8;
+static size_t fmha_tail_smem_bytes(int tail_rows, long long len_kv) {
+  const long long nbox = (len_kv + 127) / 128, Lp = (len_kv + 3) & ~3ll;
+  return (size_t)(1024 + nbox * 16384 + (tail_rows * Lp + kTailMax * 64 + 2 * kTailMax * 32) * 4 + 16);
+}
+// (T = tail_rows as a template parameter: every row loop unrolls without branches, so that the loads of a group are issued ahead of its FMAs --
+//  with one CTA of 12-20 warps per SM nothing else hides their latency)
+template <int THREADS, int T>
+__device__ __noinline__ void fmha_tail_rows(const FmhaParams& p, const CUtensorMap* tmK, const CUtensorMap* tmV, uint8_t* smem_raw, int bh) {
+  constexpr int D = 64, NW = THREADS / 32;
+  const int b = bh / p.heads, h = bh - b * p.heads;
+  const int L = p.len_kv, tid = (int)threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nbox = (L + 127) >> 7, Lp = (L + 3) & ~3;
+  const int row0 = p.len_q;   // first tail row
+  const uint32_t kv = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* kvg = smem_raw + (kv - smem_u32(smem_raw));
+  float* sc = reinterpret_cast<float*>(kvg + (size_t)nbox * 16384);   // [T][Lp]
+  float* qs = sc + (size_t)T * Lp;                                      // [kTailMax][D], pre-multiplied by scale * log2(e) [* row scale]
+  float* wmax = qs + kTailMax * D;                                      // [kTailMax][32]
+  float* wsum = wmax + kTailMax * 32;                                   // [kTailMax][32]
+  const uint32_t bar = kv + (uint32_t)nbox * 16384u + (uint32_t)((T * Lp + kTailMax * D + 2 * kTailMax * 32) * 4);
+  if (tid == 0) {
+    FMHA_TRACE(0);
+    mbar_init(bar, 1);
+    fence_barrier_init();
+    mbar_expect_tx(bar, (uint32_t)nbox * 16384u);
+    for (int x = 0; x < nbox; ++x) tma_load_4d(kv + (uint32_t)x * 16384u, tmK, bar, 0, h, x * 128, b);   // keys >= len_kv: zero-filled
+  }
+  for (int e = tid; e < kTailMax * D; e += THREADS) {
+    const int r = e / D, d = e - r * D;
+    float v = 0.0f;
+    if (r < T) {
+      const float c = p.row_scale ? p.scale_log2 * p.row_scale[(long long)b * (p.len_q + T) + row0 + r] : p.scale_log2;
+      v = c * __bfloat162float(p.Qg[(long long)b * p.q_bs + (long long)(row0 + r) * p.q_rs + (long long)h * p.q_hs + d]);
+    }
+    qs[e] = v;
+  }
+  __syncthreads();   // q staged, barrier initialised
+  mbar_wait(bar, 0);
+  if (tid == 0) FMHA_TRACE(1);
+  // ---- scores (log2 domain): a thread owns up to KPT keys at a time, so that every q chunk read from shared memory serves all of them ----
+  constexpr int KPT = 3;
+  for (int kb = 0; kb < L; kb += KPT * THREADS) {
+    float acc[KPT][T];
+    int key[KPT];
+#pragma unroll
+    for (int u = 0; u < KPT; ++u) {
+      key[u] = kb + u * THREADS + tid;
+#pragma unroll
+      for (int r = 0; r < T; ++r) acc[u][r] = 0.0f;
+    }
+#pragma unroll
+    for (int ch = 0; ch < D / 8; ++ch) {
+      float kf[KPT][8];
+#pragma unroll
+      for (int u = 0; u < KPT; ++u) {
+        const int k = min(key[u], nbox * 128 - 1);
+        const uint4 w = *reinterpret_cast<const uint4*>(kvg + (size_t)k * 128 + ((ch ^ (k & 7)) << 4));
+        const uint32_t kw[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          kf[u][2 * q] = __uint_as_float(kw[q] << 16);
+          kf[u][2 * q + 1] = __uint_as_float(kw[q] & 0xffff0000u);
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < T; ++r) {
+        const float4 qa = *reinterpret_cast<const float4*>(qs + r * D + ch * 8), qb = *reinterpret_cast<const float4*>(qs + r * D + ch * 8 + 4);
+#pragma unroll
+        for (int u = 0; u < KPT; ++u) {
+          acc[u][r] = fmaf(kf[u][0], qa.x, fmaf(kf[u][1], qa.y, fmaf(kf[u][2], qa.z, fmaf(kf[u][3], qa.w, acc[u][r]))));
+          acc[u][r] = fmaf(kf[u][4], qb.x, fmaf(kf[u][5], qb.y, fmaf(kf[u][6], qb.z, fmaf(kf[u][7], qb.w, acc[u][r]))));
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < KPT; ++u) {
+      if (key[u] < L) {
+#pragma unroll
+        for (int r = 0; r < T; ++r) sc[r * Lp + key[u]] = acc[u][r];
+      }
+    }
+  }
+  __syncthreads();   // scores complete; every read of K is done
+  fence_proxy_async_smem();
+  if (tid == 0) {
+    FMHA_TRACE(2);
+    mbar_expect_tx(bar, (uint32_t)nbox * 16384u);
+    for (int x = 0; x < nbox; ++x) tma_load_4d(kv + (uint32_t)x * 16384u, tmV, bar, 0, h, x * 128, b);   // V over K, under the softmax
+  }
+  // ---- softmax: every warp takes a share of every row; per-warp maxima / sums are combined through shared memory ----
+  {
+    float mx[T];
+#pragma unroll
+    for (int r = 0; r < T; ++r) mx[r] = -INFINITY;
+    for (int k = tid; k < L; k += THREADS) {
+#pragma unroll
+      for (int r = 0; r < T; ++r) mx[r] = fmaxf(mx[r], sc[r * Lp + k]);
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+#pragma unroll
+      for (int r = 0; r < T; ++r) mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], o));
+    }
+    if (lane == 0) {
+#pragma unroll
+      for (int r = 0; r < T; ++r) wmax[r * 32 + warp] = mx[r];
+    }
+    __syncthreads();
+    float sum[T];
+#pragma unroll
+    for (int r = 0; r < T; ++r) {
+      mx[r] = wmax[r * 32 + (lane < NW ? lane : 0)];
+      sum[r] = 0.0f;
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+#pragma unroll
+      for (int r = 0; r < T; ++r) mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], o));
+    }
+    for (int k = tid; k < L; k += THREADS) {
+#pragma unroll
+      for (int r = 0; r < T; ++r) {
+        const float e = ex2_approx(sc[r * Lp + k] - mx[r]);
+        sc[r * Lp + k] = e;
+        sum[r] += e;
+      }
+    }
+    if (tid < Lp - L) {   // padding of the rows (read by the 4-key groups below)
+#pragma unroll
+      for (int r = 0; r < T; ++r) sc[r * Lp + L + tid] = 0.0f;
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+#pragma unroll
+      for (int r = 0; r < T; ++r) sum[r] += __shfl_xor_sync(0xffffffffu, sum[r], o);
+    }
+    if (lane == 0) {
+#pragma unroll
+      for (int r = 0; r < T; ++r) wsum[r * 32 + warp] = sum[r];
+    }
+  }
+  __syncthreads();   // P and the row sums are complete
+  if (tid == 0) FMHA_TRACE(3);
+  mbar_wait(bar, 1);
+  if (tid == 0) FMHA_TRACE(4);
+  // ---- P V: warp w owns every NW-th group of four keys, a thread two head-dim columns ----
+  float a0[T], a1[T];
+#pragma unroll
+  for (int r = 0; r < T; ++r) a0[r] = a1[r] = 0.0f;
+  for (int kg = warp; kg * 4 < L; kg += NW) {
+    float v0[4], v1[4];
+    float4 pr[T];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int k = kg * 4 + u;   // (< nbox * 128; keys >= len_kv hold zeros and meet P = 0)
+      const uint32_t vv = *reinterpret_cast<const uint32_t*>(kvg + (size_t)k * 128 + (((lane >> 2) ^ (k & 7)) << 4) + ((lane & 3) << 2));
+      v0[u] = __uint_as_float(vv << 16);
+      v1[u] = __uint_as_float(vv & 0xffff0000u);
+    }
+#pragma unroll
+    for (int r = 0; r < T; ++r) pr[r] = *reinterpret_cast<const float4*>(sc + r * Lp + kg * 4);
+#pragma unroll
+    for (int r = 0; r < T; ++r) {
+      a0[r] = fmaf(pr[r].x, v0[0], fmaf(pr[r].y, v0[1], fmaf(pr[r].z, v0[2], fmaf(pr[r].w, v0[3], a0[r]))));
+      a1[r] = fmaf(pr[r].x, v1[0], fmaf(pr[r].y, v1[1], fmaf(pr[r].z, v1[2], fmaf(pr[r].w, v1[3], a1[r]))));
+    }
+  }
+  __syncthreads();   // V is no longer read: its place takes the per-warp partial outputs [NW][kTailMax][D]
+  if (tid == 0) FMHA_TRACE(5);
+  float* part = reinterpret_cast<float*>(kvg);
+#pragma unroll
+  for (int r = 0; r < T; ++r) {
+    part[((size_t)warp * kTailMax + r) * D + 2 * lane] = a0[r];
+    part[((size_t)warp * kTailMax + r) * D + 2 * lane + 1] = a1[r];
+  }
+  __syncthreads();
+  for (int e = tid; e < T * D; e += THREADS) {
+    const int r = e / D, d = e - r * D;
+    float acc = 0.0f, sum = 0.0f;
+    for (int w = 0; w < NW; ++w) {
+      acc += part[((size_t)w * kTailMax + r) * D + d];
+      sum += wsum[r * 32 + w];
+    }
+    static_cast<__nv_bfloat16*>(p.O)[(long long)b * p.o_bs + (long long)(row0 + r) * p.o_rs + (long long)h * p.o_hs + d] = __float2bfloat16(acc / sum);
+  }
+  if (tid == 0) FMHA_TRACE(6);
+}
 
 // QT_ = 1 (round 2): ONE 128-row query tile per CTA with two softmax threads per row.  Tensor memory then has room for double-buffered
 // 128-key score tiles at d=128 (S0|P0 [0,128)  S1|P1 [128,256)  O [256,384)), so Q K^T of step j+1 runs under the softmax of step j without
@@ -137,6 +338,27 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const uint32_t tmem_slot = bar_base + 8u * Cfg::NBARS;
   const uint32_t xch_base = tmem_slot + 16u;  // float [2 parities][2 tiles][2 halves][128 rows]
 
+  if ((int)blockIdx.z >= p.batch) {
+    // (extra z-slices of the grid: the tail rows of one (batch, head) per CTA; they are scheduled last and fill the grid's last, partial wave)
+    const int bh = (int)(((blockIdx.z - p.batch) * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x);
+    pdl_launch_dependents();
+    pdl_wait();
+    if constexpr (D == 64) {
+      if (bh < p.batch * p.heads) {
+        switch (p.tail_rows) {
+          case 1: fmha_tail_rows<Cfg::THREADS, 1>(p, &tmK, &tmV, smem_raw, bh); break;
+          case 2: fmha_tail_rows<Cfg::THREADS, 2>(p, &tmK, &tmV, smem_raw, bh); break;
+          case 3: fmha_tail_rows<Cfg::THREADS, 3>(p, &tmK, &tmV, smem_raw, bh); break;
+          case 4: fmha_tail_rows<Cfg::THREADS, 4>(p, &tmK, &tmV, smem_raw, bh); break;
+          case 5: fmha_tail_rows<Cfg::THREADS, 5>(p, &tmK, &tmV, smem_raw, bh); break;
+          case 6: fmha_tail_rows<Cfg::THREADS, 6>(p, &tmK, &tmV, smem_raw, bh); break;
+          case 7: fmha_tail_rows<Cfg::THREADS, 7>(p, &tmK, &tmV, smem_raw, bh); break;
+          default: fmha_tail_rows<Cfg::THREADS, 8>(p, &tmK, &tmV, smem_raw, bh); break;
+        }
+      }
+    }
+    return;
+  }
   const uint32_t warp = warp_id_sync();
   const uint32_t lane = lane_id();
   const int q0 = blockIdx.x * (Cfg::BQ * Cfg::QT);
@@ -399,7 +621,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const uint32_t pair_bar = 1u + (uint32_t)i * 4u + wq;  // named barrier shared by the two warps that own these 32 rows
       float m_run = -INFINITY;  // running (possibly stale) row max of raw scores
       float l_run = 0.0f;       // running sum of exp2((s - m_run) * scale_log2) over this thread's columns
-      const float c = (p.row_scale && row < p.len_q) ? p.scale_log2 * p.row_scale[(long long)batch * p.len_q + row] : p.scale_log2;
+      const float c = (p.row_scale && row < p.len_q) ? p.scale_log2 * p.row_scale[(long long)batch * (p.len_q + p.tail_rows) + row] : p.scale_log2;
       const uint64_t cc2 = pack2(c, c);
       const bool tr = p.trace != nullptr && warp == 4;
       long long ph_wait = 0, ph_ld = 0, ph_max = 0, ph_exp = 0, ph_st = 0, tt = 0;
@@ -891,13 +1113,28 @@ static int launch_fmha(const vist3a_fmha_args& a, cudaStream_t stream) {
   using Cfg = FmhaCfg<D, BKV_, POLY_, SPLIT_, FAST_, QT_>;
   CUtensorMap tmQ, tmK, tmV, tmO;
   int rc;
-  if ((rc = make_qkv_map(&tmQ, a.Q, a.batch, a.heads, a.len_q, D, a.q_bs, a.q_rs, a.q_hs, Cfg::BQ))) return rc;
+  // a few rows more than a multiple of the CTA's query rows: those rows can go to CUDA-core tail CTAs (FmhaParams).  OPT-IN (flags bit 21):
+  // measured on B200 at the decoder's frame attention (13 x 16 heads, 1029 x 1029, d 64; tools/fmha_tail_trace.py): a tail CTA takes 21.2 k
+  // cycles (K by TMA 3.0 k, scores 5.5 k, softmax 3.4 k, P V 8.0 k: shared-memory wavefronts of the broadcast reads, 12 warps per SM) against
+  // 25.3 k of the one-tile tensor-core CTA it replaces -- 377 vs 377 TFLOP/s for the launch, so the default stays without it
+  const long long rows_per_cta = Cfg::BQ * Cfg::QT;
+  long long tail = a.len_q % rows_per_cta;
+  if (D != 64 || Cfg::BKV != 128 || tail > kTailMax || a.len_q < rows_per_cta || !(a.flags & (1u << 21)) || (a.flags & 4096u) ||
+      a.len_kv <= 256 || fmha_tail_smem_bytes((int)tail, a.len_kv) > (size_t)Cfg::SMEM_BYTES)
+    tail = 0;
+  const long long len_q_main = a.len_q - tail;
+  if ((rc = make_qkv_map(&tmQ, a.Q, a.batch, a.heads, len_q_main, D, a.q_bs, a.q_rs, a.q_hs, Cfg::BQ))) return rc;
   if ((rc = make_qkv_map(&tmK, a.K, a.batch, a.heads, a.len_kv, D, a.k_bs, a.k_rs, a.k_hs, Cfg::BKV))) return rc;
   if ((rc = make_qkv_map(&tmV, a.V, a.batch, a.heads, a.len_kv, D, a.v_bs, a.v_rs, a.v_hs, Cfg::BKV))) return rc;
-  if ((rc = make_qkv_map(&tmO, a.O, a.batch, a.heads, a.len_q, D, a.o_bs, a.o_rs, a.o_hs, Cfg::BQ))) return rc;
+  if ((rc = make_qkv_map(&tmO, a.O, a.batch, a.heads, len_q_main, D, a.o_bs, a.o_rs, a.o_hs, Cfg::BQ))) return rc;
   FmhaParams p;
   p.O = a.O; p.o_bs = a.o_bs; p.o_rs = a.o_rs; p.o_hs = a.o_hs;
-  p.len_q = (int)a.len_q; p.len_kv = (int)a.len_kv;
+  p.len_q = (int)len_q_main; p.len_kv = (int)a.len_kv;
+  p.tail_rows = (int)tail; p.batch = (int)a.batch; p.heads = (int)a.heads;
+  p.Qg = static_cast<const __nv_bfloat16*>(a.Q); p.Kg = static_cast<const __nv_bfloat16*>(a.K); p.Vg = static_cast<const __nv_bfloat16*>(a.V);
+  p.q_bs = a.q_bs; p.q_rs = a.q_rs; p.q_hs = a.q_hs;
+  p.k_bs = a.k_bs; p.k_rs = a.k_rs; p.k_hs = a.k_hs;
+  p.v_bs = a.v_bs; p.v_rs = a.v_rs; p.v_hs = a.v_hs;
   p.scale_log2 = a.scale * 1.4426950408889634f;
   p.row_scale = a.q_row_scale;
   p.trace = g_fmha_trace.load(std::memory_order_relaxed);
@@ -908,8 +1145,9 @@ static int launch_fmha(const vist3a_fmha_args& a, cudaStream_t stream) {
   auto kern = fmha_fwd_kernel<D, BKV_, POLY_, SPLIT_, FAST_, QT_>;
   static std::atomic<unsigned long long> attr_done{0};  // per template instantiation, one bit per device
   V3A_CUDA_OK(ensure_dynamic_smem(kern, Cfg::SMEM_BYTES, attr_done));
-  const long long rows_per_cta = Cfg::BQ * Cfg::QT;
-  dim3 grid((unsigned)((a.len_q + rows_per_cta - 1) / rows_per_cta), (unsigned)a.heads, (unsigned)a.batch);
+  dim3 grid((unsigned)((len_q_main + rows_per_cta - 1) / rows_per_cta), (unsigned)a.heads, (unsigned)a.batch);
+  if (tail) grid.z += (unsigned)((a.batch * a.heads + (long long)grid.x * grid.y - 1) / ((long long)grid.x * grid.y));
+  V3A_REQUIRE(grid.z <= 65535u, VIST3A_ERR_INVALID, "fmha: batch exceeds grid limits");
   V3A_CUDA_OK(launch_kernel(kern, grid, dim3(Cfg::THREADS), Cfg::SMEM_BYTES, stream, /*pdl=*/true, 1, tmQ, tmK, tmV, tmO, p));
   launch_counter().fetch_add(1);
   return VIST3A_OK;
@@ -946,8 +1184,8 @@ int fmha_entry(const vist3a_fmha_args* args, cudaStream_t stream, long long* ws_
   // and >= 1024 keys on CTA pairs (+5.5 % over the former default at 4096 keys, device time in a CUDA graph), below that on one CTA (+1.7 % at 512
   // keys; +5.5 % on the decoder's 1029-key frame attention, +2.7 % on its 13 377-key global attention).  flags bit 13
   // selects the former default (two threads per row, exact running maximum) for A/B.
-  // (flags bits 17-20 steer the work decomposition of the pair kernel and do not select a kernel)
-  if ((a.flags & ~(15u << 17)) == 0u) {
+  // (flags bits 17-20 steer the work decomposition of the pair kernel, bit 21 switches the tail-row CTAs on; they do not select a kernel)
+  if ((a.flags & ~(31u << 17)) == 0u) {
     if (ws_query && (a.head_dim == 64 || a.len_kv < 512)) return VIST3A_OK;
     // (head_dim 64, long key sequences -- the decoder's global attention: two threads per row, +2 % over one thread per row at 13 377 keys; -7 % at 1029)
     if (a.head_dim == 64) return a.len_kv >= 4096 ? launch_fmha<64, 128, 0, 2, 2>(a, stream) : launch_fmha<64, 128, 2, 1, 1>(a, stream);
