@@ -222,13 +222,14 @@ def test_fmha_outlier_keys_late_in_the_sequence(ops, flags, D):
     assert _rel_l2(out.float(), ref) < 6e-3, flags
 
 
-@pytest.mark.parametrize("shape", [(1, 2, 600, 2048), (1, 15, 1024, 4096), (2, 3, 700, 2000), (1, 12, 2048, 4096)])
-@pytest.mark.parametrize("flags", [0, 1 << 18, 2 << 18, 3 << 18, 256 | (3 << 9), 256 | (2 << 18)])
+@pytest.mark.parametrize("shape", [(1, 2, 600, 2048), (1, 15, 1024, 4096), (2, 3, 700, 2000), (1, 12, 2048, 4096), (2, 10, 4096, 1100), (1, 19, 2048, 1024)])
+@pytest.mark.parametrize("flags", [0, 256 | (3 << 9), 256 | (4 << 9), 256])
 def test_fmha_key_split_last_wave(ops, shape, flags):
-    """head_dim 128 on CTA pairs: the query blocks of the grid's last, partly filled wave are cut along the keys (chunk clusters write partial
-    results, a merge kernel follows).  Shapes that split into equal chunks, into a mix of k and k + 1 chunks, with a ragged last key tile, with
-    per-row logit scales and with the largest logits in the LAST chunk; flags force 1 / 2 / 3 short waves and the non-speculative kernels.
-    Compared with fp32 SDPA and with the unsplit kernel (flags bit 17)."""
+    """head_dim 128 on CTA pairs: the query blocks of the grid's last, partly filled wave are laid end to end and cut along the keys into one
+    equal range per cluster (partial results in a workspace, a merge kernel follows).  Shapes with fewer units than clusters (pieces of a few
+    key steps, many per unit), with whole waves in front of the tail, with a ragged last key tile, with per-row logit scales and with the
+    largest logits in the LAST piece; flags select the speculative / exact-maximum kernels.  Compared with fp32 SDPA and with the unsplit
+    kernel (flags bit 17)."""
     from vist3a_b200 import _lib
     B, H, Lq, Lk = shape
     g = torch.Generator(device="cuda").manual_seed(Lq + Lk + flags)

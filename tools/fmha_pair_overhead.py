@@ -26,7 +26,9 @@ ops.fmha(q, k, v, out=o, flags=flags)
 torch.cuda.synchronize()
 lib.v3a_debug_fmha_pair_trace(None)
 t = buf.cpu()[1024:].view(NCL, 8)
-cl = [r.tolist() for r in t if int(r[0])]
+cl = [r.tolist() + [int(r[7]) >> 16, idx // 74] for idx, r in enumerate(t) if int(r[0])]
+for r in cl:
+    r[7] &= 0xffff
 t0 = min(r[6] for r in cl)
 print(f"flags {flags:#x}: {len(cl)} items, kernel span (first entry -> last store) {(max(r[5] for r in cl) - t0) / 1000:.1f} us")
 names = ["item start->Q requested", "Q requested->first S", "first S->last P", "last P->PV done", "PV done->stored", "total"]
@@ -44,3 +46,10 @@ if gaps:
     print(f"  tensor pipe idle between items on the same SM (last P V done -> next item's first S): median {statistics.median(gaps) / 1000:.2f} us  min {min(gaps) / 1000:.2f}  max {max(gaps) / 1000:.2f}  ({len(by_sm)} leader SMs)")
 starts = sorted(r[0] - t0 for r in cl)
 print("  item start times (us), every", len(by_sm), "th:", [round(x / 1000, 1) for x in starts[::len(by_sm)]])
+# by position in the cluster's item list: duration of the key loop per key step
+for pos in sorted(set(r[9] for r in cl)):
+    rs = [r for r in cl if r[9] == pos]
+    per = [(r[3] - r[2]) / 1000 / max(r[8] - 0.5, 0.5) for r in rs]
+    print(f"  item #{pos}: {len(rs)} items, key steps {min(r[8] for r in rs)}..{max(r[8] for r in rs)}, first S -> last P per step: median {statistics.median(per):.2f} us"
+          f"  (min {min(per):.2f}, max {max(per):.2f});  Q requested -> output stored: median {statistics.median((r[5] - r[1]) / 1000 for r in rs):.1f} us;"
+          f"  output stored at median {statistics.median((r[5] - t0) / 1000 for r in rs):.1f} us, max {max((r[5] - t0) / 1000 for r in rs):.1f}")

@@ -1,5 +1,5 @@
-"""Key-split last wave of the CTA-pair attention kernel (fmha_pair_sm100.cu): correctness against fp32 SDPA and against the unsplit kernel,
-then device time (CUDA graph, variants interleaved) of: default plan | no split (flags bit 17) | forced 1 / 2 / 3 short waves (bits 18-19)."""
+"""Work decomposition of the CTA-pair attention kernel (fmha_pair_sm100.cu): correctness against fp32 SDPA with and without the key split of the
+tail, then device time (CUDA graph, variants interleaved) of: default | no key split (flags bit 17) | one cluster per unit, no split (bits 17 + 20)."""
 import json
 import os
 import sys
@@ -26,17 +26,17 @@ def main():
         ref = torch.nn.functional.scaled_dot_product_attention((q.float() * rs.view(B, Lq, 1, 1)).transpose(1, 2), k.transpose(1, 2).float(),
                                                                v.transpose(1, 2).float()).transpose(1, 2)
         rec = {"shape": [B, H, Lq, Lk]}
-        for name, fl in (("split", 0), ("nosplit", NOSPLIT), ("r1", 1 << 18), ("r2", 2 << 18), ("r3", 3 << 18)):
+        for name, fl in (("split", 0), ("nosplit", NOSPLIT)):
             o = ops.fmha(q, k, v, flags=fl, q_row_scale=rs)
             rec[name] = round(float((o.float() - ref).norm() / ref.norm()), 5)
         out["check"].append(rec)
         print(json.dumps(rec), flush=True)
     if "--no-time" in sys.argv:
         return
-    # persistent clusters + key split (0) | one cluster per item (bit 20) | no key split (bit 17) | neither: the round-2 kernel's decomposition
-    variants = (("persist+split", 0), ("split", 1 << 20), ("persist", NOSPLIT), ("neither", NOSPLIT | (1 << 20)), ("r1", 1 << 18), ("r3", 3 << 18))
-    for name, B, H, Lq, Lk in (("dit_self_1.3b", 2, 12, 4096, 4096), ("dit_cross", 2, 12, 4096, 512), ("dit_self_14b", 2, 40, 4096, 4096), ("b1", 1, 12, 4096, 4096),
-                               ("small", 1, 12, 1024, 4096)):
+    # persistent clusters + balanced key split of the tail (0) | no key split (bit 17) | neither (bit 20): the round-2 kernel's decomposition
+    variants = (("persist+split", 0), ("persist", NOSPLIT), ("neither", NOSPLIT | (1 << 20)))
+    for name, B, H, Lq, Lk in (("dit_self_1.3b", 2, 12, 4096, 4096), ("dit_cross", 2, 12, 4096, 512), ("dit_self_14b", 2, 40, 4096, 4096), ("dit_self_14b_21v", 2, 40, 6144, 6144),
+                               ("b1", 1, 12, 4096, 4096), ("small", 1, 12, 1024, 4096)):
         q = torch.randn(B, Lq, H, 128, device="cuda").bfloat16()
         k = torch.randn(B, Lk, H, 128, device="cuda").bfloat16()
         v = torch.randn(B, Lk, H, 128, device="cuda").bfloat16()

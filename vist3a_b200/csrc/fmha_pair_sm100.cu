@@ -36,14 +36,15 @@ struct FmhaPairParams {
   const float* row_scale;  // optional per-(batch, query row) positive factor on the logits
   long long* trace;        // debug (v3a_debug_fmha_pair_trace): clock64 stamps of CTA (0,0,0), normally null
   uint32_t zero;           // 0 (a value ptxas cannot fold: scheduling aid of the speculative softmax)
-  // Work decomposition (1-D grid, cluster c = blockIdx.x / 2).  A unit = (batch, head, block of 256 QT query rows), q-block fastest.  Clusters
-  // [0, n_full) process one unit each over all keys.  The units behind them -- the last, partly filled wave of the grid -- are cut along
-  // the KEYS: the first split_a of them into split_k chunks, the others into split_k + 1, one cluster per chunk; a chunk cluster writes its
-  // normalised partial O (bf16) and per row (reference maximum * c, row sum) to the workspace and fmha_pair_combine_kernel merges them.
+  // Work decomposition (1-D grid of G persistent clusters, cluster c = blockIdx.x / 2).  A unit = (batch, head, block of 256 QT query rows),
+  // q-block fastest.  Units [0, n_full) -- whole waves of the grid -- go round-robin: cluster c takes c, c + G, ... over all keys.  The
+  // tail_units behind them, which would leave most SMs idle for a whole pass over the keys, are laid end to end as tail_units * n_kv key
+  // steps and cut into G equal ranges: cluster c takes steps [c T / G, (c + 1) T / G), i.e. the end of one unit and / or the beginning of the
+  // next.  A partial piece writes its normalised O (bf16) and per row (reference maximum * c, row sum) to workspace slot 2 c (the cluster's
+  // first piece) or 2 c + 1 (its last) and fmha_pair_combine_kernel merges the pieces of every unit.
   int q_blocks, heads;
-  int n_full, split_a, split_k;
-  int n_items;             // n_full + number of chunks: cluster c works on items c, c + gridDim.x / 2, ... (persistent clusters, one per SM pair)
-  float* ws_ml;            // [chunk][256 QT rows][2] fp32 (behind the partial O tiles the workspace tensor map tmW addresses)
+  int n_full, tail_units;
+  float* ws_ml;            // [slot][256 QT rows][2] fp32 (behind the partial O tiles the workspace tensor map tmW addresses)
 };
 
 // debug hook (tools/fmha_pair_trace.py), off unless armed: [step][tile][8] stamps of the leader CTA of cluster 0:
@@ -53,15 +54,16 @@ static std::atomic<long long*> g_pair_trace{nullptr};
 extern "C" void v3a_debug_fmha_pair_trace(void* buf) { g_pair_trace.store(reinterpret_cast<long long*>(buf)); }
 #define PAIR_TRACE(j, i, slot)                                                                         \
   do {                                                                                                 \
-    if (p.trace && blockIdx.x == 0 && item == item0 && (j) < 64) p.trace[((j) * 2 + (i)) * 8 + (slot)] = clock64(); \
+    if (p.trace && blockIdx.x == 0 && item == 0 && (j) < 64) p.trace[((j) * 2 + (i)) * 8 + (slot)] = clock64(); \
   } while (0)
 
-// second part of the debug buffer, [item][8] at offset 1024: %globaltimer (ns) in the leader CTA of the cluster that works on the item:
+// second part of the debug buffer, [item number in the cluster][cluster][8] at offset 1024 (512 rows): %globaltimer (ns) in the leader CTA of the cluster that works on the item:
 //   0 producer turns to the item   1 Q requested (the previous item's output has left the Q buffers)   2 tile 0 sees its first S
-//   3 tile 0 has handed over its last P   4 last P V complete   5 tile 0's output stored   6 kernel entry of the cluster   7 SM id
+//   3 tile 0 has handed over its last P   4 last P V complete   5 tile 0's output stored   6 kernel entry of the cluster   7 SM id | key steps << 16
 #define PAIR_STAMP(slot)                                                                                    \
   do {                                                                                                      \
-    if (p.trace && rank == 0) p.trace[1024 + (long long)item * 8 + (slot)] = (long long)globaltimer_ns();   \
+    if (p.trace && rank == 0 && item * (int)(gridDim.x >> 1) + (int)(blockIdx.x >> 1) < 512)             \
+      p.trace[1024 + (long long)(item * (int)(gridDim.x >> 1) + (int)(blockIdx.x >> 1)) * 8 + (slot)] = (long long)globaltimer_ns(); \
   } while (0)
 
 template <int QT_, int SPLIT_, int POLY_, int FAST_ = 0>
@@ -89,7 +91,8 @@ struct FmhaPairCfg {
   static_assert(!FAST || (SPLIT_ == 1 && QT_ == 2), "the speculative softmax runs one thread per row on two tiles per CTA");
   static constexpr int XCH_BYTES = SPLIT == 1 ? 0 : 2 * QT * SPLIT * 128 * 4;  // [step parity][tile][slice][row] fp32 (slices of a row exchange max / sum)
   static constexpr int OSTAGE_BYTES = OSTAGE ? Q_TILE_BYTES : 0;
-  static constexpr int SMEM_BYTES = QT * Q_TILE_BYTES + ST * (K_HALF_BYTES + V_HALF_BYTES) + OSTAGE_BYTES + 1024 + 8 * NBARS + 16 + XCH_BYTES;
+  static constexpr int MAX_ITEMS = 60;                 // items of one cluster (its list lives in shared memory)
+  static constexpr int SMEM_BYTES = QT * Q_TILE_BYTES + ST * (K_HALF_BYTES + V_HALF_BYTES) + OSTAGE_BYTES + 1024 + 8 * NBARS + 16 + XCH_BYTES + 16 * (MAX_ITEMS + 1);
   static constexpr uint32_t TILE_COLS = 256, TM_S = 0, S_STRIDE = 128, TM_O = NSB * 128;
   static_assert(SPLIT == 1 || SPLIT == 2 || SPLIT == 4, "SPLIT");
   static_assert(QT == 1 || (QT == 2 && SPLIT <= 2), "two tiles per CTA run one or two threads per row (384 / 640 threads)");
@@ -123,43 +126,24 @@ fmha_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   auto ostage_done = [&](int i) { return bar_base + 8u * (2 + 4 * ST + 10 * QT + i); };   // tile i's output has been read out of the staging buffer
   const uint32_t tmem_slot = bar_base + 8u * Cfg::NBARS;
   const uint32_t xch_base = tmem_slot + 16u;
+  const uint32_t items_base = xch_base + Cfg::XCH_BYTES;   // [0]: number of items, [1 + n]: {unit, first key step, key steps, workspace slot or -1}
 
   const uint32_t warp = warp_id_sync();
   const uint32_t lane = lane_id();
   const uint32_t rank = cluster_ctarank();          // 0 = leader
   const bool leader = rank == 0;
-  // Persistent clusters: cluster c works on items c, c + G, c + 2 G, ... (G clusters in the grid).  Items [0, n_full) are whole units, the
-  // others key chunks (FmhaPairParams).  A unit owns 256 * QT consecutive query rows: tile i of the pair = rows [256 i, 256 i + 256), this
-  // CTA's half = [128 rank, +128).
+  // Persistent clusters: every role walks the cluster's item list (FmhaPairParams; built below by one thread before the set-up sync).
+  // A unit owns 256 * QT consecutive query rows: tile i of the pair = rows [256 i, 256 i + 256), this CTA's half = [128 rank, +128).
   const int n_kv_all = (p.len_kv + BKV - 1) / BKV;
-  const int item0 = (int)(blockIdx.x >> 1), item_step = (int)(gridDim.x >> 1);
   struct Item {
     int qb, head, batch;
     int kv0, n_kv;   // first 128-key step and number of steps
-    int part;        // >= 0: chunk number (its slot in the workspace)
+    int part;        // >= 0: partial piece, its slot in the workspace
   };
   auto get_item = [&](int item) {
     Item w;
-    int unit = item;
-    w.kv0 = 0;
-    w.n_kv = n_kv_all;
-    w.part = item - p.n_full;
-    if (w.part >= 0) {
-      int k = p.split_k, u, ci;
-      const int na = p.split_a * p.split_k;
-      if (w.part < na) {
-        u = w.part / k;
-        ci = w.part - u * k;
-      } else {
-        ++k;
-        u = (w.part - na) / k;
-        ci = (w.part - na) - u * k;
-        u += p.split_a;
-      }
-      unit = p.n_full + u;
-      w.kv0 = ci * n_kv_all / k;
-      w.n_kv = (ci + 1) * n_kv_all / k - w.kv0;
-    }
+    int unit;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(unit), "=r"(w.kv0), "=r"(w.n_kv), "=r"(w.part) : "r"(items_base + 16u * (uint32_t)(item + 1)));
     w.qb = unit % p.q_blocks;
     w.head = (unit / p.q_blocks) % p.heads;
     w.batch = unit / (p.q_blocks * p.heads);
@@ -168,15 +152,6 @@ fmha_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   auto q0_of = [&](const Item& w, int i) { return w.qb * (2 * QT * Cfg::BQ) + (2 * i + (int)rank) * Cfg::BQ; };
 
   if (warp == 0 && lane == 0) {
-    if (p.trace && rank == 0) {
-      uint32_t smid;
-      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-      const long long now = (long long)globaltimer_ns();
-      for (int item = item0; item < p.n_items; item += item_step) {
-        p.trace[1024 + (long long)item * 8 + 6] = now;
-        p.trace[1024 + (long long)item * 8 + 7] = smid;
-      }
-    }
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
@@ -201,6 +176,24 @@ fmha_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       }
     }
     fence_barrier_init();
+    // this cluster's items
+    const int c = (int)(blockIdx.x >> 1), G = (int)(gridDim.x >> 1);
+    int n = 0;
+    auto put = [&](int unit, int kv0, int n_kv, int part) {
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(items_base + 16u * (uint32_t)(n + 1)), "r"(unit), "r"(kv0), "r"(n_kv), "r"(part) : "memory");
+      ++n;
+    };
+    for (int u = c; u < p.n_full && n < Cfg::MAX_ITEMS; u += G) put(u, 0, n_kv_all, -1);
+    if (p.tail_units > 0) {
+      const long long T = (long long)p.tail_units * n_kv_all;
+      const int lo = (int)(c * T / G), hi = (int)((c + 1) * T / G);
+      for (int pos = lo; pos < hi && n < Cfg::MAX_ITEMS;) {
+        const int u = pos / n_kv_all, end = min(hi, (u + 1) * n_kv_all);
+        put(p.n_full + u, pos - u * n_kv_all, end - pos, end - pos == n_kv_all ? -1 : 2 * c + (pos == lo ? 0 : 1));
+        pos = end;
+      }
+    }
+    asm volatile("st.shared.b32 [%0], %1;" ::"r"(items_base), "r"(n) : "memory");
   }
   if (warp == 2) tmem_alloc<2>(tmem_slot, 512);
   tc_fence_before();
@@ -208,14 +201,28 @@ fmha_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  int n_local;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(n_local) : "r"(items_base));
   pdl_launch_dependents();
   pdl_wait();  // PDL: q / k / v written by the previous kernel are read (and O written) only after this point
+  if (p.trace && rank == 0 && threadIdx.x == 0) {
+    uint32_t smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    const long long now = (long long)globaltimer_ns();
+    for (int item = 0; item < n_local; ++item) {
+      const int row = item * (int)(gridDim.x >> 1) + (int)(blockIdx.x >> 1);
+      if (row < 512) {
+        p.trace[1024 + (long long)row * 8 + 6] = now;
+        p.trace[1024 + (long long)row * 8 + 7] = smid | ((long long)get_item(item).n_kv << 16);
+      }
+    }
+  }
 
   if (warp == 0) {
     // ------------------------------ TMA producer (warp-uniform control flow, one elected lane issues) ------------------------------
     int s = 0, n_it = 0, s_last = 0;
     uint32_t ph = 0, ph_last = 0;   // (s_last, ph_last): ring slot and phase of the previous item's last key tile
-    for (int item = item0; item < p.n_items; item += item_step, ++n_it) {
+    for (int item = 0; item < n_local; ++item, ++n_it) {
       const Item w = get_item(item);
       if (lane == 0) PAIR_STAMP(0);
       if (n_it > 0) {
@@ -312,9 +319,9 @@ fmha_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         if (i == QT - 1 && hh == NH - 1) { if (++vs == ST) { vs = 0; vph ^= 1u; } }
       };
       int g0 = 0, n_it = 0;
-      for (int item = item0; item < p.n_items; item += item_step, ++n_it) {
+      for (int item = 0; item < n_local; ++item, ++n_it) {
         const Item w = get_item(item);
-        const bool has_next = item + item_step < p.n_items;
+        const bool has_next = item + 1 < n_local;
         if (!Cfg::OSTAGE || n_it == 0) {
           // Q of this item is in shared memory (without the staging buffer: both CTAs have stored the previous item's output from there)
           mbar_wait(q_full, (uint32_t)n_it & 1u);
@@ -359,7 +366,7 @@ fmha_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     auto xch = [&](int par, int slice) { return xch_base + 4u * (uint32_t)(((par * QT + i) * SPLIT + slice) * 128 + rit); };
     const uint32_t quad_bar = 1u + (uint32_t)i * 4u + wq;   // named barrier of the SPLIT warps that own these 32 rows
     int g = 0;                                         // step counted over all items of this cluster (barrier parities)
-    for (int item = item0; item < p.n_items; item += item_step) {
+    for (int item = 0; item < n_local; ++item) {
     // (only what the key loop needs stays live across it; the epilogue decodes the item again)
     int n_kv, kvalid;                                // steps of this item; keys from its first step to the end of the sequence
     float c;
@@ -594,7 +601,7 @@ fmha_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     const uint32_t stage = Cfg::OSTAGE ? smem_ostage : smem_q(i);
     if constexpr (Cfg::OSTAGE) {
       // the two tiles take turns on the staging buffer: tile 1 after tile 0 of the same item, tile 0 after tile 1 of the previous item
-      const int n_done = (item - item0) / item_step;
+      const int n_done = item;
       if (i == 1) mbar_wait(ostage_done(0), (uint32_t)n_done & 1u);
       else if (n_done > 0) mbar_wait(ostage_done(1), (uint32_t)(n_done - 1) & 1u);
     }
@@ -649,7 +656,7 @@ fmha_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     }   // items
   } else if (warp == 3 && Cfg::OSTAGE) {
     // ------------------------------ output store (both CTAs): staging buffer -> global memory, tile 0 and tile 1 of every item in turn ------
-    for (int item = item0; item < p.n_items; item += item_step) {
+    for (int item = 0; item < n_local; ++item) {
       const Item w = get_item(item);
 #pragma unroll 1
       for (int i = 0; i < QT; ++i) {
@@ -691,33 +698,49 @@ static int make_map4(CUtensorMap* tm, const void* ptr, long long B, long long H,
   return encode_tensor_map(tm, ptr, 2, false, 4, dims, strides, box, true);
 }
 
-// ---- merge of the key chunks of the split units: one warp per query row ------------------------------------------------------------------
-// O[row] = sum_k w_k O_k[row] / sum_k w_k,  w_k = l_k 2^(m_k - max_k m_k)   (m_k = the chunk's reference maximum in the log2 domain, l_k its row sum)
+constexpr int kPairMaxClusters = 128;
+// ---- merge of the pieces of the units that were cut: one warp per (range boundary, query row) ---------------------------------------------
+// O[row] = sum_k w_k O_k[row] / sum_k w_k,  w_k = l_k 2^(m_k - max_k m_k)   (m_k = the piece's reference maximum in the log2 domain, l_k its row sum)
 struct FmhaPairCombineParams {
-  const __nv_bfloat16* ws_o;   // [chunk][rows_per_unit][128] normalised partial O
-  const float* ws_ml;          // [chunk][rows_per_unit][2]
+  const __nv_bfloat16* ws_o;   // [slot][rows_per_unit][128] normalised partial O
+  const float* ws_ml;          // [slot][rows_per_unit][2]
   __nv_bfloat16* O;
   long long o_bs, o_rs, o_hs;
   int len_q, q_blocks, heads, rows_per_unit;
-  int n_full, split_a, split_k, n_split_units;
+  int n_full, tail_units, n_kv, clusters;
+  int lo[kPairMaxClusters + 1];   // lo[c] = c T / clusters: first tail step of cluster c (host-computed: the kernel would spend its time in 64-bit divisions)
 };
 __global__ void __launch_bounds__(256) fmha_pair_combine_kernel(const FmhaPairCombineParams p) {
   pdl_launch_dependents();
   pdl_wait();
   const int w = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = (int)(threadIdx.x & 31u);
-  const int u = w / p.rows_per_unit, r = w - u * p.rows_per_unit;
-  if (u >= p.n_split_units) return;
+  const int c = w / p.rows_per_unit + 1, r = w - (c - 1) * p.rows_per_unit;   // boundary between the ranges of clusters c - 1 and c
+  if (c >= p.clusters) return;
+  auto lo_of = [&](int cc) { return p.lo[cc]; };
+  const int bnd = lo_of(c);
+  const int u = bnd / p.n_kv, u_lo = u * p.n_kv, u_hi = u_lo + p.n_kv;
+  // a boundary on a unit's edge cuts nothing; of several boundaries inside one unit the first one's warp merges it
+  if (bnd == u_lo || lo_of(c - 1) > u_lo) return;
   const int unit = p.n_full + u;
   const int qb = unit % p.q_blocks, head = (unit / p.q_blocks) % p.heads, batch = unit / (p.q_blocks * p.heads);
   const int row = qb * p.rows_per_unit + r;
   if (row >= p.len_q) return;
-  const int k = u < p.split_a ? p.split_k : p.split_k + 1;
-  const int first = u < p.split_a ? u * p.split_k : p.split_a * p.split_k + (u - p.split_a) * (p.split_k + 1);
+  // pieces: clusters c - 1, c, ... while their range starts inside the unit; a cluster's piece is its first item (slot 2 cc) when its range
+  // starts inside this unit, else its last (slot 2 cc + 1)
   float mx = -INFINITY;
-  for (int ci = 0; ci < k; ++ci) mx = fmaxf(mx, p.ws_ml[2ll * ((long long)(first + ci) * p.rows_per_unit + r)]);
+  for (int cc = c - 1; cc < p.clusters; ++cc) {
+    const int lo = lo_of(cc), hi = lo_of(cc + 1);
+    if (lo >= u_hi) break;
+    if (hi <= max(lo, u_lo)) continue;
+    const long long wrow = (long long)(2 * cc + (lo >= u_lo ? 0 : 1)) * p.rows_per_unit + r;
+    mx = fmaxf(mx, p.ws_ml[2 * wrow]);
+  }
   float acc[4] = {0.f, 0.f, 0.f, 0.f}, wsum = 0.f;
-  for (int ci = 0; ci < k; ++ci) {
-    const long long wrow = (long long)(first + ci) * p.rows_per_unit + r;
+  for (int cc = c - 1; cc < p.clusters; ++cc) {
+    const int lo = lo_of(cc), hi = lo_of(cc + 1);
+    if (lo >= u_hi) break;
+    if (hi <= max(lo, u_lo)) continue;
+    const long long wrow = (long long)(2 * cc + (lo >= u_lo ? 0 : 1)) * p.rows_per_unit + r;
     const float2 ml = *reinterpret_cast<const float2*>(p.ws_ml + 2 * wrow);
     const float wk = ml.y * ex2_approx(ml.x - mx);
     const uint2 v = *reinterpret_cast<const uint2*>(p.ws_o + wrow * 128 + lane * 4);
@@ -734,40 +757,25 @@ __global__ void __launch_bounds__(256) fmha_pair_combine_kernel(const FmhaPairCo
   *reinterpret_cast<uint2*>(p.O + (long long)batch * p.o_bs + (long long)row * p.o_rs + (long long)head * p.o_hs + lane * 4) = o;
 }
 
-// Key split of the last wave.  `slots` clusters run at a time; units % slots units are left for a wave that would keep most SMs idle for a
-// whole pass over the keys.  They are cut into slots * r chunks (r = 1..3 short waves), the variant with the smallest estimated time wins;
-// a chunk costs its steps plus kChunkOverhead steps (prologue, pipeline fill, epilogue), the merge kMergeCost steps.
-struct PairSplitPlan {
-  int n_full, split_a, split_k, n_chunks, n_split_units;
+// The decomposition (FmhaPairParams).  `slots` clusters run at a time.  The key split pays when the balanced share of the tail plus the cost of
+// two partial pieces and the merge (kSplitCost steps) is shorter than the whole pass over the keys the tail units would otherwise take.
+struct PairPlan {
+  int clusters, n_full, tail_units;
 };
-static PairSplitPlan plan_pair_split(long long units, int n_kv, int slots, unsigned force_rounds) {
-  constexpr int kMinSteps = 4, kChunkOverhead = 3, kMergeCost = 2;
-  PairSplitPlan none{(int)units, 0, 1, 0, 0};
-  if (slots <= 0 || units > (1ll << 24)) return none;
-  const int rem = (int)(units % slots);
-  if (rem == 0) return none;
-  const int cap = n_kv / kMinSteps;      // most chunks a unit may be cut into
-  if (cap < 2) return none;
-  PairSplitPlan best = none;
-  int best_cost = n_kv + kChunkOverhead;
-  for (int r = 1; r <= 3; ++r) {
-    if (force_rounds && (int)force_rounds != r) continue;
-    const int total = slots * r;
-    int base = total / rem;
-    if (base < 1) continue;
-    int extra = total - base * rem;      // units that get base + 1 chunks
-    if (base >= cap) { base = cap; extra = 0; }
-    if (base < 2 && extra == 0) continue;
-    const int longest = (n_kv + base - 1) / base;
-    const int cost = r * (longest + kChunkOverhead) + kMergeCost;
-    if (cost < best_cost || force_rounds) {
-      best_cost = cost;
-      best = PairSplitPlan{(int)(units - rem), rem - extra, base, (rem - extra) * base + extra * (base + 1), rem};
-    }
-  }
-  return best;
+static PairPlan plan_pair(long long units, int n_kv, int slots, bool allow_split, bool persistent, int max_items) {
+  constexpr int kMinSteps = 4, kSplitCost = 4, kMinKv = 8;
+  PairPlan whole{(int)std::min<long long>(slots, units), (int)units, 0};
+  if (!persistent || slots <= 0 || (units + whole.clusters - 1) / whole.clusters > max_items) return PairPlan{(int)units, (int)units, 0};
+  if (!allow_split || n_kv < kMinKv) return whole;
+  // small problems: as many clusters as there are kMinSteps-step pieces, at most one per SM pair
+  const int G = (int)std::min<long long>(slots, std::max<long long>(units, units * n_kv / kMinSteps));
+  const int n_full = (int)(units / G) * G, tail = (int)(units - n_full);
+  if (tail == 0) return whole;
+  const long long share = ((long long)tail * n_kv + G - 1) / G;
+  if (share + kSplitCost >= n_kv || n_full / G + share / n_kv + 3 > max_items) return whole;
+  return PairPlan{G, n_full, tail};
 }
-static constexpr long long kPairChunkBytes(int rows_per_unit) { return (long long)rows_per_unit * (128 * 2 + 2 * 4); }
+static constexpr long long kPairSlotBytes(int rows_per_unit) { return (long long)rows_per_unit * (128 * 2 + 2 * 4); }
 
 template <int QT_, int SPLIT_, int POLY_, int FAST_ = 0>
 static int pair_slots(int* slots) {
@@ -803,7 +811,7 @@ static int pair_slots(int* slots) {
   return VIST3A_OK;
 }
 
-// flags bit 17: no key split; bits 18-19: force the number of short waves; bit 20: one cluster per item instead of persistent clusters (A/B measurements)
+// flags bit 17: no key split; bit 20: one cluster per unit instead of persistent clusters (the round-2 decomposition; A/B measurements)
 template <int QT_, int SPLIT_, int POLY_, int FAST_ = 0>
 static int launch_fmha_pair(const vist3a_fmha_args& a, cudaStream_t stream, long long* ws_query) {
   using Cfg = FmhaPairCfg<QT_, SPLIT_, POLY_, FAST_>;
@@ -815,17 +823,18 @@ static int launch_fmha_pair(const vist3a_fmha_args& a, cudaStream_t stream, long
   const long long units = q_blocks * a.heads * a.batch;
   V3A_REQUIRE(units < (1ll << 29), VIST3A_ERR_INVALID, "fmha: too many query blocks");
   const int n_kv = (int)((a.len_kv + Cfg::BKV - 1) / Cfg::BKV);
-  PairSplitPlan plan{(int)units, 0, 1, 0, 0};
   int slots = 0, rc = pair_slots<QT_, SPLIT_, POLY_, FAST_>(&slots);
   if (rc) return rc;
-  if (!(a.flags & (1u << 17))) plan = plan_pair_split(units, n_kv, slots, (a.flags >> 18) & 3u);
-  const long long ws_bytes = (long long)plan.n_chunks * kPairChunkBytes(rows_per_unit);
+  slots = std::min(slots, kPairMaxClusters);
+  const bool persistent = !(a.flags & (1u << 20));
+  PairPlan plan = plan_pair(units, n_kv, slots, !(a.flags & (1u << 17)), persistent, Cfg::MAX_ITEMS);
+  const long long ws_bytes = plan.tail_units ? 2ll * plan.clusters * kPairSlotBytes(rows_per_unit) : 0;
   if (ws_query) {
     *ws_query = ws_bytes;
     return VIST3A_OK;
   }
-  if (plan.n_chunks && (a.workspace == nullptr || a.workspace_bytes < ws_bytes || ((uintptr_t)a.workspace & 127) != 0))
-    plan = PairSplitPlan{(int)units, 0, 1, 0, 0};   // no (usable) workspace: every unit over all keys
+  if (plan.tail_units && (a.workspace == nullptr || a.workspace_bytes < ws_bytes || ((uintptr_t)a.workspace & 127) != 0))
+    plan = plan_pair(units, n_kv, slots, false, persistent, Cfg::MAX_ITEMS);   // no (usable) workspace: every unit over all keys
   CUtensorMap tmQ, tmK, tmV, tmO, tmW;
   if ((rc = make_map4(&tmQ, a.Q, a.batch, a.heads, a.len_q, 128, a.q_bs, a.q_rs, a.q_hs, Cfg::BQ))) return rc;
   if ((rc = make_map4(&tmK, a.K, a.batch, a.heads, a.len_kv, 128, a.k_bs, a.k_rs, a.k_hs, Cfg::BKV / 2))) return rc;
@@ -841,22 +850,19 @@ static int launch_fmha_pair(const vist3a_fmha_args& a, cudaStream_t stream, long
   p.q_blocks = (int)q_blocks;
   p.heads = (int)a.heads;
   p.n_full = plan.n_full;
-  p.split_a = plan.split_a;
-  p.split_k = plan.split_k;
-  p.n_items = plan.n_full + plan.n_chunks;
+  p.tail_units = plan.tail_units;
   p.ws_ml = nullptr;
-  if (plan.n_chunks) {
-    const long long wrows = (long long)plan.n_chunks * rows_per_unit;
+  if (plan.tail_units) {
+    const long long wrows = 2ll * plan.clusters * rows_per_unit;
     if ((rc = make_map4(&tmW, a.workspace, 1, 1, wrows, 128, wrows * 128, 128, 128, Cfg::BQ))) return rc;
     p.ws_ml = reinterpret_cast<float*>(static_cast<char*>(a.workspace) + wrows * 128 * 2);
   } else {
     tmW = tmO;
   }
-  // persistent clusters, one per SM pair, each working through every slots-th item (flags bit 20: one cluster per item, scheduled by the hardware)
-  dim3 grid((unsigned)(2 * ((a.flags & (1u << 20)) ? p.n_items : std::min(slots, p.n_items))));
+  dim3 grid((unsigned)(2 * plan.clusters));
   V3A_CUDA_OK(launch_kernel(kern, grid, dim3(Cfg::THREADS), Cfg::SMEM_BYTES, stream, /*pdl=*/true, 2, tmQ, tmK, tmV, tmO, tmW, p));
   launch_counter().fetch_add(1);
-  if (plan.n_chunks) {
+  if (plan.tail_units) {
     FmhaPairCombineParams c;
     c.ws_o = static_cast<const __nv_bfloat16*>(a.workspace);
     c.ws_ml = p.ws_ml;
@@ -869,12 +875,15 @@ static int launch_fmha_pair(const vist3a_fmha_args& a, cudaStream_t stream, long
     c.heads = (int)a.heads;
     c.rows_per_unit = rows_per_unit;
     c.n_full = plan.n_full;
-    c.split_a = plan.split_a;
-    c.split_k = plan.split_k;
-    c.n_split_units = plan.n_split_units;
-    const long long warps = (long long)plan.n_split_units * rows_per_unit;
-    V3A_CUDA_OK(launch_kernel(fmha_pair_combine_kernel, dim3((unsigned)((warps + 7) / 8)), dim3(256), 0, stream, /*pdl=*/true, 1, c));
-    launch_counter().fetch_add(1);
+    c.tail_units = plan.tail_units;
+    c.n_kv = n_kv;
+    c.clusters = plan.clusters;
+    for (int cc = 0; cc <= plan.clusters; ++cc) c.lo[cc] = (int)((long long)cc * plan.tail_units * n_kv / plan.clusters);
+    const long long warps = (long long)(plan.clusters - 1) * rows_per_unit;
+    if (warps > 0) {
+      V3A_CUDA_OK(launch_kernel(fmha_pair_combine_kernel, dim3((unsigned)((warps + 7) / 8)), dim3(256), 0, stream, /*pdl=*/true, 1, c));
+      launch_counter().fetch_add(1);
+    }
   }
   return VIST3A_OK;
 }

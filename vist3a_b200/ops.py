@@ -179,11 +179,16 @@ def fmha(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, scale: Optional[f
                 L.check(need)
             _FMHA_WS_BYTES[key] = need
         if need:
-            skey = (q.device.index, st or 0)
-            ws = _FMHA_WS.get(skey)
-            if ws is None or ws.numel() < need:
+            if torch.cuda.is_current_stream_capturing():
+                # a buffer of the graph's own pool, like any temporary of captured code: the cache below must neither hand a graph-pool
+                # buffer to eager callers nor bake one eager buffer into several graphs that may replay on different streams
                 ws = torch.empty(need, dtype=torch.uint8, device=q.device)
-                _FMHA_WS[skey] = ws
+            else:
+                skey = (q.device.index, st or 0)
+                ws = _FMHA_WS.get(skey)
+                if ws is None or ws.numel() < need:
+                    ws = torch.empty(need, dtype=torch.uint8, device=q.device)
+                    _FMHA_WS[skey] = ws
             a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
     L.check(L.load().vist3a_fmha_fwd(C.byref(a), st))
     return out
