@@ -34,7 +34,7 @@ def main():
     if "--no-time" in sys.argv:
         return
     # persistent clusters + balanced key split of the tail (0) | no key split (bit 17) | neither (bit 20): the round-2 kernel's decomposition
-    variants = (("persist+split", 0), ("persist", NOSPLIT), ("neither", NOSPLIT | (1 << 20)))
+    variants = (("persist+split", 0), ("persist", NOSPLIT), ("neither", NOSPLIT | (1 << 20)), ("persist+split, merge kernel skipped", 1 << 22))
     for name, B, H, Lq, Lk in (("dit_self_1.3b", 2, 12, 4096, 4096), ("dit_cross", 2, 12, 4096, 512), ("dit_self_14b", 2, 40, 4096, 4096), ("dit_self_14b_21v", 2, 40, 6144, 6144),
                                ("b1", 1, 12, 4096, 4096), ("small", 1, 12, 1024, 4096)):
         q = torch.randn(B, Lq, H, 128, device="cuda").bfloat16()

@@ -707,54 +707,89 @@ struct FmhaPairCombineParams {
   __nv_bfloat16* O;
   long long o_bs, o_rs, o_hs;
   int len_q, q_blocks, heads, rows_per_unit;
-  int n_full, tail_units, n_kv, clusters;
+  int n_full, tail_units, n_kv, clusters, n_cut;
   int lo[kPairMaxClusters + 1];   // lo[c] = c T / clusters: first tail step of cluster c (host-computed: the kernel would spend its time in 64-bit divisions)
+  int cut[kPairMaxClusters];      // the cut units: for each, the first range boundary c (between clusters c - 1 and c) inside it
 };
+// One warp per (cut unit, 4 query rows); a lane owns 4 head-dim columns.  The kernel is pure latency (15 MB out of L2 for the whole merge):
+// the loads of up to 4 pieces x 4 rows are issued together, and the grid is one wave.
+constexpr int kCombineRows = 4, kCombineBatch = 4;
 __global__ void __launch_bounds__(256) fmha_pair_combine_kernel(const FmhaPairCombineParams p) {
   pdl_launch_dependents();
-  pdl_wait();
   const int w = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = (int)(threadIdx.x & 31u);
-  const int c = w / p.rows_per_unit + 1, r = w - (c - 1) * p.rows_per_unit;   // boundary between the ranges of clusters c - 1 and c
-  if (c >= p.clusters) return;
-  auto lo_of = [&](int cc) { return p.lo[cc]; };
-  const int bnd = lo_of(c);
-  const int u = bnd / p.n_kv, u_lo = u * p.n_kv, u_hi = u_lo + p.n_kv;
-  // a boundary on a unit's edge cuts nothing; of several boundaries inside one unit the first one's warp merges it
-  if (bnd == u_lo || lo_of(c - 1) > u_lo) return;
+  const int groups = p.rows_per_unit / kCombineRows;
+  const int ci = w / groups, r0 = (w - ci * groups) * kCombineRows;
+  if (ci >= p.n_cut) return;
+  const int c = p.cut[ci];
+  const int u = p.lo[c] / p.n_kv, u_lo = u * p.n_kv, u_hi = u_lo + p.n_kv;
   const int unit = p.n_full + u;
   const int qb = unit % p.q_blocks, head = (unit / p.q_blocks) % p.heads, batch = unit / (p.q_blocks * p.heads);
-  const int row = qb * p.rows_per_unit + r;
-  if (row >= p.len_q) return;
   // pieces: clusters c - 1, c, ... while their range starts inside the unit; a cluster's piece is its first item (slot 2 cc) when its range
   // starts inside this unit, else its last (slot 2 cc + 1)
-  float mx = -INFINITY;
-  for (int cc = c - 1; cc < p.clusters; ++cc) {
-    const int lo = lo_of(cc), hi = lo_of(cc + 1);
-    if (lo >= u_hi) break;
-    if (hi <= max(lo, u_lo)) continue;
-    const long long wrow = (long long)(2 * cc + (lo >= u_lo ? 0 : 1)) * p.rows_per_unit + r;
-    mx = fmaxf(mx, p.ws_ml[2 * wrow]);
+  float mx[kCombineRows], wsum[kCombineRows], acc[kCombineRows][4];
+#pragma unroll
+  for (int rr = 0; rr < kCombineRows; ++rr) {
+    mx[rr] = -INFINITY;
+    wsum[rr] = 0.f;
+    acc[rr][0] = acc[rr][1] = acc[rr][2] = acc[rr][3] = 0.f;
   }
-  float acc[4] = {0.f, 0.f, 0.f, 0.f}, wsum = 0.f;
-  for (int cc = c - 1; cc < p.clusters; ++cc) {
-    const int lo = lo_of(cc), hi = lo_of(cc + 1);
-    if (lo >= u_hi) break;
-    if (hi <= max(lo, u_lo)) continue;
-    const long long wrow = (long long)(2 * cc + (lo >= u_lo ? 0 : 1)) * p.rows_per_unit + r;
-    const float2 ml = *reinterpret_cast<const float2*>(p.ws_ml + 2 * wrow);
-    const float wk = ml.y * ex2_approx(ml.x - mx);
-    const uint2 v = *reinterpret_cast<const uint2*>(p.ws_o + wrow * 128 + lane * 4);
-    wsum += wk;
-    acc[0] = fmaf(wk, __uint_as_float(v.x << 16), acc[0]);
-    acc[1] = fmaf(wk, __uint_as_float(v.x & 0xffff0000u), acc[1]);
-    acc[2] = fmaf(wk, __uint_as_float(v.y << 16), acc[2]);
-    acc[3] = fmaf(wk, __uint_as_float(v.y & 0xffff0000u), acc[3]);
+  pdl_wait();
+  int cc = c - 1;
+  bool more = true;
+  while (more) {
+    int slot[kCombineBatch];
+#pragma unroll
+    for (int k = 0; k < kCombineBatch; ++k) {
+      slot[k] = -1;
+      while (more && slot[k] < 0) {
+        if (cc >= p.clusters || p.lo[cc] >= u_hi) {
+          more = false;
+        } else {
+          const int lo = p.lo[cc], hi = p.lo[cc + 1];
+          if (hi > max(lo, u_lo)) slot[k] = 2 * cc + (lo >= u_lo ? 0 : 1);
+          ++cc;
+        }
+      }
+    }
+    float2 ml[kCombineBatch][kCombineRows];
+    uint2 v[kCombineBatch][kCombineRows];
+#pragma unroll
+    for (int k = 0; k < kCombineBatch; ++k) {
+#pragma unroll
+      for (int rr = 0; rr < kCombineRows; ++rr) {
+        const long long wrow = (long long)max(slot[k], 0) * p.rows_per_unit + r0 + rr;
+        ml[k][rr] = *reinterpret_cast<const float2*>(p.ws_ml + 2 * wrow);
+        v[k][rr] = *reinterpret_cast<const uint2*>(p.ws_o + wrow * 128 + lane * 4);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < kCombineBatch; ++k) {
+      if (slot[k] >= 0) {
+#pragma unroll
+        for (int rr = 0; rr < kCombineRows; ++rr) {
+          const float m_new = fmaxf(mx[rr], ml[k][rr].x);
+          const float f = ex2_approx(mx[rr] - m_new), wk = ml[k][rr].y * ex2_approx(ml[k][rr].x - m_new);
+          mx[rr] = m_new;
+          wsum[rr] = wsum[rr] * f + wk;
+          acc[rr][0] = fmaf(wk, __uint_as_float(v[k][rr].x << 16), acc[rr][0] * f);
+          acc[rr][1] = fmaf(wk, __uint_as_float(v[k][rr].x & 0xffff0000u), acc[rr][1] * f);
+          acc[rr][2] = fmaf(wk, __uint_as_float(v[k][rr].y << 16), acc[rr][2] * f);
+          acc[rr][3] = fmaf(wk, __uint_as_float(v[k][rr].y & 0xffff0000u), acc[rr][3] * f);
+        }
+      }
+    }
   }
-  const float inv = 1.0f / wsum;
-  uint2 o;
-  o.x = pack_bf16(acc[0] * inv, acc[1] * inv);
-  o.y = pack_bf16(acc[2] * inv, acc[3] * inv);
-  *reinterpret_cast<uint2*>(p.O + (long long)batch * p.o_bs + (long long)row * p.o_rs + (long long)head * p.o_hs + lane * 4) = o;
+#pragma unroll
+  for (int rr = 0; rr < kCombineRows; ++rr) {
+    const int row = qb * p.rows_per_unit + r0 + rr;
+    if (row < p.len_q) {
+      const float inv = 1.0f / wsum[rr];
+      uint2 o;
+      o.x = pack_bf16(acc[rr][0] * inv, acc[rr][1] * inv);
+      o.y = pack_bf16(acc[rr][2] * inv, acc[rr][3] * inv);
+      *reinterpret_cast<uint2*>(p.O + (long long)batch * p.o_bs + (long long)row * p.o_rs + (long long)head * p.o_hs + lane * 4) = o;
+    }
+  }
 }
 
 // The decomposition (FmhaPairParams).  `slots` clusters run at a time.  The key split pays when the balanced share of the tail plus the cost of
@@ -879,8 +914,14 @@ static int launch_fmha_pair(const vist3a_fmha_args& a, cudaStream_t stream, long
     c.n_kv = n_kv;
     c.clusters = plan.clusters;
     for (int cc = 0; cc <= plan.clusters; ++cc) c.lo[cc] = (int)((long long)cc * plan.tail_units * n_kv / plan.clusters);
-    const long long warps = (long long)(plan.clusters - 1) * rows_per_unit;
-    if (warps > 0) {
+    // a boundary on a unit's edge cuts nothing; of several boundaries inside one unit the first one stands for it
+    c.n_cut = 0;
+    for (int cc = 1; cc < plan.clusters; ++cc) {
+      const int u_lo = c.lo[cc] / n_kv * n_kv;
+      if (c.lo[cc] != u_lo && c.lo[cc - 1] <= u_lo) c.cut[c.n_cut++] = cc;
+    }
+    const long long warps = (long long)c.n_cut * (rows_per_unit / kCombineRows);
+    if (warps > 0 && !(a.flags & (1u << 22))) {   // (flags bit 22, timing only: no merge -- the cut units keep their stale output)
       V3A_CUDA_OK(launch_kernel(fmha_pair_combine_kernel, dim3((unsigned)((warps + 7) / 8)), dim3(256), 0, stream, /*pdl=*/true, 1, c));
       launch_counter().fetch_add(1);
     }

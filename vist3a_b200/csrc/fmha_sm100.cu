@@ -1185,7 +1185,7 @@ int fmha_entry(const vist3a_fmha_args* args, cudaStream_t stream, long long* ws_
   // keys; +5.5 % on the decoder's 1029-key frame attention, +2.7 % on its 13 377-key global attention).  flags bit 13
   // selects the former default (two threads per row, exact running maximum) for A/B.
   // (flags bits 17-20 steer the work decomposition of the pair kernel, bit 21 switches the tail-row CTAs on; they do not select a kernel)
-  if ((a.flags & ~(31u << 17)) == 0u) {
+  if ((a.flags & ~(63u << 17)) == 0u) {
     if (ws_query && (a.head_dim == 64 || a.len_kv < 512)) return VIST3A_OK;
     // (head_dim 64, long key sequences -- the decoder's global attention: two threads per row, +2 % over one thread per row at 13 377 keys; -7 % at 1029)
     if (a.head_dim == 64) return a.len_kv >= 4096 ? launch_fmha<64, 128, 0, 2, 2>(a, stream) : launch_fmha<64, 128, 2, 1, 1>(a, stream);
