@@ -74,6 +74,8 @@ def _peaks():
 def _graph_time_fmha(B, H, Lq, Lk, D, iters=10):
     """device ms per attention call (kernel + merge kernel where the key split applies) inside a CUDA graph of `iters` back-to-back calls --
     how the step itself runs them; an eager event bracket also counts the host-side gap between the two launches of a call"""
+    import torch
+
     from vist3a_b200 import ops
     q = torch.randn(B, Lq, H, D, device="cuda").bfloat16()
     k = torch.randn(B, Lk, H, D, device="cuda").bfloat16()
