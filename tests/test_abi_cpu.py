@@ -233,3 +233,38 @@ def test_every_compute_entry_point_rejects_zeroed_arguments(lib):
         assert ":" in msg, (name, msg)            # "<entry point>: <what is wrong>"
         checked += 1
     assert checked == len(lib.EXPORTS) - len(skip) and h.vist3a_launch_count() == n0
+
+
+def test_fmha_pair_key_split_plan_is_consistent(lib):
+    """The work decomposition of the CTA-pair attention kernel (persistent clusters; the tail units laid end to end and cut into one equal
+    range per cluster; a merge kernel) is index arithmetic shared by three places: the kernel's per-cluster item list, the host's list of cut
+    units and the merge kernel's walk over a unit's pieces.  v3a_debug_fmha_pair_plan_check rebuilds all three with the functions the kernels
+    use (no CUDA call) and checks coverage (every key step of every unit exactly once), the item-list bound, slot uniqueness and that the
+    merge visits exactly the slots that were written.  Swept over unit counts around multiples of the cluster count, short and long key
+    sequences, odd cluster counts, with the split / the persistence switched off."""
+    h = lib.load()
+    fn = h.v3a_debug_fmha_pair_plan_check
+    fn.restype = C.c_int
+    fn.argtypes = [C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]
+    out = (C.c_int * 5)()
+    split_seen = whole_seen = 0
+    for slots in (1, 2, 7, 66, 74, 128, 200):
+        for units in list(range(1, 40)) + [73, 74, 75, 96, 147, 148, 149, 192, 222, 640, 960, 4439, 4441, 5000]:
+            for n_kv in (1, 3, 4, 7, 8, 9, 16, 31, 32, 48, 105, 257):
+                for allow_split, persistent in ((1, 1), (0, 1), (1, 0)):
+                    rc = fn(units, n_kv, slots, allow_split, persistent, out)
+                    assert rc == 0, (rc, units, n_kv, slots, allow_split, persistent)
+                    clusters, n_full, tail, n_cut, partial = list(out)
+                    assert n_full + tail == units and clusters >= 1
+                    if not allow_split or not persistent or n_kv < 8:
+                        assert tail == 0 and partial == 0
+                    if tail:
+                        split_seen += 1
+                        assert clusters <= min(slots, 128) and partial <= 2 * clusters and n_cut <= tail
+                    else:
+                        whole_seen += 1
+    assert split_seen > 500 and whole_seen > 500
+    # the BASELINE shapes on a B200 (74 cluster slots): B2 H12 L4096 -> 192 units of 32 steps: two whole waves + 44 tail units in 74 ranges
+    assert fn(192, 32, 74, 1, 1, out) == 0 and list(out)[:3] == [74, 148, 44]
+    assert fn(192, 4, 74, 1, 1, out) == 0 and list(out)[:3] == [74, 192, 0]          # cross-attention (512 keys): too short to cut
+    assert fn(24, 32, 74, 1, 1, out) == 0 and list(out)[:3] == [74, 0, 24]           # fewer units than clusters: everything is "tail"

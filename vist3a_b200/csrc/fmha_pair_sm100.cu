@@ -27,6 +27,8 @@
 #include "common.cuh"
 #include "fmha_math.cuh"
 #include "host_util.cuh"
+#include <algorithm>
+#include <vector>
 
 namespace v3a {
 
@@ -65,6 +67,38 @@ extern "C" void v3a_debug_fmha_pair_trace(void* buf) { g_pair_trace.store(reinte
     if (p.trace && rank == 0 && item * (int)(gridDim.x >> 1) + (int)(blockIdx.x >> 1) < 512)             \
       p.trace[1024 + (long long)(item * (int)(gridDim.x >> 1) + (int)(blockIdx.x >> 1)) * 8 + (slot)] = (long long)globaltimer_ns(); \
   } while (0)
+
+// ---- the key split of the tail: index arithmetic shared by the attention kernel (its item list), the merge kernel and the host-side
+//      self-check (v3a_debug_fmha_pair_plan_check, tests/test_abi_cpu.py) ------------------------------------------------------------------
+// pieces of the tail range [lo, hi) of cluster c, in order: f(unit in the tail, first key step, key steps, workspace slot or -1 for a whole unit)
+template <class F>
+__host__ __device__ inline void pair_tail_pieces(int c, int lo, int hi, int n_kv_all, F&& f) {
+  for (int pos = lo; pos < hi;) {
+    const int u = pos / n_kv_all, end = hi < (u + 1) * n_kv_all ? hi : (u + 1) * n_kv_all;
+    f(u, pos - u * n_kv_all, end - pos, end - pos == n_kv_all ? -1 : 2 * c + (pos == lo ? 0 : 1));
+    pos = end;
+  }
+}
+// merge side: the next piece of the unit with tail steps [u_lo, u_hi), walking the clusters from cc on (lo[] = the range boundaries); returns its
+// workspace slot, or -1 when the unit has no further piece.  A cluster's piece is its first item (slot 2 cc) when its range starts inside
+// the unit, else its last (slot 2 cc + 1).
+__host__ __device__ inline int pair_next_piece_slot(const int* lo, int clusters, int u_lo, int u_hi, int& cc) {
+  while (cc < clusters && lo[cc] < u_hi) {
+    const int l = lo[cc], h = lo[cc + 1];
+    const int at = cc++;
+    if (h > (l > u_lo ? l : u_lo)) return 2 * at + (l >= u_lo ? 0 : 1);
+  }
+  return -1;
+}
+// the cut units: a boundary on a unit's edge cuts nothing; of several boundaries inside one unit the first one stands for it
+__host__ inline int pair_cut_list(const int* lo, int clusters, int n_kv_all, int* cut) {
+  int n = 0;
+  for (int cc = 1; cc < clusters; ++cc) {
+    const int u_lo = lo[cc] / n_kv_all * n_kv_all;
+    if (lo[cc] != u_lo && lo[cc - 1] <= u_lo) cut[n++] = cc;
+  }
+  return n;
+}
 
 template <int QT_, int SPLIT_, int POLY_, int FAST_ = 0>
 struct FmhaPairCfg {
@@ -187,11 +221,9 @@ fmha_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     if (p.tail_units > 0) {
       const long long T = (long long)p.tail_units * n_kv_all;
       const int lo = (int)(c * T / G), hi = (int)((c + 1) * T / G);
-      for (int pos = lo; pos < hi && n < Cfg::MAX_ITEMS;) {
-        const int u = pos / n_kv_all, end = min(hi, (u + 1) * n_kv_all);
-        put(p.n_full + u, pos - u * n_kv_all, end - pos, end - pos == n_kv_all ? -1 : 2 * c + (pos == lo ? 0 : 1));
-        pos = end;
-      }
+      pair_tail_pieces(c, lo, hi, n_kv_all, [&](int u, int kv0, int n_kv, int slot) {
+        if (n < Cfg::MAX_ITEMS) put(p.n_full + u, kv0, n_kv, slot);
+      });
     }
     asm volatile("st.shared.b32 [%0], %1;" ::"r"(items_base), "r"(n) : "memory");
   }
@@ -740,16 +772,8 @@ __global__ void __launch_bounds__(256) fmha_pair_combine_kernel(const FmhaPairCo
     int slot[kCombineBatch];
 #pragma unroll
     for (int k = 0; k < kCombineBatch; ++k) {
-      slot[k] = -1;
-      while (more && slot[k] < 0) {
-        if (cc >= p.clusters || p.lo[cc] >= u_hi) {
-          more = false;
-        } else {
-          const int lo = p.lo[cc], hi = p.lo[cc + 1];
-          if (hi > max(lo, u_lo)) slot[k] = 2 * cc + (lo >= u_lo ? 0 : 1);
-          ++cc;
-        }
-      }
+      slot[k] = more ? pair_next_piece_slot(p.lo, p.clusters, u_lo, u_hi, cc) : -1;
+      more = slot[k] >= 0;
     }
     float2 ml[kCombineBatch][kCombineRows];
     uint2 v[kCombineBatch][kCombineRows];
@@ -914,12 +938,7 @@ static int launch_fmha_pair(const vist3a_fmha_args& a, cudaStream_t stream, long
     c.n_kv = n_kv;
     c.clusters = plan.clusters;
     for (int cc = 0; cc <= plan.clusters; ++cc) c.lo[cc] = (int)((long long)cc * plan.tail_units * n_kv / plan.clusters);
-    // a boundary on a unit's edge cuts nothing; of several boundaries inside one unit the first one stands for it
-    c.n_cut = 0;
-    for (int cc = 1; cc < plan.clusters; ++cc) {
-      const int u_lo = c.lo[cc] / n_kv * n_kv;
-      if (c.lo[cc] != u_lo && c.lo[cc - 1] <= u_lo) c.cut[c.n_cut++] = cc;
-    }
+    c.n_cut = pair_cut_list(c.lo, plan.clusters, n_kv, c.cut);
     const long long warps = (long long)c.n_cut * (rows_per_unit / kCombineRows);
     if (warps > 0 && !(a.flags & (1u << 22))) {   // (flags bit 22, timing only: no merge -- the cut units keep their stale output)
       V3A_CUDA_OK(launch_kernel(fmha_pair_combine_kernel, dim3((unsigned)((warps + 7) / 8)), dim3(256), 0, stream, /*pdl=*/true, 1, c));
@@ -927,6 +946,75 @@ static int launch_fmha_pair(const vist3a_fmha_args& a, cudaStream_t stream, long
     }
   }
   return VIST3A_OK;
+}
+
+// Host-side self-check of the decomposition (no CUDA call; tests/test_abi_cpu.py sweeps it): builds every cluster's item list and the merge's
+// piece lists with the functions the kernels use and verifies that (1) every key step of every unit is covered exactly once, (2) no cluster
+// exceeds max_items, (3) every workspace slot is written at most once, (4) the merge visits, for every cut unit, exactly the slots its partial
+// pieces were written to and each uncut unit is written whole.  Returns 0, or the number of the violated property; out = {clusters, n_full,
+// tail_units, cut units, partial pieces}.
+extern "C" int v3a_debug_fmha_pair_plan_check(long long units, int n_kv, int slots, int allow_split, int persistent, int* out) {
+  constexpr int kMaxItems = FmhaPairCfg<2, 1, 3, 1>::MAX_ITEMS;
+  if (units <= 0 || units > (1 << 20) || n_kv <= 0 || n_kv > (1 << 14) || slots <= 0) return -1;
+  slots = std::min(slots, kPairMaxClusters);
+  const PairPlan plan = plan_pair(units, n_kv, slots, allow_split != 0, persistent != 0, kMaxItems);
+  const int G = plan.clusters;
+  std::vector<int> covered((size_t)units * n_kv, 0), slot_unit(2 * (size_t)G, -1), lo(G + 1, 0);
+  std::vector<char> whole(units, 0);
+  int partial = 0;
+  for (int c = 0; c <= G; ++c) lo[c] = (int)((long long)c * plan.tail_units * n_kv / G);
+  for (int c = 0; c < G; ++c) {
+    int items = 0;
+    for (int u = c; u < plan.n_full; u += G) {
+      ++items;
+      whole[u] = 1;
+      for (int j = 0; j < n_kv; ++j) ++covered[(size_t)u * n_kv + j];
+    }
+    int bad = 0;
+    if (plan.tail_units) {
+      pair_tail_pieces(c, lo[c], lo[c + 1], n_kv, [&](int u, int kv0, int n, int slot) {
+        ++items;
+        const int unit = plan.n_full + u;
+        for (int j = 0; j < n; ++j) ++covered[(size_t)unit * n_kv + kv0 + j];
+        if (slot < 0) {
+          whole[unit] = 1;
+        } else {
+          ++partial;
+          if (slot >= 2 * G || slot_unit[slot] != -1) bad = 3;
+          else slot_unit[slot] = unit;
+        }
+      });
+    }
+    if (bad) return bad;
+    if (items > kMaxItems) return 2;
+  }
+  for (int v : covered)
+    if (v != 1) return 1;
+  int n_cut = 0;
+  if (plan.tail_units) {
+    if (G > kPairMaxClusters) return -2;
+    int cut[kPairMaxClusters];
+    n_cut = pair_cut_list(lo.data(), G, n_kv, cut);
+    std::vector<char> merged(units, 0);
+    int visited = 0;
+    for (int i = 0; i < n_cut; ++i) {
+      const int u = lo[cut[i]] / n_kv, unit = plan.n_full + u;
+      if (whole[unit] || merged[unit]) return 4;
+      merged[unit] = 1;
+      int cc = cut[i] - 1;
+      for (int slot; (slot = pair_next_piece_slot(lo.data(), G, u * n_kv, (u + 1) * n_kv, cc)) >= 0; ++visited)
+        if (slot_unit[slot] != unit) return 4;
+    }
+    if (visited != partial) return 4;
+    for (long long u = 0; u < units; ++u)
+      if (!whole[u] && !merged[u]) return 4;
+  } else if (partial) {
+    return 4;
+  }
+  if (out) {
+    out[0] = G; out[1] = plan.n_full; out[2] = plan.tail_units; out[3] = n_cut; out[4] = partial;
+  }
+  return 0;
 }
 
 // head_dim 128 on CTA pairs; `variant` (A/B measurements): 0 = default: two query tiles per CTA, one thread per query row, P handed over in
