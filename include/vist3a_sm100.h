@@ -139,7 +139,11 @@ typedef struct vist3a_fmha_args {
   int64_t o_bs, o_rs, o_hs;
   float scale; /* multiplies QK^T; 1/sqrt(head_dim) in both references */
   uint32_t flags; /* 0 = tuned default; kernel-variant selectors for A/B measurements only (results identical up to rounding):
-                     bit0 one thread per query row, bit1 128-key steps (d=128), bit2 single MMA-issuing warp, bits 3.. = 1 + FMA-pipe exp2 share */
+                     bit0 one thread per query row, bit1 128-key steps (d=128), bit2 single MMA-issuing warp, bits 3.. = 1 + FMA-pipe exp2 share,
+                     bit8 | variant << 9 the CTA-pair kernel, bit13 / 14 / 16 former default / two threads per row / one tile per CTA;
+                     work decomposition, no kernel selection: bit17 no key split of the last wave, bit20 one cluster per query block
+                     instead of persistent clusters, bit21 CUDA-core CTAs for 1..8 tail rows (head_dim 64);
+                     timing only (WRONG results): bit12 softmax skipped, bit22 merge kernel skipped */
   const float* q_row_scale; /* optional [batch * len_q] fp32: extra positive factor on the logits of query row (b, i), all heads */
   void* workspace;          /* optional scratch (128-byte aligned), see vist3a_fmha_workspace_bytes; NULL / too small: the call still succeeds */
   int64_t workspace_bytes;
