@@ -277,6 +277,25 @@ def test_fmha_tail_rows(ops, shape):
     assert _rel_l2(o[:, -t:], default.float()[:, -t:]) < 6e-3
 
 
+def test_fmha_pair_decompositions_are_bit_identical_on_whole_units(ops):
+    """The CTA-pair kernel's work decomposition does not change the arithmetic of a query block that is processed over all keys: persistent
+    clusters (default, key split off), one cluster per block (flags bit 20), and the automatic fall-back to one cluster per block when a
+    cluster's item list would exceed its shared-memory table (4800 blocks > 60 x 74) give the same bits."""
+    g = torch.Generator(device="cuda").manual_seed(11)
+    B, H, Lq, Lk = 10, 60, 4096, 640
+    q = torch.randn(B, Lq, H, 128, device="cuda", generator=g).bfloat16()
+    k = torch.randn(B, Lk, H, 128, device="cuda", generator=g).bfloat16()
+    v = torch.randn(B, Lk, H, 128, device="cuda", generator=g).bfloat16()
+    big = ops.fmha(q, k, v)                                    # 4800 query blocks: one cluster per block
+    for b in (0, 7):
+        persistent = ops.fmha(q[b:b + 1], k[b:b + 1], v[b:b + 1], flags=1 << 17)
+        per_block = ops.fmha(q[b:b + 1], k[b:b + 1], v[b:b + 1], flags=(1 << 17) | (1 << 20))
+        assert torch.equal(persistent, per_block)
+        assert torch.equal(persistent, big[b:b + 1])
+    ref = torch.nn.functional.scaled_dot_product_attention(q[:1].float().transpose(1, 2), k[:1].float().transpose(1, 2), v[:1].float().transpose(1, 2)).transpose(1, 2)
+    assert _rel_l2(big[:1].float(), ref) < 6e-3
+
+
 def test_fmha_large_scores(ops):
     # rows whose max moves by > 2^8 between kv tiles exercise the lazy-rescale path
     g = torch.Generator(device="cuda").manual_seed(5)
