@@ -7,12 +7,20 @@
 // = 96 B/clk, and P V (A = P from tensor memory, B = half of V's head-dim columns: 2 KB per MMA) needs 32 B/clk.  TMA traffic halves too
 // (each CTA loads half of every K and V tile: 32 KB per 128-key step).
 //
-// One cluster of two CTAs per (batch, head, 256 query rows); CTA r owns query rows [128 r, 128 r + 128).
-//   warp 0        TMA producer (both CTAs): own Q tile once; per 128-key step the CTA's half of K (keys [64 r, 64 r + 64), all of d) and its half
+// Work decomposition (FmhaPairParams, plan_pair): PERSISTENT clusters of two CTAs, one per SM pair, each walking its own list of items
+// (built in shared memory at start-up).  An item is a unit = (batch, head, 256 QT query rows) over all keys, or -- for the units of the grid's
+// last, partial wave -- a range of its key steps: those units are laid end to end and cut into one equal range per cluster; partial pieces
+// go to a workspace and fmha_pair_combine_kernel merges them.  Within a tile of the pair CTA r owns query rows [128 r, 128 r + 128).
+// Barrier parities follow a step counter that runs across the items of a cluster.  Between items: the output leaves through its own 32 KB
+// staging buffer (OSTAGE; the two tiles take turns), so the producer reloads the Q buffers as soon as the item's last Q K^T has completed
+// and the MMA warp issues the next item's first Q K^T right behind the last P V.
+//   warp 0        TMA producer (both CTAs): per item its own Q tiles; per 128-key step the CTA's half of K (keys [64 r, 64 r + 64), all of d) and its half
 //                 of V (all 128 keys, head-dim columns [64 r, 64 r + 64)); "full" barriers live in the leader CTA (2-SM TMA completion)
 //   warp 1        MMA issuer, leader CTA only: S(j) = Q K(j)^T into TMEM score buffer j % 2, O += P(j) V(j) (P read from TMEM), for both CTAs;
 //                 completion is multicast to both CTAs' barriers (tcgen05.commit ... multicast::cluster)
 //   warp 2        TMEM allocator (cta_group::2, 512 columns)
+//   warp 3        output store (OSTAGE): waits for a tile's softmax threads to stage their rows, issues the bulk tensor store (to O, or to
+//                 the workspace for a partial piece) and releases the staging buffer to the other tile
 //   warps 4..     softmax, SPLIT threads per query row (thread = TMEM lane x column slice): tcgen05.ld S, row max (slices exchange through
 //                 shared memory + a named barrier), lazy rescale of O, exp2, bf16 P -> tcgen05.st over the S buffer it came from, arrive on
 //                 the LEADER's p_full barrier (remote arrive from the peer CTA)
