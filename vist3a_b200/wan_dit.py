@@ -175,10 +175,12 @@ class WanTransformer3DModelB200(torch.nn.Module):
             w[short + ".w"], w[short + ".b"] = W(p + full), Bv(p + full)
         w["out.table"] = V32("scale_shift_table").reshape(2, D).contiguous()
         w["out.w"], w["out.b"] = W("proj_out"), Bv("proj_out")
+        # the AdaLN tables of all blocks in one [layers, 6, D] tensor: one modulation launch per batch row covers every block of a forward
+        w["tables"] = torch.stack([V32(f"blocks.{i}.scale_shift_table").reshape(6, D) for i in range(c.num_layers)]).contiguous()
         for i in range(c.num_layers):
             b = f"blocks.{i}."
             k = f"b{i}."
-            w[k + "table"] = V32(b + "scale_shift_table").reshape(6, D).contiguous()
+            w[k + "table"] = w["tables"][i]
             w[k + "qkv.w"] = W(b + "attn1.to_q", b + "attn1.to_k", b + "attn1.to_v")
             w[k + "qkv.b"] = Bv(b + "attn1.to_q", b + "attn1.to_k", b + "attn1.to_v")
             w[k + "nqk1"] = torch.cat([V32(b + "attn1.norm_q.weight"), V32(b + "attn1.norm_k.weight")]).contiguous()
@@ -247,7 +249,7 @@ class WanTransformer3DModelB200(torch.nn.Module):
                 x=torch.empty((M, D), dtype=bf, device=dev), h=torch.empty((M, D), dtype=bf, device=dev),
                 qkv=torch.empty((M, 3 * D), dtype=bf, device=dev), q2=torch.empty((M, D), dtype=bf, device=dev),
                 att=torch.empty((M, D), dtype=bf, device=dev), ffn=torch.empty((M, c.ffn_dim), dtype=bf, device=dev),
-                mod=torch.empty((B, 6, D), dtype=torch.float32, device=dev),
+                mod=torch.empty((B, c.num_layers, 6, D), dtype=torch.float32, device=dev),
                 mod2=torch.empty((B, 2, D), dtype=torch.float32, device=dev),
                 po=torch.empty((M, self.w["out.w"].shape[0]), dtype=bf, device=dev),
                 rq=torch.empty((M,), dtype=torch.float32, device=dev))
@@ -294,13 +296,19 @@ class WanTransformer3DModelB200(torch.nn.Module):
         a = ops.patchify(hidden_states)
         x = ops.gemm(a, w["patch.w"], w["patch.b"], out=ws.x)
 
+        # AdaLN vectors of every block: mod[b, i] = [shift1, 1+scale1, gate1, shift2, 1+scale2, gate2] = table_i + timestep_proj[b].  The
+        # kernel adds a [6, D] "table" to a batch of [6, D] vectors: here the batch runs over the blocks and the timestep projection of row b
+        # plays the table -- B launches per forward instead of one per block (30 kernel boundaries less on the step)
+        NL = c.num_layers
+        for b_ in range(B):
+            ops.modulation(tproj[b_].view(6, D), w["tables"].view(NL, 6 * D), nvec=6, broadcast=False, one_plus_mask=0b010010, out=ws.mod[b_])
+        mbs = NL * 6 * D   # batch stride of the per-block views below
+
         for i in range(c.num_layers):
             k = f"b{i}."
-            # mod = [shift1, 1+scale1, gate1, shift2, 1+scale2, gate2]
-            ops.modulation(w[k + "table"], tproj, nvec=6, broadcast=False, one_plus_mask=0b010010, out=ws.mod)
-            mod = ws.mod
+            mod = ws.mod[:, i]
             # --- self-attention
-            ops.layernorm(x, mul=mod[:, 1], add=mod[:, 0], mul_bstride=6 * D, add_bstride=6 * D, rows_per_batch=L,
+            ops.layernorm(x, mul=mod[:, 1], add=mod[:, 0], mul_bstride=mbs, add_bstride=mbs, rows_per_batch=L,
                           eps=c.eps, out=ws.h)
             # (multicast=True: clusters of two CTA pairs share the activation rows by TMA multicast where the tile grid allows it -- slower in
             #  isolation, -0.8 % on the power-capped step: 27.93 -> 27.69 ms in an alternating same-box A/B, tools/runs/gpu_r3n.sh)
@@ -308,7 +316,7 @@ class WanTransformer3DModelB200(torch.nn.Module):
             ops.rmsnorm_rope_(ws.qkv[:, :2 * D], w[k + "nqk1"], hd, eps=c.eps, cos=cos, sin=sin, nseg=2)
             qkv5 = ws.qkv.view(B, L, 3, H_, hd)
             ops.fmha(qkv5[:, :, 0], qkv5[:, :, 1], qkv5[:, :, 2], out=ws.att.view(B, L, H_, hd))
-            ops.gemm(ws.att, w[k + "o1.w"], w[k + "o1.b"], gate=mod[:, 2], gate_bstride=6 * D, rows_per_batch=L,
+            ops.gemm(ws.att, w[k + "o1.w"], w[k + "o1.b"], gate=mod[:, 2], gate_bstride=mbs, rows_per_batch=L,
                      residual=x, out=x, round_linear=True, multicast=True)
             # --- cross-attention
             if c.cross_attn_norm:
@@ -322,10 +330,10 @@ class WanTransformer3DModelB200(torch.nn.Module):
             ops.fmha(ws.q2.view(B, L, H_, hd), kv5[:, :, 0], kv5[:, :, 1], out=ws.att.view(B, L, H_, hd), q_row_scale=ws.rq)
             ops.gemm(ws.att, w[k + "o2.w"], w[k + "o2.b"], residual=x, out=x, round_linear=True, multicast=True)
             # --- feed-forward
-            ops.layernorm(x, mul=mod[:, 4], add=mod[:, 3], mul_bstride=6 * D, add_bstride=6 * D, rows_per_batch=L,
+            ops.layernorm(x, mul=mod[:, 4], add=mod[:, 3], mul_bstride=mbs, add_bstride=mbs, rows_per_batch=L,
                           eps=c.eps, out=ws.h)
             ops.gemm(ws.h, w[k + "f1.w"], w[k + "f1.b"], act="gelu_tanh", out=ws.ffn, multicast=True)
-            ops.gemm(ws.ffn, w[k + "f2.w"], w[k + "f2.b"], gate=mod[:, 5], gate_bstride=6 * D, rows_per_batch=L,
+            ops.gemm(ws.ffn, w[k + "f2.w"], w[k + "f2.b"], gate=mod[:, 5], gate_bstride=mbs, rows_per_batch=L,
                      residual=x, out=x, round_linear=True, multicast=True)
 
         # output head: mod2 = [shift, 1+scale] from table + temb
