@@ -92,14 +92,17 @@ def _graph_time_fmha(B, H, Lq, Lk, D, iters=10):
             for _ in range(iters):
                 ops.fmha(q, k, v, out=o)
     torch.cuda.synchronize()
-    gr.replay()
-    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    s.record()
-    for _ in range(3):
+    for _ in range(3):   # clocks ramp after the host-side work in front of this measurement
         gr.replay()
-    e.record()
-    torch.cuda.synchronize()
-    return s.elapsed_time(e) / (3 * iters)
+    ts = []
+    for _ in range(7):
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        gr.replay()
+        e.record()
+        torch.cuda.synchronize()
+        ts.append(s.elapsed_time(e) / iters)
+    return statistics.median(ts)
 
 
 def _attention_roofline(detail, pk):
@@ -115,7 +118,7 @@ def _attention_roofline(detail, pk):
         ms_call = _graph_time_fmha(*dims)
         tf = v["flops"] / v["launches"] / (ms_call / 1e3) / 1e12
         out[name] = {"shape_BxHxLqxLkxD": k.split("|")[1], "launches": v["launches"], "ms": round(ms_call * v["launches"], 4), "eager_ms": round(v["ms"], 4),
-                     "achieved": tf, "unit": "TFLOP/s", "timing": "CUDA graph of 10 back-to-back calls, random q/k/v of the step's shape",
+                     "achieved": tf, "unit": "TFLOP/s", "timing": "CUDA graph of 10 back-to-back calls (median of 7 replays), random q/k/v of the step's shape",
                      "frac": tf / pk["bf16_sustained"], "frac_of_burst": tf / pk["bf16_burst"]}
     return out
 

@@ -1027,7 +1027,7 @@ extern "C" int v3a_debug_fmha_pair_plan_check(long long units, int n_kv, int slo
 
 // head_dim 128 on CTA pairs; `variant` (A/B measurements): 0 = default: two query tiles per CTA, one thread per query row, P handed over in
 // two key halves, all exponentials on the MUFU; 1 / 2 = the same with 1 / 2 of every 8 column pairs on the FMA pipe; 3 = speculative
-// softmax (stale maximum, 64-column half-steps), all MUFU; 4 = the same with 2 of 8 on the FMA pipe; 5 / 6 = default with 3 / 4 of 8; 7 = speculative, 3 of 8
+// softmax (stale maximum, 64-column half-steps), all MUFU; 4 = the same with 2 of 8 on the FMA pipe; 5 = default with 3 of 8; 6 = speculative, 1 of 8; 7 = speculative, 3 of 8
 // ws_query != nullptr: no launch, *ws_query = workspace bytes the key split of this problem would use (0: no split)
 int fmha_pair_entry(const vist3a_fmha_args& a, int variant, cudaStream_t stream, long long* ws_query) {
   switch (variant) {
@@ -1036,7 +1036,7 @@ int fmha_pair_entry(const vist3a_fmha_args& a, int variant, cudaStream_t stream,
     case 3: return launch_fmha_pair<2, 1, 0, 1>(a, stream, ws_query);
     case 4: return launch_fmha_pair<2, 1, 2, 1>(a, stream, ws_query);
     case 5: return launch_fmha_pair<2, 1, 3>(a, stream, ws_query);
-    case 6: return launch_fmha_pair<2, 1, 4>(a, stream, ws_query);
+    case 6: return launch_fmha_pair<2, 1, 1, 1>(a, stream, ws_query);
     case 7: return launch_fmha_pair<2, 1, 3, 1>(a, stream, ws_query);
     default: return launch_fmha_pair<2, 1, 0>(a, stream, ws_query);
   }

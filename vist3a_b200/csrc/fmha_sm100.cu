@@ -1189,8 +1189,10 @@ int fmha_entry(const vist3a_fmha_args* args, cudaStream_t stream, long long* ws_
     if (ws_query && (a.head_dim == 64 || a.len_kv < 512)) return VIST3A_OK;
     // (head_dim 64, long key sequences -- the decoder's global attention: two threads per row, +2 % over one thread per row at 13 377 keys; -7 % at 1029)
     if (a.head_dim == 64) return a.len_kv >= 4096 ? launch_fmha<64, 128, 0, 2, 2>(a, stream) : launch_fmha<64, 128, 2, 1, 1>(a, stream);
-    if (a.len_kv >= 1024) return fmha_pair_entry(a, 7, stream, ws_query);
-    if (a.len_kv >= 512) return fmha_pair_entry(a, 4, stream, ws_query);   // cross-attention (512 text tokens): 676 vs 659 TFLOP/s on one CTA
+    // (>= 512 keys: CTA pairs with 2 of every 8 exponentials on the FMA pipe.  On the persistent kernel 1 or 2 of 8 are 2.3 % ahead of 3 of 8 --
+    //  the round-2 choice for >= 1024 keys -- at 4096 keys: 1151-1156 vs 1123-1132 TFLOP/s, and 817 vs 780-790 at the 512 text keys;
+    //  tools/runs/gpu_r4s.sh, profiles/r2_fmha_variants_persistent.jsonl)
+    if (a.len_kv >= 512) return fmha_pair_entry(a, 4, stream, ws_query);
     return launch_fmha<128, 64, 2, 1, 1>(a, stream);
   }
   if (ws_query) return VIST3A_OK;   // the single-CTA variants below use no workspace
