@@ -496,15 +496,20 @@ def run_ours(args):
         img = img_h.to(device)
         outs = {}
 
-        def dec_step(i):
-            outs["o"] = dec.forward_with_latent(lat, img)
+        # the decoder forward as the prompt pipeline runs it (t23d.TextTo3DGS): replayed from a CUDA graph, outputs copied out per call
+        dec_fwd = dec.forward_with_latent if args.no_decoder_graph else dec.forward_with_latent_graph
 
+        def dec_step(i):
+            outs["o"] = dec_fwd(lat, img)
+
+        n2 = _lib.launch_count()
+        dec.forward_with_latent(lat, img)              # (eager: the launch counter does not see graph replays)
+        dec_launches_fwd = _lib.launch_count() - n2
         for i in range(2):
             dec_step(i)
-        n2 = _lib.launch_count()
         kd = max(2, min(args.steps, args.decoder_iters))
         ms_dec = timed(dec_step, kd) / kd
-        dec_launches = _lib.launch_count() - n2
+        dec_launches = dec_launches_fwd * kd
         ms_gather = 0.0
         if world > 1:
             def gather_step(i):
@@ -544,7 +549,7 @@ def run_ours(args):
                 else:
                     img.copy_(img_h, non_blocking=True)
                     views = img
-                o = dec.forward_with_latent(lat_i, views)
+                o = dec_fwd(lat_i, views)
                 h = all_gather_gaussians_async(o.gaussians, fixed_count=not args.voxelize) if world > 1 else None
                 if pending is not None:
                     pending[1].wait()
@@ -569,7 +574,7 @@ def run_ours(args):
                  "e2e_what": ("one prompt per GPU" if world == 1 else "two prompts per GPU, time per prompt") + ": H2D text + noise, text projections, 50 CFG denoise steps, de-normalise, " +
                              ("Wan VAE decode + 448 resize, " if vae is not None else "H2D views, ") + "stitched decode" +
                              (", asynchronous NCCL all-gather of all ranks' Gaussians (under the next prompt's denoising)" if world > 1 else "") + ", D2H of scene_scale",
-                 "decoder_launches_per_forward": dec_launches // kd,
+                 "decoder_launches_per_forward": dec_launches // kd, "decoder_cuda_graph": not args.no_decoder_graph,
                  "latent": "denoised latent of the random-weight DiT, clamped to [-4, 4] before de-normalisation (real VAE latents are O(1))",
                  "workload": f"VIST3A-{'1.3B' if args.model == '1.3b' else '14B'} full stitched path: DiT -> conv3d_k5x3x3 stitch -> AnySplat "
                              f"enc_blocks_2 -> 3DGS, 512x512x{VIEWS}v"}
@@ -695,6 +700,7 @@ def main():
     ap.add_argument("--cpu-blocks", type=int, default=30, help="full-size blocks of the cpu_baseline leg (30 = one whole forward, ~10 s on 16 cores)")
     ap.add_argument("--prompts-per-gpu", type=int, default=1, help="prompts batched per GPU (BASELINE configs[4] sweep: 1/2/4/8)")
     ap.add_argument("--no-decoder", action="store_true", help="skip the Gaussians/s leg (decoder + gather)")
+    ap.add_argument("--no-decoder-graph", action="store_true", help="eager stitched-decoder forward instead of the CUDA-graph replay (A/B)")
     ap.add_argument("--decoder-iters", type=int, default=3)
     ap.add_argument("--no-vae", action="store_true", help="end-to-end prompt without the Wan VAE decode (views copied from the host instead)")
     ap.add_argument("--model", default="1.3b", choices=["1.3b", "14b"], help="Wan DiT size (BASELINE configs[1-2] / configs[3])")

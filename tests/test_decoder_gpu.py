@@ -181,6 +181,70 @@ def test_decoder_properties_at_13_views():
     assert torch.allclose(cam[..., 2], d, rtol=2e-3, atol=1e-4)
 
 
+def test_decoder_graph_replay_equals_the_eager_forward():
+    """`forward_with_latent_graph` (one CUDA graph per input shape, what the prompt pipeline runs): bit-identical to the eager forward for new
+    inputs of the captured shape (but for the atomically summed scene scale), outputs freshly allocated per call (the second call does not overwrite the first result), the Gaussian
+    fields still views of one field-major buffer (the gather's zero-copy layout), a second shape gets its own graph, and the data-dependent
+    configurations fall back to the eager call."""
+    from oracle import decoder_ref as D
+    from vist3a_b200.stitched_decoder import DecoderConfig
+
+    sd = D.init_state_dict(D.TINY, seed=3)
+    m = _engine(sd, D.TINY, 64)
+    outs = []
+    for seed in (5, 6):
+        lat, img = D.synthetic_inputs(D.TINY, views_latent=2, latent_hw=8, image_hw=56, seed=seed)
+        got = m.forward_with_latent_graph(lat.cuda(), img.cuda())
+        want = _as_dict(m.forward_with_latent(lat.cuda(), img.cuda()))
+        outs.append((got, want))
+    assert len(m._graphs) == 1
+    for got, want in outs:     # checked after BOTH replays: the first result must have survived the second
+        gd = _as_dict(got)
+        for k, v in want.items():
+            if k == "scene_scale":   # a block-wise atomicAdd reduction: the summation order differs from run to run
+                assert torch.allclose(gd[k], v, rtol=1e-5), k
+            else:
+                assert torch.equal(gd[k], v), k
+        pk = got.gaussians.packed
+        assert pk is not None
+        for f in GAUSS:
+            t = getattr(got.gaussians, f)
+            assert t.untyped_storage().data_ptr() == pk.untyped_storage().data_ptr(), f
+    assert outs[0][0].gaussians.packed.data_ptr() != outs[1][0].gaussians.packed.data_ptr()
+    lat, img = D.synthetic_inputs(D.TINY, views_latent=3, latent_hw=8, image_hw=56, seed=7)    # 9 views: another graph
+    got = _as_dict(m.forward_with_latent_graph(lat.cuda(), img.cuda()))
+    want = _as_dict(m.forward_with_latent(lat.cuda(), img.cuda()))
+    assert len(m._graphs) == 2 and all(torch.equal(got[k], v) for k, v in want.items() if k != "scene_scale")
+
+
+def test_prompt_pipeline_with_and_without_the_decoder_graph():
+    """t23d.TextTo3DGS.generate (denoise -> stitched decode) with the decoder replayed from its CUDA graph (default) and with the eager decoder:
+    same Gaussians for two prompts in a row, and the first prompt's output is still intact after the second prompt has been decoded."""
+    from oracle import decoder_ref as D
+    from oracle import wan_dit_ref as R
+    from vist3a_b200.t23d import TextTo3DGS
+    from vist3a_b200.wan_dit import WanTransformer3DModelB200
+
+    tr = WanTransformer3DModelB200.from_state_dict(R.init_state_dict(R.WAN_TINY, seed=5, bias_std=0.02), R.WAN_TINY)
+    dec = _engine(D.init_state_dict(D.TINY, seed=3), D.TINY, 64)
+    kw = dict(views=5, resolution=64, text_len=12, num_inference_steps=4)
+    graphed, eager = TextTo3DGS(tr, dec, **kw), TextTo3DGS(tr, dec, decoder_graph=False, **kw)
+    assert graphed.decoder_graph and not eager.decoder_graph
+    res = []
+    for seed in (1, 2):
+        g = torch.Generator().manual_seed(seed)
+        noise = torch.randn(1, 16, 2, 8, 8, generator=g)
+        _, tc = R.synthetic_inputs(R.WAN_TINY, text_len=12, text_valid=9, seed=seed)
+        _, tu = R.synthetic_inputs(R.WAN_TINY, text_len=12, text_valid=4, seed=seed + 10)
+        img = (torch.rand(1, 3, 5, 56, 56, generator=g) * 2 - 1).cuda()
+        res.append((graphed.generate(noise, tc, tu, img), eager.generate(noise, tc, tu, img)))
+    assert not torch.equal(res[0][1].gaussians.means, res[1][1].gaussians.means)
+    for a, b in res:
+        for f in GAUSS:
+            assert torch.equal(getattr(a.gaussians, f), getattr(b.gaussians, f)), f
+        assert torch.equal(a.depth_dict["depth"], b.depth_dict["depth"])
+
+
 def test_latent_grid_is_resampled_to_resolution_over_8():
     """upsampling_layer (stitched_model.py:92-107) resizes T *and* H, W: a latent whose grid is not resolution/8 is interpolated
     (trilinear, align_corners=True) before the stitching conv"""

@@ -231,6 +231,70 @@ def random_state_dict(cfg: DecoderConfig, seed: int = 0, device="cuda") -> Dict[
     return sd
 
 
+def _clone_tree(obj, packed_src=None, packed_dst=None):
+    """Deep copy of the tensors of a decoder output (dataclasses, dicts, lists); tensors that are views of `packed_src` (the field-major
+    Gaussian buffer) become the same views of `packed_dst`, so that the copy keeps the zero-copy layout the multi-GPU gather relies on."""
+    if isinstance(obj, torch.Tensor):
+        if packed_src is not None and obj.untyped_storage().data_ptr() == packed_src.untyped_storage().data_ptr() and obj.dtype == packed_src.dtype:
+            return packed_dst.as_strided(obj.size(), obj.stride(), obj.storage_offset() - packed_src.storage_offset())
+        return obj.clone()
+    if isinstance(obj, dict):
+        return {k: _clone_tree(v, packed_src, packed_dst) for k, v in obj.items()}
+    if isinstance(obj, (list, tuple)):
+        return type(obj)(_clone_tree(v, packed_src, packed_dst) for v in obj)
+    if hasattr(obj, "__dataclass_fields__"):
+        return type(obj)(**{k: _clone_tree(getattr(obj, k), packed_src, packed_dst) for k in obj.__dataclass_fields__})
+    return obj
+
+
+def clone_output(out: EncoderOutput) -> EncoderOutput:
+    src = out.gaussians.packed
+    dst = src.clone() if src is not None else None
+    g = _clone_tree(out.gaussians, src, dst)
+    if dst is not None:
+        g.packed = dst
+    rest = {k: _clone_tree(getattr(out, k)) for k in out.__dataclass_fields__ if k != "gaussians"}
+    return EncoderOutput(gaussians=g, **rest)
+
+
+class DecoderGraph:
+    """One `StitchVAE3DB200.forward_with_latent` of fixed input shapes as a CUDA graph.  The eager forward queues ~900 kernels and needs
+    ~60 ms of host time for 80 ms of device time (measured, tools/decoder_graph_try.py): a busy host makes it host-bound; the replay costs
+    0.3 ms of host time and 78 ms on the device.  Inputs are copied into the graph's static buffers; `clone=True` (default) returns freshly
+    allocated outputs like the eager call does (0.9 GB copied at 13 views: 0.3 ms), `clone=False` the graph's own output tensors, valid
+    until the next replay.  Not available for the data-dependent branches (voxelised fusion, confidence quantiles): those read counts on
+    the host."""
+
+    def __init__(self, dec: "StitchVAE3DB200", latent: torch.Tensor, feedforward_image: torch.Tensor):
+        cfg = dec.cfg
+        if cfg.voxelize or cfg.render_conf or cfg.opacity_conf:
+            raise NotImplementedError("DecoderGraph: the voxelised / confidence-filtered outputs have data-dependent sizes")
+        self.dec = dec
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            self.latent = latent.detach().to(dec.device).clone()
+            self.image = feedforward_image.detach().to(dec.device).clone()
+            for _ in range(2):   # warm-up outside the capture: function attributes, tensor-map caches, allocator pools
+                dec.forward_with_latent(self.latent, self.image)
+        cur.wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.out = dec.forward_with_latent(self.latent, self.image)
+
+    @torch.no_grad()
+    def __call__(self, latent: torch.Tensor, feedforward_image: torch.Tensor, clone: bool = True) -> EncoderOutput:
+        if latent.shape != self.latent.shape or feedforward_image.shape != self.image.shape:
+            raise ValueError(f"DecoderGraph captured for latent {tuple(self.latent.shape)} / views {tuple(self.image.shape)}, "
+                             f"got {tuple(latent.shape)} / {tuple(feedforward_image.shape)}")
+        self.latent.copy_(latent, non_blocking=True)
+        self.image.copy_(feedforward_image, non_blocking=True)
+        self.graph.replay()
+        return clone_output(self.out) if clone else self.out
+
+
 class StitchVAE3DB200(torch.nn.Module):
     """B200-native StitchVAE3D (inference: `forward_with_latent`)."""
 
@@ -616,6 +680,20 @@ class StitchVAE3DB200(torch.nn.Module):
             x = ops.bilinear_nhwc(x, lat_hw, lat_hw)
             latent = x.view(Bl, Tl, lat_hw, lat_hw, Cl).permute(0, 4, 1, 2, 3).contiguous()
         return self._decode(latent, feedforward_image, B, V, H, W)
+
+    @torch.no_grad()
+    def forward_with_latent_graph(self, latent: torch.Tensor, feedforward_image: torch.Tensor, clone: bool = True) -> EncoderOutput:
+        """`forward_with_latent` replayed from a CUDA graph (`DecoderGraph`, one per input shape, captured on first use); the eager call
+        for the configurations a graph cannot hold."""
+        cfg = self.cfg
+        if cfg.voxelize or cfg.render_conf or cfg.opacity_conf or cfg.patch_embed or not latent.is_cuda or torch.cuda.is_current_stream_capturing():
+            return self.forward_with_latent(latent, feedforward_image)
+        graphs = self.__dict__.setdefault("_graphs", {})
+        key = (tuple(latent.shape), latent.dtype, tuple(feedforward_image.shape), feedforward_image.dtype)
+        g = graphs.get(key)
+        if g is None:
+            g = graphs[key] = DecoderGraph(self, latent, feedforward_image)
+        return g(latent, feedforward_image, clone=clone)
 
     @torch.no_grad()
     def forward_images(self, image: torch.Tensor) -> EncoderOutput:

@@ -41,10 +41,14 @@ class TextTo3DGS:
     """One prompt -> EncoderOutput; owns the CUDA-graphed denoise engine and the decoder."""
 
     def __init__(self, transformer, decoder, *, views: int = 13, resolution: int = 512, text_len: int = 512,
-                 num_inference_steps: int = 50, guidance_scale: float = 6.0, flow_shift: float = 5.0, use_graph: bool = True):
+                 num_inference_steps: int = 50, guidance_scale: float = 6.0, flow_shift: float = 5.0, use_graph: bool = True,
+                 decoder_graph: bool = True):
         if (views - 1) % 4:
             raise ValueError("views must be 4k+1 (Wan VAE temporal stride 4)")
         self.tr, self.dec = transformer, decoder
+        # the stitched decode replayed from a CUDA graph as well (stitched_decoder.DecoderGraph: the eager forward needs 60 ms of host time
+        # to queue 80 ms of kernels); outputs are copies, freshly allocated per prompt as in the eager call
+        self.decoder_graph = decoder_graph and use_graph and hasattr(decoder, "forward_with_latent_graph")
         self.dev = transformer.device
         T = (views - 1) // 4 + 1
         self.latent_shape = (1, 16, T, resolution // 8, resolution // 8)
@@ -74,6 +78,8 @@ class TextTo3DGS:
             if vae is None:
                 raise ValueError("generate: pass feedforward_image, or vae= to decode the views from the latent")
             feedforward_image = views_from_vae(vae, latent)
+        if self.decoder_graph:
+            return self.dec.forward_with_latent_graph(latent, feedforward_image)
         return self.dec.forward_with_latent(latent, feedforward_image, train=False)
 
 
