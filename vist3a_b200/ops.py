@@ -188,7 +188,10 @@ def fmha(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, scale: Optional[f
                 ws = _FMHA_WS.get(skey)
                 if ws is None or ws.numel() < need:
                     ws = torch.empty(need, dtype=torch.uint8, device=q.device)
+                    _FMHA_WS.pop(skey, None)
                     _FMHA_WS[skey] = ws
+                    while len(_FMHA_WS) > 8:   # streams come and go: keep the most recent few (a dropped buffer is freed stream-ordered)
+                        _FMHA_WS.pop(next(iter(_FMHA_WS)))
             a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
     L.check(L.load().vist3a_fmha_fwd(C.byref(a), st))
     return out

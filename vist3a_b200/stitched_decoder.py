@@ -692,6 +692,8 @@ class StitchVAE3DB200(torch.nn.Module):
         key = (tuple(latent.shape), latent.dtype, tuple(feedforward_image.shape), feedforward_image.dtype)
         g = graphs.get(key)
         if g is None:
+            while len(graphs) >= 3:   # a graph pins the memory of a whole forward (8.8 GB at 13 views): keep the most recent shapes
+                graphs.pop(next(iter(graphs)))
             g = graphs[key] = DecoderGraph(self, latent, feedforward_image)
         return g(latent, feedforward_image, clone=clone)
 
