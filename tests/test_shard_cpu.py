@@ -167,3 +167,38 @@ def test_stitched_forward_mirrors_the_reference_surface():
     assert m.forward(clip, views) == "decoded"
     assert m.diffusion_vae.seen is clip and got["image"] is views and got["train"] is False
     assert got["latent"].shape == (2, 16, 2, 2, 2) and float(got["latent"].mean()) == 0.25
+
+
+def test_clone_output_keeps_the_field_major_layout():
+    """stitched_decoder.clone_output (what a CUDA-graph replay of the decoder hands to the caller): every tensor is copied, the Gaussian fields of
+    the copy are views of ONE new flat buffer at the offsets they had in the source (the layout all_gather_gaussians sends without packing),
+    nested containers and non-tensor entries survive, and writing to the source afterwards does not reach the copy."""
+    from vist3a_b200.stitched_decoder import EncoderOutput, clone_output
+
+    B, N, d_sh = 1, 7, 4
+    sizes = {"means": 3, "scales": 3, "rotations": 4, "opacities": 1, "harmonics": 3 * d_sh, "covariances": 9}
+    flat = torch.arange(B * N * sum(sizes.values()), dtype=torch.float32)
+    views, off = {}, 0
+    for k, c in sizes.items():
+        views[k] = flat[off:off + B * N * c].view(B, N, c)
+        off += B * N * c
+    g = Gaussians(means=views["means"], covariances=views["covariances"].view(B, N, 3, 3), harmonics=views["harmonics"].view(B, N, 3, d_sh),
+                  opacities=views["opacities"].view(B, N), scales=views["scales"], rotations=views["rotations"], packed=flat)
+    out = EncoderOutput(gaussians=g, pred_pose_enc_list=[torch.ones(1, 2, 9), torch.zeros(1, 2, 9)],
+                        pred_context_pose={"extrinsic": torch.eye(4).expand(1, 2, 4, 4), "intrinsic": torch.eye(3).expand(1, 2, 3, 3)},
+                        depth_dict={"depth": torch.rand(1, 2, 4, 4, 1)}, infos={"scene_scale": torch.tensor(2.0), "voxelize_ratio": 1.0},
+                        last_pred_pose_enc=torch.ones(1, 2, 9))
+    c = clone_output(out)
+    assert c.gaussians.packed is not None and c.gaussians.packed.data_ptr() != flat.data_ptr()
+    for f in ("means", "covariances", "harmonics", "opacities", "scales", "rotations"):
+        a, b = getattr(g, f), getattr(c.gaussians, f)
+        assert torch.equal(a, b) and b.shape == a.shape
+        assert b.untyped_storage().data_ptr() == c.gaussians.packed.untyped_storage().data_ptr(), f
+        assert b.storage_offset() == a.storage_offset() and b.stride() == a.stride(), f
+    assert torch.equal(c.gaussians.packed, flat)
+    assert c.infos["voxelize_ratio"] == 1.0 and torch.equal(c.infos["scene_scale"], out.infos["scene_scale"])
+    assert len(c.pred_pose_enc_list) == 2 and c.pred_pose_enc_list[0].data_ptr() != out.pred_pose_enc_list[0].data_ptr()
+    assert torch.equal(c.pred_context_pose["extrinsic"], out.pred_context_pose["extrinsic"]) and c.distill_infos is None
+    flat.zero_()
+    out.depth_dict["depth"].zero_()
+    assert float(c.gaussians.means.sum()) > 0 and float(c.depth_dict["depth"].sum()) > 0
